@@ -1,0 +1,89 @@
+"""ctypes loader for libgalah_b200.so (the C ABI declared in include/galah_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or no sm_100 device can be
+bound, every compute call raises.
+"""
+import ctypes
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libgalah_b200.so")
+
+
+class GalahB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"[galah_b200 rc={code}] {message}")
+        self.code = code
+        self.message = message
+
+
+class Pair(ctypes.Structure):
+    _fields_ = [("i", ctypes.c_uint32), ("j", ctypes.c_uint32), ("common", ctypes.c_uint32),
+                ("total", ctypes.c_uint32), ("ani", ctypes.c_float)]
+
+
+_lib = None
+
+u8p = ctypes.POINTER(ctypes.c_uint8)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+u64p = ctypes.POINTER(ctypes.c_uint64)
+f32p = ctypes.POINTER(ctypes.c_float)
+pairpp = ctypes.POINTER(ctypes.POINTER(Pair))
+sizep = ctypes.POINTER(ctypes.c_size_t)
+strp = ctypes.POINTER(ctypes.c_char_p)
+vp = ctypes.c_void_p
+
+_SIGNATURES = {
+    "galah_b200_init": (ctypes.c_int, [ctypes.c_int]),
+    "galah_b200_device_count": (ctypes.c_int, []),
+    "galah_b200_last_error": (ctypes.c_char_p, []),
+    "galah_b200_version": (ctypes.c_char_p, []),
+    "galah_b200_free": (None, [vp]),
+    "galah_b200_launch_count": (ctypes.c_uint64, []),
+    "galah_b200_sketch_files": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_uint8, ctypes.c_uint32,
+                                               ctypes.c_uint64, ctypes.c_int, u64p, u32p]),
+    "galah_b200_sketch_packed": (ctypes.c_int, [u32p, u32p, u64p, ctypes.c_size_t, ctypes.c_uint8,
+                                                ctypes.c_uint32, ctypes.c_uint64, u64p, u32p]),
+    "galah_b200_sketch_packed_device": (ctypes.c_int, [vp, vp, vp, ctypes.c_size_t, ctypes.c_uint8,
+                                                       ctypes.c_uint32, ctypes.c_uint64, vp, vp, vp]),
+    "galah_b200_prefilter": (ctypes.c_int, [u64p, u32p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint8,
+                                            ctypes.c_float, pairpp, sizep]),
+    "galah_b200_prefilter_shard": (ctypes.c_int, [u64p, u32p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint8,
+                                                  ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32, pairpp, sizep]),
+    "galah_b200_prefilter_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint8,
+                                                   ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32, vp,
+                                                   pairpp, sizep]),
+    "galah_b200_prefilter_enqueue": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint8,
+                                                    ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32,
+                                                    ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
+    "galah_b200_finch_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32,
+                                                  ctypes.c_uint8, ctypes.c_int, pairpp, sizep]),
+    "galah_b200_synth_packed_device": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
+                                                      ctypes.c_uint64, vp, vp, vp, vp]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/galah_b200.h declares (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GalahB200Error(
+                -1, f"{LIB_PATH} is missing: build it with `python -m galah_b200.build` "
+                    "(there is no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GalahB200Error(rc, lib().galah_b200_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,138 @@
+"""Python face of the C ABI: marshals numpy arrays / torch device pointers, nothing else.
+
+Host-side logic (FASTA ingest, clustering) lives in C++ behind the same ABI; the CUDA kernels are
+the only compute path.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native
+from ._native import GalahB200Error, Pair, check, lib
+
+PAIR_DTYPE = np.dtype(
+    [("i", "<u4"), ("j", "<u4"), ("common", "<u4"), ("total", "<u4"), ("ani", "<f4")]
+)
+ROW_BLOCK = 8
+PAD = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+_bound_device = None
+
+
+def init(device=0):
+    """Bind this process to CUDA device `device` (galah_b200_init)."""
+    global _bound_device
+    check(lib().galah_b200_init(int(device)))
+    _bound_device = int(device)
+    return _bound_device
+
+
+def device_count():
+    return int(lib().galah_b200_device_count())
+
+
+def launch_count():
+    return int(lib().galah_b200_launch_count())
+
+
+def version():
+    return lib().galah_b200_version().decode()
+
+
+def _paths_array(paths):
+    arr = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    return arr
+
+
+def _take_pairs(out, n_out):
+    n = n_out.value
+    res = np.zeros(n, PAIR_DTYPE)
+    if n:
+        ctypes.memmove(res.ctypes.data, out, n * ctypes.sizeof(Pair))
+    lib().galah_b200_free(out)
+    return res
+
+
+def sketch_files(paths, k=21, s=1000, seed=0, threads=0):
+    """GPU replacement for finch::sketch_files (reference src/finch.rs:55-69)."""
+    n = len(paths)
+    table = np.full((n, s), PAD, np.uint64)
+    counts = np.zeros(n, np.uint32)
+    check(lib().galah_b200_sketch_files(_paths_array(paths), n, k, s, seed, threads,
+                                        table.ctypes.data_as(_native.u64p),
+                                        counts.ctypes.data_as(_native.u32p)))
+    return table, counts
+
+
+def sketch_packed(seq2, valid, base_off, k=21, s=1000, seed=0):
+    seq2 = np.ascontiguousarray(seq2, np.uint32)
+    valid = np.ascontiguousarray(valid, np.uint32)
+    base_off = np.ascontiguousarray(base_off, np.uint64)
+    n = len(base_off) - 1
+    table = np.full((n, s), PAD, np.uint64)
+    counts = np.zeros(n, np.uint32)
+    check(lib().galah_b200_sketch_packed(seq2.ctypes.data_as(_native.u32p),
+                                         valid.ctypes.data_as(_native.u32p),
+                                         base_off.ctypes.data_as(_native.u64p), n, k, s, seed,
+                                         table.ctypes.data_as(_native.u64p),
+                                         counts.ctypes.data_as(_native.u32p)))
+    return table, counts
+
+
+def sketch_packed_device(d_seq2, d_valid, d_base_off, n, k, s, seed, d_hashes, d_counts, stream=0):
+    """All arguments are raw device pointers (ints); enqueues on `stream`."""
+    check(lib().galah_b200_sketch_packed_device(d_seq2, d_valid, d_base_off, n, k, s, seed, d_hashes,
+                                                d_counts, stream))
+
+
+def prefilter(table, counts, k=21, min_ani=0.9, shard=0, n_shards=1):
+    """GPU replacement for the pair loop at reference src/finch.rs:75-95 (host buffers).
+    With n_shards > 1 only the row blocks shard, shard + n_shards, ... are evaluated."""
+    table = np.ascontiguousarray(table, np.uint64)
+    counts = np.ascontiguousarray(counts, np.uint32)
+    n, stride = table.shape
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    check(lib().galah_b200_prefilter_shard(table.ctypes.data_as(_native.u64p),
+                                           counts.ctypes.data_as(_native.u32p), n, stride, k,
+                                           ctypes.c_float(min_ani), shard, n_shards,
+                                           ctypes.byref(out), ctypes.byref(n_out)))
+    return _take_pairs(out, n_out)
+
+
+def prefilter_device(d_hashes, d_counts, n, stride, k=21, min_ani=0.9, shard=0, n_shards=1, stream=0):
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    check(lib().galah_b200_prefilter_device(d_hashes, d_counts, n, stride, k, ctypes.c_float(min_ani),
+                                            shard, n_shards, stream, ctypes.byref(out),
+                                            ctypes.byref(n_out)))
+    return _take_pairs(out, n_out)
+
+
+def prefilter_enqueue(d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, mode, stream, d_cand,
+                      cand_cap, d_n_cand):
+    check(lib().galah_b200_prefilter_enqueue(d_hashes, d_counts, n, stride, k, ctypes.c_float(min_ani),
+                                             shard, n_shards, mode, stream, d_cand, cand_cap, d_n_cand))
+
+
+def finch_distances(paths, min_ani=0.9, num_kmers=1000, kmer_length=21, threads=0):
+    """GPU replacement for galah::finch::distances (reference src/finch.rs:48-97)."""
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    check(lib().galah_b200_finch_distances(_paths_array(paths), len(paths), ctypes.c_float(min_ani),
+                                           num_kmers, kmer_length, threads, ctypes.byref(out),
+                                           ctypes.byref(n_out)))
+    return _take_pairs(out, n_out)
+
+
+def synth_layout(n, length):
+    """Sizes (in uint32 / uint64 elements) of the packed buffers for n synthetic genomes."""
+    padded = (length + 127) // 128 * 128
+    return {"seq2_words": n * padded // 16 + 4, "valid_words": n * padded // 32 + 4,
+            "base_off": n + 1, "padded": padded}
+
+
+def synth_packed_device(seed, index_begin, n, length, d_seq2, d_valid, d_base_off, stream=0):
+    check(lib().galah_b200_synth_packed_device(seed, index_begin, n, length, d_seq2, d_valid,
+                                               d_base_off, stream))

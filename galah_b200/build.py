@@ -1,0 +1,83 @@
+"""Builds libgalah_b200.so (CUDA kernels + C ABI + C++ host side) in-tree with nvcc for sm_100a.
+
+The built .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libgalah_b200.so")
+CLI_PATH = os.path.join(PKG_DIR, "bin", "galah-b200")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function,-pthread", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; cannot build libgalah_b200.so")
+    return nvcc
+
+
+def sources():
+    cu = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    cpp = sorted(glob.glob(os.path.join(CSRC, "host", "*.cpp")))
+    return cu + cpp
+
+
+def _deps():
+    deps = sources()
+    deps += glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "host", "*.hpp"))
+    deps += glob.glob(os.path.join(PKG_DIR, "..", "include", "*.h"))
+    return deps
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile the shared library (and the CLI, if its source exists). Returns the .so path."""
+    if force or _stale(LIB_PATH, _deps()):
+        objdir = os.path.join(PKG_DIR, "build")
+        os.makedirs(objdir, exist_ok=True)
+        objs = []
+        procs = []
+        for src in sources():
+            obj = os.path.join(objdir, os.path.basename(src) + ".o")
+            objs.append(obj)
+            if not force and not _stale(obj, [src] + [d for d in _deps() if d.endswith((".cuh", ".hpp", ".h"))]):
+                continue
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu"] * src.endswith(".cu") + ["-c", src, "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        for src, p in procs:
+            out, _ = p.communicate()
+            if verbose or p.returncode:
+                sys.stderr.write(out)
+            if p.returncode:
+                raise RuntimeError(f"nvcc failed on {src}")
+        link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                               "-Xcompiler", "-pthread", "-l:libz.so.1"]
+        subprocess.check_call(link)
+    cli_src = os.path.join(CSRC, "cli", "main.cpp")
+    if os.path.exists(cli_src) and (force or _stale(CLI_PATH, [cli_src, LIB_PATH])):
+        os.makedirs(os.path.dirname(CLI_PATH), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(PKG_DIR, "..", "include"),
+                               cli_src, "-o", CLI_PATH, "-L", PKG_DIR, "-lgalah_b200",
+                               "-Wl,-rpath,$ORIGIN/..", "-pthread"])
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB_PATH)

@@ -1,0 +1,331 @@
+// extern "C" boundary of libgalah_b200.so (declared in include/galah_b200.h).
+#include "../../include/galah_b200.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+#include "host/fasta.hpp"
+#include "prefilter.cuh"
+#include "sketch.cuh"
+
+namespace gb200 {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const std::string &msg) { t_error = msg; }
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+    t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+              std::to_string(line) + ")";
+    return GALAH_B200_ERR_CUDA;
+}
+
+struct Context {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    PrefilterWorkspace pws;
+    SketchWorkspace sws;
+};
+static Context g_ctx;
+static std::mutex g_mu;
+
+static int require_ctx() {
+    if (g_ctx.device < 0) {
+        set_error("galah_b200: no device bound -- call galah_b200_init(device) first "
+                  "(there is no CPU fallback)");
+        return GALAH_B200_ERR_NO_DEVICE;
+    }
+    GB_CUDA(cudaSetDevice(g_ctx.device));
+    return 0;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+        return 0;
+    }
+};
+
+// Run the prefilter kernels for one shard and finish the survivors on the host in f64
+// (reference: src/finch.rs:78-93).
+static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                         int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
+                         galah_b200_pair_t **out, size_t *n_out) {
+    *out = nullptr; *n_out = 0;
+    if ((reinterpret_cast<uintptr_t>(d_hashes) & 15) != 0) {
+        set_error("prefilter: sketch table must be 16-byte aligned");
+        return GALAH_B200_ERR_ARG;
+    }
+    DevBuf<unsigned long long> d_n;
+    if (d_n.alloc(1)) return GALAH_B200_ERR_CUDA;
+    size_t cap = std::max<size_t>(1 << 16, 32 * n);
+    std::vector<uint4> cand;
+    for (;;) {
+        DevBuf<uint4> d_cand;
+        if (d_cand.alloc(cap)) return GALAH_B200_ERR_CUDA;
+        int rc = prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards,
+                                   0, stream, d_cand.p, cap, d_n.p);
+        if (rc) return rc;
+        unsigned long long got = 0;
+        GB_CUDA(cudaMemcpyAsync(&got, d_n.p, sizeof(got), cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaStreamSynchronize(stream));
+        if (got > cap) { cap = (size_t)got; continue; }
+        cand.resize((size_t)got);
+        if (got) GB_CUDA(cudaMemcpy(cand.data(), d_cand.p, (size_t)got * sizeof(uint4), cudaMemcpyDeviceToHost));
+        break;
+    }
+    std::vector<galah_b200_pair_t> pass;
+    pass.reserve(cand.size());
+    const double thr = (double)min_ani;
+    for (const uint4 &c : cand) {
+        const double ani = mash_ani_f64(c.z, c.w, k);
+        if (ani >= thr) pass.push_back(galah_b200_pair_t{c.x, c.y, c.z, c.w, (float)ani});
+    }
+    std::sort(pass.begin(), pass.end(), [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) {
+        return a.i != b.i ? a.i < b.i : a.j < b.j;
+    });
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(pass.size(), 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!pass.empty()) memcpy(res, pass.data(), pass.size() * sizeof(galah_b200_pair_t));
+    *out = res; *n_out = pass.size();
+    return 0;
+}
+
+// Sketch a set of packed genomes that live on the host; results land in host rows.
+static int sketch_packed_host(const std::vector<const PackedGenome *> &genomes, int k, uint32_t s,
+                              uint64_t seed, uint64_t *hashes, uint32_t *counts) {
+    const size_t n = genomes.size();
+    if (n == 0) return 0;
+    std::vector<uint64_t> base_off(n + 1, 0);
+    for (size_t g = 0; g < n; g++) base_off[g + 1] = base_off[g] + genomes[g]->padded_bases();
+    const uint64_t total = base_off[n];
+    std::vector<uint32_t> seq2(total / 16 + 4, 0u), valid(total / 32 + 4, 0u);
+    for (size_t g = 0; g < n; g++) {
+        const uint64_t pb = genomes[g]->padded_bases();
+        memcpy(seq2.data() + base_off[g] / 16, genomes[g]->seq2.data(), pb / 16 * 4);
+        memcpy(valid.data() + base_off[g] / 32, genomes[g]->valid.data(), pb / 32 * 4);
+    }
+    DevBuf<uint32_t> d_seq2, d_valid, d_counts;
+    DevBuf<uint64_t> d_off, d_hashes;
+    if (d_seq2.alloc(seq2.size()) || d_valid.alloc(valid.size()) || d_off.alloc(n + 1) ||
+        d_hashes.alloc(n * (size_t)s) || d_counts.alloc(n))
+        return GALAH_B200_ERR_CUDA;
+    cudaStream_t st = g_ctx.stream;
+    GB_CUDA(cudaMemcpyAsync(d_seq2.p, seq2.data(), seq2.size() * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_valid.p, valid.data(), valid.size() * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_off.p, base_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, n, k, s, seed, d_hashes.p,
+                            d_counts.p, s, st);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(hashes, d_hashes.p, n * (size_t)s * 8, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(counts, d_counts.p, n * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace gb200
+
+using namespace gb200;
+
+extern "C" {
+
+const char *galah_b200_last_error(void) { return t_error.c_str(); }
+const char *galah_b200_version(void) { return "galah-b200 0.1.0 (sm_100a)"; }
+void galah_b200_free(void *p) { free(p); }
+uint64_t galah_b200_launch_count(void) { return g_launch_count.load(); }
+
+int galah_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int galah_b200_init(int device) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("galah_b200_init: no CUDA device visible (this library has no CPU fallback)");
+        return GALAH_B200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("galah_b200_init: device index out of range"); return GALAH_B200_ERR_ARG; }
+    cudaDeviceProp prop;
+    GB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("galah_b200_init: device '") + prop.name +
+                  "' is not sm_100; kernels are built for sm_100a only");
+        return GALAH_B200_ERR_NO_DEVICE;
+    }
+    if (g_ctx.device >= 0 && g_ctx.device != device) {
+        cudaSetDevice(g_ctx.device);
+        g_ctx.pws.release(); g_ctx.sws.release();
+        if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+        g_ctx.stream = nullptr;
+    }
+    GB_CUDA(cudaSetDevice(device));
+    if (!g_ctx.stream) GB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    g_ctx.device = device;
+    return 0;
+}
+
+int galah_b200_sketch_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
+                                    const uint64_t *d_base_off, size_t n, uint8_t k, uint32_t s,
+                                    uint64_t seed, uint64_t *d_hashes, uint32_t *d_counts, void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_base_off, n, k, s, seed, d_hashes, d_counts, s, st);
+}
+
+int galah_b200_sketch_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                             size_t n, uint8_t k, uint32_t s, uint64_t seed, uint64_t *hashes,
+                             uint32_t *counts) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (n == 0) return 0;
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("sketch_packed: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
+    const uint64_t total = base_off[n];
+    DevBuf<uint32_t> d_seq2, d_valid, d_counts;
+    DevBuf<uint64_t> d_off, d_hashes;
+    if (d_seq2.alloc(total / 16 + 4) || d_valid.alloc(total / 32 + 4) || d_off.alloc(n + 1) ||
+        d_hashes.alloc(n * (size_t)s) || d_counts.alloc(n))
+        return GALAH_B200_ERR_CUDA;
+    cudaStream_t st = g_ctx.stream;
+    GB_CUDA(cudaMemsetAsync(d_seq2.p, 0, (total / 16 + 4) * 4, st));
+    GB_CUDA(cudaMemsetAsync(d_valid.p, 0, (total / 32 + 4) * 4, st));
+    GB_CUDA(cudaMemcpyAsync(d_seq2.p, seq2, total / 16 * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_valid.p, valid, total / 32 * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_off.p, base_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, n, k, s, seed, d_hashes.p,
+                            d_counts.p, s, st);
+    if (rc) return rc;
+    GB_CUDA(cudaMemcpyAsync(hashes, d_hashes.p, n * (size_t)s * 8, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(counts, d_counts.p, n * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int galah_b200_sketch_files(const char *const *paths, size_t n, uint8_t k, uint32_t s, uint64_t seed,
+                            int host_threads, uint64_t *hashes, uint32_t *counts) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (s & 1) { set_error("sketch_files: s must be even (row stride alignment)"); return GALAH_B200_ERR_ARG; }
+    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    // Batches bounded by genome count and packed size; parse on host threads, sketch on the GPU.
+    const size_t kMaxBatchGenomes = 512;
+    const uint64_t kMaxBatchBases = 3ull << 30;
+    size_t done = 0;
+    while (done < n) {
+        const size_t want = std::min(kMaxBatchGenomes, n - done);
+        std::vector<PackedGenome> batch(want);
+        std::vector<std::string> errs(want);
+        std::vector<int> rcs(want, 0);
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                size_t x = next.fetch_add(1);
+                if (x >= want) break;
+                rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
+            }
+        };
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
+        for (int t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &t : th) t.join();
+        for (size_t x = 0; x < want; x++)
+            if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
+        // split the batch further if it is too large for one upload
+        size_t b0 = 0;
+        while (b0 < want) {
+            size_t b1 = b0; uint64_t bases = 0;
+            while (b1 < want && (b1 == b0 || bases + batch[b1].padded_bases() <= kMaxBatchBases)) {
+                bases += batch[b1].padded_bases(); b1++;
+            }
+            std::vector<const PackedGenome *> ptrs;
+            for (size_t x = b0; x < b1; x++) ptrs.push_back(&batch[x]);
+            int rc = sketch_packed_host(ptrs, k, s, seed, hashes + (done + b0) * (size_t)s, counts + done + b0);
+            if (rc) return rc;
+            b0 = b1;
+        }
+        done += want;
+    }
+    return 0;
+}
+
+int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                                 size_t stride, uint8_t k, float min_ani, uint32_t shard,
+                                 uint32_t n_shards, int mode, void *stream, uint32_t *d_cand,
+                                 size_t cand_cap, unsigned long long *d_n_cand) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, mode,
+                             st, reinterpret_cast<uint4 *>(d_cand), cand_cap, d_n_cand);
+}
+
+int galah_b200_prefilter_device(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                                size_t stride, uint8_t k, float min_ani, uint32_t shard,
+                                uint32_t n_shards, void *stream, galah_b200_pair_t **out, size_t *n_out) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return run_prefilter(d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, st, out, n_out);
+}
+
+int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, size_t n, size_t stride,
+                               uint8_t k, float min_ani, uint32_t shard, uint32_t n_shards,
+                               galah_b200_pair_t **out, size_t *n_out) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    *out = nullptr; *n_out = 0;
+    if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return GALAH_B200_ERR_ARG; }
+    DevBuf<uint64_t> d_hashes;
+    DevBuf<uint32_t> d_counts;
+    if (d_hashes.alloc(n * stride) || d_counts.alloc(n)) return GALAH_B200_ERR_CUDA;
+    cudaStream_t st = g_ctx.stream;
+    GB_CUDA(cudaMemcpyAsync(d_hashes.p, hashes, n * stride * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_counts.p, counts, n * 4, cudaMemcpyHostToDevice, st));
+    return run_prefilter(d_hashes.p, d_counts.p, n, stride, k, min_ani, shard, n_shards, st, out, n_out);
+}
+
+int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t n, size_t stride,
+                         uint8_t k, float min_ani, galah_b200_pair_t **out, size_t *n_out) {
+    return galah_b200_prefilter_shard(hashes, counts, n, stride, k, min_ani, 0, 1, out, n_out);
+}
+
+int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani, uint32_t num_kmers,
+                               uint8_t kmer_length, int host_threads, galah_b200_pair_t **out,
+                               size_t *n_out) {
+    *out = nullptr; *n_out = 0;
+    const uint32_t s = num_kmers + (num_kmers & 1);  // even row stride; rows hold <= num_kmers
+    std::vector<uint64_t> hashes((size_t)n * s);
+    std::vector<uint32_t> counts(n);
+    if (num_kmers & 1) { set_error("finch_distances: odd num_kmers not supported yet"); return GALAH_B200_ERR_UNSUPPORTED; }
+    int rc = galah_b200_sketch_files(paths, n, kmer_length, s, 0, host_threads, hashes.data(), counts.data());
+    if (rc) return rc;
+    return galah_b200_prefilter(hashes.data(), counts.data(), n, s, kmer_length, min_ani, out, n_out);
+}
+
+int galah_b200_synth_packed_device(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,
+                                   uint32_t *d_seq2, uint32_t *d_valid, uint64_t *d_base_off, void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return synth_enqueue(seed, index_begin, n, length, d_seq2, d_valid, d_base_off, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Shared helpers for the sm_100a kernels: error plumbing, PTX wrappers for mbarrier + 1-D TMA
+// bulk copies (cp.async.bulk, SASS UBLKCP), warp utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+
+namespace gb200 {
+
+constexpr uint64_t kPad = 0xFFFFFFFFFFFFFFFFull;  // sketch-row padding value
+constexpr int kNumSMsFallback = 148;
+
+// ---- host-side error state (thread-local message, see abi.cu) --------------------------------
+void set_error(const std::string &msg);
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define GB_CUDA(call)                                                        \
+    do {                                                                     \
+        cudaError_t _e = (call);                                             \
+        if (_e != cudaSuccess) return ::gb200::fail_cuda(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define GB_LAUNCH_CHECK()                                  \
+    do {                                                   \
+        ::gb200::g_launch_count.fetch_add(1);              \
+        GB_CUDA(cudaGetLastError());                       \
+    } while (0)
+
+// ---- device-side PTX wrappers ------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0,
+// both addresses 16-byte aligned).
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#endif
+
+}  // namespace gb200

@@ -1,0 +1,368 @@
+// Stage 1b (K2): all-pairs sketch intersection on sm_100a.
+//
+// Replaces the serial loop at /root/reference/src/finch.rs:75-95, i.e. for every i<j
+//   finch::distance::distance(s_i, s_j, false)  ->  raw_distance: two-pointer merge while both
+//   sketches have elements, common = #equal, total = i + j - common
+// followed by the Mash-ANI threshold.  The kernels here produce the INTEGERS (common, total);
+// the f64 formula and the `>= min_ani as f64` comparison are finished on the host (abi.cu) so
+// that `ln` rounds exactly like the reference's.
+//
+// Exactness notes
+//   * raw_distance's loop ends when either list is exhausted, so with A the list whose maximum
+//     is smaller (or equal):  i = |A|,  j = #{b in B : b <= max A},  common = |A n B|.
+//     (Every common element is <= min(max A, max B), hence counted before the loop ends.)
+//     `common` can therefore be computed by any intersection method; `total` follows from one
+//     rank query.  Verified against the sequential merge in tests/test_prefilter_gpu.py.
+//   * a pair can only pass if common >= cmin_by_tmin[min(|A|,|B|)] (total >= min(|A|,|B|) and
+//     ANI is monotone in common/total); the tables are built on the host from the same f64
+//     formula with one unit of slack, and every survivor is re-evaluated exactly on the host.
+//
+// Data movement: a work item = one block of kRowBlock row sketches kept resident in shared
+// memory + up to kColChunk column blocks streamed through a 2-stage ring.  Every block of
+// sketches is contiguous in the table, so each stage is ONE 1-D TMA bulk copy
+// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) of kColBlock*stride*8 bytes.
+// Each warp intersects one pair at a time with a merge-path split across its 32 lanes.
+#include "prefilter.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gb200 {
+
+// ------------------------------------------------------------------------------------------
+// host: exact f64 formula + conservative integer thresholds
+// ------------------------------------------------------------------------------------------
+double mash_ani_f64(uint64_t common, uint64_t total, int k) {
+    // finch 0.6 distance(): jaccard = common / total; mash_distance = -ln(2j/(1+j))/k clamped by
+    // f64::min(1, f64::max(0, d)) (NaN-ignoring, like fmin/fmax); galah: 1.0 - mash_distance.
+    double jaccard = (double)common / (double)total;
+    double md = -1.0 * log((2.0 * jaccard) / (1.0 + jaccard)) / (double)k;
+    md = fmin(1.0, fmax(0.0, md));
+    return 1.0 - md;
+}
+
+PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani) {
+    PrefilterThresholds t;
+    const double thr = (double)min_ani;
+    // cmin_by_total[T] = (smallest c in [0, T] with ani(c, T) >= thr) - 1 slack, T+1 if none.
+    // ani is monotone non-decreasing in c for fixed T, so a binary search would do; the table is
+    // tiny, so scan exactly.
+    t.cmin_by_total.resize(2 * (size_t)s_max + 1);
+    for (uint32_t T = 0; T <= 2 * s_max; T++) {
+        uint32_t c = 0;
+        while (c <= T && !(mash_ani_f64(c, T, k) >= thr)) c++;
+        t.cmin_by_total[T] = c > 0 && c <= T ? c - 1 : c;
+    }
+    // cmin_by_tmin[m]: total >= m and common <= m, so the pair needs
+    // common >= min over T >= m of cmin_by_total[T]; cmin_by_total is non-decreasing in T except
+    // for the "none" sentinel, so take the running minimum from the right to stay conservative.
+    t.cmin_by_tmin.resize((size_t)s_max + 1);
+    uint32_t run = 0xFFFFFFFFu;
+    std::vector<uint32_t> suffix_min(2 * (size_t)s_max + 2, 0xFFFFFFFFu);
+    for (int64_t T = 2 * (int64_t)s_max; T >= 0; T--) {
+        run = std::min(run, t.cmin_by_total[T]);
+        suffix_min[T] = run;
+    }
+    for (uint32_t m = 0; m <= s_max; m++) t.cmin_by_tmin[m] = suffix_min[m];
+    return t;
+}
+
+int PrefilterWorkspace::release() {
+    cudaFree(d_cmin_by_tmin); cudaFree(d_cmin_by_total); cudaFree(d_item_prefix);
+    cudaFree(d_work_counter);
+    *this = PrefilterWorkspace();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// device: warp-cooperative exact intersection of two sorted distinct u64 lists
+// ------------------------------------------------------------------------------------------
+struct KernelParams {
+    const uint64_t *hashes;
+    const uint32_t *counts;
+    uint32_t n, stride;
+    uint32_t shard, n_shards;
+    uint32_t n_row_blocks;   // ceil(n / kRowBlock), global
+    uint32_t n_local_rb;     // row blocks owned by this shard
+    const uint64_t *item_prefix;  // [n_local_rb + 1]
+    unsigned long long *work_counter;
+    const uint32_t *cmin_by_tmin;
+    const uint32_t *cmin_by_total;
+    uint4 *cand;
+    unsigned long long cand_cap;
+    unsigned long long *n_cand;
+};
+
+// Merge-path intersection.  All 32 lanes call with the same (A, na, B, nb); returns |A n B| on
+// every lane.  Ties go to A first, so a common value is seen as "take b while the previous a
+// equals it"; that test also works across lane boundaries because A[i-1] is re-read.
+template <typename PtrT>
+__device__ __forceinline__ uint32_t warp_intersect(PtrT A, uint32_t na, PtrT B, uint32_t nb) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t len = na + nb;
+    const uint32_t per = (len + 31) >> 5;
+    const uint32_t d0 = min(lane * per, len);
+    const uint32_t d1 = min(d0 + per, len);
+    // partition: smallest i with !(A[i] <= B[d0-1-i])
+    uint32_t lo = d0 > nb ? d0 - nb : 0, hi = min(d0, na);
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (A[mid] <= B[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    uint32_t i = lo, j = d0 - lo;
+    uint64_t a = i < na ? A[i] : 0, b = j < nb ? B[j] : 0;
+    uint64_t a_prev = i > 0 ? A[i - 1] : 0;
+    bool have_prev = i > 0;
+    uint32_t common = 0;
+    for (uint32_t t = d0; t < d1; t++) {
+        bool take_a = (j >= nb) || (i < na && a <= b);
+        if (take_a) {
+            a_prev = a; have_prev = true; i++;
+            if (i < na) a = A[i];
+        } else {
+            common += (have_prev && a_prev == b) ? 1u : 0u;
+            j++;
+            if (j < nb) b = B[j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) common += __shfl_xor_sync(0xffffffffu, common, o);
+    return common;
+}
+
+// #{x in X[0..nx) : x <= v}
+template <typename PtrT>
+__device__ __forceinline__ uint32_t upper_rank(PtrT X, uint32_t nx, uint64_t v) {
+    uint32_t lo = 0, hi = nx;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (X[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Lane 0 finishes a pair: conservative test, exact `total`, append.
+template <typename PtrT>
+__device__ __forceinline__ void finish_pair(const KernelParams &p, uint32_t gi, uint32_t gj, PtrT A,
+                                            uint32_t na, PtrT B, uint32_t nb, uint32_t common) {
+    const uint32_t tmin = min(na, nb);
+    if (common < p.cmin_by_tmin[tmin]) return;
+    uint32_t total;
+    if (na == 0 || nb == 0) {
+        total = 0;  // the reference's loop body never runs: i = j = 0
+    } else {
+        const uint64_t amax = A[na - 1], bmax = B[nb - 1];
+        if (amax <= bmax) total = na + upper_rank(B, nb, amax) - common;
+        else total = nb + upper_rank(A, na, bmax) - common;
+    }
+    if (common < p.cmin_by_total[total]) return;
+    unsigned long long slot = atomicAdd(p.n_cand, 1ull);
+    if (slot < p.cand_cap) p.cand[slot] = make_uint4(gi, gj, common, total);
+}
+
+// ------------------------------------------------------------------------------------------
+// tiled kernel: TMA-staged shared-memory tiles, warp per pair
+// ------------------------------------------------------------------------------------------
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+
+__global__ void __launch_bounds__(kThreads, 1) prefilter_tiled_kernel(const KernelParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const uint32_t stride = p.stride;
+    const uint32_t blk_elems = kColBlock * stride;           // u64 elements per block of 8 sketches
+    uint64_t *rows = reinterpret_cast<uint64_t *>(smem_raw);  // kRowBlock * stride
+    uint64_t *cols0 = rows + (size_t)kRowBlock * stride;      // 2 stages * kColBlock * stride
+    uint64_t *bars = cols0 + 2 * (size_t)blk_elems;           // [0]=rows, [1..2]=col stages
+    __shared__ unsigned long long s_item;
+    __shared__ uint32_t s_row_cnt[kRowBlock];
+    __shared__ uint32_t s_col_cnt[2][kColBlock];
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t ph_rows = 0, ph_col[2] = {0, 0};
+    const uint64_t n_items = p.item_prefix[p.n_local_rb];
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(p.work_counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = s_item;
+        if (item >= n_items) break;
+        // item -> (local row block, column chunk)
+        uint32_t lo = 0, hi = p.n_local_rb;  // last lr with item_prefix[lr] <= item
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint32_t rb = p.shard + lo * p.n_shards;
+        const uint32_t chunk = (uint32_t)(item - p.item_prefix[lo]);
+        const uint32_t cb0 = rb + chunk * kColChunk;
+        const uint32_t cb1 = min(cb0 + (uint32_t)kColChunk, p.n_row_blocks);
+        const uint32_t row0 = rb * kRowBlock;
+        const uint32_t nrows = min((uint32_t)kRowBlock, p.n - row0);
+
+        if (tid == 0) {
+            const uint32_t bytes = nrows * stride * 8u;
+            mbar_arrive_expect_tx(&bars[0], bytes);
+            tma_load_1d(rows, p.hashes + (size_t)row0 * stride, bytes, &bars[0]);
+            const uint32_t c0 = cb0 * kColBlock, nc = min((uint32_t)kColBlock, p.n - c0);
+            mbar_arrive_expect_tx(&bars[1], nc * stride * 8u);
+            tma_load_1d(cols0, p.hashes + (size_t)c0 * stride, nc * stride * 8u, &bars[1]);
+        }
+        if (tid < nrows) s_row_cnt[tid] = p.counts[row0 + tid];
+        {
+            const uint32_t c0 = cb0 * kColBlock, nc = min((uint32_t)kColBlock, p.n - c0);
+            if (tid >= 32 && tid < 32 + nc) s_col_cnt[0][tid - 32] = p.counts[c0 + tid - 32];
+        }
+        mbar_wait(&bars[0], ph_rows); ph_rows ^= 1;
+
+        for (uint32_t cb = cb0; cb < cb1; cb++) {
+            const uint32_t st = (cb - cb0) & 1;
+            const uint32_t col0 = cb * kColBlock;
+            const uint32_t ncols = min((uint32_t)kColBlock, p.n - col0);
+            if (cb + 1 < cb1) {  // prefetch next column block into the other stage
+                const uint32_t c0 = (cb + 1) * kColBlock, nc = min((uint32_t)kColBlock, p.n - c0);
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&bars[1 + (st ^ 1)], nc * stride * 8u);
+                    tma_load_1d(cols0 + (size_t)(st ^ 1) * blk_elems, p.hashes + (size_t)c0 * stride,
+                                nc * stride * 8u, &bars[1 + (st ^ 1)]);
+                }
+                if (tid >= 32 && tid < 32 + nc) s_col_cnt[st ^ 1][tid - 32] = p.counts[c0 + tid - 32];
+            }
+            mbar_wait(&bars[1 + st], ph_col[st]); ph_col[st] ^= 1;
+            __syncthreads();  // counts visible
+            const uint64_t *cols = cols0 + (size_t)st * blk_elems;
+            for (uint32_t q = warp; q < kRowBlock * kColBlock; q += kWarps) {
+                const uint32_t r = q >> 3, c = q & 7;
+                const uint32_t gi = row0 + r, gj = col0 + c;
+                if (r >= nrows || c >= ncols || gj <= gi) continue;
+                const uint64_t *A = rows + (size_t)r * stride;
+                const uint64_t *B = cols + (size_t)c * stride;
+                const uint32_t na = s_row_cnt[r], nb = s_col_cnt[st][c];
+                const uint32_t common = warp_intersect(A, na, B, nb);
+                if (lane == 0) finish_pair(p, gi, gj, A, na, B, nb, common);
+            }
+            __syncthreads();  // stage `st` (and rows, at the last cb) free for the next TMA
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic kernel for sketches too large for the shared-memory tiles: warp per pair from global
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prefilter_generic_kernel(const KernelParams p) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_items = p.item_prefix[p.n_local_rb];
+    const uint32_t warps_per_cta = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    for (;;) {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1ull);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        uint32_t lo = 0, hi = p.n_local_rb;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint32_t rb = p.shard + lo * p.n_shards;
+        const uint32_t chunk = (uint32_t)(item - p.item_prefix[lo]);
+        const uint32_t cb0 = rb + chunk * kColChunk;
+        const uint32_t cb1 = min(cb0 + (uint32_t)kColChunk, p.n_row_blocks);
+        const uint32_t row0 = rb * kRowBlock;
+        for (uint32_t gi = row0; gi < min(row0 + kRowBlock, p.n); gi++) {
+            for (uint32_t gj = max(gi + 1, cb0 * kColBlock); gj < min(cb1 * kColBlock, p.n); gj++) {
+                const uint64_t *A = p.hashes + (size_t)gi * p.stride;
+                const uint64_t *B = p.hashes + (size_t)gj * p.stride;
+                const uint32_t na = p.counts[gi], nb = p.counts[gj];
+                const uint32_t common = warp_intersect(A, na, B, nb);
+                if (lane == 0) finish_pair(p, gi, gj, A, na, B, nb, common);
+            }
+        }
+    }
+    (void)warps_per_cta; (void)warp;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launcher
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int ensure(T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return 0;
+    if (ptr) GB_CUDA(cudaFree(ptr));
+    ptr = nullptr; cap = 0;
+    GB_CUDA(cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
+static size_t tiled_smem_bytes(size_t stride) {
+    return (size_t)(kRowBlock + 2 * kColBlock) * stride * 8 + 3 * 8;
+}
+
+int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
+                      size_t n, size_t stride, int k, float min_ani, uint32_t shard,
+                      uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
+                      size_t cand_cap, unsigned long long *d_n_cand) {
+    (void)mode;
+    if (n_shards == 0 || shard >= n_shards) { set_error("prefilter: bad shard"); return 3; }
+    if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return 3; }
+    if (n >= 0x7FFFFFFFull) { set_error("prefilter: n too large"); return 3; }
+    GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
+    if (n < 2) return 0;
+
+    const uint32_t nrb = (uint32_t)((n + kRowBlock - 1) / kRowBlock);
+    std::vector<uint64_t> prefix;
+    prefix.push_back(0);
+    for (uint32_t rb = shard; rb < nrb; rb += n_shards) {
+        uint32_t chunks = (nrb - rb + kColChunk - 1) / kColChunk;
+        prefix.push_back(prefix.back() + chunks);
+    }
+    const uint32_t n_local = (uint32_t)prefix.size() - 1;
+    if (n_local == 0) return 0;
+
+    PrefilterThresholds th = make_thresholds((uint32_t)stride, k, min_ani);
+    if (ensure(ws.d_cmin_by_tmin, ws.cap_tmin, th.cmin_by_tmin.size())) return 2;
+    if (ensure(ws.d_cmin_by_total, ws.cap_total, th.cmin_by_total.size())) return 2;
+    if (ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;
+    if (!ws.d_work_counter) GB_CUDA(cudaMalloc(&ws.d_work_counter, sizeof(unsigned long long)));
+    GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_tmin, th.cmin_by_tmin.data(),
+                            th.cmin_by_tmin.size() * 4, cudaMemcpyHostToDevice, stream));
+    GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_total, th.cmin_by_total.data(),
+                            th.cmin_by_total.size() * 4, cudaMemcpyHostToDevice, stream));
+    GB_CUDA(cudaMemcpyAsync(ws.d_item_prefix, prefix.data(), prefix.size() * 8,
+                            cudaMemcpyHostToDevice, stream));
+    GB_CUDA(cudaMemsetAsync(ws.d_work_counter, 0, sizeof(unsigned long long), stream));
+
+    KernelParams p;
+    p.hashes = d_hashes; p.counts = d_counts; p.n = (uint32_t)n; p.stride = (uint32_t)stride;
+    p.shard = shard; p.n_shards = n_shards; p.n_row_blocks = nrb; p.n_local_rb = n_local;
+    p.item_prefix = ws.d_item_prefix; p.work_counter = ws.d_work_counter;
+    p.cmin_by_tmin = ws.d_cmin_by_tmin; p.cmin_by_total = ws.d_cmin_by_total;
+    p.cand = d_cand; p.cand_cap = cand_cap; p.n_cand = d_n_cand;
+
+    int dev = 0, sms = kNumSMsFallback, max_smem = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const uint64_t n_items = prefix.back();
+    const size_t smem = tiled_smem_bytes(stride);
+    if (smem + 1024 <= (size_t)max_smem) {
+        GB_CUDA(cudaFuncSetAttribute(prefilter_tiled_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms);
+        prefilter_tiled_kernel<<<grid, kThreads, smem, stream>>>(p);
+    } else {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_items + 7) / 8, (uint64_t)sms * 8);
+        prefilter_generic_kernel<<<std::max(grid, 1u), 256, 0, stream>>>(p);
+    }
+    GB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace gb200

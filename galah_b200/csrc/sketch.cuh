@@ -1,0 +1,25 @@
+// Stage 1a (K1): per-genome bottom-s MinHash sketch.  Host-side launch interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gb200 {
+
+struct SketchWorkspace {
+    unsigned long long *d_work_counter = nullptr;
+    int release();
+};
+
+uint32_t sketch_set_capacity(uint32_t s);
+
+// Enqueue the sketch kernel over n packed genomes (layout: see sketch.cu / galah_b200.h).
+// d_hashes: n rows of out_stride uint64 (>= s), padded with 2^64-1; d_counts: n.
+int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
+                   const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
+                   uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream);
+
+// Synthetic genomes, generated directly in packed form on the device.
+int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length, uint32_t *d_seq2,
+                  uint32_t *d_valid, uint64_t *d_base_off, cudaStream_t stream);
+
+}  // namespace gb200

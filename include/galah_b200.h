@@ -1,0 +1,127 @@
+/*
+ * galah_b200.h -- C ABI of libgalah_b200.so, the B200 (sm_100a) implementation of Galah's
+ * two-stage dereplication hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Each entry point names the reference interface it replaces (file:line into wwood/galah
+ * v0.5.1).  The Rust-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; galah_b200_last_error() then
+ *     returns a thread-local, NUL-terminated message.  There is NO CPU fallback: with no usable
+ *     sm_100 device every compute entry point fails with GALAH_B200_ERR_NO_DEVICE.
+ *   - "host" entry points take host pointers and do their own H2D/D2H copies;
+ *     "_device" entry points take device pointers valid on the current device and enqueue on
+ *     the given cudaStream_t (passed as void*; NULL = the CUDA default stream, as usual).
+ *   - a sketch table is n rows of `stride` uint64 (stride >= s, stride even), row g holding
+ *     counts[g] ascending distinct hashes followed by 0xFFFFFFFFFFFFFFFF padding.
+ *   - buffers returned through `**out` are owned by the library; release with galah_b200_free().
+ */
+#ifndef GALAH_B200_H
+#define GALAH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GALAH_B200_OK 0
+#define GALAH_B200_ERR_NO_DEVICE 1
+#define GALAH_B200_ERR_CUDA 2
+#define GALAH_B200_ERR_ARG 3
+#define GALAH_B200_ERR_IO 4
+#define GALAH_B200_ERR_UNSUPPORTED 5 /* mirrors a reference panic; message carries its text */
+
+/* One stage-1 hit.  (i, j) are positions in the caller's genome slice with i < j -- the key of
+ * SortedPairGenomeDistanceCache (src/sorted_pair_genome_distance_cache.rs:22-28); `ani` is the
+ * `Some(distance as f32)` value stored at src/finch.rs:92; common/total are finch's
+ * raw_distance integers, exposed so parity can be checked bit-exactly. */
+typedef struct galah_b200_pair {
+    uint32_t i, j;
+    uint32_t common, total;
+    float ani;
+} galah_b200_pair_t;
+
+/* ---- library / device ------------------------------------------------------------------ */
+
+/* Bind the calling process to CUDA device `device` (>= 0) and create the library stream.
+ * Must be called before any compute entry point; may be called again to switch device. */
+int galah_b200_init(int device);
+int galah_b200_device_count(void);
+const char *galah_b200_last_error(void);
+const char *galah_b200_version(void);
+void galah_b200_free(void *p);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t galah_b200_launch_count(void);
+
+/* ---- stage 1a: sketching ----------------------------------------------------------------
+ * Replaces `finch::sketch_files(paths, SketchParams::Mash{kmers_to_sketch: s, final_size: s,
+ * no_strict: true, kmer_length: k, hash_seed: seed}, filters off)` at src/finch.rs:55-69.
+ * FASTA/FASTQ, plain or gzip; all records of a file pooled; needletail normalize(false)
+ * semantics.  hashes: n*s uint64 (row stride s, s even), counts: n. */
+int galah_b200_sketch_files(const char *const *paths, size_t n, uint8_t k, uint32_t s,
+                            uint64_t seed, int host_threads, uint64_t *hashes, uint32_t *counts);
+
+/* Same kernel on sequence already packed on the HOST: 2 bits/base LSB-first in uint32 words
+ * (A0 C1 G2 T3), plus a validity bitmap (1 bit/base, 1 = ACGT).  Genome g covers bases
+ * [base_off[g], base_off[g+1]) of the concatenated arrays; base_off[g] must be a multiple of
+ * 128.  Records inside a genome are separated by at least one invalid base. */
+int galah_b200_sketch_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                             size_t n, uint8_t k, uint32_t s, uint64_t seed, uint64_t *hashes,
+                             uint32_t *counts);
+
+/* Device-resident variant (all pointers are device pointers; d_hashes has row stride s). */
+int galah_b200_sketch_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
+                                    const uint64_t *d_base_off, size_t n, uint8_t k, uint32_t s,
+                                    uint64_t seed, uint64_t *d_hashes, uint32_t *d_counts,
+                                    void *stream);
+
+/* ---- stage 1b: all-pairs prefilter --------------------------------------------------------
+ * Replaces the serial pair loop at src/finch.rs:75-95 (finch::distance::distance ->
+ * raw_distance -> mash_distance; keep iff 1 - d >= min_ani as f64; store as f32).
+ * Evaluates every pair i < j.
+ * Output is sorted by (i, j).  min_ani is a FRACTION (src/finch.rs:5-6). */
+int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t n, size_t stride,
+                         uint8_t k, float min_ani, galah_b200_pair_t **out, size_t *n_out);
+
+/* Row-sharded variants for multi-GPU runs: the call covers row blocks
+ * rb = shard, shard + n_shards, ... (blocks of GALAH_B200_ROW_BLOCK rows), which balances the
+ * triangular pair area across shards.  _shard takes host pointers, _device device pointers;
+ * result pairs always land on the HOST. */
+#define GALAH_B200_ROW_BLOCK 8
+int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, size_t n,
+                               size_t stride, uint8_t k, float min_ani, uint32_t shard,
+                               uint32_t n_shards, galah_b200_pair_t **out, size_t *n_out);
+int galah_b200_prefilter_device(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                                size_t stride, uint8_t k, float min_ani, uint32_t shard,
+                                uint32_t n_shards, void *stream, galah_b200_pair_t **out,
+                                size_t *n_out);
+
+/* Kernel-only timing hook used by bench.py: enqueues the prefilter kernels for one shard on
+ * `stream` and leaves the candidate list on the device (d_cand, capacity cand_cap entries of
+ * 4 x uint32 {i, j, common, total}; d_n_cand is a device uint64 counter).  No host sync.
+ * mode: 0 = default (screen + exact merge), 1 = exhaustive exact merge of every pair. */
+int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                                 size_t stride, uint8_t k, float min_ani, uint32_t shard,
+                                 uint32_t n_shards, int mode, void *stream, uint32_t *d_cand,
+                                 size_t cand_cap, unsigned long long *d_n_cand);
+
+/* Whole `finch::distances(paths, min_ani, num_kmers, kmer_length)` (src/finch.rs:48-97):
+ * sketch every path on the GPU, then the all-pairs prefilter. */
+int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani,
+                               uint32_t num_kmers, uint8_t kmer_length, int host_threads,
+                               galah_b200_pair_t **out, size_t *n_out);
+
+/* ---- synthetic genomes (bench / tests) ------------------------------------- */
+/* Generates genomes [index_begin, index_begin+n) of `length` bases each directly in packed
+ * form on the device.  d_seq2 needs n * words_per_genome uint32 with
+ * words_per_genome = round_up(length, 128) / 16; d_valid n * round_up(length,128)/32. */
+int galah_b200_synth_packed_device(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,
+                                   uint32_t *d_seq2, uint32_t *d_valid, uint64_t *d_base_off,
+                                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GALAH_B200_H */

@@ -1,0 +1,118 @@
+"""K2 parity: the CUDA all-pairs prefilter vs the CPU oracle (bit-exact), through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle
+from util import PAD, assert_pairs_equal, random_family_table
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_fixture_pair_list(gb, golden):
+    """Sketches of the reference's own test genomes -> identical pair list (i, j, common, total,
+    ani bits), including the reference-pinned (502, 1000, 0.9808188) row."""
+    got = gb.prefilter(golden["table"], golden["counts"], 21, 0.9)
+    assert_pairs_equal(got, golden["pairs_min_ani_0p9"])
+    assert (got[0]["i"], got[0]["j"], got[0]["common"], got[0]["total"]) == (0, 1, 502, 1000)
+    assert got[0]["ani"] == np.float32(0.9808188)
+
+
+@pytest.mark.parametrize("n,s,seed", [(2, 1000, 0), (9, 1000, 1), (64, 1000, 2), (301, 1000, 3), (130, 10, 4), (77, 500, 5)])
+def test_random_families_match_oracle(gb, n, s, seed):
+    rng = np.random.default_rng(seed)
+    table, counts = random_family_table(n, s, rng)
+    for min_ani in (0.9, 0.95):
+        assert_pairs_equal(gb.prefilter(table, counts, 21, min_ani), oracle.prefilter(table, counts, 21, min_ani))
+
+
+def test_ragged_and_empty_sketches(gb):
+    rng = np.random.default_rng(7)
+    table, counts = random_family_table(120, 1000, rng, ragged=True)
+    counts[3] = 0; table[3] = PAD
+    counts[17] = 0; table[17] = PAD
+    counts[40] = 1; table[40, 1:] = PAD
+    exp = oracle.prefilter(table, counts, 21, 0.9)
+    got = gb.prefilter(table, counts, 21, 0.9)
+    assert_pairs_equal(got, exp)
+    # two empty sketches: 0/0 -> NaN -> clamped to distance 0 -> ANI 1.0 (flagged reference quirk)
+    hit = [(int(p["i"]), int(p["j"])) for p in got if p["total"] == 0]
+    assert (3, 17) in hit
+
+
+@pytest.mark.parametrize("min_ani", [0.0, 0.5, 0.99, 1.0])
+def test_threshold_extremes(gb, min_ani):
+    rng = np.random.default_rng(11)
+    table, counts = random_family_table(60, 1000, rng)
+    table[5] = table[4]; counts[5] = counts[4]  # an identical pair (ANI exactly 1.0)
+    exp = oracle.prefilter(table, counts, 21, min_ani)
+    got = gb.prefilter(table, counts, 21, min_ani)
+    assert_pairs_equal(got, exp)
+    if min_ani == 0.0:
+        assert len(got) == 60 * 59 // 2
+    if min_ani == 1.0:
+        assert (4, 5) in [(int(p["i"]), int(p["j"])) for p in got]
+
+
+def test_genuine_max_hash_value(gb):
+    """2^64-1 is also the padding value; a real hash of that value must still be counted."""
+    rng = np.random.default_rng(13)
+    table, counts = random_family_table(20, 1000, rng)
+    for g in (0, 1, 2):
+        table[g, counts[g] - 1] = PAD  # genuine element (still sorted, still distinct)
+    assert_pairs_equal(gb.prefilter(table, counts, 21, 0.5), oracle.prefilter(table, counts, 21, 0.5))
+
+
+def test_large_sketches_use_generic_kernel(gb):
+    rng = np.random.default_rng(17)
+    table, counts = random_family_table(24, 2000, rng)
+    assert_pairs_equal(gb.prefilter(table, counts, 21, 0.9), oracle.prefilter(table, counts, 21, 0.9))
+
+
+def test_other_kmer_lengths(gb):
+    rng = np.random.default_rng(19)
+    table, counts = random_family_table(50, 1000, rng)
+    for k in (15, 31):
+        assert_pairs_equal(gb.prefilter(table, counts, k, 0.9), oracle.prefilter(table, counts, k, 0.9))
+
+
+def test_degenerate_sizes(gb):
+    t = np.full((1, 1000), PAD, np.uint64)
+    assert len(gb.prefilter(t, np.zeros(1, np.uint32), 21, 0.9)) == 0
+    assert len(gb.prefilter(np.zeros((0, 1000), np.uint64), np.zeros(0, np.uint32), 21, 0.9)) == 0
+
+
+def test_row_shards_partition_the_pair_list(gb):
+    import torch
+    rng = np.random.default_rng(23)
+    n, s = 333, 1000
+    table, counts = random_family_table(n, s, rng)
+    exp = oracle.prefilter(table, counts, 21, 0.9)
+    d_t = torch.from_numpy(table.view(np.int64)).cuda()
+    d_c = torch.from_numpy(counts.view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+    for n_shards in (1, 2, 4, 8):
+        parts = [gb.prefilter_device(d_t.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, r, n_shards, stream)
+                 for r in range(n_shards)]
+        allp = np.concatenate(parts)
+        allp = allp[np.lexsort((allp["j"], allp["i"]))]
+        assert_pairs_equal(allp, exp)
+        # shard r owns row blocks r, r+n_shards, ...
+        for r, part in enumerate(parts):
+            assert np.all((part["i"] // gb.ROW_BLOCK) % n_shards == r)
+
+
+def test_medium_table_sampled_rows(gb):
+    """N=3000 (4.5 M pairs) on the GPU; the oracle checks a row sample and the all-core count."""
+    rng = np.random.default_rng(29)
+    n, s = 3000, 1000
+    table, counts = random_family_table(n, s, rng)
+    got = gb.prefilter(table, counts, 21, 0.9)
+    assert len(got) == oracle.prefilter_count_mt(table, counts, 21, 0.9)
+    for r0 in (0, 1492, 2990):
+        exp = oracle.prefilter(table, counts, 21, 0.9, row_begin=r0, row_end=r0 + 8)
+        sub = got[(got["i"] >= r0) & (got["i"] < r0 + 8)]
+        assert_pairs_equal(sub, exp)
+    # size-independent properties: keys strictly increasing, i < j, common <= total
+    key = got["i"].astype(np.int64) * n + got["j"]
+    assert np.all(np.diff(key) > 0) and np.all(got["i"] < got["j"]) and np.all(got["common"] <= got["total"])
