@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -138,13 +138,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-genomes", type=int, default=10000, help="genomes at 1 GPU (x sqrt(G) at G GPUs)")
     ap.add_argument("--genome-len", type=int, default=2_000_000)
-    ap.add_argument("--mode", type=int, default=0, help="0 = default path, 1 = exhaustive exact merge")
+    ap.add_argument("--mode", type=int, default=0, help="0 = block-list join (default), 1 = pairwise warp merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip timing the other kernel path")
     ap.add_argument("--cpu-rows", type=int, default=100)
     ap.add_argument("--ref-genomes", type=int, default=2000)
     ap.add_argument("--ref-rows", type=int, default=100)
@@ -208,12 +209,38 @@ def main():
     d_ncand = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.int8, device=dev)  # > 126 MB L2
 
-    def step():
+    def timed(mode, steps, warmup):
+        """`steps` timed passes of `mode`; returns (total_ms max over ranks, launches, per-kernel ms)."""
+        def step():
+            if world > 1:
+                dist.all_gather_into_tensor(table, my_table)
+                dist.all_gather_into_tensor(counts, my_counts)
+            gb.prefilter_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, rank, world,
+                                 mode, st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
+        for _ in range(warmup):
+            flush.fill_(1)
+            step()
+        sync_all()
+        if steps == 0:
+            return 0.0, 0, 0.0, 0.0
+        launches0 = gb.launch_count()
+        step_ms, build_ms, main_ms = [], [], []
+        for _ in range(steps):
+            flush.fill_(1)  # L2 flush between timed iterations (outside the events)
+            sync_all()
+            ev0.record(stream)
+            step()
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            step_ms.append(ev0.elapsed_time(ev1))
+            b, m = gb.prefilter_last_timing()
+            build_ms.append(b); main_ms.append(m)
+        sync_all()
+        launches = gb.launch_count() - launches0
+        tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_gather_into_tensor(table, my_table)
-            dist.all_gather_into_tensor(counts, my_counts)
-        gb.prefilter_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, rank, world,
-                             args.mode, st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), launches, float(np.mean(build_ms)), float(np.mean(main_ms))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -221,35 +248,23 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        flush.fill_(1)
-        step()
-    sync_all()
-
     sampler = ClockSampler(local_rank)
+    timed(args.mode, 0, args.warmup)
     if rank == 0:
         sampler.start()
-    launches0 = gb.launch_count()
-    step_ms = []
-    sync_all()
-    for _ in range(args.steps):
-        flush.fill_(1)  # L2 flush between timed iterations (outside the events)
-        sync_all()
-        ev0.record(stream)
-        step()
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        step_ms.append(ev0.elapsed_time(ev1))
-    sync_all()
-    launches = gb.launch_count() - launches0
+    total_ms, launches, build_ms, main_ms = timed(args.mode, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
     pairs = n * (n - 1) // 2
     value = pairs * args.steps / (total_ms * 1e-3)
     n_cand = int(d_ncand.item())
+    # the other exact kernel path, for comparison (fewer steps: the pairwise kernel is ~100x slower)
+    other = None
+    if not args.no_other_mode:
+        o_steps = max(1, min(args.steps, 3))
+        o_total, o_launches, o_build, o_main = timed(1 - args.mode, o_steps, 1)
+        other = {"mode": 1 - args.mode, "value": pairs * o_steps / (o_total * 1e-3), "unit": "pairs/s",
+                 "ms_per_step": o_total / o_steps, "steps": o_steps, "main_kernel_ms": o_main,
+                 "candidates": int(d_ncand.item())}
 
     # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H + host finish)
     h_table = table.cpu().pin_memory()
@@ -277,9 +292,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        kernel_ms = total_ms / args.steps
+        kernel_names = {0: "prefilter_join_kernel", 1: "prefilter_tiled_kernel"}
         pairs_per_launch = pairs / world
-        achieved = BYTES_PER_PAIR * pairs_per_launch / (kernel_ms * 1e-3) / 1e9
+        achieved = BYTES_PER_PAIR * pairs_per_launch / (main_ms * 1e-3) / 1e9
+        # bytes the join kernel itself has to read: each (rb, cb) item streams two block lists of
+        # 64*s entries x 9 B (value + tag) once for 64*64 pairs
+        own_bytes_per_pair = 2 * S * 9 / 64 if args.mode == 0 else BYTES_PER_PAIR
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             import oracle
@@ -314,17 +332,26 @@ def main():
                                    f"{' scaled by sqrt(G) genomes' if world > 1 else ''})",
                        "pairs_per_step": pairs, "mode": args.mode,
                        "l2": "flushed between timed iterations (256 MiB write)",
-                       "sharding": "cyclic row blocks of 8; NCCL all-gather of the sketch table inside the step"
+                       "sharding": "cyclic row blocks of 64; NCCL all-gather of the sketch table inside the step"
                                    if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "passing_pairs": int(n_pass_t.item())},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "prefilter_tiled_kernel",
+                         "frac": achieved / peak, "traffic": None, "kernel": kernel_names[args.mode],
+                         "kernel_ms": main_ms, "build_kernels_ms": build_ms,
                          "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src,
-                         "note": "tiled kernel re-uses staged sketches from shared memory, so the fraction of "
-                                 "the HBM roofline at 16 kB/pair can exceed 1 (SURVEY.md 7)"},
+                         "kernel_own_bytes_per_pair": own_bytes_per_pair,
+                         "kernel_own_gbs": own_bytes_per_pair * pairs_per_launch / (main_ms * 1e-3) / 1e9,
+                         "note": "achieved uses the reference algorithm's 2*s*8 B/pair (SURVEY.md 8d). The join "
+                                 "kernel computes every pair's exact intersection from ONE merge of two 64-sketch "
+                                 "block lists per 64x64 pairs, so it reads 2*s*9/64 B/pair (kernel_own_*) and the "
+                                 "fraction of the 16 kB/pair roofline exceeds 1 by design (DESIGN.md K2)"
+                                 if args.mode == 0 else
+                                 "pairwise kernel re-uses staged sketches from shared memory (16 kB/pair is read "
+                                 "from shared memory, not HBM)"},
+            "other_mode": other,
             "cpu_baseline": cpu,
             "candidates": n_cand,
             "sketch": {"genomes_per_s": n_local / (sketch_ms * 1e-3) if sketch_ms else None,

@@ -14,7 +14,7 @@ from ._native import GalahB200Error, Pair, check, lib
 PAIR_DTYPE = np.dtype(
     [("i", "<u4"), ("j", "<u4"), ("common", "<u4"), ("total", "<u4"), ("ani", "<f4")]
 )
-ROW_BLOCK = 8
+ROW_BLOCK = 64
 PAD = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 _bound_device = None
@@ -34,6 +34,19 @@ def device_count():
 
 def launch_count():
     return int(lib().galah_b200_launch_count())
+
+
+def prefilter_mode(mode=-1):
+    """Select the K2 kernel path (0 = block-list join, 1 = pairwise warp merge); returns the
+    previous mode.  Both are exact; mode 1 exists for cross-checks and as the large-s fallback."""
+    return int(lib().galah_b200_prefilter_mode(int(mode)))
+
+
+def prefilter_last_timing():
+    """(build_ms, main_ms) of the most recent prefilter launch (library-recorded CUDA events)."""
+    b, m = ctypes.c_float(0), ctypes.c_float(0)
+    check(lib().galah_b200_prefilter_last_timing(ctypes.byref(b), ctypes.byref(m)))
+    return float(b.value), float(m.value)
 
 
 def version():

@@ -30,8 +30,21 @@ int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
 struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;
+    int prefilter_mode = 0;
     PrefilterWorkspace pws;
     SketchWorkspace sws;
+    // buffers re-used across host-pointer prefilter calls (cudaMalloc is a device-wide sync)
+    uint64_t *d_table = nullptr; size_t cap_table = 0;
+    uint32_t *d_counts = nullptr; size_t cap_counts = 0;
+    uint4 *d_cand = nullptr; size_t cap_cand = 0;
+    unsigned long long *d_n_cand = nullptr;
+    int release() {
+        pws.release(); sws.release();
+        cudaFree(d_table); cudaFree(d_counts); cudaFree(d_cand); cudaFree(d_n_cand);
+        d_table = nullptr; d_counts = nullptr; d_cand = nullptr; d_n_cand = nullptr;
+        cap_table = cap_counts = cap_cand = 0;
+        return 0;
+    }
 };
 static Context g_ctx;
 static std::mutex g_mu;
@@ -67,22 +80,24 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
         set_error("prefilter: sketch table must be 16-byte aligned");
         return GALAH_B200_ERR_ARG;
     }
-    DevBuf<unsigned long long> d_n;
-    if (d_n.alloc(1)) return GALAH_B200_ERR_CUDA;
+    if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
     size_t cap = std::max<size_t>(1 << 16, 32 * n);
     std::vector<uint4> cand;
     for (;;) {
-        DevBuf<uint4> d_cand;
-        if (d_cand.alloc(cap)) return GALAH_B200_ERR_CUDA;
+        if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
         int rc = prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards,
-                                   0, stream, d_cand.p, cap, d_n.p);
+                                   g_ctx.prefilter_mode, stream, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand);
         if (rc) return rc;
         unsigned long long got = 0;
-        GB_CUDA(cudaMemcpyAsync(&got, d_n.p, sizeof(got), cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaMemcpyAsync(&got, g_ctx.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, stream));
         GB_CUDA(cudaStreamSynchronize(stream));
-        if (got > cap) { cap = (size_t)got; continue; }
+        if (got > g_ctx.cap_cand) { cap = (size_t)got; continue; }
         cand.resize((size_t)got);
-        if (got) GB_CUDA(cudaMemcpy(cand.data(), d_cand.p, (size_t)got * sizeof(uint4), cudaMemcpyDeviceToHost));
+        if (got) {
+            GB_CUDA(cudaMemcpyAsync(cand.data(), g_ctx.d_cand, (size_t)got * sizeof(uint4),
+                                    cudaMemcpyDeviceToHost, stream));
+            GB_CUDA(cudaStreamSynchronize(stream));
+        }
         break;
     }
     std::vector<galah_b200_pair_t> pass;
@@ -145,6 +160,19 @@ const char *galah_b200_version(void) { return "galah-b200 0.1.0 (sm_100a)"; }
 void galah_b200_free(void *p) { free(p); }
 uint64_t galah_b200_launch_count(void) { return g_launch_count.load(); }
 
+int galah_b200_prefilter_mode(int mode) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    const int prev = g_ctx.prefilter_mode;
+    if (mode == 0 || mode == 1) g_ctx.prefilter_mode = mode;
+    return prev;
+}
+
+int galah_b200_prefilter_last_timing(float *build_ms, float *main_ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    return g_ctx.pws.last_timing(build_ms, main_ms);
+}
+
 int galah_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -170,7 +198,7 @@ int galah_b200_init(int device) {
     }
     if (g_ctx.device >= 0 && g_ctx.device != device) {
         cudaSetDevice(g_ctx.device);
-        g_ctx.pws.release(); g_ctx.sws.release();
+        g_ctx.release();
         if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
         g_ctx.stream = nullptr;
     }
@@ -293,13 +321,15 @@ int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, s
     if (int rc = require_ctx()) return rc;
     *out = nullptr; *n_out = 0;
     if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return GALAH_B200_ERR_ARG; }
-    DevBuf<uint64_t> d_hashes;
-    DevBuf<uint32_t> d_counts;
-    if (d_hashes.alloc(n * stride) || d_counts.alloc(n)) return GALAH_B200_ERR_CUDA;
+    if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, std::max<size_t>(n * stride, 2)) ||
+        ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
+        return GALAH_B200_ERR_CUDA;
     cudaStream_t st = g_ctx.stream;
-    GB_CUDA(cudaMemcpyAsync(d_hashes.p, hashes, n * stride * 8, cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(d_counts.p, counts, n * 4, cudaMemcpyHostToDevice, st));
-    return run_prefilter(d_hashes.p, d_counts.p, n, stride, k, min_ani, shard, n_shards, st, out, n_out);
+    if (n) {
+        GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, hashes, n * stride * 8, cudaMemcpyHostToDevice, st));
+        GB_CUDA(cudaMemcpyAsync(g_ctx.d_counts, counts, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    return run_prefilter(g_ctx.d_table, g_ctx.d_counts, n, stride, k, min_ani, shard, n_shards, st, out, n_out);
 }
 
 int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t n, size_t stride,

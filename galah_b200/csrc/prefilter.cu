@@ -17,11 +17,20 @@
 //     ANI is monotone in common/total); the tables are built on the host from the same f64
 //     formula with one unit of slack, and every survivor is re-evaluated exactly on the host.
 //
-// Data movement: a work item = one block of kRowBlock row sketches kept resident in shared
-// memory + up to kColChunk column blocks streamed through a 2-stage ring.  Every block of
-// sketches is contiguous in the table, so each stage is ONE 1-D TMA bulk copy
-// (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) of kColBlock*stride*8 bytes.
-// Each warp intersects one pair at a time with a merge-path split across its 32 lanes.
+// Two paths, identical results (both compute |A n B| exactly for EVERY pair i < j):
+//
+//  mode 0 "block join" (default, prefilter_join.cu): the table is cut into blocks of kShardRows
+//    consecutive sketches; each block is merged once into one sorted (value, row-tag) list, and a
+//    work item intersects TWO BLOCK LISTS with a CTA-wide merge path, scattering matches into a
+//    kShardRows x kShardRows count matrix in shared memory.  One merge of 2*64*s elements yields
+//    the exact `common` of 64*64 pairs, i.e. 2s/64 merge steps per pair instead of 2s.
+//
+//  mode 1 "pairwise" (this file): prefilter_tiled_kernel -- a work item = one block of kRowBlock
+//    row sketches resident in shared memory + up to kColChunk column blocks streamed through a
+//    2-stage ring.  Every block of sketches is contiguous in the table, so each stage is ONE 1-D
+//    TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) of kColBlock*stride*8
+//    bytes.  Each warp intersects one pair at a time with a merge-path split across its lanes.
+//    Also the fallback for sketches too large for the join's shared-memory tiles.
 #include "prefilter.cuh"
 
 #include <math.h>
@@ -29,6 +38,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "prefilter_dev.cuh"
 
 namespace gb200 {
 
@@ -70,97 +80,29 @@ PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani) {
     return t;
 }
 
-int PrefilterWorkspace::release() {
-    cudaFree(d_cmin_by_tmin); cudaFree(d_cmin_by_total); cudaFree(d_item_prefix);
-    cudaFree(d_work_counter);
-    *this = PrefilterWorkspace();
+int PrefilterWorkspace::record(int which, cudaStream_t stream) {
+    if (!ev[which]) GB_CUDA(cudaEventCreate(&ev[which]));
+    GB_CUDA(cudaEventRecord(ev[which], stream));
+    if (which == 2) ev_recorded = true;
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// device: warp-cooperative exact intersection of two sorted distinct u64 lists
-// ------------------------------------------------------------------------------------------
-struct KernelParams {
-    const uint64_t *hashes;
-    const uint32_t *counts;
-    uint32_t n, stride;
-    uint32_t shard, n_shards;
-    uint32_t n_row_blocks;   // ceil(n / kRowBlock), global
-    uint32_t n_local_rb;     // row blocks owned by this shard
-    const uint64_t *item_prefix;  // [n_local_rb + 1]
-    unsigned long long *work_counter;
-    const uint32_t *cmin_by_tmin;
-    const uint32_t *cmin_by_total;
-    uint4 *cand;
-    unsigned long long cand_cap;
-    unsigned long long *n_cand;
-};
-
-// Merge-path intersection.  All 32 lanes call with the same (A, na, B, nb); returns |A n B| on
-// every lane.  Ties go to A first, so a common value is seen as "take b while the previous a
-// equals it"; that test also works across lane boundaries because A[i-1] is re-read.
-template <typename PtrT>
-__device__ __forceinline__ uint32_t warp_intersect(PtrT A, uint32_t na, PtrT B, uint32_t nb) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t len = na + nb;
-    const uint32_t per = (len + 31) >> 5;
-    const uint32_t d0 = min(lane * per, len);
-    const uint32_t d1 = min(d0 + per, len);
-    // partition: smallest i with !(A[i] <= B[d0-1-i])
-    uint32_t lo = d0 > nb ? d0 - nb : 0, hi = min(d0, na);
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (A[mid] <= B[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
-    }
-    uint32_t i = lo, j = d0 - lo;
-    uint64_t a = i < na ? A[i] : 0, b = j < nb ? B[j] : 0;
-    uint64_t a_prev = i > 0 ? A[i - 1] : 0;
-    bool have_prev = i > 0;
-    uint32_t common = 0;
-    for (uint32_t t = d0; t < d1; t++) {
-        bool take_a = (j >= nb) || (i < na && a <= b);
-        if (take_a) {
-            a_prev = a; have_prev = true; i++;
-            if (i < na) a = A[i];
-        } else {
-            common += (have_prev && a_prev == b) ? 1u : 0u;
-            j++;
-            if (j < nb) b = B[j];
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) common += __shfl_xor_sync(0xffffffffu, common, o);
-    return common;
+int PrefilterWorkspace::last_timing(float *build_ms, float *main_ms) {
+    *build_ms = 0.f; *main_ms = 0.f;
+    if (!ev_recorded) { set_error("prefilter: no completed launch to time"); return 3; }
+    GB_CUDA(cudaEventSynchronize(ev[2]));
+    GB_CUDA(cudaEventElapsedTime(build_ms, ev[0], ev[1]));
+    GB_CUDA(cudaEventElapsedTime(main_ms, ev[1], ev[2]));
+    return 0;
 }
 
-// #{x in X[0..nx) : x <= v}
-template <typename PtrT>
-__device__ __forceinline__ uint32_t upper_rank(PtrT X, uint32_t nx, uint64_t v) {
-    uint32_t lo = 0, hi = nx;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (X[mid] <= v) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// Lane 0 finishes a pair: conservative test, exact `total`, append.
-template <typename PtrT>
-__device__ __forceinline__ void finish_pair(const KernelParams &p, uint32_t gi, uint32_t gj, PtrT A,
-                                            uint32_t na, PtrT B, uint32_t nb, uint32_t common) {
-    const uint32_t tmin = min(na, nb);
-    if (common < p.cmin_by_tmin[tmin]) return;
-    uint32_t total;
-    if (na == 0 || nb == 0) {
-        total = 0;  // the reference's loop body never runs: i = j = 0
-    } else {
-        const uint64_t amax = A[na - 1], bmax = B[nb - 1];
-        if (amax <= bmax) total = na + upper_rank(B, nb, amax) - common;
-        else total = nb + upper_rank(A, na, bmax) - common;
-    }
-    if (common < p.cmin_by_total[total]) return;
-    unsigned long long slot = atomicAdd(p.n_cand, 1ull);
-    if (slot < p.cand_cap) p.cand[slot] = make_uint4(gi, gj, common, total);
+int PrefilterWorkspace::release() {
+    for (int x = 0; x < 3; x++) if (ev[x]) cudaEventDestroy(ev[x]);
+    cudaFree(d_cmin_by_tmin); cudaFree(d_cmin_by_total); cudaFree(d_item_prefix);
+    cudaFree(d_local_rb); cudaFree(d_work_counter); cudaFree(d_bl_len);
+    for (int x = 0; x < 2; x++) { cudaFree(d_bl_vals[x]); cudaFree(d_bl_tags[x]); }
+    *this = PrefilterWorkspace();
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefilter_tiled_kernel(const Kern
             uint32_t mid = (lo + hi) >> 1;
             if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
         }
-        const uint32_t rb = p.shard + lo * p.n_shards;
+        const uint32_t rb = p.local_rb[lo];
         const uint32_t chunk = (uint32_t)(item - p.item_prefix[lo]);
         const uint32_t cb0 = rb + chunk * kColChunk;
         const uint32_t cb1 = min(cb0 + (uint32_t)kColChunk, p.n_row_blocks);
@@ -270,7 +212,7 @@ __global__ void __launch_bounds__(256) prefilter_generic_kernel(const KernelPara
             uint32_t mid = (lo + hi) >> 1;
             if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
         }
-        const uint32_t rb = p.shard + lo * p.n_shards;
+        const uint32_t rb = p.local_rb[lo];
         const uint32_t chunk = (uint32_t)(item - p.item_prefix[lo]);
         const uint32_t cb0 = rb + chunk * kColChunk;
         const uint32_t cb1 = min(cb0 + (uint32_t)kColChunk, p.n_row_blocks);
@@ -292,7 +234,7 @@ __global__ void __launch_bounds__(256) prefilter_generic_kernel(const KernelPara
 // host launcher
 // ------------------------------------------------------------------------------------------
 template <typename T>
-static int ensure(T *&ptr, size_t &cap, size_t need) {
+int ws_ensure(T *&ptr, size_t &cap, size_t need) {
     if (need <= cap) return 0;
     if (ptr) GB_CUDA(cudaFree(ptr));
     ptr = nullptr; cap = 0;
@@ -300,58 +242,91 @@ static int ensure(T *&ptr, size_t &cap, size_t need) {
     cap = need;
     return 0;
 }
+template int ws_ensure<uint32_t>(uint32_t *&, size_t &, size_t);
+template int ws_ensure<uint64_t>(uint64_t *&, size_t &, size_t);
+template int ws_ensure<uint8_t>(uint8_t *&, size_t &, size_t);
+template int ws_ensure<uint4>(uint4 *&, size_t &, size_t);
 
 static size_t tiled_smem_bytes(size_t stride) {
     return (size_t)(kRowBlock + 2 * kColBlock) * stride * 8 + 3 * 8;
+}
+
+// Work list of one shard: the shard owns the kShardRows-row groups g = shard, shard + n_shards,
+// ... (cyclic, so the triangular pair area is balanced); a row block of `block_rows` rows
+// (block_rows divides kShardRows) belongs to the group it lies in.  An item is `chunk_blocks`
+// consecutive column blocks starting at the row block's own index.
+static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_rows, uint32_t chunk_blocks,
+                            uint32_t shard, uint32_t n_shards, cudaStream_t stream, KernelParams &p) {
+    const uint32_t nrb = (uint32_t)((n + block_rows - 1) / block_rows);
+    const uint32_t per_group = kShardRows / block_rows;
+    std::vector<uint32_t> local;
+    std::vector<uint64_t> prefix(1, 0);
+    for (uint32_t rb = 0; rb < nrb; rb++) {
+        if ((rb / per_group) % n_shards != shard) continue;
+        local.push_back(rb);
+        prefix.push_back(prefix.back() + (nrb - rb + chunk_blocks - 1) / chunk_blocks);
+    }
+    p.n_row_blocks = nrb;
+    p.n_local_rb = (uint32_t)local.size();
+    if (local.empty()) return 0;
+    if (ws_ensure(ws.d_local_rb, ws.cap_local_rb, local.size())) return 2;
+    if (ws_ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;
+    if (!ws.d_work_counter) GB_CUDA(cudaMalloc(&ws.d_work_counter, sizeof(unsigned long long)));
+    // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may die
+    GB_CUDA(cudaMemcpyAsync(ws.d_local_rb, local.data(), local.size() * 4, cudaMemcpyHostToDevice, stream));
+    GB_CUDA(cudaMemcpyAsync(ws.d_item_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, stream));
+    GB_CUDA(cudaMemsetAsync(ws.d_work_counter, 0, sizeof(unsigned long long), stream));
+    p.local_rb = ws.d_local_rb; p.item_prefix = ws.d_item_prefix; p.work_counter = ws.d_work_counter;
+    return 0;
 }
 
 int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
                       size_t n, size_t stride, int k, float min_ani, uint32_t shard,
                       uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
                       size_t cand_cap, unsigned long long *d_n_cand) {
-    (void)mode;
     if (n_shards == 0 || shard >= n_shards) { set_error("prefilter: bad shard"); return 3; }
     if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return 3; }
     if (n >= 0x7FFFFFFFull) { set_error("prefilter: n too large"); return 3; }
+    if (stride >= (1ull << 30)) { set_error("prefilter: stride too large"); return 3; }
+    if (mode != 0 && mode != 1) { set_error("prefilter: mode must be 0 or 1"); return 3; }
     GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
     if (n < 2) return 0;
 
-    const uint32_t nrb = (uint32_t)((n + kRowBlock - 1) / kRowBlock);
-    std::vector<uint64_t> prefix;
-    prefix.push_back(0);
-    for (uint32_t rb = shard; rb < nrb; rb += n_shards) {
-        uint32_t chunks = (nrb - rb + kColChunk - 1) / kColChunk;
-        prefix.push_back(prefix.back() + chunks);
+    if (!ws.th_valid || ws.th_s != (uint32_t)stride || ws.th_k != k || ws.th_min_ani != min_ani) {
+        PrefilterThresholds th = make_thresholds((uint32_t)stride, k, min_ani);
+        if (ws_ensure(ws.d_cmin_by_tmin, ws.cap_tmin, th.cmin_by_tmin.size())) return 2;
+        if (ws_ensure(ws.d_cmin_by_total, ws.cap_total, th.cmin_by_total.size())) return 2;
+        GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_tmin, th.cmin_by_tmin.data(), th.cmin_by_tmin.size() * 4,
+                                cudaMemcpyHostToDevice, stream));
+        GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_total, th.cmin_by_total.data(), th.cmin_by_total.size() * 4,
+                                cudaMemcpyHostToDevice, stream));
+        ws.th_s = (uint32_t)stride; ws.th_k = k; ws.th_min_ani = min_ani; ws.th_valid = true;
     }
-    const uint32_t n_local = (uint32_t)prefix.size() - 1;
-    if (n_local == 0) return 0;
 
-    PrefilterThresholds th = make_thresholds((uint32_t)stride, k, min_ani);
-    if (ensure(ws.d_cmin_by_tmin, ws.cap_tmin, th.cmin_by_tmin.size())) return 2;
-    if (ensure(ws.d_cmin_by_total, ws.cap_total, th.cmin_by_total.size())) return 2;
-    if (ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;
-    if (!ws.d_work_counter) GB_CUDA(cudaMalloc(&ws.d_work_counter, sizeof(unsigned long long)));
-    GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_tmin, th.cmin_by_tmin.data(),
-                            th.cmin_by_tmin.size() * 4, cudaMemcpyHostToDevice, stream));
-    GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_total, th.cmin_by_total.data(),
-                            th.cmin_by_total.size() * 4, cudaMemcpyHostToDevice, stream));
-    GB_CUDA(cudaMemcpyAsync(ws.d_item_prefix, prefix.data(), prefix.size() * 8,
-                            cudaMemcpyHostToDevice, stream));
-    GB_CUDA(cudaMemsetAsync(ws.d_work_counter, 0, sizeof(unsigned long long), stream));
-
-    KernelParams p;
+    KernelParams p = {};
     p.hashes = d_hashes; p.counts = d_counts; p.n = (uint32_t)n; p.stride = (uint32_t)stride;
-    p.shard = shard; p.n_shards = n_shards; p.n_row_blocks = nrb; p.n_local_rb = n_local;
-    p.item_prefix = ws.d_item_prefix; p.work_counter = ws.d_work_counter;
     p.cmin_by_tmin = ws.d_cmin_by_tmin; p.cmin_by_total = ws.d_cmin_by_total;
     p.cand = d_cand; p.cand_cap = cand_cap; p.n_cand = d_n_cand;
 
+    ws.ev_recorded = false;
+    if (ws.record(0, stream)) return 2;
+    if (mode == 0 && join_supported(stride)) return join_build_and_launch(ws, p, shard, n_shards, stream);
+
+    if (int rc = upload_work_list(ws, n, kRowBlock, kColChunk, shard, n_shards, stream, p)) return rc;
+    if (p.n_local_rb == 0) return 0;
     int dev = 0, sms = kNumSMsFallback, max_smem = 0;
     GB_CUDA(cudaGetDevice(&dev));
     GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     GB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const uint64_t n_items = prefix.back();
+    // number of items = last prefix entry; recompute on the host side
+    uint64_t n_items = 0;
+    {
+        const uint32_t per_group = kShardRows / kRowBlock;
+        for (uint32_t rb = 0; rb < p.n_row_blocks; rb++)
+            if ((rb / per_group) % n_shards == shard) n_items += (p.n_row_blocks - rb + kColChunk - 1) / kColChunk;
+    }
     const size_t smem = tiled_smem_bytes(stride);
+    if (ws.record(1, stream)) return 2;
     if (smem + 1024 <= (size_t)max_smem) {
         GB_CUDA(cudaFuncSetAttribute(prefilter_tiled_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -362,7 +337,13 @@ int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
         prefilter_generic_kernel<<<std::max(grid, 1u), 256, 0, stream>>>(p);
     }
     GB_LAUNCH_CHECK();
+    if (ws.record(2, stream)) return 2;
     return 0;
+}
+
+int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
+                          cudaStream_t stream, KernelParams &p) {
+    return upload_work_list(ws, n, kShardRows, 1, shard, n_shards, stream, p);
 }
 
 }  // namespace gb200

@@ -1,4 +1,6 @@
-// Stage 1b (K2): all-pairs sketch intersection.  Host-side launch interface.
+// Stage 1b (K2): all-pairs sketch intersection.  Host-side launch interface shared by
+// prefilter.cu (thresholds, pairwise kernels, dispatcher) and prefilter_join.cu (block-list
+// build + block-pair join kernels).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,25 +21,78 @@ struct PrefilterThresholds {
 };
 PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani);
 
+// Sharding granularity in rows == sketches per block list (== GALAH_B200_ROW_BLOCK).
+constexpr int kShardRows = 64;
+// pairwise tiled merge kernel (mode 1)
+constexpr int kRowBlock = 8;    // rows resident per work item (divides kShardRows)
+constexpr int kColBlock = 8;    // columns streamed per TMA stage
+constexpr int kColChunk = 16;   // column blocks per work item
+
 struct PrefilterWorkspace {
+    // thresholds, cached per (s_max, k, min_ani)
     uint32_t *d_cmin_by_tmin = nullptr;
     uint32_t *d_cmin_by_total = nullptr;
+    size_t cap_tmin = 0, cap_total = 0;
+    uint32_t th_s = 0; int th_k = 0; float th_min_ani = -1.f; bool th_valid = false;
+    // work list of the current launch: local row blocks + item prefix + atomic work counter
+    uint32_t *d_local_rb = nullptr;
     uint64_t *d_item_prefix = nullptr;
+    size_t cap_local_rb = 0, cap_prefix = 0;
     unsigned long long *d_work_counter = nullptr;
-    size_t cap_tmin = 0, cap_total = 0, cap_prefix = 0;
+    // block lists (mode 0): two ping-pong buffers of n_blocks * kShardRows * stride entries
+    uint64_t *d_bl_vals[2] = {nullptr, nullptr};
+    uint8_t *d_bl_tags[2] = {nullptr, nullptr};
+    uint32_t *d_bl_len = nullptr;
+    size_t cap_bl = 0, cap_bl_len = 0;
+    // CUDA events on the launch stream: [0] before the build kernels, [1] before the main
+    // (join / pairwise) kernel, [2] after it.  Read back with last_timing() after a sync.
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool ev_recorded = false;
+    int record(int which, cudaStream_t stream);
+    int last_timing(float *build_ms, float *main_ms);
     int release();
 };
 
-constexpr int kRowBlock = 8;    // rows resident per work item (== GALAH_B200_ROW_BLOCK)
-constexpr int kColBlock = 8;    // columns streamed per TMA stage
-constexpr int kColChunk = 16;   // column blocks per work item
+// Shared by both modes: kernel-side view of one launch.
+struct KernelParams {
+    const uint64_t *hashes;
+    const uint32_t *counts;
+    uint32_t n, stride;
+    uint32_t n_row_blocks;        // number of row blocks (of the mode's block size), global
+    uint32_t n_local_rb;          // row blocks owned by this shard
+    const uint32_t *local_rb;     // [n_local_rb] global row-block index of each local one
+    const uint64_t *item_prefix;  // [n_local_rb + 1]
+    unsigned long long *work_counter;
+    const uint32_t *cmin_by_tmin;
+    const uint32_t *cmin_by_total;
+    uint4 *cand;
+    unsigned long long cand_cap;
+    unsigned long long *n_cand;
+    // mode 0 only
+    const uint64_t *bl_vals;
+    const uint8_t *bl_tags;
+    const uint32_t *bl_len;
+    uint64_t bl_cap;  // entries per block list (kShardRows * stride)
+};
 
 // Enqueue the prefilter for one shard.  d_cand: uint4 {i, j, common, total} candidates that
 // survive the conservative integer test; *d_n_cand counts them (may exceed cand_cap, in which
 // case the surplus was dropped and the caller must retry with a larger buffer).
+// mode 0 = block-list join (default), mode 1 = pairwise warp merge of every pair.
 int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
                       size_t n, size_t stride, int k, float min_ani, uint32_t shard,
                       uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
                       size_t cand_cap, unsigned long long *d_n_cand);
+
+// prefilter_join.cu
+int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
+                          cudaStream_t stream);
+bool join_supported(size_t stride);
+// prefilter.cu: work list with one item per (local row block, column block >= it), block = kShardRows
+int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
+                          cudaStream_t stream, KernelParams &p);
+
+template <typename T>
+int ws_ensure(T *&ptr, size_t &cap, size_t need);
 
 }  // namespace gb200

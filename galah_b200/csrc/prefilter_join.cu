@@ -1,0 +1,373 @@
+// Stage 1b (K2), mode 0: all-pairs sketch intersection as a BLOCK-LIST JOIN on sm_100a.
+//
+// Replaces the serial loop at /root/reference/src/finch.rs:75-95 (for every i<j:
+// finch::distance::distance(s_i, s_j, false) -> raw_distance -> common, total).  The reference
+// walks 2s merge steps per pair.  Here the table is cut into blocks of R = kShardRows = 64
+// consecutive sketches and each block is merged ONCE into a single ascending list of
+// (value, row-tag) entries ("block list", R*s entries).  A work item (rb, cb) then merge-
+// intersects block list rb with block list cb: every equal (a, b) adds 1 to
+// cnt[tag(a)][tag(b)], an R x R matrix in shared memory, so ONE merge of 2*R*s entries yields
+// the exact |A n B| of R*R pairs -- 2s/R merge steps and 2*s*9/R bytes per pair.  `total`
+// follows from one rank query per surviving pair (see prefilter.cu, "Exactness notes").
+//
+// Kernels
+//   bl_init_kernel    table rows -> level-0 lists: entry = (value, tag = row % R), padding =
+//                     (2^64-1, 0xFF).  bl_len_kernel: valid entries per block (sum of counts).
+//   bl_merge_kernel   one level of the merge tree (runs of m entries -> runs of 2m), log2(R)
+//                     launches ping-ponging two buffers.  CTA = one 2048-entry output tile:
+//                     merge-path split in global memory, operands staged in shared memory,
+//                     8 sequential merge steps per thread.  Keys are ordered by (value, tag), so
+//                     padding sorts strictly after a genuine 2^64-1 hash and the first bl_len
+//                     entries of a block list are exactly its valid entries.
+//   prefilter_join_kernel  persistent CTAs (3 per SM) pull (rb, cb) items from an atomic
+//                     counter.  The two lists are cut into segments of D = 4608 merged entries
+//                     by merge-path splits (binary searches through L2, all segments of the
+//                     tile in parallel); each segment's A and B slices (values + tags) are
+//                     brought in by four 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//                     complete_tx, SASS UBLKCP); every thread then owns 18 consecutive merge
+//                     steps found by a second merge-path split in shared memory.  Ties are
+//                     ordered B-first, so when a thread takes b every equal a lies at or after
+//                     its A cursor and the (rare) match path scans that run -- at most R long,
+//                     the extra R entries are staged with the segment.  Diagonal items
+//                     (rb == cb) need no merge: equal values are adjacent in the one list.
+//                     After the last segment the CTA scans cnt, applies the conservative
+//                     integer thresholds and appends survivors {i, j, common, total}.
+#include <algorithm>
+
+#include "common.cuh"
+#include "prefilter.cuh"
+#include "prefilter_dev.cuh"
+
+namespace gb200 {
+
+constexpr int kJR = kShardRows;            // sketches per block list
+constexpr int kJLevels = 6;                // log2(kJR)
+static_assert((1 << kJLevels) == kJR, "kShardRows must be a power of two");
+constexpr int kJThreads = 256;
+constexpr int kJE = 18;                    // merge steps per thread per segment (kJE/2 odd: the
+                                           // expected A/B cursors of adjacent threads then fall
+                                           // in different shared-memory bank pairs)
+constexpr int kJD = kJThreads * kJE;       // merged entries per segment
+constexpr int kJCap = kJD + kJR + 96;      // staged entries incl. run overflow + alignment slack
+constexpr int kJCtasPerSm = 3;
+constexpr uint8_t kPadTag = 0xFF;
+constexpr size_t kBlSlack = 1024;          // entries of over-read slack behind the last list
+
+constexpr int kMThreads = 256;
+constexpr int kME = 8;
+constexpr int kMTile = kMThreads * kME;
+
+// ------------------------------------------------------------------------------------------
+// block-list build
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bl_init_kernel(const uint64_t *__restrict__ hashes,
+                                                      const uint32_t *__restrict__ counts, uint32_t n,
+                                                      uint32_t stride, uint64_t total,
+                                                      uint64_t *__restrict__ vals,
+                                                      uint8_t *__restrict__ tags) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
+        const uint64_t row = e / stride;
+        const uint32_t col = (uint32_t)(e - row * stride);
+        const bool valid = row < n && col < min(counts[row], stride);
+        vals[e] = valid ? hashes[e] : kPad;
+        tags[e] = valid ? (uint8_t)(row % kJR) : kPadTag;
+    }
+}
+
+__global__ void __launch_bounds__(256) bl_len_kernel(const uint32_t *__restrict__ counts, uint32_t n,
+                                                     uint32_t stride, uint32_t n_blocks,
+                                                     uint32_t *__restrict__ bl_len) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint32_t sum = 0;
+    for (uint32_t r = b * kJR; r < min(n, (b + 1) * kJR); r++) sum += min(counts[r], stride);
+    bl_len[b] = sum;
+}
+
+__device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8_t tb) {
+    return a < b || (a == b && ta <= tb);
+}
+
+// One level of the merge tree: for every output run o, dst[o*2m .. o*2m+2m) = merge of
+// src[o*2m .. +m) and src[o*2m+m .. +2m) under the (value, tag) order, first run first on ties.
+__global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__restrict__ sv,
+                                                             const uint8_t *__restrict__ st,
+                                                             uint64_t *__restrict__ dv,
+                                                             uint8_t *__restrict__ dt, uint32_t m,
+                                                             uint32_t chunks_per_run) {
+    __shared__ uint64_t s_v[kMTile];
+    __shared__ uint8_t s_t[kMTile];
+    __shared__ uint32_t s_g[2];
+    __shared__ uint32_t s_ts[kMThreads + 1];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t o = blockIdx.x / chunks_per_run, c = blockIdx.x % chunks_per_run;
+    const uint64_t base = (uint64_t)o * 2 * m;
+    const uint64_t *A = sv + base, *B = sv + base + m;
+    const uint8_t *tA = st + base, *tB = st + base + m;
+    const uint32_t d0 = c * kMTile, d1 = min(d0 + (uint32_t)kMTile, 2 * m);
+    if (tid == 0 || tid == 32) {
+        const uint32_t d = tid == 0 ? d0 : d1;
+        uint32_t lo = d > m ? d - m : 0, hi = min(d, m);
+        while (lo < hi) {  // smallest i with !(A[i] <= B[d-1-i])
+            const uint32_t mid = (lo + hi) >> 1;
+            if (key_le(A[mid], tA[mid], B[d - 1 - mid], tB[d - 1 - mid])) lo = mid + 1; else hi = mid;
+        }
+        s_g[tid >> 5] = lo;
+    }
+    __syncthreads();
+    const uint32_t i0 = s_g[0], i1 = s_g[1], j0 = d0 - i0, j1 = d1 - i1;
+    const uint32_t na = i1 - i0, nb = j1 - j0, len = na + nb;
+    for (uint32_t x = tid; x < na; x += kMThreads) { s_v[x] = A[i0 + x]; s_t[x] = tA[i0 + x]; }
+    for (uint32_t x = tid; x < nb; x += kMThreads) { s_v[na + x] = B[j0 + x]; s_t[na + x] = tB[j0 + x]; }
+    __syncthreads();
+    const uint64_t *As = s_v, *Bs = s_v + na;
+    const uint8_t *At = s_t, *Bt = s_t + na;
+    const uint32_t dt0 = min(tid * kME, len), dt1 = min(dt0 + (uint32_t)kME, len);
+    {
+        uint32_t lo = dt0 > nb ? dt0 - nb : 0, hi = min(dt0, na);
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (key_le(As[mid], At[mid], Bs[dt0 - 1 - mid], Bt[dt0 - 1 - mid])) lo = mid + 1; else hi = mid;
+        }
+        s_ts[tid] = lo;
+        if (tid == 0) s_ts[kMThreads] = na;
+    }
+    __syncthreads();
+    uint32_t i = s_ts[tid], j = dt0 - i;
+    const uint32_t ie = s_ts[tid + 1], je = dt1 - ie;
+    uint64_t *ov = dv + base + d0;
+    uint8_t *ot = dt + base + d0;
+    for (uint32_t x = dt0; x < dt1; x++) {
+        bool take_a = j >= je;
+        if (!take_a && i < ie) take_a = key_le(As[i], At[i], Bs[j], Bt[j]);
+        if (take_a) { ov[x] = As[i]; ot[x] = At[i]; i++; }
+        else { ov[x] = Bs[j]; ot[x] = Bt[j]; j++; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// block-pair join
+// ------------------------------------------------------------------------------------------
+// Merge-path split with B first on ties: smallest i in [max(0, d-lb), min(d, la)] such that
+// B[d-i-1] <= A[i].  Then A[i-1] < B[d-i] and B[d-i-1] <= A[i].
+template <typename PtrT>
+__device__ __forceinline__ uint32_t split_bfirst(PtrT A, uint32_t la, PtrT B, uint32_t lb, uint32_t d) {
+    uint32_t lo = d > lb ? d - lb : 0, hi = min(d, la);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (B[d - mid - 1] <= A[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+struct JoinSmem {
+    uint64_t vals[kJCap];
+    uint32_t cnt[kJR * kJR];
+    uint8_t tags[(kJCap + 15) / 16 * 16];
+    uint64_t bar;
+    unsigned long long item;
+    uint32_t split[kJThreads + 1];
+    uint32_t ts[kJThreads + 1];
+    uint32_t na[kJR], nb[kJR];
+};
+
+__global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(const KernelParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    JoinSmem &S = *reinterpret_cast<JoinSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t phase = 0;
+    const uint64_t n_items = p.item_prefix[p.n_local_rb];
+
+    for (;;) {
+        if (tid == 0) S.item = atomicAdd(p.work_counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = S.item;
+        if (item >= n_items) break;
+        uint32_t lo = 0, hi = p.n_local_rb;  // last lr with item_prefix[lr] <= item
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
+        }
+        const uint32_t rb = p.local_rb[lo];
+        const uint32_t cb = rb + (uint32_t)(item - p.item_prefix[lo]);
+        const uint32_t row0 = rb * kJR, col0 = cb * kJR;
+
+        for (uint32_t x = tid; x < kJR * kJR; x += kJThreads) S.cnt[x] = 0;
+        if (tid < kJR) {
+            S.na[tid] = row0 + tid < p.n ? min(p.counts[row0 + tid], p.stride) : 0;
+            S.nb[tid] = col0 + tid < p.n ? min(p.counts[col0 + tid], p.stride) : 0;
+        }
+        const uint32_t la = p.bl_len[rb], lb = p.bl_len[cb];
+        const uint64_t *A = p.bl_vals + (uint64_t)rb * p.bl_cap;
+        const uint8_t *tA = p.bl_tags + (uint64_t)rb * p.bl_cap;
+        const uint64_t *B = p.bl_vals + (uint64_t)cb * p.bl_cap;
+        const uint8_t *tB = p.bl_tags + (uint64_t)cb * p.bl_cap;
+        __syncthreads();
+
+        if (rb == cb) {
+            // ---- diagonal item: equal values are adjacent in the single list
+            for (uint32_t x0 = 0; x0 < la; x0 += kJD) {
+                const uint32_t x1 = min(la, x0 + (uint32_t)kJD);
+                const uint32_t ext = min(la, x1 + (uint32_t)kJR) - x0;
+                const uint32_t a_cnt = (ext + 15u) & ~15u;
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(&S.bar, a_cnt * 9u);
+                    tma_load_1d(S.vals, A + x0, a_cnt * 8u, &S.bar);
+                    tma_load_1d(S.tags, tA + x0, a_cnt, &S.bar);
+                }
+                mbar_wait(&S.bar, phase); phase ^= 1;
+                const uint32_t e0 = tid * kJE, e1 = min(e0 + (uint32_t)kJE, x1 - x0);
+                for (uint32_t x = e0; x < e1; x++) {
+                    const uint64_t v = S.vals[x];
+                    for (uint32_t y = x + 1; y < ext && S.vals[y] == v; y++) {
+                        const uint32_t tx = S.tags[x], ty = S.tags[y];
+                        atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
+                    }
+                }
+                __syncthreads();
+            }
+        } else if (la != 0 && lb != 0) {
+            // ---- off-diagonal item: CTA-wide merge-path intersection of two block lists
+            const uint32_t total = la + lb;
+            const uint32_t nseg = (total + kJD - 1) / kJD;
+            bool done = false;
+            for (uint32_t kb = 0; kb < nseg && !done; kb += kJThreads - 1) {
+                const uint32_t nsb = min((uint32_t)(kJThreads - 1), nseg - kb);
+                if (tid <= nsb) {
+                    const uint32_t d = (uint32_t)min((uint64_t)(kb + tid) * kJD, (uint64_t)total);
+                    S.split[tid] = split_bfirst(A, la, B, lb, d);
+                }
+                __syncthreads();
+                for (uint32_t s = 0; s < nsb; s++) {
+                    const uint32_t d0 = (kb + s) * kJD, d1 = min(d0 + (uint32_t)kJD, total);
+                    const uint32_t i0 = S.split[s], i1 = S.split[s + 1];
+                    const uint32_t j0 = d0 - i0, j1 = d1 - i1;
+                    if (i0 >= la || j0 >= lb) { done = true; break; }  // one list is exhausted
+                    const uint32_t na_s = i1 - i0, nb_s = j1 - j0;
+                    if (nb_s == 0) continue;
+                    const uint32_t a_ext = min(la, i1 + (uint32_t)kJR) - i0;
+                    const uint32_t a_lo = i0 & ~15u, a_off = i0 - a_lo;
+                    const uint32_t a_cnt = (a_off + a_ext + 15u) & ~15u;
+                    const uint32_t b_lo = j0 & ~15u, b_off = j0 - b_lo;
+                    const uint32_t b_cnt = (b_off + nb_s + 1u + 15u) & ~15u;
+                    if (tid == 0) {
+                        mbar_arrive_expect_tx(&S.bar, (a_cnt + b_cnt) * 9u);
+                        tma_load_1d(S.vals, A + a_lo, a_cnt * 8u, &S.bar);
+                        tma_load_1d(S.vals + a_cnt, B + b_lo, b_cnt * 8u, &S.bar);
+                        tma_load_1d(S.tags, tA + a_lo, a_cnt, &S.bar);
+                        tma_load_1d(S.tags + a_cnt, tB + b_lo, b_cnt, &S.bar);
+                    }
+                    mbar_wait(&S.bar, phase); phase ^= 1;
+                    const uint64_t *As = S.vals + a_off, *Bs = S.vals + a_cnt + b_off;
+                    const uint8_t *At = S.tags + a_off, *Bt = S.tags + a_cnt + b_off;
+                    const uint32_t len = na_s + nb_s;
+                    const uint32_t dt0 = min(tid * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
+                    S.ts[tid] = split_bfirst(As, na_s, Bs, nb_s, dt0);
+                    if (tid == 0) S.ts[kJThreads] = na_s;
+                    __syncthreads();
+                    uint32_t i = S.ts[tid], j = dt0 - i;
+                    const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
+                    uint64_t a = As[i], b = Bs[j];
+                    for (uint32_t t = dt0; t < dt1; t++) {
+                        const bool take_b = (i >= ie) || (j < je && b <= a);
+                        if (take_b) {
+                            if (b == a) {  // rare: scan the run of equal values on the A side
+                                const uint32_t tb = Bt[j];
+                                for (uint32_t x = i; x < a_ext && As[x] == b; x++)
+                                    atomicAdd(&S.cnt[(uint32_t)At[x] * kJR + tb], 1u);
+                            }
+                            j++; b = Bs[j];
+                        } else {
+                            i++; a = As[i];
+                        }
+                    }
+                    __syncthreads();  // staged slices free for the next TMA
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+
+        // ---- threshold the count matrix; survivors get their exact `total` and are appended
+        for (uint32_t e = tid; e < kJR * kJR; e += kJThreads) {
+            const uint32_t r = e / kJR, c = e % kJR;
+            const uint32_t gi = row0 + r, gj = col0 + c;
+            if (gi >= p.n || gj >= p.n || gj <= gi) continue;
+            finish_pair(p, gi, gj, p.hashes + (size_t)gi * p.stride, S.na[r],
+                        p.hashes + (size_t)gj * p.stride, S.nb[c], S.cnt[e]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+bool join_supported(size_t stride) { return stride <= (1u << 20); }
+
+int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
+                          cudaStream_t stream) {
+    const uint32_t n = p.n, stride = p.stride;
+    const uint32_t nb = (n + kJR - 1) / kJR;
+    const uint64_t bl_cap = (uint64_t)kJR * stride;
+    const uint64_t total = (uint64_t)nb * bl_cap;
+    if (ws.cap_bl < total + kBlSlack) {
+        for (int x = 0; x < 2; x++) {
+            if (ws.d_bl_vals[x]) GB_CUDA(cudaFree(ws.d_bl_vals[x]));
+            if (ws.d_bl_tags[x]) GB_CUDA(cudaFree(ws.d_bl_tags[x]));
+            ws.d_bl_vals[x] = nullptr; ws.d_bl_tags[x] = nullptr;
+        }
+        ws.cap_bl = 0;
+        for (int x = 0; x < 2; x++) {
+            GB_CUDA(cudaMalloc(&ws.d_bl_vals[x], (total + kBlSlack) * 8));
+            GB_CUDA(cudaMalloc(&ws.d_bl_tags[x], total + kBlSlack));
+            GB_CUDA(cudaMemsetAsync(ws.d_bl_vals[x] + total, 0xFF, kBlSlack * 8, stream));
+            GB_CUDA(cudaMemsetAsync(ws.d_bl_tags[x] + total, 0xFF, kBlSlack, stream));
+        }
+        ws.cap_bl = total + kBlSlack;
+    }
+    if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
+
+    int dev = 0, sms = kNumSMsFallback;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+    {
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 16);
+        bl_init_kernel<<<grid, 256, 0, stream>>>(p.hashes, p.counts, n, stride, total, ws.d_bl_vals[0],
+                                                 ws.d_bl_tags[0]);
+        GB_LAUNCH_CHECK();
+        bl_len_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(p.counts, n, stride, nb, ws.d_bl_len);
+        GB_LAUNCH_CHECK();
+    }
+    int src = 0;
+    for (uint64_t m = stride; m < bl_cap; m *= 2) {
+        const uint32_t chunks = (uint32_t)((2 * m + kMTile - 1) / kMTile);
+        const uint64_t outruns = total / (2 * m);
+        const uint64_t grid = outruns * chunks;
+        if (grid > 0x7FFFFFFFull) { set_error("prefilter: table too large for the merge grid"); return 3; }
+        bl_merge_kernel<<<(uint32_t)grid, kMThreads, 0, stream>>>(ws.d_bl_vals[src], ws.d_bl_tags[src],
+                                                                 ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1],
+                                                                 (uint32_t)m, chunks);
+        GB_LAUNCH_CHECK();
+        src ^= 1;
+    }
+    p.bl_vals = ws.d_bl_vals[src]; p.bl_tags = ws.d_bl_tags[src]; p.bl_len = ws.d_bl_len; p.bl_cap = bl_cap;
+
+    if (int rc = upload_join_work_list(ws, n, shard, n_shards, stream, p)) return rc;
+    if (p.n_local_rb == 0) return 0;
+    uint64_t n_items = 0;
+    for (uint32_t rb = shard; rb < nb; rb += n_shards) n_items += nb - rb;
+    const size_t smem = sizeof(JoinSmem);
+    GB_CUDA(cudaFuncSetAttribute(prefilter_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm);
+    if (ws.record(1, stream)) return 2;
+    prefilter_join_kernel<<<grid, kJThreads, smem, stream>>>(p);
+    GB_LAUNCH_CHECK();
+    if (ws.record(2, stream)) return 2;
+    return 0;
+}
+
+}  // namespace gb200

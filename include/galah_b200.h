@@ -89,7 +89,7 @@ int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t 
  * rb = shard, shard + n_shards, ... (blocks of GALAH_B200_ROW_BLOCK rows), which balances the
  * triangular pair area across shards.  _shard takes host pointers, _device device pointers;
  * result pairs always land on the HOST. */
-#define GALAH_B200_ROW_BLOCK 8
+#define GALAH_B200_ROW_BLOCK 64
 int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, size_t n,
                                size_t stride, uint8_t k, float min_ani, uint32_t shard,
                                uint32_t n_shards, galah_b200_pair_t **out, size_t *n_out);
@@ -98,10 +98,20 @@ int galah_b200_prefilter_device(const uint64_t *d_hashes, const uint32_t *d_coun
                                 uint32_t n_shards, void *stream, galah_b200_pair_t **out,
                                 size_t *n_out);
 
+/* Selects the kernel path of the prefilter entry points above (both are exact and return the
+ * same pair list): 0 = block-list join (default), 1 = pairwise warp merge of every pair.
+ * Returns the previous mode; any other value only queries. */
+int galah_b200_prefilter_mode(int mode);
+
+/* Device time of the most recent prefilter launch, from CUDA events the library records on the
+ * launch stream: build_ms = block-list build kernels (0 in mode 1), main_ms = the join /
+ * pairwise kernel alone.  Blocks until that launch has finished. */
+int galah_b200_prefilter_last_timing(float *build_ms, float *main_ms);
+
 /* Kernel-only timing hook used by bench.py: enqueues the prefilter kernels for one shard on
  * `stream` and leaves the candidate list on the device (d_cand, capacity cand_cap entries of
  * 4 x uint32 {i, j, common, total}; d_n_cand is a device uint64 counter).  No host sync.
- * mode: 0 = default (screen + exact merge), 1 = exhaustive exact merge of every pair. */
+ * mode: 0 = block-list join, 1 = pairwise warp merge of every pair. */
 int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                                  size_t stride, uint8_t k, float min_ani, uint32_t shard,
                                  uint32_t n_shards, int mode, void *stream, uint32_t *d_cand,

@@ -8,6 +8,14 @@ from util import PAD, assert_pairs_equal, random_family_table
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["join", "pairwise"], autouse=True)
+def kernel_mode(gb, request):
+    """Every parity test runs through both exact kernel paths of the C ABI."""
+    prev = gb.prefilter_mode(request.param)
+    yield request.param
+    gb.prefilter_mode(prev)
+
+
 def test_golden_fixture_pair_list(gb, golden):
     """Sketches of the reference's own test genomes -> identical pair list (i, j, common, total,
     ani bits), including the reference-pinned (502, 1000, 0.9808188) row."""
@@ -17,7 +25,8 @@ def test_golden_fixture_pair_list(gb, golden):
     assert got[0]["ani"] == np.float32(0.9808188)
 
 
-@pytest.mark.parametrize("n,s,seed", [(2, 1000, 0), (9, 1000, 1), (64, 1000, 2), (301, 1000, 3), (130, 10, 4), (77, 500, 5)])
+@pytest.mark.parametrize("n,s,seed", [(2, 1000, 0), (9, 1000, 1), (64, 1000, 2), (65, 1000, 6), (301, 1000, 3),
+                                      (130, 10, 4), (77, 500, 5), (200, 2, 8), (129, 4608, 9)])
 def test_random_families_match_oracle(gb, n, s, seed):
     rng = np.random.default_rng(seed)
     table, counts = random_family_table(n, s, rng)
@@ -60,6 +69,54 @@ def test_genuine_max_hash_value(gb):
     for g in (0, 1, 2):
         table[g, counts[g] - 1] = PAD  # genuine element (still sorted, still distinct)
     assert_pairs_equal(gb.prefilter(table, counts, 21, 0.5), oracle.prefilter(table, counts, 21, 0.5))
+
+
+def test_whole_clade_identical(gb):
+    """Worst case for the join's match path: 150 identical sketches (every value matches in every
+    block pair) next to 50 unrelated ones."""
+    rng = np.random.default_rng(31)
+    table, counts = random_family_table(200, 1000, rng)
+    table[:150] = table[0]; counts[:150] = counts[0]
+    exp = oracle.prefilter(table, counts, 21, 0.9)
+    assert_pairs_equal(gb.prefilter(table, counts, 21, 0.9), exp)
+    assert len(exp) >= 150 * 149 // 2
+
+
+def test_duplicate_heavy_small_universe(gb):
+    """Values drawn from a tiny universe: long equal runs inside and across block lists."""
+    rng = np.random.default_rng(37)
+    n, s = 260, 64
+    table = np.full((n, s), PAD, np.uint64)
+    counts = np.zeros(n, np.uint32)
+    for g in range(n):
+        m = int(rng.integers(0, s + 1))
+        v = np.sort(rng.choice(96, size=m, replace=False)).astype(np.uint64)
+        table[g, :m] = v; counts[g] = m
+    for min_ani in (0.9, 0.97):
+        assert_pairs_equal(gb.prefilter(table, counts, 21, min_ani), oracle.prefilter(table, counts, 21, min_ani))
+
+
+def test_modes_agree_on_candidates(gb):
+    """The two kernel paths emit the same integer candidate set {i, j, common, total}."""
+    import torch
+    rng = np.random.default_rng(41)
+    n, s = 700, 1000
+    table, counts = random_family_table(n, s, rng, ragged=True)
+    d_t = torch.from_numpy(table.view(np.int64)).cuda()
+    d_c = torch.from_numpy(counts.view(np.int32)).cuda()
+    cap = 1 << 20
+    out = []
+    for mode in (0, 1):
+        d_cand = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+        d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        gb.prefilter_enqueue(d_t.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, 0, 1, mode,
+                             torch.cuda.current_stream().cuda_stream, d_cand.data_ptr(), cap, d_n.data_ptr())
+        torch.cuda.synchronize()
+        m = int(d_n.item())
+        c = d_cand[:m].cpu().numpy().view(np.uint32)
+        out.append(c[np.lexsort((c[:, 1], c[:, 0]))])
+    assert out[0].shape == out[1].shape and np.array_equal(out[0], out[1])
 
 
 def test_large_sketches_use_generic_kernel(gb):
