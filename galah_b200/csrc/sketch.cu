@@ -14,18 +14,27 @@
 // (1 bit/base).  Record breaks and non-ACGT bases are invalid bases.  Genome g covers bases
 // [base_off[g], base_off[g+1]); base_off[g] % 128 == 0.  Buffers carry >= 16 bytes of padding.
 //
-// Kernel: persistent CTAs take genomes from an atomic counter.  Every thread extracts a k-mer
-// straight from the packed stream (no rolling state, so no warm-up and no divergence):
-//     V = 2k bits at bit offset 2p           (LSB-first forward k-mer)
-//     F = reverse-2-bit-groups(V)            (MSB-first forward integer)
-//     R = ~V & mask                          (MSB-first reverse-complement integer)
-//     canonical LSB-first word W = F < R ? V : ~F & mask
-// W is expanded to ASCII 8 bases at a time (bit spread + PRMT against the constant "ACGT"),
-// hashed, and hashes <= a per-genome threshold T go into a shared-memory open-addressing set
-// (atomicCAS, duplicates collapse).  T starts at ~1.3 s/n_kmers of the hash range; if the set
-// ends with fewer than s distinct values (or overflows) T is bisected and the genome is
-// re-scanned, so the result is exact for any input.  The set is then bitonic-sorted in place
-// (empty slots hold 2^64-1 and sink to the end) and the first s values are written out.
+// Kernels (one launch sequence per batch of genomes, no host round trip in between):
+//   sketch_plan_kernel    per genome: number of CHUNK-position chunks, hash threshold T_g set so that
+//                         about 1.3 s + 64 of the genome's k-mers hash below it, counters zeroed;
+//                         exclusive scan -> chunk_off.  sketch_items_kernel: chunk -> genome table.
+//   sketch_scan_kernel    one CTA per chunk (so the grid is as wide as the batch is long, not as
+//                         wide as it has genomes).  Every thread extracts a k-mer straight from
+//                         the packed stream (no rolling state, so no warm-up and no divergence):
+//                             V = 2k bits at bit offset 2p           (LSB-first forward k-mer)
+//                             F = reverse-2-bit-groups(V)            (MSB-first forward integer)
+//                             R = ~V & mask                          (MSB-first reverse-complement)
+//                             canonical LSB-first word W = F < R ? V : ~F & mask
+//                         W is expanded to ASCII 8 bases at a time (bit spread + PRMT against the
+//                         constant "ACGT"), hashed, and hashes <= T_g are appended to the genome's
+//                         candidate buffer (one global atomic per candidate, ~1.4 k per genome).
+//   sketch_select_kernel  one CTA per genome: candidates -> shared memory, bitonic sort, adjacent
+//                         de-duplication, first s distinct written out.  A genome whose
+//                         candidates overflowed or held fewer than s distinct values (repeats, N
+//                         runs, tiny T) is put on a redo list instead.
+//   sketch_kernel         the exact single-CTA-per-genome kernel (threshold bisection + shared
+//                         hash set, re-scans until it holds >= s distinct values) runs over the
+//                         redo list only, so the result is exact for any input.
 #include "sketch.cuh"
 
 #include <algorithm>
@@ -47,6 +56,8 @@ struct SketchKernelParams {
     uint32_t out_stride;
     uint32_t cap;  // hash-set slots (power of two)
     unsigned long long *work_counter;
+    const uint32_t *redo_list;  // if non-null: genomes to process (count in *redo_n)
+    const uint32_t *redo_n;
 };
 
 __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
@@ -143,8 +154,11 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const SketchKern
     for (;;) {
         if (tid == 0) s_genome = atomicAdd(p.work_counter, 1ull);
         __syncthreads();
-        const unsigned long long g = s_genome;
-        if (g >= p.n) break;
+        unsigned long long g = s_genome;
+        if (p.redo_list) {
+            if (g >= *p.redo_n) break;
+            g = p.redo_list[g];
+        } else if (g >= p.n) break;
         const uint64_t b0 = p.base_off[g], b1 = p.base_off[g + 1];
         const uint64_t len = b1 - b0;
         const uint64_t npos = len >= (uint64_t)k ? len - k + 1 : 0;
@@ -224,6 +238,170 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const SketchKern
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// chunked pipeline: plan -> scan -> select (-> exact kernel over the redo list)
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kChunk = 16384;  // k-mer start positions per scan CTA
+
+struct ChunkParams {
+    const uint32_t *seq2;
+    const uint32_t *valid;
+    const uint64_t *base_off;
+    uint32_t n;
+    int k;
+    uint32_t s;
+    uint64_t seed;
+    uint32_t cap;            // candidate slots per genome (power of two)
+    uint64_t *chunk_off;     // [n + 1]
+    uint64_t *thr;           // [n]
+    uint32_t *cand_n;        // [n]
+    uint32_t *has_max;       // [n]
+    uint32_t *item_genome;   // [max_items]
+    uint64_t max_items;
+    uint64_t *cand;          // [n * cap]
+    uint32_t *redo_list;     // [n]
+    uint32_t *redo_n;        // [1]
+    uint64_t *hashes;
+    uint32_t *counts;
+    uint32_t out_stride;
+};
+
+__global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) {
+    __shared__ uint64_t s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (p.n + 1023) / 1024;
+    const uint32_t g0 = min(tid * per, p.n), g1 = min(g0 + per, p.n);
+    uint64_t sum = 0;
+    for (uint32_t g = g0; g < g1; g++) {
+        const uint64_t len = p.base_off[g + 1] - p.base_off[g];
+        const uint64_t npos = len >= (uint64_t)p.k ? len - p.k + 1 : 0;
+        sum += (npos + kChunk - 1) / kChunk;
+        uint64_t T = kPad;
+        const double want = 1.3 * (double)p.s + 64.0;
+        if ((double)npos > want) T = (uint64_t)(18446744073709551616.0 * (want / (double)npos));
+        p.thr[g] = T;
+        p.cand_n[g] = 0;
+        p.has_max[g] = 0;
+    }
+    s_part[tid] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele scan
+        const uint64_t v = tid >= off ? s_part[tid - off] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint64_t run = s_part[tid] - sum;  // exclusive
+    for (uint32_t g = g0; g < g1; g++) {
+        p.chunk_off[g] = run;
+        const uint64_t len = p.base_off[g + 1] - p.base_off[g];
+        const uint64_t npos = len >= (uint64_t)p.k ? len - p.k + 1 : 0;
+        run += (npos + kChunk - 1) / kChunk;
+    }
+    if (tid == 1023) p.chunk_off[p.n] = s_part[1023];
+    if (tid == 0) *p.redo_n = 0;
+}
+
+__global__ void __launch_bounds__(256) sketch_items_kernel(const ChunkParams p) {
+    // one warp per genome writes that genome's index into its item slots
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.n) return;
+    const uint64_t c0 = p.chunk_off[warp], c1 = min(p.chunk_off[warp + 1], p.max_items);
+    for (uint64_t c = c0 + lane; c < c1; c += 32) p.item_genome[c] = warp;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256) sketch_scan_kernel(const ChunkParams p) {
+    const uint64_t item = blockIdx.x;
+    if (item >= p.chunk_off[p.n]) return;
+    const uint32_t g = p.item_genome[item];
+    const uint64_t b0 = p.base_off[g], len = p.base_off[g + 1] - b0;
+    const int k = KT ? KT : p.k;
+    const uint64_t npos = len - k + 1;  // >= 1: genomes without k-mers have no items
+    const uint64_t q0 = (item - p.chunk_off[g]) * kChunk;
+    const uint64_t q1 = min(q0 + (uint64_t)kChunk, npos);
+    const uint64_t T = p.thr[g];
+    uint64_t *cand = p.cand + (size_t)g * p.cap;
+    for (uint64_t q = q0 + threadIdx.x; q < q1; q += 256) {
+        uint64_t h;
+        if (!kmer_hash<KT>(p.seq2, p.valid, b0 + q, p.k, p.seed, h)) continue;
+        if (h > T) continue;
+        if (h == kPad) { p.has_max[g] = 1; continue; }
+        const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
+        if (slot < p.cap) cand[slot] = h;
+    }
+}
+
+// One CTA per genome.  Dynamic shared memory: cap uint64.
+__global__ void __launch_bounds__(256) sketch_select_kernel(const ChunkParams p) {
+    extern __shared__ __align__(16) uint64_t sel[];
+    __shared__ uint32_t s_warp_sum[8];
+    const uint32_t g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t got = p.cand_n[g];
+    const bool overflow = got > p.cap;
+    const uint32_t m = min(got, p.cap);
+    // sort only the power of two that covers m
+    uint32_t cap2 = 256;
+    while (cap2 < m) cap2 <<= 1;
+    const uint64_t *cand = p.cand + (size_t)g * p.cap;
+    for (uint32_t x = tid; x < cap2; x += 256) sel[x] = x < m ? cand[x] : kPad;
+    __syncthreads();
+    for (uint32_t size = 2; size <= cap2; size <<= 1) {
+        for (uint32_t str = size >> 1; str > 0; str >>= 1) {
+            for (uint32_t x = tid; x < (cap2 >> 1); x += 256) {
+                const uint32_t lo = 2 * x - (x & (str - 1));
+                const uint32_t hi = lo + str;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = sel[lo], b = sel[hi];
+                if ((a > b) == up) { sel[lo] = b; sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // adjacent de-duplication: thread t owns the contiguous slice [t*per, (t+1)*per)
+    const uint32_t per = cap2 / 256;
+    const uint32_t x0 = tid * per;
+    uint32_t mine = 0;
+    for (uint32_t x = x0; x < x0 + per; x++) {
+        const uint64_t v = sel[x];
+        mine += (v != kPad && (x == 0 || sel[x - 1] != v)) ? 1u : 0u;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, distinct = 0;
+    for (uint32_t w = 0; w < 8; w++) {
+        if (w < warp) base += s_warp_sum[w];
+        distinct += s_warp_sum[w];
+    }
+    const bool has_max = p.has_max[g] != 0;
+    const uint32_t total = distinct + (has_max ? 1u : 0u);
+    const bool complete = !overflow && (total >= p.s || p.thr[g] == kPad);
+    if (!complete) {
+        if (tid == 0) p.redo_list[atomicAdd(p.redo_n, 1u)] = g;
+        return;
+    }
+    const uint32_t out_n = min(total, p.s);
+    uint64_t *out = p.hashes + (size_t)g * p.out_stride;
+    uint32_t pos = base + incl - mine;
+    // distinct values first (each thread writes the ones it owns) ...
+    for (uint32_t x = x0; x < x0 + per; x++) {
+        const uint64_t v = sel[x];
+        if (v != kPad && (x == 0 || sel[x - 1] != v)) {
+            if (pos < out_n) out[pos] = v;
+            pos++;
+        }
+    }
+    // ... then padding (a genuine 2^64-1 hash, if any, is the largest value and equals the pad)
+    for (uint32_t x = min(distinct, out_n) + tid; x < p.out_stride; x += 256) out[x] = kPad;
+    if (tid == 0) p.counts[g] = out_n;
+}
+
 uint32_t sketch_set_capacity(uint32_t s) {
     // expected candidates 1.3 s + 64; inserts stop at cap / 2 (+ one in flight per thread)
     uint32_t need = (uint32_t)(2.5 * (1.3 * s + 64.0));
@@ -232,12 +410,23 @@ uint32_t sketch_set_capacity(uint32_t s) {
     return cap;
 }
 
+template <typename T>
+static int sk_ensure(T *&ptr, size_t &cap, size_t need) {
+    if (need <= cap) return 0;
+    if (ptr) GB_CUDA(cudaFree(ptr));
+    ptr = nullptr; cap = 0;
+    GB_CUDA(cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return 0;
+}
+
 int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
                    uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream) {
     if (k < 1 || k > 32) { set_error("sketch: k must be in 1..32"); return 3; }
     if (s == 0) { set_error("sketch: s must be > 0"); return 3; }
     if (out_stride < s) { set_error("sketch: out_stride < s"); return 3; }
+    if (n >= 0x7FFFFFFFull) { set_error("sketch: too many genomes in one batch"); return 3; }
     if (n == 0) return 0;
     const uint32_t cap = sketch_set_capacity(s);
     const size_t smem = (size_t)cap * 8;
@@ -249,12 +438,52 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
         set_error("sketch: num_kmers too large for the shared-memory candidate set");
         return 5;
     }
+    // the scan grid is sized from the batch length: one 8-byte read of base_off[n]
+    uint64_t total_bases = 0;
+    GB_CUDA(cudaMemcpyAsync(&total_bases, d_base_off + n, 8, cudaMemcpyDeviceToHost, stream));
+    GB_CUDA(cudaStreamSynchronize(stream));
+    uint64_t first_base = 0;
+    GB_CUDA(cudaMemcpyAsync(&first_base, d_base_off, 8, cudaMemcpyDeviceToHost, stream));
+    GB_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t max_items = (total_bases - first_base) / kChunk + n;
+    if (max_items > 0x7FFFFFFFull) { set_error("sketch: batch too long for one launch"); return 3; }
+
     if (!ws.d_work_counter) GB_CUDA(cudaMalloc(&ws.d_work_counter, sizeof(unsigned long long)));
+    if (!ws.d_redo_n) GB_CUDA(cudaMalloc(&ws.d_redo_n, sizeof(uint32_t)));
+    if (sk_ensure(ws.d_chunk_off, ws.cap_chunk_off, n + 1) || sk_ensure(ws.d_thr, ws.cap_thr, n) ||
+        sk_ensure(ws.d_cand_n, ws.cap_cand_n, n) || sk_ensure(ws.d_has_max, ws.cap_has_max, n) ||
+        sk_ensure(ws.d_redo_list, ws.cap_redo, n) ||
+        sk_ensure(ws.d_item_genome, ws.cap_items, (size_t)max_items + 1) ||
+        sk_ensure(ws.d_cand, ws.cap_cand, n * (size_t)cap))
+        return 2;
     GB_CUDA(cudaMemsetAsync(ws.d_work_counter, 0, sizeof(unsigned long long), stream));
+
+    ChunkParams c;
+    c.seq2 = d_seq2; c.valid = d_valid; c.base_off = d_base_off; c.n = (uint32_t)n; c.k = k; c.s = s;
+    c.seed = seed; c.cap = cap; c.chunk_off = ws.d_chunk_off; c.thr = ws.d_thr; c.cand_n = ws.d_cand_n;
+    c.has_max = ws.d_has_max; c.item_genome = ws.d_item_genome; c.max_items = max_items;
+    c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
+    c.hashes = d_hashes; c.counts = d_counts; c.out_stride = (uint32_t)out_stride;
+
+    sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
+    GB_LAUNCH_CHECK();
+    sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
+    GB_LAUNCH_CHECK();
+    if (max_items > 0) {
+        if (k == 21) sketch_scan_kernel<21><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else sketch_scan_kernel<0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        GB_LAUNCH_CHECK();
+    }
+    GB_CUDA(cudaFuncSetAttribute(sketch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sketch_select_kernel<<<(uint32_t)n, 256, smem, stream>>>(c);
+    GB_LAUNCH_CHECK();
+
+    // exact kernel over the redo list (normally empty: the CTAs read *redo_n == 0 and leave)
     SketchKernelParams p;
     p.seq2 = d_seq2; p.valid = d_valid; p.base_off = d_base_off; p.n = (uint32_t)n; p.k = k;
     p.s = s; p.seed = seed; p.hashes = d_hashes; p.counts = d_counts;
     p.out_stride = (uint32_t)out_stride; p.cap = cap; p.work_counter = ws.d_work_counter;
+    p.redo_list = ws.d_redo_list; p.redo_n = ws.d_redo_n;
     const int ctas_per_sm = std::max(1, std::min(4, (int)((size_t)max_smem / (smem + 2048))));
     const uint32_t grid = (uint32_t)std::min<size_t>(n, (size_t)sms * ctas_per_sm);
     if (k == 21) {
@@ -271,8 +500,10 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
 }
 
 int SketchWorkspace::release() {
-    cudaFree(d_work_counter);
-    d_work_counter = nullptr;
+    cudaFree(d_work_counter); cudaFree(d_redo_n); cudaFree(d_chunk_off); cudaFree(d_thr);
+    cudaFree(d_cand_n); cudaFree(d_has_max); cudaFree(d_redo_list); cudaFree(d_item_genome);
+    cudaFree(d_cand);
+    *this = SketchWorkspace();
     return 0;
 }
 

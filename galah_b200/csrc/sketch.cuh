@@ -7,6 +7,14 @@ namespace gb200 {
 
 struct SketchWorkspace {
     unsigned long long *d_work_counter = nullptr;
+    uint32_t *d_redo_n = nullptr;
+    uint64_t *d_chunk_off = nullptr; size_t cap_chunk_off = 0;
+    uint64_t *d_thr = nullptr; size_t cap_thr = 0;
+    uint32_t *d_cand_n = nullptr; size_t cap_cand_n = 0;
+    uint32_t *d_has_max = nullptr; size_t cap_has_max = 0;
+    uint32_t *d_redo_list = nullptr; size_t cap_redo = 0;
+    uint32_t *d_item_genome = nullptr; size_t cap_items = 0;
+    uint64_t *d_cand = nullptr; size_t cap_cand = 0;
     int release();
 };
 
