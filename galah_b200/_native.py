@@ -22,6 +22,15 @@ class Pair(ctypes.Structure):
                 ("total", ctypes.c_uint32), ("ani", ctypes.c_float)]
 
 
+class Clusters(ctypes.Structure):
+    _fields_ = [("members", ctypes.POINTER(ctypes.c_uint32)), ("offsets", ctypes.POINTER(ctypes.c_uint64)),
+                ("n_clusters", ctypes.c_size_t), ("ani_calls", ctypes.c_uint64),
+                ("n_preclusters", ctypes.c_uint32), ("largest_precluster", ctypes.c_uint32)]
+
+
+ANI_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                          ctypes.POINTER(ctypes.c_float))
+
 _lib = None
 
 u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -60,6 +69,10 @@ _SIGNATURES = {
                                                     ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "galah_b200_finch_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32,
                                                   ctypes.c_uint8, ctypes.c_int, pairpp, sizep]),
+    "galah_b200_cluster_from_distances": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p,
+                                                         ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
+                                                         ANI_FN, vp, ctypes.POINTER(Clusters)]),
+    "galah_b200_clusters_free": (None, [ctypes.POINTER(Clusters)]),
     "galah_b200_synth_packed_device": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
                                                       ctypes.c_uint64, vp, vp, vp, vp]),
 }

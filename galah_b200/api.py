@@ -139,6 +139,42 @@ def finch_distances(paths, min_ani=0.9, num_kmers=1000, kmer_length=21, threads=
     return _take_pairs(out, n_out)
 
 
+def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, skip_clusterer=False):
+    """The clustering engine behind galah::clusterer::cluster() (reference src/clusterer.rs:56-151)
+    on a precluster hit list.  `hits`: PAIR_DTYPE records (i, j, ani).  `calculate_ani(rep, genome)`
+    returns a float or None (ClusterDistanceFinder::calculate_ani on indices).  Returns
+    (clusters, info): clusters as lists of genome indices, representative first."""
+    hits = np.ascontiguousarray(hits, PAIR_DTYPE)
+    calls = {"exc": None}
+
+    def _cb(_ctx, rep, genome, out):
+        try:
+            v = calculate_ani(int(rep), int(genome))
+        except BaseException as e:  # never unwind through C
+            calls["exc"] = e
+            return 0
+        if v is None:
+            return 0
+        out[0] = float(v)
+        return 1
+
+    cb = _native.ANI_FN(_cb) if calculate_ani is not None else _native.ANI_FN()
+    res = _native.Clusters()
+    check(lib().galah_b200_cluster_from_distances(int(n_genomes), hits.ctypes.data, len(hits),
+                                                  int(bool(skip_clusterer)), ctypes.c_float(ani_threshold),
+                                                  cb, None, ctypes.byref(res)))
+    try:
+        if calls["exc"] is not None:
+            raise calls["exc"]
+        off = [res.offsets[x] for x in range(res.n_clusters + 1)]
+        clusters = [[int(res.members[y]) for y in range(off[x], off[x + 1])] for x in range(res.n_clusters)]
+        info = {"ani_calls": int(res.ani_calls), "n_preclusters": int(res.n_preclusters),
+                "largest_precluster": int(res.largest_precluster)}
+    finally:
+        lib().galah_b200_clusters_free(ctypes.byref(res))
+    return clusters, info
+
+
 def synth_layout(n, length):
     """Sizes (in uint32 / uint64 elements) of the packed buffers for n synthetic genomes."""
     padded = (length + 127) // 128 * 128

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host/cluster_engine.hpp"
 #include "host/fasta.hpp"
 #include "prefilter.cuh"
 #include "sketch.cuh"
@@ -348,6 +349,43 @@ int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani
     int rc = galah_b200_sketch_files(paths, n, kmer_length, s, 0, host_threads, hashes.data(), counts.data());
     if (rc) return rc;
     return galah_b200_prefilter(hashes.data(), counts.data(), n, s, kmer_length, min_ani, out, n_out);
+}
+
+int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                      int skip_clusterer, float ani_threshold,
+                                      galah_b200_ani_fn calculate_ani, void *ctx,
+                                      galah_b200_clusters_t *out) {
+    if (!out) { set_error("cluster: out is NULL"); return GALAH_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    std::vector<PreclusterHit> h(n_hits);
+    for (size_t x = 0; x < n_hits; x++) h[x] = PreclusterHit{hits[x].i, hits[x].j, hits[x].ani};
+    AniFn fn;
+    if (calculate_ani)
+        fn = [calculate_ani, ctx](uint32_t rep, uint32_t genome, float *ani) {
+            return calculate_ani(ctx, rep, genome, ani) != 0;
+        };
+    ClusterResult res;
+    std::string err;
+    if (cluster_from_hits(n_genomes, h.data(), n_hits, skip_clusterer != 0, ani_threshold, fn, res, err)) {
+        set_error("cluster: " + err);
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    out->n_clusters = res.offsets.size() - 1;
+    out->members = (uint32_t *)malloc(std::max<size_t>(res.members.size(), 1) * sizeof(uint32_t));
+    out->offsets = (uint64_t *)malloc(res.offsets.size() * sizeof(uint64_t));
+    if (!out->members || !out->offsets) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!res.members.empty()) memcpy(out->members, res.members.data(), res.members.size() * sizeof(uint32_t));
+    memcpy(out->offsets, res.offsets.data(), res.offsets.size() * sizeof(uint64_t));
+    out->ani_calls = res.ani_calls;
+    out->n_preclusters = res.n_preclusters;
+    out->largest_precluster = res.largest_precluster;
+    return 0;
+}
+
+void galah_b200_clusters_free(galah_b200_clusters_t *c) {
+    if (!c) return;
+    free(c->members); free(c->offsets);
+    memset(c, 0, sizeof(*c));
 }
 
 int galah_b200_synth_packed_device(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,

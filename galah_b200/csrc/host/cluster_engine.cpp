@@ -1,0 +1,214 @@
+// Greedy representative selection + membership assignment of galah::clusterer::cluster()
+// (/root/reference/src/clusterer.rs:14-152), restated over a sparse pair list.
+//
+// What is kept bit-for-bit from the reference (at --threads 1, where its output order is a
+// function of the input):
+//   * partition_sketches (:452-487): single-linkage components of the precluster hits;
+//     `sets()` ordered by smallest member, members ascending (:67-76); preclusters ordered by
+//     size, largest first (:79; ties keep smallest-member order, as Rust's sort_unstable does
+//     for the <= 20-element insertion-sort case -- beyond that the reference's own order is
+//     unspecified).
+//   * find_precluster_cluster_representatives (:182-259): genomes in ascending index order;
+//     candidates = existing representatives with a precluster hit, sorted by precluster ANI
+//     ASCENDING (:200); calculate_ani in that order until one value reaches the threshold
+//     (find_any on one thread, :276-296); genome i is a representative iff no computed ANI
+//     satisfies `ani >= threshold` in f32 (:241).  Only Some(ani) values enter the cache (:236-239).
+//   * find_precluster_cluster_memberships (:350-449): for every non-representative, ANI is
+//     computed against every representative with a precluster hit that is not cached yet (no
+//     early stop, None results are cached too, :398-405); the genome joins the representative
+//     with the highest ANI, strict `>` so ties go to the lowest representative index (:436-442);
+//     no representative with an ANI -> the reference panics on `best_rep.unwrap()` (:444).
+//   * skip_clusterer (:32-44, :209-214, :253-254): ANI values are read from the precluster
+//     cache and the whole precluster cache is handed to the membership stage.
+//
+// What is different by design: the reference probes a BTreeMap for all N(N-1)/2 pairs in
+// partition_sketches and all m(m-1)/2 pairs per precluster in transform_ids
+// (src/sorted_pair_genome_distance_cache.rs:47-58); here both are driven by the hit list
+// (CSR adjacency + union-find), O(hits) instead of O(N^2) -- SURVEY.md 8f item 1.
+#include "cluster_engine.hpp"
+
+#include <algorithm>
+#include <numeric>
+#include <unordered_map>
+
+namespace gb200 {
+
+namespace {
+
+struct Dsu {
+    std::vector<uint32_t> parent;
+    explicit Dsu(size_t n) : parent(n) { std::iota(parent.begin(), parent.end(), 0u); }
+    uint32_t find(uint32_t x) {
+        while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+        return x;
+    }
+    void join(uint32_t a, uint32_t b) {
+        a = find(a); b = find(b);
+        if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+};
+
+struct Adjacency {  // CSR over both directions, neighbours ascending
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> nbr;
+    std::vector<float> ani;
+    // index of (a, b) in nbr/ani, or -1
+    int64_t find(uint32_t a, uint32_t b) const {
+        const uint32_t *lo = nbr.data() + off[a], *hi = nbr.data() + off[a + 1];
+        const uint32_t *it = std::lower_bound(lo, hi, b);
+        return (it != hi && *it == b) ? (int64_t)(it - nbr.data()) : -1;
+    }
+};
+
+inline uint64_t pair_key(uint32_t a, uint32_t b) {
+    return a < b ? ((uint64_t)a << 32) | b : ((uint64_t)b << 32) | a;
+}
+
+struct OptAni { bool some; float ani; };
+
+}  // namespace
+
+int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool skip_clusterer,
+                      float ani_threshold, const AniFn &calculate_ani, ClusterResult &out,
+                      std::string &err) {
+    out = ClusterResult();
+    out.offsets.push_back(0);
+    if (n == 0) {
+        // the reference indexes preclusters[0] unconditionally (src/clusterer.rs:84)
+        err = "index out of bounds: the len is 0 but the index is 0";
+        return 1;
+    }
+    for (size_t h = 0; h < n_hits; h++) {
+        if (hits[h].i >= n || hits[h].j >= n || hits[h].i == hits[h].j) {
+            err = "precluster hit with genome index out of range";
+            return 1;
+        }
+    }
+    if (!skip_clusterer && !calculate_ani) { err = "calculate_ani callback required"; return 1; }
+
+    // ---- adjacency (later duplicates of a key overwrite earlier ones, as BTreeMap::insert does)
+    Adjacency adj;
+    adj.off.assign(n + 1, 0);
+    {
+        std::unordered_map<uint64_t, float> uniq;
+        uniq.reserve(n_hits * 2);
+        for (size_t h = 0; h < n_hits; h++) uniq[pair_key(hits[h].i, hits[h].j)] = hits[h].ani;
+        for (const auto &kv : uniq) {
+            adj.off[(uint32_t)(kv.first >> 32) + 1]++;
+            adj.off[(uint32_t)kv.first + 1]++;
+        }
+        for (size_t g = 0; g < n; g++) adj.off[g + 1] += adj.off[g];
+        adj.nbr.resize(adj.off[n]); adj.ani.resize(adj.off[n]);
+        std::vector<uint64_t> fill(adj.off.begin(), adj.off.end() - 1);
+        for (const auto &kv : uniq) {
+            const uint32_t a = (uint32_t)(kv.first >> 32), b = (uint32_t)kv.first;
+            adj.nbr[fill[a]] = b; adj.ani[fill[a]++] = kv.second;
+            adj.nbr[fill[b]] = a; adj.ani[fill[b]++] = kv.second;
+        }
+        std::vector<std::pair<uint32_t, float>> tmp;
+        for (size_t g = 0; g < n; g++) {
+            tmp.clear();
+            for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++) tmp.emplace_back(adj.nbr[x], adj.ani[x]);
+            std::sort(tmp.begin(), tmp.end());
+            for (size_t x = 0; x < tmp.size(); x++) { adj.nbr[adj.off[g] + x] = tmp[x].first; adj.ani[adj.off[g] + x] = tmp[x].second; }
+        }
+    }
+
+    // ---- partition_sketches: single linkage
+    Dsu dsu(n);
+    for (size_t g = 0; g < n; g++)
+        for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++)
+            if (adj.nbr[x] < g) dsu.join((uint32_t)g, adj.nbr[x]);
+    std::vector<std::vector<uint32_t>> preclusters;
+    {
+        std::vector<int64_t> set_of_root(n, -1);
+        for (uint32_t g = 0; g < n; g++) {  // root == smallest member, so sets appear in that order
+            const uint32_t r = dsu.find(g);
+            if (set_of_root[r] < 0) { set_of_root[r] = (int64_t)preclusters.size(); preclusters.emplace_back(); }
+            preclusters[set_of_root[r]].push_back(g);
+        }
+    }
+    std::stable_sort(preclusters.begin(), preclusters.end(),
+                     [](const std::vector<uint32_t> &a, const std::vector<uint32_t> &b) { return a.size() > b.size(); });
+    out.n_preclusters = (uint32_t)preclusters.size();
+    out.largest_precluster = (uint32_t)preclusters[0].size();
+
+    std::vector<uint8_t> is_rep(n, 0);
+    std::vector<uint32_t> cluster_of_rep(n, 0);
+    std::unordered_map<uint64_t, OptAni> cache;  // clusterer cache of the current precluster
+    std::vector<std::pair<float, uint32_t>> cands;
+
+    for (const auto &members : preclusters) {
+        cache.clear();
+        std::vector<uint32_t> reps;
+        // ---- representatives
+        for (const uint32_t i : members) {
+            cands.clear();
+            for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++) {
+                const uint32_t j = adj.nbr[x];
+                if (is_rep[j]) cands.emplace_back(adj.ani[x], j);  // reps found so far all have j < i
+            }
+            std::stable_sort(cands.begin(), cands.end(),
+                             [](const std::pair<float, uint32_t> &a, const std::pair<float, uint32_t> &b) { return a.first < b.first; });
+            bool rep = true;
+            for (const auto &c : cands) {
+                float ani = c.first;
+                bool some = true;
+                if (!skip_clusterer) {
+                    some = calculate_ani(c.second, i, &ani);
+                    out.ani_calls++;
+                    if (some) cache[pair_key(c.second, i)] = OptAni{true, ani};
+                }
+                if (some && ani >= ani_threshold) {
+                    rep = false;
+                    if (!skip_clusterer) break;  // find_any stops at the first hit
+                }
+            }
+            if (rep) { is_rep[i] = 1; reps.push_back(i); }
+        }
+        // ---- memberships
+        const size_t first_cluster = out.offsets.size() - 1;
+        std::vector<std::vector<uint32_t>> clusters(reps.size());
+        for (size_t c = 0; c < reps.size(); c++) { clusters[c].push_back(reps[c]); cluster_of_rep[reps[c]] = (uint32_t)c; }
+        for (const uint32_t i : members) {
+            if (is_rep[i]) continue;
+            bool have_best = false;
+            float best = 0.f;
+            uint32_t best_rep = 0;
+            for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++) {  // ascending representative index
+                const uint32_t r = adj.nbr[x];
+                if (!is_rep[r]) continue;
+                OptAni v;
+                if (skip_clusterer) {
+                    v = OptAni{true, adj.ani[x]};
+                } else {
+                    auto it = cache.find(pair_key(i, r));
+                    if (it != cache.end()) v = it->second;
+                    else {
+                        float ani = 0.f;
+                        const bool some = calculate_ani(r, i, &ani);
+                        out.ani_calls++;
+                        v = OptAni{some, ani};
+                        cache[pair_key(i, r)] = v;
+                    }
+                }
+                if (v.some && (!have_best || v.ani > best)) { have_best = true; best = v.ani; best_rep = r; }
+            }
+            if (!have_best) {
+                err = "called `Option::unwrap()` on a `None` value (genome " + std::to_string(i) +
+                      " has no representative with an ANI; src/clusterer.rs:444)";
+                return 1;
+            }
+            clusters[cluster_of_rep[best_rep]].push_back(i);
+        }
+        for (auto &c : clusters) {
+            out.members.insert(out.members.end(), c.begin(), c.end());
+            out.offsets.push_back(out.members.size());
+        }
+        (void)first_cluster;
+        for (const uint32_t r : reps) is_rep[r] = 1;  // stays set; other preclusters never touch it
+    }
+    return 0;
+}
+
+}  // namespace gb200

@@ -1,0 +1,33 @@
+// Host side of the clustering engine: the greedy two-stage logic of
+// /root/reference/src/clusterer.rs:14-487 driven by a pair list instead of BTreeMap probes.
+#pragma once
+#include <stdint.h>
+
+#include <functional>
+#include <string>
+#include <vector>
+
+namespace gb200 {
+
+struct PreclusterHit {
+    uint32_t i, j;  // i < j, positions in the genome slice
+    float ani;      // the `Some(ani)` value stored by the preclusterer
+};
+
+// calculate_ani(fasta1 = candidate representative, fasta2 = genome under consideration)
+// -> true and *ani for Some(ani), false for None  (src/lib.rs:54).
+using AniFn = std::function<bool(uint32_t rep, uint32_t genome, float *ani)>;
+
+struct ClusterResult {
+    std::vector<uint32_t> members;   // concatenated clusters, representative first
+    std::vector<uint64_t> offsets;   // n_clusters + 1
+    uint64_t ani_calls = 0;          // calculate_ani invocations made
+    uint32_t n_preclusters = 0, largest_precluster = 0;
+};
+
+// Returns 0, or non-zero with `err` set (mirrors the reference's panics).
+int cluster_from_hits(size_t n_genomes, const PreclusterHit *hits, size_t n_hits, bool skip_clusterer,
+                      float ani_threshold, const AniFn &calculate_ani, ClusterResult &out,
+                      std::string &err);
+
+}  // namespace gb200

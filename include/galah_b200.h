@@ -123,6 +123,34 @@ int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani
                                uint32_t num_kmers, uint8_t kmer_length, int host_threads,
                                galah_b200_pair_t **out, size_t *n_out);
 
+/* ---- clustering engine (host logic) --------------------------------------------------------
+ * Replaces the body of galah::clusterer::cluster() after the preclusterer has run
+ * (src/clusterer.rs:56-151): partition_sketches (:452-487), preclusters largest first (:67-79),
+ * find_precluster_cluster_representatives (:182-259), find_precluster_cluster_memberships
+ * (:350-449).  Driven by the sparse hit list instead of N^2/2 BTreeMap probes; output order is
+ * the reference's at --threads 1.  Pure host code: needs no device.
+ *
+ * hits: the preclusterer's SortedPairGenomeDistanceCache as (i, j, ani) records (common/total
+ * are ignored).  skip_clusterer: src/clusterer.rs:32-44 (same method names, or contigs).
+ * ani_threshold: ClusterDistanceFinder::get_ani_threshold() (src/lib.rs:52).
+ * calculate_ani: ClusterDistanceFinder::calculate_ani(fasta1 = representative, fasta2 = genome)
+ * (src/lib.rs:54) as indices; returns 1 and sets *ani for Some(ani), 0 for None.  May be NULL
+ * when skip_clusterer != 0. */
+typedef int (*galah_b200_ani_fn)(void *ctx, uint32_t representative, uint32_t genome, float *ani);
+typedef struct galah_b200_clusters {
+    uint32_t *members;      /* concatenated clusters; the representative is first in each */
+    uint64_t *offsets;      /* n_clusters + 1 */
+    size_t n_clusters;
+    uint64_t ani_calls;     /* calculate_ani invocations made */
+    uint32_t n_preclusters; /* "Found {} preclusters. The largest contained {} genomes" */
+    uint32_t largest_precluster;
+} galah_b200_clusters_t;
+int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t *hits,
+                                      size_t n_hits, int skip_clusterer, float ani_threshold,
+                                      galah_b200_ani_fn calculate_ani, void *ctx,
+                                      galah_b200_clusters_t *out);
+void galah_b200_clusters_free(galah_b200_clusters_t *c);
+
 /* ---- synthetic genomes (bench / tests) ------------------------------------- */
 /* Generates genomes [index_begin, index_begin+n) of `length` bases each directly in packed
  * form on the device.  d_seq2 needs n * words_per_genome uint32 with

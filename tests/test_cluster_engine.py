@@ -1,0 +1,124 @@
+"""Host clustering engine (C++ behind the C ABI) vs the pure-Python restatement of
+galah::clusterer::cluster() in oracle/cluster_oracle.py.  No GPU needed: the engine is host logic."""
+import numpy as np
+import pytest
+
+import galah_b200 as gb
+from oracle import cluster_oracle as co
+
+
+def make_hits(pairs):
+    h = np.zeros(len(pairs), gb.PAIR_DTYPE)
+    for x, (i, j, a) in enumerate(pairs):
+        h[x]["i"], h[x]["j"], h[x]["ani"] = i, j, a
+    return h
+
+
+def test_transform_ids_reference_vectors():
+    """src/sorted_pair_genome_distance_cache.rs:69-114 (the reference's own unit tests)."""
+    c = co.SortedPairGenomeDistanceCache()
+    c.insert((1, 2), np.float32(0.5))
+    c.insert((3, 2), np.float32(0.6))
+    assert c.get((2, 1)) == (True, np.float32(0.5)) and c.get((2, 3)) == (True, np.float32(0.6))
+    assert not c.contains_key((1, 3))
+    t = c.transform_ids([1, 2])
+    assert t.internal == {(0, 1): np.float32(0.5)}
+    t = c.transform_ids([2, 3, 5])
+    assert t.internal == {(0, 1): np.float32(0.6)}
+
+
+def test_hand_worked_two_stage():
+    """5 genomes, one precluster {0,1,2,3} + singleton {4}.  Stage-2 ANI: 1~0 96, 2~0 94, 2~1 97,
+    3~0 95.5, 3~2 99.  Representatives at 95: 0 and 2 (1 joins 0's candidates only; 2 sees only
+    rep 0 at 94; 3 tries rep 0 first -- lowest precluster ANI -- and stops at 95.5).  Membership is
+    by BEST ANI over all representatives with a precluster hit: 1 -> 2 (97 > 96), 3 -> 2 (99)."""
+    hits = make_hits([(0, 1, 0.97), (0, 2, 0.91), (1, 2, 0.95), (0, 3, 0.93), (2, 3, 0.99)])
+    ani = {(0, 1): 96.0, (0, 2): 94.0, (1, 2): 97.0, (0, 3): 95.5, (2, 3): 99.0}
+    calls = []
+
+    def f(rep, g):
+        calls.append((rep, g))
+        return ani[(min(rep, g), max(rep, g))]
+
+    clusters, info = gb.cluster_from_distances(5, hits, 95.0, f)
+    assert clusters == [[0], [2, 1, 3], [4]]
+    assert info["n_preclusters"] == 2 and info["largest_precluster"] == 4
+    # rep stage: (0,1); (0,2); (0,3) passes -> stop, (2,3) not computed there; membership: (2,1), (2,3)
+    assert calls == [(0, 1), (0, 2), (0, 3), (2, 1), (2, 3)]
+    exp, einfo = co.cluster(5, [(h["i"], h["j"], h["ani"]) for h in hits], 95.0, f)
+    assert exp == clusters and einfo["ani_calls"] == info["ani_calls"]
+
+
+def test_skip_clusterer_uses_precluster_ani():
+    hits = make_hits([(0, 1, 96.0), (1, 2, 97.0), (0, 2, 90.0), (3, 4, 99.5)])
+    clusters, info = gb.cluster_from_distances(6, hits, 95.0, None, skip_clusterer=True)
+    exp, _ = co.cluster(6, [(h["i"], h["j"], h["ani"]) for h in hits], 95.0, None, skip_clusterer=True)
+    # precluster {0,1,2}: 1 is not a rep (96 vs rep 0); 2 vs rep 0 is 90 -> rep; 1 then joins its
+    # BEST rep, 2 (97 > 96); then {3,4}; then {5}
+    assert clusters == exp == [[0], [2, 1], [3, 4], [5]]
+    assert info["ani_calls"] == 0
+
+
+def test_none_ani_and_unwrap_panic():
+    """calculate_ani -> None everywhere: every genome becomes a representative (None never reaches
+    the threshold), so nobody needs a membership and nothing panics."""
+    hits = make_hits([(0, 1, 0.95), (1, 2, 0.95)])
+    clusters, _ = gb.cluster_from_distances(3, hits, 95.0, lambda r, g: None)
+    assert clusters == [[0], [1], [2]]
+    # a non-rep whose only ANIs are None at membership time cannot happen in the reference either:
+    # it became a non-rep because some ANI >= threshold was cached.
+
+
+def test_zero_genomes_mirrors_reference_panic():
+    with pytest.raises(gb.GalahB200Error) as e:
+        gb.cluster_from_distances(0, make_hits([]), 95.0, lambda r, g: 99.0)
+    assert "index out of bounds" in str(e.value)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_graphs_match_oracle(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 60))
+    fam = rng.integers(0, max(1, n // 4), size=n)
+    pairs, ani2 = [], {}
+    for i in range(n):
+        for j in range(i + 1, n):
+            same = fam[i] == fam[j]
+            if rng.uniform() < (0.7 if same else 0.03):
+                pairs.append((i, j, float(np.float32(rng.uniform(0.9, 1.0)))))
+            # stage-2 ANI table with ties and Nones
+            v = rng.choice([None, 94.0, 95.0, 96.5, 99.0, float(np.float32(rng.uniform(90, 100)))],
+                           p=[0.05, 0.15, 0.2, 0.2, 0.1, 0.3])
+            ani2[(i, j)] = v
+    hits = make_hits(pairs)
+
+    def f(rep, g):
+        return ani2[(min(rep, g), max(rep, g))]
+
+    for skip in (False, True):
+        thr = 95.0 if not skip else 0.95
+        try:
+            exp, einfo = co.cluster(n, pairs, thr, f, skip_clusterer=skip)
+        except RuntimeError as ex:
+            with pytest.raises(gb.GalahB200Error) as e:
+                gb.cluster_from_distances(n, hits, thr, f, skip_clusterer=skip)
+            assert "Option::unwrap()" in str(e.value) and "unwrap" in str(ex)
+            continue
+        got, info = gb.cluster_from_distances(n, hits, thr, f, skip_clusterer=skip)
+        assert got == exp
+        assert info == einfo
+        assert sorted(x for c in got for x in c) == list(range(n))
+
+
+def test_large_sparse_is_linear_in_hits():
+    """100k genomes in families of 10 (450k hits): the engine must not be quadratic in N."""
+    import time
+    n = 100_000
+    pairs = [(f * 10 + a, f * 10 + b, 0.97) for f in range(n // 10) for a in range(10) for b in range(a + 1, 10)]
+    hits = make_hits(pairs)
+    t0 = time.time()
+    clusters, info = gb.cluster_from_distances(n, hits, 0.95, None, skip_clusterer=True)
+    dt = time.time() - t0
+    assert len(clusters) == n // 10 and all(len(c) == 10 for c in clusters)
+    assert info["n_preclusters"] == n // 10 and info["largest_precluster"] == 10
+    assert dt < 20.0
