@@ -28,6 +28,12 @@ class Clusters(ctypes.Structure):
                 ("n_preclusters", ctypes.c_uint32), ("largest_precluster", ctypes.c_uint32)]
 
 
+class AniResult(ctypes.Structure):
+    _fields_ = [("ani", ctypes.c_float), ("af_query", ctypes.c_float), ("af_ref", ctypes.c_float),
+                ("sum_m", ctypes.c_uint32), ("sum_n", ctypes.c_uint32), ("cov_q", ctypes.c_uint32),
+                ("cov_r", ctypes.c_uint32), ("swapped", ctypes.c_uint32)]
+
+
 ANI_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                           ctypes.POINTER(ctypes.c_float))
 
@@ -69,6 +75,16 @@ _SIGNATURES = {
                                                     ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "galah_b200_finch_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32,
                                                   ctypes.c_uint8, ctypes.c_int, pairpp, sizep]),
+    "galah_b200_ani_index_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
+    "galah_b200_ani_index_free": (None, [vp]),
+    "galah_b200_ani_index_add_files": (ctypes.c_int, [vp, strp, ctypes.c_size_t, ctypes.c_int]),
+    "galah_b200_ani_index_add_packed": (ctypes.c_int, [vp, u32p, u32p, u64p, ctypes.c_size_t, u64p, u32p, u32p]),
+    "galah_b200_ani_index_add_packed_device": (ctypes.c_int, [vp, vp, vp, vp, u64p, u64p, ctypes.c_size_t, vp]),
+    "galah_b200_ani_index_size": (ctypes.c_size_t, [vp]),
+    "galah_b200_ani_index_genome": (ctypes.c_int, [vp, ctypes.c_size_t, u64p, u32p, u64p]),
+    "galah_b200_ani_index_seeds": (ctypes.c_int, [vp, ctypes.c_size_t, u32p, u32p, u32p, ctypes.c_size_t]),
+    "galah_b200_ani_pairs": (ctypes.c_int, [vp, u32p, ctypes.c_size_t, ctypes.c_float, ctypes.POINTER(AniResult)]),
+    "galah_b200_ani_last_timing": (ctypes.c_int, [vp, f32p, f32p]),
     "galah_b200_cluster_from_distances": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p,
                                                          ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                                          ANI_FN, vp, ctypes.POINTER(Clusters)]),

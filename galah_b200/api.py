@@ -139,6 +139,78 @@ def finch_distances(paths, min_ani=0.9, num_kmers=1000, kmer_length=21, threads=
     return _take_pairs(out, n_out)
 
 
+ANI_RESULT_DTYPE = np.dtype([("ani", "<f4"), ("af_query", "<f4"), ("af_ref", "<f4"), ("sum_m", "<u4"),
+                             ("sum_n", "<u4"), ("cov_q", "<u4"), ("cov_r", "<u4"), ("swapped", "<u4")])
+
+
+class AniIndex:
+    """Genomes indexed for stage-2 ANI (FracMinHash seeds + hash tables resident on the GPU).
+    GPU replacement for SkaniClusterer::calculate_ani (reference src/skani.rs:689-788)."""
+
+    def __init__(self, small_genomes=False):
+        self._h = ctypes.c_void_p()
+        check(lib().galah_b200_ani_index_create(int(bool(small_genomes)), ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().galah_b200_ani_index_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(lib().galah_b200_ani_index_size(self._h))
+
+    def add_files(self, paths, threads=0):
+        check(lib().galah_b200_ani_index_add_files(self._h, _paths_array(paths), len(paths), threads))
+
+    def add_packed(self, seq2, valid, base_off, contig_off, contig_start, contig_len):
+        seq2 = np.ascontiguousarray(seq2, np.uint32); valid = np.ascontiguousarray(valid, np.uint32)
+        base_off = np.ascontiguousarray(base_off, np.uint64); contig_off = np.ascontiguousarray(contig_off, np.uint64)
+        contig_start = np.ascontiguousarray(contig_start, np.uint32); contig_len = np.ascontiguousarray(contig_len, np.uint32)
+        check(lib().galah_b200_ani_index_add_packed(
+            self._h, seq2.ctypes.data_as(_native.u32p), valid.ctypes.data_as(_native.u32p),
+            base_off.ctypes.data_as(_native.u64p), len(base_off) - 1, contig_off.ctypes.data_as(_native.u64p),
+            contig_start.ctypes.data_as(_native.u32p), contig_len.ctypes.data_as(_native.u32p)))
+
+    def add_packed_device(self, d_seq2, d_valid, d_base_off, base_off, lengths, stream=0):
+        base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+        check(lib().galah_b200_ani_index_add_packed_device(
+            self._h, d_seq2, d_valid, d_base_off, base_off.ctypes.data_as(_native.u64p),
+            lengths.ctypes.data_as(_native.u64p), len(lengths), stream))
+
+    def genome(self, g):
+        ns, nc, tl = ctypes.c_uint64(0), ctypes.c_uint32(0), ctypes.c_uint64(0)
+        check(lib().galah_b200_ani_index_genome(self._h, g, ctypes.byref(ns), ctypes.byref(nc), ctypes.byref(tl)))
+        return {"n_seeds": ns.value, "n_chunks": nc.value, "total_len": tl.value}
+
+    def seeds(self, g):
+        n = self.genome(g)["n_seeds"]
+        ks = np.zeros(max(n, 1), np.uint32); sp = np.zeros(max(n, 1), np.uint32); ch = np.zeros(max(n, 1), np.uint32)
+        check(lib().galah_b200_ani_index_seeds(self._h, g, ks.ctypes.data_as(_native.u32p),
+                                               sp.ctypes.data_as(_native.u32p), ch.ctypes.data_as(_native.u32p), max(n, 1)))
+        return ks[:n], sp[:n], ch[:n]
+
+    def pairs(self, pairs, min_af_pct=15.0):
+        """pairs: (n, 2) genome ids -> ANI_RESULT_DTYPE records (ani as galah would parse it)."""
+        pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        out = np.zeros(len(pairs), ANI_RESULT_DTYPE)
+        if len(pairs):
+            check(lib().galah_b200_ani_pairs(self._h, pairs.ctypes.data_as(_native.u32p), len(pairs),
+                                             ctypes.c_float(min_af_pct),
+                                             out.ctypes.data_as(ctypes.POINTER(_native.AniResult))))
+        return out
+
+    def last_timing(self):
+        b, c = ctypes.c_float(0), ctypes.c_float(0)
+        check(lib().galah_b200_ani_last_timing(self._h, ctypes.byref(b), ctypes.byref(c)))
+        return float(b.value), float(c.value)
+
+
 def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, skip_clusterer=False):
     """The clustering engine behind galah::clusterer::cluster() (reference src/clusterer.rs:56-151)
     on a precluster hit list.  `hits`: PAIR_DTYPE records (i, j, ani).  `calculate_ani(rep, genome)`

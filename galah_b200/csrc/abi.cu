@@ -10,6 +10,7 @@
 #include <thread>
 #include <vector>
 
+#include "ani.cuh"
 #include "common.cuh"
 #include "host/cluster_engine.hpp"
 #include "host/fasta.hpp"
@@ -349,6 +350,162 @@ int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani
     int rc = galah_b200_sketch_files(paths, n, kmer_length, s, 0, host_threads, hashes.data(), counts.data());
     if (rc) return rc;
     return galah_b200_prefilter(hashes.data(), counts.data(), n, s, kmer_length, min_ani, out, n_out);
+}
+
+struct galah_b200_ani_index { gb200::AniIndex impl; explicit galah_b200_ani_index(uint32_t c) : impl(c) {} };
+
+int galah_b200_ani_index_create(int small_genomes, galah_b200_ani_index_t **out) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!out) { set_error("ani index: out is NULL"); return GALAH_B200_ERR_ARG; }
+    *out = new galah_b200_ani_index(small_genomes ? 30u : 125u);
+    return 0;
+}
+
+void galah_b200_ani_index_free(galah_b200_ani_index_t *idx) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (idx && g_ctx.device >= 0) cudaSetDevice(g_ctx.device);
+    delete idx;
+}
+
+size_t galah_b200_ani_index_size(const galah_b200_ani_index_t *idx) { return idx ? idx->impl.size() : 0; }
+
+static int ani_add_packed_host(galah_b200_ani_index_t *idx, const uint32_t *seq2, const uint32_t *valid,
+                               const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
+                               const std::vector<uint32_t> &contig_start, const std::vector<uint32_t> &contig_len) {
+    const size_t n = base_off.size() - 1;
+    const uint64_t first = base_off[0], total = base_off[n] - first;
+    DevBuf<uint32_t> d_seq2, d_valid;
+    DevBuf<uint64_t> d_off;
+    if (d_seq2.alloc(total / 16 + 8) || d_valid.alloc(total / 32 + 8) || d_off.alloc(n + 1)) return GALAH_B200_ERR_CUDA;
+    cudaStream_t st = g_ctx.stream;
+    std::vector<uint64_t> rel(n + 1);
+    for (size_t g = 0; g <= n; g++) rel[g] = base_off[g] - first;
+    GB_CUDA(cudaMemsetAsync(d_seq2.p, 0, (total / 16 + 8) * 4, st));
+    GB_CUDA(cudaMemsetAsync(d_valid.p, 0, (total / 32 + 8) * 4, st));
+    GB_CUDA(cudaMemcpyAsync(d_seq2.p, seq2 + first / 16, total / 16 * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_valid.p, valid + first / 32, total / 32 * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_off.p, rel.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    return idx->impl.add_packed_device(d_seq2.p, d_valid.p, d_off.p, n, rel, contig_off, contig_start, contig_len, st);
+}
+
+int galah_b200_ani_index_add_packed(galah_b200_ani_index_t *idx, const uint32_t *seq2, const uint32_t *valid,
+                                    const uint64_t *base_off, size_t n, const uint64_t *contig_off,
+                                    const uint32_t *contig_start, const uint32_t *contig_len) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    if (n == 0) return 0;
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("ani index: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
+    std::vector<uint64_t> bo(base_off, base_off + n + 1), co(contig_off, contig_off + n + 1);
+    std::vector<uint32_t> cs(contig_start, contig_start + co[n]), cl(contig_len, contig_len + co[n]);
+    return ani_add_packed_host(idx, seq2, valid, bo, co, cs, cl);
+}
+
+int galah_b200_ani_index_add_packed_device(galah_b200_ani_index_t *idx, const uint32_t *d_seq2,
+                                           const uint32_t *d_valid, const uint64_t *d_base_off,
+                                           const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                           void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    std::vector<uint64_t> bo(base_off, base_off + n + 1), co(n + 1);
+    std::vector<uint32_t> cs(n, 0), cl(n);
+    for (size_t g = 0; g < n; g++) { co[g] = g; cl[g] = (uint32_t)lengths[g]; }
+    co[n] = n;
+    return idx->impl.add_packed_device(d_seq2, d_valid, d_base_off, n, bo, co, cs, cl, (cudaStream_t)stream);
+}
+
+int galah_b200_ani_index_add_files(galah_b200_ani_index_t *idx, const char *const *paths, size_t n,
+                                   int host_threads) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const size_t kMaxBatchGenomes = 256;
+    const uint64_t kMaxBatchBases = 2ull << 30;
+    size_t done = 0;
+    while (done < n) {
+        const size_t want = std::min(kMaxBatchGenomes, n - done);
+        std::vector<PackedGenome> batch(want);
+        std::vector<std::string> errs(want);
+        std::vector<int> rcs(want, 0);
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                size_t x = next.fetch_add(1);
+                if (x >= want) break;
+                rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
+            }
+        };
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
+        for (int t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &t : th) t.join();
+        for (size_t x = 0; x < want; x++)
+            if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
+        size_t b0 = 0;
+        while (b0 < want) {
+            size_t b1 = b0; uint64_t bases = 0;
+            while (b1 < want && (b1 == b0 || bases + batch[b1].padded_bases() <= kMaxBatchBases)) {
+                bases += batch[b1].padded_bases(); b1++;
+            }
+            const size_t nb = b1 - b0;
+            std::vector<uint64_t> base_off(nb + 1, 0), contig_off(nb + 1, 0);
+            std::vector<uint32_t> cs, cl;
+            for (size_t x = 0; x < nb; x++) {
+                const PackedGenome &pg = batch[b0 + x];
+                base_off[x + 1] = base_off[x] + pg.padded_bases();
+                for (size_t r = 0; r < pg.rec_start.size(); r++) {
+                    cs.push_back((uint32_t)pg.rec_start[r]);
+                    cl.push_back((uint32_t)(pg.rec_end[r] - pg.rec_start[r]));
+                }
+                contig_off[x + 1] = cs.size();
+            }
+            std::vector<uint32_t> seq2(base_off[nb] / 16 + 4, 0u), valid(base_off[nb] / 32 + 4, 0u);
+            for (size_t x = 0; x < nb; x++) {
+                const PackedGenome &pg = batch[b0 + x];
+                memcpy(seq2.data() + base_off[x] / 16, pg.seq2.data(), pg.padded_bases() / 16 * 4);
+                memcpy(valid.data() + base_off[x] / 32, pg.valid.data(), pg.padded_bases() / 32 * 4);
+            }
+            int rc = ani_add_packed_host(idx, seq2.data(), valid.data(), base_off, contig_off, cs, cl);
+            if (rc) return rc;
+            b0 = b1;
+        }
+        done += want;
+    }
+    return 0;
+}
+
+int galah_b200_ani_index_genome(const galah_b200_ani_index_t *idx, size_t g, uint64_t *n_seeds,
+                                uint32_t *n_chunks, uint64_t *total_len) {
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    return idx->impl.genome_info(g, n_seeds, n_chunks, total_len);
+}
+
+int galah_b200_ani_index_seeds(const galah_b200_ani_index_t *idx, size_t g, uint32_t *kmer_strand,
+                               uint32_t *spread, uint32_t *chunk, size_t cap) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    return idx->impl.genome_seeds(g, kmer_strand, spread, chunk, cap, g_ctx.stream);
+}
+
+int galah_b200_ani_pairs(galah_b200_ani_index_t *idx, const uint32_t *pairs, size_t n_pairs, float min_af_pct,
+                         galah_b200_ani_result_t *results) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    static_assert(sizeof(galah_b200_ani_result_t) == sizeof(AniPairResult), "result layout");
+    return idx->impl.pairs(pairs, n_pairs, min_af_pct, reinterpret_cast<AniPairResult *>(results), g_ctx.stream);
+}
+
+int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_ms, float *chain_ms) {
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    *build_ms = idx->impl.last_build_ms; *chain_ms = idx->impl.last_chain_ms;
+    return 0;
 }
 
 int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,

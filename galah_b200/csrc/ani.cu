@@ -1,0 +1,527 @@
+// Stage 2 (K3): FracMinHash seed-and-chain ANI on sm_100a.
+//
+// Replaces the `skani dist` subprocess spawned per genome pair at
+// /root/reference/src/skani.rs:718-788 (ClusterDistanceFinder::calculate_ani, src/lib.rs:54).
+// The algorithm is specified, constant by constant, in oracle/skani_oracle.c (a restatement of
+// skani's published method without its learned correction; numeric parity with the skani binary
+// is unpinned).  Everything on the device is integer arithmetic, so the kernels
+// are bit-exact against that restatement.
+//
+// Index build (once per genome, genomes stay resident in HBM):
+//   ani_mark_kernel   every k-mer start position of the batch: canonical 15-mer straight from the
+//                     packed 2-bit stream (funnel shift + bit reversal, as K1), mm_hash64,
+//                     selected iff hash < (2^64-1)/c; one ballot word per 32 positions.
+//   ani_count_kernel  seeds per genome (popc reduction) -> host sizes the arrays.
+//   ani_emit_kernel   one CTA per genome: block-scan of the popcounts gives every seed its rank,
+//                     so seeds land in POSITION ORDER without a sort; per seed the contig (binary
+//                     search), spread position and chunk id; then the chunk -> seed-range table
+//                     and the genome's open-addressing hash table
+//                     (entry = kmer << 33 | strand << 32 | spread, atomicCAS linear probing).
+// Pair evaluation:
+//   ani_chain_kernel  one THREAD per (pair, query chunk): walks the chunk's seeds in order,
+//                     probes the reference genome's hash table (<= 8 occurrences, emitted in
+//                     ascending reference position), and runs the banded chaining DP over a ring
+//                     of the last 32 anchors held in shared memory ([slot][field][thread], so a
+//                     warp's accesses never conflict).  Each anchor carries (count, first seed,
+//                     first reference position) of its best chain, so no backtracking pass.
+//                     Accepted chunks add (M-2, N-2, covq, covr) to the pair's accumulators.
+//                     Bound: latency of random 8-byte reads of the reference table (L2/HBM);
+//                     algorithmic bytes per pair = 2 * (L/c) * 12 B.
+#include "ani.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gb200 {
+
+template <typename T>
+int DevVec<T>::reserve(size_t need, cudaStream_t st) {
+    if (need <= cap) return 0;
+    size_t ncap = std::max(need, cap + cap / 2 + 1024);
+    T *np = nullptr;
+    GB_CUDA(cudaMalloc(&np, ncap * sizeof(T)));
+    if (p && n) GB_CUDA(cudaMemcpyAsync(np, p, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    if (p) GB_CUDA(cudaFree(p));
+    p = np; cap = ncap;
+    return 0;
+}
+
+constexpr unsigned long long kEmpty = ~0ull;
+
+__device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
+    key = ~key + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+// Canonical 15-mer at absolute packed position P; false if the window holds an invalid base.
+__device__ __forceinline__ bool canon15(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ valid,
+                                        uint64_t P, uint32_t &canon, uint32_t &strand) {
+    const uint64_t vw = P >> 5;
+    const uint32_t vm = __funnelshift_r(__ldg(valid + vw), __ldg(valid + vw + 1), (uint32_t)P & 31u);
+    if ((vm & 0x7FFFu) != 0x7FFFu) return false;
+    const uint64_t w = P >> 4;
+    const uint32_t V = __funnelshift_r(__ldg(seq2 + w), __ldg(seq2 + w + 1), ((uint32_t)P & 15u) * 2u) & 0x3FFFFFFFu;
+    uint32_t F = __brev(V);
+    F = ((F >> 1) & 0x55555555u) | ((F & 0x55555555u) << 1);
+    F >>= 2;
+    const uint32_t R = ~V & 0x3FFFFFFFu;
+    canon = min(F, R);
+    strand = R < F ? 1u : 0u;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) ani_mark_kernel(const uint32_t *__restrict__ seq2,
+                                                       const uint32_t *__restrict__ valid, uint64_t first_base,
+                                                       uint64_t end_base, uint64_t thr,
+                                                       uint32_t *__restrict__ sel) {
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    // first_base and end_base are multiples of 128, so every warp covers whole mask words
+    for (uint64_t P = first_base + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; P < end_base; P += step) {
+        uint32_t canon, strand;
+        bool pick = canon15(seq2, valid, P, canon, strand);
+        if (pick) pick = mm_hash64(canon) < thr;
+        const uint32_t word = __ballot_sync(0xffffffffu, pick);
+        if ((threadIdx.x & 31) == 0) sel[(P - first_base) >> 5] = word;
+    }
+}
+
+// Mask word w (absolute word index relative to first_base) of a genome whose k-mer start
+// positions end at `limit` (relative to first_base): a window must not run into the next genome.
+__device__ __forceinline__ uint32_t sel_word(const uint32_t *__restrict__ sel, uint64_t w, uint64_t limit) {
+    const uint64_t wp = w << 5;
+    if (wp >= limit) return 0u;
+    const uint32_t word = sel[w];
+    return limit - wp >= 32 ? word : word & ((1u << (uint32_t)(limit - wp)) - 1u);
+}
+
+__global__ void __launch_bounds__(256) ani_count_kernel(const uint32_t *__restrict__ sel,
+                                                        const uint64_t *__restrict__ base_off, uint64_t first_base,
+                                                        uint32_t *__restrict__ count) {
+    __shared__ uint32_t s_sum[8];
+    const uint32_t g = blockIdx.x;
+    const uint64_t w0 = (base_off[g] - first_base) >> 5, w1 = (base_off[g + 1] - first_base) >> 5;
+    const uint64_t len = base_off[g + 1] - base_off[g];
+    const uint64_t limit = (base_off[g] - first_base) + (len >= (uint64_t)kAniK ? len - kAniK + 1 : 0);
+    uint32_t sum = 0;
+    for (uint64_t w = w0 + threadIdx.x; w < w1; w += 256) sum += __popc(sel_word(sel, w, limit));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; w++) t += s_sum[w];
+        count[g] = t;
+    }
+}
+
+struct EmitParams {
+    const uint32_t *seq2, *valid, *sel;
+    const uint64_t *base_off;      // batch-local [n + 1]
+    uint64_t first_base;
+    const uint64_t *contig_off;    // batch-local [n + 1]
+    const uint32_t *contig_start;  // per contig, relative to the genome's first base
+    const uint32_t *contig_chunk_base;
+    const uint64_t *seed_off;      // batch-local [n + 1], absolute offsets into ks/spread
+    const uint64_t *cso_off;       // batch-local [n + 1], absolute offsets into cso
+    const uint32_t *n_chunks;      // batch-local [n]
+    const uint64_t *table_off;     // batch-local [n + 1], absolute offsets into table
+    uint32_t *ks, *spread, *cso, *chunk_tmp;
+    unsigned long long *table;
+};
+
+__device__ __forceinline__ uint32_t table_slot(uint32_t km, uint32_t mask) {
+    return (uint32_t)(((uint64_t)km * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+}
+
+__global__ void __launch_bounds__(256) ani_emit_kernel(const EmitParams p) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_running;
+    const uint32_t g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t b0 = p.base_off[g];
+    const uint64_t w0 = (b0 - p.first_base) >> 5, w1 = (p.base_off[g + 1] - p.first_base) >> 5;
+    const uint64_t so = p.seed_off[g];
+    const uint32_t n_seeds = (uint32_t)(p.seed_off[g + 1] - so);
+    const uint64_t c0 = p.contig_off[g];
+    const uint32_t n_contigs = (uint32_t)(p.contig_off[g + 1] - c0);
+    const uint64_t glen = p.base_off[g + 1] - b0;
+    const uint64_t limit = (b0 - p.first_base) + (glen >= (uint64_t)kAniK ? glen - kAniK + 1 : 0);
+    if (tid == 0) s_running = 0;
+    __syncthreads();
+    for (uint64_t wb = w0; wb < w1; wb += 256) {
+        const uint64_t w = wb + tid;
+        uint32_t word = w < w1 ? sel_word(p.sel, w, limit) : 0u;
+        const uint32_t pc = __popc(word);
+        uint32_t incl = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t base = s_running;
+        for (uint32_t x = 0; x < warp; x++) base += s_warp[x];
+        uint32_t rank = base + incl - pc;
+        while (word) {
+            const uint32_t bit = __ffs(word) - 1;
+            word &= word - 1;
+            const uint64_t P = p.first_base + (w << 5) + bit;
+            uint32_t canon = 0, strand = 0;
+            canon15(p.seq2, p.valid, P, canon, strand);
+            const uint32_t rel = (uint32_t)(P - b0);
+            uint32_t lo = 0, hi = n_contigs;  // last contig with start <= rel
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (p.contig_start[c0 + mid] <= rel) lo = mid; else hi = mid;
+            }
+            p.ks[so + rank] = (canon << 1) | strand;
+            p.spread[so + rank] = rel + lo * (uint32_t)(kAniBand + 1);
+            p.chunk_tmp[so + rank] = p.contig_chunk_base[c0 + lo] + (rel - p.contig_start[c0 + lo]) / kAniChunk;
+            rank++;
+        }
+        __syncthreads();
+        if (tid == 0) { uint32_t t = 0; for (int x = 0; x < 8; x++) t += s_warp[x]; s_running += t; }
+        __syncthreads();
+    }
+    // chunk -> first seed table (cso[t] = index of the first seed with chunk >= t; cso[n_chunks] = n_seeds)
+    const uint32_t nch = p.n_chunks[g];
+    uint32_t *cso = p.cso + p.cso_off[g];
+    if (n_seeds == 0) {
+        for (uint32_t t = tid; t <= nch; t += 256) cso[t] = 0;
+    } else {
+        for (uint32_t x = tid; x < n_seeds; x += 256) {
+            const uint32_t ch = p.chunk_tmp[so + x];
+            const uint32_t first = x == 0 ? 0 : p.chunk_tmp[so + x - 1] + 1;
+            for (uint32_t t = first; t <= ch; t++) cso[t] = x;
+            if (x == n_seeds - 1) for (uint32_t t = ch + 1; t <= nch; t++) cso[t] = n_seeds;
+        }
+    }
+    // hash table of this genome's seeds
+    const uint64_t to = p.table_off[g];
+    const uint32_t mask = (uint32_t)(p.table_off[g + 1] - to) - 1;
+    unsigned long long *table = p.table + to;
+    for (uint32_t x = tid; x < n_seeds; x += 256) {
+        const uint32_t ks = p.ks[so + x];
+        const unsigned long long e = ((unsigned long long)(ks >> 1) << 33) | ((unsigned long long)(ks & 1) << 32) |
+                                     p.spread[so + x];
+        uint32_t slot = table_slot(ks >> 1, mask);
+        while (atomicCAS(&table[slot], kEmpty, e) != kEmpty) slot = (slot + 1) & mask;
+    }
+}
+
+struct ChainParams {
+    const uint32_t *pairs;  // (query, reference) genome ids
+    const uint32_t *ks, *spread, *cso;
+    const unsigned long long *table;
+    const uint64_t *seed_off, *cso_off, *table_off;
+    const uint32_t *n_chunks;
+    uint32_t *acc;  // 4 per pair: sumM, sumN, covq, covr
+};
+
+constexpr int kChainThreads = 128;
+constexpr int kRingFields = 5;  // q, r, f, rel<<31 | cnt<<16 | first_x, first_r
+
+__global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainParams p) {
+    extern __shared__ int ring[];  // [kAniH][kRingFields][kChainThreads]
+    const uint32_t pair = blockIdx.y, tid = threadIdx.x;
+    const uint32_t t = blockIdx.x * kChainThreads + tid;
+    const uint32_t q = p.pairs[2 * pair], r = p.pairs[2 * pair + 1];
+    if (t >= p.n_chunks[q]) return;
+    const uint32_t *cso = p.cso + p.cso_off[q];
+    const uint32_t x0 = cso[t], x1 = cso[t + 1];
+    if (x1 - x0 < (uint32_t)kAniMinAnchors) return;
+    const uint32_t *qks = p.ks + p.seed_off[q], *qsp = p.spread + p.seed_off[q];
+    const unsigned long long *table = p.table + p.table_off[r];
+    const uint32_t mask = (uint32_t)(p.table_off[r + 1] - p.table_off[r]) - 1;
+#define RING(slot, field) ring[((slot) * kRingFields + (field)) * kChainThreads + tid]
+    uint32_t n_anchor = 0;
+    int best_f = 0, best_first_r = 0, best_last_r = 0;
+    uint32_t best_cnt = 0, best_first_x = 0, best_last_x = 0;
+    for (uint32_t x = x0; x < x1; x++) {
+        const uint32_t ks = qks[x], km = ks >> 1, qs = ks & 1;
+        const int qpos = (int)qsp[x];
+        // occurrences of km in the reference
+        const uint32_t home = table_slot(km, mask);
+        uint32_t occ = 0;
+        for (uint32_t slot = home;; slot = (slot + 1) & mask) {
+            const unsigned long long e = table[slot];
+            if (e == kEmpty) break;
+            occ += (uint32_t)(e >> 33) == km ? 1u : 0u;
+        }
+        if (occ == 0 || occ > (uint32_t)kAniMaxOcc) continue;
+        long long prev = -1;  // matches in ascending (strand << 32 | spread) is NOT the order: sort by spread
+        for (uint32_t m = 0; m < occ; m++) {
+            // next match in ascending reference spread position
+            unsigned long long pick = kEmpty;
+            for (uint32_t slot = home;; slot = (slot + 1) & mask) {
+                const unsigned long long e = table[slot];
+                if (e == kEmpty) break;
+                if ((uint32_t)(e >> 33) != km) continue;
+                const long long sp = (long long)(uint32_t)e;
+                if (sp > prev && (pick == kEmpty || sp < (long long)(uint32_t)pick)) pick = e;
+            }
+            prev = (long long)(uint32_t)pick;
+            const int rpos = (int)(uint32_t)pick;
+            const uint32_t rel = qs ^ (uint32_t)((pick >> 32) & 1);
+            int f = kAniAlpha, first_r = rpos;
+            uint32_t cnt = 1, first_x = x - x0;
+            const uint32_t look = min(n_anchor, (uint32_t)kAniH);
+            for (uint32_t b = 1; b <= look; b++) {
+                const uint32_t slot = (n_anchor - b) % kAniH;
+                const int dq = qpos - RING(slot, 0);
+                if (dq > kAniBand) break;
+                const uint32_t meta = (uint32_t)RING(slot, 3);
+                if (dq <= 0 || (meta >> 31) != rel) continue;
+                const int rb = RING(slot, 1);
+                const int dr = rel ? rb - rpos : rpos - rb;
+                if (dr <= 0 || dr > kAniBand) continue;
+                const int gap = abs(dq - dr);
+                if (gap > kAniMaxGap) continue;
+                const int cand = RING(slot, 2) + kAniAlpha - gap;
+                if (cand > f) {
+                    f = cand; cnt = ((meta >> 16) & 0x7FFFu) + 1; first_x = meta & 0xFFFFu;
+                    first_r = RING(slot, 4);
+                }
+            }
+            const uint32_t slot = n_anchor % kAniH;
+            RING(slot, 0) = qpos; RING(slot, 1) = rpos; RING(slot, 2) = f;
+            RING(slot, 3) = (int)((rel << 31) | (cnt << 16) | first_x);
+            RING(slot, 4) = first_r;
+            n_anchor++;
+            if (f > best_f) {
+                best_f = f; best_cnt = cnt; best_first_x = first_x; best_last_x = x - x0;
+                best_first_r = first_r; best_last_r = rpos;
+            }
+        }
+    }
+#undef RING
+    if (best_cnt >= (uint32_t)kAniMinAnchors) {
+        const uint32_t N = best_last_x - best_first_x + 1;
+        uint32_t *acc = p.acc + 4 * (size_t)pair;
+        atomicAdd(&acc[0], best_cnt - 2);
+        atomicAdd(&acc[1], N - 2);
+        atomicAdd(&acc[2], qsp[x0 + best_last_x] - qsp[x0 + best_first_x] + kAniK);
+        atomicAdd(&acc[3], (uint32_t)abs(best_last_r - best_first_r) + kAniK);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
+                         uint64_t len_r, float min_af_pct, bool swapped) {
+    AniPairResult res;
+    double afq = len_q ? (double)cov_q / (double)len_q : 0.0, afr = len_r ? (double)cov_r / (double)len_r : 0.0;
+    afq = std::min(afq, 1.0); afr = std::min(afr, 1.0);
+    res.af_query = (float)afq; res.af_ref = (float)afr;
+    res.sum_m = sum_m; res.sum_n = sum_n; res.cov_q = cov_q; res.cov_r = cov_r; res.swapped = swapped ? 1u : 0u;
+    res.ani = 0.0f;
+    if (sum_n == 0 || sum_m == 0) return res;
+    const double ani = 100.0 * pow((double)sum_m / (double)sum_n, 1.0 / kAniK);
+    if (std::max(afq, afr) * 100.0 < (double)min_af_pct) return res;  // skani prints no row
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.2f", ani);  // skani prints {:.2}; galah parses the text as f32
+    res.ani = strtof(buf, nullptr);
+    return res;
+}
+
+AniIndex::~AniIndex() {
+    d_ks_.release(); d_spread_.release(); d_cso_.release(); d_table_.release();
+    d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
+    for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);
+}
+
+template <typename T>
+struct TmpBuf {
+    T *p = nullptr;
+    ~TmpBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); return 0; }
+    int upload(const std::vector<T> &v, cudaStream_t st) {
+        if (alloc(v.size())) return 2;
+        if (!v.empty()) GB_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+};
+
+int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
+                                size_t n, const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
+                                const std::vector<uint32_t> &contig_start, const std::vector<uint32_t> &contig_len,
+                                cudaStream_t st) {
+    if (n == 0) return 0;
+    if (base_off.size() != n + 1 || contig_off.size() != n + 1) { set_error("ani index: bad offset arrays"); return 3; }
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("ani index: base_off must be multiples of 128"); return 3; }
+    if (!ev_[0]) { GB_CUDA(cudaEventCreate(&ev_[0])); GB_CUDA(cudaEventCreate(&ev_[1])); }
+    int dev = 0, sms = kNumSMsFallback;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const uint64_t first = base_off[0], end = base_off[n];
+    const uint64_t n_words = (end - first) / 32;
+
+    // per-contig chunk bases, per-genome chunk counts and lengths (host)
+    std::vector<uint32_t> chunk_base(contig_start.size(), 0), n_chunks(n, 0);
+    std::vector<uint64_t> total_len(n, 0);
+    for (size_t g = 0; g < n; g++) {
+        uint32_t base = 0;
+        if (base_off[g + 1] - base_off[g] >= (1ull << 31)) { set_error("ani index: genome longer than 2^31 bases"); return 3; }
+        for (uint64_t c = contig_off[g]; c < contig_off[g + 1]; c++) {
+            chunk_base[c] = base;
+            base += (contig_len[c] + kAniChunk - 1) / kAniChunk;
+            total_len[g] += contig_len[c];
+        }
+        n_chunks[g] = base;
+    }
+
+    GB_CUDA(cudaEventRecord(ev_[0], st));
+    TmpBuf<uint32_t> d_sel, d_count, d_contig_start, d_chunk_base, d_chunk_tmp, d_nch;
+    TmpBuf<uint64_t> d_contig_off, d_seed_off_b, d_cso_off_b, d_table_off_b;
+    if (d_sel.alloc(n_words + 1) || d_count.alloc(n)) return 2;
+    const uint64_t thr = ~0ull / c_;
+    {
+        const uint64_t blocks = std::min<uint64_t>((end - first + 255) / 256, (uint64_t)sms * 32);
+        ani_mark_kernel<<<(uint32_t)std::max<uint64_t>(blocks, 1), 256, 0, st>>>(d_seq2, d_valid, first, end, thr, d_sel.p);
+        GB_LAUNCH_CHECK();
+        ani_count_kernel<<<(uint32_t)n, 256, 0, st>>>(d_sel.p, d_base_off, first, d_count.p);
+        GB_LAUNCH_CHECK();
+    }
+    std::vector<uint32_t> count(n);
+    GB_CUDA(cudaMemcpyAsync(count.data(), d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+
+    // absolute offsets of the new genomes in the index arrays
+    const size_t g0 = size();
+    std::vector<uint64_t> seed_off(n + 1), cso_off(n + 1), table_off(n + 1);
+    seed_off[0] = seed_off_.back(); cso_off[0] = cso_off_.back(); table_off[0] = table_off_.back();
+    for (size_t g = 0; g < n; g++) {
+        seed_off[g + 1] = seed_off[g] + count[g];
+        cso_off[g + 1] = cso_off[g] + n_chunks[g] + 1;
+        uint64_t slots = 16;
+        while (slots < 2ull * count[g]) slots <<= 1;
+        table_off[g + 1] = table_off[g] + slots;
+    }
+    if (d_ks_.reserve(seed_off[n] + 1, st) || d_spread_.reserve(seed_off[n] + 1, st) ||
+        d_cso_.reserve(cso_off[n] + 1, st) || d_table_.reserve(table_off[n] + 1, st) ||
+        d_seed_off_.reserve(g0 + n + 2, st) || d_cso_off_.reserve(g0 + n + 2, st) ||
+        d_table_off_.reserve(g0 + n + 2, st) || d_n_chunks_.reserve(g0 + n + 1, st))
+        return 2;
+    GB_CUDA(cudaMemsetAsync(d_table_.p + table_off[0], 0xFF, (table_off[n] - table_off[0]) * 8, st));
+    if (d_contig_start.upload(contig_start, st) || d_chunk_base.upload(chunk_base, st) ||
+        d_contig_off.upload(contig_off, st) || d_seed_off_b.upload(seed_off, st) ||
+        d_cso_off_b.upload(cso_off, st) || d_table_off_b.upload(table_off, st) || d_nch.upload(n_chunks, st) ||
+        d_chunk_tmp.alloc(seed_off[n] - seed_off[0] + 1))
+        return 2;
+    EmitParams e;
+    e.seq2 = d_seq2; e.valid = d_valid; e.sel = d_sel.p; e.base_off = d_base_off; e.first_base = first;
+    e.contig_off = d_contig_off.p; e.contig_start = d_contig_start.p; e.contig_chunk_base = d_chunk_base.p;
+    e.seed_off = d_seed_off_b.p; e.cso_off = d_cso_off_b.p; e.n_chunks = d_nch.p; e.table_off = d_table_off_b.p;
+    e.ks = d_ks_.p; e.spread = d_spread_.p; e.cso = d_cso_.p;
+    e.chunk_tmp = d_chunk_tmp.p - seed_off[0];  // indexed with absolute seed offsets
+    e.table = d_table_.p;
+    ani_emit_kernel<<<(uint32_t)n, 256, 0, st>>>(e);
+    GB_LAUNCH_CHECK();
+    // persistent per-genome metadata (device copies hold n+1 offsets: entry g0+n is the running end)
+    GB_CUDA(cudaMemcpyAsync(d_seed_off_.p + g0, seed_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_cso_off_.p + g0, cso_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_table_off_.p + g0, table_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_n_chunks_.p + g0, n_chunks.data(), n * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaEventRecord(ev_[1], st));
+    GB_CUDA(cudaStreamSynchronize(st));  // temporaries die here
+    float ms = 0.f;
+    GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+    last_build_ms = ms;
+    d_ks_.n = d_spread_.n = seed_off[n]; d_cso_.n = cso_off[n]; d_table_.n = table_off[n];
+    d_seed_off_.n = d_cso_off_.n = d_table_off_.n = g0 + n + 1; d_n_chunks_.n = g0 + n;
+    for (size_t g = 0; g < n; g++) {
+        seed_off_.push_back(seed_off[g + 1]); cso_off_.push_back(cso_off[g + 1]);
+        table_off_.push_back(table_off[g + 1]); n_chunks_.push_back(n_chunks[g]);
+        total_len_.push_back(total_len[g]);
+    }
+    return 0;
+}
+
+int AniIndex::genome_info(size_t g, uint64_t *n_seeds, uint32_t *n_chunks, uint64_t *total_len) const {
+    if (g >= size()) { set_error("ani index: genome out of range"); return 3; }
+    *n_seeds = seed_off_[g + 1] - seed_off_[g]; *n_chunks = n_chunks_[g]; *total_len = total_len_[g];
+    return 0;
+}
+
+int AniIndex::genome_seeds(size_t g, uint32_t *ks, uint32_t *spread, uint32_t *chunk_of_seed, size_t cap,
+                           cudaStream_t st) const {
+    if (g >= size()) { set_error("ani index: genome out of range"); return 3; }
+    const size_t ns = seed_off_[g + 1] - seed_off_[g];
+    if (cap < ns) { set_error("ani index: seed buffer too small"); return 3; }
+    std::vector<uint32_t> cso(n_chunks_[g] + 1);
+    GB_CUDA(cudaMemcpyAsync(ks, d_ks_.p + seed_off_[g], ns * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(spread, d_spread_.p + seed_off_[g], ns * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(cso.data(), d_cso_.p + cso_off_[g], cso.size() * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t t = 0; t < n_chunks_[g]; t++)
+        for (uint32_t x = cso[t]; x < cso[t + 1]; x++) chunk_of_seed[x] = t;
+    return 0;
+}
+
+int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, AniPairResult *out, cudaStream_t st) {
+    if (n_pairs == 0) return 0;
+    if (!ev_[0]) { GB_CUDA(cudaEventCreate(&ev_[0])); GB_CUDA(cudaEventCreate(&ev_[1])); }
+    std::vector<uint32_t> oriented(2 * n_pairs);
+    std::vector<uint8_t> swapped(n_pairs);
+    for (size_t x = 0; x < n_pairs; x++) {
+        const uint32_t a = pairs[2 * x], b = pairs[2 * x + 1];
+        if (a >= size() || b >= size()) { set_error("ani pairs: genome index out of range"); return 3; }
+        swapped[x] = total_len_[b] < total_len_[a];
+        oriented[2 * x] = swapped[x] ? b : a;
+        oriented[2 * x + 1] = swapped[x] ? a : b;
+    }
+    TmpBuf<uint32_t> d_pairs, d_acc;
+    if (d_pairs.upload(oriented, st) || d_acc.alloc(4 * n_pairs)) return 2;
+    GB_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * n_pairs, st));
+    const size_t smem = (size_t)kAniH * kRingFields * kChainThreads * sizeof(int);
+    GB_CUDA(cudaFuncSetAttribute(ani_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaEventRecord(ev_[0], st));
+    const size_t kBatch = 32768;
+    for (size_t b0 = 0; b0 < n_pairs; b0 += kBatch) {
+        const size_t nb = std::min(kBatch, n_pairs - b0);
+        uint32_t max_chunks = 0;
+        for (size_t x = b0; x < b0 + nb; x++) max_chunks = std::max(max_chunks, n_chunks_[oriented[2 * x]]);
+        if (max_chunks == 0) continue;
+        ChainParams p;
+        p.pairs = d_pairs.p + 2 * b0; p.ks = d_ks_.p; p.spread = d_spread_.p; p.cso = d_cso_.p;
+        p.table = d_table_.p; p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p; p.table_off = d_table_off_.p;
+        p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + 4 * b0;
+        dim3 grid((max_chunks + kChainThreads - 1) / kChainThreads, (uint32_t)nb);
+        ani_chain_kernel<<<grid, kChainThreads, smem, st>>>(p);
+        GB_LAUNCH_CHECK();
+    }
+    GB_CUDA(cudaEventRecord(ev_[1], st));
+    std::vector<uint32_t> acc(4 * n_pairs);
+    GB_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 16 * n_pairs, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+    last_chain_ms = ms;
+    for (size_t x = 0; x < n_pairs; x++) {
+        const uint32_t q = oriented[2 * x], r = oriented[2 * x + 1];
+        out[x] = ani_finish(acc[4 * x], acc[4 * x + 1], acc[4 * x + 2], acc[4 * x + 3], total_len_[q],
+                            total_len_[r], min_af_pct, swapped[x] != 0);
+    }
+    return 0;
+}
+
+template struct DevVec<uint32_t>;
+template struct DevVec<uint64_t>;
+template struct DevVec<unsigned long long>;
+
+}  // namespace gb200

@@ -1,0 +1,78 @@
+// Stage 2 (K3): FracMinHash seed-and-chain ANI on sm_100a.  Host-side interface.
+//
+// Replaces the per-pair `skani dist` subprocess of /root/reference/src/skani.rs:718-788.  The
+// algorithm (every constant and tie-break) is specified in oracle/skani_oracle.c's header; the
+// kernels are integer-only and are checked bit-exactly against that file, the final
+// 100 * (sumM / sumN)^(1/15) and the two-decimal print/parse are evaluated on the host.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace gb200 {
+
+constexpr int kAniK = 15;
+constexpr uint32_t kAniChunk = 20000;
+constexpr int kAniBand = 2500;
+constexpr int kAniMaxGap = 300;
+constexpr int kAniAlpha = 20;
+constexpr int kAniH = 32;
+constexpr int kAniMaxOcc = 8;
+constexpr int kAniMinAnchors = 3;
+
+struct AniPairResult {
+    float ani;            // what galah parses from skani's TSV column 3 (0.0 = no row)
+    float af_query, af_ref;
+    uint32_t sum_m, sum_n, cov_q, cov_r;
+    uint32_t swapped;     // 1 if the second genome of the pair was the query
+};
+
+// Growable device array.
+template <typename T>
+struct DevVec {
+    T *p = nullptr;
+    size_t n = 0, cap = 0;
+    int reserve(size_t need, cudaStream_t st);
+    void release() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
+};
+
+class AniIndex {
+public:
+    explicit AniIndex(uint32_t c) : c_(c) {}
+    ~AniIndex();
+    // Adds genomes from packed sequence that is already on the device (layout of K1).
+    // contig_off: n+1 offsets into contig_start/contig_len (positions relative to the genome's
+    // first base, ascending).  All host vectors.
+    int add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
+                          size_t n, const std::vector<uint64_t> &base_off_host,
+                          const std::vector<uint64_t> &contig_off, const std::vector<uint32_t> &contig_start,
+                          const std::vector<uint32_t> &contig_len, cudaStream_t st);
+    int pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, AniPairResult *out, cudaStream_t st);
+    size_t size() const { return total_len_.size(); }
+    uint32_t c() const { return c_; }
+    // parity hooks
+    int genome_info(size_t g, uint64_t *n_seeds, uint32_t *n_chunks, uint64_t *total_len) const;
+    int genome_seeds(size_t g, uint32_t *ks, uint32_t *spread, uint32_t *chunk_of_seed, size_t cap,
+                     cudaStream_t st) const;
+    float last_chain_ms = 0.f, last_build_ms = 0.f;
+
+private:
+    uint32_t c_;
+    // host copies of per-genome metadata
+    std::vector<uint64_t> seed_off_{0}, cso_off_{0}, table_off_{0}, total_len_;
+    std::vector<uint32_t> n_chunks_;
+    // device
+    DevVec<uint32_t> d_ks_, d_spread_, d_cso_;
+    DevVec<unsigned long long> d_table_;
+    DevVec<uint64_t> d_seed_off_, d_cso_off_, d_table_off_;
+    DevVec<uint32_t> d_n_chunks_;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+};
+
+// integers -> the f32 galah would parse (host; mirrors oracle/skani_oracle.c skani_oracle_finish)
+AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
+                         uint64_t len_r, float min_af_pct, bool swapped);
+
+}  // namespace gb200

@@ -123,6 +123,54 @@ int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani
                                uint32_t num_kmers, uint8_t kmer_length, int host_threads,
                                galah_b200_pair_t **out, size_t *n_out);
 
+/* ---- stage 2: ANI of genome pairs -----------------------------------------------------------
+ * Replaces ClusterDistanceFinder::calculate_ani for SkaniClusterer (src/skani.rs:689-788: one
+ * `skani dist --min-af X [--small-genomes] -q fasta1 -r fasta2` subprocess per pair, ANI = TSV
+ * column 3 parsed as f32, 0.0 when skani prints no row).  Genomes are indexed ONCE (FracMinHash
+ * seeds + hash table, resident in HBM) and any number of pairs is evaluated per call.  The method
+ * is a restatement of skani's published algorithm, specified in oracle/skani_oracle.c; numeric
+ * parity with the skani binary is unpinned. */
+typedef struct galah_b200_ani_index galah_b200_ani_index_t;
+typedef struct galah_b200_ani_result {
+    float ani;                /* percent, two decimals as skani prints; 0.0 = "no row" */
+    float af_query, af_ref;   /* aligned fractions (0..1) of the query / reference genome */
+    uint32_t sum_m, sum_n;    /* chained anchors / seeds in chained spans (end anchors excluded) */
+    uint32_t cov_q, cov_r;    /* bases covered by chains on the query / reference */
+    uint32_t swapped;         /* 1 if the pair's second genome was the (shorter) query */
+} galah_b200_ani_result_t;
+
+/* small_genomes != 0 selects c = 30 (skani --small-genomes, src/skani.rs:735-737), else c = 125 */
+int galah_b200_ani_index_create(int small_genomes, galah_b200_ani_index_t **out);
+void galah_b200_ani_index_free(galah_b200_ani_index_t *idx);
+/* Appends genomes; genome ids are assigned in order of addition, starting at 0. */
+int galah_b200_ani_index_add_files(galah_b200_ani_index_t *idx, const char *const *paths, size_t n,
+                                   int host_threads);
+/* Host packed sequence (layout of galah_b200_sketch_packed) plus contig tables: genome g has
+ * contigs contig_off[g]..contig_off[g+1], each [contig_start, contig_start + contig_len) relative
+ * to the genome's first base, separated by at least one invalid base. */
+int galah_b200_ani_index_add_packed(galah_b200_ani_index_t *idx, const uint32_t *seq2,
+                                    const uint32_t *valid, const uint64_t *base_off, size_t n,
+                                    const uint64_t *contig_off, const uint32_t *contig_start,
+                                    const uint32_t *contig_len);
+/* Device-resident packed genomes, one contig each of `lengths[g]` bases (synthetic inputs).
+ * base_off and lengths are HOST arrays (n+1 and n entries); d_* are device pointers. */
+int galah_b200_ani_index_add_packed_device(galah_b200_ani_index_t *idx, const uint32_t *d_seq2,
+                                           const uint32_t *d_valid, const uint64_t *d_base_off,
+                                           const uint64_t *base_off, const uint64_t *lengths,
+                                           size_t n, void *stream);
+size_t galah_b200_ani_index_size(const galah_b200_ani_index_t *idx);
+int galah_b200_ani_index_genome(const galah_b200_ani_index_t *idx, size_t g, uint64_t *n_seeds,
+                                uint32_t *n_chunks, uint64_t *total_len);
+/* Parity hook: the seeds of genome g in position order (kmer << 1 | strand, spread position,
+ * chunk id), cap >= n_seeds entries each. */
+int galah_b200_ani_index_seeds(const galah_b200_ani_index_t *idx, size_t g, uint32_t *kmer_strand,
+                               uint32_t *spread, uint32_t *chunk, size_t cap);
+/* pairs: 2 * n_pairs genome ids; results: n_pairs entries.  min_af_pct as skani's --min-af. */
+int galah_b200_ani_pairs(galah_b200_ani_index_t *idx, const uint32_t *pairs, size_t n_pairs,
+                         float min_af_pct, galah_b200_ani_result_t *results);
+/* Device time (CUDA events) of the last index batch build and the last pair evaluation. */
+int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_ms, float *chain_ms);
+
 /* ---- clustering engine (host logic) --------------------------------------------------------
  * Replaces the body of galah::clusterer::cluster() after the preclusterer has run
  * (src/clusterer.rs:56-151): partition_sketches (:452-487), preclusters largest first (:67-79),

@@ -174,3 +174,117 @@ def sketch_synth(seed, index_begin, n, length, k=21, s=1000, hash_seed=0):
     lib().oracle_sketch_synth_mt(seed, index_begin, n, length, k, s, hash_seed,
                                  _p(table, ctypes.c_uint64), _p(counts, ctypes.c_uint32))
     return table, counts
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 2 (skani_oracle.c)
+# ---------------------------------------------------------------------------------------------
+def _skani_sigs():
+    L = lib()
+    if getattr(L, "_skani_ready", False):
+        return L
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    L.oracle_load_codes.restype = ctypes.c_int
+    L.oracle_load_codes.argtypes = [ctypes.c_char_p, ctypes.POINTER(u8p), u64p, ctypes.POINTER(u64p),
+                                    ctypes.POINTER(u64p), u32p]
+    L.oracle_free.restype = None
+    L.oracle_free.argtypes = [ctypes.c_void_p]
+    L.skani_oracle_mm_hash64.restype = ctypes.c_uint64
+    L.skani_oracle_mm_hash64.argtypes = [ctypes.c_uint64]
+    L.skani_oracle_seeds.restype = ctypes.c_uint64
+    L.skani_oracle_seeds.argtypes = [u8p, ctypes.c_uint64, u64p, u64p, ctypes.c_uint32, ctypes.c_uint32,
+                                     u32p, u32p, u32p, ctypes.c_uint64, u32p, u64p]
+    L.skani_oracle_chain.restype = None
+    L.skani_oracle_chain.argtypes = [u32p, u32p, u32p, ctypes.c_uint64, u32p, u32p, ctypes.c_uint64, u64p]
+    L.skani_oracle_finish.restype = ctypes.c_float
+    L.skani_oracle_finish.argtypes = [ctypes.c_uint64] * 6 + [ctypes.c_float, ctypes.POINTER(ctypes.c_double),
+                                                              ctypes.POINTER(ctypes.c_double)]
+    L._skani_ready = True
+    return L
+
+
+def load_codes(path):
+    """(codes uint8[n] with 0..3 = ACGT, 4 = other; rec_start; rec_end) in packed coordinates."""
+    L = _skani_sigs()
+    codes = ctypes.POINTER(ctypes.c_uint8)()
+    rs = ctypes.POINTER(ctypes.c_uint64)()
+    re_ = ctypes.POINTER(ctypes.c_uint64)()
+    n = ctypes.c_uint64(0)
+    nrec = ctypes.c_uint32(0)
+    rc = L.oracle_load_codes(os.fsencode(path), ctypes.byref(codes), ctypes.byref(n), ctypes.byref(rs),
+                             ctypes.byref(re_), ctypes.byref(nrec))
+    if rc:
+        raise RuntimeError(f"oracle_load_codes({path}) rc={rc}")
+    try:
+        c = np.ctypeslib.as_array(codes, shape=(max(n.value, 1),))[: n.value].copy()
+        s = np.ctypeslib.as_array(rs, shape=(max(nrec.value, 1),))[: nrec.value].copy()
+        e = np.ctypeslib.as_array(re_, shape=(max(nrec.value, 1),))[: nrec.value].copy()
+    finally:
+        L.oracle_free(codes); L.oracle_free(rs); L.oracle_free(re_)
+    return c, s, e
+
+
+def codes_from_ascii(seq: bytes):
+    """One record of raw ACGT bytes -> (codes, rec_start, rec_end)."""
+    lut = np.full(256, 4, np.uint8)
+    for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        lut[ch] = v
+    c = lut[np.frombuffer(seq, np.uint8)]
+    return c, np.array([0], np.uint64), np.array([len(c)], np.uint64)
+
+
+class AniGenome:
+    """Seeds of one genome under the skani_oracle.c specification."""
+
+    def __init__(self, codes, rec_start, rec_end, c=125):
+        L = _skani_sigs()
+        codes = np.ascontiguousarray(codes, np.uint8)
+        rs = np.ascontiguousarray(rec_start, np.uint64)
+        re_ = np.ascontiguousarray(rec_end, np.uint64)
+        cap = max(1024, int(len(codes) // c * 2 + 1024))
+        while True:
+            ks = np.zeros(cap, np.uint32); sp = np.zeros(cap, np.uint32); ch = np.zeros(cap, np.uint32)
+            nch = ctypes.c_uint32(0); tl = ctypes.c_uint64(0)
+            n = L.skani_oracle_seeds(_p(codes, ctypes.c_uint8), len(codes), _p(rs, ctypes.c_uint64),
+                                     _p(re_, ctypes.c_uint64), len(rs), c, _p(ks, ctypes.c_uint32),
+                                     _p(sp, ctypes.c_uint32), _p(ch, ctypes.c_uint32), cap,
+                                     ctypes.byref(nch), ctypes.byref(tl))
+            if n <= cap:
+                break
+            cap = int(n)
+        self.kmer_strand, self.spread, self.chunk = ks[:n].copy(), sp[:n].copy(), ch[:n].copy()
+        self.n_chunks, self.total_len = nch.value, tl.value
+
+    @classmethod
+    def from_file(cls, path, c=125):
+        return cls(*load_codes(path), c=c)
+
+
+def ani_pair_integers(a: "AniGenome", b: "AniGenome"):
+    """(sumM, sumN, covq, covr, len_q, len_r, swapped): query = the shorter genome (ties: a)."""
+    L = _skani_sigs()
+    swapped = b.total_len < a.total_len
+    q, r = (b, a) if swapped else (a, b)
+    out = np.zeros(4, np.uint64)
+    L.skani_oracle_chain(_p(q.kmer_strand, ctypes.c_uint32), _p(q.spread, ctypes.c_uint32),
+                         _p(q.chunk, ctypes.c_uint32), len(q.kmer_strand),
+                         _p(r.kmer_strand, ctypes.c_uint32), _p(r.spread, ctypes.c_uint32),
+                         len(r.kmer_strand), _p(out, ctypes.c_uint64))
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3]), q.total_len, r.total_len, swapped
+
+
+def ani_finish(sumM, sumN, covq, covr, len_q, len_r, min_af_pct):
+    """-> (ani f32 as galah parses it, af_q, af_r, unrounded ani)."""
+    L = _skani_sigs()
+    af = (ctypes.c_double * 2)()
+    un = ctypes.c_double(0)
+    v = L.skani_oracle_finish(sumM, sumN, covq, covr, len_q, len_r, ctypes.c_float(min_af_pct), af,
+                              ctypes.byref(un))
+    return np.float32(v), af[0], af[1], un.value
+
+
+def ani_pair(a, b, min_af_pct=15.0):
+    ints = ani_pair_integers(a, b)
+    return ani_finish(*ints[:6], min_af_pct)

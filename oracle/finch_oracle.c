@@ -417,3 +417,46 @@ int oracle_sketch_synth_mt(uint64_t seed, uint64_t index_begin, uint64_t n, uint
         oracle_sketch_synth(seed, index_begin + g, L, k, s, hash_seed, hashes + g * (uint64_t)s, &counts[g]);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Per-base codes of a FASTA/FASTQ file, in the packed coordinate system the product uses      */
+/* (galah_b200/csrc/host/fasta.cpp): records concatenated, ONE invalid base between records,   */
+/* whitespace dropped, 0..3 = ACGT (after normalize(false)), 4 = any other base.               */
+/* Used by skani_oracle.c.  Caller frees *codes, *rec_start, *rec_end with oracle_free().       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { bytes_t codes; uint64_t *rs, *re; uint32_t nrec, cap; } codes_ctx;
+static void codes_cb(void *c, const uint8_t *seq, size_t len) {
+    codes_ctx *x = (codes_ctx *)c;
+    norm_init();
+    if (x->nrec == x->cap) {
+        x->cap = x->cap ? x->cap * 2 : 64;
+        x->rs = (uint64_t *)realloc(x->rs, x->cap * sizeof(uint64_t));
+        x->re = (uint64_t *)realloc(x->re, x->cap * sizeof(uint64_t));
+    }
+    if (x->nrec > 0) { uint8_t sep = 4; bytes_push(&x->codes, &sep, 1); }
+    x->rs[x->nrec] = x->codes.n;
+    uint8_t buf[4096]; size_t m = 0;
+    for (size_t i = 0; i < len; i++) {
+        uint8_t ch = norm_table[seq[i]];
+        if (ch == 0) continue;
+        int code = base_code(ch);
+        buf[m++] = code < 0 ? 4 : (uint8_t)code;
+        if (m == sizeof(buf)) { bytes_push(&x->codes, buf, m); m = 0; }
+    }
+    if (m) bytes_push(&x->codes, buf, m);
+    x->re[x->nrec] = x->codes.n;
+    x->nrec++;
+}
+int oracle_load_codes(const char *path, uint8_t **codes, uint64_t *n, uint64_t **rec_start,
+                      uint64_t **rec_end, uint32_t *nrec) {
+    bytes_t b = {0, 0, 0};
+    int rc = slurp(path, &b);
+    if (rc) { free(b.d); return 10 + rc; }
+    codes_ctx x; memset(&x, 0, sizeof(x));
+    rc = for_each_record(b.d, b.n, codes_cb, &x);
+    free(b.d);
+    if (rc) { free(x.codes.d); free(x.rs); free(x.re); return 20 + rc; }
+    *codes = x.codes.d; *n = x.codes.n; *rec_start = x.rs; *rec_end = x.re; *nrec = x.nrec;
+    return 0;
+}
+void oracle_free(void *p) { free(p); }
