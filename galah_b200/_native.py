@@ -34,6 +34,11 @@ class AniResult(ctypes.Structure):
                 ("cov_r", ctypes.c_uint32), ("swapped", ctypes.c_uint32)]
 
 
+class ClusterStats(ctypes.Structure):
+    _fields_ = [("n_precluster_hits", ctypes.c_uint64), ("n_ani_pairs", ctypes.c_uint64),
+                ("ani_chain_ms", ctypes.c_float)]
+
+
 ANI_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                           ctypes.POINTER(ctypes.c_float))
 
@@ -89,6 +94,9 @@ _SIGNATURES = {
                                                          ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                                          ANI_FN, vp, ctypes.POINTER(Clusters)]),
     "galah_b200_clusters_free": (None, [ctypes.POINTER(Clusters)]),
+    "galah_b200_cluster_files": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                ctypes.c_int, ctypes.c_int, ctypes.POINTER(Clusters),
+                                                ctypes.POINTER(ClusterStats)]),
     "galah_b200_synth_packed_device": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
                                                       ctypes.c_uint64, vp, vp, vp, vp]),
 }

@@ -247,6 +247,33 @@ def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, s
     return clusters, info
 
 
+def _take_clusters(res):
+    try:
+        off = [res.offsets[x] for x in range(res.n_clusters + 1)]
+        clusters = [[int(res.members[y]) for y in range(off[x], off[x + 1])] for x in range(res.n_clusters)]
+        info = {"ani_calls": int(res.ani_calls), "n_preclusters": int(res.n_preclusters),
+                "largest_precluster": int(res.largest_precluster)}
+    finally:
+        lib().galah_b200_clusters_free(ctypes.byref(res))
+    return clusters, info
+
+
+def cluster(genomes, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0, small_genomes=False, threads=0):
+    """galah::clusterer::cluster() with FinchPreclusterer + SkaniClusterer (reference
+    src/clusterer.rs:14-152), entirely on the GPU path.  precluster_ani is a FRACTION (finch),
+    ani and min_aligned_fraction are PERCENTAGES (skani), as in the reference's structs.
+    Returns (clusters, info): clusters as lists of indices into `genomes`, representative first."""
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    check(lib().galah_b200_cluster_files(_paths_array(genomes), len(genomes), ctypes.c_float(precluster_ani),
+                                         ctypes.c_float(ani), ctypes.c_float(min_aligned_fraction),
+                                         int(bool(small_genomes)), threads, ctypes.byref(res), ctypes.byref(stats)))
+    clusters, info = _take_clusters(res)
+    info.update(n_precluster_hits=int(stats.n_precluster_hits), n_ani_pairs=int(stats.n_ani_pairs),
+                ani_chain_ms=float(stats.ani_chain_ms))
+    return clusters, info
+
+
 def synth_layout(n, length):
     """Sizes (in uint32 / uint64 elements) of the packed buffers for n synthetic genomes."""
     padded = (length + 127) // 128 * 128

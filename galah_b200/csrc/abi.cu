@@ -119,35 +119,94 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
     return 0;
 }
 
-// Sketch a set of packed genomes that live on the host; results land in host rows.
-static int sketch_packed_host(const std::vector<const PackedGenome *> &genomes, int k, uint32_t s,
-                              uint64_t seed, uint64_t *hashes, uint32_t *counts) {
-    const size_t n = genomes.size();
-    if (n == 0) return 0;
-    std::vector<uint64_t> base_off(n + 1, 0);
-    for (size_t g = 0; g < n; g++) base_off[g + 1] = base_off[g] + genomes[g]->padded_bases();
-    const uint64_t total = base_off[n];
-    std::vector<uint32_t> seq2(total / 16 + 4, 0u), valid(total / 32 + 4, 0u);
-    for (size_t g = 0; g < n; g++) {
-        const uint64_t pb = genomes[g]->padded_bases();
-        memcpy(seq2.data() + base_off[g] / 16, genomes[g]->seq2.data(), pb / 16 * 4);
-        memcpy(valid.data() + base_off[g] / 32, genomes[g]->valid.data(), pb / 32 * 4);
-    }
-    DevBuf<uint32_t> d_seq2, d_valid, d_counts;
-    DevBuf<uint64_t> d_off, d_hashes;
-    if (d_seq2.alloc(seq2.size()) || d_valid.alloc(valid.size()) || d_off.alloc(n + 1) ||
-        d_hashes.alloc(n * (size_t)s) || d_counts.alloc(n))
-        return GALAH_B200_ERR_CUDA;
+// One pass over FASTA files feeding K1 (sketches) and/or the K3 index from the SAME upload:
+// files are parsed and packed on host threads, a batch is concatenated (genome offsets multiples
+// of 128), copied to the device once, and handed to the requested sinks.
+struct IngestSinks {
+    bool sketch = false;
+    int k = 21; uint32_t s = 1000; uint64_t seed = 0;
+    uint64_t *hashes = nullptr; uint32_t *counts = nullptr;  // host rows, stride s
+    AniIndex *ani = nullptr;
+};
+
+static int ingest_files(const char *const *paths, size_t n, int host_threads, const IngestSinks &sinks) {
+    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const size_t kMaxBatchGenomes = 512;
+    const uint64_t kMaxBatchBases = 2ull << 30;
     cudaStream_t st = g_ctx.stream;
-    GB_CUDA(cudaMemcpyAsync(d_seq2.p, seq2.data(), seq2.size() * 4, cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(d_valid.p, valid.data(), valid.size() * 4, cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(d_off.p, base_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, n, k, s, seed, d_hashes.p,
-                            d_counts.p, s, st);
-    if (rc) return rc;
-    GB_CUDA(cudaMemcpyAsync(hashes, d_hashes.p, n * (size_t)s * 8, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaMemcpyAsync(counts, d_counts.p, n * 4, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaStreamSynchronize(st));
+    size_t done = 0;
+    while (done < n) {
+        const size_t want = std::min(kMaxBatchGenomes, n - done);
+        std::vector<PackedGenome> batch(want);
+        std::vector<std::string> errs(want);
+        std::vector<int> rcs(want, 0);
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                size_t x = next.fetch_add(1);
+                if (x >= want) break;
+                rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
+            }
+        };
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
+        for (int t = 1; t < nt; t++) th.emplace_back(worker);
+        worker();
+        for (auto &t : th) t.join();
+        for (size_t x = 0; x < want; x++)
+            if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
+        size_t b0 = 0;
+        while (b0 < want) {  // split further if the batch is too large for one upload
+            size_t b1 = b0; uint64_t bases = 0;
+            while (b1 < want && (b1 == b0 || bases + batch[b1].padded_bases() <= kMaxBatchBases)) {
+                bases += batch[b1].padded_bases(); b1++;
+            }
+            const size_t nb = b1 - b0;
+            std::vector<uint64_t> base_off(nb + 1, 0), contig_off(nb + 1, 0);
+            std::vector<uint32_t> cs, cl;
+            for (size_t x = 0; x < nb; x++) {
+                const PackedGenome &pg = batch[b0 + x];
+                base_off[x + 1] = base_off[x] + pg.padded_bases();
+                for (size_t r = 0; r < pg.rec_start.size(); r++) {
+                    cs.push_back((uint32_t)pg.rec_start[r]);
+                    cl.push_back((uint32_t)(pg.rec_end[r] - pg.rec_start[r]));
+                }
+                contig_off[x + 1] = cs.size();
+            }
+            const uint64_t total = base_off[nb];
+            std::vector<uint32_t> seq2(total / 16 + 4, 0u), valid(total / 32 + 4, 0u);
+            for (size_t x = 0; x < nb; x++) {
+                const PackedGenome &pg = batch[b0 + x];
+                memcpy(seq2.data() + base_off[x] / 16, pg.seq2.data(), pg.padded_bases() / 16 * 4);
+                memcpy(valid.data() + base_off[x] / 32, pg.valid.data(), pg.padded_bases() / 32 * 4);
+            }
+            DevBuf<uint32_t> d_seq2, d_valid;
+            DevBuf<uint64_t> d_off;
+            if (d_seq2.alloc(seq2.size()) || d_valid.alloc(valid.size()) || d_off.alloc(nb + 1)) return GALAH_B200_ERR_CUDA;
+            GB_CUDA(cudaMemcpyAsync(d_seq2.p, seq2.data(), seq2.size() * 4, cudaMemcpyHostToDevice, st));
+            GB_CUDA(cudaMemcpyAsync(d_valid.p, valid.data(), valid.size() * 4, cudaMemcpyHostToDevice, st));
+            GB_CUDA(cudaMemcpyAsync(d_off.p, base_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (sinks.sketch) {
+                DevBuf<uint64_t> d_hashes;
+                DevBuf<uint32_t> d_counts;
+                if (d_hashes.alloc(nb * (size_t)sinks.s) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
+                int rc = sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, nb, sinks.k, sinks.s, sinks.seed,
+                                        d_hashes.p, d_counts.p, sinks.s, st);
+                if (rc) return rc;
+                GB_CUDA(cudaMemcpyAsync(sinks.hashes + (done + b0) * (size_t)sinks.s, d_hashes.p,
+                                        nb * (size_t)sinks.s * 8, cudaMemcpyDeviceToHost, st));
+                GB_CUDA(cudaMemcpyAsync(sinks.counts + done + b0, d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
+                GB_CUDA(cudaStreamSynchronize(st));
+            }
+            if (sinks.ani) {
+                int rc = sinks.ani->add_packed_device(d_seq2.p, d_valid.p, d_off.p, nb, base_off, contig_off, cs, cl, st);
+                if (rc) return rc;
+            }
+            GB_CUDA(cudaStreamSynchronize(st));
+            b0 = b1;
+        }
+        done += want;
+    }
     return 0;
 }
 
@@ -253,47 +312,9 @@ int galah_b200_sketch_files(const char *const *paths, size_t n, uint8_t k, uint3
     std::lock_guard<std::mutex> lock(g_mu);
     if (int rc = require_ctx()) return rc;
     if (s & 1) { set_error("sketch_files: s must be even (row stride alignment)"); return GALAH_B200_ERR_ARG; }
-    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    // Batches bounded by genome count and packed size; parse on host threads, sketch on the GPU.
-    const size_t kMaxBatchGenomes = 512;
-    const uint64_t kMaxBatchBases = 3ull << 30;
-    size_t done = 0;
-    while (done < n) {
-        const size_t want = std::min(kMaxBatchGenomes, n - done);
-        std::vector<PackedGenome> batch(want);
-        std::vector<std::string> errs(want);
-        std::vector<int> rcs(want, 0);
-        std::atomic<size_t> next{0};
-        auto worker = [&]() {
-            for (;;) {
-                size_t x = next.fetch_add(1);
-                if (x >= want) break;
-                rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
-            }
-        };
-        std::vector<std::thread> th;
-        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
-        for (int t = 1; t < nt; t++) th.emplace_back(worker);
-        worker();
-        for (auto &t : th) t.join();
-        for (size_t x = 0; x < want; x++)
-            if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
-        // split the batch further if it is too large for one upload
-        size_t b0 = 0;
-        while (b0 < want) {
-            size_t b1 = b0; uint64_t bases = 0;
-            while (b1 < want && (b1 == b0 || bases + batch[b1].padded_bases() <= kMaxBatchBases)) {
-                bases += batch[b1].padded_bases(); b1++;
-            }
-            std::vector<const PackedGenome *> ptrs;
-            for (size_t x = b0; x < b1; x++) ptrs.push_back(&batch[x]);
-            int rc = sketch_packed_host(ptrs, k, s, seed, hashes + (done + b0) * (size_t)s, counts + done + b0);
-            if (rc) return rc;
-            b0 = b1;
-        }
-        done += want;
-    }
-    return 0;
+    IngestSinks sinks;
+    sinks.sketch = true; sinks.k = k; sinks.s = s; sinks.seed = seed; sinks.hashes = hashes; sinks.counts = counts;
+    return ingest_files(paths, n, host_threads, sinks);
 }
 
 int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
@@ -422,61 +443,9 @@ int galah_b200_ani_index_add_files(galah_b200_ani_index_t *idx, const char *cons
     std::lock_guard<std::mutex> lock(g_mu);
     if (int rc = require_ctx()) return rc;
     if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
-    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    const size_t kMaxBatchGenomes = 256;
-    const uint64_t kMaxBatchBases = 2ull << 30;
-    size_t done = 0;
-    while (done < n) {
-        const size_t want = std::min(kMaxBatchGenomes, n - done);
-        std::vector<PackedGenome> batch(want);
-        std::vector<std::string> errs(want);
-        std::vector<int> rcs(want, 0);
-        std::atomic<size_t> next{0};
-        auto worker = [&]() {
-            for (;;) {
-                size_t x = next.fetch_add(1);
-                if (x >= want) break;
-                rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
-            }
-        };
-        std::vector<std::thread> th;
-        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
-        for (int t = 1; t < nt; t++) th.emplace_back(worker);
-        worker();
-        for (auto &t : th) t.join();
-        for (size_t x = 0; x < want; x++)
-            if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
-        size_t b0 = 0;
-        while (b0 < want) {
-            size_t b1 = b0; uint64_t bases = 0;
-            while (b1 < want && (b1 == b0 || bases + batch[b1].padded_bases() <= kMaxBatchBases)) {
-                bases += batch[b1].padded_bases(); b1++;
-            }
-            const size_t nb = b1 - b0;
-            std::vector<uint64_t> base_off(nb + 1, 0), contig_off(nb + 1, 0);
-            std::vector<uint32_t> cs, cl;
-            for (size_t x = 0; x < nb; x++) {
-                const PackedGenome &pg = batch[b0 + x];
-                base_off[x + 1] = base_off[x] + pg.padded_bases();
-                for (size_t r = 0; r < pg.rec_start.size(); r++) {
-                    cs.push_back((uint32_t)pg.rec_start[r]);
-                    cl.push_back((uint32_t)(pg.rec_end[r] - pg.rec_start[r]));
-                }
-                contig_off[x + 1] = cs.size();
-            }
-            std::vector<uint32_t> seq2(base_off[nb] / 16 + 4, 0u), valid(base_off[nb] / 32 + 4, 0u);
-            for (size_t x = 0; x < nb; x++) {
-                const PackedGenome &pg = batch[b0 + x];
-                memcpy(seq2.data() + base_off[x] / 16, pg.seq2.data(), pg.padded_bases() / 16 * 4);
-                memcpy(valid.data() + base_off[x] / 32, pg.valid.data(), pg.padded_bases() / 32 * 4);
-            }
-            int rc = ani_add_packed_host(idx, seq2.data(), valid.data(), base_off, contig_off, cs, cl);
-            if (rc) return rc;
-            b0 = b1;
-        }
-        done += want;
-    }
-    return 0;
+    IngestSinks sinks;
+    sinks.ani = &idx->impl;
+    return ingest_files(paths, n, host_threads, sinks);
 }
 
 int galah_b200_ani_index_genome(const galah_b200_ani_index_t *idx, size_t g, uint64_t *n_seeds,
@@ -537,6 +506,63 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
     out->n_preclusters = res.n_preclusters;
     out->largest_precluster = res.largest_precluster;
     return 0;
+}
+
+int galah_b200_cluster_files(const char *const *paths, size_t n, float precluster_min_ani, float ani_threshold_pct,
+                             float min_af_pct, int small_genomes, int host_threads,
+                             galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (!out) { set_error("cluster_files: out is NULL"); return GALAH_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    // SkaniClusterer::initialise (src/skani.rs:696-698) asserts a percentage
+    if (!(ani_threshold_pct > 1.0f)) { set_error("assertion failed: self.threshold > 1.0"); return GALAH_B200_ERR_UNSUPPORTED; }
+    const uint32_t s = 1000;  // FinchPreclusterer{num_kmers: 1000, kmer_length: 21}, cluster_argument_parsing.rs:1301-1302
+    const uint8_t k = 21;
+    std::vector<uint64_t> hashes((size_t)n * s);
+    std::vector<uint32_t> counts(n);
+    galah_b200_ani_index_t *idx = nullptr;
+    if (int rc = galah_b200_ani_index_create(small_genomes, &idx)) return rc;
+    struct Guard { galah_b200_ani_index_t *i; ~Guard() { galah_b200_ani_index_free(i); } } guard{idx};
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (int rc = require_ctx()) return rc;
+        IngestSinks sinks;
+        sinks.sketch = true; sinks.k = k; sinks.s = s; sinks.seed = 0; sinks.hashes = hashes.data();
+        sinks.counts = counts.data(); sinks.ani = &idx->impl;
+        if (int rc = ingest_files(paths, n, host_threads, sinks)) return rc;
+    }
+    galah_b200_pair_t *hits = nullptr;
+    size_t n_hits = 0;
+    if (int rc = galah_b200_prefilter(hashes.data(), counts.data(), n, s, k, precluster_min_ani, &hits, &n_hits)) return rc;
+    struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
+    // stage 2 for every precluster hit (a superset of what the reference's find_any evaluates;
+    // the greedy decisions only ever read values of hit pairs, so the clusters are the same)
+    std::vector<uint32_t> pairs(2 * n_hits);
+    for (size_t x = 0; x < n_hits; x++) { pairs[2 * x] = hits[x].i; pairs[2 * x + 1] = hits[x].j; }
+    std::vector<galah_b200_ani_result_t> res(n_hits);
+    if (int rc = galah_b200_ani_pairs(idx, pairs.data(), n_hits, min_af_pct, res.data())) return rc;
+    struct Table { const galah_b200_pair_t *hits; size_t n; const galah_b200_ani_result_t *res; } table{hits, n_hits, res.data()};
+    auto lookup = [](void *ctx, uint32_t rep, uint32_t genome, float *ani) -> int {
+        const Table *t = (const Table *)ctx;
+        const uint32_t a = std::min(rep, genome), b = std::max(rep, genome);
+        size_t lo = 0, hi = t->n;  // hits are sorted by (i, j)
+        while (lo < hi) {
+            const size_t mid = (lo + hi) >> 1;
+            if (t->hits[mid].i < a || (t->hits[mid].i == a && t->hits[mid].j < b)) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= t->n || t->hits[lo].i != a || t->hits[lo].j != b) return 0;
+        *ani = t->res[lo].ani;  // skani never yields None (src/skani.rs:760: 0.0 when no row)
+        return 1;
+    };
+    int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, lookup, &table, out);
+    if (stats) {
+        stats->n_precluster_hits = n_hits;
+        stats->n_ani_pairs = n_hits;
+        float b = 0, c = 0;
+        galah_b200_ani_last_timing(idx, &b, &c);
+        stats->ani_chain_ms = c;
+    }
+    return rc;
 }
 
 void galah_b200_clusters_free(galah_b200_clusters_t *c) {

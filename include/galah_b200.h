@@ -199,6 +199,23 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
                                       galah_b200_clusters_t *out);
 void galah_b200_clusters_free(galah_b200_clusters_t *c);
 
+/* The whole hot path: galah::clusterer::cluster(genomes, &FinchPreclusterer{min_ani:
+ * precluster_min_ani (FRACTION), num_kmers: 1000, kmer_length: 21}, &SkaniClusterer{threshold:
+ * ani_threshold_pct (PERCENT), min_aligned_threshold: min_af_pct / 100, small_genomes}, false,
+ * None, None) (src/clusterer.rs:14-152 as called from src/cluster_argument_parsing.rs:1514-1530).
+ * Every file is read and uploaded once; K1 sketches and the K3 index are built from the same
+ * device buffers; K2 gives the precluster hits; K3 evaluates every hit pair; the host engine
+ * does the greedy selection.  Cluster order is the reference's at --threads 1. */
+typedef struct galah_b200_cluster_stats {
+    uint64_t n_precluster_hits;
+    uint64_t n_ani_pairs;
+    float ani_chain_ms;
+} galah_b200_cluster_stats_t;
+int galah_b200_cluster_files(const char *const *paths, size_t n, float precluster_min_ani,
+                             float ani_threshold_pct, float min_af_pct, int small_genomes,
+                             int host_threads, galah_b200_clusters_t *out,
+                             galah_b200_cluster_stats_t *stats);
+
 /* ---- synthetic genomes (bench / tests) ------------------------------------- */
 /* Generates genomes [index_begin, index_begin+n) of `length` bases each directly in packed
  * form on the device.  d_seq2 needs n * words_per_genome uint32 with

@@ -141,3 +141,11 @@ def test_committed_real_genomes_reproduce_reference_clusters(gb):
     assert [sorted(c) for c in c95] == [[0, 1, 2, 3]]
     assert sorted(sorted(c) for c in c99) == [[0, 1, 3], [2]]
     idx.close()
+    # the same through the one-call drop-in for galah::clusterer::cluster()
+    c95, info = gb.cluster(paths, precluster_ani=0.9, ani=95.0, min_aligned_fraction=20.0)
+    assert c95 == [[0, 1, 2, 3]] and info["n_precluster_hits"] == 6 and info["n_preclusters"] == 1
+    c99, _ = gb.cluster(paths, precluster_ani=0.9, ani=99.0, min_aligned_fraction=20.0)
+    assert c99 == [[0, 1, 3], [2]]  # representative first, clusters in representative order
+    with pytest.raises(gb.GalahB200Error) as e:
+        gb.cluster(paths, ani=0.95)  # SkaniClusterer::initialise asserts a percentage (src/skani.rs:696-698)
+    assert "threshold > 1.0" in str(e.value)
