@@ -385,7 +385,7 @@ def main():
                                    f"{' scaled by sqrt(G) genomes' if world > 1 else ''})",
                        "pairs_per_step": pairs, "mode": args.mode,
                        "l2": "flushed between timed iterations (256 MiB write)",
-                       "sharding": "cyclic row blocks of 64; NCCL all-gather of the sketch table inside the step"
+                       "sharding": "boustrophedon row blocks of 64; NCCL all-gather of the sketch table inside the step"
                                    if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

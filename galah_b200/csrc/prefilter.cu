@@ -251,8 +251,8 @@ static size_t tiled_smem_bytes(size_t stride) {
     return (size_t)(kRowBlock + 2 * kColBlock) * stride * 8 + 3 * 8;
 }
 
-// Work list of one shard: the shard owns the kShardRows-row groups g = shard, shard + n_shards,
-// ... (cyclic, so the triangular pair area is balanced); a row block of `block_rows` rows
+// Work list of one shard: the shard owns the kShardRows-row groups that shard_of_group() gives it
+// (boustrophedon, so the triangular pair area is balanced); a row block of `block_rows` rows
 // (block_rows divides kShardRows) belongs to the group it lies in.  An item is `chunk_blocks`
 // consecutive column blocks starting at the row block's own index.
 static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_rows, uint32_t chunk_blocks,
@@ -262,7 +262,7 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
     std::vector<uint32_t> local;
     std::vector<uint64_t> prefix(1, 0);
     for (uint32_t rb = 0; rb < nrb; rb++) {
-        if ((rb / per_group) % n_shards != shard) continue;
+        if (shard_of_group(rb / per_group, n_shards) != shard) continue;
         local.push_back(rb);
         prefix.push_back(prefix.back() + (nrb - rb + chunk_blocks - 1) / chunk_blocks);
     }
@@ -323,7 +323,7 @@ int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
     {
         const uint32_t per_group = kShardRows / kRowBlock;
         for (uint32_t rb = 0; rb < p.n_row_blocks; rb++)
-            if ((rb / per_group) % n_shards == shard) n_items += (p.n_row_blocks - rb + kColChunk - 1) / kColChunk;
+            if (shard_of_group(rb / per_group, n_shards) == shard) n_items += (p.n_row_blocks - rb + kColChunk - 1) / kColChunk;
     }
     const size_t smem = tiled_smem_bytes(stride);
     if (ws.record(1, stream)) return 2;

@@ -23,6 +23,13 @@ PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani);
 
 // Sharding granularity in rows == sketches per block list (== GALAH_B200_ROW_BLOCK).
 constexpr int kShardRows = 64;
+// Owner of row group `group` (kShardRows rows) among n_shards: boustrophedon order
+// 0,1,..,G-1,G-1,..,1,0,0,1,.. so that the triangular pair area (row i has n-1-i pairs) is
+// balanced to within one group per two rounds.
+inline uint32_t shard_of_group(uint32_t group, uint32_t n_shards) {
+    const uint32_t round = group / n_shards, pos = group % n_shards;
+    return (round & 1u) ? n_shards - 1 - pos : pos;
+}
 // pairwise tiled merge kernel (mode 1)
 constexpr int kRowBlock = 8;    // rows resident per work item (divides kShardRows)
 constexpr int kColBlock = 8;    // columns streamed per TMA stage

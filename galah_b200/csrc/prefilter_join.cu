@@ -359,7 +359,7 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
     if (int rc = upload_join_work_list(ws, n, shard, n_shards, stream, p)) return rc;
     if (p.n_local_rb == 0) return 0;
     uint64_t n_items = 0;
-    for (uint32_t rb = shard; rb < nb; rb += n_shards) n_items += nb - rb;
+    for (uint32_t rb = 0; rb < nb; rb++) if (shard_of_group(rb, n_shards) == shard) n_items += nb - rb;
     const size_t smem = sizeof(JoinSmem);
     GB_CUDA(cudaFuncSetAttribute(prefilter_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm);

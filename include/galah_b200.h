@@ -85,9 +85,10 @@ int galah_b200_sketch_packed_device(const uint32_t *d_seq2, const uint32_t *d_va
 int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t n, size_t stride,
                          uint8_t k, float min_ani, galah_b200_pair_t **out, size_t *n_out);
 
-/* Row-sharded variants for multi-GPU runs: the call covers row blocks
- * rb = shard, shard + n_shards, ... (blocks of GALAH_B200_ROW_BLOCK rows), which balances the
- * triangular pair area across shards.  _shard takes host pointers, _device device pointers;
+/* Row-sharded variants for multi-GPU runs: the call covers the row blocks (of
+ * GALAH_B200_ROW_BLOCK rows) that the boustrophedon rule gives `shard`: block b belongs to
+ * shard p = b % n_shards in even rounds (b / n_shards) and n_shards-1-p in odd rounds, which
+ * balances the triangular pair area across shards.  _shard takes host pointers, _device device pointers;
  * result pairs always land on the HOST. */
 #define GALAH_B200_ROW_BLOCK 64
 int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, size_t n,

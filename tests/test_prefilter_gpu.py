@@ -154,9 +154,10 @@ def test_row_shards_partition_the_pair_list(gb):
         allp = np.concatenate(parts)
         allp = allp[np.lexsort((allp["j"], allp["i"]))]
         assert_pairs_equal(allp, exp)
-        # shard r owns row blocks r, r+n_shards, ...
+        # shard r owns the row blocks the boustrophedon rule gives it
+        from galah_b200 import distributed as gd
         for r, part in enumerate(parts):
-            assert np.all((part["i"] // gb.ROW_BLOCK) % n_shards == r)
+            assert np.all(gd.owner_of_row(part["i"], n_shards) == r)
 
 
 def test_medium_table_sampled_rows(gb):
