@@ -180,7 +180,7 @@ def main():
     # ---------------- setup (untimed): synthetic genomes -> K1 sketches of this rank's slice
     my_table = torch.empty((n_local, S), dtype=torch.int64, device=dev)
     my_counts = torch.empty(n_local, dtype=torch.int32, device=dev)
-    batch = max(1, min(n_local, (1 << 28) // max(L, 1)))  # ~256 M bases per batch
+    batch = max(1, min(n_local, (1 << 30) // max(L, 1)))  # ~1 G bases (375 MB packed) per batch
     lay = gb.synth_layout(batch, L)
     d_seq = torch.zeros(lay["seq2_words"], dtype=torch.int32, device=dev)
     d_val = torch.zeros(lay["valid_words"], dtype=torch.int32, device=dev)

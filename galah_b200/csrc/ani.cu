@@ -338,23 +338,42 @@ AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_
     return res;
 }
 
-AniIndex::~AniIndex() {
-    d_ks_.release(); d_spread_.release(); d_cso_.release(); d_table_.release();
-    d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
-    for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);
-}
 
+// Grow-only scratch buffer (cudaMalloc / cudaFree are device-wide synchronisations, so the
+// per-batch temporaries are kept across calls).
 template <typename T>
 struct TmpBuf {
     T *p = nullptr;
+    size_t cap = 0;
     ~TmpBuf() { if (p) cudaFree(p); }
-    int alloc(size_t n) { GB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T))); return 0; }
+    int alloc(size_t n) {
+        n = std::max<size_t>(n, 1);
+        if (n <= cap) return 0;
+        if (p) GB_CUDA(cudaFree(p));
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4;
+        GB_CUDA(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        return 0;
+    }
     int upload(const std::vector<T> &v, cudaStream_t st) {
         if (alloc(v.size())) return 2;
         if (!v.empty()) GB_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
         return 0;
     }
 };
+
+struct AniScratch {
+    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc;
+    TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
+};
+
+AniIndex::~AniIndex() {
+    d_ks_.release(); d_spread_.release(); d_cso_.release(); d_table_.release();
+    d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
+    for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);
+    delete scratch_;
+}
 
 int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
                                 size_t n, const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
@@ -386,8 +405,11 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     }
 
     GB_CUDA(cudaEventRecord(ev_[0], st));
-    TmpBuf<uint32_t> d_sel, d_count, d_contig_start, d_chunk_base, d_chunk_tmp, d_nch;
-    TmpBuf<uint64_t> d_contig_off, d_seed_off_b, d_cso_off_b, d_table_off_b;
+    if (!scratch_) scratch_ = new AniScratch();
+    TmpBuf<uint32_t> &d_sel = scratch_->sel, &d_count = scratch_->count, &d_contig_start = scratch_->contig_start,
+                     &d_chunk_base = scratch_->chunk_base, &d_chunk_tmp = scratch_->chunk_tmp, &d_nch = scratch_->nch;
+    TmpBuf<uint64_t> &d_contig_off = scratch_->contig_off, &d_seed_off_b = scratch_->seed_off_b,
+                     &d_cso_off_b = scratch_->cso_off_b, &d_table_off_b = scratch_->table_off_b;
     if (d_sel.alloc(n_words + 1) || d_count.alloc(n)) return 2;
     const uint64_t thr = ~0ull / c_;
     {
@@ -438,7 +460,7 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     GB_CUDA(cudaMemcpyAsync(d_table_off_.p + g0, table_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     GB_CUDA(cudaMemcpyAsync(d_n_chunks_.p + g0, n_chunks.data(), n * 4, cudaMemcpyHostToDevice, st));
     GB_CUDA(cudaEventRecord(ev_[1], st));
-    GB_CUDA(cudaStreamSynchronize(st));  // temporaries die here
+    GB_CUDA(cudaStreamSynchronize(st));  // host staging vectors die here
     float ms = 0.f;
     GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     last_build_ms = ms;
@@ -485,7 +507,8 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, Ani
         oriented[2 * x] = swapped[x] ? b : a;
         oriented[2 * x + 1] = swapped[x] ? a : b;
     }
-    TmpBuf<uint32_t> d_pairs, d_acc;
+    if (!scratch_) scratch_ = new AniScratch();
+    TmpBuf<uint32_t> &d_pairs = scratch_->pairs, &d_acc = scratch_->acc;
     if (d_pairs.upload(oriented, st) || d_acc.alloc(4 * n_pairs)) return 2;
     GB_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * n_pairs, st));
     const size_t smem = (size_t)kAniH * kRingFields * kChainThreads * sizeof(int);

@@ -38,6 +38,8 @@ struct DevVec {
     void release() { if (p) cudaFree(p); p = nullptr; n = cap = 0; }
 };
 
+struct AniScratch;
+
 class AniIndex {
 public:
     explicit AniIndex(uint32_t c) : c_(c) {}
@@ -69,6 +71,7 @@ private:
     DevVec<uint64_t> d_seed_off_, d_cso_off_, d_table_off_;
     DevVec<uint32_t> d_n_chunks_;
     cudaEvent_t ev_[2] = {nullptr, nullptr};
+    AniScratch *scratch_ = nullptr;
 };
 
 // integers -> the f32 galah would parse (host; mirrors oracle/skani_oracle.c skani_oracle_finish)
