@@ -50,6 +50,7 @@ struct PrefilterWorkspace {
     uint64_t *d_bl_vals[2] = {nullptr, nullptr};
     uint8_t *d_bl_tags[2] = {nullptr, nullptr};
     uint32_t *d_bl_len = nullptr;
+    unsigned long long *d_gmax = nullptr;  // largest valid hash of the table (device scalar)
     size_t cap_bl = 0, cap_bl_len = 0;
     // CUDA events on the launch stream: [0] before the build kernels, [1] before the main
     // (join / pairwise) kernel, [2] after it.  Read back with last_timing() after a sync.
@@ -76,7 +77,7 @@ struct KernelParams {
     unsigned long long cand_cap;
     unsigned long long *n_cand;
     // mode 0 only
-    const uint64_t *bl_vals;
+    const uint32_t *bl_hi, *bl_lo;  // block lists, structure of arrays: (value << sh) split in two
     const uint8_t *bl_tags;
     const uint32_t *bl_len;
     uint64_t bl_cap;  // entries per block list (kShardRows * stride)

@@ -18,17 +18,23 @@
 //                     merge-path split in global memory, operands staged in shared memory,
 //                     8 sequential merge steps per thread.  Keys are ordered by (value, tag), so
 //                     padding sorts strictly after a genuine 2^64-1 hash and the first bl_len
-//                     entries of a block list are exactly its valid entries.
+//                     entries of a block list are exactly its valid entries.  The LAST level
+//                     writes the lists as structure-of-arrays: with sh = clz(largest valid hash
+//                     of the table), w = value << sh is lossless, hi = w >> 32 is an
+//                     order-preserving 32-bit key and (hi, lo) equality is value equality.
 //   prefilter_join_kernel  persistent CTAs (3 per SM) pull (rb, cb) items from an atomic
 //                     counter.  The two lists are cut into segments of D = 4608 merged entries
 //                     by merge-path splits (binary searches through L2, all segments of the
-//                     tile in parallel); each segment's A and B slices (values + tags) are
-//                     brought in by four 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//                     tile in parallel); each segment's A and B slices (hi, lo, tags) are
+//                     brought in by six 1-D TMA bulk copies (cp.async.bulk + mbarrier
 //                     complete_tx, SASS UBLKCP); every thread then owns 18 consecutive merge
-//                     steps found by a second merge-path split in shared memory.  Ties are
-//                     ordered B-first, so when a thread takes b every equal a lies at or after
-//                     its A cursor and the (rare) match path scans that run -- at most R long,
-//                     the extra R entries are staged with the segment.  Diagonal items
+//                     steps found by a second merge-path split in shared memory.  The merge
+//                     runs on the dense 32-bit hi keys only (one LDS.32 per step, branch-free,
+//                     fully unrolled when the segment touches no list end).  Ties are ordered
+//                     B-first, so when a thread takes b every a with the same key lies at or
+//                     after its A cursor; the (rare) tie path walks that key run and compares
+//                     lo words -- R extra entries are staged with the segment, and a key run
+//                     that outlasts them is followed in global memory.  Diagonal items
 //                     (rb == cb) need no merge: equal values are adjacent in the one list.
 //                     After the last segment the CTA scans cnt, applies the conservative
 //                     integer thresholds and appends survivors {i, j, common, total}.
@@ -75,14 +81,22 @@ __global__ void __launch_bounds__(256) bl_init_kernel(const uint64_t *__restrict
     }
 }
 
-__global__ void __launch_bounds__(256) bl_len_kernel(const uint32_t *__restrict__ counts, uint32_t n,
+__global__ void __launch_bounds__(256) bl_len_kernel(const uint64_t *__restrict__ hashes,
+                                                     const uint32_t *__restrict__ counts, uint32_t n,
                                                      uint32_t stride, uint32_t n_blocks,
-                                                     uint32_t *__restrict__ bl_len) {
+                                                     uint32_t *__restrict__ bl_len,
+                                                     unsigned long long *__restrict__ gmax) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     uint32_t sum = 0;
-    for (uint32_t r = b * kJR; r < min(n, (b + 1) * kJR); r++) sum += min(counts[r], stride);
+    unsigned long long mx = 0;
+    for (uint32_t r = b * kJR; r < min(n, (b + 1) * kJR); r++) {
+        const uint32_t c = min(counts[r], stride);
+        sum += c;
+        if (c) mx = max(mx, (unsigned long long)hashes[(size_t)r * stride + c - 1]);  // rows ascend
+    }
     bl_len[b] = sum;
+    if (mx) atomicMax(gmax, mx);
 }
 
 __device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8_t tb) {
@@ -91,11 +105,15 @@ __device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8
 
 // One level of the merge tree: for every output run o, dst[o*2m .. o*2m+2m) = merge of
 // src[o*2m .. +m) and src[o*2m+m .. +2m) under the (value, tag) order, first run first on ties.
+template <bool kLast>
 __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__restrict__ sv,
                                                              const uint8_t *__restrict__ st,
                                                              uint64_t *__restrict__ dv,
                                                              uint8_t *__restrict__ dt, uint32_t m,
-                                                             uint32_t chunks_per_run) {
+                                                             uint32_t chunks_per_run,
+                                                             const unsigned long long *__restrict__ gmax,
+                                                             uint32_t *__restrict__ dhi,
+                                                             uint32_t *__restrict__ dlo) {
     __shared__ uint64_t s_v[kMTile];
     __shared__ uint8_t s_t[kMTile];
     __shared__ uint32_t s_g[2];
@@ -136,13 +154,23 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__r
     __syncthreads();
     uint32_t i = s_ts[tid], j = dt0 - i;
     const uint32_t ie = s_ts[tid + 1], je = dt1 - ie;
-    uint64_t *ov = dv + base + d0;
     uint8_t *ot = dt + base + d0;
+    int sh = 0;
+    if (kLast) { const unsigned long long g = *gmax; sh = g ? __clzll((long long)g) : 0; }
     for (uint32_t x = dt0; x < dt1; x++) {
         bool take_a = j >= je;
         if (!take_a && i < ie) take_a = key_le(As[i], At[i], Bs[j], Bt[j]);
-        if (take_a) { ov[x] = As[i]; ot[x] = At[i]; i++; }
-        else { ov[x] = Bs[j]; ot[x] = Bt[j]; j++; }
+        uint64_t v; uint8_t tg;
+        if (take_a) { v = As[i]; tg = At[i]; i++; }
+        else { v = Bs[j]; tg = Bt[j]; j++; }
+        ot[x] = tg;
+        if (kLast) {
+            const uint64_t w = v << sh;
+            dhi[base + d0 + x] = tg == kPadTag ? 0xFFFFFFFFu : (uint32_t)(w >> 32);
+            dlo[base + d0 + x] = (uint32_t)w;
+        } else {
+            dv[base + d0 + x] = v;
+        }
     }
 }
 
@@ -162,7 +190,8 @@ __device__ __forceinline__ uint32_t split_bfirst(PtrT A, uint32_t la, PtrT B, ui
 }
 
 struct JoinSmem {
-    uint64_t vals[kJCap];
+    uint32_t hi[kJCap];
+    uint32_t lo[kJCap];
     uint32_t cnt[kJR * kJR];
     uint8_t tags[(kJCap + 15) / 16 * 16];
     uint64_t bar;
@@ -171,6 +200,68 @@ struct JoinSmem {
     uint32_t ts[kJThreads + 1];
     uint32_t na[kJR], nb[kJR];
 };
+
+// One block list in global memory (structure of arrays).
+struct ListView {
+    const uint32_t *hi, *lo;
+    const uint8_t *tag;
+    uint32_t len;
+};
+
+// All entries of A at or after staged index i whose key equals kb: count those whose lo word
+// equals lob.  Staged entries first, then (only if the key run outlasts them) global memory.
+__device__ __forceinline__ void match_run(JoinSmem &S, const uint32_t *Ah, const uint32_t *Al, const uint8_t *At,
+                                          uint32_t a_ext, uint32_t i, uint32_t kb, uint32_t lob, uint32_t tagb,
+                                          const ListView &A, uint32_t i0) {
+    uint32_t x = i;
+    for (; x < a_ext && Ah[x] == kb; x++)
+        if (Al[x] == lob) atomicAdd(&S.cnt[(uint32_t)At[x] * kJR + tagb], 1u);
+    if (x == a_ext)
+        for (uint32_t gx = i0 + x; gx < A.len && A.hi[gx] == kb; gx++)
+            if (A.lo[gx] == lob) atomicAdd(&S.cnt[(uint32_t)A.tag[gx] * kJR + tagb], 1u);
+}
+
+// Merge-intersect one staged segment.  kChecked = false requires that the segment touches no
+// list end (every key a thread can look at is a real entry), so each thread runs exactly kJE
+// branch-free steps; kChecked = true bounds every step by the thread's own split.
+template <bool kChecked>
+__device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, uint32_t i0, uint32_t a_off,
+                                             uint32_t a_cnt, uint32_t b_off, uint32_t na_s, uint32_t nb_s,
+                                             uint32_t a_ext, uint32_t tid) {
+    const uint32_t *Ah = S.hi + a_off, *Bh = S.hi + a_cnt + b_off;
+    const uint32_t *Al = S.lo + a_off, *Bl = S.lo + a_cnt + b_off;
+    const uint8_t *At = S.tags + a_off, *Bt = S.tags + a_cnt + b_off;
+    const uint32_t len = na_s + nb_s;
+    const uint32_t dt0 = min(tid * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
+    S.ts[tid] = split_bfirst(Ah, na_s, Bh, nb_s, dt0);
+    if (tid == 0) S.ts[kJThreads] = na_s;
+    __syncthreads();
+    uint32_t i = S.ts[tid], j = dt0 - i;
+    uint32_t ka = Ah[i], kb = Bh[j];
+    if (!kChecked) {
+#pragma unroll
+        for (int t = 0; t < kJE; t++) {
+            const bool tb = kb <= ka;
+            if (kb == ka) match_run(S, Ah, Al, At, a_ext, i, kb, Bl[j], Bt[j], A, i0);
+            j += tb ? 1u : 0u;
+            i += tb ? 0u : 1u;
+            const uint32_t nv = *(tb ? Bh + j : Ah + i);
+            kb = tb ? nv : kb;
+            ka = tb ? ka : nv;
+        }
+    } else {
+        const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
+        for (uint32_t t = dt0; t < dt1; t++) {
+            const bool tb = (i >= ie) || (j < je && kb <= ka);
+            if (tb && kb == ka) match_run(S, Ah, Al, At, a_ext, i, kb, Bl[j], Bt[j], A, i0);
+            j += tb ? 1u : 0u;
+            i += tb ? 0u : 1u;
+            const uint32_t nv = *(tb ? Bh + j : Ah + i);
+            kb = tb ? nv : kb;
+            ka = tb ? ka : nv;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(const KernelParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -200,11 +291,12 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
             S.na[tid] = row0 + tid < p.n ? min(p.counts[row0 + tid], p.stride) : 0;
             S.nb[tid] = col0 + tid < p.n ? min(p.counts[col0 + tid], p.stride) : 0;
         }
-        const uint32_t la = p.bl_len[rb], lb = p.bl_len[cb];
-        const uint64_t *A = p.bl_vals + (uint64_t)rb * p.bl_cap;
-        const uint8_t *tA = p.bl_tags + (uint64_t)rb * p.bl_cap;
-        const uint64_t *B = p.bl_vals + (uint64_t)cb * p.bl_cap;
-        const uint8_t *tB = p.bl_tags + (uint64_t)cb * p.bl_cap;
+        ListView A, B;
+        A.hi = p.bl_hi + (uint64_t)rb * p.bl_cap; A.lo = p.bl_lo + (uint64_t)rb * p.bl_cap;
+        A.tag = p.bl_tags + (uint64_t)rb * p.bl_cap; A.len = p.bl_len[rb];
+        B.hi = p.bl_hi + (uint64_t)cb * p.bl_cap; B.lo = p.bl_lo + (uint64_t)cb * p.bl_cap;
+        B.tag = p.bl_tags + (uint64_t)cb * p.bl_cap; B.len = p.bl_len[cb];
+        const uint32_t la = A.len, lb = B.len;
         __syncthreads();
 
         if (rb == cb) {
@@ -214,18 +306,28 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                 const uint32_t ext = min(la, x1 + (uint32_t)kJR) - x0;
                 const uint32_t a_cnt = (ext + 15u) & ~15u;
                 if (tid == 0) {
+                    fence_proxy_async();
                     mbar_arrive_expect_tx(&S.bar, a_cnt * 9u);
-                    tma_load_1d(S.vals, A + x0, a_cnt * 8u, &S.bar);
-                    tma_load_1d(S.tags, tA + x0, a_cnt, &S.bar);
+                    tma_load_1d(S.hi, A.hi + x0, a_cnt * 4u, &S.bar);
+                    tma_load_1d(S.lo, A.lo + x0, a_cnt * 4u, &S.bar);
+                    tma_load_1d(S.tags, A.tag + x0, a_cnt, &S.bar);
                 }
                 mbar_wait(&S.bar, phase); phase ^= 1;
                 const uint32_t e0 = tid * kJE, e1 = min(e0 + (uint32_t)kJE, x1 - x0);
                 for (uint32_t x = e0; x < e1; x++) {
-                    const uint64_t v = S.vals[x];
-                    for (uint32_t y = x + 1; y < ext && S.vals[y] == v; y++) {
-                        const uint32_t tx = S.tags[x], ty = S.tags[y];
-                        atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
-                    }
+                    const uint32_t h = S.hi[x], l = S.lo[x], tx = S.tags[x];
+                    uint32_t y = x + 1;
+                    for (; y < ext && S.hi[y] == h; y++)
+                        if (S.lo[y] == l) {
+                            const uint32_t ty = S.tags[y];
+                            atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
+                        }
+                    if (y == ext)
+                        for (uint32_t gy = x0 + y; gy < la && A.hi[gy] == h; gy++)
+                            if (A.lo[gy] == l) {
+                                const uint32_t ty = A.tag[gy];
+                                atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
+                            }
                 }
                 __syncthreads();
             }
@@ -238,7 +340,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                 const uint32_t nsb = min((uint32_t)(kJThreads - 1), nseg - kb);
                 if (tid <= nsb) {
                     const uint32_t d = (uint32_t)min((uint64_t)(kb + tid) * kJD, (uint64_t)total);
-                    S.split[tid] = split_bfirst(A, la, B, lb, d);
+                    S.split[tid] = split_bfirst(A.hi, la, B.hi, lb, d);
                 }
                 __syncthreads();
                 for (uint32_t s = 0; s < nsb; s++) {
@@ -250,40 +352,25 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     if (nb_s == 0) continue;
                     const uint32_t a_ext = min(la, i1 + (uint32_t)kJR) - i0;
                     const uint32_t a_lo = i0 & ~15u, a_off = i0 - a_lo;
-                    const uint32_t a_cnt = (a_off + a_ext + 15u) & ~15u;
+                    const uint32_t a_cnt = (a_off + a_ext + 1u + 15u) & ~15u;
                     const uint32_t b_lo = j0 & ~15u, b_off = j0 - b_lo;
                     const uint32_t b_cnt = (b_off + nb_s + 1u + 15u) & ~15u;
                     if (tid == 0) {
+                        fence_proxy_async();
                         mbar_arrive_expect_tx(&S.bar, (a_cnt + b_cnt) * 9u);
-                        tma_load_1d(S.vals, A + a_lo, a_cnt * 8u, &S.bar);
-                        tma_load_1d(S.vals + a_cnt, B + b_lo, b_cnt * 8u, &S.bar);
-                        tma_load_1d(S.tags, tA + a_lo, a_cnt, &S.bar);
-                        tma_load_1d(S.tags + a_cnt, tB + b_lo, b_cnt, &S.bar);
+                        tma_load_1d(S.hi, A.hi + a_lo, a_cnt * 4u, &S.bar);
+                        tma_load_1d(S.hi + a_cnt, B.hi + b_lo, b_cnt * 4u, &S.bar);
+                        tma_load_1d(S.lo, A.lo + a_lo, a_cnt * 4u, &S.bar);
+                        tma_load_1d(S.lo + a_cnt, B.lo + b_lo, b_cnt * 4u, &S.bar);
+                        tma_load_1d(S.tags, A.tag + a_lo, a_cnt, &S.bar);
+                        tma_load_1d(S.tags + a_cnt, B.tag + b_lo, b_cnt, &S.bar);
                     }
                     mbar_wait(&S.bar, phase); phase ^= 1;
-                    const uint64_t *As = S.vals + a_off, *Bs = S.vals + a_cnt + b_off;
-                    const uint8_t *At = S.tags + a_off, *Bt = S.tags + a_cnt + b_off;
-                    const uint32_t len = na_s + nb_s;
-                    const uint32_t dt0 = min(tid * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
-                    S.ts[tid] = split_bfirst(As, na_s, Bs, nb_s, dt0);
-                    if (tid == 0) S.ts[kJThreads] = na_s;
-                    __syncthreads();
-                    uint32_t i = S.ts[tid], j = dt0 - i;
-                    const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
-                    uint64_t a = As[i], b = Bs[j];
-                    for (uint32_t t = dt0; t < dt1; t++) {
-                        const bool take_b = (i >= ie) || (j < je && b <= a);
-                        if (take_b) {
-                            if (b == a) {  // rare: scan the run of equal values on the A side
-                                const uint32_t tb = Bt[j];
-                                for (uint32_t x = i; x < a_ext && As[x] == b; x++)
-                                    atomicAdd(&S.cnt[(uint32_t)At[x] * kJR + tb], 1u);
-                            }
-                            j++; b = Bs[j];
-                        } else {
-                            i++; a = As[i];
-                        }
-                    }
+                    // a segment that ends before either list does holds only real entries
+                    if (i1 < la && j1 < lb && d1 - d0 == (uint32_t)kJD)
+                        join_segment<false>(S, A, i0, a_off, a_cnt, b_off, na_s, nb_s, a_ext, tid);
+                    else
+                        join_segment<true>(S, A, i0, a_off, a_cnt, b_off, na_s, nb_s, a_ext, tid);
                     __syncthreads();  // staged slices free for the next TMA
                 }
                 __syncthreads();
@@ -329,6 +416,8 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
         ws.cap_bl = total + kBlSlack;
     }
     if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
+    if (!ws.d_gmax) GB_CUDA(cudaMalloc(&ws.d_gmax, sizeof(unsigned long long)));
+    GB_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(unsigned long long), stream));
 
     int dev = 0, sms = kNumSMsFallback;
     GB_CUDA(cudaGetDevice(&dev));
@@ -339,7 +428,7 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
         bl_init_kernel<<<grid, 256, 0, stream>>>(p.hashes, p.counts, n, stride, total, ws.d_bl_vals[0],
                                                  ws.d_bl_tags[0]);
         GB_LAUNCH_CHECK();
-        bl_len_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(p.counts, n, stride, nb, ws.d_bl_len);
+        bl_len_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(p.hashes, p.counts, n, stride, nb, ws.d_bl_len, ws.d_gmax);
         GB_LAUNCH_CHECK();
     }
     int src = 0;
@@ -348,13 +437,23 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
         const uint64_t outruns = total / (2 * m);
         const uint64_t grid = outruns * chunks;
         if (grid > 0x7FFFFFFFull) { set_error("prefilter: table too large for the merge grid"); return 3; }
-        bl_merge_kernel<<<(uint32_t)grid, kMThreads, 0, stream>>>(ws.d_bl_vals[src], ws.d_bl_tags[src],
-                                                                 ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1],
-                                                                 (uint32_t)m, chunks);
+        // the last level writes (hi, lo) as two uint32 arrays into the destination value buffer
+        uint32_t *dhi = reinterpret_cast<uint32_t *>(ws.d_bl_vals[src ^ 1]);
+        uint32_t *dlo = dhi + (total + kBlSlack);
+        if (2 * m >= bl_cap) {
+            bl_merge_kernel<true><<<(uint32_t)grid, kMThreads, 0, stream>>>(
+                ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
+                ws.d_gmax, dhi, dlo);
+            p.bl_hi = dhi; p.bl_lo = dlo;
+        } else {
+            bl_merge_kernel<false><<<(uint32_t)grid, kMThreads, 0, stream>>>(
+                ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
+                ws.d_gmax, dhi, dlo);
+        }
         GB_LAUNCH_CHECK();
         src ^= 1;
     }
-    p.bl_vals = ws.d_bl_vals[src]; p.bl_tags = ws.d_bl_tags[src]; p.bl_len = ws.d_bl_len; p.bl_cap = bl_cap;
+    p.bl_tags = ws.d_bl_tags[src]; p.bl_len = ws.d_bl_len; p.bl_cap = bl_cap;
 
     if (int rc = upload_join_work_list(ws, n, shard, n_shards, stream, p)) return rc;
     if (p.n_local_rb == 0) return 0;
