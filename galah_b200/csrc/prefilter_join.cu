@@ -55,7 +55,7 @@ constexpr int kJE = 18;                    // merge steps per thread per segment
                                            // in different shared-memory bank pairs)
 constexpr int kJD = kJThreads * kJE;       // merged entries per segment
 constexpr int kJCap = kJD + kJR + 96;      // staged entries incl. run overflow + alignment slack
-constexpr int kJCtasPerSm = 3;
+constexpr int kJCtasPerSm = 2;
 constexpr uint8_t kPadTag = 0xFF;
 constexpr size_t kBlSlack = 1024;          // entries of over-read slack behind the last list
 
@@ -189,12 +189,16 @@ __device__ __forceinline__ uint32_t split_bfirst(PtrT A, uint32_t la, PtrT B, ui
     return lo;
 }
 
-struct JoinSmem {
+struct JoinStage {
     uint32_t hi[kJCap];
     uint32_t lo[kJCap];
-    uint32_t cnt[kJR * kJR];
     uint8_t tags[(kJCap + 15) / 16 * 16];
-    uint64_t bar;
+};
+
+struct JoinSmem {
+    JoinStage st[2];  // double buffer: the next segment streams in while the current one is merged
+    uint32_t cnt[kJR * kJR];
+    uint64_t bar[2];
     unsigned long long item;
     uint32_t split[kJThreads + 1];
     uint32_t ts[kJThreads + 1];
@@ -210,31 +214,37 @@ struct ListView {
 
 // All entries of A at or after staged index i whose key equals kb: count those whose lo word
 // equals lob.  Staged entries first, then (only if the key run outlasts them) global memory.
-__device__ __forceinline__ void match_run(JoinSmem &S, const uint32_t *Ah, const uint32_t *Al, const uint8_t *At,
-                                          uint32_t a_ext, uint32_t i, uint32_t kb, uint32_t lob, uint32_t tagb,
-                                          const ListView &A, uint32_t i0) {
+// Deliberately not inlined: it is the rare path, and inlining it 18 times bloats the hot loop.
+__device__ __noinline__ void match_run(uint32_t *cnt, const uint32_t *Ah, const uint32_t *Al, const uint8_t *At,
+                                       uint32_t a_ext, uint32_t i, uint32_t kb, uint32_t lob, uint32_t tagb,
+                                       const uint32_t *gAh, const uint32_t *gAl, const uint8_t *gAt, uint32_t la,
+                                       uint32_t i0) {
     uint32_t x = i;
     for (; x < a_ext && Ah[x] == kb; x++)
-        if (Al[x] == lob) atomicAdd(&S.cnt[(uint32_t)At[x] * kJR + tagb], 1u);
+        if (Al[x] == lob) atomicAdd(&cnt[(uint32_t)At[x] * kJR + tagb], 1u);
     if (x == a_ext)
-        for (uint32_t gx = i0 + x; gx < A.len && A.hi[gx] == kb; gx++)
-            if (A.lo[gx] == lob) atomicAdd(&S.cnt[(uint32_t)A.tag[gx] * kJR + tagb], 1u);
+        for (uint32_t gx = i0 + x; gx < la && gAh[gx] == kb; gx++)
+            if (gAl[gx] == lob) atomicAdd(&cnt[(uint32_t)gAt[gx] * kJR + tagb], 1u);
 }
+
+// Geometry of one segment of an off-diagonal item (uniform across the CTA).
+struct SegGeom {
+    uint32_t i0, i1, j0, j1, d0, d1, na_s, nb_s, a_ext, a_lo, a_off, a_cnt, b_lo, b_off, b_cnt;
+};
 
 // Merge-intersect one staged segment.  kChecked = false requires that the segment touches no
 // list end (every key a thread can look at is a real entry), so each thread runs exactly kJE
 // branch-free steps; kChecked = true bounds every step by the thread's own split.
 template <bool kChecked>
-__device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, uint32_t i0, uint32_t a_off,
-                                             uint32_t a_cnt, uint32_t b_off, uint32_t na_s, uint32_t nb_s,
-                                             uint32_t a_ext, uint32_t tid) {
-    const uint32_t *Ah = S.hi + a_off, *Bh = S.hi + a_cnt + b_off;
-    const uint32_t *Al = S.lo + a_off, *Bl = S.lo + a_cnt + b_off;
-    const uint8_t *At = S.tags + a_off, *Bt = S.tags + a_cnt + b_off;
-    const uint32_t len = na_s + nb_s;
+__device__ __forceinline__ void join_segment(JoinSmem &S, const JoinStage &T, const ListView &A, const SegGeom &g,
+                                             uint32_t tid) {
+    const uint32_t *Ah = T.hi + g.a_off, *Bh = T.hi + g.a_cnt + g.b_off;
+    const uint32_t *Al = T.lo + g.a_off, *Bl = T.lo + g.a_cnt + g.b_off;
+    const uint8_t *At = T.tags + g.a_off, *Bt = T.tags + g.a_cnt + g.b_off;
+    const uint32_t len = g.na_s + g.nb_s;
     const uint32_t dt0 = min(tid * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
-    S.ts[tid] = split_bfirst(Ah, na_s, Bh, nb_s, dt0);
-    if (tid == 0) S.ts[kJThreads] = na_s;
+    S.ts[tid] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt0);
+    if (tid == 0) S.ts[kJThreads] = g.na_s;
     __syncthreads();
     uint32_t i = S.ts[tid], j = dt0 - i;
     uint32_t ka = Ah[i], kb = Bh[j];
@@ -242,7 +252,7 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, uin
 #pragma unroll
         for (int t = 0; t < kJE; t++) {
             const bool tb = kb <= ka;
-            if (kb == ka) match_run(S, Ah, Al, At, a_ext, i, kb, Bl[j], Bt[j], A, i0);
+            if (kb == ka) match_run(S.cnt, Ah, Al, At, g.a_ext, i, kb, Bl[j], Bt[j], A.hi, A.lo, A.tag, A.len, g.i0);
             j += tb ? 1u : 0u;
             i += tb ? 0u : 1u;
             const uint32_t nv = *(tb ? Bh + j : Ah + i);
@@ -253,7 +263,7 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, uin
         const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
         for (uint32_t t = dt0; t < dt1; t++) {
             const bool tb = (i >= ie) || (j < je && kb <= ka);
-            if (tb && kb == ka) match_run(S, Ah, Al, At, a_ext, i, kb, Bl[j], Bt[j], A, i0);
+            if (tb && kb == ka) match_run(S.cnt, Ah, Al, At, g.a_ext, i, kb, Bl[j], Bt[j], A.hi, A.lo, A.tag, A.len, g.i0);
             j += tb ? 1u : 0u;
             i += tb ? 0u : 1u;
             const uint32_t nv = *(tb ? Bh + j : Ah + i);
@@ -267,9 +277,9 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
     extern __shared__ __align__(128) uint8_t smem_raw[];
     JoinSmem &S = *reinterpret_cast<JoinSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); fence_mbar_init(); }
     __syncthreads();
-    uint32_t phase = 0;
+    uint32_t phase_bits = 0;  // bit b = parity the next wait on bar[b] expects
     const uint64_t n_items = p.item_prefix[p.n_local_rb];
 
     for (;;) {
@@ -301,25 +311,31 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
 
         if (rb == cb) {
             // ---- diagonal item: equal values are adjacent in the single list
-            for (uint32_t x0 = 0; x0 < la; x0 += kJD) {
-                const uint32_t x1 = min(la, x0 + (uint32_t)kJD);
+            const uint32_t nseg = (la + kJD - 1) / kJD;
+            auto issue = [&](uint32_t s, uint32_t buf) {
+                const uint32_t x0 = s * kJD, x1 = min(la, x0 + (uint32_t)kJD);
+                const uint32_t a_cnt = (min(la, x1 + (uint32_t)kJR) - x0 + 15u) & ~15u;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&S.bar[buf], a_cnt * 9u);
+                tma_load_1d(S.st[buf].hi, A.hi + x0, a_cnt * 4u, &S.bar[buf]);
+                tma_load_1d(S.st[buf].lo, A.lo + x0, a_cnt * 4u, &S.bar[buf]);
+                tma_load_1d(S.st[buf].tags, A.tag + x0, a_cnt, &S.bar[buf]);
+            };
+            if (tid == 0 && nseg > 0) issue(0, 0);
+            for (uint32_t s = 0; s < nseg; s++) {
+                const uint32_t buf = s & 1;
+                if (tid == 0 && s + 1 < nseg) issue(s + 1, buf ^ 1);
+                mbar_wait(&S.bar[buf], (phase_bits >> buf) & 1u); phase_bits ^= 1u << buf;
+                const JoinStage &T = S.st[buf];
+                const uint32_t x0 = s * kJD, x1 = min(la, x0 + (uint32_t)kJD);
                 const uint32_t ext = min(la, x1 + (uint32_t)kJR) - x0;
-                const uint32_t a_cnt = (ext + 15u) & ~15u;
-                if (tid == 0) {
-                    fence_proxy_async();
-                    mbar_arrive_expect_tx(&S.bar, a_cnt * 9u);
-                    tma_load_1d(S.hi, A.hi + x0, a_cnt * 4u, &S.bar);
-                    tma_load_1d(S.lo, A.lo + x0, a_cnt * 4u, &S.bar);
-                    tma_load_1d(S.tags, A.tag + x0, a_cnt, &S.bar);
-                }
-                mbar_wait(&S.bar, phase); phase ^= 1;
                 const uint32_t e0 = tid * kJE, e1 = min(e0 + (uint32_t)kJE, x1 - x0);
                 for (uint32_t x = e0; x < e1; x++) {
-                    const uint32_t h = S.hi[x], l = S.lo[x], tx = S.tags[x];
+                    const uint32_t h = T.hi[x], l = T.lo[x], tx = T.tags[x];
                     uint32_t y = x + 1;
-                    for (; y < ext && S.hi[y] == h; y++)
-                        if (S.lo[y] == l) {
-                            const uint32_t ty = S.tags[y];
+                    for (; y < ext && T.hi[y] == h; y++)
+                        if (T.lo[y] == l) {
+                            const uint32_t ty = T.tags[y];
                             atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
                         }
                     if (y == ext)
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                                 atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
                             }
                 }
-                __syncthreads();
+                __syncthreads();  // stage `buf` is free for the TMA issued in the next iteration
             }
         } else if (la != 0 && lb != 0) {
             // ---- off-diagonal item: CTA-wide merge-path intersection of two block lists
@@ -343,35 +359,56 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     S.split[tid] = split_bfirst(A.hi, la, B.hi, lb, d);
                 }
                 __syncthreads();
-                for (uint32_t s = 0; s < nsb; s++) {
-                    const uint32_t d0 = (kb + s) * kJD, d1 = min(d0 + (uint32_t)kJD, total);
-                    const uint32_t i0 = S.split[s], i1 = S.split[s + 1];
-                    const uint32_t j0 = d0 - i0, j1 = d1 - i1;
-                    if (i0 >= la || j0 >= lb) { done = true; break; }  // one list is exhausted
-                    const uint32_t na_s = i1 - i0, nb_s = j1 - j0;
-                    if (nb_s == 0) continue;
-                    const uint32_t a_ext = min(la, i1 + (uint32_t)kJR) - i0;
-                    const uint32_t a_lo = i0 & ~15u, a_off = i0 - a_lo;
-                    const uint32_t a_cnt = (a_off + a_ext + 1u + 15u) & ~15u;
-                    const uint32_t b_lo = j0 & ~15u, b_off = j0 - b_lo;
-                    const uint32_t b_cnt = (b_off + nb_s + 1u + 15u) & ~15u;
-                    if (tid == 0) {
-                        fence_proxy_async();
-                        mbar_arrive_expect_tx(&S.bar, (a_cnt + b_cnt) * 9u);
-                        tma_load_1d(S.hi, A.hi + a_lo, a_cnt * 4u, &S.bar);
-                        tma_load_1d(S.hi + a_cnt, B.hi + b_lo, b_cnt * 4u, &S.bar);
-                        tma_load_1d(S.lo, A.lo + a_lo, a_cnt * 4u, &S.bar);
-                        tma_load_1d(S.lo + a_cnt, B.lo + b_lo, b_cnt * 4u, &S.bar);
-                        tma_load_1d(S.tags, A.tag + a_lo, a_cnt, &S.bar);
-                        tma_load_1d(S.tags + a_cnt, B.tag + b_lo, b_cnt, &S.bar);
+                // geometry of segment s of this batch; false = nothing (more) to do there
+                // state: 0 = process, 1 = skip (no B entries), 2 = one list is exhausted: stop
+                auto geom = [&](uint32_t s, SegGeom &g) -> int {
+                    g.d0 = (kb + s) * kJD; g.d1 = min(g.d0 + (uint32_t)kJD, total);
+                    g.i0 = S.split[s]; g.i1 = S.split[s + 1];
+                    g.j0 = g.d0 - g.i0; g.j1 = g.d1 - g.i1;
+                    if (g.i0 >= la || g.j0 >= lb) return 2;
+                    g.na_s = g.i1 - g.i0; g.nb_s = g.j1 - g.j0;
+                    if (g.nb_s == 0) return 1;
+                    g.a_ext = min(la, g.i1 + (uint32_t)kJR) - g.i0;
+                    g.a_lo = g.i0 & ~15u; g.a_off = g.i0 - g.a_lo;
+                    g.a_cnt = (g.a_off + g.a_ext + 1u + 15u) & ~15u;
+                    g.b_lo = g.j0 & ~15u; g.b_off = g.j0 - g.b_lo;
+                    g.b_cnt = (g.b_off + g.nb_s + 1u + 15u) & ~15u;
+                    return 0;
+                };
+                // next segment >= s that has work; nsb if none (sets done when a list ran out)
+                auto next_work = [&](uint32_t s, SegGeom &g) -> uint32_t {
+                    for (; s < nsb; s++) {
+                        const int st = geom(s, g);
+                        if (st == 0) return s;
+                        if (st == 2) { done = true; return nsb; }
                     }
-                    mbar_wait(&S.bar, phase); phase ^= 1;
+                    return nsb;
+                };
+                auto issue = [&](const SegGeom &g, uint32_t buf) {
+                    JoinStage &T = S.st[buf];
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&S.bar[buf], (g.a_cnt + g.b_cnt) * 9u);
+                    tma_load_1d(T.hi, A.hi + g.a_lo, g.a_cnt * 4u, &S.bar[buf]);
+                    tma_load_1d(T.hi + g.a_cnt, B.hi + g.b_lo, g.b_cnt * 4u, &S.bar[buf]);
+                    tma_load_1d(T.lo, A.lo + g.a_lo, g.a_cnt * 4u, &S.bar[buf]);
+                    tma_load_1d(T.lo + g.a_cnt, B.lo + g.b_lo, g.b_cnt * 4u, &S.bar[buf]);
+                    tma_load_1d(T.tags, A.tag + g.a_lo, g.a_cnt, &S.bar[buf]);
+                    tma_load_1d(T.tags + g.a_cnt, B.tag + g.b_lo, g.b_cnt, &S.bar[buf]);
+                };
+                SegGeom cur, nxt;
+                uint32_t s = next_work(0, cur), buf = 0;
+                if (s < nsb && tid == 0) issue(cur, buf);
+                while (s < nsb) {
+                    const uint32_t s2 = next_work(s + 1, nxt);
+                    if (s2 < nsb && tid == 0) issue(nxt, buf ^ 1);
+                    mbar_wait(&S.bar[buf], (phase_bits >> buf) & 1u); phase_bits ^= 1u << buf;
                     // a segment that ends before either list does holds only real entries
-                    if (i1 < la && j1 < lb && d1 - d0 == (uint32_t)kJD)
-                        join_segment<false>(S, A, i0, a_off, a_cnt, b_off, na_s, nb_s, a_ext, tid);
+                    if (cur.i1 < la && cur.j1 < lb && cur.d1 - cur.d0 == (uint32_t)kJD)
+                        join_segment<false>(S, S.st[buf], A, cur, tid);
                     else
-                        join_segment<true>(S, A, i0, a_off, a_cnt, b_off, na_s, nb_s, a_ext, tid);
-                    __syncthreads();  // staged slices free for the next TMA
+                        join_segment<true>(S, S.st[buf], A, cur, tid);
+                    __syncthreads();  // stage `buf` is free for the TMA issued in the next iteration
+                    cur = nxt; s = s2; buf ^= 1;
                 }
                 __syncthreads();
             }
