@@ -55,7 +55,7 @@ constexpr int kJE = 18;                    // merge steps per thread per segment
                                            // in different shared-memory bank pairs)
 constexpr int kJD = kJThreads * kJE;       // merged entries per segment
 constexpr int kJCap = kJD + kJR + 96;      // staged entries incl. run overflow + alignment slack
-constexpr int kJCtasPerSm = 2;
+constexpr int kJCtasPerSm = 3;
 constexpr uint8_t kPadTag = 0xFF;
 constexpr size_t kBlSlack = 1024;          // entries of over-read slack behind the last list
 
@@ -189,15 +189,10 @@ __device__ __forceinline__ uint32_t split_bfirst(PtrT A, uint32_t la, PtrT B, ui
     return lo;
 }
 
-struct JoinStage {
-    uint32_t hi[kJCap];
-    uint32_t lo[kJCap];
-    uint8_t tags[(kJCap + 15) / 16 * 16];
-};
-
 struct JoinSmem {
-    JoinStage st[2];  // double buffer: the next segment streams in while the current one is merged
+    uint32_t hi[2][kJCap];  // off-diagonal: double-buffered key slices; diagonal: [0] = hi, [1] = lo
     uint32_t cnt[kJR * kJR];
+    uint8_t tags[(kJCap + 15) / 16 * 16];  // diagonal items only
     uint64_t bar[2];
     unsigned long long item;
     uint32_t split[kJThreads + 1];
@@ -212,19 +207,20 @@ struct ListView {
     uint32_t len;
 };
 
-// All entries of A at or after staged index i whose key equals kb: count those whose lo word
-// equals lob.  Staged entries first, then (only if the key run outlasts them) global memory.
-// Deliberately not inlined: it is the rare path, and inlining it 18 times bloats the hot loop.
-__device__ __noinline__ void match_run(uint32_t *cnt, const uint32_t *Ah, const uint32_t *Al, const uint8_t *At,
-                                       uint32_t a_ext, uint32_t i, uint32_t kb, uint32_t lob, uint32_t tagb,
+// Tie path of an off-diagonal item: B entry gj met an A key equal to its own at staged A index i.
+// Walk A's run of that key (staged keys first, then global memory) and count the entries whose lo
+// word also matches -- (hi, lo) equality is value equality.  lo words and tags are read from
+// global memory (L2): ties are rare unless the two blocks hold related genomes.  Deliberately
+// not inlined: inlining it into the 18 unrolled steps bloats the hot loop.
+__device__ __noinline__ void match_run(uint32_t *cnt, const uint32_t *Ah, uint32_t a_ext, uint32_t i, uint32_t kb,
                                        const uint32_t *gAh, const uint32_t *gAl, const uint8_t *gAt, uint32_t la,
-                                       uint32_t i0) {
-    uint32_t x = i;
-    for (; x < a_ext && Ah[x] == kb; x++)
-        if (Al[x] == lob) atomicAdd(&cnt[(uint32_t)At[x] * kJR + tagb], 1u);
-    if (x == a_ext)
-        for (uint32_t gx = i0 + x; gx < la && gAh[gx] == kb; gx++)
-            if (gAl[gx] == lob) atomicAdd(&cnt[(uint32_t)gAt[gx] * kJR + tagb], 1u);
+                                       uint32_t i0, const uint32_t *gBl, const uint8_t *gBt, uint32_t gj) {
+    const uint32_t lob = gBl[gj], tagb = gBt[gj];
+    for (uint32_t x = i; i0 + x < la; x++) {
+        const uint32_t key = x < a_ext ? Ah[x] : gAh[i0 + x];
+        if (key != kb) break;
+        if (gAl[i0 + x] == lob) atomicAdd(&cnt[(uint32_t)gAt[i0 + x] * kJR + tagb], 1u);
+    }
 }
 
 // Geometry of one segment of an off-diagonal item (uniform across the CTA).
@@ -236,11 +232,9 @@ struct SegGeom {
 // list end (every key a thread can look at is a real entry), so each thread runs exactly kJE
 // branch-free steps; kChecked = true bounds every step by the thread's own split.
 template <bool kChecked>
-__device__ __forceinline__ void join_segment(JoinSmem &S, const JoinStage &T, const ListView &A, const SegGeom &g,
-                                             uint32_t tid) {
-    const uint32_t *Ah = T.hi + g.a_off, *Bh = T.hi + g.a_cnt + g.b_off;
-    const uint32_t *Al = T.lo + g.a_off, *Bl = T.lo + g.a_cnt + g.b_off;
-    const uint8_t *At = T.tags + g.a_off, *Bt = T.tags + g.a_cnt + g.b_off;
+__device__ __forceinline__ void join_segment(JoinSmem &S, const uint32_t *stage, const ListView &A, const ListView &B,
+                                             const SegGeom &g, uint32_t tid) {
+    const uint32_t *Ah = stage + g.a_off, *Bh = stage + g.a_cnt + g.b_off;
     const uint32_t len = g.na_s + g.nb_s;
     const uint32_t dt0 = min(tid * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
     S.ts[tid] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt0);
@@ -252,7 +246,7 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const JoinStage &T, co
 #pragma unroll
         for (int t = 0; t < kJE; t++) {
             const bool tb = kb <= ka;
-            if (kb == ka) match_run(S.cnt, Ah, Al, At, g.a_ext, i, kb, Bl[j], Bt[j], A.hi, A.lo, A.tag, A.len, g.i0);
+            if (kb == ka) match_run(S.cnt, Ah, g.a_ext, i, kb, A.hi, A.lo, A.tag, A.len, g.i0, B.lo, B.tag, g.j0 + j);
             j += tb ? 1u : 0u;
             i += tb ? 0u : 1u;
             const uint32_t nv = *(tb ? Bh + j : Ah + i);
@@ -263,7 +257,7 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const JoinStage &T, co
         const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
         for (uint32_t t = dt0; t < dt1; t++) {
             const bool tb = (i >= ie) || (j < je && kb <= ka);
-            if (tb && kb == ka) match_run(S.cnt, Ah, Al, At, g.a_ext, i, kb, Bl[j], Bt[j], A.hi, A.lo, A.tag, A.len, g.i0);
+            if (tb && kb == ka) match_run(S.cnt, Ah, g.a_ext, i, kb, A.hi, A.lo, A.tag, A.len, g.i0, B.lo, B.tag, g.j0 + j);
             j += tb ? 1u : 0u;
             i += tb ? 0u : 1u;
             const uint32_t nv = *(tb ? Bh + j : Ah + i);
@@ -310,32 +304,28 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         __syncthreads();
 
         if (rb == cb) {
-            // ---- diagonal item: equal values are adjacent in the single list
-            const uint32_t nseg = (la + kJD - 1) / kJD;
-            auto issue = [&](uint32_t s, uint32_t buf) {
-                const uint32_t x0 = s * kJD, x1 = min(la, x0 + (uint32_t)kJD);
-                const uint32_t a_cnt = (min(la, x1 + (uint32_t)kJR) - x0 + 15u) & ~15u;
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&S.bar[buf], a_cnt * 9u);
-                tma_load_1d(S.st[buf].hi, A.hi + x0, a_cnt * 4u, &S.bar[buf]);
-                tma_load_1d(S.st[buf].lo, A.lo + x0, a_cnt * 4u, &S.bar[buf]);
-                tma_load_1d(S.st[buf].tags, A.tag + x0, a_cnt, &S.bar[buf]);
-            };
-            if (tid == 0 && nseg > 0) issue(0, 0);
-            for (uint32_t s = 0; s < nseg; s++) {
-                const uint32_t buf = s & 1;
-                if (tid == 0 && s + 1 < nseg) issue(s + 1, buf ^ 1);
-                mbar_wait(&S.bar[buf], (phase_bits >> buf) & 1u); phase_bits ^= 1u << buf;
-                const JoinStage &T = S.st[buf];
-                const uint32_t x0 = s * kJD, x1 = min(la, x0 + (uint32_t)kJD);
+            // ---- diagonal item: equal values are adjacent in the single list; hi, lo and tags
+            // are all staged (ties are the rule here: family members sit in the same block)
+            for (uint32_t x0 = 0; x0 < la; x0 += kJD) {
+                const uint32_t x1 = min(la, x0 + (uint32_t)kJD);
                 const uint32_t ext = min(la, x1 + (uint32_t)kJR) - x0;
+                const uint32_t a_cnt = (ext + 15u) & ~15u;
+                if (tid == 0) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&S.bar[0], a_cnt * 9u);
+                    tma_load_1d(S.hi[0], A.hi + x0, a_cnt * 4u, &S.bar[0]);
+                    tma_load_1d(S.hi[1], A.lo + x0, a_cnt * 4u, &S.bar[0]);
+                    tma_load_1d(S.tags, A.tag + x0, a_cnt, &S.bar[0]);
+                }
+                mbar_wait(&S.bar[0], phase_bits & 1u); phase_bits ^= 1u;
+                const uint32_t *Th = S.hi[0], *Tl = S.hi[1];
                 const uint32_t e0 = tid * kJE, e1 = min(e0 + (uint32_t)kJE, x1 - x0);
                 for (uint32_t x = e0; x < e1; x++) {
-                    const uint32_t h = T.hi[x], l = T.lo[x], tx = T.tags[x];
+                    const uint32_t h = Th[x], l = Tl[x], tx = S.tags[x];
                     uint32_t y = x + 1;
-                    for (; y < ext && T.hi[y] == h; y++)
-                        if (T.lo[y] == l) {
-                            const uint32_t ty = T.tags[y];
+                    for (; y < ext && Th[y] == h; y++)
+                        if (Tl[y] == l) {
+                            const uint32_t ty = S.tags[y];
                             atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
                         }
                     if (y == ext)
@@ -345,7 +335,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                                 atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
                             }
                 }
-                __syncthreads();  // stage `buf` is free for the TMA issued in the next iteration
+                __syncthreads();
             }
         } else if (la != 0 && lb != 0) {
             // ---- off-diagonal item: CTA-wide merge-path intersection of two block lists
@@ -359,7 +349,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     S.split[tid] = split_bfirst(A.hi, la, B.hi, lb, d);
                 }
                 __syncthreads();
-                // geometry of segment s of this batch; false = nothing (more) to do there
+                // geometry of segment s of this batch
                 // state: 0 = process, 1 = skip (no B entries), 2 = one list is exhausted: stop
                 auto geom = [&](uint32_t s, SegGeom &g) -> int {
                     g.d0 = (kb + s) * kJD; g.d1 = min(g.d0 + (uint32_t)kJD, total);
@@ -368,7 +358,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     if (g.i0 >= la || g.j0 >= lb) return 2;
                     g.na_s = g.i1 - g.i0; g.nb_s = g.j1 - g.j0;
                     if (g.nb_s == 0) return 1;
-                    g.a_ext = min(la, g.i1 + (uint32_t)kJR) - g.i0;
+                    g.a_ext = min(la, g.i1 + 16u) - g.i0;  // a few keys past the slice for short runs
                     g.a_lo = g.i0 & ~15u; g.a_off = g.i0 - g.a_lo;
                     g.a_cnt = (g.a_off + g.a_ext + 1u + 15u) & ~15u;
                     g.b_lo = g.j0 & ~15u; g.b_off = g.j0 - g.b_lo;
@@ -385,15 +375,10 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     return nsb;
                 };
                 auto issue = [&](const SegGeom &g, uint32_t buf) {
-                    JoinStage &T = S.st[buf];
                     fence_proxy_async();
-                    mbar_arrive_expect_tx(&S.bar[buf], (g.a_cnt + g.b_cnt) * 9u);
-                    tma_load_1d(T.hi, A.hi + g.a_lo, g.a_cnt * 4u, &S.bar[buf]);
-                    tma_load_1d(T.hi + g.a_cnt, B.hi + g.b_lo, g.b_cnt * 4u, &S.bar[buf]);
-                    tma_load_1d(T.lo, A.lo + g.a_lo, g.a_cnt * 4u, &S.bar[buf]);
-                    tma_load_1d(T.lo + g.a_cnt, B.lo + g.b_lo, g.b_cnt * 4u, &S.bar[buf]);
-                    tma_load_1d(T.tags, A.tag + g.a_lo, g.a_cnt, &S.bar[buf]);
-                    tma_load_1d(T.tags + g.a_cnt, B.tag + g.b_lo, g.b_cnt, &S.bar[buf]);
+                    mbar_arrive_expect_tx(&S.bar[buf], (g.a_cnt + g.b_cnt) * 4u);
+                    tma_load_1d(S.hi[buf], A.hi + g.a_lo, g.a_cnt * 4u, &S.bar[buf]);
+                    tma_load_1d(S.hi[buf] + g.a_cnt, B.hi + g.b_lo, g.b_cnt * 4u, &S.bar[buf]);
                 };
                 SegGeom cur, nxt;
                 uint32_t s = next_work(0, cur), buf = 0;
@@ -404,9 +389,9 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     mbar_wait(&S.bar[buf], (phase_bits >> buf) & 1u); phase_bits ^= 1u << buf;
                     // a segment that ends before either list does holds only real entries
                     if (cur.i1 < la && cur.j1 < lb && cur.d1 - cur.d0 == (uint32_t)kJD)
-                        join_segment<false>(S, S.st[buf], A, cur, tid);
+                        join_segment<false>(S, S.hi[buf], A, B, cur, tid);
                     else
-                        join_segment<true>(S, S.st[buf], A, cur, tid);
+                        join_segment<true>(S, S.hi[buf], A, B, cur, tid);
                     __syncthreads();  // stage `buf` is free for the TMA issued in the next iteration
                     cur = nxt; s = s2; buf ^= 1;
                 }
