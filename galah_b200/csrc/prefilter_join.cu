@@ -53,8 +53,12 @@ constexpr int kJThreads = 256;
 constexpr int kJE = 18;                    // merge steps per thread per segment (kJE/2 odd: the
                                            // expected A/B cursors of adjacent threads then fall
                                            // in different shared-memory bank pairs)
-constexpr int kJD = kJThreads * kJE;       // merged entries per segment
-constexpr int kJCap = kJD + kJR + 96;      // staged entries incl. run overflow + alignment slack
+constexpr int kJChains = 2;                // independent merge chains per thread (ILP: each step
+                                           // is a dependent LDS -> compare -> select -> LDS)
+constexpr int kJD = kJThreads * kJE * kJChains;  // merged entries per segment
+constexpr int kJCap = kJD + 16 + 80;       // staged entries incl. short-run overflow + alignment slack
+constexpr int kJDiag = 3072;               // entries per diagonal-item segment (hi, lo, tags staged)
+static_assert(2 * (kJDiag + kJR + 16) * 4 + (kJDiag + kJR + 16) <= kJCap * 4, "diagonal staging must fit");
 constexpr int kJCtasPerSm = 3;
 constexpr uint8_t kPadTag = 0xFF;
 constexpr size_t kBlSlack = 1024;          // entries of over-read slack behind the last list
@@ -190,13 +194,12 @@ __device__ __forceinline__ uint32_t split_bfirst(PtrT A, uint32_t la, PtrT B, ui
 }
 
 struct JoinSmem {
-    uint32_t hi[2][kJCap];  // off-diagonal: double-buffered key slices; diagonal: [0] = hi, [1] = lo
+    uint32_t hi[kJCap];  // off-diagonal: the segment's A and B key slices; diagonal: hi | lo | tags
     uint32_t cnt[kJR * kJR];
-    uint8_t tags[(kJCap + 15) / 16 * 16];  // diagonal items only
-    uint64_t bar[2];
+    uint64_t bar;
     unsigned long long item;
     uint32_t split[kJThreads + 1];
-    uint32_t ts[kJThreads + 1];
+    uint32_t ts[kJChains * kJThreads + 1];
     uint32_t na[kJR], nb[kJR];
 };
 
@@ -210,16 +213,14 @@ struct ListView {
 // Tie path of an off-diagonal item: B entry gj met an A key equal to its own at staged A index i.
 // Walk A's run of that key (staged keys first, then global memory) and count the entries whose lo
 // word also matches -- (hi, lo) equality is value equality.  lo words and tags are read from
-// global memory (L2): ties are rare unless the two blocks hold related genomes.  Deliberately
-// not inlined: inlining it into the 18 unrolled steps bloats the hot loop.
-__device__ __noinline__ void match_run(uint32_t *cnt, const uint32_t *Ah, uint32_t a_ext, uint32_t i, uint32_t kb,
-                                       const uint32_t *gAh, const uint32_t *gAl, const uint8_t *gAt, uint32_t la,
-                                       uint32_t i0, const uint32_t *gBl, const uint8_t *gBt, uint32_t gj) {
-    const uint32_t lob = gBl[gj], tagb = gBt[gj];
-    for (uint32_t x = i; i0 + x < la; x++) {
-        const uint32_t key = x < a_ext ? Ah[x] : gAh[i0 + x];
+// global memory (L2): ties are rare unless the two blocks hold related genomes.
+__device__ __forceinline__ void match_run(uint32_t *cnt, const uint32_t *Ah, uint32_t a_ext, uint32_t i, uint32_t kb,
+                                          const ListView &A, uint32_t i0, const ListView &B, uint32_t gj) {
+    const uint32_t lob = B.lo[gj], tagb = B.tag[gj];
+    for (uint32_t x = i; i0 + x < A.len; x++) {
+        const uint32_t key = x < a_ext ? Ah[x] : A.hi[i0 + x];
         if (key != kb) break;
-        if (gAl[i0 + x] == lob) atomicAdd(&cnt[(uint32_t)gAt[i0 + x] * kJR + tagb], 1u);
+        if (A.lo[i0 + x] == lob) atomicAdd(&cnt[(uint32_t)A.tag[i0 + x] * kJR + tagb], 1u);
     }
 }
 
@@ -228,41 +229,88 @@ struct SegGeom {
     uint32_t i0, i1, j0, j1, d0, d1, na_s, nb_s, a_ext, a_lo, a_off, a_cnt, b_lo, b_off, b_cnt;
 };
 
-// Merge-intersect one staged segment.  kChecked = false requires that the segment touches no
-// list end (every key a thread can look at is a real entry), so each thread runs exactly kJE
-// branch-free steps; kChecked = true bounds every step by the thread's own split.
-template <bool kChecked>
-__device__ __forceinline__ void join_segment(JoinSmem &S, const uint32_t *stage, const ListView &A, const ListView &B,
-                                             const SegGeom &g, uint32_t tid) {
-    const uint32_t *Ah = stage + g.a_off, *Bh = stage + g.a_cnt + g.b_off;
-    const uint32_t len = g.na_s + g.nb_s;
-    const uint32_t dt0 = min(tid * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
-    S.ts[tid] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt0);
-    if (tid == 0) S.ts[kJThreads] = g.na_s;
-    __syncthreads();
-    uint32_t i = S.ts[tid], j = dt0 - i;
+// Re-walk `steps` merge steps from (i, j) and run the tie path at every step whose bit is set in
+// `ties`.  Out of line: the hot loop only records ties in a bit mask and never branches.
+__device__ __noinline__ void replay_ties(uint32_t *cnt, const uint32_t *Ah, const uint32_t *Bh, uint32_t a_ext,
+                                         uint32_t i, uint32_t j, uint32_t steps, uint32_t ties, const ListView A,
+                                         uint32_t i0, const ListView B, uint32_t j0) {
     uint32_t ka = Ah[i], kb = Bh[j];
+    for (uint32_t t = 0; t < steps && (ties >> t) != 0; t++) {
+        const bool tb = kb <= ka;
+        if ((ties >> t) & 1u) match_run(cnt, Ah, a_ext, i, kb, A, i0, B, j0 + j);
+        if (tb) { j++; kb = Bh[j]; } else { i++; ka = Ah[i]; }
+    }
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Merge-intersect one staged segment.  kChecked = false requires that the segment is full and
+// touches no list end (every key a thread can look at is a real entry): every thread then runs
+// kJChains independent chains of exactly kJE branch-free steps, interleaved for ILP.
+// kChecked = true bounds every step by the chain's own split.
+template <bool kChecked>
+__device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, const ListView &B, const SegGeom &g,
+                                             uint32_t tid) {
+    const uint32_t *Ah = S.hi + g.a_off, *Bh = S.hi + g.a_cnt + g.b_off;
+    const uint32_t len = g.na_s + g.nb_s;
+#pragma unroll
+    for (int c = 0; c < kJChains; c++) {
+        const uint32_t dt0 = min((c * kJThreads + tid) * kJE, len);
+        S.ts[c * kJThreads + tid] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt0);
+    }
+    if (tid == 0) S.ts[kJChains * kJThreads] = g.na_s;
+    __syncthreads();
     if (!kChecked) {
+        uint32_t pa[kJChains], pb[kJChains], ka[kJChains], kb[kJChains], ties[kJChains], is[kJChains];
+        const uint32_t a_base = smem_u32(Ah), b_base = smem_u32(Bh);
+#pragma unroll
+        for (int c = 0; c < kJChains; c++) {
+            const uint32_t slot = c * kJThreads + tid;
+            is[c] = S.ts[slot];
+            pa[c] = a_base + 4u * is[c];
+            pb[c] = b_base + 4u * (slot * kJE - is[c]);
+            ka[c] = lds32(pa[c]); kb[c] = lds32(pb[c]);
+            ties[c] = 0;
+        }
 #pragma unroll
         for (int t = 0; t < kJE; t++) {
-            const bool tb = kb <= ka;
-            if (kb == ka) match_run(S.cnt, Ah, g.a_ext, i, kb, A.hi, A.lo, A.tag, A.len, g.i0, B.lo, B.tag, g.j0 + j);
-            j += tb ? 1u : 0u;
-            i += tb ? 0u : 1u;
-            const uint32_t nv = *(tb ? Bh + j : Ah + i);
-            kb = tb ? nv : kb;
-            ka = tb ? ka : nv;
+#pragma unroll
+            for (int c = 0; c < kJChains; c++) {
+                const bool tb = kb[c] <= ka[c];
+                ties[c] |= kb[c] == ka[c] ? (1u << t) : 0u;
+                const uint32_t pn = (tb ? pb[c] : pa[c]) + 4u;
+                const uint32_t nv = lds32(pn);
+                pb[c] = tb ? pn : pb[c];
+                pa[c] = tb ? pa[c] : pn;
+                kb[c] = tb ? nv : kb[c];
+                ka[c] = tb ? ka[c] : nv;
+            }
         }
+#pragma unroll
+        for (int c = 0; c < kJChains; c++)
+            if (ties[c])
+                replay_ties(S.cnt, Ah, Bh, g.a_ext, is[c], (c * kJThreads + tid) * kJE - is[c], kJE, ties[c], A, g.i0,
+                            B, g.j0);
     } else {
-        const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
-        for (uint32_t t = dt0; t < dt1; t++) {
-            const bool tb = (i >= ie) || (j < je && kb <= ka);
-            if (tb && kb == ka) match_run(S.cnt, Ah, g.a_ext, i, kb, A.hi, A.lo, A.tag, A.len, g.i0, B.lo, B.tag, g.j0 + j);
-            j += tb ? 1u : 0u;
-            i += tb ? 0u : 1u;
-            const uint32_t nv = *(tb ? Bh + j : Ah + i);
-            kb = tb ? nv : kb;
-            ka = tb ? ka : nv;
+        for (int c = 0; c < kJChains; c++) {
+            const uint32_t slot = c * kJThreads + tid;
+            const uint32_t dt0 = min(slot * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
+            uint32_t i = S.ts[slot], j = dt0 - i;
+            const uint32_t ie = S.ts[slot + 1], je = dt1 - ie;
+            uint32_t ka = Ah[i], kb = Bh[j];
+            for (uint32_t t = dt0; t < dt1; t++) {
+                const bool tb = (i >= ie) || (j < je && kb <= ka);
+                if (tb && kb == ka) match_run(S.cnt, Ah, g.a_ext, i, kb, A, g.i0, B, g.j0 + j);
+                j += tb ? 1u : 0u;
+                i += tb ? 0u : 1u;
+                const uint32_t nv = *(tb ? Bh + j : Ah + i);
+                kb = tb ? nv : kb;
+                ka = tb ? ka : nv;
+            }
         }
     }
 }
@@ -271,9 +319,9 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
     extern __shared__ __align__(128) uint8_t smem_raw[];
     JoinSmem &S = *reinterpret_cast<JoinSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&S.bar[0], 1); mbar_init(&S.bar[1], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
     __syncthreads();
-    uint32_t phase_bits = 0;  // bit b = parity the next wait on bar[b] expects
+    uint32_t phase = 0;
     const uint64_t n_items = p.item_prefix[p.n_local_rb];
 
     for (;;) {
@@ -306,26 +354,29 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         if (rb == cb) {
             // ---- diagonal item: equal values are adjacent in the single list; hi, lo and tags
             // are all staged (ties are the rule here: family members sit in the same block)
-            for (uint32_t x0 = 0; x0 < la; x0 += kJD) {
-                const uint32_t x1 = min(la, x0 + (uint32_t)kJD);
+            constexpr uint32_t kSlice = kJDiag + kJR + 16;  // staged entries per array
+            uint32_t *Th = S.hi, *Tl = S.hi + kSlice;
+            uint8_t *Tt = reinterpret_cast<uint8_t *>(S.hi + 2 * kSlice);
+            constexpr uint32_t kPer = (kJDiag + kJThreads - 1) / kJThreads;
+            for (uint32_t x0 = 0; x0 < la; x0 += kJDiag) {
+                const uint32_t x1 = min(la, x0 + (uint32_t)kJDiag);
                 const uint32_t ext = min(la, x1 + (uint32_t)kJR) - x0;
                 const uint32_t a_cnt = (ext + 15u) & ~15u;
                 if (tid == 0) {
                     fence_proxy_async();
-                    mbar_arrive_expect_tx(&S.bar[0], a_cnt * 9u);
-                    tma_load_1d(S.hi[0], A.hi + x0, a_cnt * 4u, &S.bar[0]);
-                    tma_load_1d(S.hi[1], A.lo + x0, a_cnt * 4u, &S.bar[0]);
-                    tma_load_1d(S.tags, A.tag + x0, a_cnt, &S.bar[0]);
+                    mbar_arrive_expect_tx(&S.bar, a_cnt * 9u);
+                    tma_load_1d(Th, A.hi + x0, a_cnt * 4u, &S.bar);
+                    tma_load_1d(Tl, A.lo + x0, a_cnt * 4u, &S.bar);
+                    tma_load_1d(Tt, A.tag + x0, a_cnt, &S.bar);
                 }
-                mbar_wait(&S.bar[0], phase_bits & 1u); phase_bits ^= 1u;
-                const uint32_t *Th = S.hi[0], *Tl = S.hi[1];
-                const uint32_t e0 = tid * kJE, e1 = min(e0 + (uint32_t)kJE, x1 - x0);
+                mbar_wait(&S.bar, phase); phase ^= 1;
+                const uint32_t e0 = tid * kPer, e1 = min(e0 + kPer, x1 - x0);
                 for (uint32_t x = e0; x < e1; x++) {
-                    const uint32_t h = Th[x], l = Tl[x], tx = S.tags[x];
+                    const uint32_t h = Th[x], l = Tl[x], tx = Tt[x];
                     uint32_t y = x + 1;
                     for (; y < ext && Th[y] == h; y++)
                         if (Tl[y] == l) {
-                            const uint32_t ty = S.tags[y];
+                            const uint32_t ty = Tt[y];
                             atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
                         }
                     if (y == ext)
@@ -349,51 +400,32 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     S.split[tid] = split_bfirst(A.hi, la, B.hi, lb, d);
                 }
                 __syncthreads();
-                // geometry of segment s of this batch
-                // state: 0 = process, 1 = skip (no B entries), 2 = one list is exhausted: stop
-                auto geom = [&](uint32_t s, SegGeom &g) -> int {
+                for (uint32_t s = 0; s < nsb; s++) {
+                    SegGeom g;
                     g.d0 = (kb + s) * kJD; g.d1 = min(g.d0 + (uint32_t)kJD, total);
                     g.i0 = S.split[s]; g.i1 = S.split[s + 1];
                     g.j0 = g.d0 - g.i0; g.j1 = g.d1 - g.i1;
-                    if (g.i0 >= la || g.j0 >= lb) return 2;
+                    if (g.i0 >= la || g.j0 >= lb) { done = true; break; }  // one list is exhausted
                     g.na_s = g.i1 - g.i0; g.nb_s = g.j1 - g.j0;
-                    if (g.nb_s == 0) return 1;
+                    if (g.nb_s == 0) continue;
                     g.a_ext = min(la, g.i1 + 16u) - g.i0;  // a few keys past the slice for short runs
                     g.a_lo = g.i0 & ~15u; g.a_off = g.i0 - g.a_lo;
                     g.a_cnt = (g.a_off + g.a_ext + 1u + 15u) & ~15u;
                     g.b_lo = g.j0 & ~15u; g.b_off = g.j0 - g.b_lo;
                     g.b_cnt = (g.b_off + g.nb_s + 1u + 15u) & ~15u;
-                    return 0;
-                };
-                // next segment >= s that has work; nsb if none (sets done when a list ran out)
-                auto next_work = [&](uint32_t s, SegGeom &g) -> uint32_t {
-                    for (; s < nsb; s++) {
-                        const int st = geom(s, g);
-                        if (st == 0) return s;
-                        if (st == 2) { done = true; return nsb; }
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        mbar_arrive_expect_tx(&S.bar, (g.a_cnt + g.b_cnt) * 4u);
+                        tma_load_1d(S.hi, A.hi + g.a_lo, g.a_cnt * 4u, &S.bar);
+                        tma_load_1d(S.hi + g.a_cnt, B.hi + g.b_lo, g.b_cnt * 4u, &S.bar);
                     }
-                    return nsb;
-                };
-                auto issue = [&](const SegGeom &g, uint32_t buf) {
-                    fence_proxy_async();
-                    mbar_arrive_expect_tx(&S.bar[buf], (g.a_cnt + g.b_cnt) * 4u);
-                    tma_load_1d(S.hi[buf], A.hi + g.a_lo, g.a_cnt * 4u, &S.bar[buf]);
-                    tma_load_1d(S.hi[buf] + g.a_cnt, B.hi + g.b_lo, g.b_cnt * 4u, &S.bar[buf]);
-                };
-                SegGeom cur, nxt;
-                uint32_t s = next_work(0, cur), buf = 0;
-                if (s < nsb && tid == 0) issue(cur, buf);
-                while (s < nsb) {
-                    const uint32_t s2 = next_work(s + 1, nxt);
-                    if (s2 < nsb && tid == 0) issue(nxt, buf ^ 1);
-                    mbar_wait(&S.bar[buf], (phase_bits >> buf) & 1u); phase_bits ^= 1u << buf;
-                    // a segment that ends before either list does holds only real entries
-                    if (cur.i1 < la && cur.j1 < lb && cur.d1 - cur.d0 == (uint32_t)kJD)
-                        join_segment<false>(S, S.hi[buf], A, B, cur, tid);
+                    mbar_wait(&S.bar, phase); phase ^= 1;
+                    // a full segment that ends before either list does holds only real entries
+                    if (g.i1 < la && g.j1 < lb && g.d1 - g.d0 == (uint32_t)kJD)
+                        join_segment<false>(S, A, B, g, tid);
                     else
-                        join_segment<true>(S, S.hi[buf], A, B, cur, tid);
-                    __syncthreads();  // stage `buf` is free for the TMA issued in the next iteration
-                    cur = nxt; s = s2; buf ^= 1;
+                        join_segment<true>(S, A, B, g, tid);
+                    __syncthreads();  // the staged slices are free for the next TMA
                 }
                 __syncthreads();
             }
