@@ -348,9 +348,9 @@ def main():
         kernel_names = {0: "prefilter_join_kernel", 1: "prefilter_tiled_kernel"}
         pairs_per_launch = pairs / world
         achieved = BYTES_PER_PAIR * pairs_per_launch / (main_ms * 1e-3) / 1e9
-        # bytes the join kernel itself has to read: each (rb, cb) item streams two block lists of
-        # 64*s entries x 9 B (value + tag) once for 64*64 pairs
-        own_bytes_per_pair = 2 * S * 9 / 64 if args.mode == 0 else BYTES_PER_PAIR
+        # bytes the join kernel itself has to read: each (rb, cb) item streams the 32-bit keys of two
+        # block lists of 64*s entries once for 64*64 pairs (lo words / tags only on key ties)
+        own_bytes_per_pair = 2 * S * 4 / 64 if args.mode == 0 else BYTES_PER_PAIR
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             import oracle
@@ -399,7 +399,7 @@ def main():
                          "kernel_own_gbs": own_bytes_per_pair * pairs_per_launch / (main_ms * 1e-3) / 1e9,
                          "note": "achieved uses the reference algorithm's 2*s*8 B/pair (SURVEY.md 8d). The join "
                                  "kernel computes every pair's exact intersection from ONE merge of two 64-sketch "
-                                 "block lists per 64x64 pairs, so it reads 2*s*9/64 B/pair (kernel_own_*) and the "
+                                 "block lists per 64x64 pairs, so it reads 2*s*4/64 B/pair (kernel_own_*) and the "
                                  "fraction of the 16 kB/pair roofline exceeds 1 by design (DESIGN.md K2)"
                                  if args.mode == 0 else
                                  "pairwise kernel re-uses staged sketches from shared memory (16 kB/pair is read "
