@@ -218,12 +218,37 @@ def main():
     d_ncand = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.int8, device=dev)  # > 126 MB L2
 
+    if world > 1:
+        # multi-GPU: the block-list BUILD shards too -- every rank builds a contiguous slice of
+        # blocks and the slices are all-gathered (hi, lo, tags, lengths) before the join
+        nb, epb, slack = gb.blocklist_layout(n, S)
+        nbp = (nb + world - 1) // world
+        my_hi = torch.empty(nbp * epb, dtype=torch.int32, device=dev)
+        my_lo = torch.empty_like(my_hi)
+        my_tags = torch.empty(nbp * epb, dtype=torch.uint8, device=dev)
+        my_len = torch.empty(nbp, dtype=torch.int32, device=dev)
+        all_hi = torch.zeros(world * nbp * epb + slack, dtype=torch.int32, device=dev)
+        all_lo = torch.zeros_like(all_hi)
+        all_tags = torch.zeros(world * nbp * epb + slack, dtype=torch.uint8, device=dev)
+        all_len = torch.empty(world * nbp, dtype=torch.int32, device=dev)
+
     def timed(mode, steps, warmup):
         """`steps` timed passes of `mode`; returns (total_ms max over ranks, launches, per-kernel ms)."""
         def step():
             if world > 1:
                 dist.all_gather_into_tensor(table, my_table)
                 dist.all_gather_into_tensor(counts, my_counts)
+            if world > 1 and mode == 0:
+                gb.blocklist_build(table.data_ptr(), counts.data_ptr(), n, S, rank * nbp, (rank + 1) * nbp,
+                                   my_hi.data_ptr(), my_lo.data_ptr(), my_tags.data_ptr(), my_len.data_ptr(), st)
+                dist.all_gather_into_tensor(all_hi[: world * nbp * epb], my_hi)
+                dist.all_gather_into_tensor(all_lo[: world * nbp * epb], my_lo)
+                dist.all_gather_into_tensor(all_tags[: world * nbp * epb], my_tags)
+                dist.all_gather_into_tensor(all_len, my_len)
+                gb.prefilter_join_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, all_hi.data_ptr(),
+                                          all_lo.data_ptr(), all_tags.data_ptr(), all_len.data_ptr(), rank, world,
+                                          st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
+                return
             gb.prefilter_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, rank, world,
                                  mode, st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
         for _ in range(warmup):
@@ -385,7 +410,8 @@ def main():
                                    f"{' scaled by sqrt(G) genomes' if world > 1 else ''})",
                        "pairs_per_step": pairs, "mode": args.mode,
                        "l2": "flushed between timed iterations (256 MiB write)",
-                       "sharding": "boustrophedon row blocks of 64; NCCL all-gather of the sketch table inside the step"
+                       "sharding": "boustrophedon row blocks of 64; inside the step: NCCL all-gather of the sketch "
+                                   "table, per-rank build of 1/G of the block lists, NCCL all-gather of the lists"
                                    if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -129,6 +129,26 @@ def prefilter_enqueue(d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards
                                              shard, n_shards, mode, stream, d_cand, cand_cap, d_n_cand))
 
 
+def blocklist_layout(n, stride):
+    """(n_blocks, entries_per_block, slack) of the block lists of an n x stride sketch table."""
+    a, b, c = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+    check(lib().galah_b200_blocklist_layout(n, stride, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def blocklist_build(d_hashes, d_counts, n, stride, block_begin, block_end, d_hi, d_lo, d_tags, d_len, stream=0):
+    """Build the block lists of blocks [block_begin, block_end) (slice-based device buffers)."""
+    check(lib().galah_b200_blocklist_build(d_hashes, d_counts, n, stride, block_begin, block_end, d_hi, d_lo,
+                                           d_tags, d_len, stream))
+
+
+def prefilter_join_enqueue(d_hashes, d_counts, n, stride, k, min_ani, d_hi, d_lo, d_tags, d_len, shard, n_shards,
+                           stream, d_cand, cand_cap, d_n_cand):
+    check(lib().galah_b200_prefilter_join_enqueue(d_hashes, d_counts, n, stride, k, ctypes.c_float(min_ani), d_hi,
+                                                  d_lo, d_tags, d_len, shard, n_shards, stream, d_cand, cand_cap,
+                                                  d_n_cand))
+
+
 def finch_distances(paths, min_ani=0.9, num_kmers=1000, kmer_length=21, threads=0):
     """GPU replacement for galah::finch::distances (reference src/finch.rs:48-97)."""
     out = ctypes.POINTER(Pair)()

@@ -328,6 +328,39 @@ int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_cou
                              st, reinterpret_cast<uint4 *>(d_cand), cand_cap, d_n_cand);
 }
 
+int galah_b200_blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack) {
+    blocklist_layout(n, stride, n_blocks, entries_per_block, slack);
+    return 0;
+}
+
+int galah_b200_blocklist_build(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                               size_t block_begin, size_t block_end, uint32_t *d_hi, uint32_t *d_lo,
+                               uint8_t *d_tags, uint32_t *d_len, void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (stride == 0 || (stride & 1) || !join_supported(stride)) { set_error("blocklist_build: unsupported stride"); return GALAH_B200_ERR_ARG; }
+    if (n >= 0x7FFFFFFFull) { set_error("blocklist_build: n too large"); return GALAH_B200_ERR_ARG; }
+    return blocklist_build(g_ctx.pws, d_hashes, d_counts, n, stride, (uint32_t)block_begin, (uint32_t)block_end, d_hi,
+                           d_lo, d_tags, d_len, (cudaStream_t)stream);
+}
+
+int galah_b200_prefilter_join_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                                      uint8_t k, float min_ani, const uint32_t *d_hi, const uint32_t *d_lo,
+                                      const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard,
+                                      uint32_t n_shards, void *stream, uint32_t *d_cand, size_t cand_cap,
+                                      unsigned long long *d_n_cand) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!join_supported(stride)) { set_error("prefilter_join: unsupported stride"); return GALAH_B200_ERR_ARG; }
+    KernelParams p;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = prefilter_prepare(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, st,
+                                   reinterpret_cast<uint4 *>(d_cand), cand_cap, d_n_cand, p))
+        return rc;
+    if (n < 2) return 0;
+    return join_launch(g_ctx.pws, p, d_hi, d_lo, d_tags, d_len, shard, n_shards, st);
+}
+
 int galah_b200_prefilter_device(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                                 size_t stride, uint8_t k, float min_ani, uint32_t shard,
                                 uint32_t n_shards, void *stream, galah_b200_pair_t **out, size_t *n_out) {

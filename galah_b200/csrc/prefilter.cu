@@ -100,6 +100,7 @@ int PrefilterWorkspace::release() {
     for (int x = 0; x < 3; x++) if (ev[x]) cudaEventDestroy(ev[x]);
     cudaFree(d_cmin_by_tmin); cudaFree(d_cmin_by_total); cudaFree(d_item_prefix);
     cudaFree(d_local_rb); cudaFree(d_work_counter); cudaFree(d_bl_len); cudaFree(d_gmax);
+    cudaFree(d_fin_hi); cudaFree(d_fin_lo); cudaFree(d_fin_tags);
     for (int x = 0; x < 2; x++) { cudaFree(d_bl_vals[x]); cudaFree(d_bl_tags[x]); }
     *this = PrefilterWorkspace();
     return 0;
@@ -280,18 +281,14 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
     return 0;
 }
 
-int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
-                      size_t n, size_t stride, int k, float min_ani, uint32_t shard,
-                      uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
-                      size_t cand_cap, unsigned long long *d_n_cand) {
+int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                      size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
+                      uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p) {
     if (n_shards == 0 || shard >= n_shards) { set_error("prefilter: bad shard"); return 3; }
     if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return 3; }
     if (n >= 0x7FFFFFFFull) { set_error("prefilter: n too large"); return 3; }
     if (stride >= (1ull << 30)) { set_error("prefilter: stride too large"); return 3; }
-    if (mode != 0 && mode != 1) { set_error("prefilter: mode must be 0 or 1"); return 3; }
     GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
-    if (n < 2) return 0;
-
     if (!ws.th_valid || ws.th_s != (uint32_t)stride || ws.th_k != k || ws.th_min_ani != min_ani) {
         PrefilterThresholds th = make_thresholds((uint32_t)stride, k, min_ani);
         if (ws_ensure(ws.d_cmin_by_tmin, ws.cap_tmin, th.cmin_by_tmin.size())) return 2;
@@ -302,14 +299,25 @@ int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
                                 cudaMemcpyHostToDevice, stream));
         ws.th_s = (uint32_t)stride; ws.th_k = k; ws.th_min_ani = min_ani; ws.th_valid = true;
     }
-
-    KernelParams p = {};
+    p = KernelParams{};
     p.hashes = d_hashes; p.counts = d_counts; p.n = (uint32_t)n; p.stride = (uint32_t)stride;
     p.cmin_by_tmin = ws.d_cmin_by_tmin; p.cmin_by_total = ws.d_cmin_by_total;
     p.cand = d_cand; p.cand_cap = cand_cap; p.n_cand = d_n_cand;
-
     ws.ev_recorded = false;
     if (ws.record(0, stream)) return 2;
+    return 0;
+}
+
+int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
+                      size_t n, size_t stride, int k, float min_ani, uint32_t shard,
+                      uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
+                      size_t cand_cap, unsigned long long *d_n_cand) {
+    if (mode != 0 && mode != 1) { set_error("prefilter: mode must be 0 or 1"); return 3; }
+    KernelParams p;
+    if (int rc = prefilter_prepare(ws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, stream, d_cand,
+                                   cand_cap, d_n_cand, p))
+        return rc;
+    if (n < 2) return 0;
     if (mode == 0 && join_supported(stride)) return join_build_and_launch(ws, p, shard, n_shards, stream);
 
     if (int rc = upload_work_list(ws, n, kRowBlock, kColChunk, shard, n_shards, stream, p)) return rc;

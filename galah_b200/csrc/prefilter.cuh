@@ -52,6 +52,10 @@ struct PrefilterWorkspace {
     uint32_t *d_bl_len = nullptr;
     unsigned long long *d_gmax = nullptr;  // largest valid hash of the table (device scalar)
     size_t cap_bl = 0, cap_bl_len = 0;
+    // finished lists of the single-device path (structure of arrays)
+    uint32_t *d_fin_hi = nullptr, *d_fin_lo = nullptr;
+    uint8_t *d_fin_tags = nullptr;
+    size_t cap_fin = 0;
     // CUDA events on the launch stream: [0] before the build kernels, [1] before the main
     // (join / pairwise) kernel, [2] after it.  Read back with last_timing() after a sync.
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -96,6 +100,17 @@ int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
 int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream);
 bool join_supported(size_t stride);
+void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack);
+int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                    size_t stride, uint32_t b0, uint32_t b1, uint32_t *d_hi, uint32_t *d_lo, uint8_t *d_tags,
+                    uint32_t *d_len, cudaStream_t stream);
+int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, const uint32_t *d_lo,
+                const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard, uint32_t n_shards,
+                cudaStream_t stream);
+// prefilter.cu: fills the thresholds / common fields of p for a launch (shared by both entry paths)
+int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                      size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
+                      uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p);
 // prefilter.cu: work list with one item per (local row block, column block >= it), block = kShardRows
 int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream, KernelParams &p);

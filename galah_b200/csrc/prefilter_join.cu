@@ -70,37 +70,47 @@ constexpr int kMTile = kMThreads * kME;
 // ------------------------------------------------------------------------------------------
 // block-list build
 // ------------------------------------------------------------------------------------------
+// Level-0 lists of the blocks [row0 / R, ...): `total` entries starting at table row row0.
 __global__ void __launch_bounds__(256) bl_init_kernel(const uint64_t *__restrict__ hashes,
                                                       const uint32_t *__restrict__ counts, uint32_t n,
-                                                      uint32_t stride, uint64_t total,
+                                                      uint32_t stride, uint64_t row0, uint64_t total,
                                                       uint64_t *__restrict__ vals,
                                                       uint8_t *__restrict__ tags) {
     const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += step) {
-        const uint64_t row = e / stride;
-        const uint32_t col = (uint32_t)(e - row * stride);
+        const uint64_t row = row0 + e / stride;
+        const uint32_t col = (uint32_t)(e % stride);
         const bool valid = row < n && col < min(counts[row], stride);
-        vals[e] = valid ? hashes[e] : kPad;
+        vals[e] = valid ? hashes[row * stride + col] : kPad;
         tags[e] = valid ? (uint8_t)(row % kJR) : kPadTag;
     }
 }
 
+// One warp per block of the WHOLE table: largest valid hash -> gmax (every rank needs the same
+// shift), and for the blocks [b0, b1) being built the number of valid entries -> bl_len[b - b0].
 __global__ void __launch_bounds__(256) bl_len_kernel(const uint64_t *__restrict__ hashes,
                                                      const uint32_t *__restrict__ counts, uint32_t n,
-                                                     uint32_t stride, uint32_t n_blocks,
-                                                     uint32_t *__restrict__ bl_len,
+                                                     uint32_t stride, uint32_t n_blocks, uint32_t b0,
+                                                     uint32_t b1, uint32_t *__restrict__ bl_len,
                                                      unsigned long long *__restrict__ gmax) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= n_blocks) return;
     uint32_t sum = 0;
     unsigned long long mx = 0;
-    for (uint32_t r = b * kJR; r < min(n, (b + 1) * kJR); r++) {
+    for (uint32_t r = b * kJR + lane; r < min(n, (b + 1) * kJR); r += 32) {
         const uint32_t c = min(counts[r], stride);
         sum += c;
         if (c) mx = max(mx, (unsigned long long)hashes[(size_t)r * stride + c - 1]);  // rows ascend
     }
-    bl_len[b] = sum;
-    if (mx) atomicMax(gmax, mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+        if (b >= b0 && b < b1) bl_len[b - b0] = sum;
+        if (mx) atomicMax(gmax, mx);
+    }
 }
 
 __device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8_t tb) {
@@ -448,13 +458,33 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
 // ------------------------------------------------------------------------------------------
 bool join_supported(size_t stride) { return stride <= (1u << 20); }
 
-int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
-                          cudaStream_t stream) {
-    const uint32_t n = p.n, stride = p.stride;
-    const uint32_t nb = (n + kJR - 1) / kJR;
+void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack) {
+    *n_blocks = (n + kJR - 1) / kJR;
+    *entries_per_block = (size_t)kJR * stride;
+    *slack = kBlSlack;
+}
+
+// Builds the block lists of blocks [b0, b1) from the full table into d_hi / d_lo / d_tags /
+// d_len, which are SLICE-based: block b lands at offset (b - b0) * entries_per_block.
+int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                    size_t stride, uint32_t b0, uint32_t b1, uint32_t *d_hi, uint32_t *d_lo, uint8_t *d_tags,
+                    uint32_t *d_len, cudaStream_t stream) {
+    const uint32_t nb = (uint32_t)((n + kJR - 1) / kJR);
+    if (b0 > b1 || b1 > nb + 64) { set_error("blocklist_build: bad block range"); return 3; }
+    if (!ws.d_gmax) GB_CUDA(cudaMalloc(&ws.d_gmax, sizeof(unsigned long long)));
+    GB_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(unsigned long long), stream));
+    if (nb == 0) return 0;
+    int dev = 0, sms = kNumSMsFallback;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    bl_len_kernel<<<(uint32_t)(((uint64_t)std::max(nb, b1) * 32 + 255) / 256), 256, 0, stream>>>(
+        d_hashes, d_counts, (uint32_t)n, (uint32_t)stride, std::max(nb, b1), b0, b1, d_len, ws.d_gmax);
+    GB_LAUNCH_CHECK();
+    if (b1 == b0) return 0;
+
     const uint64_t bl_cap = (uint64_t)kJR * stride;
-    const uint64_t total = (uint64_t)nb * bl_cap;
-    if (ws.cap_bl < total + kBlSlack) {
+    const uint64_t total = (uint64_t)(b1 - b0) * bl_cap;
+    if (ws.cap_bl < total) {
         for (int x = 0; x < 2; x++) {
             if (ws.d_bl_vals[x]) GB_CUDA(cudaFree(ws.d_bl_vals[x]));
             if (ws.d_bl_tags[x]) GB_CUDA(cudaFree(ws.d_bl_tags[x]));
@@ -462,54 +492,46 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
         }
         ws.cap_bl = 0;
         for (int x = 0; x < 2; x++) {
-            GB_CUDA(cudaMalloc(&ws.d_bl_vals[x], (total + kBlSlack) * 8));
-            GB_CUDA(cudaMalloc(&ws.d_bl_tags[x], total + kBlSlack));
-            GB_CUDA(cudaMemsetAsync(ws.d_bl_vals[x] + total, 0xFF, kBlSlack * 8, stream));
-            GB_CUDA(cudaMemsetAsync(ws.d_bl_tags[x] + total, 0xFF, kBlSlack, stream));
+            GB_CUDA(cudaMalloc(&ws.d_bl_vals[x], total * 8));
+            GB_CUDA(cudaMalloc(&ws.d_bl_tags[x], total));
         }
-        ws.cap_bl = total + kBlSlack;
+        ws.cap_bl = total;
     }
-    if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
-    if (!ws.d_gmax) GB_CUDA(cudaMalloc(&ws.d_gmax, sizeof(unsigned long long)));
-    GB_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(unsigned long long), stream));
-
-    int dev = 0, sms = kNumSMsFallback;
-    GB_CUDA(cudaGetDevice(&dev));
-    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-
     {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 16);
-        bl_init_kernel<<<grid, 256, 0, stream>>>(p.hashes, p.counts, n, stride, total, ws.d_bl_vals[0],
-                                                 ws.d_bl_tags[0]);
-        GB_LAUNCH_CHECK();
-        bl_len_kernel<<<(nb + 255) / 256, 256, 0, stream>>>(p.hashes, p.counts, n, stride, nb, ws.d_bl_len, ws.d_gmax);
+        bl_init_kernel<<<grid, 256, 0, stream>>>(d_hashes, d_counts, (uint32_t)n, (uint32_t)stride,
+                                                 (uint64_t)b0 * kJR, total, ws.d_bl_vals[0], ws.d_bl_tags[0]);
         GB_LAUNCH_CHECK();
     }
     int src = 0;
     for (uint64_t m = stride; m < bl_cap; m *= 2) {
         const uint32_t chunks = (uint32_t)((2 * m + kMTile - 1) / kMTile);
-        const uint64_t outruns = total / (2 * m);
-        const uint64_t grid = outruns * chunks;
+        const uint64_t grid = total / (2 * m) * chunks;
         if (grid > 0x7FFFFFFFull) { set_error("prefilter: table too large for the merge grid"); return 3; }
-        // the last level writes (hi, lo) as two uint32 arrays into the destination value buffer
-        uint32_t *dhi = reinterpret_cast<uint32_t *>(ws.d_bl_vals[src ^ 1]);
-        uint32_t *dlo = dhi + (total + kBlSlack);
-        if (2 * m >= bl_cap) {
+        if (2 * m >= bl_cap)  // last level: structure-of-arrays output into the caller's buffers
             bl_merge_kernel<true><<<(uint32_t)grid, kMThreads, 0, stream>>>(
-                ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
-                ws.d_gmax, dhi, dlo);
-            p.bl_hi = dhi; p.bl_lo = dlo;
-        } else {
+                ws.d_bl_vals[src], ws.d_bl_tags[src], nullptr, d_tags, (uint32_t)m, chunks, ws.d_gmax, d_hi, d_lo);
+        else
             bl_merge_kernel<false><<<(uint32_t)grid, kMThreads, 0, stream>>>(
                 ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
-                ws.d_gmax, dhi, dlo);
-        }
+                ws.d_gmax, nullptr, nullptr);
         GB_LAUNCH_CHECK();
         src ^= 1;
     }
-    p.bl_tags = ws.d_bl_tags[src]; p.bl_len = ws.d_bl_len; p.bl_cap = bl_cap;
+    return 0;
+}
 
-    if (int rc = upload_join_work_list(ws, n, shard, n_shards, stream, p)) return rc;
+// Launches the join of one shard over block lists that cover the WHOLE table (block b at offset
+// b * entries_per_block; at least kBlSlack entries of readable slack behind the last list).
+int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, const uint32_t *d_lo,
+                const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard, uint32_t n_shards,
+                cudaStream_t stream) {
+    const uint32_t nb = (p.n + kJR - 1) / kJR;
+    p.bl_hi = d_hi; p.bl_lo = d_lo; p.bl_tags = d_tags; p.bl_len = d_len; p.bl_cap = (uint64_t)kJR * p.stride;
+    int dev = 0, sms = kNumSMsFallback;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (int rc = upload_join_work_list(ws, p.n, shard, n_shards, stream, p)) return rc;
     if (p.n_local_rb == 0) return 0;
     uint64_t n_items = 0;
     for (uint32_t rb = 0; rb < nb; rb++) if (shard_of_group(rb, n_shards) == shard) n_items += nb - rb;
@@ -521,6 +543,31 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
     GB_LAUNCH_CHECK();
     if (ws.record(2, stream)) return 2;
     return 0;
+}
+
+// Single-device path: build every list into workspace-owned arrays, then join.
+int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
+                          cudaStream_t stream) {
+    const uint32_t nb = (p.n + kJR - 1) / kJR;
+    const uint64_t total = (uint64_t)nb * kJR * p.stride;
+    if (ws.cap_fin < total + kBlSlack) {
+        if (ws.d_fin_hi) GB_CUDA(cudaFree(ws.d_fin_hi));
+        if (ws.d_fin_lo) GB_CUDA(cudaFree(ws.d_fin_lo));
+        if (ws.d_fin_tags) GB_CUDA(cudaFree(ws.d_fin_tags));
+        ws.d_fin_hi = ws.d_fin_lo = nullptr; ws.d_fin_tags = nullptr; ws.cap_fin = 0;
+        GB_CUDA(cudaMalloc(&ws.d_fin_hi, (total + kBlSlack) * 4));
+        GB_CUDA(cudaMalloc(&ws.d_fin_lo, (total + kBlSlack) * 4));
+        GB_CUDA(cudaMalloc(&ws.d_fin_tags, total + kBlSlack));
+        GB_CUDA(cudaMemsetAsync(ws.d_fin_hi + total, 0xFF, kBlSlack * 4, stream));
+        GB_CUDA(cudaMemsetAsync(ws.d_fin_lo + total, 0xFF, kBlSlack * 4, stream));
+        GB_CUDA(cudaMemsetAsync(ws.d_fin_tags + total, 0xFF, kBlSlack, stream));
+        ws.cap_fin = total + kBlSlack;
+    }
+    if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
+    if (int rc = blocklist_build(ws, p.hashes, p.counts, p.n, p.stride, 0, nb, ws.d_fin_hi, ws.d_fin_lo,
+                                 ws.d_fin_tags, ws.d_bl_len, stream))
+        return rc;
+    return join_launch(ws, p, ws.d_fin_hi, ws.d_fin_lo, ws.d_fin_tags, ws.d_bl_len, shard, n_shards, stream);
 }
 
 }  // namespace gb200

@@ -118,6 +118,28 @@ int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_cou
                                  uint32_t n_shards, int mode, void *stream, uint32_t *d_cand,
                                  size_t cand_cap, unsigned long long *d_n_cand);
 
+/* Two-phase form of the block-list join for multi-GPU runs, so that the BUILD shards too: every
+ * rank builds the lists of a contiguous slice of blocks from the (all-gathered) table, the slices
+ * are all-gathered (9 bytes per table entry), and every rank joins its row-block shard.
+ *   layout: n_blocks = ceil(n / 64) lists of entries_per_block = 64 * stride entries each; the
+ *           gathered arrays need `slack` readable entries behind the last list.
+ *   build:  lists of blocks [block_begin, block_end) -> d_hi / d_lo (uint32), d_tags (uint8),
+ *           d_len (uint32), all SLICE-based (block b at offset (b - block_begin) * entries_per_block).
+ *           block_end may exceed n_blocks (empty lists) so that slices are equal-sized.
+ *   join:   d_hi / d_lo / d_tags / d_len cover blocks 0 .. (block b at b * entries_per_block).
+ * All pointers are device pointers; everything is enqueued on `stream`. */
+int galah_b200_blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block,
+                                size_t *slack);
+int galah_b200_blocklist_build(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                               size_t stride, size_t block_begin, size_t block_end, uint32_t *d_hi,
+                               uint32_t *d_lo, uint8_t *d_tags, uint32_t *d_len, void *stream);
+int galah_b200_prefilter_join_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                                      size_t stride, uint8_t k, float min_ani, const uint32_t *d_hi,
+                                      const uint32_t *d_lo, const uint8_t *d_tags,
+                                      const uint32_t *d_len, uint32_t shard, uint32_t n_shards,
+                                      void *stream, uint32_t *d_cand, size_t cand_cap,
+                                      unsigned long long *d_n_cand);
+
 /* Whole `finch::distances(paths, min_ani, num_kmers, kmer_length)` (src/finch.rs:48-97):
  * sketch every path on the GPU, then the all-pairs prefilter. */
 int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani,

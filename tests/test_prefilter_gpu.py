@@ -119,6 +119,48 @@ def test_modes_agree_on_candidates(gb):
     assert out[0].shape == out[1].shape and np.array_equal(out[0], out[1])
 
 
+def test_sliced_blocklist_build_then_join_matches(gb, kernel_mode):
+    """The multi-GPU form: lists built in 3 equal slices (last one padded past the table), gathered,
+    then joined per shard -- the union of the shards' candidates equals the one-call result."""
+    if kernel_mode != 0:
+        pytest.skip("block lists belong to the join path")
+    import torch
+    rng = np.random.default_rng(43)
+    n, s, G = 500, 1000, 3
+    table, counts = random_family_table(n, s, rng, ragged=True)
+    d_t = torch.from_numpy(table.view(np.int64)).cuda()
+    d_c = torch.from_numpy(counts.view(np.int32)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    nb, epb, slack = gb.blocklist_layout(n, s)
+    nbp = (nb + G - 1) // G
+    hi = torch.zeros(G * nbp * epb + slack, dtype=torch.int32, device="cuda")
+    lo = torch.zeros_like(hi)
+    tags = torch.zeros(G * nbp * epb + slack, dtype=torch.uint8, device="cuda")
+    ln = torch.zeros(G * nbp, dtype=torch.int32, device="cuda")
+    for r in range(G):  # what each rank would build, written straight into its slot of the gathered arrays
+        off = r * nbp * epb
+        gb.blocklist_build(d_t.data_ptr(), d_c.data_ptr(), n, s, r * nbp, (r + 1) * nbp,
+                           hi[off:].data_ptr(), lo[off:].data_ptr(), tags[off:].data_ptr(), ln[r * nbp:].data_ptr(), st)
+    cap = 1 << 20
+    got = []
+    for shard in range(G):
+        d_cand = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+        d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+        gb.prefilter_join_enqueue(d_t.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, hi.data_ptr(), lo.data_ptr(),
+                                  tags.data_ptr(), ln.data_ptr(), shard, G, st, d_cand.data_ptr(), cap, d_n.data_ptr())
+        torch.cuda.synchronize()
+        got.append(d_cand[: int(d_n.item())].cpu().numpy().view(np.uint32))
+    got = np.concatenate(got)
+    got = got[np.lexsort((got[:, 1], got[:, 0]))]
+    d_cand = torch.zeros((cap, 4), dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    gb.prefilter_enqueue(d_t.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, 0, 1, 0, st, d_cand.data_ptr(), cap, d_n.data_ptr())
+    torch.cuda.synchronize()
+    exp = d_cand[: int(d_n.item())].cpu().numpy().view(np.uint32)
+    exp = exp[np.lexsort((exp[:, 1], exp[:, 0]))]
+    assert got.shape == exp.shape and np.array_equal(got, exp) and len(exp) > 0
+
+
 def test_large_sketches_use_generic_kernel(gb):
     rng = np.random.default_rng(17)
     table, counts = random_family_table(24, 2000, rng)
