@@ -168,6 +168,9 @@ def main():
     torch.cuda.set_device(local_rank)
     gb.init(local_rank)
     if world > 1:
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.current_stream()
