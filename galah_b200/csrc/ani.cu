@@ -21,8 +21,10 @@
 //   ani_chain_kernel  one THREAD per (pair, query chunk): walks the chunk's seeds in order,
 //                     probes the reference genome's hash table (<= 8 occurrences, emitted in
 //                     ascending reference position), and runs the banded chaining DP over a ring
-//                     of the last 32 anchors held in shared memory ([slot][field][thread], so a
-//                     warp's accesses never conflict).  Each anchor carries (count, first seed,
+//                     of the last 16 anchors held in shared memory ([slot][field][thread], so a
+//                     warp's accesses never conflict).  The walk is a state machine (advance to
+//                     the next anchor, then one chaining step) so that the lanes of a warp --
+//                     different chunks -- run the chaining step converged.  Each anchor carries (count, first seed,
 //                     first reference position) of its best chain, so no backtracking pass.
 //                     Accepted chunks add (M-2, N-2, covq, covr) to the pair's accumulators.
 //                     Bound: latency of random 8-byte reads of the reference table (L2/HBM);
@@ -250,61 +252,72 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     uint32_t n_anchor = 0;
     int best_f = 0, best_first_r = 0, best_last_r = 0;
     uint32_t best_cnt = 0, best_first_x = 0, best_last_x = 0;
-    for (uint32_t x = x0; x < x1; x++) {
-        const uint32_t ks = qks[x], km = ks >> 1, qs = ks & 1;
-        const int qpos = (int)qsp[x];
-        // occurrences of km in the reference
-        const uint32_t home = table_slot(km, mask);
-        uint32_t occ = 0;
-        for (uint32_t slot = home;; slot = (slot + 1) & mask) {
-            const unsigned long long e = table[slot];
-            if (e == kEmpty) break;
-            occ += (uint32_t)(e >> 33) == km ? 1u : 0u;
-        }
-        if (occ == 0 || occ > (uint32_t)kAniMaxOcc) continue;
-        long long prev = -1;  // matches in ascending (strand << 32 | spread) is NOT the order: sort by spread
-        for (uint32_t m = 0; m < occ; m++) {
-            // next match in ascending reference spread position
-            unsigned long long pick = kEmpty;
+    // The lanes of a warp are different chunks.  To keep them converged in the expensive part, the
+    // walk is a state machine: every lane first advances (cheap, divergent) to its next anchor --
+    // the next seed with 1..8 occurrences in the reference, then occurrence m of that seed in
+    // ascending reference position -- and then ALL lanes run one chaining step together.
+    uint32_t x = x0 - 1, occ = 0, m = 0, km = 0, qs = 0, home = 0;
+    int qpos = 0;
+    long long prev = -1;
+    bool alive = true;
+    for (;;) {
+        while (alive && m == occ) {
+            x++;
+            if (x >= x1) { alive = false; break; }
+            const uint32_t ks = qks[x];
+            km = ks >> 1; qs = ks & 1; qpos = (int)qsp[x];
+            home = table_slot(km, mask);
+            uint32_t c = 0;
             for (uint32_t slot = home;; slot = (slot + 1) & mask) {
                 const unsigned long long e = table[slot];
                 if (e == kEmpty) break;
-                if ((uint32_t)(e >> 33) != km) continue;
-                const long long sp = (long long)(uint32_t)e;
-                if (sp > prev && (pick == kEmpty || sp < (long long)(uint32_t)pick)) pick = e;
+                c += (uint32_t)(e >> 33) == km ? 1u : 0u;
             }
-            prev = (long long)(uint32_t)pick;
-            const int rpos = (int)(uint32_t)pick;
-            const uint32_t rel = qs ^ (uint32_t)((pick >> 32) & 1);
-            int f = kAniAlpha, first_r = rpos;
-            uint32_t cnt = 1, first_x = x - x0;
-            const uint32_t look = min(n_anchor, (uint32_t)kAniH);
-            for (uint32_t b = 1; b <= look; b++) {
-                const uint32_t slot = (n_anchor - b) % kAniH;
-                const int dq = qpos - RING(slot, 0);
-                if (dq > kAniBand) break;
-                const uint32_t meta = (uint32_t)RING(slot, 3);
-                if (dq <= 0 || (meta >> 31) != rel) continue;
-                const int rb = RING(slot, 1);
-                const int dr = rel ? rb - rpos : rpos - rb;
-                if (dr <= 0 || dr > kAniBand) continue;
-                const int gap = abs(dq - dr);
-                if (gap > kAniMaxGap) continue;
-                const int cand = RING(slot, 2) + kAniAlpha - gap;
-                if (cand > f) {
-                    f = cand; cnt = ((meta >> 16) & 0x7FFFu) + 1; first_x = meta & 0xFFFFu;
-                    first_r = RING(slot, 4);
-                }
+            occ = c > (uint32_t)kAniMaxOcc ? 0u : c;
+            m = 0; prev = -1;
+        }
+        if (!alive) break;
+        // occurrence m: the smallest reference position above the previous one
+        unsigned long long pick = kEmpty;
+        for (uint32_t slot = home;; slot = (slot + 1) & mask) {
+            const unsigned long long e = table[slot];
+            if (e == kEmpty) break;
+            if ((uint32_t)(e >> 33) != km) continue;
+            const long long sp = (long long)(uint32_t)e;
+            if (sp > prev && (pick == kEmpty || sp < (long long)(uint32_t)pick)) pick = e;
+        }
+        prev = (long long)(uint32_t)pick;
+        m++;
+        const int rpos = (int)(uint32_t)pick;
+        const uint32_t rel = qs ^ (uint32_t)((pick >> 32) & 1);
+        int f = kAniAlpha, first_r = rpos;
+        uint32_t cnt = 1, first_x = x - x0;
+        const uint32_t look = min(n_anchor, (uint32_t)kAniH);
+        for (uint32_t b = 1; b <= look; b++) {
+            const uint32_t slot = (n_anchor - b) % kAniH;
+            const int dq = qpos - RING(slot, 0);
+            if (dq > kAniBand) break;
+            const uint32_t meta = (uint32_t)RING(slot, 3);
+            if (dq <= 0 || (meta >> 31) != rel) continue;
+            const int rb = RING(slot, 1);
+            const int dr = rel ? rb - rpos : rpos - rb;
+            if (dr <= 0 || dr > kAniBand) continue;
+            const int gap = abs(dq - dr);
+            if (gap > kAniMaxGap) continue;
+            const int cand = RING(slot, 2) + kAniAlpha - gap;
+            if (cand > f) {
+                f = cand; cnt = ((meta >> 16) & 0x7FFFu) + 1; first_x = meta & 0xFFFFu;
+                first_r = RING(slot, 4);
             }
-            const uint32_t slot = n_anchor % kAniH;
-            RING(slot, 0) = qpos; RING(slot, 1) = rpos; RING(slot, 2) = f;
-            RING(slot, 3) = (int)((rel << 31) | (cnt << 16) | first_x);
-            RING(slot, 4) = first_r;
-            n_anchor++;
-            if (f > best_f) {
-                best_f = f; best_cnt = cnt; best_first_x = first_x; best_last_x = x - x0;
-                best_first_r = first_r; best_last_r = rpos;
-            }
+        }
+        const uint32_t slot = n_anchor % kAniH;
+        RING(slot, 0) = qpos; RING(slot, 1) = rpos; RING(slot, 2) = f;
+        RING(slot, 3) = (int)((rel << 31) | (cnt << 16) | first_x);
+        RING(slot, 4) = first_r;
+        n_anchor++;
+        if (f > best_f) {
+            best_f = f; best_cnt = cnt; best_first_x = first_x; best_last_x = x - x0;
+            best_first_r = first_r; best_last_r = rpos;
         }
     }
 #undef RING

@@ -18,7 +18,7 @@ constexpr uint32_t kAniChunk = 20000;
 constexpr int kAniBand = 2500;
 constexpr int kAniMaxGap = 300;
 constexpr int kAniAlpha = 20;
-constexpr int kAniH = 32;
+constexpr int kAniH = 16;
 constexpr int kAniMaxOcc = 8;
 constexpr int kAniMinAnchors = 3;
 

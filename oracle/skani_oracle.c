@@ -28,7 +28,7 @@
  *              same canonical k-mer, unless that k-mer occurs more than MAXOCC = 8 times in the
  *              reference; matches in ascending reference spread position.
  *              rel = strand_q xor strand_r.
- *   chaining   f(a) = max(ALPHA, max_b f(b) + ALPHA - |dq - dr|) over the previous H = 32 anchors b
+ *   chaining   f(a) = max(ALPHA, max_b f(b) + ALPHA - |dq - dr|) over the previous H = 16 anchors b
  *              (most recent first, scan stops at the first b with dq > BAND) that have the same
  *              rel, 0 < dq <= BAND, 0 < dr <= BAND (dr measured in chain direction) and
  *              |dq - dr| <= MAXGAP = 300; strict improvement only, so ties keep the more recent b.
@@ -53,7 +53,7 @@
 #define SK_BAND 2500
 #define SK_MAXGAP 300
 #define SK_ALPHA 20
-#define SK_H 32
+#define SK_H 16
 #define SK_MAXOCC 8
 #define SK_MIN_ANCHORS 3
 
