@@ -303,17 +303,27 @@ def main():
                  "ms_per_step": o_total / o_steps, "steps": o_steps, "main_kernel_ms": o_main,
                  "candidates": int(d_ncand.item())}
 
-    # ---------------- e2e: host buffers through the C ABI (H2D + kernel + D2H + host finish)
+    # ---------------- e2e: host buffers through the public API (H2D + kernels + D2H + host finish)
+    # 1 GPU: the host-buffer C-ABI call.  G GPUs: galah_b200.distributed.ShardedPrefilter -- every
+    # rank uploads ITS slice of the table, all-gather over NVLink, sharded build + join.
     h_table = table.cpu().pin_memory()
     h_counts = counts.cpu().pin_memory()
     np_table = h_table.numpy().view(np.uint64)   # views of the pinned host buffers
     np_counts = h_counts.numpy().view(np.uint32)
     e2e_times = []
     n_pass = 0
+    if world > 1:
+        from galah_b200.distributed import ShardedPrefilter
+        sp = ShardedPrefilter(gb, dist, n_local, S, dev)
+        h_my_table = h_table[rank * n_local:(rank + 1) * n_local]
+        h_my_counts = h_counts[rank * n_local:(rank + 1) * n_local]
     for it in range(2 + min(args.steps, 5)):
         sync_all()
         t0 = time.perf_counter()
-        res = gb.prefilter(np_table, np_counts, K, MIN_ANI, shard=rank, n_shards=world)
+        if world > 1:
+            res = sp(h_my_table, h_my_counts, K, MIN_ANI)
+        else:
+            res = gb.prefilter(np_table, np_counts, K, MIN_ANI, shard=rank, n_shards=world)
         dt = time.perf_counter() - t0
         n_pass = len(res)
         if it >= 2:
@@ -324,7 +334,7 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n_pass_t, op=dist.ReduceOp.SUM)
     e2e_value = pairs / float(e2e_t.item())
-    h2d = h_table.numel() * 8 + h_counts.numel() * 4
+    h2d = h_table.numel() * 8 + h_counts.numel() * 4  # whole job: at G GPUs every rank uploads 1/G of it
     d2h = int(n_pass) * 16 + 8
 
     # ---------------- stage 2: ANI of every prefilter survivor (K3), then the greedy engine

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "galah_b200_prefilter_enqueue": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint8,
                                                     ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32,
                                                     ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
+    "galah_b200_finish_candidates": (ctypes.c_int, [vp, ctypes.c_size_t, ctypes.c_uint8, ctypes.c_float, pairpp, sizep]),
     "galah_b200_blocklist_layout": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_size_t, sizep, sizep, sizep]),
     "galah_b200_blocklist_build": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
                                                   ctypes.c_size_t, vp, vp, vp, vp, vp]),

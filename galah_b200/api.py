@@ -129,6 +129,17 @@ def prefilter_enqueue(d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards
                                              shard, n_shards, mode, stream, d_cand, cand_cap, d_n_cand))
 
 
+def finish_candidates(cand, k=21, min_ani=0.9):
+    """Device candidates (n x 4 uint32 {i, j, common, total}, already on the host) -> PAIR_DTYPE records
+    after the reference's f64 formula / threshold / f32 store, sorted by (i, j)."""
+    cand = np.ascontiguousarray(cand, np.uint32).reshape(-1, 4)
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    check(lib().galah_b200_finish_candidates(cand.ctypes.data, len(cand), k, ctypes.c_float(min_ani),
+                                             ctypes.byref(out), ctypes.byref(n_out)))
+    return _take_pairs(out, n_out)
+
+
 def blocklist_layout(n, stride):
     """(n_blocks, entries_per_block, slack) of the block lists of an n x stride sketch table."""
     a, b, c = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)

@@ -72,6 +72,28 @@ struct DevBuf {
     }
 };
 
+// Integer candidates {i, j, common, total} -> the reference's f64 formula, threshold and f32 store
+// (src/finch.rs:78-93), sorted by (i, j).  Host only.
+static int finish_candidates(const uint4 *cand, size_t n_cand, int k, float min_ani, galah_b200_pair_t **out,
+                             size_t *n_out) {
+    std::vector<galah_b200_pair_t> pass;
+    pass.reserve(n_cand);
+    const double thr = (double)min_ani;
+    for (size_t x = 0; x < n_cand; x++) {
+        const uint4 &c = cand[x];
+        const double ani = mash_ani_f64(c.z, c.w, k);
+        if (ani >= thr) pass.push_back(galah_b200_pair_t{c.x, c.y, c.z, c.w, (float)ani});
+    }
+    std::sort(pass.begin(), pass.end(), [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) {
+        return a.i != b.i ? a.i < b.i : a.j < b.j;
+    });
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(pass.size(), 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!pass.empty()) memcpy(res, pass.data(), pass.size() * sizeof(galah_b200_pair_t));
+    *out = res; *n_out = pass.size();
+    return 0;
+}
+
 // Run the prefilter kernels for one shard and finish the survivors on the host in f64
 // (reference: src/finch.rs:78-93).
 static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
@@ -102,21 +124,7 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
         }
         break;
     }
-    std::vector<galah_b200_pair_t> pass;
-    pass.reserve(cand.size());
-    const double thr = (double)min_ani;
-    for (const uint4 &c : cand) {
-        const double ani = mash_ani_f64(c.z, c.w, k);
-        if (ani >= thr) pass.push_back(galah_b200_pair_t{c.x, c.y, c.z, c.w, (float)ani});
-    }
-    std::sort(pass.begin(), pass.end(), [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) {
-        return a.i != b.i ? a.i < b.i : a.j < b.j;
-    });
-    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(pass.size(), 1) * sizeof(galah_b200_pair_t));
-    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
-    if (!pass.empty()) memcpy(res, pass.data(), pass.size() * sizeof(galah_b200_pair_t));
-    *out = res; *n_out = pass.size();
-    return 0;
+    return finish_candidates(cand.data(), cand.size(), k, min_ani, out, n_out);
 }
 
 // One pass over FASTA files feeding K1 (sketches) and/or the K3 index from the SAME upload:
@@ -326,6 +334,12 @@ int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_cou
     cudaStream_t st = (cudaStream_t)stream;
     return prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, mode,
                              st, reinterpret_cast<uint4 *>(d_cand), cand_cap, d_n_cand);
+}
+
+int galah_b200_finish_candidates(const uint32_t *cand, size_t n_cand, uint8_t k, float min_ani,
+                                 galah_b200_pair_t **out, size_t *n_out) {
+    *out = nullptr; *n_out = 0;
+    return finish_candidates(reinterpret_cast<const uint4 *>(cand), n_cand, k, min_ani, out, n_out);
 }
 
 int galah_b200_blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack) {

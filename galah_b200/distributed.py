@@ -68,3 +68,66 @@ def gpu_shard_fn(gb):
         return gb.prefilter_device(table.data_ptr(), counts.data_ptr(), n, s, k, min_ani, shard, n_shards,
                                    torch.cuda.current_stream().cuda_stream)
     return fn
+
+
+class ShardedPrefilter:
+    """The N-GPU stage-1 prefilter behind one call (the public multi-GPU API; bench.py's `e2e` at
+    --gpus > 1): every rank passes ITS slice of the sketch table in host memory; per call the rank
+    uploads the slice (H2D), the table is all-gathered over NVLink, every rank builds 1/G of the
+    block lists, the lists are all-gathered, every rank joins its row-block shard and finishes its
+    candidates on the host.  Buffers are allocated once and re-used."""
+
+    def __init__(self, gb, dist, n_local, stride, device):
+        import torch
+        self.gb, self.dist, self.torch = gb, dist, torch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.n_local, self.s, self.dev = n_local, stride, device
+        n = self.n = n_local * self.world
+        t = torch
+        self.my_table = t.empty((n_local, stride), dtype=t.int64, device=device)
+        self.my_counts = t.empty(n_local, dtype=t.int32, device=device)
+        self.table = t.empty((n, stride), dtype=t.int64, device=device)
+        self.counts = t.empty(n, dtype=t.int32, device=device)
+        nb, epb, slack = gb.blocklist_layout(n, stride)
+        self.nbp = nbp = (nb + self.world - 1) // self.world
+        self.epb = epb
+        self.my_hi = t.empty(nbp * epb, dtype=t.int32, device=device)
+        self.my_lo = t.empty_like(self.my_hi)
+        self.my_tags = t.empty(nbp * epb, dtype=t.uint8, device=device)
+        self.my_len = t.empty(nbp, dtype=t.int32, device=device)
+        self.all_hi = t.zeros(self.world * nbp * epb + slack, dtype=t.int32, device=device)
+        self.all_lo = t.zeros_like(self.all_hi)
+        self.all_tags = t.zeros(self.world * nbp * epb + slack, dtype=t.uint8, device=device)
+        self.all_len = t.empty(self.world * nbp, dtype=t.int32, device=device)
+        self.cand_cap = max(1 << 20, 64 * n)
+        self.d_cand = t.empty((self.cand_cap, 4), dtype=t.int32, device=device)
+        self.d_ncand = t.zeros(1, dtype=t.int64, device=device)
+        self.h_cand = t.empty((self.cand_cap, 4), dtype=t.int32).pin_memory()
+
+    def __call__(self, h_table, h_counts, k=21, min_ani=0.9):
+        """h_table / h_counts: this rank's slice as (pinned) host torch tensors (int64 / int32 views of
+        the uint64 / uint32 data).  Returns this rank's PAIR_DTYPE records, sorted by (i, j)."""
+        t, gb, dist = self.torch, self.gb, self.dist
+        st = t.cuda.current_stream().cuda_stream
+        n, s, w, r = self.n, self.s, self.world, self.rank
+        self.my_table.copy_(h_table, non_blocking=True)
+        self.my_counts.copy_(h_counts, non_blocking=True)
+        dist.all_gather_into_tensor(self.table, self.my_table)
+        dist.all_gather_into_tensor(self.counts, self.my_counts)
+        gb.blocklist_build(self.table.data_ptr(), self.counts.data_ptr(), n, s, r * self.nbp, (r + 1) * self.nbp,
+                           self.my_hi.data_ptr(), self.my_lo.data_ptr(), self.my_tags.data_ptr(),
+                           self.my_len.data_ptr(), st)
+        m = w * self.nbp * self.epb
+        dist.all_gather_into_tensor(self.all_hi[:m], self.my_hi)
+        dist.all_gather_into_tensor(self.all_lo[:m], self.my_lo)
+        dist.all_gather_into_tensor(self.all_tags[:m], self.my_tags)
+        dist.all_gather_into_tensor(self.all_len, self.my_len)
+        gb.prefilter_join_enqueue(self.table.data_ptr(), self.counts.data_ptr(), n, s, k, min_ani,
+                                  self.all_hi.data_ptr(), self.all_lo.data_ptr(), self.all_tags.data_ptr(),
+                                  self.all_len.data_ptr(), r, w, st, self.d_cand.data_ptr(), self.cand_cap,
+                                  self.d_ncand.data_ptr())
+        got = int(self.d_ncand.item())  # D2H + sync
+        if got > self.cand_cap:
+            raise RuntimeError("candidate buffer too small")
+        self.h_cand[:got].copy_(self.d_cand[:got])
+        return gb.finish_candidates(self.h_cand[:got].numpy().view(np.uint32), k, min_ani)

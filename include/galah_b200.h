@@ -118,6 +118,12 @@ int galah_b200_prefilter_enqueue(const uint64_t *d_hashes, const uint32_t *d_cou
                                  uint32_t n_shards, int mode, void *stream, uint32_t *d_cand,
                                  size_t cand_cap, unsigned long long *d_n_cand);
 
+/* Host finish of device candidates (n_cand x {i, j, common, total} as 4 x uint32, copied back
+ * by the caller): the reference's f64 Mash-ANI formula, the `>= min_ani as f64` test and the f32
+ * store (src/finch.rs:78-93); result sorted by (i, j).  Pure host code. */
+int galah_b200_finish_candidates(const uint32_t *cand, size_t n_cand, uint8_t k, float min_ani,
+                                 galah_b200_pair_t **out, size_t *n_out);
+
 /* Two-phase form of the block-list join for multi-GPU runs, so that the BUILD shards too: every
  * rank builds the lists of a contiguous slice of blocks from the (all-gathered) table, the slices
  * are all-gathered (9 bytes per table entry), and every rank joins its row-block shard.

@@ -161,6 +161,26 @@ def test_sliced_blocklist_build_then_join_matches(gb, kernel_mode):
     assert got.shape == exp.shape and np.array_equal(got, exp) and len(exp) > 0
 
 
+def test_sharded_prefilter_driver_single_rank(gb, kernel_mode):
+    """galah_b200.distributed.ShardedPrefilter (the multi-GPU public API) on a 1-rank NCCL group."""
+    if kernel_mode != 0:
+        pytest.skip("driver uses the join path")
+    import torch
+    import torch.distributed as dist
+    from galah_b200.distributed import ShardedPrefilter
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    rng = np.random.default_rng(47)
+    n, s = 400, 1000
+    table, counts = random_family_table(n, s, rng)
+    sp = ShardedPrefilter(gb, dist, n, s, torch.device("cuda", 0))
+    h_t = torch.from_numpy(table.view(np.int64)).pin_memory()
+    h_c = torch.from_numpy(counts.view(np.int32)).pin_memory()
+    for _ in range(2):
+        assert_pairs_equal(sp(h_t, h_c, 21, 0.9), oracle.prefilter(table, counts, 21, 0.9))
+
+
 def test_large_sketches_use_generic_kernel(gb):
     rng = np.random.default_rng(17)
     table, counts = random_family_table(24, 2000, rng)
