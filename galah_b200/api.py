@@ -305,6 +305,17 @@ def cluster(genomes, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0, sm
     return clusters, info
 
 
+GENOME_STATS_DTYPE = np.dtype([("num_contigs", "<u8"), ("num_ambiguous_bases", "<u8"), ("n50", "<u8")])
+
+
+def genome_stats(paths, threads=0):
+    """galah::genome_stats::calculate_genome_stats (reference src/genome_stats.rs:11-51) for each path
+    (host side of the ingest pass; needs no device)."""
+    out = np.zeros(len(paths), GENOME_STATS_DTYPE)
+    check(lib().galah_b200_genome_stats(_paths_array(paths), len(paths), threads, out.ctypes.data))
+    return out
+
+
 def synth_layout(n, length):
     """Sizes (in uint32 / uint64 elements) of the packed buffers for n synthetic genomes."""
     padded = (length + 127) // 128 * 128

@@ -618,6 +618,33 @@ void galah_b200_clusters_free(galah_b200_clusters_t *c) {
     memset(c, 0, sizeof(*c));
 }
 
+int galah_b200_genome_stats(const char *const *paths, size_t n, int host_threads, galah_b200_genome_stats_t *out) {
+    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::vector<std::string> errs(n);
+    std::vector<int> rcs(n, 0);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t x = next.fetch_add(1);
+            if (x >= n) break;
+            PackedGenome pg;
+            rcs[x] = pack_fasta_file(paths[x], pg, false, errs[x]);
+            if (rcs[x]) continue;
+            const GenomeAssemblyStats st = genome_stats(pg);
+            if (!st.n50_valid) { rcs[x] = GALAH_B200_ERR_UNSUPPORTED; errs[x] = std::string("Failed to calculate n50 from ") + paths[x]; continue; }
+            out[x] = galah_b200_genome_stats_t{st.num_contigs, st.num_ambiguous_bases, st.n50};
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>((size_t)host_threads, std::max<size_t>(n, 1));
+    for (int t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    for (size_t x = 0; x < n; x++)
+        if (rcs[x]) { set_error(errs[x]); return rcs[x] == GALAH_B200_ERR_UNSUPPORTED ? rcs[x] : GALAH_B200_ERR_IO; }
+    return 0;
+}
+
 int galah_b200_synth_packed_device(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,
                                    uint32_t *d_seq2, uint32_t *d_valid, uint64_t *d_base_off, void *stream) {
     std::lock_guard<std::mutex> lock(g_mu);

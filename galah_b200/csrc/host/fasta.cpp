@@ -2,6 +2,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 // zlib ships as a shared object in this image but without its header; these three entry points
 // are ABI-stable.  gzread() passes non-gzip files through unchanged.
 extern "C" {
@@ -46,7 +48,7 @@ struct Packer {
         for (size_t i = 0; i < len; i++) {
             const uint8_t c = kNorm.t[p[i]];
             if (c == 5) continue;
-            if (c == 4) { g.n_ambiguous++; push(0, false); }
+            if (c == 4) { g.n_ambiguous++; g.n_N += (p[i] == 'N' || p[i] == 'n'); push(0, false); }
             else push(c, true);
         }
     }
@@ -62,7 +64,22 @@ struct Packer {
 
 void PackedGenome::clear() {
     seq2.clear(); valid.clear(); n_bases = 0; rec_start.clear(); rec_end.clear(); rec_name.clear();
-    n_ambiguous = 0;
+    n_ambiguous = 0; n_N = 0;
+}
+
+GenomeAssemblyStats genome_stats(const PackedGenome &g) {
+    GenomeAssemblyStats st{g.rec_start.size(), g.n_N, 0, false};
+    std::vector<uint64_t> len(g.rec_start.size());
+    uint64_t total = 0;
+    for (size_t r = 0; r < len.size(); r++) { len[r] = g.rec_end[r] - g.rec_start[r]; total += len[r]; }
+    std::sort(len.begin(), len.end());
+    const uint64_t cutoff = total / 2;
+    uint64_t sum = 0;
+    for (uint64_t l : len) {
+        sum += l;
+        if (sum >= cutoff) { st.n50 = l; st.n50_valid = true; break; }
+    }
+    return st;
 }
 
 int read_file_bytes(const std::string &path, std::vector<uint8_t> &out, std::string &err) {

@@ -22,6 +22,7 @@ struct PackedGenome {
     std::vector<uint64_t> rec_start, rec_end;
     std::vector<std::string> rec_name;  // header up to first whitespace (needletail `id` prefix)
     uint64_t n_ambiguous = 0;           // bases that were not ACGT
+    uint64_t n_N = 0;                   // bases that were literally 'N' or 'n' (genome_stats.rs:27-31)
     void clear();
     // pad seq2/valid so that n_bases rounds up to a multiple of 128 with invalid bases
     uint64_t padded_bases() const { return (n_bases + 127) / 128 * 128; }
@@ -32,6 +33,12 @@ int read_file_bytes(const std::string &path, std::vector<uint8_t> &out, std::str
 int pack_fasta_bytes(const uint8_t *data, size_t n, PackedGenome &out, bool keep_names,
                      std::string &err);
 int pack_fasta_file(const std::string &path, PackedGenome &out, bool keep_names, std::string &err);
+
+// galah::genome_stats::calculate_genome_stats (/root/reference/src/genome_stats.rs:11-51) from the
+// metadata the ingest pass already has: record count, literal N/n count, and the reference's N50
+// (lengths sorted ASCENDING, first length at which the running sum reaches total/2).
+struct GenomeAssemblyStats { uint64_t num_contigs, num_ambiguous_bases, n50; bool n50_valid; };
+GenomeAssemblyStats genome_stats(const PackedGenome &g);
 
 // Packs raw (un-normalised) records that are already in memory (tests / synthetic inputs).
 void pack_records(const std::vector<std::string> &records, PackedGenome &out);

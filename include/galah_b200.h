@@ -245,6 +245,17 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
                              int host_threads, galah_b200_clusters_t *out,
                              galah_b200_cluster_stats_t *stats);
 
+/* ---- quality-ordering inputs (host logic) ---------------------------------------------------
+ * Replaces galah::genome_stats::calculate_genome_stats (src/genome_stats.rs:11-51), the per-genome
+ * inputs of the Parks2020 / dRep quality formulas: a by-product of the same ingest pass that packs
+ * the sequence.  n50 follows the reference exactly (contig lengths sorted ascending, first length at
+ * which the running sum reaches total/2); num_ambiguous_bases counts literal N / n only. */
+typedef struct galah_b200_genome_stats {
+    uint64_t num_contigs, num_ambiguous_bases, n50;
+} galah_b200_genome_stats_t;
+int galah_b200_genome_stats(const char *const *paths, size_t n, int host_threads,
+                            galah_b200_genome_stats_t *out);
+
 /* ---- synthetic genomes (bench / tests) ------------------------------------- */
 /* Generates genomes [index_begin, index_begin+n) of `length` bases each directly in packed
  * form on the device.  d_seq2 needs n * words_per_genome uint32 with
