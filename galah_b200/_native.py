@@ -104,6 +104,11 @@ _SIGNATURES = {
     "galah_b200_cluster_files": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                                 ctypes.c_int, ctypes.c_int, ctypes.POINTER(Clusters),
                                                 ctypes.POINTER(ClusterStats)]),
+    "galah_b200_skani_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_int, pairpp, sizep, sizep]),
+    "galah_b200_cluster_files_skani": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
+                                                      ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),
     "galah_b200_genome_stats": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_int, vp]),
     "galah_b200_synth_packed_device": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
                                                       ctypes.c_uint64, vp, vp, vp, vp]),

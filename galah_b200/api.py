@@ -305,6 +305,33 @@ def cluster(genomes, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0, sm
     return clusters, info
 
 
+def skani_distances(paths, threshold=90.0, min_aligned_fraction=15.0, small_genomes=False, contigs=False, threads=0):
+    """GPU replacement for SkaniPreclusterer::distances / distances_contigs (reference
+    src/skani.rs:21-56).  Returns (PAIR_DTYPE hits with ANI in percent, number of units)."""
+    out = ctypes.POINTER(Pair)()
+    n_out, n_units = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    check(lib().galah_b200_skani_distances(_paths_array(paths), len(paths), ctypes.c_float(threshold),
+                                           ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+                                           int(bool(contigs)), threads, ctypes.byref(out), ctypes.byref(n_out),
+                                           ctypes.byref(n_units)))
+    return _take_pairs(out, n_out), int(n_units.value)
+
+
+def cluster_skani(genomes, precluster_ani=90.0, ani=95.0, min_aligned_fraction=15.0, small_genomes=False,
+                  cluster_contigs=False, threads=0):
+    """galah::clusterer::cluster() with SkaniPreclusterer + SkaniClusterer (the CLI default), or contig
+    clustering with cluster_contigs=True.  All thresholds are PERCENTAGES."""
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    check(lib().galah_b200_cluster_files_skani(_paths_array(genomes), len(genomes), ctypes.c_float(precluster_ani),
+                                               ctypes.c_float(ani), ctypes.c_float(min_aligned_fraction),
+                                               int(bool(small_genomes)), int(bool(cluster_contigs)), threads,
+                                               ctypes.byref(res), ctypes.byref(stats)))
+    clusters, info = _take_clusters(res)
+    info.update(n_precluster_hits=int(stats.n_precluster_hits))
+    return clusters, info
+
+
 GENOME_STATS_DTYPE = np.dtype([("num_contigs", "<u8"), ("num_ambiguous_bases", "<u8"), ("n50", "<u8")])
 
 

@@ -135,9 +135,14 @@ struct IngestSinks {
     int k = 21; uint32_t s = 1000; uint64_t seed = 0;
     uint64_t *hashes = nullptr; uint32_t *counts = nullptr;  // host rows, stride s
     AniIndex *ani = nullptr;
+    // FracMinHash marker sketches (k = 21, density 1/c_marker): one ascending hash list per unit
+    std::vector<std::vector<uint64_t>> *markers = nullptr;
+    uint32_t c_marker = 1000;
+    bool per_record = false;  // contig mode: every FASTA record is its own unit
+    size_t n_units = 0;       // out: genomes (or records) ingested
 };
 
-static int ingest_files(const char *const *paths, size_t n, int host_threads, const IngestSinks &sinks) {
+static int ingest_files(const char *const *paths, size_t n, int host_threads, IngestSinks &sinks) {
     if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     const size_t kMaxBatchGenomes = 512;
     const uint64_t kMaxBatchBases = 2ull << 30;
@@ -146,6 +151,7 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, co
     while (done < n) {
         const size_t want = std::min(kMaxBatchGenomes, n - done);
         std::vector<PackedGenome> batch(want);
+        std::vector<std::vector<PackedGenome>> per_file(sinks.per_record ? want : 0);
         std::vector<std::string> errs(want);
         std::vector<int> rcs(want, 0);
         std::atomic<size_t> next{0};
@@ -153,7 +159,8 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, co
             for (;;) {
                 size_t x = next.fetch_add(1);
                 if (x >= want) break;
-                rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
+                if (sinks.per_record) rcs[x] = pack_fasta_file_per_record(paths[done + x], per_file[x], false, errs[x]);
+                else rcs[x] = pack_fasta_file(paths[done + x], batch[x], false, errs[x]);
             }
         };
         std::vector<std::thread> th;
@@ -163,10 +170,17 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, co
         for (auto &t : th) t.join();
         for (size_t x = 0; x < want; x++)
             if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
+        if (sinks.per_record) {  // flatten: one unit per record, file order then record order
+            batch.clear();
+            for (auto &f : per_file) for (auto &g : f) batch.push_back(std::move(g));
+        }
+        const size_t n_batch = batch.size();
+        const size_t unit0 = sinks.n_units;
+        sinks.n_units += n_batch;
         size_t b0 = 0;
-        while (b0 < want) {  // split further if the batch is too large for one upload
+        while (b0 < n_batch) {  // split further if the batch is too large for one upload
             size_t b1 = b0; uint64_t bases = 0;
-            while (b1 < want && (b1 == b0 || bases + batch[b1].padded_bases() <= kMaxBatchBases)) {
+            while (b1 < n_batch && (b1 == b0 || (bases + batch[b1].padded_bases() <= kMaxBatchBases && b1 - b0 < 65536))) {
                 bases += batch[b1].padded_bases(); b1++;
             }
             const size_t nb = b1 - b0;
@@ -201,10 +215,34 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, co
                 int rc = sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, nb, sinks.k, sinks.s, sinks.seed,
                                         d_hashes.p, d_counts.p, sinks.s, st);
                 if (rc) return rc;
-                GB_CUDA(cudaMemcpyAsync(sinks.hashes + (done + b0) * (size_t)sinks.s, d_hashes.p,
+                GB_CUDA(cudaMemcpyAsync(sinks.hashes + (unit0 + b0) * (size_t)sinks.s, d_hashes.p,
                                         nb * (size_t)sinks.s * 8, cudaMemcpyDeviceToHost, st));
-                GB_CUDA(cudaMemcpyAsync(sinks.counts + done + b0, d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
+                GB_CUDA(cudaMemcpyAsync(sinks.counts + unit0 + b0, d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
                 GB_CUDA(cudaStreamSynchronize(st));
+            }
+            if (sinks.markers) {
+                uint64_t longest = 0;
+                for (size_t x = 0; x < nb; x++) longest = std::max<uint64_t>(longest, batch[b0 + x].n_bases);
+                uint32_t cap = 256;
+                while (cap < 16384 && cap < 1.5 * (double)longest / sinks.c_marker + 256.0) cap <<= 1;
+                DevBuf<uint64_t> d_rows;
+                DevBuf<uint32_t> d_counts;
+                if (d_rows.alloc(nb * (size_t)cap) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
+                int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, nb, 21, sinks.c_marker, cap,
+                                               d_rows.p, d_counts.p, st);
+                if (rc) return rc;
+                std::vector<uint64_t> rows(nb * (size_t)cap);
+                std::vector<uint32_t> cnt(nb);
+                GB_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * 8, cudaMemcpyDeviceToHost, st));
+                GB_CUDA(cudaMemcpyAsync(cnt.data(), d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
+                GB_CUDA(cudaStreamSynchronize(st));
+                for (size_t x = 0; x < nb; x++) {
+                    if (cnt[x] == 0xFFFFFFFFu) {
+                        set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
+                        return GALAH_B200_ERR_UNSUPPORTED;
+                    }
+                    sinks.markers->emplace_back(rows.begin() + x * (size_t)cap, rows.begin() + x * (size_t)cap + cnt[x]);
+                }
             }
             if (sinks.ani) {
                 int rc = sinks.ani->add_packed_device(d_seq2.p, d_valid.p, d_off.p, nb, base_off, contig_off, cs, cl, st);
@@ -215,6 +253,83 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, co
         }
         done += want;
     }
+    return 0;
+}
+
+// Rust's `{}` for an f32 that holds a short decimal (thresholds typed on a command line).
+static std::string display_f32(float v) {
+    char buf[64];
+    for (int prec = 1; prec <= 9; prec++) {
+        snprintf(buf, sizeof(buf), "%.*g", prec, (double)v);
+        if (strtof(buf, nullptr) == v) break;
+    }
+    return buf;
+}
+
+// SkaniPreclusterer::distances / distances_contigs (src/skani.rs:21-56, 109-225, 379-498): marker
+// screen (K1 machinery + K2 join with the containment rule) -> K3 ANI on the survivors -> keep
+// ANI >= threshold.  Index handle stays with the caller (needed for nothing else; freed by it).
+static int skani_distances_impl(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
+                                bool small_genomes, bool per_record, int host_threads,
+                                std::vector<galah_b200_pair_t> &out, size_t &n_units, uint64_t &n_screened) {
+    if (threshold_pct < 85.0f) {
+        set_error("Error: skani produces inaccurate results with ANI less than 85%. Provided: " + display_f32(threshold_pct));
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    AniIndex index(small_genomes ? 30u : 125u);
+    std::vector<std::vector<uint64_t>> markers;
+    IngestSinks sinks;
+    sinks.ani = &index; sinks.markers = &markers; sinks.c_marker = small_genomes ? 200u : 1000u;
+    sinks.per_record = per_record;
+    if (int rc = ingest_files(paths, n, host_threads, sinks)) return rc;
+    n_units = sinks.n_units;
+    out.clear(); n_screened = 0;
+    if (n_units < 2) return 0;
+    // marker table with a common even stride
+    size_t stride = 2;
+    for (auto &m : markers) stride = std::max(stride, m.size() + (m.size() & 1));
+    std::vector<uint64_t> table(n_units * stride, kPad);
+    std::vector<uint32_t> counts(n_units);
+    for (size_t g = 0; g < n_units; g++) {
+        std::copy(markers[g].begin(), markers[g].end(), table.begin() + g * stride);
+        counts[g] = (uint32_t)markers[g].size();
+    }
+    markers.clear(); markers.shrink_to_fit();
+    if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, table.size()) || ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, n_units))
+        return GALAH_B200_ERR_CUDA;
+    cudaStream_t st = g_ctx.stream;
+    GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, table.data(), table.size() * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(g_ctx.d_counts, counts.data(), n_units * 4, cudaMemcpyHostToDevice, st));
+    if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
+    const double frac = pow(0.80, 21.0);  // marker containment of a pair at ~80 % identity
+    size_t cap = std::max<size_t>(1 << 16, 64 * n_units);
+    std::vector<uint4> cand;
+    for (;;) {
+        if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
+        int rc = prefilter_enqueue(g_ctx.pws, g_ctx.d_table, g_ctx.d_counts, n_units, stride, 21, 0.f, 0, 1,
+                                   join_supported(stride) ? 0 : 1, st, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand,
+                                   kRuleContainment, frac);
+        if (rc) return rc;
+        unsigned long long got = 0;
+        GB_CUDA(cudaMemcpyAsync(&got, g_ctx.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, st));
+        GB_CUDA(cudaStreamSynchronize(st));
+        if (got > g_ctx.cap_cand) { cap = (size_t)got; continue; }
+        cand.resize((size_t)got);
+        if (got) {
+            GB_CUDA(cudaMemcpyAsync(cand.data(), g_ctx.d_cand, (size_t)got * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+        }
+        break;
+    }
+    std::sort(cand.begin(), cand.end(), [](const uint4 &a, const uint4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    n_screened = cand.size();
+    std::vector<uint32_t> pairs(2 * cand.size());
+    for (size_t x = 0; x < cand.size(); x++) { pairs[2 * x] = cand[x].x; pairs[2 * x + 1] = cand[x].y; }
+    std::vector<AniPairResult> res(cand.size());
+    if (int rc = index.pairs(pairs.data(), cand.size(), min_af_pct, res.data(), st)) return rc;
+    for (size_t x = 0; x < cand.size(); x++)
+        if (res[x].ani >= threshold_pct)  // `if ani >= threshold` in f32, src/skani.rs:205
+            out.push_back(galah_b200_pair_t{cand[x].x, cand[x].y, cand[x].z, cand[x].w, res[x].ani});
     return 0;
 }
 
@@ -609,6 +724,45 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
         galah_b200_ani_last_timing(idx, &b, &c);
         stats->ani_chain_ms = c;
     }
+    return rc;
+}
+
+int galah_b200_skani_distances(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
+                               int small_genomes, int per_record, int host_threads, galah_b200_pair_t **out,
+                               size_t *n_out, size_t *n_units) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    *out = nullptr; *n_out = 0;
+    std::vector<galah_b200_pair_t> hits;
+    size_t units = 0; uint64_t screened = 0;
+    if (int rc = skani_distances_impl(paths, n, threshold_pct, min_af_pct, small_genomes != 0, per_record != 0,
+                                      host_threads, hits, units, screened))
+        return rc;
+    if (n_units) *n_units = units;
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(hits.size(), 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!hits.empty()) memcpy(res, hits.data(), hits.size() * sizeof(galah_b200_pair_t));
+    *out = res; *n_out = hits.size();
+    return 0;
+}
+
+int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct, float ani_threshold_pct,
+                                   float min_af_pct, int small_genomes, int cluster_contigs, int host_threads,
+                                   galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (!out) { set_error("cluster_files_skani: out is NULL"); return GALAH_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!(ani_threshold_pct > 1.0f)) { set_error("assertion failed: self.threshold > 1.0"); return GALAH_B200_ERR_UNSUPPORTED; }
+    galah_b200_pair_t *hits = nullptr;
+    size_t n_hits = 0, n_units = 0;
+    if (int rc = galah_b200_skani_distances(paths, n, precluster_ani_pct, min_af_pct, small_genomes, cluster_contigs,
+                                            host_threads, &hits, &n_hits, &n_units))
+        return rc;
+    struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
+    // preclusterer and clusterer are both "skani" (or contigs are clustered): skip_clusterer, the
+    // precluster ANIs are re-used against the final threshold (src/clusterer.rs:32-44)
+    int rc = galah_b200_cluster_from_distances(n_units, hits, n_hits, 1, ani_threshold_pct, nullptr, nullptr, out);
+    if (stats) { stats->n_precluster_hits = n_hits; stats->n_ani_pairs = n_hits; }
     return rc;
 }
 

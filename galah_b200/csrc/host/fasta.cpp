@@ -159,6 +159,34 @@ int pack_fasta_file(const std::string &path, PackedGenome &out, bool keep_names,
     return rc;
 }
 
+int pack_fasta_file_per_record(const std::string &path, std::vector<PackedGenome> &out, bool keep_names,
+                               std::string &err) {
+    PackedGenome whole;
+    int rc = pack_fasta_file(path, whole, keep_names, err);
+    if (rc) return rc;
+    for (size_t r = 0; r < whole.rec_start.size(); r++) {
+        out.emplace_back();
+        PackedGenome &g = out.back();
+        const uint64_t b0 = whole.rec_start[r], len = whole.rec_end[r] - b0;
+        g.seq2.assign(len / 16 + 64, 0u);
+        g.valid.assign(len / 32 + 64, 0u);
+        for (uint64_t x = 0; x < len; x++) {  // bit copy at an arbitrary offset
+            const uint64_t s = b0 + x;
+            const uint32_t code = (whole.seq2[s >> 4] >> (2 * (s & 15))) & 3u;
+            const uint32_t ok = (whole.valid[s >> 5] >> (s & 31)) & 1u;
+            g.seq2[x >> 4] |= (ok ? code : 0u) << (2 * (x & 15));
+            g.valid[x >> 5] |= ok << (x & 31);
+        }
+        g.n_bases = len;
+        g.rec_start.push_back(0); g.rec_end.push_back(len);
+        if (keep_names && r < whole.rec_name.size()) g.rec_name.push_back(whole.rec_name[r]);
+        const uint64_t padded = g.padded_bases();
+        g.seq2.resize(padded / 16 + 4, 0u);
+        g.valid.resize(padded / 32 + 4, 0u);
+    }
+    return 0;
+}
+
 void pack_records(const std::vector<std::string> &records, PackedGenome &out) {
     out.clear();
     size_t total = 0;

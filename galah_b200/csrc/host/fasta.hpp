@@ -33,6 +33,10 @@ int read_file_bytes(const std::string &path, std::vector<uint8_t> &out, std::str
 int pack_fasta_bytes(const uint8_t *data, size_t n, PackedGenome &out, bool keep_names,
                      std::string &err);
 int pack_fasta_file(const std::string &path, PackedGenome &out, bool keep_names, std::string &err);
+// Contig mode (`--cluster-contigs`, /root/reference/src/cluster_argument_parsing.rs:573-629): every
+// record of the file becomes its own single-record PackedGenome, appended to `out` in file order.
+int pack_fasta_file_per_record(const std::string &path, std::vector<PackedGenome> &out, bool keep_names,
+                               std::string &err);
 
 // galah::genome_stats::calculate_genome_stats (/root/reference/src/genome_stats.rs:11-51) from the
 // metadata the ingest pass already has: record count, literal N/n count, and the reference's N50

@@ -80,6 +80,17 @@ PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani) {
     return t;
 }
 
+PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac) {
+    PrefilterThresholds t;
+    t.cmin_by_tmin.resize((size_t)s_max + 1);
+    for (uint32_t m = 0; m <= s_max; m++) {
+        const double need = ceil(frac * (double)m);
+        t.cmin_by_tmin[m] = need < 1.0 ? 1u : (uint32_t)need;
+    }
+    t.cmin_by_total.assign(2 * (size_t)s_max + 1, 0u);
+    return t;
+}
+
 int PrefilterWorkspace::record(int which, cudaStream_t stream) {
     if (!ev[which]) GB_CUDA(cudaEventCreate(&ev[which]));
     GB_CUDA(cudaEventRecord(ev[which], stream));
@@ -283,14 +294,17 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
 
 int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                       size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
-                      uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p) {
+                      uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p, int rule,
+                      double rule_param) {
     if (n_shards == 0 || shard >= n_shards) { set_error("prefilter: bad shard"); return 3; }
     if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return 3; }
     if (n >= 0x7FFFFFFFull) { set_error("prefilter: n too large"); return 3; }
     if (stride >= (1ull << 30)) { set_error("prefilter: stride too large"); return 3; }
     GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
-    if (!ws.th_valid || ws.th_s != (uint32_t)stride || ws.th_k != k || ws.th_min_ani != min_ani) {
-        PrefilterThresholds th = make_thresholds((uint32_t)stride, k, min_ani);
+    if (!ws.th_valid || ws.th_s != (uint32_t)stride || ws.th_k != k || ws.th_min_ani != min_ani ||
+        ws.th_rule != rule || ws.th_param != rule_param) {
+        PrefilterThresholds th = rule == kRuleContainment ? make_containment_thresholds((uint32_t)stride, rule_param)
+                                                          : make_thresholds((uint32_t)stride, k, min_ani);
         if (ws_ensure(ws.d_cmin_by_tmin, ws.cap_tmin, th.cmin_by_tmin.size())) return 2;
         if (ws_ensure(ws.d_cmin_by_total, ws.cap_total, th.cmin_by_total.size())) return 2;
         GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_tmin, th.cmin_by_tmin.data(), th.cmin_by_tmin.size() * 4,
@@ -298,6 +312,7 @@ int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
         GB_CUDA(cudaMemcpyAsync(ws.d_cmin_by_total, th.cmin_by_total.data(), th.cmin_by_total.size() * 4,
                                 cudaMemcpyHostToDevice, stream));
         ws.th_s = (uint32_t)stride; ws.th_k = k; ws.th_min_ani = min_ani; ws.th_valid = true;
+        ws.th_rule = rule; ws.th_param = rule_param;
     }
     p = KernelParams{};
     p.hashes = d_hashes; p.counts = d_counts; p.n = (uint32_t)n; p.stride = (uint32_t)stride;
@@ -311,11 +326,11 @@ int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
 int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
                       size_t n, size_t stride, int k, float min_ani, uint32_t shard,
                       uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
-                      size_t cand_cap, unsigned long long *d_n_cand) {
+                      size_t cand_cap, unsigned long long *d_n_cand, int rule, double rule_param) {
     if (mode != 0 && mode != 1) { set_error("prefilter: mode must be 0 or 1"); return 3; }
     KernelParams p;
     if (int rc = prefilter_prepare(ws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards, stream, d_cand,
-                                   cand_cap, d_n_cand, p))
+                                   cand_cap, d_n_cand, p, rule, rule_param))
         return rc;
     if (n < 2) return 0;
     if (mode == 0 && join_supported(stride)) return join_build_and_launch(ws, p, shard, n_shards, stream);

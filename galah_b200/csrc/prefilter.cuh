@@ -20,6 +20,10 @@ struct PrefilterThresholds {
     std::vector<uint32_t> cmin_by_total;  // [2 * s_max + 1]
 };
 PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani);
+// Containment screen (skani-style marker screen): a pair survives iff min(|A|,|B|) > 0 and
+// common >= max(1, ceil(frac * min(|A|,|B|))); `total` is not used.
+PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac);
+enum PrefilterRule { kRuleMashAni = 0, kRuleContainment = 1 };
 
 // Sharding granularity in rows == sketches per block list (== GALAH_B200_ROW_BLOCK).
 constexpr int kShardRows = 64;
@@ -41,6 +45,7 @@ struct PrefilterWorkspace {
     uint32_t *d_cmin_by_total = nullptr;
     size_t cap_tmin = 0, cap_total = 0;
     uint32_t th_s = 0; int th_k = 0; float th_min_ani = -1.f; bool th_valid = false;
+    int th_rule = 0; double th_param = 0.0;
     // work list of the current launch: local row blocks + item prefix + atomic work counter
     uint32_t *d_local_rb = nullptr;
     uint64_t *d_item_prefix = nullptr;
@@ -94,7 +99,8 @@ struct KernelParams {
 int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts,
                       size_t n, size_t stride, int k, float min_ani, uint32_t shard,
                       uint32_t n_shards, int mode, cudaStream_t stream, uint4 *d_cand,
-                      size_t cand_cap, unsigned long long *d_n_cand);
+                      size_t cand_cap, unsigned long long *d_n_cand, int rule = kRuleMashAni,
+                      double rule_param = 0.0);
 
 // prefilter_join.cu
 int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
@@ -110,7 +116,8 @@ int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, c
 // prefilter.cu: fills the thresholds / common fields of p for a launch (shared by both entry paths)
 int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                       size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
-                      uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p);
+                      uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p,
+                      int rule = kRuleMashAni, double rule_param = 0.0);
 // prefilter.cu: work list with one item per (local row block, column block >= it), block = kShardRows
 int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream, KernelParams &p);

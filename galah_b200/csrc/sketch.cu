@@ -140,6 +140,41 @@ __device__ __forceinline__ bool kmer_hash(const uint32_t *__restrict__ seq2,
     return true;
 }
 
+// skani-style marker hash: mm_hash64 (minimap2's invertible mix) of the canonical k-mer taken as an
+// MSB-first 2-bit integer (oracle/skani_oracle.c).  Same window extraction as kmer_hash.
+__device__ __forceinline__ uint64_t mm_hash64_dev(uint64_t key) {
+    key = ~key + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+template <int KT>
+__device__ __forceinline__ bool kmer_mmhash(const uint32_t *__restrict__ seq2, const uint32_t *__restrict__ valid,
+                                            uint64_t pos, int k_rt, uint64_t &h) {
+    const int k = KT ? KT : k_rt;
+    const uint64_t vw = pos >> 5;
+    const uint32_t vsh = (uint32_t)pos & 31u;
+    const uint32_t vm = __funnelshift_r(__ldg(valid + vw), __ldg(valid + vw + 1), vsh);
+    const uint32_t need = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    if ((vm & need) != need) return false;
+    const uint64_t w = pos >> 4;
+    const uint32_t sh = ((uint32_t)pos & 15u) * 2u;
+    const uint32_t a0 = __ldg(seq2 + w), a1 = __ldg(seq2 + w + 1), a2 = __ldg(seq2 + w + 2);
+    const uint32_t v0 = __funnelshift_r(a0, a1, sh), v1 = __funnelshift_r(a1, a2, sh);
+    const uint64_t mask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+    const uint64_t V = ((uint64_t)v0 | ((uint64_t)v1 << 32)) & mask;
+    uint64_t F = __brevll(V);
+    F = ((F >> 1) & 0x5555555555555555ull) | ((F & 0x5555555555555555ull) << 1);
+    F >>= (64 - 2 * k);
+    const uint64_t R = ~V & mask;
+    h = mm_hash64_dev(F < R ? F : R);
+    return true;
+}
+
 constexpr int kSketchThreads = 256;
 
 template <int KT>
@@ -264,6 +299,7 @@ struct ChunkParams {
     uint64_t *hashes;
     uint32_t *counts;
     uint32_t out_stride;
+    uint64_t fixed_thr;      // != 0: FracMinHash mode -- keep every hash <= fixed_thr (no bottom-s cap)
 };
 
 __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) {
@@ -279,6 +315,7 @@ __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) 
         uint64_t T = kPad;
         const double want = 1.3 * (double)p.s + 64.0;
         if ((double)npos > want) T = (uint64_t)(18446744073709551616.0 * (want / (double)npos));
+        if (p.fixed_thr) T = p.fixed_thr;
         p.thr[g] = T;
         p.cand_n[g] = 0;
         p.has_max[g] = 0;
@@ -310,7 +347,7 @@ __global__ void __launch_bounds__(256) sketch_items_kernel(const ChunkParams p) 
     for (uint64_t c = c0 + lane; c < c1; c += 32) p.item_genome[c] = warp;
 }
 
-template <int KT>
+template <int KT, int HK>  // HK: 0 = MurmurHash3 of the ASCII k-mer (finch), 1 = mm_hash64 of the 2-bit k-mer
 __global__ void __launch_bounds__(256) sketch_scan_kernel(const ChunkParams p) {
     const uint64_t item = blockIdx.x;
     if (item >= p.chunk_off[p.n]) return;
@@ -324,7 +361,8 @@ __global__ void __launch_bounds__(256) sketch_scan_kernel(const ChunkParams p) {
     uint64_t *cand = p.cand + (size_t)g * p.cap;
     for (uint64_t q = q0 + threadIdx.x; q < q1; q += 256) {
         uint64_t h;
-        if (!kmer_hash<KT>(p.seq2, p.valid, b0 + q, p.k, p.seed, h)) continue;
+        if (HK == 0) { if (!kmer_hash<KT>(p.seq2, p.valid, b0 + q, p.k, p.seed, h)) continue; }
+        else { if (!kmer_mmhash<KT>(p.seq2, p.valid, b0 + q, p.k, h)) continue; }
         if (h > T) continue;
         if (h == kPad) { p.has_max[g] = 1; continue; }
         const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
@@ -381,9 +419,14 @@ __global__ void __launch_bounds__(256) sketch_select_kernel(const ChunkParams p)
     }
     const bool has_max = p.has_max[g] != 0;
     const uint32_t total = distinct + (has_max ? 1u : 0u);
-    const bool complete = !overflow && (total >= p.s || p.thr[g] == kPad);
+    const bool complete = !overflow && (p.fixed_thr != 0 || total >= p.s || p.thr[g] == kPad);
     if (!complete) {
-        if (tid == 0) p.redo_list[atomicAdd(p.redo_n, 1u)] = g;
+        // adaptive mode: the exact kernel re-does the genome; FracMinHash mode: the candidate
+        // buffer was too small -- flagged with an impossible count, the host reports it
+        if (tid == 0) {
+            if (p.fixed_thr) p.counts[g] = 0xFFFFFFFFu;
+            else p.redo_list[atomicAdd(p.redo_n, 1u)] = g;
+        }
         return;
     }
     const uint32_t out_n = min(total, p.s);
@@ -464,14 +507,15 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
     c.has_max = ws.d_has_max; c.item_genome = ws.d_item_genome; c.max_items = max_items;
     c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
     c.hashes = d_hashes; c.counts = d_counts; c.out_stride = (uint32_t)out_stride;
+    c.fixed_thr = 0;
 
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        if (k == 21) sketch_scan_kernel<21><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else sketch_scan_kernel<0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        if (k == 21) sketch_scan_kernel<21, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else sketch_scan_kernel<0, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         GB_LAUNCH_CHECK();
     }
     GB_CUDA(cudaFuncSetAttribute(sketch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -495,6 +539,53 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
                                      (int)smem));
         sketch_kernel<0><<<grid, kSketchThreads, smem, stream>>>(p);
     }
+    GB_LAUNCH_CHECK();
+    return 0;
+}
+
+// FracMinHash marker sketches (skani-style, k = 21): every distinct mm_hash64(canonical k-mer) below
+// (2^64-1)/c, ascending, one row of `cap` uint64 per genome (cap a power of two, <= 16384 so that the
+// per-genome sort fits shared memory).  counts[g] == 0xFFFFFFFF flags a genome with more than cap
+// markers.  Shares the plan / items / scan / select pipeline of K1.
+int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
+                          const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
+                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream) {
+    if (k < 1 || k > 32) { set_error("marker sketch: k must be in 1..32"); return 3; }
+    if (cap < 256 || (cap & (cap - 1)) || cap > 16384) { set_error("marker sketch: bad capacity"); return 3; }
+    if (n >= 0x7FFFFFFFull) { set_error("marker sketch: too many genomes in one batch"); return 3; }
+    if (n == 0) return 0;
+    uint64_t total_bases = 0, first_base = 0;
+    GB_CUDA(cudaMemcpyAsync(&total_bases, d_base_off + n, 8, cudaMemcpyDeviceToHost, stream));
+    GB_CUDA(cudaMemcpyAsync(&first_base, d_base_off, 8, cudaMemcpyDeviceToHost, stream));
+    GB_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t max_items = (total_bases - first_base) / kChunk + n;
+    if (max_items > 0x7FFFFFFFull) { set_error("marker sketch: batch too long for one launch"); return 3; }
+    if (!ws.d_redo_n) GB_CUDA(cudaMalloc(&ws.d_redo_n, sizeof(uint32_t)));
+    if (sk_ensure(ws.d_chunk_off, ws.cap_chunk_off, n + 1) || sk_ensure(ws.d_thr, ws.cap_thr, n) ||
+        sk_ensure(ws.d_cand_n, ws.cap_cand_n, n) || sk_ensure(ws.d_has_max, ws.cap_has_max, n) ||
+        sk_ensure(ws.d_redo_list, ws.cap_redo, n) ||
+        sk_ensure(ws.d_item_genome, ws.cap_items, (size_t)max_items + 1) ||
+        sk_ensure(ws.d_cand, ws.cap_cand, n * (size_t)cap))
+        return 2;
+    ChunkParams c;
+    c.seq2 = d_seq2; c.valid = d_valid; c.base_off = d_base_off; c.n = (uint32_t)n; c.k = k; c.s = cap;
+    c.seed = 0; c.cap = cap; c.chunk_off = ws.d_chunk_off; c.thr = ws.d_thr; c.cand_n = ws.d_cand_n;
+    c.has_max = ws.d_has_max; c.item_genome = ws.d_item_genome; c.max_items = max_items;
+    c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
+    c.hashes = d_rows; c.counts = d_counts; c.out_stride = cap;
+    c.fixed_thr = ~0ull / c_marker - 1;  // keep h < (2^64-1)/c  <=>  h <= that - 1
+    sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
+    GB_LAUNCH_CHECK();
+    sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
+    GB_LAUNCH_CHECK();
+    if (max_items > 0) {
+        if (k == 21) sketch_scan_kernel<21, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else sketch_scan_kernel<0, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        GB_LAUNCH_CHECK();
+    }
+    const size_t smem = (size_t)cap * 8;
+    GB_CUDA(cudaFuncSetAttribute(sketch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sketch_select_kernel<<<(uint32_t)n, 256, smem, stream>>>(c);
     GB_LAUNCH_CHECK();
     return 0;
 }

@@ -26,6 +26,11 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
                    uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream);
 
+// FracMinHash marker sketches for the skani-style screen (see sketch.cu).
+int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
+                          const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
+                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream);
+
 // Synthetic genomes, generated directly in packed form on the device.
 int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length, uint32_t *d_seq2,
                   uint32_t *d_valid, uint64_t *d_base_off, cudaStream_t stream);

@@ -245,6 +245,28 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
                              int host_threads, galah_b200_clusters_t *out,
                              galah_b200_cluster_stats_t *stats);
 
+/* ---- skani preclusterer / contig clustering ------------------------------------------------
+ * Replaces SkaniPreclusterer::distances and ::distances_contigs (src/skani.rs:21-56; the
+ * `skani triangle --sparse [-i]` subprocess of :109-225 and :379-498): FracMinHash marker sketches
+ * (k = 21, 1/1000, or 1/200 with small_genomes) of every unit, an all-pairs marker-containment
+ * screen on the GPU (the K2 join with the rule common >= max(1, ceil(0.8^21 * min(|A|,|B|)))), the
+ * stage-2 ANI kernel on the survivors, keep ANI >= threshold_pct (f32, src/skani.rs:205).
+ * per_record != 0 is contig mode: every FASTA record of every file is its own unit, numbered in
+ * file order then record order (the order of `contig_names`, src/cluster_argument_parsing.rs:
+ * 596-629).  *n_units receives the number of units.  threshold_pct < 85 fails with the reference's
+ * panic text (src/skani.rs:116-121).  Result: (i, j, ani in PERCENT), sorted by (i, j);
+ * common/total are the marker intersection integers. */
+int galah_b200_skani_distances(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
+                               int small_genomes, int per_record, int host_threads,
+                               galah_b200_pair_t **out, size_t *n_out, size_t *n_units);
+/* cluster() with SkaniPreclusterer + SkaniClusterer -- galah's CLI default
+ * (--precluster-method skani --cluster-method skani) -- or, with cluster_contigs != 0,
+ * `--cluster-contigs`: both run with skip_clusterer (src/clusterer.rs:32-44). */
+int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct,
+                                   float ani_threshold_pct, float min_af_pct, int small_genomes,
+                                   int cluster_contigs, int host_threads, galah_b200_clusters_t *out,
+                                   galah_b200_cluster_stats_t *stats);
+
 /* ---- quality-ordering inputs (host logic) ---------------------------------------------------
  * Replaces galah::genome_stats::calculate_genome_stats (src/genome_stats.rs:11-51), the per-genome
  * inputs of the Parks2020 / dRep quality formulas: a by-product of the same ingest pass that packs

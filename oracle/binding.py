@@ -288,3 +288,47 @@ def ani_finish(sumM, sumN, covq, covr, len_q, len_r, min_af_pct):
 def ani_pair(a, b, min_af_pct=15.0):
     ints = ani_pair_integers(a, b)
     return ani_finish(*ints[:6], min_af_pct)
+
+
+def markers(codes, rec_start, rec_end, c_marker=1000):
+    """Ascending distinct marker hashes of one unit (skani_oracle.c)."""
+    L = _skani_sigs()
+    L.skani_oracle_markers.restype = ctypes.c_uint64
+    L.skani_oracle_markers.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_uint64),
+                                       ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint32, ctypes.c_uint32,
+                                       ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64]
+    codes = np.ascontiguousarray(codes, np.uint8)
+    rs = np.ascontiguousarray(rec_start, np.uint64); re_ = np.ascontiguousarray(rec_end, np.uint64)
+    cap = max(1024, len(codes) // c_marker * 3 + 1024)
+    while True:
+        out = np.zeros(cap, np.uint64)
+        n = L.skani_oracle_markers(_p(codes, ctypes.c_uint8), _p(rs, ctypes.c_uint64), _p(re_, ctypes.c_uint64),
+                                   len(rs), c_marker, _p(out, ctypes.c_uint64), cap)
+        if n <= cap:
+            return out[:n].copy()
+        cap = int(n)
+
+
+def skani_distances(units, threshold, min_af_pct, small_genomes=False):
+    """Oracle of SkaniPreclusterer::distances on `units` = list of (codes, rec_start, rec_end):
+    marker screen -> ANI -> keep ani >= threshold.  Returns [(i, j, common, total, ani f32)]."""
+    import math
+    L = _skani_sigs()
+    L.skani_oracle_screen_fraction.restype = ctypes.c_double
+    frac = L.skani_oracle_screen_fraction()
+    c, cm = (30, 200) if small_genomes else (125, 1000)
+    gen = [AniGenome(*u, c=c) for u in units]
+    mk = [markers(*u, c_marker=cm) for u in units]
+    out = []
+    for i in range(len(units)):
+        for j in range(i + 1, len(units)):
+            m = min(len(mk[i]), len(mk[j]))
+            if m == 0:
+                continue
+            common, total = raw_distance(mk[i], mk[j])
+            if common < max(1, math.ceil(frac * m)):
+                continue
+            ani = ani_pair(gen[i], gen[j], min_af_pct)[0]
+            if np.float32(ani) >= np.float32(threshold):
+                out.append((i, j, common, total, np.float32(ani)))
+    return out

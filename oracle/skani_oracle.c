@@ -205,3 +205,42 @@ float skani_oracle_finish(uint64_t sumM, uint64_t sumN, uint64_t covq, uint64_t 
     snprintf(buf, sizeof(buf), "%.2f", ani);
     return strtof(buf, NULL);
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Marker sketches and the screen used in place of `skani triangle`'s own (src/skani.rs:109-225) */
+/*   markers  every window of 21 valid bases: canon = min(fwd, revcomp) as MSB-first 2-bit        */
+/*            integers; kept iff mm_hash64(canon) < (2^64-1)/c_marker (c_marker = 1000, or 200   */
+/*            with --small-genomes); the sketch is the ascending list of DISTINCT hashes.        */
+/*   screen   a pair is compared iff min(|A|,|B|) > 0 and                                        */
+/*            |A n B| >= max(1, ceil(0.8^21 * min(|A|,|B|)))  (marker containment ~ 80 % ANI).   */
+/* PARITY UNPINNED like the rest of this file: skani's own screen is not reproduced bit for bit. */
+/* ------------------------------------------------------------------------------------------ */
+static int cmp_u64_sk(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : (x > y);
+}
+uint64_t skani_oracle_markers(const uint8_t *codes, const uint64_t *rec_start, const uint64_t *rec_end,
+                              uint32_t nrec, uint32_t c_marker, uint64_t *out, uint64_t cap) {
+    const int K = 21;
+    const uint64_t thr = UINT64_MAX / c_marker;
+    const uint64_t mask = (1ULL << (2 * K)) - 1;
+    uint64_t n = 0;
+    for (uint32_t r = 0; r < nrec; r++) {
+        uint64_t fwd = 0, rev = 0; uint32_t run = 0;
+        for (uint64_t p = rec_start[r]; p < rec_end[r]; p++) {
+            const uint8_t cd = codes[p];
+            if (cd > 3) { run = 0; fwd = rev = 0; continue; }
+            fwd = ((fwd << 2) | cd) & mask;
+            rev = (rev >> 2) | ((uint64_t)(3 - cd) << (2 * (K - 1)));
+            if (++run < (uint32_t)K) continue;
+            const uint64_t h = mm_hash64(fwd < rev ? fwd : rev);
+            if (h < thr) { if (n < cap) out[n] = h; n++; }
+        }
+    }
+    if (n > cap) return n;
+    qsort(out, n, sizeof(uint64_t), cmp_u64_sk);
+    uint64_t m = 0;
+    for (uint64_t i = 0; i < n; i++) if (m == 0 || out[m - 1] != out[i]) out[m++] = out[i];
+    return m;
+}
+double skani_oracle_screen_fraction(void) { return pow(0.80, 21.0); }
