@@ -259,8 +259,8 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
 // Rust's `{}` for an f32 that holds a short decimal (thresholds typed on a command line).
 static std::string display_f32(float v) {
     char buf[64];
-    for (int prec = 1; prec <= 9; prec++) {
-        snprintf(buf, sizeof(buf), "%.*g", prec, (double)v);
+    for (int prec = 0; prec <= 12; prec++) {  // shortest fixed-point text that round-trips, no exponent
+        snprintf(buf, sizeof(buf), "%.*f", prec, (double)v);
         if (strtof(buf, nullptr) == v) break;
     }
     return buf;
