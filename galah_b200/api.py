@@ -332,6 +332,30 @@ def cluster_skani(genomes, precluster_ani=90.0, ani=95.0, min_aligned_fraction=1
     return clusters, info
 
 
+def pack_fasta_file(path):
+    """Host ingest of one file -> (codes uint8 per base: 0..3 = ACGT, 4 = invalid, rec_start, rec_end) in
+    packed coordinates (unpacked here for comparison with the oracle's load_codes)."""
+    seq2, valid = _native.u32p(), _native.u32p()
+    rs, re_ = _native.u64p(), _native.u64p()
+    nb, nr = ctypes.c_uint64(0), ctypes.c_size_t(0)
+    check(lib().galah_b200_pack_fasta_file(os.fsencode(path), ctypes.byref(seq2), ctypes.byref(valid), ctypes.byref(nb),
+                                           ctypes.byref(rs), ctypes.byref(re_), ctypes.byref(nr)))
+    try:
+        n = nb.value
+        w2 = np.ctypeslib.as_array(seq2, shape=((n + 15) // 16 + 1,)).astype(np.uint32)
+        wv = np.ctypeslib.as_array(valid, shape=((n + 31) // 32 + 1,)).astype(np.uint32)
+        idx = np.arange(n, dtype=np.uint64)
+        codes = ((w2[idx >> np.uint64(4)] >> (np.uint32(2) * (idx & np.uint64(15)).astype(np.uint32))) & np.uint32(3)).astype(np.uint8)
+        ok = ((wv[idx >> np.uint64(5)] >> (idx & np.uint64(31)).astype(np.uint32)) & np.uint32(1)).astype(bool)
+        codes[~ok] = 4
+        starts = np.ctypeslib.as_array(rs, shape=(max(nr.value, 1),))[: nr.value].copy()
+        ends = np.ctypeslib.as_array(re_, shape=(max(nr.value, 1),))[: nr.value].copy()
+    finally:
+        for ptr in (seq2, valid, rs, re_):
+            lib().galah_b200_free(ptr)
+    return codes, starts, ends
+
+
 GENOME_STATS_DTYPE = np.dtype([("num_contigs", "<u8"), ("num_ambiguous_bases", "<u8"), ("n50", "<u8")])
 
 

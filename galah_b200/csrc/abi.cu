@@ -772,6 +772,20 @@ void galah_b200_clusters_free(galah_b200_clusters_t *c) {
     memset(c, 0, sizeof(*c));
 }
 
+int galah_b200_pack_fasta_file(const char *path, uint32_t **seq2, uint32_t **valid, uint64_t *n_bases,
+                               uint64_t **rec_start, uint64_t **rec_end, size_t *n_records) {
+    PackedGenome pg;
+    std::string err;
+    if (pack_fasta_file(path, pg, false, err)) { set_error(err); return GALAH_B200_ERR_IO; }
+    auto dup = [](const void *src, size_t bytes) { void *p = malloc(std::max<size_t>(bytes, 8)); if (p && bytes) memcpy(p, src, bytes); return p; };
+    *seq2 = (uint32_t *)dup(pg.seq2.data(), pg.seq2.size() * 4);
+    *valid = (uint32_t *)dup(pg.valid.data(), pg.valid.size() * 4);
+    *rec_start = (uint64_t *)dup(pg.rec_start.data(), pg.rec_start.size() * 8);
+    *rec_end = (uint64_t *)dup(pg.rec_end.data(), pg.rec_end.size() * 8);
+    *n_bases = pg.n_bases; *n_records = pg.rec_start.size();
+    return 0;
+}
+
 int galah_b200_genome_stats(const char *const *paths, size_t n, int host_threads, galah_b200_genome_stats_t *out) {
     if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::vector<std::string> errs(n);

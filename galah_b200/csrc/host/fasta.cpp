@@ -1,5 +1,6 @@
 #include "fasta.hpp"
 
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -30,30 +31,60 @@ struct NormTable {
 };
 const NormTable kNorm;
 
+// Streams bases into the packed arrays.  The arrays are pre-sized from the input length (every
+// base costs at least one input byte, plus one separator per record), so the hot loop carries
+// no bounds checks: it accumulates 32 bases in registers and stores two sequence words and one
+// validity word at a time.
 struct Packer {
     PackedGenome &g;
-    uint64_t n = 0;
+    uint64_t n = 0;       // bases pushed so far
+    uint64_t acc2 = 0;    // 2-bit codes of the current group of 32 bases
+    uint32_t accv = 0;    // validity bits of the current group
     explicit Packer(PackedGenome &g_) : g(g_) {}
+    inline void flush_group() {  // n is a multiple of 32 here
+        const uint64_t grp = (n >> 5) - 1;
+        g.seq2[2 * grp] = (uint32_t)acc2;
+        g.seq2[2 * grp + 1] = (uint32_t)(acc2 >> 32);
+        g.valid[grp] = accv;
+        acc2 = 0; accv = 0;
+    }
     inline void push(uint32_t code, bool ok) {
-        const uint64_t w2 = n >> 4, wv = n >> 5;
-        if (w2 >= g.seq2.size()) g.seq2.resize(g.seq2.size() * 2 + 64, 0u);
-        if (wv >= g.valid.size()) g.valid.resize(g.valid.size() * 2 + 64, 0u);
-        if (ok) {
-            g.seq2[w2] |= code << (2 * (n & 15));
-            g.valid[wv] |= 1u << (n & 31);
-        }
+        const uint32_t sh = (uint32_t)n & 31u;
+        if (ok) { acc2 |= (uint64_t)code << (2 * sh); accv |= 1u << sh; }
         n++;
+        if ((n & 31u) == 0) flush_group();
     }
     void feed(const uint8_t *p, size_t len) {
+        uint64_t nn = n, a2 = acc2;
+        uint32_t av = accv;
+        uint64_t amb = 0, nN = 0;
         for (size_t i = 0; i < len; i++) {
-            const uint8_t c = kNorm.t[p[i]];
+            const uint8_t ch = p[i];
+            const uint8_t c = kNorm.t[ch];
             if (c == 5) continue;
-            if (c == 4) { g.n_ambiguous++; g.n_N += (p[i] == 'N' || p[i] == 'n'); push(0, false); }
-            else push(c, true);
+            const uint32_t sh = (uint32_t)nn & 31u;
+            if (c < 4) { a2 |= (uint64_t)c << (2 * sh); av |= 1u << sh; }
+            else { amb++; nN += (ch == 'N' || ch == 'n'); }
+            nn++;
+            if ((nn & 31u) == 0) {
+                const uint64_t grp = (nn >> 5) - 1;
+                g.seq2[2 * grp] = (uint32_t)a2;
+                g.seq2[2 * grp + 1] = (uint32_t)(a2 >> 32);
+                g.valid[grp] = av;
+                a2 = 0; av = 0;
+            }
         }
+        n = nn; acc2 = a2; accv = av;
+        g.n_ambiguous += amb; g.n_N += nN;
     }
     void finish() {
         g.n_bases = n;
+        if (n & 31u) {  // partial last group
+            const uint64_t grp = n >> 5;
+            g.seq2[2 * grp] = (uint32_t)acc2;
+            g.seq2[2 * grp + 1] = (uint32_t)(acc2 >> 32);
+            g.valid[grp] = accv;
+        }
         const uint64_t padded = g.padded_bases();
         // + 16 bytes of padding words so kernels may read slightly past the end
         g.seq2.resize(padded / 16 + 4, 0u);
@@ -83,9 +114,29 @@ GenomeAssemblyStats genome_stats(const PackedGenome &g) {
 }
 
 int read_file_bytes(const std::string &path, std::vector<uint8_t> &out, std::string &err) {
+    out.clear();
+    // plain files: one fread of the whole file; gzip (magic 1f 8b, as needletail sniffs it): zlib
+    FILE *fp = fopen(path.c_str(), "rb");
+    if (!fp) { err = "Failed to open fasta file " + path; return 4; }
+    unsigned char magic[2] = {0, 0};
+    const size_t got_magic = fread(magic, 1, 2, fp);
+    if (!(got_magic == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {
+        if (fseek(fp, 0, SEEK_END) == 0) {
+            const long sz = ftell(fp);
+            if (sz >= 0 && fseek(fp, 0, SEEK_SET) == 0) {
+                out.resize((size_t)sz);
+                const size_t rd = sz ? fread(out.data(), 1, (size_t)sz, fp) : 0;
+                fclose(fp);
+                if (rd != (size_t)sz) { err = "Failed to read " + path; return 4; }
+                return 0;
+            }
+        }
+        fclose(fp);  // not seekable: fall through to the streaming reader
+    } else {
+        fclose(fp);
+    }
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) { err = "Failed to open fasta file " + path; return 4; }
-    out.clear();
     const unsigned CH = 4u << 20;
     size_t n = 0;
     for (;;) {

@@ -278,6 +278,14 @@ typedef struct galah_b200_genome_stats {
 int galah_b200_genome_stats(const char *const *paths, size_t n, int host_threads,
                             galah_b200_genome_stats_t *out);
 
+/* Host ingest of one FASTA/FASTQ file (plain or gzip) into the packed layout (what the reference
+ * gets from needletail `parse_fastx_file` + normalize(false), used via finch::sketch_files at
+ * src/finch.rs:69): 2 bits/base + validity bitmap, records separated by one invalid base,
+ * rec_start/rec_end in packed coordinates.  All outputs are malloc'd: release each with
+ * galah_b200_free().  Pure host code (parity hook for the ingest stage). */
+int galah_b200_pack_fasta_file(const char *path, uint32_t **seq2, uint32_t **valid, uint64_t *n_bases,
+                               uint64_t **rec_start, uint64_t **rec_end, size_t *n_records);
+
 /* ---- synthetic genomes (bench / tests) ------------------------------------- */
 /* Generates genomes [index_begin, index_begin+n) of `length` bases each directly in packed
  * form on the device.  d_seq2 needs n * words_per_genome uint32 with
