@@ -14,7 +14,7 @@ from ._native import GalahB200Error, Pair, check, lib
 PAIR_DTYPE = np.dtype(
     [("i", "<u4"), ("j", "<u4"), ("common", "<u4"), ("total", "<u4"), ("ani", "<f4")]
 )
-ROW_BLOCK = 64
+ROW_BLOCK = 128
 PAD = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 _bound_device = None

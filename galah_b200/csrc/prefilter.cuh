@@ -26,7 +26,7 @@ PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac);
 enum PrefilterRule { kRuleMashAni = 0, kRuleContainment = 1 };
 
 // Sharding granularity in rows == sketches per block list (== GALAH_B200_ROW_BLOCK).
-constexpr int kShardRows = 64;
+constexpr int kShardRows = 128;
 // Owner of row group `group` (kShardRows rows) among n_shards: boustrophedon order
 // 0,1,..,G-1,G-1,..,1,0,0,1,.. so that the triangular pair area (row i has n-1-i pairs) is
 // balanced to within one group per two rounds.

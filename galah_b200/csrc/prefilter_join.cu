@@ -47,7 +47,7 @@
 namespace gb200 {
 
 constexpr int kJR = kShardRows;            // sketches per block list
-constexpr int kJLevels = 6;                // log2(kJR)
+constexpr int kJLevels = 7;                // log2(kJR)
 static_assert((1 << kJLevels) == kJR, "kShardRows must be a power of two");
 constexpr int kJThreads = 256;
 constexpr int kJE = 18;                    // merge steps per thread per segment (kJE/2 odd: the
@@ -205,7 +205,7 @@ __device__ __forceinline__ uint32_t split_bfirst(PtrT A, uint32_t la, PtrT B, ui
 
 struct JoinSmem {
     uint32_t hi[kJCap];  // off-diagonal: the segment's A and B key slices; diagonal: hi | lo | tags
-    uint32_t cnt[kJR * kJR];
+    uint32_t cnt[kJR * kJR / 2];  // 16-bit counters, two per word (count <= stride < 65536)
     uint64_t bar;
     unsigned long long item;
     uint32_t split[kJThreads + 1];
@@ -224,13 +224,20 @@ struct ListView {
 // Walk A's run of that key (staged keys first, then global memory) and count the entries whose lo
 // word also matches -- (hi, lo) equality is value equality.  lo words and tags are read from
 // global memory (L2): ties are rare unless the two blocks hold related genomes.
+__device__ __forceinline__ void cnt_inc(uint32_t *cnt, uint32_t idx) {
+    atomicAdd(&cnt[idx >> 1], 1u << (16u * (idx & 1u)));
+}
+__device__ __forceinline__ uint32_t cnt_get(const uint32_t *cnt, uint32_t idx) {
+    return (cnt[idx >> 1] >> (16u * (idx & 1u))) & 0xFFFFu;
+}
+
 __device__ __forceinline__ void match_run(uint32_t *cnt, const uint32_t *Ah, uint32_t a_ext, uint32_t i, uint32_t kb,
                                           const ListView &A, uint32_t i0, const ListView &B, uint32_t gj) {
     const uint32_t lob = B.lo[gj], tagb = B.tag[gj];
     for (uint32_t x = i; i0 + x < A.len; x++) {
         const uint32_t key = x < a_ext ? Ah[x] : A.hi[i0 + x];
         if (key != kb) break;
-        if (A.lo[i0 + x] == lob) atomicAdd(&cnt[(uint32_t)A.tag[i0 + x] * kJR + tagb], 1u);
+        if (A.lo[i0 + x] == lob) cnt_inc(cnt, (uint32_t)A.tag[i0 + x] * kJR + tagb);
     }
 }
 
@@ -348,10 +355,10 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         const uint32_t cb = rb + (uint32_t)(item - p.item_prefix[lo]);
         const uint32_t row0 = rb * kJR, col0 = cb * kJR;
 
-        for (uint32_t x = tid; x < kJR * kJR; x += kJThreads) S.cnt[x] = 0;
-        if (tid < kJR) {
-            S.na[tid] = row0 + tid < p.n ? min(p.counts[row0 + tid], p.stride) : 0;
-            S.nb[tid] = col0 + tid < p.n ? min(p.counts[col0 + tid], p.stride) : 0;
+        for (uint32_t x = tid; x < kJR * kJR / 2; x += kJThreads) S.cnt[x] = 0;
+        for (uint32_t x = tid; x < kJR; x += kJThreads) {
+            S.na[x] = row0 + x < p.n ? min(p.counts[row0 + x], p.stride) : 0;
+            S.nb[x] = col0 + x < p.n ? min(p.counts[col0 + x], p.stride) : 0;
         }
         ListView A, B;
         A.hi = p.bl_hi + (uint64_t)rb * p.bl_cap; A.lo = p.bl_lo + (uint64_t)rb * p.bl_cap;
@@ -387,13 +394,13 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     for (; y < ext && Th[y] == h; y++)
                         if (Tl[y] == l) {
                             const uint32_t ty = Tt[y];
-                            atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
+                            cnt_inc(S.cnt, min(tx, ty) * kJR + max(tx, ty));
                         }
                     if (y == ext)
                         for (uint32_t gy = x0 + y; gy < la && A.hi[gy] == h; gy++)
                             if (A.lo[gy] == l) {
                                 const uint32_t ty = A.tag[gy];
-                                atomicAdd(&S.cnt[min(tx, ty) * kJR + max(tx, ty)], 1u);
+                                cnt_inc(S.cnt, min(tx, ty) * kJR + max(tx, ty));
                             }
                 }
                 __syncthreads();
@@ -448,7 +455,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
             const uint32_t gi = row0 + r, gj = col0 + c;
             if (gi >= p.n || gj >= p.n || gj <= gi) continue;
             finish_pair(p, gi, gj, p.hashes + (size_t)gi * p.stride, S.na[r],
-                        p.hashes + (size_t)gj * p.stride, S.nb[c], S.cnt[e]);
+                        p.hashes + (size_t)gj * p.stride, S.nb[c], cnt_get(S.cnt, e));
         }
     }
 }
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
-bool join_supported(size_t stride) { return stride <= (1u << 20); }
+bool join_supported(size_t stride) { return stride < 65536; }  // 16-bit pair counters
 
 void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack) {
     *n_blocks = (n + kJR - 1) / kJR;

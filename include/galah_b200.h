@@ -90,7 +90,7 @@ int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t 
  * shard p = b % n_shards in even rounds (b / n_shards) and n_shards-1-p in odd rounds, which
  * balances the triangular pair area across shards.  _shard takes host pointers, _device device pointers;
  * result pairs always land on the HOST. */
-#define GALAH_B200_ROW_BLOCK 64
+#define GALAH_B200_ROW_BLOCK 128
 int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, size_t n,
                                size_t stride, uint8_t k, float min_ani, uint32_t shard,
                                uint32_t n_shards, galah_b200_pair_t **out, size_t *n_out);
