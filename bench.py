@@ -387,8 +387,8 @@ def main():
         pairs_per_launch = pairs / world
         achieved = BYTES_PER_PAIR * pairs_per_launch / (main_ms * 1e-3) / 1e9
         # bytes the join kernel itself has to read: each (rb, cb) item streams the 32-bit keys of two
-        # block lists of 64*s entries once for 64*64 pairs (lo words / tags only on key ties)
-        own_bytes_per_pair = 2 * S * 4 / 64 if args.mode == 0 else BYTES_PER_PAIR
+        # block lists of R*s entries (R = 128 sketches) once for R*R pairs (lo words / tags only on key ties)
+        own_bytes_per_pair = 2 * S * 4 / gb.ROW_BLOCK if args.mode == 0 else BYTES_PER_PAIR
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             import oracle
@@ -423,7 +423,7 @@ def main():
                                    f"{' scaled by sqrt(G) genomes' if world > 1 else ''})",
                        "pairs_per_step": pairs, "mode": args.mode,
                        "l2": "flushed between timed iterations (256 MiB write)",
-                       "sharding": "boustrophedon row blocks of 64; inside the step: NCCL all-gather of the sketch "
+                       "sharding": "boustrophedon row blocks of 128; inside the step: NCCL all-gather of the sketch "
                                    "table, per-rank build of 1/G of the block lists, NCCL all-gather of the lists"
                                    if world > 1 else "single GPU"},
             "clocks": clocks,
@@ -437,8 +437,8 @@ def main():
                          "kernel_own_bytes_per_pair": own_bytes_per_pair,
                          "kernel_own_gbs": own_bytes_per_pair * pairs_per_launch / (main_ms * 1e-3) / 1e9,
                          "note": "achieved uses the reference algorithm's 2*s*8 B/pair (SURVEY.md 8d). The join "
-                                 "kernel computes every pair's exact intersection from ONE merge of two 64-sketch "
-                                 "block lists per 64x64 pairs, so it reads 2*s*4/64 B/pair (kernel_own_*) and the "
+                                 "kernel computes every pair's exact intersection from ONE merge of two 128-sketch "
+                                 "block lists per 128x128 pairs, so it reads 2*s*4/128 B/pair (kernel_own_*) and the "
                                  "fraction of the 16 kB/pair roofline exceeds 1 by design (DESIGN.md K2)"
                                  if args.mode == 0 else
                                  "pairwise kernel re-uses staged sketches from shared memory (16 kB/pair is read "

@@ -111,7 +111,7 @@ int PrefilterWorkspace::release() {
     for (int x = 0; x < 3; x++) if (ev[x]) cudaEventDestroy(ev[x]);
     cudaFree(d_cmin_by_tmin); cudaFree(d_cmin_by_total); cudaFree(d_item_prefix);
     cudaFree(d_local_rb); cudaFree(d_work_counter); cudaFree(d_bl_len); cudaFree(d_gmax);
-    cudaFree(d_fin_hi); cudaFree(d_fin_lo); cudaFree(d_fin_tags);
+    cudaFree(d_fin_hi); cudaFree(d_fin_lo); cudaFree(d_fin_tags); cudaFree(d_splits);
     for (int x = 0; x < 2; x++) { cudaFree(d_bl_vals[x]); cudaFree(d_bl_tags[x]); }
     *this = PrefilterWorkspace();
     return 0;

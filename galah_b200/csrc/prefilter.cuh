@@ -56,6 +56,8 @@ struct PrefilterWorkspace {
     uint8_t *d_bl_tags[2] = {nullptr, nullptr};
     uint32_t *d_bl_len = nullptr;
     unsigned long long *d_gmax = nullptr;  // largest valid hash of the table (device scalar)
+    uint32_t *d_splits = nullptr;          // merge-path splits of the tile boundaries of one level
+    size_t cap_splits = 0;
     size_t cap_bl = 0, cap_bl_len = 0;
     // finished lists of the single-device path (structure of arrays)
     uint32_t *d_fin_hi = nullptr, *d_fin_lo = nullptr;

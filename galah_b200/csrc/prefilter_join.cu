@@ -119,18 +119,41 @@ __device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8
 
 // One level of the merge tree: for every output run o, dst[o*2m .. o*2m+2m) = merge of
 // src[o*2m .. +m) and src[o*2m+m .. +2m) under the (value, tag) order, first run first on ties.
+// Merge-path splits of every tile boundary of one merge level, one thread per boundary (so the
+// ~16 dependent L2 probes of a split overlap across thousands of threads instead of serialising
+// at the head of every merge CTA).  splits[o * (chunks + 1) + c] = A-side split of diagonal c*kMTile.
+__global__ void __launch_bounds__(256) bl_partition_kernel(const uint64_t *__restrict__ sv,
+                                                           const uint8_t *__restrict__ st, uint32_t m,
+                                                           uint32_t chunks_per_run, uint64_t n_bounds,
+                                                           uint32_t *__restrict__ splits) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_bounds) return;
+    const uint64_t o = b / (chunks_per_run + 1);
+    const uint32_t c = (uint32_t)(b % (chunks_per_run + 1));
+    const uint64_t base = o * 2 * m;
+    const uint64_t *A = sv + base, *B = sv + base + m;
+    const uint8_t *tA = st + base, *tB = st + base + m;
+    const uint32_t d = min(c * (uint32_t)kMTile, 2 * m);
+    uint32_t lo = d > m ? d - m : 0, hi = min(d, m);
+    while (lo < hi) {  // smallest i with !(A[i] <= B[d-1-i])
+        const uint32_t mid = (lo + hi) >> 1;
+        if (key_le(A[mid], tA[mid], B[d - 1 - mid], tB[d - 1 - mid])) lo = mid + 1; else hi = mid;
+    }
+    splits[b] = lo;
+}
+
 template <bool kLast>
 __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__restrict__ sv,
                                                              const uint8_t *__restrict__ st,
                                                              uint64_t *__restrict__ dv,
                                                              uint8_t *__restrict__ dt, uint32_t m,
                                                              uint32_t chunks_per_run,
+                                                             const uint32_t *__restrict__ splits,
                                                              const unsigned long long *__restrict__ gmax,
                                                              uint32_t *__restrict__ dhi,
                                                              uint32_t *__restrict__ dlo) {
     __shared__ uint64_t s_v[kMTile];
     __shared__ uint8_t s_t[kMTile];
-    __shared__ uint32_t s_g[2];
     __shared__ uint32_t s_ts[kMThreads + 1];
     const uint32_t tid = threadIdx.x;
     const uint32_t o = blockIdx.x / chunks_per_run, c = blockIdx.x % chunks_per_run;
@@ -138,17 +161,8 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__r
     const uint64_t *A = sv + base, *B = sv + base + m;
     const uint8_t *tA = st + base, *tB = st + base + m;
     const uint32_t d0 = c * kMTile, d1 = min(d0 + (uint32_t)kMTile, 2 * m);
-    if (tid == 0 || tid == 32) {
-        const uint32_t d = tid == 0 ? d0 : d1;
-        uint32_t lo = d > m ? d - m : 0, hi = min(d, m);
-        while (lo < hi) {  // smallest i with !(A[i] <= B[d-1-i])
-            const uint32_t mid = (lo + hi) >> 1;
-            if (key_le(A[mid], tA[mid], B[d - 1 - mid], tB[d - 1 - mid])) lo = mid + 1; else hi = mid;
-        }
-        s_g[tid >> 5] = lo;
-    }
-    __syncthreads();
-    const uint32_t i0 = s_g[0], i1 = s_g[1], j0 = d0 - i0, j1 = d1 - i1;
+    const uint64_t sb = (uint64_t)o * (chunks_per_run + 1) + c;
+    const uint32_t i0 = splits[sb], i1 = splits[sb + 1], j0 = d0 - i0, j1 = d1 - i1;
     const uint32_t na = i1 - i0, nb = j1 - j0, len = na + nb;
     for (uint32_t x = tid; x < na; x += kMThreads) { s_v[x] = A[i0 + x]; s_t[x] = tA[i0 + x]; }
     for (uint32_t x = tid; x < nb; x += kMThreads) { s_v[na + x] = B[j0 + x]; s_t[na + x] = tB[j0 + x]; }
@@ -511,17 +525,26 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
         GB_LAUNCH_CHECK();
     }
     int src = 0;
+    {   // tile-boundary splits: at most (chunks + 1) per output run, most at the first level
+        const uint64_t need = total / (2 * stride) * ((2 * stride + kMTile - 1) / kMTile + 1) + 16;
+        if (ws_ensure(ws.d_splits, ws.cap_splits, need)) return 2;
+    }
     for (uint64_t m = stride; m < bl_cap; m *= 2) {
         const uint32_t chunks = (uint32_t)((2 * m + kMTile - 1) / kMTile);
         const uint64_t grid = total / (2 * m) * chunks;
         if (grid > 0x7FFFFFFFull) { set_error("prefilter: table too large for the merge grid"); return 3; }
+        const uint64_t n_bounds = total / (2 * m) * (chunks + 1);
+        bl_partition_kernel<<<(uint32_t)((n_bounds + 255) / 256), 256, 0, stream>>>(
+            ws.d_bl_vals[src], ws.d_bl_tags[src], (uint32_t)m, chunks, n_bounds, ws.d_splits);
+        GB_LAUNCH_CHECK();
         if (2 * m >= bl_cap)  // last level: structure-of-arrays output into the caller's buffers
             bl_merge_kernel<true><<<(uint32_t)grid, kMThreads, 0, stream>>>(
-                ws.d_bl_vals[src], ws.d_bl_tags[src], nullptr, d_tags, (uint32_t)m, chunks, ws.d_gmax, d_hi, d_lo);
+                ws.d_bl_vals[src], ws.d_bl_tags[src], nullptr, d_tags, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, d_hi,
+                d_lo);
         else
             bl_merge_kernel<false><<<(uint32_t)grid, kMThreads, 0, stream>>>(
                 ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
-                ws.d_gmax, nullptr, nullptr);
+                ws.d_splits, ws.d_gmax, nullptr, nullptr);
         GB_LAUNCH_CHECK();
         src ^= 1;
     }
