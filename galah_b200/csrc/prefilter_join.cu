@@ -142,6 +142,14 @@ __global__ void __launch_bounds__(256) bl_partition_kernel(const uint64_t *__res
     splits[b] = lo;
 }
 
+struct MergeSmem {
+    uint64_t in_v[kMTile];
+    uint64_t out_v[kMTile];
+    uint8_t in_t[kMTile];
+    uint8_t out_t[kMTile];
+    uint32_t ts[kMThreads + 1];
+};
+
 template <bool kLast>
 __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__restrict__ sv,
                                                              const uint8_t *__restrict__ st,
@@ -152,9 +160,8 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__r
                                                              const unsigned long long *__restrict__ gmax,
                                                              uint32_t *__restrict__ dhi,
                                                              uint32_t *__restrict__ dlo) {
-    __shared__ uint64_t s_v[kMTile];
-    __shared__ uint8_t s_t[kMTile];
-    __shared__ uint32_t s_ts[kMThreads + 1];
+    extern __shared__ __align__(16) uint8_t merge_smem_raw[];
+    MergeSmem &S = *reinterpret_cast<MergeSmem *>(merge_smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t o = blockIdx.x / chunks_per_run, c = blockIdx.x % chunks_per_run;
     const uint64_t base = (uint64_t)o * 2 * m;
@@ -164,34 +171,44 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__r
     const uint64_t sb = (uint64_t)o * (chunks_per_run + 1) + c;
     const uint32_t i0 = splits[sb], i1 = splits[sb + 1], j0 = d0 - i0, j1 = d1 - i1;
     const uint32_t na = i1 - i0, nb = j1 - j0, len = na + nb;
-    for (uint32_t x = tid; x < na; x += kMThreads) { s_v[x] = A[i0 + x]; s_t[x] = tA[i0 + x]; }
-    for (uint32_t x = tid; x < nb; x += kMThreads) { s_v[na + x] = B[j0 + x]; s_t[na + x] = tB[j0 + x]; }
+    for (uint32_t x = tid; x < na; x += kMThreads) { S.in_v[x] = A[i0 + x]; S.in_t[x] = tA[i0 + x]; }
+    for (uint32_t x = tid; x < nb; x += kMThreads) { S.in_v[na + x] = B[j0 + x]; S.in_t[na + x] = tB[j0 + x]; }
     __syncthreads();
-    const uint64_t *As = s_v, *Bs = s_v + na;
-    const uint8_t *At = s_t, *Bt = s_t + na;
+    const uint64_t *As = S.in_v, *Bs = S.in_v + na;
+    const uint8_t *At = S.in_t, *Bt = S.in_t + na;
     const uint32_t dt0 = min(tid * kME, len), dt1 = min(dt0 + (uint32_t)kME, len);
     {
         uint32_t lo = dt0 > nb ? dt0 - nb : 0, hi = min(dt0, na);
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (key_le(As[mid], At[mid], Bs[dt0 - 1 - mid], Bt[dt0 - 1 - mid])) lo = mid + 1; else hi = mid;
+            const uint64_t a = As[mid], b = Bs[dt0 - 1 - mid];
+            const bool le = a < b || (a == b && At[mid] <= Bt[dt0 - 1 - mid]);  // tags only matter on a tie
+            if (le) lo = mid + 1; else hi = mid;
         }
-        s_ts[tid] = lo;
-        if (tid == 0) s_ts[kMThreads] = na;
+        S.ts[tid] = lo;
+        if (tid == 0) S.ts[kMThreads] = na;
     }
     __syncthreads();
-    uint32_t i = s_ts[tid], j = dt0 - i;
-    const uint32_t ie = s_ts[tid + 1], je = dt1 - ie;
-    uint8_t *ot = dt + base + d0;
+    uint32_t i = S.ts[tid], j = dt0 - i;
+    const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
+    // the values under the two cursors live in registers: one shared-memory load per step
+    uint64_t a = As[min(i, kMTile - 1u)], b = Bs[min(j, kMTile - 1u - na)];
+    for (uint32_t x = dt0; x < dt1; x++) {
+        bool take_a;
+        if (j >= je) take_a = true;
+        else if (i >= ie) take_a = false;
+        else take_a = a < b || (a == b && At[i] <= Bt[j]);
+        if (take_a) { S.out_v[x] = a; S.out_t[x] = At[i]; i++; a = As[min(i, kMTile - 1u)]; }
+        else { S.out_v[x] = b; S.out_t[x] = Bt[j]; j++; b = Bs[min(j, kMTile - 1u - na)]; }
+    }
+    __syncthreads();
+    // coalesced write-out of the merged tile
     int sh = 0;
     if (kLast) { const unsigned long long g = *gmax; sh = g ? __clzll((long long)g) : 0; }
-    for (uint32_t x = dt0; x < dt1; x++) {
-        bool take_a = j >= je;
-        if (!take_a && i < ie) take_a = key_le(As[i], At[i], Bs[j], Bt[j]);
-        uint64_t v; uint8_t tg;
-        if (take_a) { v = As[i]; tg = At[i]; i++; }
-        else { v = Bs[j]; tg = Bt[j]; j++; }
-        ot[x] = tg;
+    for (uint32_t x = tid; x < len; x += kMThreads) {
+        const uint64_t v = S.out_v[x];
+        const uint8_t tg = S.out_t[x];
+        dt[base + d0 + x] = tg;
         if (kLast) {
             const uint64_t w = v << sh;
             dhi[base + d0 + x] = tg == kPadTag ? 0xFFFFFFFFu : (uint32_t)(w >> 32);
@@ -524,6 +541,8 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
                                                  (uint64_t)b0 * kJR, total, ws.d_bl_vals[0], ws.d_bl_tags[0]);
         GB_LAUNCH_CHECK();
     }
+    GB_CUDA(cudaFuncSetAttribute(bl_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    GB_CUDA(cudaFuncSetAttribute(bl_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
     int src = 0;
     {   // tile-boundary splits: at most (chunks + 1) per output run, most at the first level
         const uint64_t need = total / (2 * stride) * ((2 * stride + kMTile - 1) / kMTile + 1) + 16;
@@ -538,11 +557,11 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
             ws.d_bl_vals[src], ws.d_bl_tags[src], (uint32_t)m, chunks, n_bounds, ws.d_splits);
         GB_LAUNCH_CHECK();
         if (2 * m >= bl_cap)  // last level: structure-of-arrays output into the caller's buffers
-            bl_merge_kernel<true><<<(uint32_t)grid, kMThreads, 0, stream>>>(
+            bl_merge_kernel<true><<<(uint32_t)grid, kMThreads, sizeof(MergeSmem), stream>>>(
                 ws.d_bl_vals[src], ws.d_bl_tags[src], nullptr, d_tags, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, d_hi,
                 d_lo);
         else
-            bl_merge_kernel<false><<<(uint32_t)grid, kMThreads, 0, stream>>>(
+            bl_merge_kernel<false><<<(uint32_t)grid, kMThreads, sizeof(MergeSmem), stream>>>(
                 ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
                 ws.d_splits, ws.d_gmax, nullptr, nullptr);
         GB_LAUNCH_CHECK();
