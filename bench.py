@@ -328,6 +328,23 @@ def main():
         n_pass = len(res)
         if it >= 2:
             e2e_times.append(dt)
+    e2e_host = gb.prefilter_last_host_timing() if world == 1 else None
+    e2e_single_upload = None
+    if world == 1:
+        # the same call with the upload pipeline off (one 80 MB copy, then the kernels)
+        prev_chunks = gb.prefilter_stream_chunks(1)
+        ts = []
+        for it in range(4):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res1 = gb.prefilter(np_table, np_counts, K, MIN_ANI)
+            if it >= 1:
+                ts.append(time.perf_counter() - t0)
+        gb.prefilter_stream_chunks(prev_chunks)
+        assert len(res1) == len(res) and np.array_equal(res1["j"], res["j"]) and np.array_equal(
+            res1["ani"].view(np.uint32), res["ani"].view(np.uint32))
+        e2e_single_upload = {"value": n * (n - 1) // 2 / (sum(ts) / len(ts)), "ms": 1e3 * sum(ts) / len(ts),
+                             "host_ms": gb.prefilter_last_host_timing()}
     e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
     n_pass_t = torch.tensor([n_pass], dtype=torch.int64, device=dev)
     if world > 1:
@@ -428,7 +445,10 @@ def main():
                                    if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "passing_pairs": int(n_pass_t.item())},
+                    "passing_pairs": int(n_pass_t.item()), "ms": 1e3 * float(e2e_t.item()),
+                    "pipeline": f"upload in {gb.prefilter_stream_chunks()} slices on a copy stream, build + join wave "
+                                "per slice" if world == 1 else "per-rank slice upload, NVLink all-gathers",
+                    "host_ms": e2e_host, "single_upload": e2e_single_upload},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "kernel": kernel_names[args.mode],

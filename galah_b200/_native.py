@@ -62,6 +62,8 @@ _SIGNATURES = {
     "galah_b200_launch_count": (ctypes.c_uint64, []),
     "galah_b200_prefilter_mode": (ctypes.c_int, [ctypes.c_int]),
     "galah_b200_prefilter_last_timing": (ctypes.c_int, [f32p, f32p]),
+    "galah_b200_prefilter_stream_chunks": (ctypes.c_int, [ctypes.c_int]),
+    "galah_b200_prefilter_last_host_timing": (ctypes.c_int, [f32p]),
     "galah_b200_sketch_files": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_uint8, ctypes.c_uint32,
                                                ctypes.c_uint64, ctypes.c_int, u64p, u32p]),
     "galah_b200_sketch_packed": (ctypes.c_int, [u32p, u32p, u64p, ctypes.c_size_t, ctypes.c_uint8,

@@ -49,6 +49,20 @@ def prefilter_last_timing():
     return float(b.value), float(m.value)
 
 
+def prefilter_stream_chunks(chunks=-1):
+    """Slices of the pipelined upload of host-buffer prefilter calls (<= 1 disables the pipeline;
+    < 0 only queries).  Returns the previous setting."""
+    return int(lib().galah_b200_prefilter_stream_chunks(int(chunks)))
+
+
+def prefilter_last_host_timing():
+    """Host wall-clock breakdown (ms) of the last host-buffer prefilter call:
+    dict(enqueue, wait, d2h_extra, finish)."""
+    ms = (ctypes.c_float * 4)()
+    check(lib().galah_b200_prefilter_last_host_timing(ms))
+    return dict(zip(("enqueue", "wait", "d2h_extra", "finish"), (float(x) for x in ms)))
+
+
 def version():
     return lib().galah_b200_version().decode()
 

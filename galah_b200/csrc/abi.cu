@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <mutex>
 #include <string>
@@ -40,10 +41,17 @@ struct Context {
     uint32_t *d_counts = nullptr; size_t cap_counts = 0;
     uint4 *d_cand = nullptr; size_t cap_cand = 0;
     unsigned long long *d_n_cand = nullptr;
+    cudaStream_t copy_stream = nullptr;  // PCIe uploads of the streamed host-buffer prefilter
+    int stream_chunks = 1;               // slices of that upload (<= 1 disables the pipeline)
+    uint4 *h_stage = nullptr;            // pinned landing zone: candidate count + first kStageCand candidates
+    float host_ms[4] = {0, 0, 0, 0};     // last host-buffer prefilter: enqueue, wait, d2h, finish
     int release() {
         pws.release(); sws.release();
         cudaFree(d_table); cudaFree(d_counts); cudaFree(d_cand); cudaFree(d_n_cand);
+        if (h_stage) cudaFreeHost(h_stage);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         d_table = nullptr; d_counts = nullptr; d_cand = nullptr; d_n_cand = nullptr;
+        h_stage = nullptr; copy_stream = nullptr;
         cap_table = cap_counts = cap_cand = 0;
         return 0;
     }
@@ -73,58 +81,112 @@ struct DevBuf {
 };
 
 // Integer candidates {i, j, common, total} -> the reference's f64 formula, threshold and f32 store
-// (src/finch.rs:78-93), sorted by (i, j).  Host only.
+// (src/finch.rs:78-93), sorted by (i, j) -- the iteration order of the reference's BTreeMap.  Host
+// only.  The order comes from a counting sort on i (candidates are sparse: a few per row) and a
+// small sort by j inside each row, O(candidates + rows) instead of a comparison sort of all.
 static int finish_candidates(const uint4 *cand, size_t n_cand, int k, float min_ani, galah_b200_pair_t **out,
                              size_t *n_out) {
-    std::vector<galah_b200_pair_t> pass;
-    pass.reserve(n_cand);
     const double thr = (double)min_ani;
+    uint32_t max_i = 0;
+    for (size_t x = 0; x < n_cand; x++) max_i = std::max(max_i, cand[x].x);
+    std::vector<uint32_t> row_start((size_t)max_i + 2, 0);
+    std::vector<float> ani(n_cand);
+    std::vector<uint8_t> keep(n_cand);
     for (size_t x = 0; x < n_cand; x++) {
-        const uint4 &c = cand[x];
-        const double ani = mash_ani_f64(c.z, c.w, k);
-        if (ani >= thr) pass.push_back(galah_b200_pair_t{c.x, c.y, c.z, c.w, (float)ani});
+        const double a = mash_ani_f64(cand[x].z, cand[x].w, k);
+        keep[x] = a >= thr;
+        ani[x] = (float)a;
+        if (keep[x]) row_start[cand[x].x + 1]++;
     }
-    std::sort(pass.begin(), pass.end(), [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) {
-        return a.i != b.i ? a.i < b.i : a.j < b.j;
-    });
-    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(pass.size(), 1) * sizeof(galah_b200_pair_t));
+    for (size_t r = 0; r + 1 < row_start.size(); r++) row_start[r + 1] += row_start[r];
+    const size_t n_pass = n_cand ? row_start.back() : 0;
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(n_pass, 1) * sizeof(galah_b200_pair_t));
     if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
-    if (!pass.empty()) memcpy(res, pass.data(), pass.size() * sizeof(galah_b200_pair_t));
-    *out = res; *n_out = pass.size();
+    std::vector<uint32_t> fill(row_start.begin(), row_start.end());
+    for (size_t x = 0; x < n_cand; x++)
+        if (keep[x]) res[fill[cand[x].x]++] = galah_b200_pair_t{cand[x].x, cand[x].y, cand[x].z, cand[x].w, ani[x]};
+    for (size_t r = 0; r + 1 < row_start.size(); r++) {
+        galah_b200_pair_t *b = res + row_start[r], *e = res + row_start[r + 1];
+        if (e - b > 1 && !std::is_sorted(b, e, [](const galah_b200_pair_t &a, const galah_b200_pair_t &c) { return a.j < c.j; }))
+            std::sort(b, e, [](const galah_b200_pair_t &a, const galah_b200_pair_t &c) { return a.j < c.j; });
+    }
+    *out = res; *n_out = n_pass;
+    return 0;
+}
+
+constexpr size_t kStageCand = 1 << 16;  // candidates fetched together with their count (1 MiB, pinned)
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Candidate count + candidates -> host, one synchronisation in the common case: the count and
+// the first kStageCand candidates land in pinned memory together; a longer list is fetched in a
+// second copy.  Returns got > cap (overflow: the caller re-runs with a larger buffer) via *overflow.
+static int fetch_candidates(cudaStream_t stream, std::vector<uint4> &cand, unsigned long long *got_out) {
+    if (!g_ctx.h_stage) GB_CUDA(cudaMallocHost(&g_ctx.h_stage, (kStageCand + 1) * sizeof(uint4)));
+    const size_t first = std::min(kStageCand, g_ctx.cap_cand);
+    GB_CUDA(cudaMemcpyAsync(g_ctx.h_stage, g_ctx.d_n_cand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    GB_CUDA(cudaMemcpyAsync(g_ctx.h_stage + 1, g_ctx.d_cand, first * sizeof(uint4), cudaMemcpyDeviceToHost, stream));
+    const double t0 = now_ms();
+    GB_CUDA(cudaStreamSynchronize(stream));
+    g_ctx.host_ms[1] = (float)(now_ms() - t0);
+    const unsigned long long got = *reinterpret_cast<unsigned long long *>(g_ctx.h_stage);
+    *got_out = got;
+    if (got > g_ctx.cap_cand) return 0;
+    cand.resize((size_t)got);
+    memcpy(cand.data(), g_ctx.h_stage + 1, std::min<size_t>(got, first) * sizeof(uint4));
+    if (got > first) {
+        GB_CUDA(cudaMemcpyAsync(cand.data() + first, g_ctx.d_cand + first, ((size_t)got - first) * sizeof(uint4),
+                                cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaStreamSynchronize(stream));
+    }
+    g_ctx.host_ms[2] = (float)(now_ms() - t0) - g_ctx.host_ms[1];
     return 0;
 }
 
 // Run the prefilter kernels for one shard and finish the survivors on the host in f64
-// (reference: src/finch.rs:78-93).
+// (reference: src/finch.rs:78-93).  h_hashes != nullptr: the table is still on the host and
+// d_hashes is its (not yet filled) device copy -- the first attempt streams it (upload pipelined
+// against build + join, join_streamed_from_host); a retry after candidate overflow finds it resident.
 static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
                          int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
-                         galah_b200_pair_t **out, size_t *n_out) {
+                         galah_b200_pair_t **out, size_t *n_out, const uint64_t *h_hashes = nullptr,
+                         const uint32_t *h_counts = nullptr) {
     *out = nullptr; *n_out = 0;
     if ((reinterpret_cast<uintptr_t>(d_hashes) & 15) != 0) {
         set_error("prefilter: sketch table must be 16-byte aligned");
         return GALAH_B200_ERR_ARG;
     }
+    const double t_begin = now_ms();
     if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
     size_t cap = std::max<size_t>(1 << 16, 32 * n);
     std::vector<uint4> cand;
     for (;;) {
         if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
-        int rc = prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards,
-                                   g_ctx.prefilter_mode, stream, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand);
-        if (rc) return rc;
-        unsigned long long got = 0;
-        GB_CUDA(cudaMemcpyAsync(&got, g_ctx.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, stream));
-        GB_CUDA(cudaStreamSynchronize(stream));
-        if (got > g_ctx.cap_cand) { cap = (size_t)got; continue; }
-        cand.resize((size_t)got);
-        if (got) {
-            GB_CUDA(cudaMemcpyAsync(cand.data(), g_ctx.d_cand, (size_t)got * sizeof(uint4),
-                                    cudaMemcpyDeviceToHost, stream));
-            GB_CUDA(cudaStreamSynchronize(stream));
+        if (h_hashes) {
+            KernelParams p;
+            if (int rc = prefilter_prepare(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, 0, 1, stream, g_ctx.d_cand,
+                                           g_ctx.cap_cand, g_ctx.d_n_cand, p))
+                return rc;
+            if (int rc = join_streamed_from_host(g_ctx.pws, p, h_hashes, h_counts, const_cast<uint64_t *>(d_hashes),
+                                                 stream, g_ctx.copy_stream, g_ctx.stream_chunks))
+                return rc;
+            h_hashes = nullptr;
+        } else {
+            int rc = prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards,
+                                       g_ctx.prefilter_mode, stream, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand);
+            if (rc) return rc;
         }
+        g_ctx.host_ms[0] = (float)(now_ms() - t_begin);
+        unsigned long long got = 0;
+        if (int rc = fetch_candidates(stream, cand, &got)) return rc;
+        if (got > g_ctx.cap_cand) { cap = (size_t)got; continue; }
         break;
     }
-    return finish_candidates(cand.data(), cand.size(), k, min_ani, out, n_out);
+    const double t0 = now_ms();
+    int rc = finish_candidates(cand.data(), cand.size(), k, min_ani, out, n_out);
+    g_ctx.host_ms[3] = (float)(now_ms() - t0);
+    return rc;
 }
 
 // One pass over FASTA files feeding K1 (sketches) and/or the K3 index from the SAME upload:
@@ -510,16 +572,35 @@ int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, s
         ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
         return GALAH_B200_ERR_CUDA;
     cudaStream_t st = g_ctx.stream;
+    // whole-table single-shard join: pipeline the upload against the kernels (slices of whole blocks)
+    const bool streamed = g_ctx.prefilter_mode == 0 && n_shards == 1 && (g_ctx.stream_chunks > 1 || getenv("GALAH_B200_STREAM_FORCE")) &&
+                          join_supported(stride) && n >= 4 * (size_t)kShardRows;
     if (n) {
-        GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, hashes, n * stride * 8, cudaMemcpyHostToDevice, st));
         GB_CUDA(cudaMemcpyAsync(g_ctx.d_counts, counts, n * 4, cudaMemcpyHostToDevice, st));
+        if (!streamed) GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, hashes, n * stride * 8, cudaMemcpyHostToDevice, st));
     }
-    return run_prefilter(g_ctx.d_table, g_ctx.d_counts, n, stride, k, min_ani, shard, n_shards, st, out, n_out);
+    if (streamed && !g_ctx.copy_stream) GB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+    return run_prefilter(g_ctx.d_table, g_ctx.d_counts, n, stride, k, min_ani, shard, n_shards, st, out, n_out,
+                         streamed ? hashes : nullptr, streamed ? counts : nullptr);
 }
 
 int galah_b200_prefilter(const uint64_t *hashes, const uint32_t *counts, size_t n, size_t stride,
                          uint8_t k, float min_ani, galah_b200_pair_t **out, size_t *n_out) {
     return galah_b200_prefilter_shard(hashes, counts, n, stride, k, min_ani, 0, 1, out, n_out);
+}
+
+int galah_b200_prefilter_stream_chunks(int chunks) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    const int prev = g_ctx.stream_chunks;
+    if (chunks >= 0) g_ctx.stream_chunks = std::min(chunks, 64);
+    return prev;
+}
+
+int galah_b200_prefilter_last_host_timing(float *ms4) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!ms4) { set_error("prefilter_last_host_timing: ms4 is NULL"); return GALAH_B200_ERR_ARG; }
+    for (int x = 0; x < 4; x++) ms4[x] = g_ctx.host_ms[x];
+    return 0;
 }
 
 int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani, uint32_t num_kmers,

@@ -113,6 +113,8 @@ int PrefilterWorkspace::release() {
     cudaFree(d_local_rb); cudaFree(d_work_counter); cudaFree(d_bl_len); cudaFree(d_gmax);
     cudaFree(d_fin_hi); cudaFree(d_fin_lo); cudaFree(d_fin_tags); cudaFree(d_splits);
     for (int x = 0; x < 2; x++) { cudaFree(d_bl_vals[x]); cudaFree(d_bl_tags[x]); }
+    cudaFree(d_wave_counters);
+    for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
     *this = PrefilterWorkspace();
     return 0;
 }
@@ -258,6 +260,7 @@ template int ws_ensure<uint32_t>(uint32_t *&, size_t &, size_t);
 template int ws_ensure<uint64_t>(uint64_t *&, size_t &, size_t);
 template int ws_ensure<uint8_t>(uint8_t *&, size_t &, size_t);
 template int ws_ensure<uint4>(uint4 *&, size_t &, size_t);
+template int ws_ensure<unsigned long long>(unsigned long long *&, size_t &, size_t);
 
 static size_t tiled_smem_bytes(size_t stride) {
     return (size_t)(kRowBlock + 2 * kColBlock) * stride * 8 + 3 * 8;

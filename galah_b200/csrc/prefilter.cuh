@@ -51,6 +51,10 @@ struct PrefilterWorkspace {
     uint64_t *d_item_prefix = nullptr;
     size_t cap_local_rb = 0, cap_prefix = 0;
     unsigned long long *d_work_counter = nullptr;
+    // streamed host-buffer path: one work counter per wave, one "slice resident" event per slice
+    unsigned long long *d_wave_counters = nullptr;
+    size_t cap_wave_counters = 0;
+    std::vector<cudaEvent_t> chunk_ev;
     // block lists (mode 0): two ping-pong buffers of n_blocks * kShardRows * stride entries
     uint64_t *d_bl_vals[2] = {nullptr, nullptr};
     uint8_t *d_bl_tags[2] = {nullptr, nullptr};
@@ -92,6 +96,9 @@ struct KernelParams {
     const uint8_t *bl_tags;
     const uint32_t *bl_len;
     uint64_t bl_cap;  // entries per block list (kShardRows * stride)
+    uint32_t dbg;
+    unsigned long long *dbg_buf;
+    uint32_t cb_lo;   // first column block of the launch's window (0 unless a streamed wave)
 };
 
 // Enqueue the prefilter for one shard.  d_cand: uint4 {i, j, common, total} candidates that
@@ -111,7 +118,10 @@ bool join_supported(size_t stride);
 void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack);
 int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                     size_t stride, uint32_t b0, uint32_t b1, uint32_t *d_hi, uint32_t *d_lo, uint8_t *d_tags,
-                    uint32_t *d_len, cudaStream_t stream);
+                    uint32_t *d_len, cudaStream_t stream, bool gmax_ready = false);
+int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint64_t *h_hashes,
+                            const uint32_t *h_counts, uint64_t *d_table, cudaStream_t compute, cudaStream_t copy,
+                            int chunks);
 int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, const uint32_t *d_lo,
                 const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard, uint32_t n_shards,
                 cudaStream_t stream);

@@ -39,6 +39,9 @@
 //                     After the last segment the CTA scans cnt, applies the conservative
 //                     integer thresholds and appends survivors {i, j, common, total}.
 #include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "prefilter.cuh"
@@ -86,15 +89,16 @@ __global__ void __launch_bounds__(256) bl_init_kernel(const uint64_t *__restrict
     }
 }
 
-// One warp per block of the WHOLE table: largest valid hash -> gmax (every rank needs the same
-// shift), and for the blocks [b0, b1) being built the number of valid entries -> bl_len[b - b0].
+// One warp per block of the range [pb0, pb1) (the WHOLE table unless the caller already knows
+// gmax): largest valid hash -> gmax (every rank needs the same shift), and for the blocks
+// [b0, b1) being built the number of valid entries -> bl_len[b - b0].
 __global__ void __launch_bounds__(256) bl_len_kernel(const uint64_t *__restrict__ hashes,
                                                      const uint32_t *__restrict__ counts, uint32_t n,
-                                                     uint32_t stride, uint32_t n_blocks, uint32_t b0,
+                                                     uint32_t stride, uint32_t pb0, uint32_t pb1, uint32_t b0,
                                                      uint32_t b1, uint32_t *__restrict__ bl_len,
                                                      unsigned long long *__restrict__ gmax) {
-    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (b >= n_blocks) return;
+    const uint32_t b = pb0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (b >= pb1) return;
     uint32_t sum = 0;
     unsigned long long mx = 0;
     for (uint32_t r = b * kJR + lane; r < min(n, (b + 1) * kJR); r += 32) {
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(256) bl_len_kernel(const uint64_t *__restrict_
     }
     if (lane == 0) {
         if (b >= b0 && b < b1) bl_len[b - b0] = sum;
-        if (mx) atomicMax(gmax, mx);
+        if (mx && gmax) atomicMax(gmax, mx);
     }
 }
 
@@ -382,9 +386,17 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
             const uint32_t mid = (lo + hi) >> 1;
             if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
         }
-        const uint32_t rb = p.local_rb[lo];
-        const uint32_t cb = rb + (uint32_t)(item - p.item_prefix[lo]);
+        uint32_t rb = p.local_rb[lo];
+        uint32_t cb = max(rb, p.cb_lo) + (uint32_t)(item - p.item_prefix[lo]);
+        if (p.dbg & 4) {  // column-major order over the full triangle (debug)
+            uint32_t c = (uint32_t)((sqrt(8.0 * (double)item + 1.0) - 1.0) * 0.5);
+            while ((unsigned long long)(c + 1) * (c + 2) / 2 <= item) c++;
+            while ((unsigned long long)c * (c + 1) / 2 > item) c--;
+            cb = c; rb = (uint32_t)(item - (unsigned long long)c * (c + 1) / 2);
+        }
         const uint32_t row0 = rb * kJR, col0 = cb * kJR;
+        unsigned long long t_item0 = 0;
+        if (p.dbg_buf && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_item0));
 
         for (uint32_t x = tid; x < kJR * kJR / 2; x += kJThreads) S.cnt[x] = 0;
         for (uint32_t x = tid; x < kJR; x += kJThreads) {
@@ -399,7 +411,9 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         const uint32_t la = A.len, lb = B.len;
         __syncthreads();
 
-        if (rb == cb) {
+        if (rb == cb && (p.dbg & 1)) {
+        } else if (rb != cb && (p.dbg & 2)) {
+        } else if (rb == cb) {
             // ---- diagonal item: equal values are adjacent in the single list; hi, lo and tags
             // are all staged (ties are the rule here: family members sit in the same block)
             constexpr uint32_t kSlice = kJDiag + kJR + 16;  // staged entries per array
@@ -488,6 +502,14 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
             finish_pair(p, gi, gj, p.hashes + (size_t)gi * p.stride, S.na[r],
                         p.hashes + (size_t)gj * p.stride, S.nb[c], cnt_get(S.cnt, e));
         }
+        if (p.dbg_buf && tid == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.dbg_buf[item * 4 + 0] = t_item0; p.dbg_buf[item * 4 + 1] = t1;
+            p.dbg_buf[item * 4 + 2] = smid; p.dbg_buf[item * 4 + 3] = ((unsigned long long)rb << 32) | cb;
+        }
     }
 }
 
@@ -506,18 +528,24 @@ void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries
 // d_len, which are SLICE-based: block b lands at offset (b - b0) * entries_per_block.
 int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                     size_t stride, uint32_t b0, uint32_t b1, uint32_t *d_hi, uint32_t *d_lo, uint8_t *d_tags,
-                    uint32_t *d_len, cudaStream_t stream) {
+                    uint32_t *d_len, cudaStream_t stream, bool gmax_ready) {
     const uint32_t nb = (uint32_t)((n + kJR - 1) / kJR);
     if (b0 > b1 || b1 > nb + 64) { set_error("blocklist_build: bad block range"); return 3; }
     if (!ws.d_gmax) GB_CUDA(cudaMalloc(&ws.d_gmax, sizeof(unsigned long long)));
-    GB_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(unsigned long long), stream));
+    if (!gmax_ready) GB_CUDA(cudaMemsetAsync(ws.d_gmax, 0, sizeof(unsigned long long), stream));
     if (nb == 0) return 0;
     int dev = 0, sms = kNumSMsFallback;
     GB_CUDA(cudaGetDevice(&dev));
     GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    bl_len_kernel<<<(uint32_t)(((uint64_t)std::max(nb, b1) * 32 + 255) / 256), 256, 0, stream>>>(
-        d_hashes, d_counts, (uint32_t)n, (uint32_t)stride, std::max(nb, b1), b0, b1, d_len, ws.d_gmax);
-    GB_LAUNCH_CHECK();
+    {   // gmax already in *ws.d_gmax (streamed path: the rest of the table may not be resident yet)
+        const uint32_t pb0 = gmax_ready ? b0 : 0, pb1 = gmax_ready ? b1 : std::max(nb, b1);
+        if (pb1 > pb0) {
+            bl_len_kernel<<<(uint32_t)(((uint64_t)(pb1 - pb0) * 32 + 255) / 256), 256, 0, stream>>>(
+                d_hashes, d_counts, (uint32_t)n, (uint32_t)stride, pb0, pb1, b0, b1, d_len,
+                gmax_ready ? nullptr : ws.d_gmax);
+            GB_LAUNCH_CHECK();
+        }
+    }
     if (b1 == b0) return 0;
 
     const uint64_t bl_cap = (uint64_t)kJR * stride;
@@ -594,29 +622,173 @@ int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, c
     return 0;
 }
 
+// Workspace-owned finished lists for `total` entries (+ readable slack behind the last list).
+static int ensure_fin(PrefilterWorkspace &ws, uint64_t total, cudaStream_t stream) {
+    if (ws.cap_fin >= total + kBlSlack) return 0;
+    if (ws.d_fin_hi) GB_CUDA(cudaFree(ws.d_fin_hi));
+    if (ws.d_fin_lo) GB_CUDA(cudaFree(ws.d_fin_lo));
+    if (ws.d_fin_tags) GB_CUDA(cudaFree(ws.d_fin_tags));
+    ws.d_fin_hi = ws.d_fin_lo = nullptr; ws.d_fin_tags = nullptr; ws.cap_fin = 0;
+    GB_CUDA(cudaMalloc(&ws.d_fin_hi, (total + kBlSlack) * 4));
+    GB_CUDA(cudaMalloc(&ws.d_fin_lo, (total + kBlSlack) * 4));
+    GB_CUDA(cudaMalloc(&ws.d_fin_tags, total + kBlSlack));
+    GB_CUDA(cudaMemsetAsync(ws.d_fin_hi + total, 0xFF, kBlSlack * 4, stream));
+    GB_CUDA(cudaMemsetAsync(ws.d_fin_lo + total, 0xFF, kBlSlack * 4, stream));
+    GB_CUDA(cudaMemsetAsync(ws.d_fin_tags + total, 0xFF, kBlSlack, stream));
+    ws.cap_fin = total + kBlSlack;
+    return 0;
+}
+
 // Single-device path: build every list into workspace-owned arrays, then join.
 int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream) {
     const uint32_t nb = (p.n + kJR - 1) / kJR;
     const uint64_t total = (uint64_t)nb * kJR * p.stride;
-    if (ws.cap_fin < total + kBlSlack) {
-        if (ws.d_fin_hi) GB_CUDA(cudaFree(ws.d_fin_hi));
-        if (ws.d_fin_lo) GB_CUDA(cudaFree(ws.d_fin_lo));
-        if (ws.d_fin_tags) GB_CUDA(cudaFree(ws.d_fin_tags));
-        ws.d_fin_hi = ws.d_fin_lo = nullptr; ws.d_fin_tags = nullptr; ws.cap_fin = 0;
-        GB_CUDA(cudaMalloc(&ws.d_fin_hi, (total + kBlSlack) * 4));
-        GB_CUDA(cudaMalloc(&ws.d_fin_lo, (total + kBlSlack) * 4));
-        GB_CUDA(cudaMalloc(&ws.d_fin_tags, total + kBlSlack));
-        GB_CUDA(cudaMemsetAsync(ws.d_fin_hi + total, 0xFF, kBlSlack * 4, stream));
-        GB_CUDA(cudaMemsetAsync(ws.d_fin_lo + total, 0xFF, kBlSlack * 4, stream));
-        GB_CUDA(cudaMemsetAsync(ws.d_fin_tags + total, 0xFF, kBlSlack, stream));
-        ws.cap_fin = total + kBlSlack;
-    }
+    if (int rc = ensure_fin(ws, total, stream)) return rc;
     if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
     if (int rc = blocklist_build(ws, p.hashes, p.counts, p.n, p.stride, 0, nb, ws.d_fin_hi, ws.d_fin_lo,
                                  ws.d_fin_tags, ws.d_bl_len, stream))
         return rc;
     return join_launch(ws, p, ws.d_fin_hi, ws.d_fin_lo, ws.d_fin_tags, ws.d_bl_len, shard, n_shards, stream);
+}
+
+// Host-buffer path, pipelined against the PCIe upload.  The table goes up in `chunks` slices of
+// whole blocks on `copy`; as soon as slice c is resident, `compute` builds its block lists and
+// joins every item (rb <= cb, cb in slice c) -- all lists such an item needs are finished by
+// then.  Slice boundaries follow nb * sqrt(c / chunks): every wave then holds about the same
+// number of items, the early (large) slices hide under the remaining upload and the last wave --
+// the only kernel time left on the critical path -- is one short round of items.  The shift of
+// the order-preserving keys needs the largest valid hash of the WHOLE table before the first
+// slice is built: the host reads it off the row ends while the first slice is in flight.
+// p must come from prefilter_prepare(.., d_table, d_counts, ..) on `compute`; d_counts resident.
+int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint64_t *h_hashes,
+                            const uint32_t *h_counts, uint64_t *d_table, cudaStream_t compute, cudaStream_t copy,
+                            int chunks) {
+    const uint32_t nb = (p.n + kJR - 1) / kJR;
+    const uint32_t stride = p.stride;
+    const uint64_t bl_cap = (uint64_t)kJR * stride;
+    chunks = std::max(1, std::min<int>(chunks, (int)nb));
+    std::vector<uint32_t> bound(chunks + 1, 0);
+    for (int c = 1; c <= chunks; c++) {
+        uint32_t b = (uint32_t)std::llround((double)nb * std::sqrt((double)c / chunks));
+        bound[c] = std::min(nb, std::max(b, bound[c - 1] + 1));
+    }
+    bound[chunks] = nb;
+    {   // drop empty slices (tables of a few blocks)
+        std::vector<uint32_t> u;
+        for (uint32_t b : bound) if (u.empty() || b > u.back()) u.push_back(b);
+        bound.swap(u);
+        chunks = (int)bound.size() - 1;
+    }
+    const bool debug = getenv("GALAH_B200_STREAM_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> dbg;
+    auto mark = [&](cudaStream_t st) {
+        if (!debug) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); dbg.push_back(e);
+    };
+    if (int rc = ensure_fin(ws, (uint64_t)nb * bl_cap, compute)) return rc;
+    if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
+    while ((int)ws.chunk_ev.size() < chunks) {
+        cudaEvent_t e;
+        GB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ws.chunk_ev.push_back(e);
+    }
+    // work lists of all waves, one upload: wave c = { (rb, cb) : rb < bound[c+1], max(rb, bound[c]) <= cb < bound[c+1] }
+    std::vector<uint32_t> local;
+    std::vector<uint64_t> prefix;
+    std::vector<size_t> off_local(chunks), off_prefix(chunks);
+    for (int c = 0; c < chunks; c++) {
+        off_local[c] = local.size(); off_prefix[c] = prefix.size();
+        prefix.push_back(0);
+        for (uint32_t rb = 0; rb < bound[c + 1]; rb++) {
+            local.push_back(rb);
+            prefix.push_back(prefix.back() + (bound[c + 1] - std::max(rb, bound[c])));
+        }
+    }
+    if (ws_ensure(ws.d_local_rb, ws.cap_local_rb, local.size())) return 2;
+    if (ws_ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;
+    if (ws_ensure(ws.d_wave_counters, ws.cap_wave_counters, (size_t)chunks)) return 2;
+    // the copy stream may not touch d_table before earlier work on `compute` is done with it
+    GB_CUDA(cudaEventRecord(ws.chunk_ev[0], compute));
+    GB_CUDA(cudaStreamWaitEvent(copy, ws.chunk_ev[0], 0));
+    for (int c = 0; c < chunks; c++) {
+        const size_t r0 = (size_t)bound[c] * kJR, r1 = std::min<size_t>((size_t)bound[c + 1] * kJR, p.n);
+        GB_CUDA(cudaMemcpyAsync(d_table + r0 * stride, h_hashes + r0 * stride, (r1 - r0) * stride * 8,
+                                cudaMemcpyHostToDevice, copy));
+        GB_CUDA(cudaEventRecord(ws.chunk_ev[c], copy));
+    }
+    if (getenv("GALAH_B200_STREAM_SERIAL")) cudaStreamSynchronize(copy);
+    unsigned long long gmax = 0;  // overlaps the first slice's DMA
+    for (size_t r = 0; r < p.n; r++) {
+        const uint32_t cnt = std::min(h_counts[r], stride);
+        if (cnt) gmax = std::max<unsigned long long>(gmax, h_hashes[r * stride + cnt - 1]);
+    }
+    if (!ws.d_gmax) GB_CUDA(cudaMalloc(&ws.d_gmax, sizeof(unsigned long long)));
+    GB_CUDA(cudaMemcpyAsync(ws.d_gmax, &gmax, sizeof(gmax), cudaMemcpyHostToDevice, compute));
+    GB_CUDA(cudaMemcpyAsync(ws.d_local_rb, local.data(), local.size() * 4, cudaMemcpyHostToDevice, compute));
+    GB_CUDA(cudaMemcpyAsync(ws.d_item_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, compute));
+    GB_CUDA(cudaMemsetAsync(ws.d_wave_counters, 0, (size_t)chunks * sizeof(unsigned long long), compute));
+    int dev = 0, sms = kNumSMsFallback;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = sizeof(JoinSmem);
+    GB_CUDA(cudaFuncSetAttribute(prefilter_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    p.bl_hi = ws.d_fin_hi; p.bl_lo = ws.d_fin_lo; p.bl_tags = ws.d_fin_tags; p.bl_len = ws.d_bl_len; p.bl_cap = bl_cap;
+    p.n_row_blocks = nb;
+    p.dbg = getenv("GALAH_B200_DBG") ? atoi(getenv("GALAH_B200_DBG")) : 0;
+    unsigned long long *d_dbg = nullptr;
+    const uint64_t dbg_items = (uint64_t)nb * (nb + 1) / 2;
+    if (getenv("GALAH_B200_ITEMLOG")) { cudaMalloc(&d_dbg, dbg_items * 32); cudaMemset(d_dbg, 0, dbg_items * 32); }
+    for (int c = 0; c < chunks; c++) {
+        const uint32_t b0 = bound[c], b1 = bound[c + 1];
+        GB_CUDA(cudaStreamWaitEvent(compute, ws.chunk_ev[c], 0));
+        mark(compute);
+        if (int rc = blocklist_build(ws, p.hashes, p.counts, p.n, stride, b0, b1, ws.d_fin_hi + b0 * bl_cap,
+                                     ws.d_fin_lo + b0 * bl_cap, ws.d_fin_tags + b0 * bl_cap, ws.d_bl_len + b0, compute,
+                                     /*gmax_ready=*/true))
+            return rc;
+        p.cb_lo = b0;
+        p.n_local_rb = b1;
+        p.local_rb = ws.d_local_rb + off_local[c];
+        p.item_prefix = ws.d_item_prefix + off_prefix[c];
+        p.work_counter = ws.d_wave_counters + c;
+        p.dbg_buf = (d_dbg && c == chunks - 1) ? d_dbg : nullptr;
+        const uint64_t n_items = prefix[off_prefix[c] + b1];
+        mark(compute);
+        if (c == chunks - 1 && ws.record(1, compute)) return 2;
+        prefilter_join_kernel<<<(uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm), kJThreads, smem,
+                                compute>>>(p);
+        GB_LAUNCH_CHECK();
+    }
+    if (ws.record(2, compute)) return 2;
+    if (debug) {
+        mark(compute);
+        cudaStreamSynchronize(compute);
+        for (int c = 0; c < chunks; c++) {
+            float b = 0, j = 0, t = 0;
+            cudaEventElapsedTime(&t, dbg[0], dbg[2 * c]);
+            cudaEventElapsedTime(&b, dbg[2 * c], dbg[2 * c + 1]);
+            cudaEventElapsedTime(&j, dbg[2 * c + 1], dbg[2 * c + 2]);
+            fprintf(stderr, "[stream] slice %d blocks [%u,%u) start +%.3f ms build %.3f ms join %.3f ms (%llu items)\n", c,
+                    bound[c], bound[c + 1], t, b, j, (unsigned long long)prefix[off_prefix[c] + bound[c + 1]]);
+        }
+        for (cudaEvent_t e : dbg) cudaEventDestroy(e);
+    }
+    if (d_dbg) {
+        cudaStreamSynchronize(compute);
+        const uint64_t n_items = prefix[off_prefix[chunks - 1] + bound[chunks]];
+        std::vector<unsigned long long> h(n_items * 4);
+        cudaMemcpy(h.data(), d_dbg, n_items * 32, cudaMemcpyDeviceToHost);
+        cudaFree(d_dbg);
+        FILE *f = fopen(getenv("GALAH_B200_ITEMLOG"), "w");
+        unsigned long long t0 = ~0ull;
+        for (uint64_t x = 0; x < n_items; x++) t0 = std::min(t0, h[x * 4]);
+        for (uint64_t x = 0; x < n_items; x++)
+            fprintf(f, "%llu %llu %llu %llu %llu %llu\n", (unsigned long long)x, h[x * 4] - t0, h[x * 4 + 1] - t0, h[x * 4 + 2],
+                    h[x * 4 + 3] >> 32, h[x * 4 + 3] & 0xFFFFFFFFull);
+        fclose(f);
+    }
+    return 0;
 }
 
 }  // namespace gb200

@@ -109,6 +109,18 @@ int galah_b200_prefilter_mode(int mode);
  * pairwise kernel alone.  Blocks until that launch has finished. */
 int galah_b200_prefilter_last_timing(float *build_ms, float *main_ms);
 
+/* Host-buffer calls (galah_b200_prefilter / _shard with n_shards == 1, mode 0) upload the table
+ * in `chunks` slices of whole row blocks on a copy stream and build + join each slice as soon
+ * as it is resident, so only the last wave of kernels is left after the PCIe transfer ends.
+ * chunks <= 1 disables the pipeline (one upload, then the kernels); < 0 only queries.  Returns
+ * the previous setting.  The pair list is identical either way. */
+int galah_b200_prefilter_stream_chunks(int chunks);
+
+/* Host wall-clock breakdown of the most recent host-buffer prefilter call, milliseconds:
+ * ms4[0] = enqueue (uploads + launches issued), [1] = wait for the device, [2] = candidate
+ * read-back beyond the first 65,536, [3] = host finish (f64 formula, threshold, ordering). */
+int galah_b200_prefilter_last_host_timing(float *ms4);
+
 /* Kernel-only timing hook used by bench.py: enqueues the prefilter kernels for one shard on
  * `stream` and leaves the candidate list on the device (d_cand, capacity cand_cap entries of
  * 4 x uint32 {i, j, common, total}; d_n_cand is a device uint64 counter).  No host sync.

@@ -236,3 +236,41 @@ def test_medium_table_sampled_rows(gb):
     # size-independent properties: keys strictly increasing, i < j, common <= total
     key = got["i"].astype(np.int64) * n + got["j"]
     assert np.all(np.diff(key) > 0) and np.all(got["i"] < got["j"]) and np.all(got["common"] <= got["total"])
+
+
+@pytest.mark.parametrize("n,chunks", [(512, 8), (700, 3), (1300, 8), (3000, 16), (2049, 64)])
+def test_streamed_upload_pipeline_matches_single_upload(gb, kernel_mode, n, chunks):
+    """Host-buffer calls upload the table in slices and build + join each slice as it lands
+    (one wave of items per slice).  The pair list must not depend on the slicing."""
+    if kernel_mode != 0:
+        pytest.skip("the upload pipeline belongs to the join path")
+    rng = np.random.default_rng(1000 + n)
+    table, counts = random_family_table(n, 1000, rng, ragged=True)
+    prev = gb.prefilter_stream_chunks(1)
+    try:
+        base = gb.prefilter(table, counts, 21, 0.9)
+        gb.prefilter_stream_chunks(chunks)
+        for _ in range(2):  # second call re-uses the workspace of the first
+            assert_pairs_equal(gb.prefilter(table, counts, 21, 0.9), base)
+        t = gb.prefilter_last_host_timing()
+        assert set(t) == {"enqueue", "wait", "d2h_extra", "finish"}
+    finally:
+        gb.prefilter_stream_chunks(prev)
+    rows = min(n, 40)
+    exp = oracle.prefilter(table, counts, 21, 0.9, row_begin=0, row_end=rows)
+    assert_pairs_equal(base[base["i"] < rows], exp)
+
+
+def test_streamed_upload_candidate_overflow_retries(gb, kernel_mode):
+    """More survivors than the first candidate buffer holds: the retry runs on the resident table."""
+    if kernel_mode != 0:
+        pytest.skip("the upload pipeline belongs to the join path")
+    n, s = 640, 1000
+    row = np.arange(1, s + 1, dtype=np.uint64) * np.uint64(1 << 40)
+    table = np.tile(row, (n, 1))
+    counts = np.full(n, s, np.uint32)
+    got = gb.prefilter(table, counts, 21, 0.9)  # all n(n-1)/2 = 204,480 pairs pass (> 65,536)
+    assert len(got) == n * (n - 1) // 2
+    assert np.all(got["common"] == s) and np.all(got["total"] == s) and np.all(got["ani"] == 1.0)
+    key = got["i"].astype(np.int64) * n + got["j"]
+    assert np.all(np.diff(key) > 0)
