@@ -271,7 +271,8 @@ static size_t tiled_smem_bytes(size_t stride) {
 // (block_rows divides kShardRows) belongs to the group it lies in.  An item is `chunk_blocks`
 // consecutive column blocks starting at the row block's own index.
 static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_rows, uint32_t chunk_blocks,
-                            uint32_t shard, uint32_t n_shards, cudaStream_t stream, KernelParams &p) {
+                            uint32_t shard, uint32_t n_shards, cudaStream_t stream, KernelParams &p,
+                            bool diag_separate = false) {
     const uint32_t nrb = (uint32_t)((n + block_rows - 1) / block_rows);
     const uint32_t per_group = kShardRows / block_rows;
     std::vector<uint32_t> local;
@@ -279,10 +280,12 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
     for (uint32_t rb = 0; rb < nrb; rb++) {
         if (shard_of_group(rb / per_group, n_shards) != shard) continue;
         local.push_back(rb);
-        prefix.push_back(prefix.back() + (nrb - rb + chunk_blocks - 1) / chunk_blocks);
+        // join: the diagonal item of every local row is scheduled ahead of all off-diagonal ones
+        prefix.push_back(prefix.back() + (nrb - rb - (diag_separate ? 1 : 0) + chunk_blocks - 1) / chunk_blocks);
     }
     p.n_row_blocks = nrb;
     p.n_local_rb = (uint32_t)local.size();
+    p.n_diag = diag_separate ? (uint32_t)local.size() : 0;
     if (local.empty()) return 0;
     if (ws_ensure(ws.d_local_rb, ws.cap_local_rb, local.size())) return 2;
     if (ws_ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;
@@ -369,7 +372,7 @@ int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
 
 int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream, KernelParams &p) {
-    return upload_work_list(ws, n, kShardRows, 1, shard, n_shards, stream, p);
+    return upload_work_list(ws, n, kShardRows, 1, shard, n_shards, stream, p, /*diag_separate=*/true);
 }
 
 }  // namespace gb200

@@ -96,8 +96,8 @@ struct KernelParams {
     const uint8_t *bl_tags;
     const uint32_t *bl_len;
     uint64_t bl_cap;  // entries per block list (kShardRows * stride)
-    uint32_t dbg;
-    unsigned long long *dbg_buf;
+    uint32_t n_diag;  // join: diagonal items, taken first; they belong to the LAST n_diag local rows
+    unsigned long long *dbg_buf;  // per-item {start ns, end ns, sm, rb << 32 | cb} log (debug), or null
     uint32_t cb_lo;   // first column block of the launch's window (0 unless a streamed wave)
 };
 
@@ -121,7 +121,7 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
                     uint32_t *d_len, cudaStream_t stream, bool gmax_ready = false);
 int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint64_t *h_hashes,
                             const uint32_t *h_counts, uint64_t *d_table, cudaStream_t compute, cudaStream_t copy,
-                            int chunks);
+                            int chunks, double wave_frac);
 int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, const uint32_t *d_lo,
                 const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard, uint32_t n_shards,
                 cudaStream_t stream);

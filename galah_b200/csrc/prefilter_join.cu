@@ -42,6 +42,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 #include "prefilter.cuh"
@@ -60,9 +61,13 @@ constexpr int kJChains = 2;                // independent merge chains per threa
                                            // is a dependent LDS -> compare -> select -> LDS)
 constexpr int kJD = kJThreads * kJE * kJChains;  // merged entries per segment
 constexpr int kJCap = kJD + 16 + 80;       // staged entries incl. short-run overflow + alignment slack
-constexpr int kJDiag = 3072;               // entries per diagonal-item segment (hi, lo, tags staged)
+constexpr int kJDiag = 3840;               // entries per diagonal-item segment (hi, lo, tags staged)
 static_assert(2 * (kJDiag + kJR + 16) * 4 + (kJDiag + kJR + 16) <= kJCap * 4, "diagonal staging must fit");
 constexpr int kJCtasPerSm = 3;
+constexpr int kDR = 5;                     // diagonal items: entries per thread whose run walks are interleaved
+static_assert(kJDiag % (kDR * kJThreads) == 0, "a full diagonal segment is whole passes");
+constexpr int kTQ = 1024;                  // deferred-tie queue entries per CTA
+constexpr int kTQSegs = 16;                // segments whose (i0, j0) bases the queue can refer to
 constexpr uint8_t kPadTag = 0xFF;
 constexpr size_t kBlSlack = 1024;          // entries of over-read slack behind the last list
 
@@ -244,9 +249,15 @@ struct JoinSmem {
     uint64_t bar;
     unsigned long long item;
     uint32_t split[kJThreads + 1];
-    uint32_t ts[kJChains * kJThreads + 1];
     uint32_t na[kJR], nb[kJR];
+    // deferred ties: the hot loop only marks tie steps; their (A cursor, B index) pairs are queued
+    // here and resolved later by the whole CTA at once (one tie per thread, loads in flight
+    // together) instead of serially behind the segment's barrier
+    uint32_t tq[kTQ];            // slot << 28 | j_rel << 14 | i_rel (relative to the segment's i0 / j0)
+    uint32_t tq_i0[kTQSegs], tq_j0[kTQSegs];
+    uint32_t tq_n;
 };
+static_assert(3 * (sizeof(JoinSmem) + 1024) <= 233472, "three join CTAs must fit one SM");
 
 // One block list in global memory (structure of arrays).
 struct ListView {
@@ -281,17 +292,48 @@ struct SegGeom {
     uint32_t i0, i1, j0, j1, d0, d1, na_s, nb_s, a_ext, a_lo, a_off, a_cnt, b_lo, b_off, b_cnt;
 };
 
-// Re-walk `steps` merge steps from (i, j) and run the tie path at every step whose bit is set in
-// `ties`.  Out of line: the hot loop only records ties in a bit mask and never branches.
-__device__ __noinline__ void replay_ties(uint32_t *cnt, const uint32_t *Ah, const uint32_t *Bh, uint32_t a_ext,
-                                         uint32_t i, uint32_t j, uint32_t steps, uint32_t ties, const ListView A,
-                                         uint32_t i0, const ListView B, uint32_t j0) {
+// Re-walk `steps` merge steps from (i, j) and queue every step whose bit is set in `ties` (the B
+// entry at j met an equal key at the A cursor i).  A queue that is full takes the tie at once.
+// Out of line: the hot loop only records ties in a bit mask and never branches.
+__device__ __noinline__ void queue_ties(JoinSmem &S, const uint32_t *Ah, const uint32_t *Bh, uint32_t a_ext,
+                                        uint32_t i, uint32_t j, uint32_t steps, uint32_t ties, uint32_t slot,
+                                        const ListView A, uint32_t i0, const ListView B, uint32_t j0) {
+    uint32_t q = atomicAdd(&S.tq_n, (uint32_t)__popc(ties));
     uint32_t ka = Ah[i], kb = Bh[j];
     for (uint32_t t = 0; t < steps && (ties >> t) != 0; t++) {
         const bool tb = kb <= ka;
-        if ((ties >> t) & 1u) match_run(cnt, Ah, a_ext, i, kb, A, i0, B, j0 + j);
+        if ((ties >> t) & 1u) {
+            if (q < (uint32_t)kTQ) S.tq[q] = (slot << 28) | (j << 14) | i;
+            else match_run(S.cnt, Ah, a_ext, i, kb, A, i0, B, j0 + j);
+            q++;
+        }
         if (tb) { j++; kb = Bh[j]; } else { i++; ka = Ah[i]; }
     }
+}
+
+// Resolve the queued ties, one per thread: all six words a tie needs first are requested
+// together (L2), so a round costs one memory latency for 256 ties.  CTA-wide; ends with the
+// queue empty.  Callers synchronise before (queue complete) -- the trailing barrier is here.
+__device__ __forceinline__ void flush_ties(JoinSmem &S, const ListView &A, const ListView &B, uint32_t tid) {
+    const uint32_t n = min(S.tq_n, (uint32_t)kTQ);
+    for (uint32_t q = tid; q < n; q += kJThreads) {
+        const uint32_t e = S.tq[q], slot = e >> 28;
+        uint32_t gi = S.tq_i0[slot] + (e & 0x3FFFu);
+        const uint32_t gj = S.tq_j0[slot] + ((e >> 14) & 0x3FFFu);
+        const uint32_t kb = B.hi[gj], lob = B.lo[gj], tagb = B.tag[gj];
+        uint32_t ka = A.hi[gi], loa = A.lo[gi], taga = A.tag[gi];
+        for (;;) {
+            if (ka != kb) break;
+            const uint32_t nx = gi + 1;
+            const bool more = nx < A.len;
+            const uint32_t ka2 = more ? A.hi[nx] : ~kb, loa2 = more ? A.lo[nx] : 0u, taga2 = more ? A.tag[nx] : 0u;
+            if (loa == lob) cnt_inc(S.cnt, taga * kJR + tagb);
+            if (!more) break;
+            gi = nx; ka = ka2; loa = loa2; taga = taga2;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) S.tq_n = 0;
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -302,29 +344,24 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 // Merge-intersect one staged segment.  kChecked = false requires that the segment is full and
 // touches no list end (every key a thread can look at is a real entry): every thread then runs
-// kJChains independent chains of exactly kJE branch-free steps, interleaved for ILP.
-// kChecked = true bounds every step by the chain's own split.
+// kJChains independent chains of exactly kJE branch-free steps, interleaved for ILP, each chain
+// starting at its own merge-path split (no shared split table, no barrier).  kChecked = true
+// bounds every step by the chain's own end split and takes ties at once (list ends only).
 template <bool kChecked>
 __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, const ListView &B, const SegGeom &g,
-                                             uint32_t tid) {
+                                             uint32_t tid, uint32_t slot) {
     const uint32_t *Ah = S.hi + g.a_off, *Bh = S.hi + g.a_cnt + g.b_off;
     const uint32_t len = g.na_s + g.nb_s;
-#pragma unroll
-    for (int c = 0; c < kJChains; c++) {
-        const uint32_t dt0 = min((c * kJThreads + tid) * kJE, len);
-        S.ts[c * kJThreads + tid] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt0);
-    }
-    if (tid == 0) S.ts[kJChains * kJThreads] = g.na_s;
-    __syncthreads();
     if (!kChecked) {
         uint32_t pa[kJChains], pb[kJChains], ka[kJChains], kb[kJChains], ties[kJChains], is[kJChains];
         const uint32_t a_base = smem_u32(Ah), b_base = smem_u32(Bh);
 #pragma unroll
+        for (int c = 0; c < kJChains; c++) is[c] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, (c * kJThreads + tid) * kJE);
+#pragma unroll
         for (int c = 0; c < kJChains; c++) {
-            const uint32_t slot = c * kJThreads + tid;
-            is[c] = S.ts[slot];
+            const uint32_t cs = c * kJThreads + tid;
             pa[c] = a_base + 4u * is[c];
-            pb[c] = b_base + 4u * (slot * kJE - is[c]);
+            pb[c] = b_base + 4u * (cs * kJE - is[c]);
             ka[c] = lds32(pa[c]); kb[c] = lds32(pb[c]);
             ties[c] = 0;
         }
@@ -345,14 +382,15 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, con
 #pragma unroll
         for (int c = 0; c < kJChains; c++)
             if (ties[c])
-                replay_ties(S.cnt, Ah, Bh, g.a_ext, is[c], (c * kJThreads + tid) * kJE - is[c], kJE, ties[c], A, g.i0,
-                            B, g.j0);
+                queue_ties(S, Ah, Bh, g.a_ext, is[c], (c * kJThreads + tid) * kJE - is[c], kJE, ties[c], slot, A, g.i0,
+                           B, g.j0);
     } else {
         for (int c = 0; c < kJChains; c++) {
-            const uint32_t slot = c * kJThreads + tid;
-            const uint32_t dt0 = min(slot * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
-            uint32_t i = S.ts[slot], j = dt0 - i;
-            const uint32_t ie = S.ts[slot + 1], je = dt1 - ie;
+            const uint32_t cs = c * kJThreads + tid;
+            const uint32_t dt0 = min(cs * kJE, len), dt1 = min(dt0 + (uint32_t)kJE, len);
+            if (dt0 == dt1) continue;
+            uint32_t i = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt0), j = dt0 - i;
+            const uint32_t ie = split_bfirst(Ah, g.na_s, Bh, g.nb_s, dt1), je = dt1 - ie;
             uint32_t ka = Ah[i], kb = Bh[j];
             for (uint32_t t = dt0; t < dt1; t++) {
                 const bool tb = (i >= ie) || (j < je && kb <= ka);
@@ -371,28 +409,31 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
     extern __shared__ __align__(128) uint8_t smem_raw[];
     JoinSmem &S = *reinterpret_cast<JoinSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); S.tq_n = 0; }
     __syncthreads();
     uint32_t phase = 0;
-    const uint64_t n_items = p.item_prefix[p.n_local_rb];
+    // Item order: the diagonal items first (ties are the rule there, so they are the longest
+    // items: started first they overlap everything else instead of forming the kernel's tail),
+    // then the off-diagonal items row by row.  Diagonal rows are the last n_diag local rows.
+    const uint64_t n_items = p.n_diag + p.item_prefix[p.n_local_rb];
 
     for (;;) {
         if (tid == 0) S.item = atomicAdd(p.work_counter, 1ull);
         __syncthreads();
         const unsigned long long item = S.item;
         if (item >= n_items) break;
-        uint32_t lo = 0, hi = p.n_local_rb;  // last lr with item_prefix[lr] <= item
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
-        }
-        uint32_t rb = p.local_rb[lo];
-        uint32_t cb = max(rb, p.cb_lo) + (uint32_t)(item - p.item_prefix[lo]);
-        if (p.dbg & 4) {  // column-major order over the full triangle (debug)
-            uint32_t c = (uint32_t)((sqrt(8.0 * (double)item + 1.0) - 1.0) * 0.5);
-            while ((unsigned long long)(c + 1) * (c + 2) / 2 <= item) c++;
-            while ((unsigned long long)c * (c + 1) / 2 > item) c--;
-            cb = c; rb = (uint32_t)(item - (unsigned long long)c * (c + 1) / 2);
+        uint32_t rb, cb;
+        if (item < p.n_diag) {
+            rb = cb = p.local_rb[p.n_local_rb - p.n_diag + (uint32_t)item];
+        } else {
+            const unsigned long long it = item - p.n_diag;
+            uint32_t lo = 0, hi = p.n_local_rb;  // last lr with item_prefix[lr] <= it (rows without items are skipped)
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (p.item_prefix[mid] <= it) lo = mid; else hi = mid;
+            }
+            rb = p.local_rb[lo];
+            cb = max(rb + 1, p.cb_lo) + (uint32_t)(it - p.item_prefix[lo]);
         }
         const uint32_t row0 = rb * kJR, col0 = cb * kJR;
         unsigned long long t_item0 = 0;
@@ -411,15 +452,15 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         const uint32_t la = A.len, lb = B.len;
         __syncthreads();
 
-        if (rb == cb && (p.dbg & 1)) {
-        } else if (rb != cb && (p.dbg & 2)) {
-        } else if (rb == cb) {
-            // ---- diagonal item: equal values are adjacent in the single list; hi, lo and tags
-            // are all staged (ties are the rule here: family members sit in the same block)
+        if (rb == cb) {
+            // ---- diagonal item: equal values are adjacent in the single list (ordered by tag
+            // inside a run); hi, lo and tags are all staged.  Thread t owns entries t, t + 256, ..
+            // of the segment and the warp walks the runs in lock step: at distance d every lane
+            // compares its entry with the one d places on (conflict-free shared-memory reads,
+            // no divergent per-lane loops); the walk ends when no lane's key run goes on.
             constexpr uint32_t kSlice = kJDiag + kJR + 16;  // staged entries per array
             uint32_t *Th = S.hi, *Tl = S.hi + kSlice;
             uint8_t *Tt = reinterpret_cast<uint8_t *>(S.hi + 2 * kSlice);
-            constexpr uint32_t kPer = (kJDiag + kJThreads - 1) / kJThreads;
             for (uint32_t x0 = 0; x0 < la; x0 += kJDiag) {
                 const uint32_t x1 = min(la, x0 + (uint32_t)kJDiag);
                 const uint32_t ext = min(la, x1 + (uint32_t)kJR) - x0;
@@ -432,21 +473,41 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     tma_load_1d(Tt, A.tag + x0, a_cnt, &S.bar);
                 }
                 mbar_wait(&S.bar, phase); phase ^= 1;
-                const uint32_t e0 = tid * kPer, e1 = min(e0 + kPer, x1 - x0);
-                for (uint32_t x = e0; x < e1; x++) {
-                    const uint32_t h = Th[x], l = Tl[x], tx = Tt[x];
-                    uint32_t y = x + 1;
-                    for (; y < ext && Th[y] == h; y++)
-                        if (Tl[y] == l) {
-                            const uint32_t ty = Tt[y];
-                            cnt_inc(S.cnt, min(tx, ty) * kJR + max(tx, ty));
+                const uint32_t nx = x1 - x0;
+                // kDR entries per thread in flight: their run walks are independent, so the
+                // shared-memory loads of one step overlap instead of forming one dependent chain
+                for (uint32_t xb = 0; xb < nx; xb += kDR * kJThreads) {  // uniform trip count across the warp
+                    uint32_t h[kDR], l[kDR], tx[kDR];
+                    bool run[kDR];
+                    uint32_t hit_end = 0;
+#pragma unroll
+                    for (int r = 0; r < kDR; r++) {
+                        const uint32_t x = xb + r * kJThreads + tid;
+                        run[r] = x < nx;
+                        h[r] = run[r] ? Th[x] : 0u; l[r] = run[r] ? Tl[x] : 0u; tx[r] = run[r] ? Tt[x] : 0u;
+                    }
+                    for (uint32_t d = 1;; d++) {
+                        bool any = false;
+#pragma unroll
+                        for (int r = 0; r < kDR; r++) {
+                            const uint32_t y = xb + r * kJThreads + tid + d;
+                            if (run[r] && y >= ext) { run[r] = false; hit_end |= 1u << r; }
+                            const uint32_t hy = run[r] ? Th[y] : 0u, ly = run[r] ? Tl[y] : 0u, ty = run[r] ? Tt[y] : 0u;
+                            run[r] = run[r] && hy == h[r];
+                            if (run[r] && ly == l[r]) cnt_inc(S.cnt, min(tx[r], ty) * kJR + max(tx[r], ty));
+                            any = any || run[r];
                         }
-                    if (y == ext)
-                        for (uint32_t gy = x0 + y; gy < la && A.hi[gy] == h; gy++)
-                            if (A.lo[gy] == l) {
-                                const uint32_t ty = A.tag[gy];
-                                cnt_inc(S.cnt, min(tx, ty) * kJR + max(tx, ty));
-                            }
+                        if (!__any_sync(0xffffffffu, any)) break;
+                    }
+                    // a key run that outlasts the staged extension (>= kJR equal keys) goes on in global memory
+#pragma unroll
+                    for (int r = 0; r < kDR; r++)
+                        if (hit_end & (1u << r))
+                            for (uint32_t gy = x0 + ext; gy < la && A.hi[gy] == h[r]; gy++)
+                                if (A.lo[gy] == l[r]) {
+                                    const uint32_t ty = A.tag[gy];
+                                    cnt_inc(S.cnt, min(tx[r], ty) * kJR + max(tx[r], ty));
+                                }
                 }
                 __syncthreads();
             }
@@ -455,6 +516,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
             const uint32_t total = la + lb;
             const uint32_t nseg = (total + kJD - 1) / kJD;
             bool done = false;
+            uint32_t slot = 0;  // segments since the last flush of the tie queue
             for (uint32_t kb = 0; kb < nseg && !done; kb += kJThreads - 1) {
                 const uint32_t nsb = min((uint32_t)(kJThreads - 1), nseg - kb);
                 if (tid <= nsb) {
@@ -476,6 +538,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     g.b_lo = g.j0 & ~15u; g.b_off = g.j0 - g.b_lo;
                     g.b_cnt = (g.b_off + g.nb_s + 1u + 15u) & ~15u;
                     if (tid == 0) {
+                        S.tq_i0[slot] = g.i0; S.tq_j0[slot] = g.j0;
                         fence_proxy_async();
                         mbar_arrive_expect_tx(&S.bar, (g.a_cnt + g.b_cnt) * 4u);
                         tma_load_1d(S.hi, A.hi + g.a_lo, g.a_cnt * 4u, &S.bar);
@@ -484,13 +547,22 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     mbar_wait(&S.bar, phase); phase ^= 1;
                     // a full segment that ends before either list does holds only real entries
                     if (g.i1 < la && g.j1 < lb && g.d1 - g.d0 == (uint32_t)kJD)
-                        join_segment<false>(S, A, B, g, tid);
+                        join_segment<false>(S, A, B, g, tid, slot);
                     else
-                        join_segment<true>(S, A, B, g, tid);
-                    __syncthreads();  // the staged slices are free for the next TMA
+                        join_segment<true>(S, A, B, g, tid, slot);
+                    // the staged slices are free for the next TMA and the queue is complete; the thread
+                    // whose enqueue came last sees the final fill, so the OR is the same for all
+                    const bool half_full =
+                        __syncthreads_or(*reinterpret_cast<volatile uint32_t *>(&S.tq_n) >= (uint32_t)(kTQ / 2));
+                    if (++slot == (uint32_t)kTQSegs || half_full) {
+                        flush_ties(S, A, B, tid);
+                        slot = 0;
+                    }
                 }
                 __syncthreads();
             }
+            __syncthreads();
+            flush_ties(S, A, B, tid);
         }
         __syncthreads();
 
@@ -652,39 +724,40 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
     return join_launch(ws, p, ws.d_fin_hi, ws.d_fin_lo, ws.d_fin_tags, ws.d_bl_len, shard, n_shards, stream);
 }
 
-// Host-buffer path, pipelined against the PCIe upload.  The table goes up in `chunks` slices of
-// whole blocks on `copy`; as soon as slice c is resident, `compute` builds its block lists and
-// joins every item (rb <= cb, cb in slice c) -- all lists such an item needs are finished by
-// then.  Slice boundaries follow nb * sqrt(c / chunks): every wave then holds about the same
-// number of items, the early (large) slices hide under the remaining upload and the last wave --
-// the only kernel time left on the critical path -- is one short round of items.  The shift of
+// Host-buffer path, pipelined against the PCIe upload.  The table goes up in `chunks` equal slices
+// of whole blocks on `copy`; as soon as a slice is resident, `compute` builds its block lists, so
+// the build hides under the transfer.  The join runs in waves: wave w covers the items (rb <= cb)
+// whose column block lies between the previous wave's end and this one's -- every list such an
+// item needs is finished by then.  A wave costs at least one diagonal item's latency, so there
+// are few of them: an early one at `wave_frac` of the blocks fills the time the GPU would idle
+// while the rest of the table is still crossing PCIe (0 = none), and the final one.  The shift of
 // the order-preserving keys needs the largest valid hash of the WHOLE table before the first
 // slice is built: the host reads it off the row ends while the first slice is in flight.
 // p must come from prefilter_prepare(.., d_table, d_counts, ..) on `compute`; d_counts resident.
 int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint64_t *h_hashes,
                             const uint32_t *h_counts, uint64_t *d_table, cudaStream_t compute, cudaStream_t copy,
-                            int chunks) {
+                            int chunks, double wave_frac) {
     const uint32_t nb = (p.n + kJR - 1) / kJR;
     const uint32_t stride = p.stride;
     const uint64_t bl_cap = (uint64_t)kJR * stride;
     chunks = std::max(1, std::min<int>(chunks, (int)nb));
     std::vector<uint32_t> bound(chunks + 1, 0);
-    for (int c = 1; c <= chunks; c++) {
-        uint32_t b = (uint32_t)std::llround((double)nb * std::sqrt((double)c / chunks));
-        bound[c] = std::min(nb, std::max(b, bound[c - 1] + 1));
+    for (int c = 1; c <= chunks; c++) bound[c] = (uint32_t)((uint64_t)nb * c / chunks);
+    // waves end after the slices listed in wave_end (ascending, last = chunks - 1)
+    std::vector<int> wave_end;
+    if (wave_frac > 0.0 && wave_frac < 1.0) {
+        const int c = (int)std::llround(wave_frac * chunks) - 1;
+        if (c >= 0 && c < chunks - 1) wave_end.push_back(c);
     }
-    bound[chunks] = nb;
-    {   // drop empty slices (tables of a few blocks)
-        std::vector<uint32_t> u;
-        for (uint32_t b : bound) if (u.empty() || b > u.back()) u.push_back(b);
-        bound.swap(u);
-        chunks = (int)bound.size() - 1;
-    }
+    wave_end.push_back(chunks - 1);
+    const int waves = (int)wave_end.size();
+
     const bool debug = getenv("GALAH_B200_STREAM_DEBUG") != nullptr;
     std::vector<cudaEvent_t> dbg;
-    auto mark = [&](cudaStream_t st) {
+    std::vector<std::string> dbg_what;
+    auto mark = [&](const std::string &what) {
         if (!debug) return;
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); dbg.push_back(e);
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, compute); dbg.push_back(e); dbg_what.push_back(what);
     };
     if (int rc = ensure_fin(ws, (uint64_t)nb * bl_cap, compute)) return rc;
     if (ws_ensure(ws.d_bl_len, ws.cap_bl_len, nb)) return 2;
@@ -693,31 +766,33 @@ int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint6
         GB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws.chunk_ev.push_back(e);
     }
-    // work lists of all waves, one upload: wave c = { (rb, cb) : rb < bound[c+1], max(rb, bound[c]) <= cb < bound[c+1] }
+    // work lists of all waves, one upload: wave w = { (rb, cb) : rb <= cb, w0 <= cb < w1 }; the
+    // diagonal items belong to its last (w1 - w0) rows
     std::vector<uint32_t> local;
     std::vector<uint64_t> prefix;
-    std::vector<size_t> off_local(chunks), off_prefix(chunks);
-    for (int c = 0; c < chunks; c++) {
-        off_local[c] = local.size(); off_prefix[c] = prefix.size();
+    std::vector<size_t> off_local(waves), off_prefix(waves);
+    for (int w = 0; w < waves; w++) {
+        const uint32_t w0 = w ? bound[wave_end[w - 1] + 1] : 0, w1 = bound[wave_end[w] + 1];
+        off_local[w] = local.size(); off_prefix[w] = prefix.size();
         prefix.push_back(0);
-        for (uint32_t rb = 0; rb < bound[c + 1]; rb++) {
+        for (uint32_t rb = 0; rb < w1; rb++) {
             local.push_back(rb);
-            prefix.push_back(prefix.back() + (bound[c + 1] - std::max(rb, bound[c])));
+            prefix.push_back(prefix.back() + (w1 - std::max(rb + 1, w0)));  // off-diagonal items
         }
     }
     if (ws_ensure(ws.d_local_rb, ws.cap_local_rb, local.size())) return 2;
     if (ws_ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;
-    if (ws_ensure(ws.d_wave_counters, ws.cap_wave_counters, (size_t)chunks)) return 2;
+    if (ws_ensure(ws.d_wave_counters, ws.cap_wave_counters, (size_t)waves)) return 2;
     // the copy stream may not touch d_table before earlier work on `compute` is done with it
     GB_CUDA(cudaEventRecord(ws.chunk_ev[0], compute));
     GB_CUDA(cudaStreamWaitEvent(copy, ws.chunk_ev[0], 0));
     for (int c = 0; c < chunks; c++) {
         const size_t r0 = (size_t)bound[c] * kJR, r1 = std::min<size_t>((size_t)bound[c + 1] * kJR, p.n);
-        GB_CUDA(cudaMemcpyAsync(d_table + r0 * stride, h_hashes + r0 * stride, (r1 - r0) * stride * 8,
-                                cudaMemcpyHostToDevice, copy));
+        if (r1 > r0)
+            GB_CUDA(cudaMemcpyAsync(d_table + r0 * stride, h_hashes + r0 * stride, (r1 - r0) * stride * 8,
+                                    cudaMemcpyHostToDevice, copy));
         GB_CUDA(cudaEventRecord(ws.chunk_ev[c], copy));
     }
-    if (getenv("GALAH_B200_STREAM_SERIAL")) cudaStreamSynchronize(copy);
     unsigned long long gmax = 0;  // overlaps the first slice's DMA
     for (size_t r = 0; r < p.n; r++) {
         const uint32_t cnt = std::min(h_counts[r], stride);
@@ -727,7 +802,7 @@ int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint6
     GB_CUDA(cudaMemcpyAsync(ws.d_gmax, &gmax, sizeof(gmax), cudaMemcpyHostToDevice, compute));
     GB_CUDA(cudaMemcpyAsync(ws.d_local_rb, local.data(), local.size() * 4, cudaMemcpyHostToDevice, compute));
     GB_CUDA(cudaMemcpyAsync(ws.d_item_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, compute));
-    GB_CUDA(cudaMemsetAsync(ws.d_wave_counters, 0, (size_t)chunks * sizeof(unsigned long long), compute));
+    GB_CUDA(cudaMemsetAsync(ws.d_wave_counters, 0, (size_t)waves * sizeof(unsigned long long), compute));
     int dev = 0, sms = kNumSMsFallback;
     GB_CUDA(cudaGetDevice(&dev));
     GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -735,58 +810,70 @@ int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint6
     GB_CUDA(cudaFuncSetAttribute(prefilter_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.bl_hi = ws.d_fin_hi; p.bl_lo = ws.d_fin_lo; p.bl_tags = ws.d_fin_tags; p.bl_len = ws.d_bl_len; p.bl_cap = bl_cap;
     p.n_row_blocks = nb;
-    p.dbg = getenv("GALAH_B200_DBG") ? atoi(getenv("GALAH_B200_DBG")) : 0;
     unsigned long long *d_dbg = nullptr;
-    const uint64_t dbg_items = (uint64_t)nb * (nb + 1) / 2;
-    if (getenv("GALAH_B200_ITEMLOG")) { cudaMalloc(&d_dbg, dbg_items * 32); cudaMemset(d_dbg, 0, dbg_items * 32); }
+    uint64_t dbg_items = 0;
+    if (getenv("GALAH_B200_ITEMLOG")) {
+        dbg_items = (uint64_t)nb * (nb + 1) / 2;
+        cudaMalloc(&d_dbg, dbg_items * 32); cudaMemset(d_dbg, 0, dbg_items * 32);
+    }
+    mark("start");
+    int w = 0;
     for (int c = 0; c < chunks; c++) {
         const uint32_t b0 = bound[c], b1 = bound[c + 1];
         GB_CUDA(cudaStreamWaitEvent(compute, ws.chunk_ev[c], 0));
-        mark(compute);
-        if (int rc = blocklist_build(ws, p.hashes, p.counts, p.n, stride, b0, b1, ws.d_fin_hi + b0 * bl_cap,
-                                     ws.d_fin_lo + b0 * bl_cap, ws.d_fin_tags + b0 * bl_cap, ws.d_bl_len + b0, compute,
-                                     /*gmax_ready=*/true))
-            return rc;
-        p.cb_lo = b0;
+        if (b1 > b0) {
+            if (int rc = blocklist_build(ws, p.hashes, p.counts, p.n, stride, b0, b1, ws.d_fin_hi + b0 * bl_cap,
+                                         ws.d_fin_lo + b0 * bl_cap, ws.d_fin_tags + b0 * bl_cap, ws.d_bl_len + b0,
+                                         compute, /*gmax_ready=*/true))
+                return rc;
+            mark("build of blocks [" + std::to_string(b0) + "," + std::to_string(b1) + ")");
+        }
+        if (c != wave_end[w]) continue;
+        const uint32_t w0 = w ? bound[wave_end[w - 1] + 1] : 0;
+        p.cb_lo = w0;
         p.n_local_rb = b1;
-        p.local_rb = ws.d_local_rb + off_local[c];
-        p.item_prefix = ws.d_item_prefix + off_prefix[c];
-        p.work_counter = ws.d_wave_counters + c;
-        p.dbg_buf = (d_dbg && c == chunks - 1) ? d_dbg : nullptr;
-        const uint64_t n_items = prefix[off_prefix[c] + b1];
-        mark(compute);
-        if (c == chunks - 1 && ws.record(1, compute)) return 2;
-        prefilter_join_kernel<<<(uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm), kJThreads, smem,
-                                compute>>>(p);
-        GB_LAUNCH_CHECK();
+        p.n_diag = b1 - w0;
+        p.local_rb = ws.d_local_rb + off_local[w];
+        p.item_prefix = ws.d_item_prefix + off_prefix[w];
+        p.work_counter = ws.d_wave_counters + w;
+        p.dbg_buf = (d_dbg && w == waves - 1) ? d_dbg : nullptr;
+        const uint64_t n_items = (b1 - w0) + prefix[off_prefix[w] + b1];
+        if (w == waves - 1 && ws.record(1, compute)) return 2;
+        if (n_items) {
+            prefilter_join_kernel<<<(uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm), kJThreads, smem,
+                                    compute>>>(p);
+            GB_LAUNCH_CHECK();
+            mark("join of column blocks [" + std::to_string(w0) + "," + std::to_string(b1) + "), " +
+                 std::to_string(n_items) + " items");
+        }
+        w++;
     }
     if (ws.record(2, compute)) return 2;
     if (debug) {
-        mark(compute);
         cudaStreamSynchronize(compute);
-        for (int c = 0; c < chunks; c++) {
-            float b = 0, j = 0, t = 0;
-            cudaEventElapsedTime(&t, dbg[0], dbg[2 * c]);
-            cudaEventElapsedTime(&b, dbg[2 * c], dbg[2 * c + 1]);
-            cudaEventElapsedTime(&j, dbg[2 * c + 1], dbg[2 * c + 2]);
-            fprintf(stderr, "[stream] slice %d blocks [%u,%u) start +%.3f ms build %.3f ms join %.3f ms (%llu items)\n", c,
-                    bound[c], bound[c + 1], t, b, j, (unsigned long long)prefix[off_prefix[c] + bound[c + 1]]);
+        for (size_t x = 1; x < dbg.size(); x++) {
+            float t = 0, d = 0;
+            cudaEventElapsedTime(&t, dbg[0], dbg[x]);
+            cudaEventElapsedTime(&d, dbg[x - 1], dbg[x]);
+            fprintf(stderr, "[stream] +%.3f ms (%.3f ms since the previous mark, waits for the upload included): %s\n", t, d,
+                    dbg_what[x].c_str());
         }
         for (cudaEvent_t e : dbg) cudaEventDestroy(e);
     }
     if (d_dbg) {
         cudaStreamSynchronize(compute);
-        const uint64_t n_items = prefix[off_prefix[chunks - 1] + bound[chunks]];
+        const uint32_t w0 = waves > 1 ? bound[wave_end[waves - 2] + 1] : 0;
+        const uint64_t n_items = (nb - w0) + prefix[off_prefix[waves - 1] + nb];
         std::vector<unsigned long long> h(n_items * 4);
         cudaMemcpy(h.data(), d_dbg, n_items * 32, cudaMemcpyDeviceToHost);
         cudaFree(d_dbg);
         FILE *f = fopen(getenv("GALAH_B200_ITEMLOG"), "w");
         unsigned long long t0 = ~0ull;
         for (uint64_t x = 0; x < n_items; x++) t0 = std::min(t0, h[x * 4]);
-        for (uint64_t x = 0; x < n_items; x++)
+        for (uint64_t x = 0; x < n_items && f; x++)
             fprintf(f, "%llu %llu %llu %llu %llu %llu\n", (unsigned long long)x, h[x * 4] - t0, h[x * 4 + 1] - t0, h[x * 4 + 2],
                     h[x * 4 + 3] >> 32, h[x * 4 + 3] & 0xFFFFFFFFull);
-        fclose(f);
+        if (f) fclose(f);
     }
     return 0;
 }

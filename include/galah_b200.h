@@ -110,10 +110,11 @@ int galah_b200_prefilter_mode(int mode);
 int galah_b200_prefilter_last_timing(float *build_ms, float *main_ms);
 
 /* Host-buffer calls (galah_b200_prefilter / _shard with n_shards == 1, mode 0) upload the table
- * in `chunks` slices of whole row blocks on a copy stream and build + join each slice as soon
- * as it is resident, so only the last wave of kernels is left after the PCIe transfer ends.
- * chunks <= 1 disables the pipeline (one upload, then the kernels); < 0 only queries.  Returns
- * the previous setting.  The pair list is identical either way. */
+ * in `chunks` slices of whole row blocks on a copy stream and build the block lists of each
+ * slice as soon as it is resident, so the build hides under the PCIe transfer and only the join
+ * is left when the transfer ends.  chunks <= 1 disables the pipeline (one upload, then the
+ * kernels); < 0 only queries.  Returns the previous setting (default 4).  The pair list is
+ * identical either way. */
 int galah_b200_prefilter_stream_chunks(int chunks);
 
 /* Host wall-clock breakdown of the most recent host-buffer prefilter call, milliseconds:

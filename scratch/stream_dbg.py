@@ -21,5 +21,12 @@ def run(chunks, label, env={}):
         os.environ.pop("GALAH_B200_STREAM_DEBUG", None)
     for e in env: os.environ.pop(e)
     print(label, chunks, f"{dt*1e3:.3f} ms", len(r), gb.prefilter_last_timing(), flush=True)
-run(1, "all", {"GALAH_B200_STREAM_FORCE": "1", "GALAH_B200_ITEMLOG": "gpurun_out/items_full.txt"})
-run(8, "w8", {"GALAH_B200_ITEMLOG": "gpurun_out/items_w8.txt"})
+run(1, "plain")
+run(8, "s8")
+run(4, "s4")
+run(16, "s16")
+run(8, "s8-w50", {"GALAH_B200_STREAM_WAVE": "0.5"})
+run(8, "s8-w625", {"GALAH_B200_STREAM_WAVE": "0.625"})
+run(8, "s8-w75", {"GALAH_B200_STREAM_WAVE": "0.75"})
+run(16, "s16-w56", {"GALAH_B200_STREAM_WAVE": "0.5625"})
+run(16, "s16-w69", {"GALAH_B200_STREAM_WAVE": "0.6875"})
