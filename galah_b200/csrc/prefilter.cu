@@ -280,12 +280,17 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
     for (uint32_t rb = 0; rb < nrb; rb++) {
         if (shard_of_group(rb / per_group, n_shards) != shard) continue;
         local.push_back(rb);
-        // join: the diagonal item of every local row is scheduled ahead of all off-diagonal ones
-        prefix.push_back(prefix.back() + (nrb - rb - (diag_separate ? 1 : 0) + chunk_blocks - 1) / chunk_blocks);
+        // join: the diagonal item and the adjacent item (rb, rb + 1) of every local row are
+        // scheduled ahead of all other items (the kernel takes the longest items first)
+        const uint32_t ahead = diag_separate ? 1u + (rb + 1 < nrb ? 1u : 0u) : 0u;
+        prefix.push_back(prefix.back() + (nrb - rb - ahead + chunk_blocks - 1) / chunk_blocks);
     }
     p.n_row_blocks = nrb;
     p.n_local_rb = (uint32_t)local.size();
     p.n_diag = diag_separate ? (uint32_t)local.size() : 0;
+    // every local row but the table's last block has an adjacent item: a prefix of the local rows
+    p.adj_lr0 = 0;
+    p.n_adj = diag_separate ? (uint32_t)local.size() - (!local.empty() && local.back() + 1 == nrb ? 1u : 0u) : 0;
     if (local.empty()) return 0;
     if (ws_ensure(ws.d_local_rb, ws.cap_local_rb, local.size())) return 2;
     if (ws_ensure(ws.d_item_prefix, ws.cap_prefix, prefix.size())) return 2;

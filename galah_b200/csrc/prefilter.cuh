@@ -97,6 +97,7 @@ struct KernelParams {
     const uint32_t *bl_len;
     uint64_t bl_cap;  // entries per block list (kShardRows * stride)
     uint32_t n_diag;  // join: diagonal items, taken first; they belong to the LAST n_diag local rows
+    uint32_t n_adj, adj_lr0;  // join: items (rb, rb + 1), taken next; local rows [adj_lr0, adj_lr0 + n_adj)
     unsigned long long *dbg_buf;  // per-item {start ns, end ns, sm, rb << 32 | cb} log (debug), or null
     uint32_t cb_lo;   // first column block of the launch's window (0 unless a streamed wave)
 };

@@ -122,6 +122,99 @@ __global__ void __launch_bounds__(256) bl_len_kernel(const uint64_t *__restrict_
     }
 }
 
+// Seed of the merge tree: one CTA takes kSeedRows consecutive table rows, forms their level-0
+// entries (value, tag = row % R; padding = (2^64-1, 0xFF)) in shared memory and runs the first
+// log2(kSeedRows) merge levels there, so those levels cost one pass over HBM instead of one
+// each.  Every level: thread t owns kSeedE consecutive outputs of one run pair (threads never
+// span pairs: a pair holds 2m = kSeedE * threads-per-pair entries or fewer), finds its start by a
+// merge-path split, merges into registers; after a barrier the registers replace the inputs.
+// Values live at index i + (i >> 5): cursors of neighbouring threads are about kSeedE / 2 = 16
+// entries apart, which the skew spreads over all banks.  Needs stride <= kSeedE * 256 / kSeedRows.
+constexpr int kSeedRows = 8;
+constexpr int kSeedThreads = 256;
+constexpr int kSeedE = 32;
+constexpr uint32_t kSeedMaxStride = kSeedE * kSeedThreads / kSeedRows;  // 1024
+__host__ __device__ constexpr uint32_t seed_skew(uint32_t i) { return i + (i >> 5); }
+static size_t seed_smem_bytes(uint32_t stride) {
+    const uint32_t ne = kSeedRows * stride;
+    return (size_t)(seed_skew(ne) + 1) * 8 + ((ne + 15u) & ~15u);
+}
+
+__global__ void __launch_bounds__(kSeedThreads) bl_seed_kernel(const uint64_t *__restrict__ hashes,
+                                                               const uint32_t *__restrict__ counts, uint32_t n,
+                                                               uint32_t stride, uint64_t row0,
+                                                               uint64_t *__restrict__ vals,
+                                                               uint8_t *__restrict__ tags) {
+    extern __shared__ __align__(16) uint8_t seed_smem_raw[];
+    const uint32_t ne = kSeedRows * stride;
+    uint64_t *V = reinterpret_cast<uint64_t *>(seed_smem_raw);
+    uint8_t *T = seed_smem_raw + (size_t)(seed_skew(ne) + 1) * 8;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t first_row = row0 + (uint64_t)blockIdx.x * kSeedRows;
+    {   // all kSeedRows loads of a column step are independent: they are in flight together
+        uint32_t cnt[kSeedRows];
+#pragma unroll
+        for (int r = 0; r < kSeedRows; r++) cnt[r] = first_row + r < n ? min(counts[first_row + r], stride) : 0u;
+        for (uint32_t col = tid; col < stride; col += kSeedThreads) {
+            uint64_t v[kSeedRows];
+#pragma unroll
+            for (int r = 0; r < kSeedRows; r++) v[r] = col < cnt[r] ? hashes[(first_row + r) * stride + col] : kPad;
+#pragma unroll
+            for (int r = 0; r < kSeedRows; r++) {
+                V[seed_skew(r * stride + col)] = v[r];
+                T[r * stride + col] = col < cnt[r] ? (uint8_t)((first_row + r) % kJR) : kPadTag;
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t tpp = kSeedThreads / (kSeedRows / 2);  // threads per run pair
+    for (uint32_t m = stride; m < ne; m *= 2, tpp *= 2) {
+        const uint32_t pair = tid / tpp, lt = tid % tpp;
+        const uint32_t base = pair * 2 * m;
+        const uint32_t d0 = min(lt * kSeedE, 2 * m), d1 = min(d0 + (uint32_t)kSeedE, 2 * m);
+        // split: smallest i in [max(0, d0 - m), min(d0, m)] with !(A[i] <= B[d0 - 1 - i]) under (value, tag)
+        uint32_t lo = d0 > m ? d0 - m : 0, hi = min(d0, m);
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t ia = base + mid, ib = base + m + d0 - 1 - mid;
+            const uint64_t a = V[seed_skew(ia)], b = V[seed_skew(ib)];
+            const bool le = a < b || (a == b && T[ia] <= T[ib]);
+            if (le) lo = mid + 1; else hi = mid;
+        }
+        uint32_t i = lo, j = d0 - lo;  // cursors inside the pair's two runs
+        uint64_t ov[kSeedE];
+        uint32_t ot[kSeedE / 4];
+#pragma unroll
+        for (int w = 0; w < kSeedE / 4; w++) ot[w] = 0;
+        uint64_t a = V[seed_skew(base + min(i, m - 1))], b = V[seed_skew(base + m + min(j, m - 1))];
+        uint32_t ta = T[base + min(i, m - 1)], tb = T[base + m + min(j, m - 1)];
+#pragma unroll
+        for (int x = 0; x < kSeedE; x++) {
+            bool take_a;
+            if (j >= m) take_a = true;
+            else if (i >= m) take_a = false;
+            else take_a = a < b || (a == b && ta <= tb);
+            ov[x] = take_a ? a : b;
+            ot[x >> 2] |= (take_a ? ta : tb) << (8 * (x & 3));
+            if (take_a) { i++; const uint32_t q = base + min(i, m - 1); a = V[seed_skew(q)]; ta = T[q]; }
+            else { j++; const uint32_t q = base + m + min(j, m - 1); b = V[seed_skew(q)]; tb = T[q]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int x = 0; x < kSeedE; x++)
+            if (d0 + x < d1) {
+                V[seed_skew(base + d0 + x)] = ov[x];
+                T[base + d0 + x] = (uint8_t)(ot[x >> 2] >> (8 * (x & 3)));
+            }
+        __syncthreads();
+    }
+    const uint64_t out0 = (uint64_t)blockIdx.x * ne;
+    for (uint32_t e = tid; e < ne; e += kSeedThreads) {
+        vals[out0 + e] = V[seed_skew(e)];
+        tags[out0 + e] = T[e];
+    }
+}
+
 __device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8_t tb) {
     return a < b || (a == b && ta <= tb);
 }
@@ -412,10 +505,12 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); S.tq_n = 0; }
     __syncthreads();
     uint32_t phase = 0;
-    // Item order: the diagonal items first (ties are the rule there, so they are the longest
-    // items: started first they overlap everything else instead of forming the kernel's tail),
-    // then the off-diagonal items row by row.  Diagonal rows are the last n_diag local rows.
-    const uint64_t n_items = p.n_diag + p.item_prefix[p.n_local_rb];
+    // Item order, longest first: the diagonal items (ties are the rule there: started first they
+    // overlap everything else instead of forming the kernel's tail), then the items of adjacent
+    // blocks (rb, rb + 1) -- input that keeps relatives together puts its cross-block ties there --
+    // then the remaining off-diagonal items row by row.  Diagonal rows are the last n_diag local
+    // rows; rows with an adjacent item are the n_adj local rows from adj_lr0.
+    const uint64_t n_items = (uint64_t)p.n_diag + p.n_adj + p.item_prefix[p.n_local_rb];
 
     for (;;) {
         if (tid == 0) S.item = atomicAdd(p.work_counter, 1ull);
@@ -425,15 +520,19 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         uint32_t rb, cb;
         if (item < p.n_diag) {
             rb = cb = p.local_rb[p.n_local_rb - p.n_diag + (uint32_t)item];
+        } else if (item < (uint64_t)p.n_diag + p.n_adj) {
+            rb = p.local_rb[p.adj_lr0 + (uint32_t)(item - p.n_diag)];
+            cb = rb + 1;
         } else {
-            const unsigned long long it = item - p.n_diag;
+            const unsigned long long it = item - p.n_diag - p.n_adj;
             uint32_t lo = 0, hi = p.n_local_rb;  // last lr with item_prefix[lr] <= it (rows without items are skipped)
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (p.item_prefix[mid] <= it) lo = mid; else hi = mid;
             }
             rb = p.local_rb[lo];
-            cb = max(rb + 1, p.cb_lo) + (uint32_t)(it - p.item_prefix[lo]);
+            const uint32_t has_adj = lo >= p.adj_lr0 && lo < p.adj_lr0 + p.n_adj ? 1u : 0u;
+            cb = max(rb + 1, p.cb_lo) + has_adj + (uint32_t)(it - p.item_prefix[lo]);
         }
         const uint32_t row0 = rb * kJR, col0 = cb * kJR;
         unsigned long long t_item0 = 0;
@@ -635,7 +734,15 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
         }
         ws.cap_bl = total;
     }
-    {
+    uint64_t m0 = stride;  // run length the global merge levels start from
+    if (stride <= kSeedMaxStride) {
+        const size_t smem = seed_smem_bytes((uint32_t)stride);
+        GB_CUDA(cudaFuncSetAttribute(bl_seed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bl_seed_kernel<<<(uint32_t)((b1 - b0) * (kJR / kSeedRows)), kSeedThreads, smem, stream>>>(
+            d_hashes, d_counts, (uint32_t)n, (uint32_t)stride, (uint64_t)b0 * kJR, ws.d_bl_vals[0], ws.d_bl_tags[0]);
+        GB_LAUNCH_CHECK();
+        m0 = (uint64_t)kSeedRows * stride;
+    } else {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)sms * 16);
         bl_init_kernel<<<grid, 256, 0, stream>>>(d_hashes, d_counts, (uint32_t)n, (uint32_t)stride,
                                                  (uint64_t)b0 * kJR, total, ws.d_bl_vals[0], ws.d_bl_tags[0]);
@@ -648,7 +755,7 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
         const uint64_t need = total / (2 * stride) * ((2 * stride + kMTile - 1) / kMTile + 1) + 16;
         if (ws_ensure(ws.d_splits, ws.cap_splits, need)) return 2;
     }
-    for (uint64_t m = stride; m < bl_cap; m *= 2) {
+    for (uint64_t m = m0; m < bl_cap; m *= 2) {
         const uint32_t chunks = (uint32_t)((2 * m + kMTile - 1) / kMTile);
         const uint64_t grid = total / (2 * m) * chunks;
         if (grid > 0x7FFFFFFFull) { set_error("prefilter: table too large for the merge grid"); return 3; }
@@ -777,7 +884,9 @@ int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint6
         prefix.push_back(0);
         for (uint32_t rb = 0; rb < w1; rb++) {
             local.push_back(rb);
-            prefix.push_back(prefix.back() + (w1 - std::max(rb + 1, w0)));  // off-diagonal items
+            const uint32_t first = std::max(rb + 1, w0);              // first off-diagonal column block in the window
+            const uint32_t has_adj = first == rb + 1 && first < w1;  // (rb, rb + 1) is scheduled ahead of the row
+            prefix.push_back(prefix.back() + (w1 - std::min(w1, first + has_adj)));
         }
     }
     if (ws_ensure(ws.d_local_rb, ws.cap_local_rb, local.size())) return 2;
@@ -833,11 +942,13 @@ int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint6
         p.cb_lo = w0;
         p.n_local_rb = b1;
         p.n_diag = b1 - w0;
+        p.adj_lr0 = std::max(w0, 1u) - 1;                    // rows w0 - 1 .. b1 - 2 have (rb, rb + 1) in the window
+        p.n_adj = b1 >= 2 && b1 - 1 > p.adj_lr0 ? b1 - 1 - p.adj_lr0 : 0;
         p.local_rb = ws.d_local_rb + off_local[w];
         p.item_prefix = ws.d_item_prefix + off_prefix[w];
         p.work_counter = ws.d_wave_counters + w;
         p.dbg_buf = (d_dbg && w == waves - 1) ? d_dbg : nullptr;
-        const uint64_t n_items = (b1 - w0) + prefix[off_prefix[w] + b1];
+        const uint64_t n_items = (uint64_t)p.n_diag + p.n_adj + prefix[off_prefix[w] + b1];
         if (w == waves - 1 && ws.record(1, compute)) return 2;
         if (n_items) {
             prefilter_join_kernel<<<(uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm), kJThreads, smem,
@@ -862,8 +973,7 @@ int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint6
     }
     if (d_dbg) {
         cudaStreamSynchronize(compute);
-        const uint32_t w0 = waves > 1 ? bound[wave_end[waves - 2] + 1] : 0;
-        const uint64_t n_items = (nb - w0) + prefix[off_prefix[waves - 1] + nb];
+        const uint64_t n_items = (uint64_t)p.n_diag + p.n_adj + prefix[off_prefix[waves - 1] + nb];
         std::vector<unsigned long long> h(n_items * 4);
         cudaMemcpy(h.data(), d_dbg, n_items * 32, cudaMemcpyDeviceToHost);
         cudaFree(d_dbg);

@@ -22,11 +22,9 @@ def run(chunks, label, env={}):
     for e in env: os.environ.pop(e)
     print(label, chunks, f"{dt*1e3:.3f} ms", len(r), gb.prefilter_last_timing(), flush=True)
 run(1, "plain")
-run(8, "s8")
 run(4, "s4")
-run(16, "s16")
-run(8, "s8-w50", {"GALAH_B200_STREAM_WAVE": "0.5"})
-run(8, "s8-w625", {"GALAH_B200_STREAM_WAVE": "0.625"})
+run(4, "s4-w50", {"GALAH_B200_STREAM_WAVE": "0.5"})
+run(4, "s4-w75", {"GALAH_B200_STREAM_WAVE": "0.75"})
+run(6, "s6")
+run(6, "s6-w66", {"GALAH_B200_STREAM_WAVE": "0.667"})
 run(8, "s8-w75", {"GALAH_B200_STREAM_WAVE": "0.75"})
-run(16, "s16-w56", {"GALAH_B200_STREAM_WAVE": "0.5625"})
-run(16, "s16-w69", {"GALAH_B200_STREAM_WAVE": "0.6875"})
