@@ -43,6 +43,19 @@ def n_genomes_for(gpus, base):
     return max(q, int(round(n / q)) * q)
 
 
+def ncu_traffic(kernel, n, world):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json);
+    only valid for the workload it was captured on (1 GPU, same N), else None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    if t.get("n_genomes") != n or kernel not in t:
+        return None
+    return t[kernel]["dram_bytes_read"] + t[kernel]["dram_bytes_write"]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -446,12 +459,14 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "passing_pairs": int(n_pass_t.item()), "ms": 1e3 * float(e2e_t.item()),
-                    "pipeline": f"upload in {gb.prefilter_stream_chunks()} slices on a copy stream, build + join wave "
-                                "per slice" if world == 1 else "per-rank slice upload, NVLink all-gathers",
+                    "pipeline": f"upload in {gb.prefilter_stream_chunks()} slices on a copy stream, block lists of a slice "
+                                "built as it lands, join after the last" if world == 1 else "per-rank slice upload, NVLink all-gathers",
                     "host_ms": e2e_host, "single_upload": e2e_single_upload},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": kernel_names[args.mode],
+                         "frac": achieved / peak, "traffic": ncu_traffic(kernel_names[args.mode], n, world),
+                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/ncu_traffic.json)",
+                         "kernel": kernel_names[args.mode],
                          "kernel_ms": main_ms, "build_kernels_ms": build_ms,
                          "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src,
                          "kernel_own_bytes_per_pair": own_bytes_per_pair,
