@@ -225,6 +225,8 @@ def main():
                                         np.arange(nb + 1, dtype=np.uint64) * np.uint64(lay["padded"]),
                                         np.full(nb, L, np.uint64), st)
             ani_build_ms += ani_index.last_timing()[0]
+            if b0 == 0:
+                ani_index.reserve(n_local)
     del d_seq, d_val, d_off
 
     table = torch.empty((n, S), dtype=torch.int64, device=dev) if world > 1 else my_table

@@ -90,6 +90,7 @@ _SIGNATURES = {
     "galah_b200_finch_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32,
                                                   ctypes.c_uint8, ctypes.c_int, pairpp, sizep]),
     "galah_b200_ani_index_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
+    "galah_b200_ani_index_reserve": (ctypes.c_int, [vp, ctypes.c_size_t]),
     "galah_b200_ani_index_free": (None, [vp]),
     "galah_b200_ani_index_add_files": (ctypes.c_int, [vp, strp, ctypes.c_size_t, ctypes.c_int]),
     "galah_b200_ani_index_add_packed": (ctypes.c_int, [vp, u32p, u32p, u64p, ctypes.c_size_t, u64p, u32p, u32p]),

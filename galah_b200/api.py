@@ -210,6 +210,10 @@ class AniIndex:
     def __len__(self):
         return int(lib().galah_b200_ani_index_size(self._h))
 
+    def reserve(self, n_total_genomes):
+        """Capacity hint after the first batch: the index will hold n_total_genomes like those added."""
+        check(lib().galah_b200_ani_index_reserve(self._h, int(n_total_genomes)))
+
     def add_files(self, paths, threads=0):
         check(lib().galah_b200_ani_index_add_files(self._h, _paths_array(paths), len(paths), threads))
 

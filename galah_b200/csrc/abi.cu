@@ -311,8 +311,15 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
                 }
             }
             if (sinks.ani) {
+                const size_t before = sinks.ani->size();
                 int rc = sinks.ani->add_packed_device(d_seq2.p, d_valid.p, d_off.p, nb, base_off, contig_off, cs, cl, st);
                 if (rc) return rc;
+                // first batch of a larger run: size the index once for everything still to come
+                // (units per file as seen so far; exact for whole-genome units)
+                if (before == 0 && done + want < n) {
+                    const double per_file = (double)sinks.n_units / (double)(done + want);
+                    if (int rc2 = sinks.ani->reserve_for((size_t)(per_file * (double)n) + 1, st)) return rc2;
+                }
             }
             GB_CUDA(cudaStreamSynchronize(st));
             b0 = b1;
@@ -634,6 +641,13 @@ void galah_b200_ani_index_free(galah_b200_ani_index_t *idx) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (idx && g_ctx.device >= 0) cudaSetDevice(g_ctx.device);
     delete idx;
+}
+
+int galah_b200_ani_index_reserve(galah_b200_ani_index_t *idx, size_t n_total_genomes) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: idx is NULL"); return GALAH_B200_ERR_ARG; }
+    return idx->impl.reserve_for(n_total_genomes, g_ctx.stream);
 }
 
 size_t galah_b200_ani_index_size(const galah_b200_ani_index_t *idx) { return idx ? idx->impl.size() : 0; }

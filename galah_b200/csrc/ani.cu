@@ -230,6 +230,8 @@ struct ChainParams {
     const unsigned long long *table;
     const uint64_t *seed_off, *cso_off, *table_off;
     const uint32_t *n_chunks;
+    const uint32_t *unit_prefix;  // [n_pairs + 1] running sum of the query genomes' chunk counts
+    uint32_t n_pairs, n_units;
     uint32_t *acc;  // 4 per pair: sumM, sumN, covq, covr
 };
 
@@ -238,10 +240,21 @@ constexpr int kRingFields = 5;  // q, r, f, rel<<31 | cnt<<16 | first_x, first_r
 
 __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainParams p) {
     extern __shared__ int ring[];  // [kAniH][kRingFields][kChainThreads]
-    const uint32_t pair = blockIdx.y, tid = threadIdx.x;
-    const uint32_t t = blockIdx.x * kChainThreads + tid;
+    const uint32_t tid = threadIdx.x;
+    // work units = (pair, query chunk), flattened over the batch so every thread has one
+    const uint32_t u = blockIdx.x * kChainThreads + tid;
+    if (u >= p.n_units) return;
+    uint32_t pair;
+    {
+        uint32_t lo = 0, hi = p.n_pairs;  // last pair with unit_prefix[pair] <= u
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.unit_prefix[mid] <= u) lo = mid; else hi = mid;
+        }
+        pair = lo;
+    }
+    const uint32_t t = u - p.unit_prefix[pair];
     const uint32_t q = p.pairs[2 * pair], r = p.pairs[2 * pair + 1];
-    if (t >= p.n_chunks[q]) return;
     const uint32_t *cso = p.cso + p.cso_off[q];
     const uint32_t x0 = cso[t], x1 = cso[t + 1];
     if (x1 - x0 < (uint32_t)kAniMinAnchors) return;
@@ -252,72 +265,107 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     uint32_t n_anchor = 0;
     int best_f = 0, best_first_r = 0, best_last_r = 0;
     uint32_t best_cnt = 0, best_first_x = 0, best_last_x = 0;
-    // The lanes of a warp are different chunks.  To keep them converged in the expensive part, the
-    // walk is a state machine: every lane first advances (cheap, divergent) to its next anchor --
-    // the next seed with 1..8 occurrences in the reference, then occurrence m of that seed in
-    // ascending reference position -- and then ALL lanes run one chaining step together.
-    uint32_t x = x0 - 1, occ = 0, m = 0, km = 0, qs = 0, home = 0;
-    int qpos = 0;
-    long long prev = -1;
-    bool alive = true;
-    for (;;) {
-        while (alive && m == occ) {
-            x++;
-            if (x >= x1) { alive = false; break; }
-            const uint32_t ks = qks[x];
-            km = ks >> 1; qs = ks & 1; qpos = (int)qsp[x];
-            home = table_slot(km, mask);
-            uint32_t c = 0;
-            for (uint32_t slot = home;; slot = (slot + 1) & mask) {
-                const unsigned long long e = table[slot];
-                if (e == kEmpty) break;
-                c += (uint32_t)(e >> 33) == km ? 1u : 0u;
-            }
-            occ = c > (uint32_t)kAniMaxOcc ? 0u : c;
-            m = 0; prev = -1;
+    int f_seen = 0;  // largest score of any anchor so far: bounds every score still in the ring
+    // The lanes of a warp are different chunks and walk their seeds in lock step: one seed per
+    // lane per iteration.  The probe of the reference table (the random read this kernel is bound
+    // by) then runs converged across the warp; only lanes whose seed occurs 1..8 times in the
+    // reference go on to the chaining step(s), which the f_seen bound keeps to one or two
+    // look-backs for colinear anchors.
+    // Two-deep software pipeline over the chunk's seeds: seed x+2's (k-mer, position) and seed
+    // x+1's home slot are requested while seed x is processed.
+    // The probe sequence is read four slots (one 32-byte sector) at a time: linear probing keeps a
+    // cluster contiguous, so one read usually holds the whole run up to its empty slot and the
+    // chain of dependent reads -- max over the warp's lanes -- is one or two long instead of
+    // the cluster length.
+    uint32_t ks1 = qks[x0], ks2 = x0 + 1 < x1 ? qks[x0 + 1] : 0u;
+    int qp1 = (int)qsp[x0], qp2 = x0 + 1 < x1 ? (int)qsp[x0 + 1] : 0;
+    ulonglong2 g1a, g1b;
+    {
+        const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + (table_slot(ks1 >> 1, mask) & ~3u));
+        g1a = gp[0]; g1b = gp[1];
+    }
+    for (uint32_t x = x0; x < x1; x++) {
+        const uint32_t ks = ks1;
+        unsigned long long v[4] = {g1a.x, g1a.y, g1b.x, g1b.y};
+        const int qpos = qp1;
+        ks1 = ks2; qp1 = qp2;
+        if (x + 1 < x1) {
+            const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + (table_slot(ks1 >> 1, mask) & ~3u));
+            g1a = gp[0]; g1b = gp[1];
         }
-        if (!alive) break;
-        // occurrence m: the smallest reference position above the previous one
-        unsigned long long pick = kEmpty;
-        for (uint32_t slot = home;; slot = (slot + 1) & mask) {
-            const unsigned long long e = table[slot];
-            if (e == kEmpty) break;
-            if ((uint32_t)(e >> 33) != km) continue;
-            const long long sp = (long long)(uint32_t)e;
-            if (sp > prev && (pick == kEmpty || sp < (long long)(uint32_t)pick)) pick = e;
-        }
-        prev = (long long)(uint32_t)pick;
-        m++;
-        const int rpos = (int)(uint32_t)pick;
-        const uint32_t rel = qs ^ (uint32_t)((pick >> 32) & 1);
-        int f = kAniAlpha, first_r = rpos;
-        uint32_t cnt = 1, first_x = x - x0;
-        const uint32_t look = min(n_anchor, (uint32_t)kAniH);
-        for (uint32_t b = 1; b <= look; b++) {
-            const uint32_t slot = (n_anchor - b) % kAniH;
-            const int dq = qpos - RING(slot, 0);
-            if (dq > kAniBand) break;
-            const uint32_t meta = (uint32_t)RING(slot, 3);
-            if (dq <= 0 || (meta >> 31) != rel) continue;
-            const int rb = RING(slot, 1);
-            const int dr = rel ? rb - rpos : rpos - rb;
-            if (dr <= 0 || dr > kAniBand) continue;
-            const int gap = abs(dq - dr);
-            if (gap > kAniMaxGap) continue;
-            const int cand = RING(slot, 2) + kAniAlpha - gap;
-            if (cand > f) {
-                f = cand; cnt = ((meta >> 16) & 0x7FFFu) + 1; first_x = meta & 0xFFFFu;
-                first_r = RING(slot, 4);
+        if (x + 2 < x1) { ks2 = qks[x + 2]; qp2 = (int)qsp[x + 2]; }
+        const uint32_t km = ks >> 1, qs = ks & 1;
+        const uint32_t home = table_slot(km, mask);
+        uint32_t c = 0;
+        unsigned long long only = kEmpty;  // the match of a seed that occurs exactly once (the common case)
+        {
+            uint32_t g = home & ~3u, o = home & 3u;
+            bool open = true;
+            for (;;) {
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++) {
+                    if (open && i >= o) {
+                        if (v[i] == kEmpty) open = false;
+                        else if ((uint32_t)(v[i] >> 33) == km) { only = v[i]; c++; }
+                    }
+                }
+                if (!open) break;
+                g = (g + 4) & mask; o = 0;
+                const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + g);
+                const ulonglong2 a = gp[0], b2 = gp[1];
+                v[0] = a.x; v[1] = a.y; v[2] = b2.x; v[3] = b2.y;
             }
         }
-        const uint32_t slot = n_anchor % kAniH;
-        RING(slot, 0) = qpos; RING(slot, 1) = rpos; RING(slot, 2) = f;
-        RING(slot, 3) = (int)((rel << 31) | (cnt << 16) | first_x);
-        RING(slot, 4) = first_r;
-        n_anchor++;
-        if (f > best_f) {
-            best_f = f; best_cnt = cnt; best_first_x = first_x; best_last_x = x - x0;
-            best_first_r = first_r; best_last_r = rpos;
+        const uint32_t occ = c > (uint32_t)kAniMaxOcc ? 0u : c;
+        long long prev = -1;
+        for (uint32_t m = 0; m < occ; m++) {
+            // occurrence m: the smallest reference position above the previous one
+            unsigned long long pick = only;
+            if (occ > 1) {
+                pick = kEmpty;
+                for (uint32_t slot = home;; slot = (slot + 1) & mask) {
+                    const unsigned long long e2 = table[slot];
+                    if (e2 == kEmpty) break;
+                    if ((uint32_t)(e2 >> 33) != km) continue;
+                    const long long sp = (long long)(uint32_t)e2;
+                    if (sp > prev && (pick == kEmpty || sp < (long long)(uint32_t)pick)) pick = e2;
+                }
+            }
+            prev = (long long)(uint32_t)pick;
+            const int rpos = (int)(uint32_t)pick;
+            const uint32_t rel = qs ^ (uint32_t)((pick >> 32) & 1);
+            int f = kAniAlpha, first_r = rpos;
+            uint32_t cnt = 1, first_x = x - x0;
+            const uint32_t look = min(n_anchor, (uint32_t)kAniH);
+            for (uint32_t b = 1; b <= look; b++) {
+                // a later predecessor can reach at most f_seen + alpha and must be strictly better
+                if (f >= f_seen + kAniAlpha) break;
+                const uint32_t slot = (n_anchor - b) % kAniH;
+                const int dq = qpos - RING(slot, 0);
+                if (dq > kAniBand) break;
+                const uint32_t meta = (uint32_t)RING(slot, 3);
+                if (dq <= 0 || (meta >> 31) != rel) continue;
+                const int rb = RING(slot, 1);
+                const int dr = rel ? rb - rpos : rpos - rb;
+                if (dr <= 0 || dr > kAniBand) continue;
+                const int gap = abs(dq - dr);
+                if (gap > kAniMaxGap) continue;
+                const int cand = RING(slot, 2) + kAniAlpha - gap;
+                if (cand > f) {
+                    f = cand; cnt = ((meta >> 16) & 0x7FFFu) + 1; first_x = meta & 0xFFFFu;
+                    first_r = RING(slot, 4);
+                }
+            }
+            const uint32_t slot = n_anchor % kAniH;
+            RING(slot, 0) = qpos; RING(slot, 1) = rpos; RING(slot, 2) = f;
+            RING(slot, 3) = (int)((rel << 31) | (cnt << 16) | first_x);
+            RING(slot, 4) = first_r;
+            n_anchor++;
+            f_seen = max(f_seen, f);
+            if (f > best_f) {
+                best_f = f; best_cnt = cnt; best_first_x = first_x; best_last_x = x - x0;
+                best_first_r = first_r; best_last_r = rpos;
+            }
         }
     }
 #undef RING
@@ -377,7 +425,7 @@ struct TmpBuf {
 };
 
 struct AniScratch {
-    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc;
+    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix;
     TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
 };
 
@@ -487,6 +535,23 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     return 0;
 }
 
+// Capacity hint: the index will hold n_total genomes like the ones already added.  Growing the
+// device arrays batch by batch re-allocates and copies gigabytes; one reservation after the
+// first batch avoids that.
+int AniIndex::reserve_for(size_t n_total, cudaStream_t st) {
+    const size_t have = size();
+    if (have == 0 || n_total <= have) return 0;
+    const double scale = 1.03 * (double)n_total / (double)have;
+    if (d_ks_.reserve((size_t)(seed_off_.back() * scale) + 1024, st) ||
+        d_spread_.reserve((size_t)(seed_off_.back() * scale) + 1024, st) ||
+        d_cso_.reserve((size_t)(cso_off_.back() * scale) + 1024, st) ||
+        d_table_.reserve((size_t)(table_off_.back() * scale) + 1024, st) ||
+        d_seed_off_.reserve(n_total + 2, st) || d_cso_off_.reserve(n_total + 2, st) ||
+        d_table_off_.reserve(n_total + 2, st) || d_n_chunks_.reserve(n_total + 1, st))
+        return 2;
+    return 0;
+}
+
 int AniIndex::genome_info(size_t g, uint64_t *n_seeds, uint32_t *n_chunks, uint64_t *total_len) const {
     if (g >= size()) { set_error("ani index: genome out of range"); return 3; }
     *n_seeds = seed_off_[g + 1] - seed_off_[g]; *n_chunks = n_chunks_[g]; *total_len = total_len_[g];
@@ -527,19 +592,35 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, Ani
     const size_t smem = (size_t)kAniH * kRingFields * kChainThreads * sizeof(int);
     GB_CUDA(cudaFuncSetAttribute(ani_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GB_CUDA(cudaEventRecord(ev_[0], st));
-    const size_t kBatch = 32768;
-    for (size_t b0 = 0; b0 < n_pairs; b0 += kBatch) {
-        const size_t nb = std::min(kBatch, n_pairs - b0);
-        uint32_t max_chunks = 0;
-        for (size_t x = b0; x < b0 + nb; x++) max_chunks = std::max(max_chunks, n_chunks_[oriented[2 * x]]);
-        if (max_chunks == 0) continue;
-        ChainParams p;
-        p.pairs = d_pairs.p + 2 * b0; p.ks = d_ks_.p; p.spread = d_spread_.p; p.cso = d_cso_.p;
-        p.table = d_table_.p; p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p; p.table_off = d_table_off_.p;
-        p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + 4 * b0;
-        dim3 grid((max_chunks + kChainThreads - 1) / kChainThreads, (uint32_t)nb);
-        ani_chain_kernel<<<grid, kChainThreads, smem, st>>>(p);
-        GB_LAUNCH_CHECK();
+    // work units of the whole call: (pair, query chunk), flattened so that every thread of the
+    // grid owns one chunk whatever the genomes' chunk counts are
+    std::vector<uint32_t> unit_prefix(n_pairs + 1, 0);
+    const size_t kMaxUnits = 1u << 30;
+    for (size_t b0 = 0; b0 < n_pairs;) {
+        size_t b1 = b0;
+        uint64_t units = 0;
+        unit_prefix[b0] = 0;
+        while (b1 < n_pairs && units + n_chunks_[oriented[2 * b1]] <= kMaxUnits) {
+            units += n_chunks_[oriented[2 * b1]];
+            unit_prefix[b1 + 1] = (uint32_t)units;
+            b1++;
+        }
+        if (b1 == b0) { set_error("ani pairs: a genome has more than 2^30 chunks"); return 3; }
+        if (units) {
+            TmpBuf<uint32_t> &d_prefix = scratch_->unit_prefix;
+            if (d_prefix.alloc(b1 - b0 + 1)) return 2;
+            // (the stream is idle between batches only when a call needs more than one, i.e. > 2^30 chunks)
+            if (b0) GB_CUDA(cudaStreamSynchronize(st));
+            GB_CUDA(cudaMemcpyAsync(d_prefix.p, unit_prefix.data() + b0, (b1 - b0 + 1) * 4, cudaMemcpyHostToDevice, st));
+            ChainParams p;
+            p.pairs = d_pairs.p + 2 * b0; p.ks = d_ks_.p; p.spread = d_spread_.p; p.cso = d_cso_.p;
+            p.table = d_table_.p; p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p; p.table_off = d_table_off_.p;
+            p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + 4 * b0;
+            p.unit_prefix = d_prefix.p; p.n_pairs = (uint32_t)(b1 - b0); p.n_units = (uint32_t)units;
+            ani_chain_kernel<<<(uint32_t)((units + kChainThreads - 1) / kChainThreads), kChainThreads, smem, st>>>(p);
+            GB_LAUNCH_CHECK();
+        }
+        b0 = b1;
     }
     GB_CUDA(cudaEventRecord(ev_[1], st));
     std::vector<uint32_t> acc(4 * n_pairs);

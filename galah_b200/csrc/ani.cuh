@@ -51,6 +51,7 @@ public:
                           size_t n, const std::vector<uint64_t> &base_off_host,
                           const std::vector<uint64_t> &contig_off, const std::vector<uint32_t> &contig_start,
                           const std::vector<uint32_t> &contig_len, cudaStream_t st);
+    int reserve_for(size_t n_total, cudaStream_t st);
     int pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, AniPairResult *out, cudaStream_t st);
     size_t size() const { return total_len_.size(); }
     uint32_t c() const { return c_; }

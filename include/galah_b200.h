@@ -200,6 +200,9 @@ int galah_b200_ani_index_add_packed_device(galah_b200_ani_index_t *idx, const ui
                                            const uint32_t *d_valid, const uint64_t *d_base_off,
                                            const uint64_t *base_off, const uint64_t *lengths,
                                            size_t n, void *stream);
+/* Capacity hint: the index will hold n_total_genomes genomes like the ones already added (call
+ * it after the first batch).  Avoids re-allocating the device arrays while the index grows. */
+int galah_b200_ani_index_reserve(galah_b200_ani_index_t *idx, size_t n_total_genomes);
 size_t galah_b200_ani_index_size(const galah_b200_ani_index_t *idx);
 int galah_b200_ani_index_genome(const galah_b200_ani_index_t *idx, size_t g, uint64_t *n_seeds,
                                 uint32_t *n_chunks, uint64_t *total_len);
