@@ -91,6 +91,8 @@ _SIGNATURES = {
                                                   ctypes.c_uint8, ctypes.c_int, pairpp, sizep]),
     "galah_b200_ani_index_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
     "galah_b200_ani_index_reserve": (ctypes.c_int, [vp, ctypes.c_size_t]),
+    "galah_b200_ani_finish": (ctypes.c_int, [ctypes.c_uint32] * 4 + [ctypes.c_uint64] * 2 + [ctypes.c_float, vp]),
+    "galah_b200_print2_parse_f32": (ctypes.c_float, [ctypes.c_double]),
     "galah_b200_ani_index_free": (None, [vp]),
     "galah_b200_ani_index_add_files": (ctypes.c_int, [vp, strp, ctypes.c_size_t, ctypes.c_int]),
     "galah_b200_ani_index_add_packed": (ctypes.c_int, [vp, u32p, u32p, u64p, ctypes.c_size_t, u64p, u32p, u32p]),
@@ -100,6 +102,8 @@ _SIGNATURES = {
     "galah_b200_ani_index_seeds": (ctypes.c_int, [vp, ctypes.c_size_t, u32p, u32p, u32p, ctypes.c_size_t]),
     "galah_b200_ani_pairs": (ctypes.c_int, [vp, u32p, ctypes.c_size_t, ctypes.c_float, ctypes.POINTER(AniResult)]),
     "galah_b200_ani_last_timing": (ctypes.c_int, [vp, f32p, f32p]),
+    "galah_b200_cluster_from_ani_table": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                                         ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]),
     "galah_b200_cluster_from_distances": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p,
                                                          ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                                          ANI_FN, vp, ctypes.POINTER(Clusters)]),

@@ -296,10 +296,26 @@ def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, s
     return clusters, info
 
 
+def cluster_from_ani_table(n_genomes, hits, ani, ani_threshold):
+    """The clustering engine with calculate_ani served from a table: ani[x] (percent) belongs to
+    hits[x]; hits sorted by (i, j) -- the batched form the Rust shim uses."""
+    hits = np.ascontiguousarray(hits, PAIR_DTYPE)
+    ani = np.ascontiguousarray(ani, np.float32)
+    if len(ani) != len(hits):
+        raise ValueError("one ANI value per hit")
+    res = _native.Clusters()
+    check(lib().galah_b200_cluster_from_ani_table(int(n_genomes), hits.ctypes.data, len(hits), ani.ctypes.data,
+                                                  ctypes.c_float(ani_threshold), ctypes.byref(res)))
+    return _take_clusters(res)
+
+
 def _take_clusters(res):
     try:
-        off = [res.offsets[x] for x in range(res.n_clusters + 1)]
-        clusters = [[int(res.members[y]) for y in range(off[x], off[x + 1])] for x in range(res.n_clusters)]
+        nc = int(res.n_clusters)
+        off = np.ctypeslib.as_array(res.offsets, shape=(nc + 1,)).astype(np.int64) if nc else np.zeros(1, np.int64)
+        mem = np.ctypeslib.as_array(res.members, shape=(int(off[-1]),)).copy() if nc and off[-1] else np.zeros(0, np.uint32)
+        m, o = mem.tolist(), off.tolist()
+        clusters = [m[o[x]:o[x + 1]] for x in range(nc)]
         info = {"ani_calls": int(res.ani_calls), "n_preclusters": int(res.n_preclusters),
                 "largest_precluster": int(res.largest_precluster)}
     finally:

@@ -643,6 +643,16 @@ void galah_b200_ani_index_free(galah_b200_ani_index_t *idx) {
     delete idx;
 }
 
+int galah_b200_ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
+                          uint64_t len_r, float min_af_pct, galah_b200_ani_result_t *out) {
+    if (!out) { set_error("ani_finish: out is NULL"); return GALAH_B200_ERR_ARG; }
+    const AniPairResult r = ani_finish(sum_m, sum_n, cov_q, cov_r, len_q, len_r, min_af_pct, false);
+    memcpy(out, &r, sizeof(r));
+    return 0;
+}
+
+float galah_b200_print2_parse_f32(double v) { return print2_parse_f32(v); }
+
 int galah_b200_ani_index_reserve(galah_b200_ani_index_t *idx, size_t n_total_genomes) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (int rc = require_ctx()) return rc;
@@ -769,6 +779,35 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
     return 0;
 }
 
+// ANI of hit pairs served from a table (hits sorted by (i, j), ani[x] belongs to hits[x]).
+namespace {
+struct AniTable { const galah_b200_pair_t *hits; size_t n; const float *ani; size_t stride; };
+int ani_table_lookup(void *ctx, uint32_t rep, uint32_t genome, float *ani) {
+    const AniTable *t = (const AniTable *)ctx;
+    const uint32_t a = std::min(rep, genome), b = std::max(rep, genome);
+    size_t lo = 0, hi = t->n;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (t->hits[mid].i < a || (t->hits[mid].i == a && t->hits[mid].j < b)) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= t->n || t->hits[lo].i != a || t->hits[lo].j != b) return 0;
+    *ani = *(const float *)((const char *)t->ani + lo * t->stride);  // skani never yields None (src/skani.rs:760)
+    return 1;
+}
+}  // namespace
+
+int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                      const float *ani, float ani_threshold, galah_b200_clusters_t *out) {
+    if (n_hits && (!hits || !ani)) { set_error("cluster_from_ani_table: NULL hits / ani"); return GALAH_B200_ERR_ARG; }
+    for (size_t x = 1; x < n_hits; x++)
+        if (hits[x - 1].i > hits[x].i || (hits[x - 1].i == hits[x].i && hits[x - 1].j >= hits[x].j)) {
+            set_error("cluster_from_ani_table: hits must be sorted by (i, j) without duplicates");
+            return GALAH_B200_ERR_ARG;
+        }
+    AniTable table{hits, n_hits, ani, sizeof(float)};
+    return galah_b200_cluster_from_distances(n_genomes, hits, n_hits, 0, ani_threshold, ani_table_lookup, &table, out);
+}
+
 int galah_b200_cluster_files(const char *const *paths, size_t n, float precluster_min_ani, float ani_threshold_pct,
                              float min_af_pct, int small_genomes, int host_threads,
                              galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
@@ -802,20 +841,8 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
     for (size_t x = 0; x < n_hits; x++) { pairs[2 * x] = hits[x].i; pairs[2 * x + 1] = hits[x].j; }
     std::vector<galah_b200_ani_result_t> res(n_hits);
     if (int rc = galah_b200_ani_pairs(idx, pairs.data(), n_hits, min_af_pct, res.data())) return rc;
-    struct Table { const galah_b200_pair_t *hits; size_t n; const galah_b200_ani_result_t *res; } table{hits, n_hits, res.data()};
-    auto lookup = [](void *ctx, uint32_t rep, uint32_t genome, float *ani) -> int {
-        const Table *t = (const Table *)ctx;
-        const uint32_t a = std::min(rep, genome), b = std::max(rep, genome);
-        size_t lo = 0, hi = t->n;  // hits are sorted by (i, j)
-        while (lo < hi) {
-            const size_t mid = (lo + hi) >> 1;
-            if (t->hits[mid].i < a || (t->hits[mid].i == a && t->hits[mid].j < b)) lo = mid + 1; else hi = mid;
-        }
-        if (lo >= t->n || t->hits[lo].i != a || t->hits[lo].j != b) return 0;
-        *ani = t->res[lo].ani;  // skani never yields None (src/skani.rs:760: 0.0 when no row)
-        return 1;
-    };
-    int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, lookup, &table, out);
+    AniTable table{hits, n_hits, n_hits ? &res[0].ani : nullptr, sizeof(galah_b200_ani_result_t)};
+    int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
     if (stats) {
         stats->n_precluster_hits = n_hits;
         stats->n_ani_pairs = n_hits;

@@ -382,6 +382,32 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
+// strtof(sprintf("%.2f", v)) without the text: v = M * 2^-k exactly (M < 2^53), so 100 v is the
+// integer P = 100 M over 2^k and the two-decimal rounding printf does (nearest, ties to even, on
+// the exact binary value) is integer arithmetic on P.  The printed number is then n / 100 with
+// n an integer; (float)((double)n / 100.0) is the float nearest to it (the double quotient is
+// within 2^-53 relative of n / 100, which is either a float itself or > 2^-27 relative away from
+// every float midpoint, so rounding twice cannot differ from rounding once).  Values outside
+// the range the ANI formula can produce take the text route.
+float print2_parse_f32(double v) {
+    if (v > 0.0 && v < 1.0e6) {
+        int exp2 = 0;
+        const double m = frexp(v, &exp2);  // v = m * 2^exp2, m in [0.5, 1)
+        const uint64_t M = (uint64_t)ldexp(m, 53);
+        const int k = 53 - exp2;  // v = M * 2^-k
+        if (k >= 1 && k <= 62) {
+            const unsigned __int128 P = (unsigned __int128)M * 100u;
+            uint64_t n = (uint64_t)(P >> k);
+            const unsigned __int128 r = P & (((unsigned __int128)1 << k) - 1), half = (unsigned __int128)1 << (k - 1);
+            if (r > half || (r == half && (n & 1))) n++;
+            return (float)((double)n / 100.0);
+        }
+    }
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.2f", v);
+    return strtof(buf, nullptr);
+}
+
 AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
                          uint64_t len_r, float min_af_pct, bool swapped) {
     AniPairResult res;
@@ -393,9 +419,7 @@ AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_
     if (sum_n == 0 || sum_m == 0) return res;
     const double ani = 100.0 * pow((double)sum_m / (double)sum_n, 1.0 / kAniK);
     if (std::max(afq, afr) * 100.0 < (double)min_af_pct) return res;  // skani prints no row
-    char buf[64];
-    snprintf(buf, sizeof(buf), "%.2f", ani);  // skani prints {:.2}; galah parses the text as f32
-    res.ani = strtof(buf, nullptr);
+    res.ani = print2_parse_f32(ani);  // skani prints {:.2}; galah parses the text as f32
     return res;
 }
 

@@ -75,6 +75,8 @@ private:
     AniScratch *scratch_ = nullptr;
 };
 
+// strtof(sprintf("%.2f", v)), computed exactly without the text for the values an ANI can take
+float print2_parse_f32(double v);
 // integers -> the f32 galah would parse (host; mirrors oracle/skani_oracle.c skani_oracle_finish)
 AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
                          uint64_t len_r, float min_af_pct, bool swapped);

@@ -29,7 +29,6 @@
 
 #include <algorithm>
 #include <numeric>
-#include <unordered_map>
 
 namespace gb200 {
 
@@ -90,9 +89,18 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     Adjacency adj;
     adj.off.assign(n + 1, 0);
     {
-        std::unordered_map<uint64_t, float> uniq;
-        uniq.reserve(n_hits * 2);
-        for (size_t h = 0; h < n_hits; h++) uniq[pair_key(hits[h].i, hits[h].j)] = hits[h].ani;
+        // unique keys, last write wins: stable sort by key, keep the last record of every run
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
+        for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
+        bool sorted = true;
+        for (size_t h = 1; h < n_hits && sorted; h++) sorted = keyed[h - 1].first < keyed[h].first;
+        if (!sorted)
+            std::stable_sort(keyed.begin(), keyed.end(),
+                             [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &b) { return a.first < b.first; });
+        std::vector<std::pair<uint64_t, float>> uniq;
+        uniq.reserve(n_hits);
+        for (size_t h = 0; h < n_hits; h++)
+            if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.emplace_back(keyed[h].first, hits[keyed[h].second].ani);
         for (const auto &kv : uniq) {
             adj.off[(uint32_t)(kv.first >> 32) + 1]++;
             adj.off[(uint32_t)kv.first + 1]++;
@@ -109,7 +117,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         for (size_t g = 0; g < n; g++) {
             tmp.clear();
             for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++) tmp.emplace_back(adj.nbr[x], adj.ani[x]);
-            std::sort(tmp.begin(), tmp.end());
+            if (!std::is_sorted(tmp.begin(), tmp.end())) std::sort(tmp.begin(), tmp.end());
             for (size_t x = 0; x < tmp.size(); x++) { adj.nbr[adj.off[g] + x] = tmp[x].first; adj.ani[adj.off[g] + x] = tmp[x].second; }
         }
     }
@@ -119,45 +127,62 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     for (size_t g = 0; g < n; g++)
         for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++)
             if (adj.nbr[x] < g) dsu.join((uint32_t)g, adj.nbr[x]);
-    std::vector<std::vector<uint32_t>> preclusters;
+    // preclusters as one flat array (CSR): sets in order of their smallest member (the root),
+    // members ascending, then ordered by size, largest first (stable)
+    std::vector<uint32_t> pc_members(n);
+    std::vector<uint64_t> pc_off;
     {
+        std::vector<uint32_t> set_id(n), set_size, root_of(n);
         std::vector<int64_t> set_of_root(n, -1);
-        for (uint32_t g = 0; g < n; g++) {  // root == smallest member, so sets appear in that order
+        for (uint32_t g = 0; g < n; g++) {
             const uint32_t r = dsu.find(g);
-            if (set_of_root[r] < 0) { set_of_root[r] = (int64_t)preclusters.size(); preclusters.emplace_back(); }
-            preclusters[set_of_root[r]].push_back(g);
+            if (set_of_root[r] < 0) { set_of_root[r] = (int64_t)set_size.size(); set_size.push_back(0); }
+            set_id[g] = (uint32_t)set_of_root[r];
+            set_size[set_id[g]]++;
         }
+        std::vector<uint32_t> order(set_size.size());
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return set_size[a] > set_size[b]; });
+        std::vector<uint64_t> start(set_size.size());
+        pc_off.assign(1, 0);
+        for (const uint32_t sid : order) { start[sid] = pc_off.back(); pc_off.push_back(pc_off.back() + set_size[sid]); }
+        for (uint32_t g = 0; g < n; g++) pc_members[start[set_id[g]]++] = g;
+        out.n_preclusters = (uint32_t)set_size.size();
+        out.largest_precluster = set_size[order[0]];
     }
-    std::stable_sort(preclusters.begin(), preclusters.end(),
-                     [](const std::vector<uint32_t> &a, const std::vector<uint32_t> &b) { return a.size() > b.size(); });
-    out.n_preclusters = (uint32_t)preclusters.size();
-    out.largest_precluster = (uint32_t)preclusters[0].size();
 
     std::vector<uint8_t> is_rep(n, 0);
     std::vector<uint32_t> cluster_of_rep(n, 0);
-    std::unordered_map<uint64_t, OptAni> cache;  // clusterer cache of the current precluster
-    std::vector<std::pair<float, uint32_t>> cands;
+    // clusterer cache (src/clusterer.rs:236-239, 398-405), one slot per adjacency edge: a pair is
+    // only ever looked up from the row of the genome being placed, so the edge index is its key
+    std::vector<uint8_t> edge_state(adj.nbr.size(), 0);  // 0 = not computed, 1 = Some(ani), 2 = None
+    std::vector<float> edge_ani(adj.nbr.size(), 0.f);
+    struct Cand { float pre; uint32_t j; uint64_t edge; };
+    std::vector<Cand> cands;
 
-    for (const auto &members : preclusters) {
-        cache.clear();
-        std::vector<uint32_t> reps;
+    std::vector<uint32_t> reps, assigned_rep;  // per precluster: representatives; (genome -> its cluster) of non-reps
+    std::vector<std::pair<uint32_t, uint32_t>> joins;  // (cluster index within the precluster, genome), genome ascending
+    std::vector<uint64_t> cl_fill;
+    for (size_t pc = 0; pc + 1 < pc_off.size(); pc++) {
+        const uint32_t *mb = pc_members.data() + pc_off[pc], *me = pc_members.data() + pc_off[pc + 1];
+        reps.clear(); joins.clear();
         // ---- representatives
-        for (const uint32_t i : members) {
+        for (const uint32_t *ip = mb; ip != me; ip++) {
+            const uint32_t i = *ip;
             cands.clear();
             for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++) {
                 const uint32_t j = adj.nbr[x];
-                if (is_rep[j]) cands.emplace_back(adj.ani[x], j);  // reps found so far all have j < i
+                if (is_rep[j]) cands.push_back(Cand{adj.ani[x], j, x});  // reps found so far all have j < i
             }
-            std::stable_sort(cands.begin(), cands.end(),
-                             [](const std::pair<float, uint32_t> &a, const std::pair<float, uint32_t> &b) { return a.first < b.first; });
+            std::stable_sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.pre < b.pre; });
             bool rep = true;
             for (const auto &c : cands) {
-                float ani = c.first;
+                float ani = c.pre;
                 bool some = true;
                 if (!skip_clusterer) {
-                    some = calculate_ani(c.second, i, &ani);
+                    some = calculate_ani(c.j, i, &ani);
                     out.ani_calls++;
-                    if (some) cache[pair_key(c.second, i)] = OptAni{true, ani};
+                    if (some) { edge_state[c.edge] = 1; edge_ani[c.edge] = ani; }
                 }
                 if (some && ani >= ani_threshold) {
                     rep = false;
@@ -167,10 +192,9 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
             if (rep) { is_rep[i] = 1; reps.push_back(i); }
         }
         // ---- memberships
-        const size_t first_cluster = out.offsets.size() - 1;
-        std::vector<std::vector<uint32_t>> clusters(reps.size());
-        for (size_t c = 0; c < reps.size(); c++) { clusters[c].push_back(reps[c]); cluster_of_rep[reps[c]] = (uint32_t)c; }
-        for (const uint32_t i : members) {
+        for (size_t c = 0; c < reps.size(); c++) cluster_of_rep[reps[c]] = (uint32_t)c;
+        for (const uint32_t *ip = mb; ip != me; ip++) {
+            const uint32_t i = *ip;
             if (is_rep[i]) continue;
             bool have_best = false;
             float best = 0.f;
@@ -182,14 +206,13 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                 if (skip_clusterer) {
                     v = OptAni{true, adj.ani[x]};
                 } else {
-                    auto it = cache.find(pair_key(i, r));
-                    if (it != cache.end()) v = it->second;
+                    if (edge_state[x]) v = OptAni{edge_state[x] == 1, edge_ani[x]};
                     else {
                         float ani = 0.f;
                         const bool some = calculate_ani(r, i, &ani);
                         out.ani_calls++;
                         v = OptAni{some, ani};
-                        cache[pair_key(i, r)] = v;
+                        edge_state[x] = some ? 1 : 2; edge_ani[x] = ani;
                     }
                 }
                 if (v.some && (!have_best || v.ani > best)) { have_best = true; best = v.ani; best_rep = r; }
@@ -199,14 +222,22 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                       " has no representative with an ANI; src/clusterer.rs:444)";
                 return 1;
             }
-            clusters[cluster_of_rep[best_rep]].push_back(i);
+            joins.emplace_back(cluster_of_rep[best_rep], i);
         }
-        for (auto &c : clusters) {
-            out.members.insert(out.members.end(), c.begin(), c.end());
-            out.offsets.push_back(out.members.size());
+        // clusters of this precluster in representative order: representative first, then its
+        // members in ascending genome order (the order they were assigned in)
+        cl_fill.assign(reps.size() + 1, 0);
+        for (const auto &jn : joins) cl_fill[jn.first + 1]++;
+        const uint64_t base = out.members.size();
+        for (size_t c = 0; c < reps.size(); c++) cl_fill[c + 1] += cl_fill[c] + 1;  // +1: the representative
+        out.members.resize(base + cl_fill[reps.size()]);
+        for (size_t c = 0; c < reps.size(); c++) {
+            const uint64_t at = base + (c ? cl_fill[c] : 0);
+            out.members[at] = reps[c];
+            out.offsets.push_back(base + cl_fill[c + 1]);
         }
-        (void)first_cluster;
-        for (const uint32_t r : reps) is_rep[r] = 1;  // stays set; other preclusters never touch it
+        for (size_t c = reps.size(); c-- > 0;) cl_fill[c + 1] = c ? cl_fill[c] + 1 : 1;  // next free slot after each representative
+        for (const auto &jn : joins) out.members[base + cl_fill[jn.first + 1]++] = jn.second;
     }
     return 0;
 }

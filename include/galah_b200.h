@@ -200,6 +200,14 @@ int galah_b200_ani_index_add_packed_device(galah_b200_ani_index_t *idx, const ui
                                            const uint32_t *d_valid, const uint64_t *d_base_off,
                                            const uint64_t *base_off, const uint64_t *lengths,
                                            size_t n, void *stream);
+/* Host finish of stage 2 (no device needed): the kernel's integer accumulators of one pair ->
+ * what galah parses from skani's TSV (src/skani.rs:773-779): ANI = 100 (sum_m / sum_n)^(1/15),
+ * printed with two decimals and parsed as f32; 0.0 when max(AF) * 100 < min_af_pct (no row,
+ * src/skani.rs:760).  galah_b200_print2_parse_f32(v) == strtof(sprintf("%.2f", v)). */
+int galah_b200_ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
+                          uint64_t len_r, float min_af_pct, galah_b200_ani_result_t *out);
+float galah_b200_print2_parse_f32(double v);
+
 /* Capacity hint: the index will hold n_total_genomes genomes like the ones already added (call
  * it after the first batch).  Avoids re-allocating the device arrays while the index grows. */
 int galah_b200_ani_index_reserve(galah_b200_ani_index_t *idx, size_t n_total_genomes);
@@ -242,6 +250,11 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
                                       size_t n_hits, int skip_clusterer, float ani_threshold,
                                       galah_b200_ani_fn calculate_ani, void *ctx,
                                       galah_b200_clusters_t *out);
+/* Same engine with calculate_ani served from a table: ani[x] is the clusterer's ANI (percent)
+ * of hits[x]; hits sorted by (i, j).  This is how the Rust shim serves calculate_ani after one
+ * batched galah_b200_ani_pairs call over every precluster hit. */
+int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                      const float *ani, float ani_threshold, galah_b200_clusters_t *out);
 void galah_b200_clusters_free(galah_b200_clusters_t *c);
 
 /* The whole hot path: galah::clusterer::cluster(genomes, &FinchPreclusterer{min_ani:

@@ -122,3 +122,31 @@ def test_large_sparse_is_linear_in_hits():
     assert len(clusters) == n // 10 and all(len(c) == 10 for c in clusters)
     assert info["n_preclusters"] == n // 10 and info["largest_precluster"] == 10
     assert dt < 20.0
+
+
+def test_ani_table_entry_matches_callback_entry():
+    """galah_b200_cluster_from_ani_table == the callback engine fed from the same table == the
+    Python restatement, on random family-structured hit lists; unsorted hits are rejected."""
+    rng = np.random.default_rng(17)
+    n = 400
+    pairs = []
+    for base in range(0, n, 8):
+        fam = list(range(base, min(n, base + 8)))
+        for a in fam:
+            for b in fam:
+                if a < b and rng.uniform() < 0.7:
+                    pairs.append((a, b, float(np.float32(rng.uniform(0.9, 1.0)))))
+    pairs.sort()
+    hits = make_hits(pairs)
+    ani = np.round(rng.uniform(90.0, 100.0, len(hits)), 2).astype(np.float32)
+    table = {(int(h["i"]), int(h["j"])): float(a) for h, a in zip(hits, ani)}
+    f = lambda rep, g: table[(min(rep, g), max(rep, g))]
+    got, ginfo = gb.cluster_from_ani_table(n, hits, ani, 95.0)
+    via_cb, cinfo = gb.cluster_from_distances(n, hits, 95.0, f)
+    exp, einfo = co.cluster(n, [(h["i"], h["j"], h["ani"]) for h in hits], 95.0, f)
+    assert got == via_cb == exp
+    assert ginfo["ani_calls"] == cinfo["ani_calls"] == einfo["ani_calls"]
+    with pytest.raises(gb.GalahB200Error):
+        gb.cluster_from_ani_table(n, hits[::-1].copy(), ani, 95.0)
+    empty, _ = gb.cluster_from_ani_table(3, hits[:0], ani[:0], 95.0)
+    assert empty == [[0], [1], [2]]
