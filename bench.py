@@ -169,6 +169,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: everything else a library prints there (the NCCL
+    # version banner, for one) is sent to stderr at the file-descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import galah_b200 as gb
@@ -488,7 +494,8 @@ def main():
                        "gbases_per_s": n_local * L / (sketch_ms * 1e-3) / 1e9 if sketch_ms else None,
                        "ms": sketch_ms, "synth_ms": synth_ms, "genomes_per_rank": n_local},
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
