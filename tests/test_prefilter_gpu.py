@@ -274,3 +274,58 @@ def test_streamed_upload_candidate_overflow_retries(gb, kernel_mode):
     assert np.all(got["common"] == s) and np.all(got["total"] == s) and np.all(got["ani"] == 1.0)
     key = got["i"].astype(np.int64) * n + got["j"]
     assert np.all(np.diff(key) > 0)
+
+
+def test_full_size_config_properties(gb, kernel_mode):
+    """BASELINE.json configs[1] at full size (10,000 synthetic 2 Mbp genomes sketched on the
+    device, 49,995,000 pairs): size-independent properties.  The two exact kernel paths agree on
+    the whole candidate set; the pair list is strictly (i, j)-ordered; shards partition it; every
+    pair is within a family of 10 (cross-family genomes share ~0 hashes); a row sample is
+    bit-exact against the oracle."""
+    if kernel_mode != 0:
+        pytest.skip("runs both paths itself")
+    import torch
+    n, L, s = 10_000, 2_000_000, 1000
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    d_h = torch.empty((n, s), dtype=torch.int64, device=dev)
+    d_c = torch.empty(n, dtype=torch.int32, device=dev)
+    batch = 500
+    lay = gb.synth_layout(batch, L)
+    d_seq = torch.zeros(lay["seq2_words"], dtype=torch.int32, device=dev)
+    d_val = torch.zeros(lay["valid_words"], dtype=torch.int32, device=dev)
+    d_off = torch.zeros(batch + 1, dtype=torch.int64, device=dev)
+    for b0 in range(0, n, batch):
+        gb.synth_packed_device(1, b0, batch, L, d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), st)
+        gb.sketch_packed_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), batch, 21, s, 0,
+                                d_h[b0:].data_ptr(), d_c[b0:].data_ptr(), st)
+    torch.cuda.synchronize()
+    del d_seq, d_val
+    cap = 1 << 20
+    cands = []
+    for mode in (0, 1):
+        d_cand = torch.zeros((cap, 4), dtype=torch.int32, device=dev)
+        d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+        gb.prefilter_enqueue(d_h.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, 0, 1, mode, st, d_cand.data_ptr(), cap,
+                             d_n.data_ptr())
+        torch.cuda.synchronize()
+        c = d_cand[: int(d_n.item())].cpu().numpy().view(np.uint32)
+        cands.append(c[np.lexsort((c[:, 1], c[:, 0]))])
+    assert cands[0].shape == cands[1].shape and np.array_equal(cands[0], cands[1])
+    full = gb.prefilter_device(d_h.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, 0, 1, st)
+    assert 20_000 < len(full) <= len(cands[0])
+    key = full["i"].astype(np.int64) * n + full["j"]
+    assert np.all(np.diff(key) > 0) and np.all(full["i"] < full["j"])
+    assert np.all(full["i"] // 10 == full["j"] // 10), "a pair across synthetic families passed"
+    assert np.all(full["common"] <= full["total"]) and np.all(full["total"] <= 2 * s) and np.all(full["total"] >= s)
+    parts = [gb.prefilter_device(d_h.data_ptr(), d_c.data_ptr(), n, s, 21, 0.9, r, 3, st) for r in range(3)]
+    merged = np.concatenate(parts)
+    merged = merged[np.lexsort((merged["j"], merged["i"]))]
+    assert_pairs_equal(merged, full)
+    table = d_h.cpu().numpy().view(np.uint64)
+    counts = d_c.cpu().numpy().view(np.uint32)
+    # host-buffer call (pipelined upload) == device-resident call
+    assert_pairs_equal(gb.prefilter(table, counts, 21, 0.9), full)
+    for r0 in (0, 4990, 9980):
+        exp = oracle.prefilter(table, counts, 21, 0.9, row_begin=r0, row_end=r0 + 10)
+        assert_pairs_equal(full[(full["i"] >= r0) & (full["i"] < r0 + 10)], exp)
