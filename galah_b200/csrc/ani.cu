@@ -144,8 +144,11 @@ struct EmitParams {
     unsigned long long *table;
 };
 
+// Home slot of a k-mer: the start of a bucket of four slots (one aligned 32-byte sector).  Keys
+// probe linearly from there, so a reader sees a whole bucket per memory transaction, and at a
+// load factor <= 1/4 (about one key per bucket) a run almost never leaves its first sector.
 __device__ __forceinline__ uint32_t table_slot(uint32_t km, uint32_t mask) {
-    return (uint32_t)(((uint64_t)km * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+    return (uint32_t)(((uint64_t)km * 0x9E3779B97F4A7C15ull) >> 32) & mask & ~3u;
 }
 
 __global__ void __launch_bounds__(256) ani_emit_kernel(const EmitParams p) {
@@ -243,24 +246,27 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     const uint32_t tid = threadIdx.x;
     // work units = (pair, query chunk), flattened over the batch so every thread has one
     const uint32_t u = blockIdx.x * kChainThreads + tid;
-    if (u >= p.n_units) return;
-    uint32_t pair;
-    {
+    // no early exits: every lane of a warp stays in the lock-step walk (idle lanes walk 0 seeds)
+    uint32_t pair = 0, x0 = 0, x1 = 0;
+    const uint32_t *qks = p.ks, *qsp = p.spread;
+    const unsigned long long *table = p.table;
+    uint32_t mask = 0;
+    if (u < p.n_units) {
         uint32_t lo = 0, hi = p.n_pairs;  // last pair with unit_prefix[pair] <= u
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
             if (p.unit_prefix[mid] <= u) lo = mid; else hi = mid;
         }
         pair = lo;
+        const uint32_t t = u - p.unit_prefix[pair];
+        const uint32_t q = p.pairs[2 * pair], r = p.pairs[2 * pair + 1];
+        const uint32_t *cso = p.cso + p.cso_off[q];
+        x0 = cso[t]; x1 = cso[t + 1];
+        if (x1 - x0 < (uint32_t)kAniMinAnchors) x1 = x0;
+        qks = p.ks + p.seed_off[q]; qsp = p.spread + p.seed_off[q];
+        table = p.table + p.table_off[r];
+        mask = (uint32_t)(p.table_off[r + 1] - p.table_off[r]) - 1;
     }
-    const uint32_t t = u - p.unit_prefix[pair];
-    const uint32_t q = p.pairs[2 * pair], r = p.pairs[2 * pair + 1];
-    const uint32_t *cso = p.cso + p.cso_off[q];
-    const uint32_t x0 = cso[t], x1 = cso[t + 1];
-    if (x1 - x0 < (uint32_t)kAniMinAnchors) return;
-    const uint32_t *qks = p.ks + p.seed_off[q], *qsp = p.spread + p.seed_off[q];
-    const unsigned long long *table = p.table + p.table_off[r];
-    const uint32_t mask = (uint32_t)(p.table_off[r + 1] - p.table_off[r]) - 1;
 #define RING(slot, field) ring[((slot) * kRingFields + (field)) * kChainThreads + tid]
     uint32_t n_anchor = 0;
     int best_f = 0, best_first_r = 0, best_last_r = 0;
@@ -277,20 +283,27 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     // cluster contiguous, so one read usually holds the whole run up to its empty slot and the
     // chain of dependent reads -- max over the warp's lanes -- is one or two long instead of
     // the cluster length.
-    uint32_t ks1 = qks[x0], ks2 = x0 + 1 < x1 ? qks[x0 + 1] : 0u;
-    int qp1 = (int)qsp[x0], qp2 = x0 + 1 < x1 ? (int)qsp[x0 + 1] : 0;
-    ulonglong2 g1a, g1b;
-    {
-        const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + (table_slot(ks1 >> 1, mask) & ~3u));
+    uint32_t ks1 = x0 < x1 ? qks[x0] : 0u, ks2 = x0 + 1 < x1 ? qks[x0 + 1] : 0u;
+    int qp1 = x0 < x1 ? (int)qsp[x0] : 0, qp2 = x0 + 1 < x1 ? (int)qsp[x0 + 1] : 0;
+    ulonglong2 g1a = make_ulonglong2(kEmpty, kEmpty), g1b = g1a;
+    if (x0 < x1) {
+        const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + table_slot(ks1 >> 1, mask));
         g1a = gp[0]; g1b = gp[1];
     }
-    for (uint32_t x = x0; x < x1; x++) {
+    // The trip count is the warp's longest chunk and every iteration starts with a warp barrier, so
+    // the lanes re-join after the divergent chaining step whatever the compiler's own
+    // reconvergence points are.
+    const uint32_t len = x1 - x0, max_len = __reduce_max_sync(0xffffffffu, len);
+    for (uint32_t it = 0; it < max_len; it++) {
+        __syncwarp();
+        if (it >= len) continue;
+        const uint32_t x = x0 + it;
         const uint32_t ks = ks1;
         unsigned long long v[4] = {g1a.x, g1a.y, g1b.x, g1b.y};
         const int qpos = qp1;
         ks1 = ks2; qp1 = qp2;
         if (x + 1 < x1) {
-            const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + (table_slot(ks1 >> 1, mask) & ~3u));
+            const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + table_slot(ks1 >> 1, mask));
             g1a = gp[0]; g1b = gp[1];
         }
         if (x + 2 < x1) { ks2 = qks[x + 2]; qp2 = (int)qsp[x + 2]; }
@@ -299,18 +312,18 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
         uint32_t c = 0;
         unsigned long long only = kEmpty;  // the match of a seed that occurs exactly once (the common case)
         {
-            uint32_t g = home & ~3u, o = home & 3u;
+            uint32_t g = home;
             bool open = true;
             for (;;) {
 #pragma unroll
                 for (uint32_t i = 0; i < 4; i++) {
-                    if (open && i >= o) {
+                    if (open) {
                         if (v[i] == kEmpty) open = false;
                         else if ((uint32_t)(v[i] >> 33) == km) { only = v[i]; c++; }
                     }
                 }
                 if (!open) break;
-                g = (g + 4) & mask; o = 0;
+                g = (g + 4) & mask;
                 const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + g);
                 const ulonglong2 a = gp[0], b2 = gp[1];
                 v[0] = a.x; v[1] = a.y; v[2] = b2.x; v[3] = b2.y;
@@ -516,7 +529,7 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
         seed_off[g + 1] = seed_off[g] + count[g];
         cso_off[g + 1] = cso_off[g] + n_chunks[g] + 1;
         uint64_t slots = 16;
-        while (slots < 2ull * count[g]) slots <<= 1;
+        while (slots < 4ull * count[g]) slots <<= 1;
         table_off[g + 1] = table_off[g] + slots;
     }
     if (d_ks_.reserve(seed_off[n] + 1, st) || d_spread_.reserve(seed_off[n] + 1, st) ||
