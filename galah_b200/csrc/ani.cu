@@ -140,9 +140,17 @@ struct EmitParams {
     const uint64_t *cso_off;       // batch-local [n + 1], absolute offsets into cso
     const uint32_t *n_chunks;      // batch-local [n]
     const uint64_t *table_off;     // batch-local [n + 1], absolute offsets into table
-    uint32_t *ks, *spread, *cso, *chunk_tmp;
+    uint2 *kq;  // per seed: x = kmer << 1 | strand, y = spread position (one 8-byte read per seed)
+    uint32_t *cso, *chunk_tmp;
     unsigned long long *table;
 };
+
+// One bucket (four 8-byte slots, 32-byte aligned) in ONE 256-bit load (SASS LDG.E.256, sm_100):
+// per lane a gather costs the LSU one transaction per instruction, so two 128-bit loads of the
+// same sector would cost two.
+__device__ __forceinline__ void load_bucket(const unsigned long long *p, unsigned long long (&v)[4]) {
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
 
 // Home slot of a k-mer: the start of a bucket of four slots (one aligned 32-byte sector).  Keys
 // probe linearly from there, so a reader sees a whole bucket per memory transaction, and at a
@@ -192,8 +200,7 @@ __global__ void __launch_bounds__(256) ani_emit_kernel(const EmitParams p) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (p.contig_start[c0 + mid] <= rel) lo = mid; else hi = mid;
             }
-            p.ks[so + rank] = (canon << 1) | strand;
-            p.spread[so + rank] = rel + lo * (uint32_t)(kAniBand + 1);
+            p.kq[so + rank] = make_uint2((canon << 1) | strand, rel + lo * (uint32_t)(kAniBand + 1));
             p.chunk_tmp[so + rank] = p.contig_chunk_base[c0 + lo] + (rel - p.contig_start[c0 + lo]) / kAniChunk;
             rank++;
         }
@@ -219,9 +226,9 @@ __global__ void __launch_bounds__(256) ani_emit_kernel(const EmitParams p) {
     const uint32_t mask = (uint32_t)(p.table_off[g + 1] - to) - 1;
     unsigned long long *table = p.table + to;
     for (uint32_t x = tid; x < n_seeds; x += 256) {
-        const uint32_t ks = p.ks[so + x];
-        const unsigned long long e = ((unsigned long long)(ks >> 1) << 33) | ((unsigned long long)(ks & 1) << 32) |
-                                     p.spread[so + x];
+        const uint2 kq = p.kq[so + x];
+        const uint32_t ks = kq.x;
+        const unsigned long long e = ((unsigned long long)(ks >> 1) << 33) | ((unsigned long long)(ks & 1) << 32) | kq.y;
         uint32_t slot = table_slot(ks >> 1, mask);
         while (atomicCAS(&table[slot], kEmpty, e) != kEmpty) slot = (slot + 1) & mask;
     }
@@ -229,7 +236,8 @@ __global__ void __launch_bounds__(256) ani_emit_kernel(const EmitParams p) {
 
 struct ChainParams {
     const uint32_t *pairs;  // (query, reference) genome ids
-    const uint32_t *ks, *spread, *cso;
+    const uint2 *kq;  // per seed: x = kmer << 1 | strand, y = spread position
+    const uint32_t *cso;
     const unsigned long long *table;
     const uint64_t *seed_off, *cso_off, *table_off;
     const uint32_t *n_chunks;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     const uint32_t u = blockIdx.x * kChainThreads + tid;
     // no early exits: every lane of a warp stays in the lock-step walk (idle lanes walk 0 seeds)
     uint32_t pair = 0, x0 = 0, x1 = 0;
-    const uint32_t *qks = p.ks, *qsp = p.spread;
+    const uint2 *qkq = p.kq;
     const unsigned long long *table = p.table;
     uint32_t mask = 0;
     if (u < p.n_units) {
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
         const uint32_t *cso = p.cso + p.cso_off[q];
         x0 = cso[t]; x1 = cso[t + 1];
         if (x1 - x0 < (uint32_t)kAniMinAnchors) x1 = x0;
-        qks = p.ks + p.seed_off[q]; qsp = p.spread + p.seed_off[q];
+        qkq = p.kq + p.seed_off[q];
         table = p.table + p.table_off[r];
         mask = (uint32_t)(p.table_off[r + 1] - p.table_off[r]) - 1;
     }
@@ -283,13 +291,11 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     // cluster contiguous, so one read usually holds the whole run up to its empty slot and the
     // chain of dependent reads -- max over the warp's lanes -- is one or two long instead of
     // the cluster length.
-    uint32_t ks1 = x0 < x1 ? qks[x0] : 0u, ks2 = x0 + 1 < x1 ? qks[x0 + 1] : 0u;
-    int qp1 = x0 < x1 ? (int)qsp[x0] : 0, qp2 = x0 + 1 < x1 ? (int)qsp[x0 + 1] : 0;
-    ulonglong2 g1a = make_ulonglong2(kEmpty, kEmpty), g1b = g1a;
-    if (x0 < x1) {
-        const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + table_slot(ks1 >> 1, mask));
-        g1a = gp[0]; g1b = gp[1];
-    }
+    const uint2 kq1 = x0 < x1 ? qkq[x0] : make_uint2(0u, 0u), kq2 = x0 + 1 < x1 ? qkq[x0 + 1] : make_uint2(0u, 0u);
+    uint32_t ks1 = kq1.x, ks2 = kq2.x;
+    int qp1 = (int)kq1.y, qp2 = (int)kq2.y;
+    unsigned long long g1[4] = {kEmpty, kEmpty, kEmpty, kEmpty};
+    if (x0 < x1) load_bucket(table + table_slot(ks1 >> 1, mask), g1);
     // The trip count is the warp's longest chunk and every iteration starts with a warp barrier, so
     // the lanes re-join after the divergent chaining step whatever the compiler's own
     // reconvergence points are.
@@ -299,14 +305,11 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
         if (it >= len) continue;
         const uint32_t x = x0 + it;
         const uint32_t ks = ks1;
-        unsigned long long v[4] = {g1a.x, g1a.y, g1b.x, g1b.y};
+        unsigned long long v[4] = {g1[0], g1[1], g1[2], g1[3]};
         const int qpos = qp1;
         ks1 = ks2; qp1 = qp2;
-        if (x + 1 < x1) {
-            const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + table_slot(ks1 >> 1, mask));
-            g1a = gp[0]; g1b = gp[1];
-        }
-        if (x + 2 < x1) { ks2 = qks[x + 2]; qp2 = (int)qsp[x + 2]; }
+        if (x + 1 < x1) load_bucket(table + table_slot(ks1 >> 1, mask), g1);
+        if (x + 2 < x1) { const uint2 kq = qkq[x + 2]; ks2 = kq.x; qp2 = (int)kq.y; }
         const uint32_t km = ks >> 1, qs = ks & 1;
         const uint32_t home = table_slot(km, mask);
         uint32_t c = 0;
@@ -324,9 +327,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
                 }
                 if (!open) break;
                 g = (g + 4) & mask;
-                const ulonglong2 *gp = reinterpret_cast<const ulonglong2 *>(table + g);
-                const ulonglong2 a = gp[0], b2 = gp[1];
-                v[0] = a.x; v[1] = a.y; v[2] = b2.x; v[3] = b2.y;
+                load_bucket(table + g, v);
             }
         }
         const uint32_t occ = c > (uint32_t)kAniMaxOcc ? 0u : c;
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
         uint32_t *acc = p.acc + 4 * (size_t)pair;
         atomicAdd(&acc[0], best_cnt - 2);
         atomicAdd(&acc[1], N - 2);
-        atomicAdd(&acc[2], qsp[x0 + best_last_x] - qsp[x0 + best_first_x] + kAniK);
+        atomicAdd(&acc[2], qkq[x0 + best_last_x].y - qkq[x0 + best_first_x].y + kAniK);
         atomicAdd(&acc[3], (uint32_t)abs(best_last_r - best_first_r) + kAniK);
     }
 }
@@ -467,7 +468,7 @@ struct AniScratch {
 };
 
 AniIndex::~AniIndex() {
-    d_ks_.release(); d_spread_.release(); d_cso_.release(); d_table_.release();
+    d_kq_.release(); d_cso_.release(); d_table_.release();
     d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
     for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);
     delete scratch_;
@@ -529,10 +530,10 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
         seed_off[g + 1] = seed_off[g] + count[g];
         cso_off[g + 1] = cso_off[g] + n_chunks[g] + 1;
         uint64_t slots = 16;
-        while (slots < 4ull * count[g]) slots <<= 1;
+        while (slots < 2ull * count[g]) slots <<= 1;
         table_off[g + 1] = table_off[g] + slots;
     }
-    if (d_ks_.reserve(seed_off[n] + 1, st) || d_spread_.reserve(seed_off[n] + 1, st) ||
+    if (d_kq_.reserve(seed_off[n] + 1, st) ||
         d_cso_.reserve(cso_off[n] + 1, st) || d_table_.reserve(table_off[n] + 1, st) ||
         d_seed_off_.reserve(g0 + n + 2, st) || d_cso_off_.reserve(g0 + n + 2, st) ||
         d_table_off_.reserve(g0 + n + 2, st) || d_n_chunks_.reserve(g0 + n + 1, st))
@@ -547,7 +548,7 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     e.seq2 = d_seq2; e.valid = d_valid; e.sel = d_sel.p; e.base_off = d_base_off; e.first_base = first;
     e.contig_off = d_contig_off.p; e.contig_start = d_contig_start.p; e.contig_chunk_base = d_chunk_base.p;
     e.seed_off = d_seed_off_b.p; e.cso_off = d_cso_off_b.p; e.n_chunks = d_nch.p; e.table_off = d_table_off_b.p;
-    e.ks = d_ks_.p; e.spread = d_spread_.p; e.cso = d_cso_.p;
+    e.kq = d_kq_.p; e.cso = d_cso_.p;
     e.chunk_tmp = d_chunk_tmp.p - seed_off[0];  // indexed with absolute seed offsets
     e.table = d_table_.p;
     ani_emit_kernel<<<(uint32_t)n, 256, 0, st>>>(e);
@@ -562,7 +563,7 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     float ms = 0.f;
     GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     last_build_ms = ms;
-    d_ks_.n = d_spread_.n = seed_off[n]; d_cso_.n = cso_off[n]; d_table_.n = table_off[n];
+    d_kq_.n = seed_off[n]; d_cso_.n = cso_off[n]; d_table_.n = table_off[n];
     d_seed_off_.n = d_cso_off_.n = d_table_off_.n = g0 + n + 1; d_n_chunks_.n = g0 + n;
     for (size_t g = 0; g < n; g++) {
         seed_off_.push_back(seed_off[g + 1]); cso_off_.push_back(cso_off[g + 1]);
@@ -579,8 +580,7 @@ int AniIndex::reserve_for(size_t n_total, cudaStream_t st) {
     const size_t have = size();
     if (have == 0 || n_total <= have) return 0;
     const double scale = 1.03 * (double)n_total / (double)have;
-    if (d_ks_.reserve((size_t)(seed_off_.back() * scale) + 1024, st) ||
-        d_spread_.reserve((size_t)(seed_off_.back() * scale) + 1024, st) ||
+    if (d_kq_.reserve((size_t)(seed_off_.back() * scale) + 1024, st) ||
         d_cso_.reserve((size_t)(cso_off_.back() * scale) + 1024, st) ||
         d_table_.reserve((size_t)(table_off_.back() * scale) + 1024, st) ||
         d_seed_off_.reserve(n_total + 2, st) || d_cso_off_.reserve(n_total + 2, st) ||
@@ -601,10 +601,11 @@ int AniIndex::genome_seeds(size_t g, uint32_t *ks, uint32_t *spread, uint32_t *c
     const size_t ns = seed_off_[g + 1] - seed_off_[g];
     if (cap < ns) { set_error("ani index: seed buffer too small"); return 3; }
     std::vector<uint32_t> cso(n_chunks_[g] + 1);
-    GB_CUDA(cudaMemcpyAsync(ks, d_ks_.p + seed_off_[g], ns * 4, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaMemcpyAsync(spread, d_spread_.p + seed_off_[g], ns * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<uint2> kq(ns);
+    GB_CUDA(cudaMemcpyAsync(kq.data(), d_kq_.p + seed_off_[g], ns * sizeof(uint2), cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaMemcpyAsync(cso.data(), d_cso_.p + cso_off_[g], cso.size() * 4, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
+    for (size_t x = 0; x < ns; x++) { ks[x] = kq[x].x; spread[x] = kq[x].y; }
     for (uint32_t t = 0; t < n_chunks_[g]; t++)
         for (uint32_t x = cso[t]; x < cso[t + 1]; x++) chunk_of_seed[x] = t;
     return 0;
@@ -650,7 +651,7 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, Ani
             if (b0) GB_CUDA(cudaStreamSynchronize(st));
             GB_CUDA(cudaMemcpyAsync(d_prefix.p, unit_prefix.data() + b0, (b1 - b0 + 1) * 4, cudaMemcpyHostToDevice, st));
             ChainParams p;
-            p.pairs = d_pairs.p + 2 * b0; p.ks = d_ks_.p; p.spread = d_spread_.p; p.cso = d_cso_.p;
+            p.pairs = d_pairs.p + 2 * b0; p.kq = d_kq_.p; p.cso = d_cso_.p;
             p.table = d_table_.p; p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p; p.table_off = d_table_off_.p;
             p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + 4 * b0;
             p.unit_prefix = d_prefix.p; p.n_pairs = (uint32_t)(b1 - b0); p.n_units = (uint32_t)units;
@@ -675,6 +676,7 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, Ani
 }
 
 template struct DevVec<uint32_t>;
+template struct DevVec<uint2>;
 template struct DevVec<uint64_t>;
 template struct DevVec<unsigned long long>;
 

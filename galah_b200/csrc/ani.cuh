@@ -67,7 +67,8 @@ private:
     std::vector<uint64_t> seed_off_{0}, cso_off_{0}, table_off_{0}, total_len_;
     std::vector<uint32_t> n_chunks_;
     // device
-    DevVec<uint32_t> d_ks_, d_spread_, d_cso_;
+    DevVec<uint2> d_kq_;  // per seed (kmer << 1 | strand, spread position)
+    DevVec<uint32_t> d_cso_;
     DevVec<unsigned long long> d_table_;
     DevVec<uint64_t> d_seed_off_, d_cso_off_, d_table_off_;
     DevVec<uint32_t> d_n_chunks_;
