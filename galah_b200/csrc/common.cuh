@@ -71,6 +71,17 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// 1-D TMA bulk copy shared -> global (bytes % 16 == 0, both addresses 16-byte aligned), tracked by
+// the thread's bulk async-group: commit, then wait until the source may be reused / the CTA exit.
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 #endif
 

@@ -221,14 +221,18 @@ __device__ __forceinline__ bool key_le(uint64_t a, uint8_t ta, uint64_t b, uint8
 
 // One level of the merge tree: for every output run o, dst[o*2m .. o*2m+2m) = merge of
 // src[o*2m .. +m) and src[o*2m+m .. +2m) under the (value, tag) order, first run first on ties.
-// Merge-path splits of every tile boundary of one merge level, one thread per boundary (so the
-// ~16 dependent L2 probes of a split overlap across thousands of threads instead of serialising
-// at the head of every merge CTA).  splits[o * (chunks + 1) + c] = A-side split of diagonal c*kMTile.
+// Merge-path splits of every tile boundary of one merge level in a pre-pass (so the dependent L2
+// probes of a split overlap across all boundaries instead of serialising at the head of every
+// merge CTA).  splits[o * (chunks + 1) + c] = A-side split of diagonal c*kMTile.
 __global__ void __launch_bounds__(256) bl_partition_kernel(const uint64_t *__restrict__ sv,
                                                            const uint8_t *__restrict__ st, uint32_t m,
                                                            uint32_t chunks_per_run, uint64_t n_bounds,
                                                            uint32_t *__restrict__ splits) {
-    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // One WARP per boundary, 32-ary search: every round the 32 lanes probe 32 evenly spaced
+    // candidate splits at once and a ballot narrows the range 33-fold, so a boundary costs
+    // log_33(m) ~ 3-4 dependent L2 round trips instead of log_2(m) ~ 17.
+    const uint64_t b = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     if (b >= n_bounds) return;
     const uint64_t o = b / (chunks_per_run + 1);
     const uint32_t c = (uint32_t)(b % (chunks_per_run + 1));
@@ -237,11 +241,21 @@ __global__ void __launch_bounds__(256) bl_partition_kernel(const uint64_t *__res
     const uint8_t *tA = st + base, *tB = st + base + m;
     const uint32_t d = min(c * (uint32_t)kMTile, 2 * m);
     uint32_t lo = d > m ? d - m : 0, hi = min(d, m);
-    while (lo < hi) {  // smallest i with !(A[i] <= B[d-1-i])
-        const uint32_t mid = (lo + hi) >> 1;
-        if (key_le(A[mid], tA[mid], B[d - 1 - mid], tB[d - 1 - mid])) lo = mid + 1; else hi = mid;
+    // invariant: key_le holds for every index < lo and fails for every index >= hi (the
+    // predicate is monotone along the diagonal); answer = smallest i with !(A[i] <= B[d-1-i])
+    while (lo < hi) {
+        const uint32_t span = hi - lo;
+        // probe positions lo + (lane + 1) * span / 33, clamped into [lo, hi - 1]
+        const uint32_t mid = min(hi - 1, lo + (uint32_t)(((uint64_t)(lane + 1) * span) / 33));
+        const bool le = key_le(A[mid], tA[mid], B[d - 1 - mid], tB[d - 1 - mid]);
+        const uint32_t ok = __ballot_sync(0xffffffffu, le);  // monotone: a prefix of the lanes
+        const uint32_t n_le = __popc(ok);
+        // lanes 0 .. n_le-1 hold: the answer lies after lane n_le-1's probe and at or before lane n_le's
+        const uint32_t new_lo = n_le ? min(hi - 1, lo + (uint32_t)(((uint64_t)n_le * span) / 33)) + 1 : lo;
+        const uint32_t new_hi = n_le < 32 ? min(hi - 1, lo + (uint32_t)(((uint64_t)(n_le + 1) * span) / 33)) : hi;
+        lo = new_lo; hi = new_hi;
     }
-    splits[b] = lo;
+    if (lane == 0) splits[b] = lo;
 }
 
 struct MergeSmem {
@@ -318,6 +332,108 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_kernel(const uint64_t *__r
         } else {
             dv[base + d0 + x] = v;
         }
+    }
+}
+
+// The same merge level with the tile moved by the TMA engine in both directions: the A and B
+// slices (values and tags) arrive by four 1-D bulk copies, the merged tile leaves by two (three
+// at the last level: hi, lo, tags), so the LSU only carries the merge itself -- the staged
+// variant above spends about half of its shared-memory wavefronts on copying.  Needs every
+// run start and tile length to be a multiple of 16 entries (m % 16 == 0: every level above the seed).
+struct MergeTmaSmem {
+    uint64_t in_v[kMTile + 4];  // A window (from an even index), then B's at the next even slot
+    uint64_t out_v[kMTile];     // last level: out_hi = first half, out_lo = second half (uint32 each)
+    uint8_t in_t[kMTile + 64];  // A tag window (from a multiple of 16), then B's
+    uint8_t out_t[kMTile];
+    uint64_t bar;
+};
+
+template <bool kLast>
+__global__ void __launch_bounds__(kMThreads) bl_merge_tma_kernel(const uint64_t *__restrict__ sv,
+                                                                 const uint8_t *__restrict__ st,
+                                                                 uint64_t *__restrict__ dv,
+                                                                 uint8_t *__restrict__ dt, uint32_t m,
+                                                                 uint32_t chunks_per_run,
+                                                                 const uint32_t *__restrict__ splits,
+                                                                 const unsigned long long *__restrict__ gmax,
+                                                                 uint32_t *__restrict__ dhi,
+                                                                 uint32_t *__restrict__ dlo) {
+    extern __shared__ __align__(128) uint8_t merge_smem_raw[];
+    MergeTmaSmem &S = *reinterpret_cast<MergeTmaSmem *>(merge_smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t o = blockIdx.x / chunks_per_run, c = blockIdx.x % chunks_per_run;
+    const uint64_t base = (uint64_t)o * 2 * m;
+    const uint32_t d0 = c * kMTile, d1 = min(d0 + (uint32_t)kMTile, 2 * m);
+    const uint64_t sb = (uint64_t)o * (chunks_per_run + 1) + c;
+    const uint32_t i0 = splits[sb], i1 = splits[sb + 1], j0 = d0 - i0, j1 = d1 - i1;
+    const uint32_t na = i1 - i0, nb = j1 - j0, len = na + nb;
+    // aligned source windows (readable slack behind the level buffers covers the round-up)
+    const uint32_t av0 = i0 & ~1u, bv0 = j0 & ~1u, at0 = i0 & ~15u, bt0 = j0 & ~15u;
+    const uint32_t avn = (i1 - av0 + 1u) & ~1u, bvn = (j1 - bv0 + 1u) & ~1u;
+    const uint32_t atn = (i1 - at0 + 15u) & ~15u, btn = (j1 - bt0 + 15u) & ~15u;
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        fence_mbar_init();
+        mbar_arrive_expect_tx(&S.bar, (avn + bvn) * 8u + atn + btn);
+        if (avn) tma_load_1d(S.in_v, sv + base + av0, avn * 8u, &S.bar);
+        if (bvn) tma_load_1d(S.in_v + avn, sv + base + m + bv0, bvn * 8u, &S.bar);
+        if (atn) tma_load_1d(S.in_t, st + base + at0, atn, &S.bar);
+        if (btn) tma_load_1d(S.in_t + atn, st + base + m + bt0, btn, &S.bar);
+    }
+    __syncthreads();  // the barrier is initialised before anyone waits on it
+    mbar_wait(&S.bar, 0);
+    const uint64_t *As = S.in_v + (i0 - av0), *Bs = S.in_v + avn + (j0 - bv0);
+    const uint8_t *At = S.in_t + (i0 - at0), *Bt = S.in_t + atn + (j0 - bt0);
+    const uint32_t dt0 = min(tid * kME, len), dt1 = min(dt0 + (uint32_t)kME, len);
+    // own start split and own end split (= the next thread's start): no split table, no barrier
+    uint32_t sp[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const uint32_t dd = e ? dt1 : dt0;
+        uint32_t lo = dd > nb ? dd - nb : 0, hi = min(dd, na);
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint64_t a = As[mid], b = Bs[dd - 1 - mid];
+            const bool le = a < b || (a == b && At[mid] <= Bt[dd - 1 - mid]);  // tags only matter on a tie
+            if (le) lo = mid + 1; else hi = mid;
+        }
+        sp[e] = lo;
+    }
+    uint32_t i = sp[0], j = dt0 - i;
+    const uint32_t ie = sp[1], je = dt1 - ie;
+    int sh = 0;
+    if (kLast) { const unsigned long long g = *gmax; sh = g ? __clzll((long long)g) : 0; }
+    uint32_t *out_hi = reinterpret_cast<uint32_t *>(S.out_v), *out_lo = out_hi + kMTile;
+    // the values under the two cursors live in registers: one shared-memory load per step
+    uint64_t a = As[min(i, na)], b = Bs[min(j, nb)];  // index na / nb is inside the windows' slack
+    for (uint32_t x = dt0; x < dt1; x++) {
+        bool take_a;
+        if (j >= je) take_a = true;
+        else if (i >= ie) take_a = false;
+        else take_a = a < b || (a == b && At[i] <= Bt[j]);
+        uint64_t v; uint8_t tg;
+        if (take_a) { v = a; tg = At[i]; i++; a = As[min(i, na)]; }
+        else { v = b; tg = Bt[j]; j++; b = Bs[min(j, nb)]; }
+        S.out_t[x] = tg;
+        if (kLast) {
+            const uint64_t w = v << sh;
+            out_hi[x] = tg == kPadTag ? 0xFFFFFFFFu : (uint32_t)(w >> 32);
+            out_lo[x] = (uint32_t)w;
+        } else {
+            S.out_v[x] = v;
+        }
+    }
+    fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk-copy engine
+    __syncthreads();
+    if (tid == 0 && len) {
+        tma_store_1d(dt + base + d0, S.out_t, len);
+        if (kLast) {
+            tma_store_1d(dhi + base + d0, out_hi, len * 4u);
+            tma_store_1d(dlo + base + d0, out_lo, len * 4u);
+        } else {
+            tma_store_1d(dv + base + d0, S.out_v, len * 8u);
+        }
+        tma_store_commit_and_wait();  // shared memory must outlive the reads of the copy engine
     }
 }
 
@@ -729,8 +845,9 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
         }
         ws.cap_bl = 0;
         for (int x = 0; x < 2; x++) {
-            GB_CUDA(cudaMalloc(&ws.d_bl_vals[x], total * 8));
-            GB_CUDA(cudaMalloc(&ws.d_bl_tags[x], total));
+            // + slack: the bulk copies of the merge levels round their windows up to 16 bytes
+            GB_CUDA(cudaMalloc(&ws.d_bl_vals[x], (total + 64) * 8));
+            GB_CUDA(cudaMalloc(&ws.d_bl_tags[x], total + 64));
         }
         ws.cap_bl = total;
     }
@@ -750,6 +867,8 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
     }
     GB_CUDA(cudaFuncSetAttribute(bl_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
     GB_CUDA(cudaFuncSetAttribute(bl_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem)));
+    GB_CUDA(cudaFuncSetAttribute(bl_merge_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeTmaSmem)));
+    GB_CUDA(cudaFuncSetAttribute(bl_merge_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeTmaSmem)));
     int src = 0;
     {   // tile-boundary splits: at most (chunks + 1) per output run, most at the first level
         const uint64_t need = total / (2 * stride) * ((2 * stride + kMTile - 1) / kMTile + 1) + 16;
@@ -760,17 +879,28 @@ int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint
         const uint64_t grid = total / (2 * m) * chunks;
         if (grid > 0x7FFFFFFFull) { set_error("prefilter: table too large for the merge grid"); return 3; }
         const uint64_t n_bounds = total / (2 * m) * (chunks + 1);
-        bl_partition_kernel<<<(uint32_t)((n_bounds + 255) / 256), 256, 0, stream>>>(
+        bl_partition_kernel<<<(uint32_t)((n_bounds * 32 + 255) / 256), 256, 0, stream>>>(
             ws.d_bl_vals[src], ws.d_bl_tags[src], (uint32_t)m, chunks, n_bounds, ws.d_splits);
         GB_LAUNCH_CHECK();
-        if (2 * m >= bl_cap)  // last level: structure-of-arrays output into the caller's buffers
+        const bool last = 2 * m >= bl_cap;  // last level: structure-of-arrays output into the caller's buffers
+        const bool tma = m % 16 == 0;  // run starts and tile lengths are then multiples of 16 entries (bulk-copy alignment)
+        uint64_t *dvv = last ? nullptr : ws.d_bl_vals[src ^ 1];
+        uint8_t *dtt = last ? d_tags : ws.d_bl_tags[src ^ 1];
+        uint32_t *dh = last ? d_hi : nullptr, *dl = last ? d_lo : nullptr;
+        if (tma) {
+            if (last)
+                bl_merge_tma_kernel<true><<<(uint32_t)grid, kMThreads, sizeof(MergeTmaSmem), stream>>>(
+                    ws.d_bl_vals[src], ws.d_bl_tags[src], dvv, dtt, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, dh, dl);
+            else
+                bl_merge_tma_kernel<false><<<(uint32_t)grid, kMThreads, sizeof(MergeTmaSmem), stream>>>(
+                    ws.d_bl_vals[src], ws.d_bl_tags[src], dvv, dtt, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, dh, dl);
+        } else if (last) {
             bl_merge_kernel<true><<<(uint32_t)grid, kMThreads, sizeof(MergeSmem), stream>>>(
-                ws.d_bl_vals[src], ws.d_bl_tags[src], nullptr, d_tags, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, d_hi,
-                d_lo);
-        else
+                ws.d_bl_vals[src], ws.d_bl_tags[src], dvv, dtt, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, dh, dl);
+        } else {
             bl_merge_kernel<false><<<(uint32_t)grid, kMThreads, sizeof(MergeSmem), stream>>>(
-                ws.d_bl_vals[src], ws.d_bl_tags[src], ws.d_bl_vals[src ^ 1], ws.d_bl_tags[src ^ 1], (uint32_t)m, chunks,
-                ws.d_splits, ws.d_gmax, nullptr, nullptr);
+                ws.d_bl_vals[src], ws.d_bl_tags[src], dvv, dtt, (uint32_t)m, chunks, ws.d_splits, ws.d_gmax, dh, dl);
+        }
         GB_LAUNCH_CHECK();
         src ^= 1;
     }
