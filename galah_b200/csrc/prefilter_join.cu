@@ -345,6 +345,7 @@ struct MergeTmaSmem {
     uint64_t out_v[kMTile];     // last level: out_hi = first half, out_lo = second half (uint32 each)
     uint8_t in_t[kMTile + 64];  // A tag window (from a multiple of 16), then B's
     uint8_t out_t[kMTile];
+    uint32_t ts[kMThreads + 1];
     uint64_t bar;
 };
 
@@ -385,22 +386,21 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_tma_kernel(const uint64_t 
     const uint64_t *As = S.in_v + (i0 - av0), *Bs = S.in_v + avn + (j0 - bv0);
     const uint8_t *At = S.in_t + (i0 - at0), *Bt = S.in_t + atn + (j0 - bt0);
     const uint32_t dt0 = min(tid * kME, len), dt1 = min(dt0 + (uint32_t)kME, len);
-    // own start split and own end split (= the next thread's start): no split table, no barrier
-    uint32_t sp[2];
-#pragma unroll
-    for (int e = 0; e < 2; e++) {
-        const uint32_t dd = e ? dt1 : dt0;
-        uint32_t lo = dd > nb ? dd - nb : 0, hi = min(dd, na);
+    // own start split; the end split is the next thread's start (shared through S.ts)
+    {
+        uint32_t lo = dt0 > nb ? dt0 - nb : 0, hi = min(dt0, na);
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            const uint64_t a = As[mid], b = Bs[dd - 1 - mid];
-            const bool le = a < b || (a == b && At[mid] <= Bt[dd - 1 - mid]);  // tags only matter on a tie
+            const uint64_t a = As[mid], b = Bs[dt0 - 1 - mid];
+            const bool le = a < b || (a == b && At[mid] <= Bt[dt0 - 1 - mid]);  // tags only matter on a tie
             if (le) lo = mid + 1; else hi = mid;
         }
-        sp[e] = lo;
+        S.ts[tid] = lo;
+        if (tid == 0) S.ts[kMThreads] = na;
     }
-    uint32_t i = sp[0], j = dt0 - i;
-    const uint32_t ie = sp[1], je = dt1 - ie;
+    __syncthreads();
+    uint32_t i = S.ts[tid], j = dt0 - i;
+    const uint32_t ie = S.ts[tid + 1], je = dt1 - ie;
     int sh = 0;
     if (kLast) { const unsigned long long g = *gmax; sh = g ? __clzll((long long)g) : 0; }
     uint32_t *out_hi = reinterpret_cast<uint32_t *>(S.out_v), *out_lo = out_hi + kMTile;
