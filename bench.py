@@ -468,7 +468,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "passing_pairs": int(n_pass_t.item()), "ms": 1e3 * float(e2e_t.item()),
                     "pipeline": f"upload in {gb.prefilter_stream_chunks()} slices on a copy stream, block lists of a slice "
-                                "built as it lands, join after the last" if world == 1 else "per-rank slice upload, NVLink all-gathers",
+                                "built as it lands, join after the last; survivors land in mapped pinned memory and "
+                                "their f64 finish runs on the host while the kernels run" if world == 1 else "per-rank slice upload, NVLink all-gathers",
                     "host_ms": e2e_host, "single_upload": e2e_single_upload},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

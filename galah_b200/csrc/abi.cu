@@ -43,13 +43,19 @@ struct Context {
     unsigned long long *d_n_cand = nullptr;
     cudaStream_t copy_stream = nullptr;  // PCIe uploads of the streamed host-buffer prefilter
     double stream_wave_frac = 0.0;       // early join wave after this fraction of the slices (0 = none)
-    int stream_chunks = 4;               // slices of that upload (<= 1 disables the pipeline)
+    int stream_chunks = 8;               // slices of that upload (<= 1 disables the pipeline)
     uint4 *h_stage = nullptr;            // pinned landing zone: candidate count + first kStageCand candidates
     float host_ms[4] = {0, 0, 0, 0};     // last host-buffer prefilter: enqueue, wait, d2h, finish
+    uint4 *h_cand_map = nullptr;         // zero-copy candidate list of the streamed call (mapped pinned, all-zero between calls)
+    size_t cap_cand_map = 0;
+    cudaEvent_t ev_done = nullptr;
     int release() {
         pws.release(); sws.release();
         cudaFree(d_table); cudaFree(d_counts); cudaFree(d_cand); cudaFree(d_n_cand);
         if (h_stage) cudaFreeHost(h_stage);
+        if (h_cand_map) cudaFreeHost(h_cand_map);
+        if (ev_done) cudaEventDestroy(ev_done);
+        h_cand_map = nullptr; cap_cand_map = 0; ev_done = nullptr;
         if (copy_stream) cudaStreamDestroy(copy_stream);
         d_table = nullptr; d_counts = nullptr; d_cand = nullptr; d_n_cand = nullptr;
         h_stage = nullptr; copy_stream = nullptr;
@@ -85,35 +91,49 @@ struct DevBuf {
 // (src/finch.rs:78-93), sorted by (i, j) -- the iteration order of the reference's BTreeMap.  Host
 // only.  The order comes from a counting sort on i (candidates are sparse: a few per row) and a
 // small sort by j inside each row, O(candidates + rows) instead of a comparison sort of all.
+struct CandFinisher {
+    int k;
+    double thr;
+    std::vector<uint4> c;
+    std::vector<float> ani;
+    std::vector<uint8_t> keep;
+    CandFinisher(int k_, float min_ani) : k(k_), thr((double)min_ani) {}
+    void reserve(size_t n) { c.reserve(n); ani.reserve(n); keep.reserve(n); }
+    void clear() { c.clear(); ani.clear(); keep.clear(); }
+    void add(const uint4 &x) {  // the f64 `ln` dominates the host finish (~13 ns per candidate)
+        const double a = mash_ani_f64(x.z, x.w, k);
+        c.push_back(x); ani.push_back((float)a); keep.push_back(a >= thr ? 1 : 0);
+    }
+    int finalize(galah_b200_pair_t **out, size_t *n_out) const {
+        const size_t n_cand = c.size();
+        uint32_t max_i = 0;
+        for (size_t x = 0; x < n_cand; x++) max_i = std::max(max_i, c[x].x);
+        std::vector<uint32_t> row_start((size_t)max_i + 2, 0);
+        for (size_t x = 0; x < n_cand; x++)
+            if (keep[x]) row_start[c[x].x + 1]++;
+        for (size_t r = 0; r + 1 < row_start.size(); r++) row_start[r + 1] += row_start[r];
+        const size_t n_pass = n_cand ? row_start.back() : 0;
+        galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(n_pass, 1) * sizeof(galah_b200_pair_t));
+        if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+        std::vector<uint32_t> fill(row_start.begin(), row_start.end());
+        for (size_t x = 0; x < n_cand; x++)
+            if (keep[x]) res[fill[c[x].x]++] = galah_b200_pair_t{c[x].x, c[x].y, c[x].z, c[x].w, ani[x]};
+        auto by_j = [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) { return a.j < b.j; };
+        for (size_t r = 0; r + 1 < row_start.size(); r++) {
+            galah_b200_pair_t *b = res + row_start[r], *e = res + row_start[r + 1];
+            if (e - b > 1 && !std::is_sorted(b, e, by_j)) std::sort(b, e, by_j);
+        }
+        *out = res; *n_out = n_pass;
+        return 0;
+    }
+};
+
 static int finish_candidates(const uint4 *cand, size_t n_cand, int k, float min_ani, galah_b200_pair_t **out,
                              size_t *n_out) {
-    const double thr = (double)min_ani;
-    uint32_t max_i = 0;
-    for (size_t x = 0; x < n_cand; x++) max_i = std::max(max_i, cand[x].x);
-    std::vector<uint32_t> row_start((size_t)max_i + 2, 0);
-    std::vector<float> ani(n_cand);
-    std::vector<uint8_t> keep(n_cand);
-    for (size_t x = 0; x < n_cand; x++) {  // the f64 `ln` dominates the host finish (~13 ns per candidate)
-        const double a = mash_ani_f64(cand[x].z, cand[x].w, k);
-        keep[x] = a >= thr;
-        ani[x] = (float)a;
-    }
-    for (size_t x = 0; x < n_cand; x++)
-        if (keep[x]) row_start[cand[x].x + 1]++;
-    for (size_t r = 0; r + 1 < row_start.size(); r++) row_start[r + 1] += row_start[r];
-    const size_t n_pass = n_cand ? row_start.back() : 0;
-    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(n_pass, 1) * sizeof(galah_b200_pair_t));
-    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
-    std::vector<uint32_t> fill(row_start.begin(), row_start.end());
-    for (size_t x = 0; x < n_cand; x++)
-        if (keep[x]) res[fill[cand[x].x]++] = galah_b200_pair_t{cand[x].x, cand[x].y, cand[x].z, cand[x].w, ani[x]};
-    for (size_t r = 0; r + 1 < row_start.size(); r++) {
-        galah_b200_pair_t *b = res + row_start[r], *e = res + row_start[r + 1];
-        if (e - b > 1 && !std::is_sorted(b, e, [](const galah_b200_pair_t &a, const galah_b200_pair_t &c) { return a.j < c.j; }))
-            std::sort(b, e, [](const galah_b200_pair_t &a, const galah_b200_pair_t &c) { return a.j < c.j; });
-    }
-    *out = res; *n_out = n_pass;
-    return 0;
+    CandFinisher fin(k, min_ani);
+    fin.reserve(n_cand);
+    for (size_t x = 0; x < n_cand; x++) fin.add(cand[x]);
+    return fin.finalize(out, n_out);
 }
 
 constexpr size_t kStageCand = 1 << 16;  // candidates fetched together with their count (1 MiB, pinned)
@@ -166,16 +186,68 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
     for (;;) {
         if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
         if (h_hashes) {
+            // Streamed call: the join appends its survivors straight into MAPPED pinned host
+            // memory (one 16-byte store each, so a slot is either all zero or complete; j >= 1
+            // marks it written) and this thread evaluates the f64 formula of every candidate
+            // while the kernels are still running -- the host finish costs no wall time.
+            if (g_ctx.cap_cand_map < cap) {
+                if (g_ctx.h_cand_map) GB_CUDA(cudaFreeHost(g_ctx.h_cand_map));
+                g_ctx.h_cand_map = nullptr; g_ctx.cap_cand_map = 0;
+                GB_CUDA(cudaHostAlloc(&g_ctx.h_cand_map, cap * sizeof(uint4), cudaHostAllocMapped));
+                memset(g_ctx.h_cand_map, 0, cap * sizeof(uint4));
+                g_ctx.cap_cand_map = cap;
+            }
+            if (!g_ctx.ev_done) GB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_done, cudaEventDisableTiming));
+            uint4 *d_map = nullptr;
+            GB_CUDA(cudaHostGetDevicePointer(&d_map, g_ctx.h_cand_map, 0));
             KernelParams p;
-            if (int rc = prefilter_prepare(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, 0, 1, stream, g_ctx.d_cand,
-                                           g_ctx.cap_cand, g_ctx.d_n_cand, p))
+            if (int rc = prefilter_prepare(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, 0, 1, stream, d_map,
+                                           g_ctx.cap_cand_map, g_ctx.d_n_cand, p))
                 return rc;
             if (int rc = join_streamed_from_host(g_ctx.pws, p, h_hashes, h_counts, const_cast<uint64_t *>(d_hashes),
                                                  stream, g_ctx.copy_stream, g_ctx.stream_chunks,
-                                                 getenv("GALAH_B200_STREAM_WAVE") ? atof(getenv("GALAH_B200_STREAM_WAVE"))
-                                                                                  : g_ctx.stream_wave_frac))
+                                                 g_ctx.stream_wave_frac))
                 return rc;
             h_hashes = nullptr;
+            if (!g_ctx.h_stage) GB_CUDA(cudaMallocHost(&g_ctx.h_stage, (kStageCand + 1) * sizeof(uint4)));
+            GB_CUDA(cudaMemcpyAsync(g_ctx.h_stage, g_ctx.d_n_cand, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            GB_CUDA(cudaEventRecord(g_ctx.ev_done, stream));
+            g_ctx.host_ms[0] = (float)(now_ms() - t_begin);
+            const double t_wait = now_ms();
+            CandFinisher fin(k, min_ani);
+            fin.reserve(1 << 16);
+            const volatile uint4 *hc = g_ctx.h_cand_map;
+            size_t next = 0;
+            auto drain = [&](size_t limit) {
+                while (next < limit && hc[next].y != 0) {
+                    fin.add(make_uint4(hc[next].x, hc[next].y, hc[next].z, hc[next].w));
+                    next++;
+                }
+            };
+            for (;;) {
+                const cudaError_t q = cudaEventQuery(g_ctx.ev_done);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail_cuda(q, "cudaEventQuery", __FILE__, __LINE__);
+                drain(g_ctx.cap_cand_map);
+                if (q == cudaSuccess) break;
+            }
+            const unsigned long long got = *reinterpret_cast<const volatile unsigned long long *>(g_ctx.h_stage);
+            g_ctx.host_ms[1] = (float)(now_ms() - t_wait);
+            const size_t written = (size_t)std::min<unsigned long long>(got, g_ctx.cap_cand_map);
+            if (got <= g_ctx.cap_cand_map) {
+                drain(written);  // everything is in place once the kernels have completed
+                if (next != written) {
+                    memset(g_ctx.h_cand_map, 0, g_ctx.cap_cand_map * sizeof(uint4));
+                    set_error("prefilter: candidate list in mapped memory is incomplete");
+                    return GALAH_B200_ERR_CUDA;
+                }
+            }
+            memset(g_ctx.h_cand_map, 0, written * sizeof(uint4));  // all-zero again for the next call
+            g_ctx.host_ms[2] = 0.f;
+            if (got > g_ctx.cap_cand_map) { cap = (size_t)got; continue; }  // overflow: re-run on the resident table
+            const double t0 = now_ms();
+            const int rc = fin.finalize(out, n_out);
+            g_ctx.host_ms[3] = (float)(now_ms() - t0);
+            return rc;
         } else {
             int rc = prefilter_enqueue(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, shard, n_shards,
                                        g_ctx.prefilter_mode, stream, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand);

@@ -112,8 +112,9 @@ int galah_b200_prefilter_last_timing(float *build_ms, float *main_ms);
 /* Host-buffer calls (galah_b200_prefilter / _shard with n_shards == 1, mode 0) upload the table
  * in `chunks` slices of whole row blocks on a copy stream and build the block lists of each
  * slice as soon as it is resident, so the build hides under the PCIe transfer and only the join
- * is left when the transfer ends.  chunks <= 1 disables the pipeline (one upload, then the
- * kernels); < 0 only queries.  Returns the previous setting (default 4).  The pair list is
+ * is left when the transfer ends; the join writes its survivors into mapped pinned host memory
+ * and the calling thread evaluates their f64 formula while the kernels still run.  chunks <= 1 disables the pipeline (one upload, then the
+ * kernels); < 0 only queries.  Returns the previous setting (default 8).  The pair list is
  * identical either way. */
 int galah_b200_prefilter_stream_chunks(int chunks);
 

@@ -13,18 +13,17 @@ t = ht.numpy().view(np.uint64); c = hc.numpy().view(np.uint32)
 def run(chunks, label, env={}):
     gb.prefilter_stream_chunks(chunks)
     for e, v in env.items(): os.environ[e] = v
-    for it in range(4):
-        if it == 3: os.environ["GALAH_B200_STREAM_DEBUG"] = "1"
+    ts = []
+    for it in range(12):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         r = gb.prefilter(t, c, 21, 0.9)
         dt = time.perf_counter() - t0
-        os.environ.pop("GALAH_B200_STREAM_DEBUG", None)
+        if it >= 2: ts.append(dt)
     for e in env: os.environ.pop(e)
-    print(label, chunks, f"{dt*1e3:.3f} ms", len(r), gb.prefilter_last_timing(), flush=True)
-run(1, "plain")
-run(4, "s4")
-run(4, "s4-w50", {"GALAH_B200_STREAM_WAVE": "0.5"})
-run(4, "s4-w75", {"GALAH_B200_STREAM_WAVE": "0.75"})
-run(6, "s6")
-run(6, "s6-w66", {"GALAH_B200_STREAM_WAVE": "0.667"})
-run(8, "s8-w75", {"GALAH_B200_STREAM_WAVE": "0.75"})
+    print(label, chunks, f"mean {np.mean(ts)*1e3:.3f} ms min {np.min(ts)*1e3:.3f}", len(r), gb.prefilter_last_host_timing(), flush=True)
+for rep in range(2):
+    run(1, "plain")
+    run(4, "s4-map")
+    run(4, "s4-nomap", {"GALAH_B200_NO_MAP": "1"})
+    run(8, "s8-map")
+    run(2, "s2-map")
