@@ -39,7 +39,9 @@ BYTES_PER_PAIR = 2 * S * 8
 
 def n_genomes_for(gpus, base):
     n = base * math.sqrt(gpus)
-    q = 10 * gpus * 8
+    # per rank a whole number of families of 10 AND of row blocks of 128 (so a rank's slice is whole
+    # block lists and its build needs no gathered table): multiples of lcm(10, 128) = 640
+    q = 640 * gpus if gpus > 1 else 80
     return max(q, int(round(n / q)) * q)
 
 
@@ -235,44 +237,32 @@ def main():
                 ani_index.reserve(n_local)
     del d_seq, d_val, d_off
 
-    table = torch.empty((n, S), dtype=torch.int64, device=dev) if world > 1 else my_table
-    counts = torch.empty(n, dtype=torch.int32, device=dev) if world > 1 else my_counts
-    cand_cap = max(1 << 20, 64 * n)
-    d_cand = torch.empty((cand_cap, 4), dtype=torch.int32, device=dev)
-    d_ncand = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.int8, device=dev)  # > 126 MB L2
-
+    sp = None
     if world > 1:
-        # multi-GPU: the block-list BUILD shards too -- every rank builds a contiguous slice of
-        # blocks and the slices are all-gathered (hi, lo, tags, lengths) before the join
-        nb, epb, slack = gb.blocklist_layout(n, S)
-        nbp = (nb + world - 1) // world
-        my_hi = torch.empty(nbp * epb, dtype=torch.int32, device=dev)
-        my_lo = torch.empty_like(my_hi)
-        my_tags = torch.empty(nbp * epb, dtype=torch.uint8, device=dev)
-        my_len = torch.empty(nbp, dtype=torch.int32, device=dev)
-        all_hi = torch.zeros(world * nbp * epb + slack, dtype=torch.int32, device=dev)
-        all_lo = torch.zeros_like(all_hi)
-        all_tags = torch.zeros(world * nbp * epb + slack, dtype=torch.uint8, device=dev)
-        all_len = torch.empty(world * nbp, dtype=torch.int32, device=dev)
+        # multi-GPU: galah_b200.distributed.ShardedPrefilter is the product path; the timed step is
+        # its device part (all-reduce of the largest hash, table all-gather overlapped with the
+        # per-rank build of its own block lists, all-gather of the lists, join of the rank's shard)
+        from galah_b200.distributed import ShardedPrefilter
+        sp = ShardedPrefilter(gb, dist, n_local, S, dev)
+        sp.my_table.copy_(my_table)
+        sp.my_counts.copy_(my_counts)
+        table, counts, d_cand, d_ncand, cand_cap = sp.table, sp.counts, sp.d_cand, sp.d_ncand, sp.cand_cap
+    else:
+        table, counts = my_table, my_counts
+        cand_cap = max(1 << 20, 64 * n)
+        d_cand = torch.empty((cand_cap, 4), dtype=torch.int32, device=dev)
+        d_ncand = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def timed(mode, steps, warmup):
         """`steps` timed passes of `mode`; returns (total_ms max over ranks, launches, per-kernel ms)."""
         def step():
+            if world > 1 and mode == 0:
+                sp.step_device(K, MIN_ANI)
+                return
             if world > 1:
                 dist.all_gather_into_tensor(table, my_table)
                 dist.all_gather_into_tensor(counts, my_counts)
-            if world > 1 and mode == 0:
-                gb.blocklist_build(table.data_ptr(), counts.data_ptr(), n, S, rank * nbp, (rank + 1) * nbp,
-                                   my_hi.data_ptr(), my_lo.data_ptr(), my_tags.data_ptr(), my_len.data_ptr(), st)
-                dist.all_gather_into_tensor(all_hi[: world * nbp * epb], my_hi)
-                dist.all_gather_into_tensor(all_lo[: world * nbp * epb], my_lo)
-                dist.all_gather_into_tensor(all_tags[: world * nbp * epb], my_tags)
-                dist.all_gather_into_tensor(all_len, my_len)
-                gb.prefilter_join_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, all_hi.data_ptr(),
-                                          all_lo.data_ptr(), all_tags.data_ptr(), all_len.data_ptr(), rank, world,
-                                          st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
-                return
             gb.prefilter_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, rank, world,
                                  mode, st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
         for _ in range(warmup):
@@ -334,8 +324,6 @@ def main():
     e2e_times = []
     n_pass = 0
     if world > 1:
-        from galah_b200.distributed import ShardedPrefilter
-        sp = ShardedPrefilter(gb, dist, n_local, S, dev)
         h_my_table = h_table[rank * n_local:(rank + 1) * n_local]
         h_my_counts = h_counts[rank * n_local:(rank + 1) * n_local]
     for it in range(2 + min(args.steps, 5)):
@@ -461,8 +449,9 @@ def main():
                                    f"{' scaled by sqrt(G) genomes' if world > 1 else ''})",
                        "pairs_per_step": pairs, "mode": args.mode,
                        "l2": "flushed between timed iterations (256 MiB write)",
-                       "sharding": "boustrophedon row blocks of 128; inside the step: NCCL all-gather of the sketch "
-                                   "table, per-rank build of 1/G of the block lists, NCCL all-gather of the lists"
+                       "sharding": "boustrophedon row blocks of 128; inside the step: 8-byte all-reduce (largest hash), "
+                                   "NCCL all-gather of the sketch table overlapped with the per-rank build of its own "
+                                   "block lists, NCCL all-gather of the lists, join of the rank's shard"
                                    if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

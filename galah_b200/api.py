@@ -167,6 +167,18 @@ def blocklist_build(d_hashes, d_counts, n, stride, block_begin, block_end, d_hi,
                                            d_tags, d_len, stream))
 
 
+def table_max_device(d_hashes, d_counts, n, stride, d_max, stream=0):
+    """Largest valid hash of a (slice of a) device sketch table -> device uint64 scalar d_max."""
+    check(lib().galah_b200_table_max_device(d_hashes, d_counts, n, stride, d_max, stream))
+
+
+def blocklist_build_local(d_rows, d_counts, n_rows, stride, d_table_max, n_blocks_out, d_hi, d_lo, d_tags, d_len,
+                          stream=0):
+    """Block lists of a local slice of whole row blocks, table-wide maximum supplied by the caller."""
+    check(lib().galah_b200_blocklist_build_local(d_rows, d_counts, n_rows, stride, d_table_max, n_blocks_out,
+                                                 d_hi, d_lo, d_tags, d_len, stream))
+
+
 def prefilter_join_enqueue(d_hashes, d_counts, n, stride, k, min_ani, d_hi, d_lo, d_tags, d_len, shard, n_shards,
                            stream, d_cand, cand_cap, d_n_cand):
     check(lib().galah_b200_prefilter_join_enqueue(d_hashes, d_counts, n, stride, k, ctypes.c_float(min_ani), d_hi,

@@ -618,6 +618,26 @@ int galah_b200_blocklist_build(const uint64_t *d_hashes, const uint32_t *d_count
                            d_lo, d_tags, d_len, (cudaStream_t)stream);
 }
 
+int galah_b200_table_max_device(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                                unsigned long long *d_max, void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (stride == 0 || n >= 0x7FFFFFFFull || !d_max) { set_error("table_max: bad arguments"); return GALAH_B200_ERR_ARG; }
+    return table_max_enqueue(d_hashes, d_counts, n, stride, d_max, (cudaStream_t)stream);
+}
+
+int galah_b200_blocklist_build_local(const uint64_t *d_rows, const uint32_t *d_counts, size_t n_rows, size_t stride,
+                                     const unsigned long long *d_table_max, size_t n_blocks_out, uint32_t *d_hi,
+                                     uint32_t *d_lo, uint8_t *d_tags, uint32_t *d_len, void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (stride == 0 || (stride & 1) || !join_supported(stride)) { set_error("blocklist_build_local: unsupported stride"); return GALAH_B200_ERR_ARG; }
+    if (n_rows >= 0x7FFFFFFFull || !d_table_max) { set_error("blocklist_build_local: bad arguments"); return GALAH_B200_ERR_ARG; }
+    if (n_blocks_out * (size_t)GALAH_B200_ROW_BLOCK < n_rows) { set_error("blocklist_build_local: n_blocks_out does not cover the rows"); return GALAH_B200_ERR_ARG; }
+    return blocklist_build_local(g_ctx.pws, d_rows, d_counts, n_rows, stride, d_table_max, d_hi, d_lo, d_tags, d_len,
+                                 (uint32_t)n_blocks_out, (cudaStream_t)stream);
+}
+
 int galah_b200_prefilter_join_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
                                       uint8_t k, float min_ani, const uint32_t *d_hi, const uint32_t *d_lo,
                                       const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard,

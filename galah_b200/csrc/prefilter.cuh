@@ -120,6 +120,11 @@ void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries
 int blocklist_build(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                     size_t stride, uint32_t b0, uint32_t b1, uint32_t *d_hi, uint32_t *d_lo, uint8_t *d_tags,
                     uint32_t *d_len, cudaStream_t stream, bool gmax_ready = false);
+int table_max_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                      unsigned long long *d_max, cudaStream_t stream);
+int blocklist_build_local(PrefilterWorkspace &ws, const uint64_t *d_rows, const uint32_t *d_counts, size_t n_rows,
+                          size_t stride, const unsigned long long *d_gmax, uint32_t *d_hi, uint32_t *d_lo,
+                          uint8_t *d_tags, uint32_t *d_len, uint32_t n_blocks_out, cudaStream_t stream);
 int join_streamed_from_host(PrefilterWorkspace &ws, KernelParams &p, const uint64_t *h_hashes,
                             const uint32_t *h_counts, uint64_t *d_table, cudaStream_t compute, cudaStream_t copy,
                             int chunks, double wave_frac);

@@ -805,6 +805,30 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
 // ------------------------------------------------------------------------------------------
 bool join_supported(size_t stride) { return stride < 65536; }  // 16-bit pair counters
 
+// Largest valid hash of a (slice of a) sketch table -> *d_max (device scalar), no host sync.
+int table_max_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                      unsigned long long *d_max, cudaStream_t stream) {
+    GB_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), stream));
+    const uint32_t nb = (uint32_t)((n + kJR - 1) / kJR);
+    if (nb == 0) return 0;
+    bl_len_kernel<<<(uint32_t)(((uint64_t)nb * 32 + 255) / 256), 256, 0, stream>>>(
+        d_hashes, d_counts, (uint32_t)n, (uint32_t)stride, 0, nb, 0, 0, nullptr, d_max);
+    GB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Block lists of a LOCAL slice of rows (the slice starts at a multiple of kShardRows rows of the
+// global table, so local and global row tags agree) with the table-wide largest hash supplied by
+// the caller (device scalar; at G ranks: an all-reduce MAX of table_max_enqueue's results).
+int blocklist_build_local(PrefilterWorkspace &ws, const uint64_t *d_rows, const uint32_t *d_counts, size_t n_rows,
+                          size_t stride, const unsigned long long *d_gmax, uint32_t *d_hi, uint32_t *d_lo,
+                          uint8_t *d_tags, uint32_t *d_len, uint32_t n_blocks_out, cudaStream_t stream) {
+    if (!ws.d_gmax) GB_CUDA(cudaMalloc(&ws.d_gmax, sizeof(unsigned long long)));
+    GB_CUDA(cudaMemcpyAsync(ws.d_gmax, d_gmax, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+    return blocklist_build(ws, d_rows, d_counts, n_rows, stride, 0, n_blocks_out, d_hi, d_lo, d_tags, d_len, stream,
+                           /*gmax_ready=*/true);
+}
+
 void blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_t *entries_per_block, size_t *slack) {
     *n_blocks = (n + kJR - 1) / kJR;
     *entries_per_block = (size_t)kJR * stride;

@@ -71,11 +71,16 @@ def gpu_shard_fn(gb):
 
 
 class ShardedPrefilter:
-    """The N-GPU stage-1 prefilter behind one call (the public multi-GPU API; bench.py's `e2e` at
-    --gpus > 1): every rank passes ITS slice of the sketch table in host memory; per call the rank
-    uploads the slice (H2D), the table is all-gathered over NVLink, every rank builds 1/G of the
-    block lists, the lists are all-gathered, every rank joins its row-block shard and finishes its
-    candidates on the host.  Buffers are allocated once and re-used."""
+    """The N-GPU stage-1 prefilter behind one call (the public multi-GPU API; bench.py's `value` and
+    `e2e` at --gpus > 1): every rank passes ITS slice of the sketch table; per call the rank uploads
+    the slice (H2D), builds the block lists of its own rows, the lists are all-gathered over NVLink,
+    every rank joins its row-block shard and finishes its candidates on the host.
+
+    When the slice is a whole number of row blocks (n_local % ROW_BLOCK == 0) the build needs no
+    gathered table: the ranks agree on the table-wide largest hash with one 8-byte all-reduce, and
+    the all-gather of the sketch table (the join needs it for the survivors' exact `total`) runs
+    on NCCL's stream WHILE the lists are built.  Otherwise the table is gathered first and every
+    rank builds 1/G of the blocks from it.  Buffers are allocated once and re-used."""
 
     def __init__(self, gb, dist, n_local, stride, device):
         import torch
@@ -89,7 +94,8 @@ class ShardedPrefilter:
         self.table = t.empty((n, stride), dtype=t.int64, device=device)
         self.counts = t.empty(n, dtype=t.int32, device=device)
         nb, epb, slack = gb.blocklist_layout(n, stride)
-        self.nbp = nbp = (nb + self.world - 1) // self.world
+        self.local_build = n_local % ROW_BLOCK == 0
+        self.nbp = nbp = n_local // ROW_BLOCK if self.local_build else (nb + self.world - 1) // self.world
         self.epb = epb
         self.my_hi = t.empty(nbp * epb, dtype=t.int32, device=device)
         self.my_lo = t.empty_like(self.my_hi)
@@ -99,35 +105,60 @@ class ShardedPrefilter:
         self.all_lo = t.zeros_like(self.all_hi)
         self.all_tags = t.zeros(self.world * nbp * epb + slack, dtype=t.uint8, device=device)
         self.all_len = t.empty(self.world * nbp, dtype=t.int32, device=device)
+        self.gmax = t.zeros(1, dtype=t.int64, device=device)  # uint64 bits of the largest valid hash
         self.cand_cap = max(1 << 20, 64 * n)
         self.d_cand = t.empty((self.cand_cap, 4), dtype=t.int32, device=device)
         self.d_ncand = t.zeros(1, dtype=t.int64, device=device)
         self.h_cand = t.empty((self.cand_cap, 4), dtype=t.int32).pin_memory()
 
-    def __call__(self, h_table, h_counts, k=21, min_ani=0.9):
-        """h_table / h_counts: this rank's slice as (pinned) host torch tensors (int64 / int32 views of
-        the uint64 / uint32 data).  Returns this rank's PAIR_DTYPE records, sorted by (i, j)."""
+    def step_device(self, k=21, min_ani=0.9):
+        """Everything after the upload, enqueued on the current stream: my_table / my_counts (device)
+        -> candidates in d_cand / d_ncand.  No host synchronisation."""
         t, gb, dist = self.torch, self.gb, self.dist
         st = t.cuda.current_stream().cuda_stream
         n, s, w, r = self.n, self.s, self.world, self.rank
-        self.my_table.copy_(h_table, non_blocking=True)
-        self.my_counts.copy_(h_counts, non_blocking=True)
-        dist.all_gather_into_tensor(self.table, self.my_table)
-        dist.all_gather_into_tensor(self.counts, self.my_counts)
-        gb.blocklist_build(self.table.data_ptr(), self.counts.data_ptr(), n, s, r * self.nbp, (r + 1) * self.nbp,
-                           self.my_hi.data_ptr(), self.my_lo.data_ptr(), self.my_tags.data_ptr(),
-                           self.my_len.data_ptr(), st)
         m = w * self.nbp * self.epb
-        dist.all_gather_into_tensor(self.all_hi[:m], self.my_hi)
-        dist.all_gather_into_tensor(self.all_lo[:m], self.my_lo)
-        dist.all_gather_into_tensor(self.all_tags[:m], self.my_tags)
-        dist.all_gather_into_tensor(self.all_len, self.my_len)
+        if self.local_build:
+            gb.table_max_device(self.my_table.data_ptr(), self.my_counts.data_ptr(), self.n_local, s,
+                                self.gmax.data_ptr(), st)
+            # the collective compares int64: flipping the top bit maps unsigned order onto signed order
+            self.gmax.bitwise_xor_(-(1 << 63))
+            dist.all_reduce(self.gmax, op=dist.ReduceOp.MAX)
+            self.gmax.bitwise_xor_(-(1 << 63))
+            work_t = dist.all_gather_into_tensor(self.table, self.my_table, async_op=True)
+            work_c = dist.all_gather_into_tensor(self.counts, self.my_counts, async_op=True)
+            gb.blocklist_build_local(self.my_table.data_ptr(), self.my_counts.data_ptr(), self.n_local, s,
+                                     self.gmax.data_ptr(), self.nbp, self.my_hi.data_ptr(), self.my_lo.data_ptr(),
+                                     self.my_tags.data_ptr(), self.my_len.data_ptr(), st)
+            dist.all_gather_into_tensor(self.all_hi[:m], self.my_hi)
+            dist.all_gather_into_tensor(self.all_lo[:m], self.my_lo)
+            dist.all_gather_into_tensor(self.all_tags[:m], self.my_tags)
+            dist.all_gather_into_tensor(self.all_len, self.my_len)
+            work_t.wait()
+            work_c.wait()
+        else:
+            dist.all_gather_into_tensor(self.table, self.my_table)
+            dist.all_gather_into_tensor(self.counts, self.my_counts)
+            gb.blocklist_build(self.table.data_ptr(), self.counts.data_ptr(), n, s, r * self.nbp, (r + 1) * self.nbp,
+                               self.my_hi.data_ptr(), self.my_lo.data_ptr(), self.my_tags.data_ptr(),
+                               self.my_len.data_ptr(), st)
+            dist.all_gather_into_tensor(self.all_hi[:m], self.my_hi)
+            dist.all_gather_into_tensor(self.all_lo[:m], self.my_lo)
+            dist.all_gather_into_tensor(self.all_tags[:m], self.my_tags)
+            dist.all_gather_into_tensor(self.all_len, self.my_len)
         gb.prefilter_join_enqueue(self.table.data_ptr(), self.counts.data_ptr(), n, s, k, min_ani,
                                   self.all_hi.data_ptr(), self.all_lo.data_ptr(), self.all_tags.data_ptr(),
                                   self.all_len.data_ptr(), r, w, st, self.d_cand.data_ptr(), self.cand_cap,
                                   self.d_ncand.data_ptr())
+
+    def __call__(self, h_table, h_counts, k=21, min_ani=0.9):
+        """h_table / h_counts: this rank's slice as (pinned) host torch tensors (int64 / int32 views of
+        the uint64 / uint32 data).  Returns this rank's PAIR_DTYPE records, sorted by (i, j)."""
+        self.my_table.copy_(h_table, non_blocking=True)
+        self.my_counts.copy_(h_counts, non_blocking=True)
+        self.step_device(k, min_ani)
         got = int(self.d_ncand.item())  # D2H + sync
         if got > self.cand_cap:
             raise RuntimeError("candidate buffer too small")
         self.h_cand[:got].copy_(self.d_cand[:got])
-        return gb.finish_candidates(self.h_cand[:got].numpy().view(np.uint32), k, min_ani)
+        return self.gb.finish_candidates(self.h_cand[:got].numpy().view(np.uint32), k, min_ani)

@@ -153,6 +153,18 @@ int galah_b200_blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_
 int galah_b200_blocklist_build(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                                size_t stride, size_t block_begin, size_t block_end, uint32_t *d_hi,
                                uint32_t *d_lo, uint8_t *d_tags, uint32_t *d_len, void *stream);
+/* Multi-GPU form that needs no gathered table for the build: every rank holds a slice of whole
+ * row blocks (its first row a multiple of GALAH_B200_ROW_BLOCK).  table_max: largest valid hash
+ * of the slice -> *d_max (device uint64; combine across ranks with an all-reduce MAX).
+ * build_local: the lists of the slice's blocks (n_blocks_out >= ceil(n_rows / ROW_BLOCK); surplus
+ * blocks come out empty) with the table-wide maximum supplied in *d_table_max, slice-based
+ * outputs as above.  The table all-gather can then overlap the build. */
+int galah_b200_table_max_device(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                                unsigned long long *d_max, void *stream);
+int galah_b200_blocklist_build_local(const uint64_t *d_rows, const uint32_t *d_counts, size_t n_rows,
+                                     size_t stride, const unsigned long long *d_table_max,
+                                     size_t n_blocks_out, uint32_t *d_hi, uint32_t *d_lo, uint8_t *d_tags,
+                                     uint32_t *d_len, void *stream);
 int galah_b200_prefilter_join_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                                       size_t stride, uint8_t k, float min_ani, const uint32_t *d_hi,
                                       const uint32_t *d_lo, const uint8_t *d_tags,

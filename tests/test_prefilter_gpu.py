@@ -161,8 +161,11 @@ def test_sliced_blocklist_build_then_join_matches(gb, kernel_mode):
     assert got.shape == exp.shape and np.array_equal(got, exp) and len(exp) > 0
 
 
-def test_sharded_prefilter_driver_single_rank(gb, kernel_mode):
-    """galah_b200.distributed.ShardedPrefilter (the multi-GPU public API) on a 1-rank NCCL group."""
+@pytest.mark.parametrize("n,top_bit", [(400, False), (512, False), (640, True)])
+def test_sharded_prefilter_driver_single_rank(gb, kernel_mode, n, top_bit):
+    """galah_b200.distributed.ShardedPrefilter (the multi-GPU public API) on a 1-rank NCCL group:
+    n = 400 takes the gather-first path, multiples of the row block build from the local slice with
+    the all-reduced largest hash (a hash with the top bit set checks the unsigned MAX)."""
     if kernel_mode != 0:
         pytest.skip("driver uses the join path")
     import torch
@@ -171,10 +174,13 @@ def test_sharded_prefilter_driver_single_rank(gb, kernel_mode):
     if not dist.is_initialized():
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
                                 device_id=torch.device("cuda", 0))
-    rng = np.random.default_rng(47)
-    n, s = 400, 1000
-    table, counts = random_family_table(n, s, rng)
+    rng = np.random.default_rng(47 + n)
+    s = 1000
+    table, counts = random_family_table(n, s, rng, hi_bits=64 if top_bit else 53)
+    if top_bit:
+        assert int(table[counts > 0].max()) >> 63 == 1 or int(table[table != PAD].max()) >> 63 == 1
     sp = ShardedPrefilter(gb, dist, n, s, torch.device("cuda", 0))
+    assert sp.local_build == (n % gb.ROW_BLOCK == 0)
     h_t = torch.from_numpy(table.view(np.int64)).pin_memory()
     h_c = torch.from_numpy(counts.view(np.int32)).pin_memory()
     for _ in range(2):
