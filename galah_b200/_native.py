@@ -119,6 +119,10 @@ _SIGNATURES = {
     "galah_b200_cluster_files_skani": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                       ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),
+    "galah_b200_device_ingest": (ctypes.c_int, [ctypes.c_int]),
+    "galah_b200_decode_fasta_device": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_size_t),
+                                                      ctypes.c_size_t] + [ctypes.POINTER(u32p)] * 2 +
+                                       [ctypes.POINTER(u64p)] * 7 + [f32p]),
     "galah_b200_pack_fasta_file": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(u32p), ctypes.POINTER(u32p), u64p,
                                                   ctypes.POINTER(u64p), ctypes.POINTER(u64p), sizep]),
     "galah_b200_genome_stats": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_int, vp]),

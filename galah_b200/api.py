@@ -402,6 +402,58 @@ def pack_fasta_file(path):
     return codes, starts, ends
 
 
+def device_ingest(enable=-1):
+    """K0 switch: decode FASTA bytes on the device (1, default) or pack on host threads (0);
+    < 0 only queries.  Returns the previous setting."""
+    return int(lib().galah_b200_device_ingest(int(enable)))
+
+
+def decode_fasta_device(files, unpack=True):
+    """K0 parity hook: a list of in-memory FASTA files (bytes) -> per file (codes uint8 per base:
+    0..3 = ACGT, 4 = invalid; rec_start; rec_end; n_ambiguous; n_N), decoded on the device, plus the
+    device time in ms.  unpack=False skips the per-base unpacking (timing runs)."""
+    n = len(files)
+    arr = (ctypes.c_char_p * n)(*files)
+    lens = (ctypes.c_size_t * n)(*[len(f) for f in files])
+    seq2, valid = _native.u32p(), _native.u32p()
+    ptrs = [_native.u64p() for _ in range(7)]
+    ms = ctypes.c_float(0)
+    check(lib().galah_b200_decode_fasta_device(arr, lens, n, ctypes.byref(seq2), ctypes.byref(valid),
+                                               *[ctypes.byref(p) for p in ptrs], ctypes.byref(ms)))
+    base_off, n_bases, rec_off, rec_start, rec_end, n_amb, n_N = ptrs
+    try:
+        bo = np.ctypeslib.as_array(base_off, shape=(n + 1,)).copy()
+        nb = np.ctypeslib.as_array(n_bases, shape=(max(n, 1),))[:n].copy()
+        ro = np.ctypeslib.as_array(rec_off, shape=(n + 1,)).copy()
+        nrec = int(ro[-1])
+        rs = np.ctypeslib.as_array(rec_start, shape=(max(nrec, 1),))[:nrec].copy()
+        re_ = np.ctypeslib.as_array(rec_end, shape=(max(nrec, 1),))[:nrec].copy()
+        amb = np.ctypeslib.as_array(n_amb, shape=(max(n, 1),))[:n].copy()
+        nn = np.ctypeslib.as_array(n_N, shape=(max(n, 1),))[:n].copy()
+        total = int(bo[-1])
+        w2 = np.ctypeslib.as_array(seq2, shape=(total // 16 + 4,)).astype(np.uint32)
+        wv = np.ctypeslib.as_array(valid, shape=(total // 32 + 4,)).astype(np.uint32)
+        out = []
+        for f in range(n):
+            if not unpack:
+                out.append({"n_bases": int(nb[f]), "n_records": int(ro[f + 1] - ro[f]), "n_ambiguous": int(amb[f]),
+                            "n_N": int(nn[f])})
+                continue
+            idx = np.arange(int(bo[f]), int(bo[f]) + int(nb[f]), dtype=np.uint64)
+            codes = ((w2[idx >> np.uint64(4)] >> (np.uint32(2) * (idx & np.uint64(15)).astype(np.uint32))) & np.uint32(3)).astype(np.uint8)
+            ok = ((wv[idx >> np.uint64(5)] >> (idx & np.uint64(31)).astype(np.uint32)) & np.uint32(1)).astype(bool)
+            codes[~ok] = 4
+            # nothing may be set in the padding up to the next multiple of 128
+            pad = np.arange(int(bo[f]) + int(nb[f]), int(bo[f + 1]), dtype=np.uint64)
+            pad_bits = (wv[pad >> np.uint64(5)] >> (pad & np.uint64(31)).astype(np.uint32)) & np.uint32(1)
+            out.append({"codes": codes, "rec_start": rs[int(ro[f]):int(ro[f + 1])], "rec_end": re_[int(ro[f]):int(ro[f + 1])],
+                        "n_ambiguous": int(amb[f]), "n_N": int(nn[f]), "padding_clean": not pad_bits.any()})
+    finally:
+        for ptr in [seq2, valid] + ptrs:
+            lib().galah_b200_free(ptr)
+    return out, float(ms.value)
+
+
 GENOME_STATS_DTYPE = np.dtype([("num_contigs", "<u8"), ("num_ambiguous_bases", "<u8"), ("n50", "<u8")])
 
 

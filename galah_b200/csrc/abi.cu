@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "host/cluster_engine.hpp"
 #include "host/fasta.hpp"
+#include "ingest.cuh"
 #include "prefilter.cuh"
 #include "sketch.cuh"
 
@@ -36,6 +37,9 @@ struct Context {
     int prefilter_mode = 0;
     PrefilterWorkspace pws;
     SketchWorkspace sws;
+    FastaDecoder fasta;
+    uint8_t *h_raw = nullptr; size_t cap_raw = 0;  // pinned staging of raw file bytes for K0
+    int device_ingest = 1;               // K0: decode FASTA bytes on the device (0 = host packer)
     // buffers re-used across host-pointer prefilter calls (cudaMalloc is a device-wide sync)
     uint64_t *d_table = nullptr; size_t cap_table = 0;
     uint32_t *d_counts = nullptr; size_t cap_counts = 0;
@@ -50,7 +54,9 @@ struct Context {
     size_t cap_cand_map = 0;
     cudaEvent_t ev_done = nullptr;
     int release() {
-        pws.release(); sws.release();
+        pws.release(); sws.release(); fasta.release();
+        if (h_raw) cudaFreeHost(h_raw);
+        h_raw = nullptr; cap_raw = 0;
         cudaFree(d_table); cudaFree(d_counts); cudaFree(d_cand); cudaFree(d_n_cand);
         if (h_stage) cudaFreeHost(h_stage);
         if (h_cand_map) cudaFreeHost(h_cand_map);
@@ -265,6 +271,41 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
     return rc;
 }
 
+// Raw bytes of a batch of files laid out for K0: every file starts at a multiple of 32.
+struct RawBatch {
+    uint8_t *bytes = nullptr;  // pinned staging buffer owned by the context (re-used across batches)
+    std::vector<uint64_t> file_off, file_len, first_byte;
+    bool all_fasta = true;  // every non-empty file starts (after blank lines) with '>'
+};
+
+static int stage_raw(const std::vector<std::vector<uint8_t>> &files, RawBatch &rb) {
+    const size_t n = files.size();
+    rb.file_off.assign(n + 1, 0); rb.file_len.assign(n, 0); rb.first_byte.assign(n, 0);
+    for (size_t f = 0; f < n; f++) {
+        rb.file_len[f] = files[f].size();
+        rb.file_off[f + 1] = (rb.file_off[f] + files[f].size() + 31) / 32 * 32;
+    }
+    const size_t need = rb.file_off[n] + 64;
+    if (g_ctx.cap_raw < need) {
+        if (g_ctx.h_raw) GB_CUDA(cudaFreeHost(g_ctx.h_raw));
+        g_ctx.h_raw = nullptr; g_ctx.cap_raw = 0;
+        const size_t want = need + need / 4;
+        GB_CUDA(cudaMallocHost(&g_ctx.h_raw, want));
+        g_ctx.cap_raw = want;
+    }
+    rb.bytes = g_ctx.h_raw;
+    rb.all_fasta = true;
+    for (size_t f = 0; f < n; f++) {
+        if (!files[f].empty()) memcpy(rb.bytes + rb.file_off[f], files[f].data(), files[f].size());
+        memset(rb.bytes + rb.file_off[f] + files[f].size(), '\n', rb.file_off[f + 1] - rb.file_off[f] - files[f].size());
+        size_t p = 0;
+        while (p < files[f].size() && (files[f][p] == '\n' || files[f][p] == '\r')) p++;
+        rb.first_byte[f] = rb.file_off[f] + p;
+        if (p < files[f].size() && files[f][p] != '>') rb.all_fasta = false;
+    }
+    return 0;
+}
+
 // One pass over FASTA files feeding K1 (sketches) and/or the K3 index from the SAME upload:
 // files are parsed and packed on host threads, a batch is concatenated (genome offsets multiples
 // of 128), copied to the device once, and handed to the requested sinks.
@@ -286,13 +327,132 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
     const uint64_t kMaxBatchBases = 2ull << 30;
     cudaStream_t st = g_ctx.stream;
     size_t done = 0;
+
+    // Hands one batch that is resident on the device in the K1 / K3 layout to the requested sinks.
+    // unit_first: index of the batch's first unit among all units ingested so far.
+    auto feed = [&](const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_off, size_t nb,
+                    const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
+                    const std::vector<uint32_t> &cs, const std::vector<uint32_t> &cl, uint64_t longest,
+                    size_t unit_first, size_t files_done) -> int {
+        if (sinks.sketch) {
+            DevBuf<uint64_t> d_hashes;
+            DevBuf<uint32_t> d_counts;
+            if (d_hashes.alloc(nb * (size_t)sinks.s) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
+            int rc = sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, sinks.k, sinks.s, sinks.seed, d_hashes.p,
+                                    d_counts.p, sinks.s, st);
+            if (rc) return rc;
+            GB_CUDA(cudaMemcpyAsync(sinks.hashes + unit_first * (size_t)sinks.s, d_hashes.p, nb * (size_t)sinks.s * 8,
+                                    cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaMemcpyAsync(sinks.counts + unit_first, d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+        }
+        if (sinks.markers) {
+            uint32_t cap = 256;
+            while (cap < 16384 && cap < 1.5 * (double)longest / sinks.c_marker + 256.0) cap <<= 1;
+            DevBuf<uint64_t> d_rows;
+            DevBuf<uint32_t> d_counts;
+            if (d_rows.alloc(nb * (size_t)cap) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
+            int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, 21, sinks.c_marker, cap, d_rows.p,
+                                           d_counts.p, st);
+            if (rc) return rc;
+            std::vector<uint64_t> rows(nb * (size_t)cap);
+            std::vector<uint32_t> cnt(nb);
+            GB_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * 8, cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaMemcpyAsync(cnt.data(), d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+            for (size_t x = 0; x < nb; x++) {
+                if (cnt[x] == 0xFFFFFFFFu) {
+                    set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
+                    return GALAH_B200_ERR_UNSUPPORTED;
+                }
+                sinks.markers->emplace_back(rows.begin() + x * (size_t)cap, rows.begin() + x * (size_t)cap + cnt[x]);
+            }
+        }
+        if (sinks.ani) {
+            const size_t before = sinks.ani->size();
+            int rc = sinks.ani->add_packed_device(d_seq2, d_valid, d_off, nb, base_off, contig_off, cs, cl, st);
+            if (rc) return rc;
+            // first batch of a larger run: size the index once for everything still to come
+            // (units per file as seen so far; exact for whole-genome units)
+            if (before == 0 && files_done < n) {
+                const double per_file = (double)sinks.n_units / (double)std::max<size_t>(files_done, 1);
+                if (int rc2 = sinks.ani->reserve_for((size_t)(per_file * (double)n) + 1, st)) return rc2;
+            }
+        }
+        GB_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    };
+
     while (done < n) {
         const size_t want = std::min(kMaxBatchGenomes, n - done);
-        std::vector<PackedGenome> batch(want);
-        std::vector<std::vector<PackedGenome>> per_file(sinks.per_record ? want : 0);
         std::vector<std::string> errs(want);
         std::vector<int> rcs(want, 0);
         std::atomic<size_t> next{0};
+        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
+
+        // ---- K0 path (whole-genome units): host threads only read (and inflate) the files; the
+        // raw bytes cross PCIe once and are decoded on the device (csrc/ingest.cu)
+        if (!sinks.per_record && g_ctx.device_ingest) {
+            std::vector<std::vector<uint8_t>> raw(want);
+            auto reader = [&]() {
+                for (;;) {
+                    size_t x = next.fetch_add(1);
+                    if (x >= want) break;
+                    rcs[x] = read_file_bytes(paths[done + x], raw[x], errs[x]);
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; t++) th.emplace_back(reader);
+            reader();
+            for (auto &t : th) t.join();
+            for (size_t x = 0; x < want; x++)
+                if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
+            bool all_fasta = true;
+            for (size_t x = 0; x < want && all_fasta; x++) {
+                size_t p = 0;
+                while (p < raw[x].size() && (raw[x][p] == '\n' || raw[x][p] == '\r')) p++;
+                if (p < raw[x].size() && raw[x][p] != '>') all_fasta = false;
+            }
+            if (all_fasta) {
+                const size_t unit0 = sinks.n_units;
+                sinks.n_units += want;
+                size_t b0 = 0;
+                while (b0 < want) {  // sub-batches of at most ~2 GiB of raw bytes
+                    size_t b1 = b0; uint64_t bytes = 0;
+                    while (b1 < want && (b1 == b0 || bytes + raw[b1].size() + 32 <= kMaxBatchBases)) { bytes += raw[b1].size() + 32; b1++; }
+                    const size_t nb = b1 - b0;
+                    RawBatch rb;
+                    if (int rc = stage_raw(std::vector<std::vector<uint8_t>>(std::make_move_iterator(raw.begin() + b0),
+                                                                            std::make_move_iterator(raw.begin() + b1)), rb))
+                        return rc;
+                    DecodedFiles dec;
+                    if (int rc = g_ctx.fasta.decode(rb.bytes, rb.file_off, rb.file_len, rb.first_byte, dec, st)) return rc;
+                    std::vector<uint64_t> contig_off(nb + 1, 0);
+                    std::vector<uint32_t> cs, cl;
+                    uint64_t longest = 0;
+                    for (size_t x = 0; x < nb; x++) {
+                        for (uint64_t r = dec.rec_off[x]; r < dec.rec_off[x + 1]; r++) {
+                            cs.push_back((uint32_t)dec.rec_start[r]);
+                            cl.push_back((uint32_t)(dec.rec_end[r] - dec.rec_start[r]));
+                        }
+                        contig_off[x + 1] = cs.size();
+                        longest = std::max(longest, dec.n_bases[x]);
+                    }
+                    if (int rc = feed(dec.d_seq2, dec.d_valid, dec.d_base_off, nb, dec.base_off, contig_off, cs, cl, longest,
+                                      unit0 + b0, done + b1))
+                        return rc;
+                    b0 = b1;
+                }
+                done += want;
+                continue;
+            }
+            // FASTQ (or anything else the host packer understands) in this batch: pack on the host below
+            next = 0;
+        }
+
+        // ---- host packer path (contig mode, FASTQ input, or device ingest switched off)
+        std::vector<PackedGenome> batch(want);
+        std::vector<std::vector<PackedGenome>> per_file(sinks.per_record ? want : 0);
         auto worker = [&]() {
             for (;;) {
                 size_t x = next.fetch_add(1);
@@ -302,7 +462,6 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
             }
         };
         std::vector<std::thread> th;
-        const int nt = (int)std::min<size_t>((size_t)host_threads, want);
         for (int t = 1; t < nt; t++) th.emplace_back(worker);
         worker();
         for (auto &t : th) t.join();
@@ -324,6 +483,7 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
             const size_t nb = b1 - b0;
             std::vector<uint64_t> base_off(nb + 1, 0), contig_off(nb + 1, 0);
             std::vector<uint32_t> cs, cl;
+            uint64_t longest = 0;
             for (size_t x = 0; x < nb; x++) {
                 const PackedGenome &pg = batch[b0 + x];
                 base_off[x + 1] = base_off[x] + pg.padded_bases();
@@ -332,6 +492,7 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
                     cl.push_back((uint32_t)(pg.rec_end[r] - pg.rec_start[r]));
                 }
                 contig_off[x + 1] = cs.size();
+                longest = std::max<uint64_t>(longest, pg.n_bases);
             }
             const uint64_t total = base_off[nb];
             std::vector<uint32_t> seq2(total / 16 + 4, 0u), valid(total / 32 + 4, 0u);
@@ -346,54 +507,8 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
             GB_CUDA(cudaMemcpyAsync(d_seq2.p, seq2.data(), seq2.size() * 4, cudaMemcpyHostToDevice, st));
             GB_CUDA(cudaMemcpyAsync(d_valid.p, valid.data(), valid.size() * 4, cudaMemcpyHostToDevice, st));
             GB_CUDA(cudaMemcpyAsync(d_off.p, base_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
-            if (sinks.sketch) {
-                DevBuf<uint64_t> d_hashes;
-                DevBuf<uint32_t> d_counts;
-                if (d_hashes.alloc(nb * (size_t)sinks.s) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
-                int rc = sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, nb, sinks.k, sinks.s, sinks.seed,
-                                        d_hashes.p, d_counts.p, sinks.s, st);
-                if (rc) return rc;
-                GB_CUDA(cudaMemcpyAsync(sinks.hashes + (unit0 + b0) * (size_t)sinks.s, d_hashes.p,
-                                        nb * (size_t)sinks.s * 8, cudaMemcpyDeviceToHost, st));
-                GB_CUDA(cudaMemcpyAsync(sinks.counts + unit0 + b0, d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
-                GB_CUDA(cudaStreamSynchronize(st));
-            }
-            if (sinks.markers) {
-                uint64_t longest = 0;
-                for (size_t x = 0; x < nb; x++) longest = std::max<uint64_t>(longest, batch[b0 + x].n_bases);
-                uint32_t cap = 256;
-                while (cap < 16384 && cap < 1.5 * (double)longest / sinks.c_marker + 256.0) cap <<= 1;
-                DevBuf<uint64_t> d_rows;
-                DevBuf<uint32_t> d_counts;
-                if (d_rows.alloc(nb * (size_t)cap) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
-                int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2.p, d_valid.p, d_off.p, nb, 21, sinks.c_marker, cap,
-                                               d_rows.p, d_counts.p, st);
-                if (rc) return rc;
-                std::vector<uint64_t> rows(nb * (size_t)cap);
-                std::vector<uint32_t> cnt(nb);
-                GB_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * 8, cudaMemcpyDeviceToHost, st));
-                GB_CUDA(cudaMemcpyAsync(cnt.data(), d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
-                GB_CUDA(cudaStreamSynchronize(st));
-                for (size_t x = 0; x < nb; x++) {
-                    if (cnt[x] == 0xFFFFFFFFu) {
-                        set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
-                        return GALAH_B200_ERR_UNSUPPORTED;
-                    }
-                    sinks.markers->emplace_back(rows.begin() + x * (size_t)cap, rows.begin() + x * (size_t)cap + cnt[x]);
-                }
-            }
-            if (sinks.ani) {
-                const size_t before = sinks.ani->size();
-                int rc = sinks.ani->add_packed_device(d_seq2.p, d_valid.p, d_off.p, nb, base_off, contig_off, cs, cl, st);
-                if (rc) return rc;
-                // first batch of a larger run: size the index once for everything still to come
-                // (units per file as seen so far; exact for whole-genome units)
-                if (before == 0 && done + want < n) {
-                    const double per_file = (double)sinks.n_units / (double)(done + want);
-                    if (int rc2 = sinks.ani->reserve_for((size_t)(per_file * (double)n) + 1, st)) return rc2;
-                }
-            }
-            GB_CUDA(cudaStreamSynchronize(st));
+            if (int rc = feed(d_seq2.p, d_valid.p, d_off.p, nb, base_off, contig_off, cs, cl, longest, unit0 + b0, done + want))
+                return rc;
             b0 = b1;
         }
         done += want;
@@ -1002,6 +1117,48 @@ int galah_b200_pack_fasta_file(const char *path, uint32_t **seq2, uint32_t **val
     *rec_end = (uint64_t *)dup(pg.rec_end.data(), pg.rec_end.size() * 8);
     *n_bases = pg.n_bases; *n_records = pg.rec_start.size();
     return 0;
+}
+
+// K0 parity / measurement hook: decode a batch of in-memory FASTA files on the device and return
+// the packed arrays (host copies) with the per-file metadata -- compared bit for bit with the
+// host packer (galah_b200_pack_fasta_file) by the tests.
+int galah_b200_decode_fasta_device(const uint8_t *const *files, const size_t *lens, size_t n, uint32_t **seq2,
+                                   uint32_t **valid, uint64_t **base_off, uint64_t **n_bases, uint64_t **rec_off,
+                                   uint64_t **rec_start, uint64_t **rec_end, uint64_t **n_ambiguous, uint64_t **n_N,
+                                   float *device_ms) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    std::vector<std::vector<uint8_t>> raw(n);
+    for (size_t f = 0; f < n; f++) raw[f].assign(files[f], files[f] + lens[f]);
+    RawBatch rb;
+    if (int rc = stage_raw(raw, rb)) return rc;
+    if (!rb.all_fasta) { set_error("decode_fasta_device: a file does not start with '>'"); return GALAH_B200_ERR_UNSUPPORTED; }
+    DecodedFiles dec;
+    if (int rc = g_ctx.fasta.decode(rb.bytes, rb.file_off, rb.file_len, rb.first_byte, dec, g_ctx.stream)) return rc;
+    const uint64_t total = dec.base_off[n];
+    std::vector<uint32_t> h_seq2(total / 16 + 4, 0u), h_valid(total / 32 + 4, 0u);
+    GB_CUDA(cudaMemcpyAsync(h_seq2.data(), dec.d_seq2, (total / 16) * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    GB_CUDA(cudaMemcpyAsync(h_valid.data(), dec.d_valid, (total / 32) * 4, cudaMemcpyDeviceToHost, g_ctx.stream));
+    GB_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    auto dup = [](const void *src, size_t bytes) { void *p = malloc(std::max<size_t>(bytes, 8)); if (p && bytes) memcpy(p, src, bytes); return p; };
+    *seq2 = (uint32_t *)dup(h_seq2.data(), h_seq2.size() * 4);
+    *valid = (uint32_t *)dup(h_valid.data(), h_valid.size() * 4);
+    *base_off = (uint64_t *)dup(dec.base_off.data(), (n + 1) * 8);
+    *n_bases = (uint64_t *)dup(dec.n_bases.data(), n * 8);
+    *rec_off = (uint64_t *)dup(dec.rec_off.data(), (n + 1) * 8);
+    *rec_start = (uint64_t *)dup(dec.rec_start.data(), dec.rec_start.size() * 8);
+    *rec_end = (uint64_t *)dup(dec.rec_end.data(), dec.rec_end.size() * 8);
+    *n_ambiguous = (uint64_t *)dup(dec.n_ambiguous.data(), n * 8);
+    *n_N = (uint64_t *)dup(dec.n_N.data(), n * 8);
+    if (device_ms) *device_ms = g_ctx.fasta.last_ms;
+    return 0;
+}
+
+int galah_b200_device_ingest(int enable) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    const int prev = g_ctx.device_ingest;
+    if (enable >= 0) g_ctx.device_ingest = enable ? 1 : 0;
+    return prev;
 }
 
 int galah_b200_genome_stats(const char *const *paths, size_t n, int host_threads, galah_b200_genome_stats_t *out) {

@@ -1,0 +1,409 @@
+// Stage 0 (K0): FASTA bytes -> packed 2-bit sequence + validity bitmap on sm_100a.
+//
+// Semantics = csrc/host/fasta.cpp (needletail 0.5 parse_fastx + normalize(false) as finch uses
+// it, /root/reference/src/finch.rs:55-69): a record starts at a '>' that is the file's first
+// non-blank byte or follows '\n'; its header runs to the next '\n'; every other byte of the record
+// is sequence: ACGT / acgt / Uu -> 2-bit code, blank (space, tab, CR, LF) dropped, anything else an
+// ambiguous (invalid) base; one invalid separator base between records so no k-mer spans them.
+//
+// Whether a byte lies inside a header line depends on everything before it, so the work is
+// three passes over chunks of 8 kB (one CTA each, 32 bytes per thread held in registers):
+//   fasta_scan_kernel   per chunk: position of its last record start and of its last '\n'
+//                       (host: running maxima over a file's chunks -> "chunk starts inside a header")
+//   fasta_pack_kernel<false>  per chunk: bases, record starts, ambiguous, N  (host: prefix sums ->
+//                       every chunk's first base / record index, per-file totals, padded offsets)
+//   fasta_pack_kernel<true>   writes: a CTA assembles its <= 8192 bases in shared memory (atomicOr
+//                       on 2-bit fields) and ORs the words into the zero-filled output; record
+//                       starts/ends are written by the thread that sees the '>'.
+// Inside a chunk "in header" is H > N with H / N the running maxima (position + 1) of record
+// starts / newlines: a block-wide exclusive max-scan over the threads' 32-byte summaries.
+// Bound: HBM streaming (3 reads of the raw bytes + 0.375 B/base written); the two host round
+// trips carry 8-16 bytes per 8 kB chunk.
+#include "ingest.cuh"
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gb200 {
+
+constexpr int kDecThreads = 256;
+constexpr int kDecPer = 32;                       // bytes per thread
+constexpr int kDecChunk = kDecThreads * kDecPer;  // 8192 bytes per CTA
+
+__device__ __forceinline__ uint32_t norm_code(uint32_t b) {  // 0..3 base, 4 ambiguous, 5 dropped
+    if (b == ' ' || b == '\t' || b == '\r' || b == '\n') return 5u;
+    const uint32_t u = b & 0xDFu;  // upper-case; no non-letter byte maps onto a letter
+    return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : (u == 'T' || u == 'U') ? 3u : 4u;
+}
+
+struct DecParams {
+    const uint8_t *bytes;
+    const uint64_t *chunk_begin, *chunk_end;  // absolute byte range of every chunk (begin % 32 == 0)
+    const uint32_t *chunk_file;
+    const uint64_t *file_first;               // per file: absolute offset of its first non-blank byte
+    const uint8_t *chunk_in_header;           // chunk starts inside a header line
+    uint32_t *summ;                           // scan: [2c] last record start + 1, [2c+1] last '\n' + 1 (0 = none)
+    uint32_t *counts;                         // count: [4c..] bases, record starts, ambiguous, N
+    // write pass
+    const uint32_t *chunk_base0, *chunk_rec0; // bases / record starts of the file before the chunk
+    const uint64_t *base_off, *rec_off;       // per file
+    uint32_t *seq2, *valid;
+    uint64_t *rec_start, *rec_end;
+};
+
+// 32 bytes of this thread, as 8 words
+struct Bytes32 {
+    uint32_t w[8];
+    __device__ __forceinline__ uint32_t at(int k) const { return (w[k >> 2] >> (8 * (k & 3))) & 0xFFu; }
+};
+
+__device__ __forceinline__ Bytes32 load32(const uint8_t *p) {
+    Bytes32 b;
+    const uint4 a = *reinterpret_cast<const uint4 *>(p), c = *reinterpret_cast<const uint4 *>(p + 16);
+    b.w[0] = a.x; b.w[1] = a.y; b.w[2] = a.z; b.w[3] = a.w; b.w[4] = c.x; b.w[5] = c.y; b.w[6] = c.z; b.w[7] = c.w;
+    return b;
+}
+
+// Exclusive block scan (256 threads) of two running maxima, seeded with a carry.
+__device__ __forceinline__ void block_excl_max2(uint32_t h, uint32_t n, uint32_t carry_h, uint32_t carry_n,
+                                                uint32_t &ex_h, uint32_t &ex_n, uint32_t *s_tmp /* >= 16 */) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ih = h, in = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t uh = __shfl_up_sync(0xffffffffu, ih, o), un = __shfl_up_sync(0xffffffffu, in, o);
+        if (lane >= (uint32_t)o) { ih = max(ih, uh); in = max(in, un); }
+    }
+    if (lane == 31) { s_tmp[warp] = ih; s_tmp[8 + warp] = in; }
+    __syncthreads();
+    uint32_t ph = carry_h, pn = carry_n;
+    for (uint32_t w = 0; w < warp; w++) { ph = max(ph, s_tmp[w]); pn = max(pn, s_tmp[8 + w]); }
+    const uint32_t uh = __shfl_up_sync(0xffffffffu, ih, 1), un = __shfl_up_sync(0xffffffffu, in, 1);
+    ex_h = lane ? max(ph, uh) : ph;
+    ex_n = lane ? max(pn, un) : pn;
+    __syncthreads();
+}
+
+// Exclusive block scan (256 threads) of two counters.
+__device__ __forceinline__ void block_excl_sum2(uint32_t a, uint32_t b, uint32_t &ex_a, uint32_t &ex_b,
+                                                uint32_t *s_tmp /* >= 16 */) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ua = __shfl_up_sync(0xffffffffu, ia, o), ub = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= (uint32_t)o) { ia += ua; ib += ub; }
+    }
+    if (lane == 31) { s_tmp[warp] = ia; s_tmp[8 + warp] = ib; }
+    __syncthreads();
+    uint32_t pa = 0, pb = 0;
+    for (uint32_t w = 0; w < warp; w++) { pa += s_tmp[w]; pb += s_tmp[8 + w]; }
+    ex_a = pa + ia - a;
+    ex_b = pb + ib - b;
+    __syncthreads();
+}
+
+// Record start at absolute position p holding byte b?  (prev = byte at p - 1, read only if p > first)
+__device__ __forceinline__ bool is_record_start(uint32_t b, uint64_t p, uint64_t first, uint32_t prev) {
+    return b == '>' && (p == first || (p > first && prev == '\n'));
+}
+
+__global__ void __launch_bounds__(kDecThreads) fasta_scan_kernel(const DecParams q) {
+    __shared__ uint32_t s_h[8], s_n[8];
+    const uint32_t c = blockIdx.x, tid = threadIdx.x;
+    const uint64_t begin = q.chunk_begin[c], end = q.chunk_end[c];
+    const uint64_t first = q.file_first[q.chunk_file[c]];
+    const uint64_t p0 = begin + (uint64_t)tid * kDecPer;
+    uint32_t last_h = 0, last_n = 0;
+    if (p0 < end) {
+        const Bytes32 by = load32(q.bytes + p0);
+        uint32_t prev = p0 > first ? q.bytes[p0 - 1] : 0u;
+        const int lim = (int)min((uint64_t)kDecPer, end - p0);
+#pragma unroll
+        for (int k = 0; k < kDecPer; k++) {
+            if (k < lim) {
+                const uint32_t b = by.at(k);
+                const uint64_t p = p0 + k;
+                if (is_record_start(b, p, first, prev)) last_h = (uint32_t)p + 1u;
+                if (b == '\n') last_n = (uint32_t)p + 1u;
+                prev = b;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        last_h = max(last_h, __shfl_xor_sync(0xffffffffu, last_h, o));
+        last_n = max(last_n, __shfl_xor_sync(0xffffffffu, last_n, o));
+    }
+    if ((tid & 31) == 0) { s_h[tid >> 5] = last_h; s_n[tid >> 5] = last_n; }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t h = 0, n = 0;
+        for (int w = 0; w < 8; w++) { h = max(h, s_h[w]); n = max(n, s_n[w]); }
+        q.summ[2 * c] = h; q.summ[2 * c + 1] = n;
+    }
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(kDecThreads) fasta_pack_kernel(const DecParams q) {
+    __shared__ uint32_t s_tmp[16];
+    __shared__ uint32_t s_cnt[4];
+    __shared__ uint32_t s_seq[kWrite ? kDecChunk / 16 + 4 : 1];
+    __shared__ uint32_t s_val[kWrite ? kDecChunk / 32 + 4 : 1];
+    const uint32_t c = blockIdx.x, tid = threadIdx.x;
+    const uint64_t begin = q.chunk_begin[c], end = q.chunk_end[c];
+    const uint32_t f = q.chunk_file[c];
+    const uint64_t first = q.file_first[f];
+    const uint64_t p0 = begin + (uint64_t)tid * kDecPer;
+    const bool live = p0 < end;
+    const int lim = live ? (int)min((uint64_t)kDecPer, end - p0) : 0;
+    Bytes32 by;
+#pragma unroll
+    for (int k = 0; k < 8; k++) by.w[k] = 0;
+    uint32_t prev0 = 0;
+    if (live) { by = load32(q.bytes + p0); prev0 = p0 > first ? q.bytes[p0 - 1] : 0u; }
+    if (tid < 4) s_cnt[tid] = 0;
+    if (kWrite) {
+        for (uint32_t x = tid; x < kDecChunk / 16 + 4; x += kDecThreads) s_seq[x] = 0;
+        for (uint32_t x = tid; x < kDecChunk / 32 + 4; x += kDecThreads) s_val[x] = 0;
+    }
+    // ---- phase A: this thread's last record start / newline
+    uint32_t last_h = 0, last_n = 0;
+    {
+        uint32_t prev = prev0;
+#pragma unroll
+        for (int k = 0; k < kDecPer; k++) {
+            if (k < lim) {
+                const uint32_t b = by.at(k);
+                const uint64_t p = p0 + k;
+                if (is_record_start(b, p, first, prev)) last_h = (uint32_t)p + 1u;
+                if (b == '\n') last_n = (uint32_t)p + 1u;
+                prev = b;
+            }
+        }
+    }
+    // ---- phase B: running maxima before this thread (carry: the chunk starts inside a header)
+    uint32_t H0, N0;
+    block_excl_max2(last_h, last_n, q.chunk_in_header[c] ? (uint32_t)begin : 0u, 0u, H0, N0, s_tmp);
+    // ---- phase C: classify and count
+    uint32_t nb = 0, nrec = 0, namb = 0, nN = 0;
+    {
+        uint32_t H = H0, N = N0, prev = prev0;
+#pragma unroll
+        for (int k = 0; k < kDecPer; k++) {
+            if (k < lim) {
+                const uint32_t b = by.at(k);
+                const uint64_t p = p0 + k;
+                if (is_record_start(b, p, first, prev)) { H = (uint32_t)p + 1u; nrec++; }
+                const uint32_t code = norm_code(b);
+                if (H <= N && code != 5u) {
+                    nb++;
+                    if (code == 4u) { namb++; nN += (b == 'N' || b == 'n') ? 1u : 0u; }
+                }
+                if (b == '\n') N = (uint32_t)p + 1u;
+                prev = b;
+            }
+        }
+    }
+    if (!kWrite) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nb += __shfl_xor_sync(0xffffffffu, nb, o); nrec += __shfl_xor_sync(0xffffffffu, nrec, o);
+            namb += __shfl_xor_sync(0xffffffffu, namb, o); nN += __shfl_xor_sync(0xffffffffu, nN, o);
+        }
+        if ((tid & 31) == 0) {
+            atomicAdd(&s_cnt[0], nb); atomicAdd(&s_cnt[1], nrec); atomicAdd(&s_cnt[2], namb); atomicAdd(&s_cnt[3], nN);
+        }
+        __syncthreads();
+        if (tid < 4) q.counts[4 * c + tid] = s_cnt[tid];
+        return;
+    }
+    // ---- phase D: positions, then write
+    uint32_t eb, er;
+    block_excl_sum2(nb, nrec, eb, er, s_tmp);
+    const uint32_t cb0 = q.chunk_base0[c], cr0 = q.chunk_rec0[c];
+    const uint64_t off = q.base_off[f], roff = q.rec_off[f];
+    // every position this CTA writes is >= G0 and < G0 + kDecChunk + 1
+    const uint64_t G0 = off + cb0 + (cr0 ? cr0 - 1u : 0u);
+    const uint64_t ws0 = G0 >> 4, wv0 = G0 >> 5;
+    {
+        uint32_t H = H0, N = N0, prev = prev0;
+        uint64_t nbase = (uint64_t)cb0 + eb;  // bases of the file before the current byte
+        uint64_t r = (uint64_t)cr0 + er;      // record starts of the file before the current byte
+#pragma unroll
+        for (int k = 0; k < kDecPer; k++) {
+            if (k < lim) {
+                const uint32_t b = by.at(k);
+                const uint64_t p = p0 + k;
+                if (is_record_start(b, p, first, prev)) {
+                    H = (uint32_t)p + 1u;
+                    if (r > 0) q.rec_end[roff + r - 1] = nbase + (r - 1);
+                    q.rec_start[roff + r] = nbase + r;
+                    r++;
+                }
+                const uint32_t code = norm_code(b);
+                if (H <= N && code != 5u) {
+                    if (code < 4u) {
+                        const uint64_t G = off + nbase + (r - 1);
+                        atomicOr(&s_seq[(G >> 4) - ws0], code << (2u * ((uint32_t)G & 15u)));
+                        atomicOr(&s_val[(G >> 5) - wv0], 1u << ((uint32_t)G & 31u));
+                    }
+                    nbase++;
+                }
+                if (b == '\n') N = (uint32_t)p + 1u;
+                prev = b;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t x = tid; x < kDecChunk / 16 + 4; x += kDecThreads)
+        if (s_seq[x]) atomicOr(&q.seq2[ws0 + x], s_seq[x]);
+    for (uint32_t x = tid; x < kDecChunk / 32 + 4; x += kDecThreads)
+        if (s_val[x]) atomicOr(&q.valid[wv0 + x], s_val[x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------
+template <typename T>
+int FastaDecoder::Buf<T>::ensure(size_t n) {
+    n = std::max<size_t>(n, 1);
+    if (n <= cap) return 0;
+    if (p) GB_CUDA(cudaFree(p));
+    p = nullptr; cap = 0;
+    const size_t want = n + n / 8;
+    GB_CUDA(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+    return 0;
+}
+template <typename T>
+void FastaDecoder::Buf<T>::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+void FastaDecoder::release() {
+    d_bytes_.release(); d_inhdr_.release(); d_seq2_.release(); d_valid_.release(); d_chunk_file_.release();
+    d_summ_.release(); d_counts_.release(); d_chunk_base_.release(); d_chunk_rec_.release();
+    d_chunk_begin_.release(); d_chunk_end_.release(); d_file_first_.release(); d_base_off_.release();
+    d_rec_off_.release(); d_rec_start_.release(); d_rec_end_.release();
+    for (int x = 0; x < 2; x++) if (ev_[x]) { cudaEventDestroy(ev_[x]); ev_[x] = nullptr; }
+}
+FastaDecoder::~FastaDecoder() { release(); }
+
+int FastaDecoder::decode(const uint8_t *h_bytes, const std::vector<uint64_t> &file_off,
+                         const std::vector<uint64_t> &file_len, const std::vector<uint64_t> &first_byte,
+                         DecodedFiles &out, cudaStream_t st) {
+    const size_t nf = file_off.empty() ? 0 : file_off.size() - 1;
+    out = DecodedFiles();
+    out.n_bases.assign(nf, 0); out.n_ambiguous.assign(nf, 0); out.n_N.assign(nf, 0);
+    out.rec_off.assign(nf + 1, 0); out.base_off.assign(nf + 1, 0);
+    if (nf == 0) return 0;
+    if (first_byte.size() != nf || file_len.size() != nf) { set_error("fasta decode: first_byte size mismatch"); return 3; }
+    const uint64_t total = file_off[nf];
+    if (total >= 0xFFFF0000ull) { set_error("fasta decode: batch larger than 4 GiB"); return 3; }
+    for (size_t f = 0; f <= nf; f++)
+        if (file_off[f] % 32) { set_error("fasta decode: file offsets must be multiples of 32"); return 3; }
+    if (!ev_[0]) { GB_CUDA(cudaEventCreate(&ev_[0])); GB_CUDA(cudaEventCreate(&ev_[1])); }
+
+    // chunk table: every file cut into 8 kB chunks (a chunk never spans files)
+    std::vector<uint64_t> cbegin, cend;
+    std::vector<uint32_t> cfile;
+    std::vector<size_t> first_chunk(nf + 1, 0);
+    for (size_t f = 0; f < nf; f++) {
+        first_chunk[f] = cbegin.size();
+        const uint64_t file_end = file_off[f] + file_len[f];
+        if (file_end > file_off[f + 1]) { set_error("fasta decode: file longer than its slot"); return 3; }
+        for (uint64_t b = file_off[f]; b < file_end; b += kDecChunk) {
+            cbegin.push_back(b); cend.push_back(std::min<uint64_t>(b + kDecChunk, file_end)); cfile.push_back((uint32_t)f);
+        }
+    }
+    first_chunk[nf] = cbegin.size();
+    const size_t nc = cbegin.size();
+
+    if (d_bytes_.ensure(total + 64) || d_chunk_begin_.ensure(nc) || d_chunk_end_.ensure(nc) || d_chunk_file_.ensure(nc) ||
+        d_file_first_.ensure(nf) || d_summ_.ensure(2 * nc) || d_counts_.ensure(4 * nc) || d_inhdr_.ensure(nc) ||
+        d_chunk_base_.ensure(nc) || d_chunk_rec_.ensure(nc) || d_base_off_.ensure(nf + 1) || d_rec_off_.ensure(nf + 1))
+        return 2;
+    GB_CUDA(cudaEventRecord(ev_[0], st));
+    GB_CUDA(cudaMemcpyAsync(d_bytes_.p, h_bytes, total, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemsetAsync(d_bytes_.p + total, '\n', 64, st));
+    if (nc == 0) {
+        GB_CUDA(cudaMemsetAsync(d_base_off_.p, 0, (nf + 1) * 8, st));
+        GB_CUDA(cudaStreamSynchronize(st));
+        if (d_seq2_.ensure(16) || d_valid_.ensure(16)) return 2;
+        out.d_seq2 = d_seq2_.p; out.d_valid = d_valid_.p; out.d_base_off = d_base_off_.p;
+        return 0;
+    }
+    GB_CUDA(cudaMemcpyAsync(d_chunk_begin_.p, cbegin.data(), nc * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_chunk_end_.p, cend.data(), nc * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_chunk_file_.p, cfile.data(), nc * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_file_first_.p, first_byte.data(), nf * 8, cudaMemcpyHostToDevice, st));
+    DecParams q{};
+    q.bytes = d_bytes_.p; q.chunk_begin = d_chunk_begin_.p; q.chunk_end = d_chunk_end_.p; q.chunk_file = d_chunk_file_.p;
+    q.file_first = d_file_first_.p; q.chunk_in_header = d_inhdr_.p; q.summ = d_summ_.p; q.counts = d_counts_.p;
+
+    // ---- pass 1: last record start / newline per chunk -> does a chunk start inside a header line?
+    fasta_scan_kernel<<<(uint32_t)nc, kDecThreads, 0, st>>>(q);
+    GB_LAUNCH_CHECK();
+    std::vector<uint32_t> summ(2 * nc);
+    GB_CUDA(cudaMemcpyAsync(summ.data(), d_summ_.p, 2 * nc * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint8_t> inhdr(nc, 0);
+    for (size_t f = 0; f < nf; f++) {
+        uint32_t H = 0, N = 0;
+        for (size_t c = first_chunk[f]; c < first_chunk[f + 1]; c++) {
+            inhdr[c] = H > N;
+            H = std::max(H, summ[2 * c]); N = std::max(N, summ[2 * c + 1]);
+        }
+    }
+    GB_CUDA(cudaMemcpyAsync(d_inhdr_.p, inhdr.data(), nc, cudaMemcpyHostToDevice, st));
+
+    // ---- pass 2: counts per chunk -> positions, totals, padded offsets
+    fasta_pack_kernel<false><<<(uint32_t)nc, kDecThreads, 0, st>>>(q);
+    GB_LAUNCH_CHECK();
+    std::vector<uint32_t> counts(4 * nc);
+    GB_CUDA(cudaMemcpyAsync(counts.data(), d_counts_.p, 4 * nc * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint32_t> cbase(nc), crec(nc);
+    for (size_t f = 0; f < nf; f++) {
+        uint64_t nb = 0, nr = 0, na = 0, nn = 0;
+        for (size_t c = first_chunk[f]; c < first_chunk[f + 1]; c++) {
+            cbase[c] = (uint32_t)nb; crec[c] = (uint32_t)nr;
+            nb += counts[4 * c]; nr += counts[4 * c + 1]; na += counts[4 * c + 2]; nn += counts[4 * c + 3];
+        }
+        if (nb + nr >= 0xFFFFFFFFull) { set_error("fasta decode: a file holds 2^32 bases or more"); return 3; }
+        out.n_bases[f] = nb + (nr ? nr - 1 : 0);
+        out.n_ambiguous[f] = na; out.n_N[f] = nn;
+        out.rec_off[f + 1] = out.rec_off[f] + nr;
+        out.base_off[f + 1] = out.base_off[f] + (out.n_bases[f] + 127) / 128 * 128;
+    }
+    const uint64_t total_bases = out.base_off[nf], total_recs = out.rec_off[nf];
+    if (d_seq2_.ensure(total_bases / 16 + 16) || d_valid_.ensure(total_bases / 32 + 16) ||
+        d_rec_start_.ensure(total_recs) || d_rec_end_.ensure(total_recs))
+        return 2;
+    GB_CUDA(cudaMemsetAsync(d_seq2_.p, 0, (total_bases / 16 + 16) * 4, st));
+    GB_CUDA(cudaMemsetAsync(d_valid_.p, 0, (total_bases / 32 + 16) * 4, st));
+    GB_CUDA(cudaMemcpyAsync(d_chunk_base_.p, cbase.data(), nc * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_chunk_rec_.p, crec.data(), nc * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_base_off_.p, out.base_off.data(), (nf + 1) * 8, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_rec_off_.p, out.rec_off.data(), (nf + 1) * 8, cudaMemcpyHostToDevice, st));
+    q.chunk_base0 = d_chunk_base_.p; q.chunk_rec0 = d_chunk_rec_.p; q.base_off = d_base_off_.p; q.rec_off = d_rec_off_.p;
+    q.seq2 = d_seq2_.p; q.valid = d_valid_.p; q.rec_start = d_rec_start_.p; q.rec_end = d_rec_end_.p;
+
+    // ---- pass 3: write
+    fasta_pack_kernel<true><<<(uint32_t)nc, kDecThreads, 0, st>>>(q);
+    GB_LAUNCH_CHECK();
+    out.rec_start.assign(total_recs, 0); out.rec_end.assign(total_recs, 0);
+    if (total_recs) {
+        GB_CUDA(cudaMemcpyAsync(out.rec_start.data(), d_rec_start_.p, total_recs * 8, cudaMemcpyDeviceToHost, st));
+        GB_CUDA(cudaMemcpyAsync(out.rec_end.data(), d_rec_end_.p, total_recs * 8, cudaMemcpyDeviceToHost, st));
+    }
+    GB_CUDA(cudaEventRecord(ev_[1], st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    GB_CUDA(cudaEventElapsedTime(&last_ms, ev_[0], ev_[1]));
+    for (size_t f = 0; f < nf; f++)  // the last record of a file ends with the file
+        if (out.rec_off[f + 1] > out.rec_off[f]) out.rec_end[out.rec_off[f + 1] - 1] = out.n_bases[f];
+    out.d_seq2 = d_seq2_.p; out.d_valid = d_valid_.p; out.d_base_off = d_base_off_.p;
+    return 0;
+}
+
+}  // namespace gb200

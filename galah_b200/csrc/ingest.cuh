@@ -1,0 +1,57 @@
+// Stage 0 (K0): FASTA bytes -> packed 2-bit sequence + validity bitmap ON THE DEVICE.
+//
+// The reference reads FASTA through needletail inside finch::sketch_files
+// (/root/reference/src/finch.rs:55-69) and again per pair inside skani
+// (/root/reference/src/skani.rs:80-107); SURVEY.md 8f.2 names this ingest as the next row after
+// the hot path: at 20-200 GB of input it is the end-to-end bound.  Host threads only read (and
+// inflate) the files; the raw bytes cross PCIe once and three kernels classify, count and pack
+// them into exactly the layout K1 / K3 read (csrc/host/fasta.cpp is the host packer with the
+// same semantics; tests compare the two bit for bit).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace gb200 {
+
+struct DecodedFiles {
+    // host metadata, one entry per file
+    std::vector<uint64_t> n_bases;      // packed length incl. one separator per record boundary
+    std::vector<uint64_t> n_ambiguous;  // bases that were not ACGT(U)
+    std::vector<uint64_t> n_N;          // bases that were literally 'N' / 'n'
+    std::vector<uint64_t> rec_off;      // n_files + 1 offsets into rec_start / rec_end
+    std::vector<uint64_t> rec_start, rec_end;  // per record, packed coordinates relative to its file
+    std::vector<uint64_t> base_off;     // n_files + 1, multiples of 128: file f covers [base_off[f], base_off[f+1])
+    // device arrays (owned by the decoder, valid until its next decode): the layout K1 / K3 read
+    uint32_t *d_seq2 = nullptr, *d_valid = nullptr;
+    uint64_t *d_base_off = nullptr;
+};
+
+class FastaDecoder {
+public:
+    ~FastaDecoder();
+    // h_bytes: the files' raw (already inflated) bytes, file f at [file_off[f], file_off[f] + file_len[f])
+    // with every file_off a multiple of 32 (file_off[n] = size of the buffer); first_byte[f]: absolute
+    // offset of the file's first byte that is neither '\n' nor '\r' (must be '>'), or the file's end
+    // if there is none.  All files FASTA.
+    int decode(const uint8_t *h_bytes, const std::vector<uint64_t> &file_off, const std::vector<uint64_t> &file_len,
+               const std::vector<uint64_t> &first_byte, DecodedFiles &out, cudaStream_t st);
+    float last_ms = 0.f;  // device time of the last decode (three kernels + the scans' round trips)
+    void release();
+
+private:
+    template <typename T>
+    struct Buf {
+        T *p = nullptr;
+        size_t cap = 0;
+        int ensure(size_t n);
+        void release();
+    };
+    Buf<uint8_t> d_bytes_, d_inhdr_;
+    Buf<uint32_t> d_seq2_, d_valid_, d_chunk_file_, d_summ_, d_counts_, d_chunk_base_, d_chunk_rec_;
+    Buf<uint64_t> d_chunk_begin_, d_chunk_end_, d_file_first_, d_base_off_, d_rec_off_, d_rec_start_, d_rec_end_;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+};
+
+}  // namespace gb200

@@ -328,6 +328,24 @@ int galah_b200_genome_stats(const char *const *paths, size_t n, int host_threads
 int galah_b200_pack_fasta_file(const char *path, uint32_t **seq2, uint32_t **valid, uint64_t *n_bases,
                                uint64_t **rec_start, uint64_t **rec_end, size_t *n_records);
 
+/* K0: the same ingest ON THE DEVICE (csrc/ingest.cu).  The file-taking entry points
+ * (galah_b200_sketch_files, _ani_index_add_files, _finch_distances, _cluster_files, ...) use it for
+ * whole-genome FASTA input: host threads only read / inflate the files, the raw bytes are uploaded
+ * once and three kernels classify, count and pack them into the layout K1 / K3 read.  FASTQ
+ * input and contig mode (one unit per record) take the host packer.
+ * galah_b200_device_ingest(0 / 1) switches the device path off / on (< 0 only queries); returns
+ * the previous setting (default 1).
+ * galah_b200_decode_fasta_device is the parity / measurement hook: n in-memory FASTA files ->
+ * host copies of the packed arrays (file f at bases [base_off[f], base_off[f+1]), multiples of
+ * 128) and per-file n_bases, record ranges (rec_off, rec_start, rec_end: file-relative packed
+ * coordinates), ambiguous and literal-N counts (src/genome_stats.rs:27-31).  All outputs are
+ * malloc'd (galah_b200_free); *device_ms = device time of the decode incl. the upload. */
+int galah_b200_device_ingest(int enable);
+int galah_b200_decode_fasta_device(const uint8_t *const *files, const size_t *lens, size_t n, uint32_t **seq2,
+                                   uint32_t **valid, uint64_t **base_off, uint64_t **n_bases,
+                                   uint64_t **rec_off, uint64_t **rec_start, uint64_t **rec_end,
+                                   uint64_t **n_ambiguous, uint64_t **n_N, float *device_ms);
+
 /* ---- synthetic genomes (bench / tests) ------------------------------------- */
 /* Generates genomes [index_begin, index_begin+n) of `length` bases each directly in packed
  * form on the device.  d_seq2 needs n * words_per_genome uint32 with

@@ -1,0 +1,107 @@
+"""K0 parity: FASTA bytes decoded on the device (csrc/ingest.cu) vs the host packer
+(csrc/host/fasta.cpp, itself checked against the oracle's reader in test_ingest_host.py) and the
+oracle's reader directly -- bit for bit: base codes, validity, record ranges, ambiguous / N counts."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from util import random_dna, write_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+def host_pack(gb, tmp_path, data, name="x.fna"):
+    p = str(tmp_path / name)
+    with open(p, "wb") as f:
+        f.write(data)
+    return gb.pack_fasta_file(p)
+
+
+def check_same(gb, tmp_path, files):
+    got, ms = gb.decode_fasta_device(files)
+    assert len(got) == len(files)
+    for k, (data, g) in enumerate(zip(files, got)):
+        codes, starts, ends = host_pack(gb, tmp_path, data, f"f{k}.fna")
+        assert np.array_equal(g["codes"], codes), f"file {k}: codes"
+        assert np.array_equal(g["rec_start"], starts) and np.array_equal(g["rec_end"], ends), f"file {k}: records"
+        assert g["padding_clean"]
+        # counts: ambiguous = invalid bases that are not record separators
+        n_sep = max(len(starts) - 1, 0)
+        assert g["n_ambiguous"] == int((codes == 4).sum()) - n_sep
+    return got
+
+
+def test_edge_cases_match_host_packer(gb, tmp_path):
+    rng = np.random.default_rng(5)
+    files = [
+        b">a\nACGT\n",
+        b">a\nACGT",                                   # no trailing newline
+        b"\n\r\n>a desc\r\nACgtNnRYu\r\nUUAA\r\n>b\r\n\r\nGG\r\n",  # CRLF, blank lines, lower case, U, ambiguity codes
+        b">only_header\n",
+        b">h1\n>h2\nAC\n>h3\n",                        # empty records
+        b">a\nAC>GT\nA>C\n>b\nTT\n",                   # '>' inside a sequence line is an ambiguous base
+        b">a\n" + b"ACGT" * 5000 + b"\n",              # one long line (crosses chunks without a newline)
+        b">" + b"h" * 20000 + b"\nACGTACGT\n>x\nAC\n", # a header longer than two chunks
+        b"",                                           # empty file
+        b"\n\n\r\n",                                   # only blank lines
+        b">a\n \t A C\tG T \n",                         # blanks inside sequence lines
+        b">a\n" + random_dna(8191, rng) + b"\n>b\n" + random_dna(8192, rng) + b"\n>c\n" + random_dna(3, rng),
+    ]
+    got = check_same(gb, tmp_path, files)
+    assert got[2]["n_N"] == 2 and got[5]["n_ambiguous"] == 2
+
+
+def test_random_multi_record_files(gb, tmp_path):
+    rng = np.random.default_rng(11)
+    files = []
+    for k in range(24):
+        recs = []
+        for r in range(int(rng.integers(1, 40))):
+            n = int(rng.integers(0, 30_000))
+            seq = bytearray(random_dna(n, rng))
+            for _ in range(int(rng.integers(0, 6))):   # N runs / IUPAC codes / lower case
+                if n:
+                    a = int(rng.integers(0, n)); b = min(n, a + int(rng.integers(1, 300)))
+                    seq[a:b] = bytes(rng.choice(list(b"NnRYKMacgtu"), size=b - a).astype(np.uint8))
+            recs.append((f"contig_{k}_{r} some description", bytes(seq)))
+        width = int(rng.choice([60, 70, 80, 1 << 30]))
+        nl = "\r\n" if k % 5 == 0 else "\n"
+        p = write_fasta(str(tmp_path / f"r{k}.fna"), recs, width=min(width, 1 << 20), newline=nl)
+        files.append(open(p, "rb").read())
+    check_same(gb, tmp_path, files)
+
+
+def test_matches_oracle_reader_and_committed_genomes(gb, tmp_path):
+    """The committed gz copies of the reference's fixtures: device decode == oracle reader."""
+    from conftest import GOLDEN
+    paths = [os.path.join(GOLDEN, "set1_1mbp.fna.gz"), os.path.join(GOLDEN, "set1_500kb.fna.gz")]
+    paths += sorted(os.path.join(GOLDEN, "abisko4", f) for f in os.listdir(os.path.join(GOLDEN, "abisko4")))[:2]
+    files = [gzip.open(p, "rb").read() for p in paths]
+    got, ms = gb.decode_fasta_device(files)
+    for p, data, g in zip(paths, files, got):
+        plain = str(tmp_path / (os.path.basename(p)[:-3]))
+        with open(plain, "wb") as f:
+            f.write(data)
+        codes, rs, re_ = oracle.load_codes(plain)
+        assert np.array_equal(g["codes"], codes)
+        assert np.array_equal(g["rec_start"], rs) and np.array_equal(g["rec_end"], re_)
+
+
+def test_file_entry_points_agree_with_host_ingest(gb, tmp_path):
+    """sketch_files through K0 == sketch_files through the host packer (bit-exact tables)."""
+    rng = np.random.default_rng(3)
+    paths = []
+    for k in range(6):
+        recs = [(f"c{r}", random_dna(int(rng.integers(2_000, 60_000)), rng)) for r in range(int(rng.integers(1, 5)))]
+        paths.append(write_fasta(str(tmp_path / f"g{k}.fna"), recs, gz=(k % 2 == 1)))
+    prev = gb.device_ingest(1)
+    try:
+        t1, c1 = gb.sketch_files(paths, 21, 1000)
+        gb.device_ingest(0)
+        t0, c0 = gb.sketch_files(paths, 21, 1000)
+    finally:
+        gb.device_ingest(prev)
+    assert np.array_equal(t1, t0) and np.array_equal(c1, c0)
