@@ -421,7 +421,7 @@ def main():
             body = np.concatenate([seq, np.full((seq.shape[0], 1), 10, np.uint8)], axis=1).tobytes()
             files.append(b">genome_%d synthetic\n" % g + body)
         raw_bytes = sum(len(f) for f in files)
-        gb.decode_fasta_device(files[:4], unpack=False)  # warm-up (allocations)
+        gb.decode_fasta_device(files, unpack=False)  # warm-up: sizes the decoder's device buffers
         meta, dec_ms = gb.decode_fasta_device(files, unpack=False)
         with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
             paths = []
