@@ -116,6 +116,10 @@ _SIGNATURES = {
                                                 ctypes.POINTER(ClusterStats)]),
     "galah_b200_skani_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_int, pairpp, sizep, sizep]),
+    "galah_b200_skani_distances_packed_device": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
+                                                                ctypes.c_float, ctypes.c_int, vp,
+                                                                ctypes.POINTER(ctypes.POINTER(Pair)), sizep,
+                                                                ctypes.POINTER(ctypes.c_uint64), f32p]),
     "galah_b200_cluster_files_skani": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                       ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),

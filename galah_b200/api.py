@@ -402,6 +402,24 @@ def pack_fasta_file(path):
     return codes, starts, ends
 
 
+def skani_distances_packed_device(d_seq2, d_valid, d_base_off, base_off, lengths, threshold=95.0,
+                                  min_aligned_fraction=15.0, small_genomes=False, stream=0):
+    """SkaniPreclusterer on units already packed on the device (contig mode at scale).  Returns
+    (PAIR_DTYPE hits with ani in PERCENT, info dict with n_screened and the stage times in ms)."""
+    base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    scr = ctypes.c_uint64(0)
+    ms = (ctypes.c_float * 5)()
+    check(lib().galah_b200_skani_distances_packed_device(
+        d_seq2, d_valid, d_base_off, base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p),
+        len(lengths), ctypes.c_float(threshold), ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+        stream, ctypes.byref(out), ctypes.byref(n_out), ctypes.byref(scr), ms))
+    info = {"n_screened": int(scr.value),
+            **dict(zip(("index_ms", "markers_ms", "screen_ms", "ani_ms", "total_ms"), (float(x) for x in ms)))}
+    return _take_pairs(out, n_out), info
+
+
 def device_ingest(enable=-1):
     """K0 switch: decode FASTA bytes on the device (1, default) or pack on host threads (0);
     < 0 only queries.  Returns the previous setting."""

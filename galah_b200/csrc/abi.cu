@@ -529,6 +529,49 @@ static std::string display_f32(float v) {
 // SkaniPreclusterer::distances / distances_contigs (src/skani.rs:21-56, 109-225, 379-498): marker
 // screen (K1 machinery + K2 join with the containment rule) -> K3 ANI on the survivors -> keep
 // ANI >= threshold.  Index handle stays with the caller (needed for nothing else; freed by it).
+// The skani-style preclusterer once the units are indexed (K3) and their marker table is on the
+// device: marker-containment screen through the K2 join (containment rule), K3 ANI of every
+// screened pair, `ani >= threshold` in f32 (src/skani.rs:205).  ms3 (optional): screen, ANI, total.
+static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const uint32_t *d_counts, size_t n_units,
+                                size_t stride, float threshold_pct, float min_af_pct, cudaStream_t st,
+                                std::vector<galah_b200_pair_t> &out, uint64_t &n_screened, float *ms3) {
+    const double t_begin = now_ms();
+    if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
+    const double frac = pow(0.80, 21.0);  // marker containment of a pair at ~80 % identity
+    size_t cap = std::max<size_t>(1 << 16, 64 * n_units);
+    std::vector<uint4> cand;
+    for (;;) {
+        if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
+        int rc = prefilter_enqueue(g_ctx.pws, d_table, d_counts, n_units, stride, 21, 0.f, 0, 1,
+                                   join_supported(stride) ? 0 : 1, st, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand,
+                                   kRuleContainment, frac);
+        if (rc) return rc;
+        unsigned long long got = 0;
+        GB_CUDA(cudaMemcpyAsync(&got, g_ctx.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, st));
+        GB_CUDA(cudaStreamSynchronize(st));
+        if (got > g_ctx.cap_cand) { cap = (size_t)got; continue; }
+        cand.resize((size_t)got);
+        if (got) {
+            GB_CUDA(cudaMemcpyAsync(cand.data(), g_ctx.d_cand, (size_t)got * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+        }
+        break;
+    }
+    const double t_screen = now_ms();
+    std::sort(cand.begin(), cand.end(), [](const uint4 &a, const uint4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    n_screened = cand.size();
+    std::vector<uint32_t> pairs(2 * cand.size());
+    for (size_t x = 0; x < cand.size(); x++) { pairs[2 * x] = cand[x].x; pairs[2 * x + 1] = cand[x].y; }
+    std::vector<AniPairResult> res(cand.size());
+    if (int rc = index.pairs(pairs.data(), cand.size(), min_af_pct, res.data(), st)) return rc;
+    out.clear();
+    for (size_t x = 0; x < cand.size(); x++)
+        if (res[x].ani >= threshold_pct)  // `if ani >= threshold` in f32, src/skani.rs:205
+            out.push_back(galah_b200_pair_t{cand[x].x, cand[x].y, cand[x].z, cand[x].w, res[x].ani});
+    if (ms3) { ms3[0] = (float)(t_screen - t_begin); ms3[1] = (float)(now_ms() - t_screen); ms3[2] = (float)(now_ms() - t_begin); }
+    return 0;
+}
+
 static int skani_distances_impl(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
                                 bool small_genomes, bool per_record, int host_threads,
                                 std::vector<galah_b200_pair_t> &out, size_t &n_units, uint64_t &n_screened) {
@@ -560,37 +603,8 @@ static int skani_distances_impl(const char *const *paths, size_t n, float thresh
     cudaStream_t st = g_ctx.stream;
     GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, table.data(), table.size() * 8, cudaMemcpyHostToDevice, st));
     GB_CUDA(cudaMemcpyAsync(g_ctx.d_counts, counts.data(), n_units * 4, cudaMemcpyHostToDevice, st));
-    if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
-    const double frac = pow(0.80, 21.0);  // marker containment of a pair at ~80 % identity
-    size_t cap = std::max<size_t>(1 << 16, 64 * n_units);
-    std::vector<uint4> cand;
-    for (;;) {
-        if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
-        int rc = prefilter_enqueue(g_ctx.pws, g_ctx.d_table, g_ctx.d_counts, n_units, stride, 21, 0.f, 0, 1,
-                                   join_supported(stride) ? 0 : 1, st, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand,
-                                   kRuleContainment, frac);
-        if (rc) return rc;
-        unsigned long long got = 0;
-        GB_CUDA(cudaMemcpyAsync(&got, g_ctx.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, st));
-        GB_CUDA(cudaStreamSynchronize(st));
-        if (got > g_ctx.cap_cand) { cap = (size_t)got; continue; }
-        cand.resize((size_t)got);
-        if (got) {
-            GB_CUDA(cudaMemcpyAsync(cand.data(), g_ctx.d_cand, (size_t)got * sizeof(uint4), cudaMemcpyDeviceToHost, st));
-            GB_CUDA(cudaStreamSynchronize(st));
-        }
-        break;
-    }
-    std::sort(cand.begin(), cand.end(), [](const uint4 &a, const uint4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
-    n_screened = cand.size();
-    std::vector<uint32_t> pairs(2 * cand.size());
-    for (size_t x = 0; x < cand.size(); x++) { pairs[2 * x] = cand[x].x; pairs[2 * x + 1] = cand[x].y; }
-    std::vector<AniPairResult> res(cand.size());
-    if (int rc = index.pairs(pairs.data(), cand.size(), min_af_pct, res.data(), st)) return rc;
-    for (size_t x = 0; x < cand.size(); x++)
-        if (res[x].ani >= threshold_pct)  // `if ani >= threshold` in f32, src/skani.rs:205
-            out.push_back(galah_b200_pair_t{cand[x].x, cand[x].y, cand[x].z, cand[x].w, res[x].ani});
-    return 0;
+    return skani_screen_and_ani(index, g_ctx.d_table, g_ctx.d_counts, n_units, stride, threshold_pct, min_af_pct, st, out,
+                                n_screened, nullptr);
 }
 
 }  // namespace gb200
@@ -1072,6 +1086,62 @@ int galah_b200_skani_distances(const char *const *paths, size_t n, float thresho
                                       host_threads, hits, units, screened))
         return rc;
     if (n_units) *n_units = units;
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(hits.size(), 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!hits.empty()) memcpy(res, hits.data(), hits.size() * sizeof(galah_b200_pair_t));
+    *out = res; *n_out = hits.size();
+    return 0;
+}
+
+int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
+                                             const uint64_t *d_base_off, const uint64_t *base_off,
+                                             const uint64_t *lengths, size_t n, float threshold_pct,
+                                             float min_af_pct, int small_genomes, void *stream,
+                                             galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened,
+                                             float *ms5) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    *out = nullptr; *n_out = 0;
+    if (threshold_pct < 85.0f) {
+        set_error("Error: skani produces inaccurate results with ANI less than 85%. Provided: " + display_f32(threshold_pct));
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const double t0 = now_ms();
+    AniIndex index(small_genomes ? 30u : 125u);
+    std::vector<uint64_t> bo(base_off, base_off + n + 1), co(n + 1);
+    std::vector<uint32_t> cs(n, 0), cl(n);
+    uint64_t longest = 0;
+    for (size_t g = 0; g < n; g++) { co[g] = g; cl[g] = (uint32_t)lengths[g]; longest = std::max(longest, lengths[g]); }
+    co[n] = n;
+    if (int rc = index.add_packed_device(d_seq2, d_valid, d_base_off, n, bo, co, cs, cl, st)) return rc;
+    const double t1 = now_ms();
+    // marker sketches straight into the K2 table layout (row stride = cap): they never leave the device
+    const uint32_t c_marker = small_genomes ? 200u : 1000u;
+    uint32_t cap = 256;
+    while (cap < 16384 && cap < 1.5 * (double)longest / c_marker + 256.0) cap <<= 1;
+    DevBuf<uint64_t> d_rows;
+    DevBuf<uint32_t> d_counts;
+    if (d_rows.alloc(n * (size_t)cap) || d_counts.alloc(n)) return GALAH_B200_ERR_CUDA;
+    if (int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_base_off, n, 21, c_marker, cap, d_rows.p, d_counts.p, st))
+        return rc;
+    std::vector<uint32_t> cnt(n);
+    GB_CUDA(cudaMemcpyAsync(cnt.data(), d_counts.p, n * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    for (size_t g = 0; g < n; g++)
+        if (cnt[g] == 0xFFFFFFFFu) {
+            set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
+            return GALAH_B200_ERR_UNSUPPORTED;
+        }
+    const double t2 = now_ms();
+    std::vector<galah_b200_pair_t> hits;
+    uint64_t screened = 0;
+    float ms3[3] = {0, 0, 0};
+    if (n >= 2)
+        if (int rc = skani_screen_and_ani(index, d_rows.p, d_counts.p, n, cap, threshold_pct, min_af_pct, st, hits, screened, ms3))
+            return rc;
+    if (n_screened) *n_screened = screened;
+    if (ms5) { ms5[0] = (float)(t1 - t0); ms5[1] = (float)(t2 - t1); ms5[2] = ms3[0]; ms5[3] = ms3[1]; ms5[4] = (float)(now_ms() - t0); }
     galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(hits.size(), 1) * sizeof(galah_b200_pair_t));
     if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
     if (!hits.empty()) memcpy(res, hits.data(), hits.size() * sizeof(galah_b200_pair_t));

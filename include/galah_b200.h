@@ -304,6 +304,18 @@ int galah_b200_skani_distances(const char *const *paths, size_t n, float thresho
 /* cluster() with SkaniPreclusterer + SkaniClusterer -- galah's CLI default
  * (--precluster-method skani --cluster-method skani) -- or, with cluster_contigs != 0,
  * `--cluster-contigs`: both run with skip_clusterer (src/clusterer.rs:32-44). */
+/* The same preclusterer on units that are already packed on the device (K1 layout, one record per
+ * unit of `lengths[g]` bases at base_off[g]): K3 index, marker sketches written straight into the
+ * K2 table (they never leave the device), containment screen, K3 ANI.  This is the contig-mode
+ * path (`--cluster-contigs --small-genomes`, BASELINE.json configs[4]) at scale; bench / tests
+ * feed it synthetic contigs.  n_screened: pairs that passed the marker screen; ms5 (optional):
+ * host wall clock of index build, marker sketches, screen, ANI, total. */
+int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
+                                             const uint64_t *d_base_off, const uint64_t *base_off,
+                                             const uint64_t *lengths, size_t n, float threshold_pct,
+                                             float min_af_pct, int small_genomes, void *stream,
+                                             galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened,
+                                             float *ms5);
 int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct,
                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
                                    int cluster_contigs, int host_threads, galah_b200_clusters_t *out,

@@ -91,3 +91,33 @@ def test_default_cli_path_on_reference_genomes(gb):
     c99, _ = gb.cluster_skani(paths, precluster_ani=90.0, ani=99.0, min_aligned_fraction=20.0)
     assert c95 == [[0, 1, 2, 3]]
     assert c99 == [[0, 1, 3], [2]]
+
+
+def test_device_resident_contigs_match_file_path_and_oracle(gb, tmp_path):
+    """galah_b200_skani_distances_packed_device (units packed on the device, marker table never
+    leaves it) == the file-based contig-mode call on the same synthetic contigs == the oracle."""
+    import torch
+    seed, n, L = 1, 60, 30_000
+    lay = gb.synth_layout(n, L)
+    dev = torch.device("cuda", 0)
+    d_seq = torch.zeros(lay["seq2_words"], dtype=torch.int32, device=dev)
+    d_val = torch.zeros(lay["valid_words"], dtype=torch.int32, device=dev)
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gb.synth_packed_device(seed, 0, n, L, d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), st)
+    torch.cuda.synchronize()
+    base_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(lay["padded"])
+    got, info = gb.skani_distances_packed_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), base_off,
+                                                 np.full(n, L, np.uint64), 90.0, 15.0, small_genomes=True, stream=st)
+    assert info["n_screened"] >= len(got) > 0
+    path = write_fasta(str(tmp_path / "contigs.fna"), [(f"c{g}", oracle.synth_genome(seed, g, L)) for g in range(n)])
+    via_files, n_units = gb.skani_distances([path], 90.0, 15.0, small_genomes=True, contigs=True)
+    assert n_units == n
+    assert len(got) == len(via_files)
+    for f in ("i", "j", "common", "total"):
+        assert np.array_equal(got[f], via_files[f]), f
+    assert np.array_equal(got["ani"].view(np.uint32), via_files["ani"].view(np.uint32))
+    exp = oracle.skani_distances(units_of([path], per_record=True), 90.0, 15.0, small_genomes=True)
+    check(got, exp)
+    # members of a synthetic family of 10 only ever pair with each other
+    assert np.all(got["i"] // 10 == got["j"] // 10)
