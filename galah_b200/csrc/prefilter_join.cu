@@ -67,6 +67,7 @@ constexpr int kJCtasPerSm = 3;
 constexpr int kDR = 5;                     // diagonal items: entries per thread whose run walks are interleaved
 static_assert(kJDiag % (kDR * kJThreads) == 0, "a full diagonal segment is whole passes");
 constexpr int kTQ = 1024;                  // deferred-tie queue entries per CTA
+constexpr uint32_t kDenseTies = 64;        // ties in an item after which its segments track B-takes in the hot loop
 constexpr int kTQSegs = 16;                // segments whose (i0, j0) bases the queue can refer to
 constexpr uint8_t kPadTag = 0xFF;
 constexpr size_t kBlSlack = 1024;          // entries of over-read slack behind the last list
@@ -465,6 +466,7 @@ struct JoinSmem {
     uint32_t tq[kTQ];            // slot << 28 | j_rel << 14 | i_rel (relative to the segment's i0 / j0)
     uint32_t tq_i0[kTQSegs], tq_j0[kTQSegs];
     uint32_t tq_n;
+    uint32_t item_ties;          // ties seen by the replay variant in the current item (picks the variant)
 };
 static_assert(3 * (sizeof(JoinSmem) + 1024) <= 233472, "three join CTAs must fit one SM");
 
@@ -501,13 +503,35 @@ struct SegGeom {
     uint32_t i0, i1, j0, j1, d0, d1, na_s, nb_s, a_ext, a_lo, a_off, a_cnt, b_lo, b_off, b_cnt;
 };
 
-// Re-walk `steps` merge steps from (i, j) and queue every step whose bit is set in `ties` (the B
-// entry at j met an equal key at the A cursor i).  A queue that is full takes the tie at once.
-// Out of line: the hot loop only records ties in a bit mask and never branches.
+// Queue the tie steps of one chain: bit t of `ties` marks a step whose B entry met an equal key
+// at the A cursor, bit t of `took_b` says whether step t consumed a B entry, so the cursors at
+// step t follow from a population count -- no re-walk of the chain, no shared-memory reads.
+// (i0, j0) are the chain's cursors before step 0.  A queue that is full takes the tie at once.
+// Out of line: the hot loop only records the two bit masks and never branches.
 __device__ __noinline__ void queue_ties(JoinSmem &S, const uint32_t *Ah, const uint32_t *Bh, uint32_t a_ext,
-                                        uint32_t i, uint32_t j, uint32_t steps, uint32_t ties, uint32_t slot,
+                                        uint32_t i0c, uint32_t j0c, uint32_t ties, uint32_t took_b, uint32_t slot,
                                         const ListView A, uint32_t i0, const ListView B, uint32_t j0) {
     uint32_t q = atomicAdd(&S.tq_n, (uint32_t)__popc(ties));
+    while (ties) {
+        const uint32_t t = (uint32_t)__ffs((int)ties) - 1u;
+        ties &= ties - 1u;
+        const uint32_t nb = (uint32_t)__popc(took_b & ((1u << t) - 1u));
+        const uint32_t j = j0c + nb, i = i0c + t - nb;
+        if (q < (uint32_t)kTQ) S.tq[q] = (slot << 28) | (j << 14) | i;
+        else match_run(S.cnt, Ah, a_ext, i, Bh[j], A, i0, B, j0 + j);
+        q++;
+    }
+}
+
+// The same without the took_b mask: re-walk the chain's steps from (i, j) in shared memory.  Used
+// while an item has shown few ties, where keeping the second mask in the hot loop costs more
+// (one instruction per step) than the occasional re-walk.
+__device__ __noinline__ void queue_ties_replay(JoinSmem &S, const uint32_t *Ah, const uint32_t *Bh, uint32_t a_ext,
+                                               uint32_t i, uint32_t j, uint32_t steps, uint32_t ties, uint32_t slot,
+                                               const ListView A, uint32_t i0, const ListView B, uint32_t j0) {
+    const uint32_t n_ties = (uint32_t)__popc(ties);
+    atomicAdd(&S.item_ties, n_ties);
+    uint32_t q = atomicAdd(&S.tq_n, n_ties);
     uint32_t ka = Ah[i], kb = Bh[j];
     for (uint32_t t = 0; t < steps && (ties >> t) != 0; t++) {
         const bool tb = kb <= ka;
@@ -556,13 +580,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 // kJChains independent chains of exactly kJE branch-free steps, interleaved for ILP, each chain
 // starting at its own merge-path split (no shared split table, no barrier).  kChecked = true
 // bounds every step by the chain's own end split and takes ties at once (list ends only).
-template <bool kChecked>
+template <bool kChecked, bool kTrack>
 __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, const ListView &B, const SegGeom &g,
                                              uint32_t tid, uint32_t slot) {
     const uint32_t *Ah = S.hi + g.a_off, *Bh = S.hi + g.a_cnt + g.b_off;
     const uint32_t len = g.na_s + g.nb_s;
     if (!kChecked) {
-        uint32_t pa[kJChains], pb[kJChains], ka[kJChains], kb[kJChains], ties[kJChains], is[kJChains];
+        uint32_t pa[kJChains], pb[kJChains], ka[kJChains], kb[kJChains], ties[kJChains], tookb[kJChains], is[kJChains];
         const uint32_t a_base = smem_u32(Ah), b_base = smem_u32(Bh);
 #pragma unroll
         for (int c = 0; c < kJChains; c++) is[c] = split_bfirst(Ah, g.na_s, Bh, g.nb_s, (c * kJThreads + tid) * kJE);
@@ -572,7 +596,7 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, con
             pa[c] = a_base + 4u * is[c];
             pb[c] = b_base + 4u * (cs * kJE - is[c]);
             ka[c] = lds32(pa[c]); kb[c] = lds32(pb[c]);
-            ties[c] = 0;
+            ties[c] = 0; tookb[c] = 0;
         }
 #pragma unroll
         for (int t = 0; t < kJE; t++) {
@@ -580,6 +604,7 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, con
             for (int c = 0; c < kJChains; c++) {
                 const bool tb = kb[c] <= ka[c];
                 ties[c] |= kb[c] == ka[c] ? (1u << t) : 0u;
+                if (kTrack) tookb[c] |= tb ? (1u << t) : 0u;
                 const uint32_t pn = (tb ? pb[c] : pa[c]) + 4u;
                 const uint32_t nv = lds32(pn);
                 pb[c] = tb ? pn : pb[c];
@@ -590,9 +615,14 @@ __device__ __forceinline__ void join_segment(JoinSmem &S, const ListView &A, con
         }
 #pragma unroll
         for (int c = 0; c < kJChains; c++)
-            if (ties[c])
-                queue_ties(S, Ah, Bh, g.a_ext, is[c], (c * kJThreads + tid) * kJE - is[c], kJE, ties[c], slot, A, g.i0,
-                           B, g.j0);
+            if (ties[c]) {
+                if (kTrack)
+                    queue_ties(S, Ah, Bh, g.a_ext, is[c], (c * kJThreads + tid) * kJE - is[c], ties[c], tookb[c], slot, A,
+                               g.i0, B, g.j0);
+                else
+                    queue_ties_replay(S, Ah, Bh, g.a_ext, is[c], (c * kJThreads + tid) * kJE - is[c], kJE, ties[c], slot,
+                                      A, g.i0, B, g.j0);
+            }
     } else {
         for (int c = 0; c < kJChains; c++) {
             const uint32_t cs = c * kJThreads + tid;
@@ -655,6 +685,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         if (p.dbg_buf && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_item0));
 
         for (uint32_t x = tid; x < kJR * kJR / 2; x += kJThreads) S.cnt[x] = 0;
+        if (tid == 0) S.item_ties = 0;
         for (uint32_t x = tid; x < kJR; x += kJThreads) {
             S.na[x] = row0 + x < p.n ? min(p.counts[row0 + x], p.stride) : 0;
             S.nb[x] = col0 + x < p.n ? min(p.counts[col0 + x], p.stride) : 0;
@@ -730,7 +761,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
             // ---- off-diagonal item: CTA-wide merge-path intersection of two block lists
             const uint32_t total = la + lb;
             const uint32_t nseg = (total + kJD - 1) / kJD;
-            bool done = false;
+            bool done = false, dense = false;
             uint32_t slot = 0;  // segments since the last flush of the tie queue
             for (uint32_t kb = 0; kb < nseg && !done; kb += kJThreads - 1) {
                 const uint32_t nsb = min((uint32_t)(kJThreads - 1), nseg - kb);
@@ -761,14 +792,20 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
                     }
                     mbar_wait(&S.bar, phase); phase ^= 1;
                     // a full segment that ends before either list does holds only real entries
-                    if (g.i1 < la && g.j1 < lb && g.d1 - g.d0 == (uint32_t)kJD)
-                        join_segment<false>(S, A, B, g, tid, slot);
-                    else
-                        join_segment<true>(S, A, B, g, tid, slot);
+                    if (g.i1 < la && g.j1 < lb && g.d1 - g.d0 == (uint32_t)kJD) {
+                        if (dense) join_segment<false, true>(S, A, B, g, tid, slot);
+                        else join_segment<false, false>(S, A, B, g, tid, slot);
+                    } else {
+                        join_segment<true, false>(S, A, B, g, tid, slot);
+                    }
                     // the staged slices are free for the next TMA and the queue is complete; the thread
                     // whose enqueue came last sees the final fill, so the OR is the same for all
                     const bool half_full =
                         __syncthreads_or(*reinterpret_cast<volatile uint32_t *>(&S.tq_n) >= (uint32_t)(kTQ / 2));
+                    // an item whose segments tie often (relatives in the two blocks) switches to the
+                    // variant that tracks the B-takes in the hot loop instead of re-walking chains
+                    if (!dense)
+                        dense = __syncthreads_or(*reinterpret_cast<volatile uint32_t *>(&S.item_ties) >= kDenseTies);
                     if (++slot == (uint32_t)kTQSegs || half_full) {
                         flush_ties(S, A, B, tid);
                         slot = 0;
