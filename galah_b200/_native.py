@@ -84,6 +84,9 @@ _SIGNATURES = {
     "galah_b200_blocklist_layout": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_size_t, sizep, sizep, sizep]),
     "galah_b200_blocklist_build": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
                                                   ctypes.c_size_t, vp, vp, vp, vp, vp]),
+    "galah_b200_prefilter_join_items_enqueue": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint8,
+                                                               ctypes.c_float, vp, vp, vp, vp, vp, ctypes.c_size_t,
+                                                               ctypes.c_int, vp, vp, ctypes.c_size_t, vp]),
     "galah_b200_table_max_device": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, vp]),
     "galah_b200_blocklist_build_local": (ctypes.c_int, [vp, vp, ctypes.c_size_t, ctypes.c_size_t, vp, ctypes.c_size_t,
                                                         vp, vp, vp, vp, vp]),

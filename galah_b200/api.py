@@ -167,6 +167,15 @@ def blocklist_build(d_hashes, d_counts, n, stride, block_begin, block_end, d_hi,
                                            d_tags, d_len, stream))
 
 
+def prefilter_join_items_enqueue(d_hashes, d_counts, n, stride, k, min_ani, d_hi, d_lo, d_tags, d_len, d_items,
+                                 n_items, reset_candidates, stream, d_cand, cand_cap, d_n_cand):
+    """Join of an explicit device list of (rb, cb) block pairs; candidates are appended."""
+    check(lib().galah_b200_prefilter_join_items_enqueue(d_hashes, d_counts, n, stride, k, ctypes.c_float(min_ani),
+                                                        d_hi, d_lo, d_tags, d_len, d_items, n_items,
+                                                        int(bool(reset_candidates)), stream, d_cand, cand_cap,
+                                                        d_n_cand))
+
+
 def table_max_device(d_hashes, d_counts, n, stride, d_max, stream=0):
     """Largest valid hash of a (slice of a) device sketch table -> device uint64 scalar d_max."""
     check(lib().galah_b200_table_max_device(d_hashes, d_counts, n, stride, d_max, stream))

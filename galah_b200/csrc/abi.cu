@@ -784,6 +784,24 @@ int galah_b200_prefilter_join_enqueue(const uint64_t *d_hashes, const uint32_t *
     return join_launch(g_ctx.pws, p, d_hi, d_lo, d_tags, d_len, shard, n_shards, st);
 }
 
+int galah_b200_prefilter_join_items_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
+                                            uint8_t k, float min_ani, const uint32_t *d_hi, const uint32_t *d_lo,
+                                            const uint8_t *d_tags, const uint32_t *d_len, const uint32_t *d_items,
+                                            size_t n_items, int reset_candidates, void *stream, uint32_t *d_cand,
+                                            size_t cand_cap, unsigned long long *d_n_cand) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!join_supported(stride)) { set_error("prefilter_join: unsupported stride"); return GALAH_B200_ERR_ARG; }
+    KernelParams p;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = prefilter_prepare(g_ctx.pws, d_hashes, d_counts, n, stride, k, min_ani, 0, 1, st,
+                                   reinterpret_cast<uint4 *>(d_cand), cand_cap, d_n_cand, p, kRuleMashAni, 0.0,
+                                   reset_candidates != 0))
+        return rc;
+    if (n < 2) return 0;
+    return join_launch_items(g_ctx.pws, p, d_hi, d_lo, d_tags, d_len, d_items, n_items, st);
+}
+
 int galah_b200_prefilter_device(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                                 size_t stride, uint8_t k, float min_ani, uint32_t shard,
                                 uint32_t n_shards, void *stream, galah_b200_pair_t **out, size_t *n_out) {

@@ -113,7 +113,7 @@ int PrefilterWorkspace::release() {
     cudaFree(d_local_rb); cudaFree(d_work_counter); cudaFree(d_bl_len); cudaFree(d_gmax);
     cudaFree(d_fin_hi); cudaFree(d_fin_lo); cudaFree(d_fin_tags); cudaFree(d_splits);
     for (int x = 0; x < 2; x++) { cudaFree(d_bl_vals[x]); cudaFree(d_bl_tags[x]); }
-    cudaFree(d_wave_counters);
+    cudaFree(d_wave_counters); cudaFree(d_item_counters);
     for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
     *this = PrefilterWorkspace();
     return 0;
@@ -306,12 +306,12 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
 int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                       size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
                       uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p, int rule,
-                      double rule_param) {
+                      double rule_param, bool reset_counter) {
     if (n_shards == 0 || shard >= n_shards) { set_error("prefilter: bad shard"); return 3; }
     if (stride == 0 || (stride & 1)) { set_error("prefilter: stride must be even and > 0"); return 3; }
     if (n >= 0x7FFFFFFFull) { set_error("prefilter: n too large"); return 3; }
     if (stride >= (1ull << 30)) { set_error("prefilter: stride too large"); return 3; }
-    GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
+    if (reset_counter) GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
     if (!ws.th_valid || ws.th_s != (uint32_t)stride || ws.th_k != k || ws.th_min_ani != min_ani ||
         ws.th_rule != rule || ws.th_param != rule_param) {
         PrefilterThresholds th = rule == kRuleContainment ? make_containment_thresholds((uint32_t)stride, rule_param)

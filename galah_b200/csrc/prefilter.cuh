@@ -54,6 +54,8 @@ struct PrefilterWorkspace {
     // streamed host-buffer path: one work counter per wave, one "slice resident" event per slice
     unsigned long long *d_wave_counters = nullptr;
     size_t cap_wave_counters = 0;
+    unsigned long long *d_item_counters = nullptr;  // pool of work counters for explicit-item launches
+    uint32_t item_counter_next = 0;
     std::vector<cudaEvent_t> chunk_ev;
     // block lists (mode 0): two ping-pong buffers of n_blocks * kShardRows * stride entries
     uint64_t *d_bl_vals[2] = {nullptr, nullptr};
@@ -97,6 +99,8 @@ struct KernelParams {
     const uint32_t *bl_len;
     uint64_t bl_cap;  // entries per block list (kShardRows * stride)
     uint32_t n_diag;  // join: diagonal items, taken first; they belong to the LAST n_diag local rows
+    const uint32_t *items;    // join: explicit work list of (rb, cb) pairs, rb <= cb, longest first; or null
+    uint32_t n_explicit;      // number of explicit items
     uint32_t n_adj, adj_lr0;  // join: items (rb, rb + 1), taken next; local rows [adj_lr0, adj_lr0 + n_adj)
     unsigned long long *dbg_buf;  // per-item {start ns, end ns, sm, rb << 32 | cb} log (debug), or null
     uint32_t cb_lo;   // first column block of the launch's window (0 unless a streamed wave)
@@ -135,7 +139,11 @@ int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, c
 int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                       size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
                       uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p,
-                      int rule = kRuleMashAni, double rule_param = 0.0);
+                      int rule = kRuleMashAni, double rule_param = 0.0, bool reset_counter = true);
+// prefilter_join.cu: join of an explicit list of block pairs (device array of (rb, cb), rb <= cb)
+int join_launch_items(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, const uint32_t *d_lo,
+                      const uint8_t *d_tags, const uint32_t *d_len, const uint32_t *d_items, size_t n_items,
+                      cudaStream_t stream);
 // prefilter.cu: work list with one item per (local row block, column block >= it), block = kShardRows
 int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream, KernelParams &p);

@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
     // blocks (rb, rb + 1) -- input that keeps relatives together puts its cross-block ties there --
     // then the remaining off-diagonal items row by row.  Diagonal rows are the last n_diag local
     // rows; rows with an adjacent item are the n_adj local rows from adj_lr0.
-    const uint64_t n_items = (uint64_t)p.n_diag + p.n_adj + p.item_prefix[p.n_local_rb];
+    const uint64_t n_items = p.items ? (uint64_t)p.n_explicit : (uint64_t)p.n_diag + p.n_adj + p.item_prefix[p.n_local_rb];
 
     for (;;) {
         if (tid == 0) S.item = atomicAdd(p.work_counter, 1ull);
@@ -664,7 +664,9 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         const unsigned long long item = S.item;
         if (item >= n_items) break;
         uint32_t rb, cb;
-        if (item < p.n_diag) {
+        if (p.items) {
+            rb = p.items[2 * item]; cb = p.items[2 * item + 1];
+        } else if (item < p.n_diag) {
             rb = cb = p.local_rb[p.n_local_rb - p.n_diag + (uint32_t)item];
         } else if (item < (uint64_t)p.n_diag + p.n_adj) {
             rb = p.local_rb[p.adj_lr0 + (uint32_t)(item - p.n_diag)];
@@ -982,6 +984,33 @@ int join_launch(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, c
     if (p.n_local_rb == 0) return 0;
     uint64_t n_items = 0;
     for (uint32_t rb = 0; rb < nb; rb++) if (shard_of_group(rb, n_shards) == shard) n_items += nb - rb;
+    const size_t smem = sizeof(JoinSmem);
+    GB_CUDA(cudaFuncSetAttribute(prefilter_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm);
+    if (ws.record(1, stream)) return 2;
+    prefilter_join_kernel<<<grid, kJThreads, smem, stream>>>(p);
+    GB_LAUNCH_CHECK();
+    if (ws.record(2, stream)) return 2;
+    return 0;
+}
+
+// Join of an explicit list of block pairs over lists that cover the whole table (multi-GPU ring:
+// one launch per peer slice as its lists arrive).  Candidates are appended to the caller's list.
+int join_launch_items(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d_hi, const uint32_t *d_lo,
+                      const uint8_t *d_tags, const uint32_t *d_len, const uint32_t *d_items, size_t n_items,
+                      cudaStream_t stream) {
+    if (n_items == 0) return 0;
+    if (n_items >= 0xFFFFFFFFull) { set_error("prefilter_join: too many explicit items"); return 3; }
+    constexpr uint32_t kPool = 64;
+    if (!ws.d_item_counters) GB_CUDA(cudaMalloc(&ws.d_item_counters, kPool * sizeof(unsigned long long)));
+    unsigned long long *ctr = ws.d_item_counters + (ws.item_counter_next++ % kPool);
+    GB_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream));
+    p.bl_hi = d_hi; p.bl_lo = d_lo; p.bl_tags = d_tags; p.bl_len = d_len; p.bl_cap = (uint64_t)kJR * p.stride;
+    p.n_row_blocks = (p.n + kJR - 1) / kJR;
+    p.items = d_items; p.n_explicit = (uint32_t)n_items; p.work_counter = ctr;
+    int dev = 0, sms = kNumSMsFallback;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = sizeof(JoinSmem);
     GB_CUDA(cudaFuncSetAttribute(prefilter_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms * kJCtasPerSm);

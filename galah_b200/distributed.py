@@ -80,7 +80,14 @@ class ShardedPrefilter:
     gathered table: the ranks agree on the table-wide largest hash with one 8-byte all-reduce, and
     the all-gather of the sketch table (the join needs it for the survivors' exact `total`) runs
     on NCCL's stream WHILE the lists are built.  Otherwise the table is gathered first and every
-    rank builds 1/G of the blocks from it.  Buffers are allocated once and re-used."""
+    rank builds 1/G of the blocks from it.  Buffers are allocated once and re-used.
+
+    With whole-block slices and G > 1 the exchange is a RING instead of all-gathers: block pair
+    {b1 <= b2} belongs to the rank that built b1 if b1 + b2 is even, else to the one that built b2
+    (every rank gets the same share and every item has one local list).  In round k a rank sends
+    its lists + table slice to rank r+k and receives those of rank r-k (NCCL send/recv over
+    NVLink); the join of the items against peer r-k is enqueued as soon as that round has landed,
+    so rounds k+1.. travel while round k is joined: the exchange hides behind the join."""
 
     def __init__(self, gb, dist, n_local, stride, device):
         import torch
@@ -110,6 +117,79 @@ class ShardedPrefilter:
         self.d_cand = t.empty((self.cand_cap, 4), dtype=t.int32, device=device)
         self.d_ncand = t.zeros(1, dtype=t.int64, device=device)
         self.h_cand = t.empty((self.cand_cap, 4), dtype=t.int32).pin_memory()
+        import os
+        self.ring = self.local_build and self.world > 1 and not os.environ.get("GALAH_B200_NO_RING")
+        if self.ring:
+            self._init_ring()
+
+    def _init_ring(self):
+        """Per round k the explicit item list (rb, cb) this rank joins once peer (rank - k)'s lists are
+        resident; round 0 = the items inside its own slice (diagonal items first: they take longest)."""
+        t, G, r, nbp = self.torch, self.world, self.rank, self.nbp
+        mine = np.arange(r * nbp, (r + 1) * nbp, dtype=np.int64)
+        self.round_items, self.round_n = [], []
+        for k in range(G):
+            peer = (r - k) % G
+            if k == 0:
+                a, b = np.meshgrid(mine, mine, indexing="ij")
+                keep = a <= b
+                lo, hi = a[keep], b[keep]
+                order = np.lexsort((hi, lo, hi - lo))  # diagonal, then adjacent, then by distance
+                lo, hi = lo[order], hi[order]
+            else:
+                theirs = np.arange(peer * nbp, (peer + 1) * nbp, dtype=np.int64)
+                a, b = np.meshgrid(mine, theirs, indexing="ij")
+                lo, hi = np.minimum(a, b).ravel(), np.maximum(a, b).ravel()
+                owner = np.where((lo + hi) % 2 == 0, lo // nbp, hi // nbp)
+                keep = owner == r
+                lo, hi = lo[keep], hi[keep]
+            items = np.stack([lo, hi], axis=1).astype(np.int32)
+            self.round_n.append(len(items))
+            self.round_items.append(t.from_numpy(np.ascontiguousarray(items)).to(self.dev) if len(items) else None)
+        # views of this rank's slice inside the table-wide buffers: lists are built and the slice is
+        # uploaded in place, peers' slices are received into theirs
+        e, nl = nbp * self.epb, self.n_local
+        self.v_table = lambda q: self.table[q * nl:(q + 1) * nl]
+        self.v_counts = lambda q: self.counts[q * nl:(q + 1) * nl]
+        self.v_hi = lambda q: self.all_hi[q * e:(q + 1) * e]
+        self.v_lo = lambda q: self.all_lo[q * e:(q + 1) * e]
+        self.v_tags = lambda q: self.all_tags[q * e:(q + 1) * e]
+        self.v_len = lambda q: self.all_len[q * nbp:(q + 1) * nbp]
+
+    def _step_ring(self, k, min_ani):
+        t, gb, dist = self.torch, self.gb, self.dist
+        st = t.cuda.current_stream().cuda_stream
+        n, s, G, r = self.n, self.s, self.world, self.rank
+        self.v_table(r).copy_(self.my_table, non_blocking=True)
+        self.v_counts(r).copy_(self.my_counts, non_blocking=True)
+        gb.table_max_device(self.my_table.data_ptr(), self.my_counts.data_ptr(), self.n_local, s,
+                            self.gmax.data_ptr(), st)
+        self.gmax.bitwise_xor_(-(1 << 63))  # the collective compares int64: map unsigned order onto signed
+        dist.all_reduce(self.gmax, op=dist.ReduceOp.MAX)
+        self.gmax.bitwise_xor_(-(1 << 63))
+        gb.blocklist_build_local(self.my_table.data_ptr(), self.my_counts.data_ptr(), self.n_local, s,
+                                 self.gmax.data_ptr(), self.nbp, self.v_hi(r).data_ptr(), self.v_lo(r).data_ptr(),
+                                 self.v_tags(r).data_ptr(), self.v_len(r).data_ptr(), st)
+        works = []
+        for rnd in range(1, G):
+            dst, src = (r + rnd) % G, (r - rnd) % G
+            ops = []
+            for view in (self.v_hi, self.v_lo, self.v_tags, self.v_len, self.v_table, self.v_counts):
+                ops.append(dist.P2POp(dist.isend, view(r), dst))
+                ops.append(dist.P2POp(dist.irecv, view(src), src))
+            works.append(dist.batch_isend_irecv(ops))
+        for rnd in range(G):
+            if rnd:
+                for w in works[rnd - 1]:
+                    w.wait()
+            if self.round_n[rnd]:
+                gb.prefilter_join_items_enqueue(self.table.data_ptr(), self.counts.data_ptr(), n, s, k, min_ani,
+                                                self.all_hi.data_ptr(), self.all_lo.data_ptr(),
+                                                self.all_tags.data_ptr(), self.all_len.data_ptr(),
+                                                self.round_items[rnd].data_ptr(), self.round_n[rnd], rnd == 0, st,
+                                                self.d_cand.data_ptr(), self.cand_cap, self.d_ncand.data_ptr())
+            elif rnd == 0:
+                self.d_ncand.zero_()
 
     def step_device(self, k=21, min_ani=0.9):
         """Everything after the upload, enqueued on the current stream: my_table / my_counts (device)
@@ -118,6 +198,8 @@ class ShardedPrefilter:
         st = t.cuda.current_stream().cuda_stream
         n, s, w, r = self.n, self.s, self.world, self.rank
         m = w * self.nbp * self.epb
+        if self.ring:
+            return self._step_ring(k, min_ani)
         if self.local_build:
             gb.table_max_device(self.my_table.data_ptr(), self.my_counts.data_ptr(), self.n_local, s,
                                 self.gmax.data_ptr(), st)

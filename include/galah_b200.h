@@ -153,6 +153,18 @@ int galah_b200_blocklist_layout(size_t n, size_t stride, size_t *n_blocks, size_
 int galah_b200_blocklist_build(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                                size_t stride, size_t block_begin, size_t block_end, uint32_t *d_hi,
                                uint32_t *d_lo, uint8_t *d_tags, uint32_t *d_len, void *stream);
+/* Join of an explicit list of block pairs: d_items holds n_items (rb, cb) pairs of uint32 with
+ * rb <= cb (put the diagonal pairs first: they take longest).  Every pair's two lists and the
+ * table rows of both blocks must be resident; candidates are APPENDED to d_cand (reset_candidates
+ * != 0 zeroes the counter first).  The multi-GPU ring uses one call per peer slice as its lists
+ * arrive, so the exchange overlaps the join. */
+int galah_b200_prefilter_join_items_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
+                                            size_t stride, uint8_t k, float min_ani, const uint32_t *d_hi,
+                                            const uint32_t *d_lo, const uint8_t *d_tags, const uint32_t *d_len,
+                                            const uint32_t *d_items, size_t n_items, int reset_candidates,
+                                            void *stream, uint32_t *d_cand, size_t cand_cap,
+                                            unsigned long long *d_n_cand);
+
 /* Multi-GPU form that needs no gathered table for the build: every rank holds a slice of whole
  * row blocks (its first row a multiple of GALAH_B200_ROW_BLOCK).  table_max: largest valid hash
  * of the slice -> *d_max (device uint64; combine across ranks with an all-reduce MAX).
