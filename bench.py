@@ -284,7 +284,9 @@ def main():
             flush.fill_(1)  # L2 flush between timed iterations (outside the events)
             sync_all()
             ev0.record(stream)
+            t_host = time.perf_counter()
             step()
+            host_enqueue_ms.append(1e3 * (time.perf_counter() - t_host))
             ev1.record(stream)
             torch.cuda.synchronize()
             step_ms.append(ev0.elapsed_time(ev1))
@@ -296,6 +298,8 @@ def main():
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         return float(tot.item()), launches, float(np.mean(build_ms)), float(np.mean(main_ms))
+
+    host_enqueue_ms = []
 
     def sync_all():
         torch.cuda.synchronize()
@@ -505,6 +509,7 @@ def main():
                                 "their f64 finish runs on the host while the kernels run" if world == 1 else "per-rank slice upload, NVLink all-gathers",
                     "host_ms": e2e_host, "single_upload": e2e_single_upload},
             "gpu_launches": launches,
+            "host_enqueue_ms_per_step": float(np.median(host_enqueue_ms[: args.steps])) if host_enqueue_ms else None,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(kernel_names[args.mode], n, world),
                          "traffic_unit": "bytes per launch (ncu dram read + write, profiles/ncu_traffic.json)",

@@ -82,7 +82,8 @@ class ShardedPrefilter:
     on NCCL's stream WHILE the lists are built.  Otherwise the table is gathered first and every
     rank builds 1/G of the blocks from it.  Buffers are allocated once and re-used.
 
-    With whole-block slices and G > 1 the exchange is a RING instead of all-gathers: block pair
+    Experimental (GALAH_B200_RING=1): with whole-block slices and G > 1 the exchange can be a RING
+    instead of all-gathers: block pair
     {b1 <= b2} belongs to the rank that built b1 if b1 + b2 is even, else to the one that built b2
     (every rank gets the same share and every item has one local list).  In round k a rank sends
     its lists + table slice to rank r+k and receives those of rank r-k (NCCL send/recv over
@@ -118,7 +119,10 @@ class ShardedPrefilter:
         self.d_ncand = t.zeros(1, dtype=t.int64, device=device)
         self.h_cand = t.empty((self.cand_cap, 4), dtype=t.int32).pin_memory()
         import os
-        self.ring = self.local_build and self.world > 1 and not os.environ.get("GALAH_B200_NO_RING")
+        # experimental, off by default (GALAH_B200_RING=1): bit-exact (tools/check_sharded.py), but at
+        # G = 2 it measured no faster than the all-gathers -- NCCL's send/recv kernels get no SM while
+        # the persistent join CTAs run, so the rounds do not overlap the join yet
+        self.ring = self.local_build and self.world > 1 and os.environ.get("GALAH_B200_RING") == "1"
         if self.ring:
             self._init_ring()
 

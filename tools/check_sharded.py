@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ok = True
-    for n_local, ragged in ((256, False), (384, True), (200, False)):  # whole-block slices (ring) and not (gather-first)
+    # whole-block slices (local build; ring exchange when GALAH_B200_RING=1) and not (gather-first)
+    for n_local, ragged in ((256, False), (384, True), (200, False)):
         n = n_local * world
         rng = np.random.default_rng(100 + n_local)
         table, counts = random_family_table(n, 1000, rng, ragged=ragged)
