@@ -91,6 +91,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Drop what was sampled so far, but keep the latest row so that a timed region shorter
+        than the sampling interval still has a reading taken under the same load."""
+        self.rows = self.rows[-1:]
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -308,9 +313,11 @@ def main():
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a moment to start: launched ahead of the warm-up passes
     timed(args.mode, 0, args.warmup)
     if rank == 0:
-        sampler.start()
+        sampler.mark()   # only samples from here on (the timed region) are kept
     total_ms, launches, build_ms, main_ms = timed(args.mode, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     pairs = n * (n - 1) // 2
