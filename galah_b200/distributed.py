@@ -31,6 +31,35 @@ def pairs_of_shard(n, shard, n_shards, row_block=ROW_BLOCK):
     return int(np.sum(n - 1 - rows))
 
 
+def ring_round_items(rank, world, blocks_per_rank):
+    """Work lists of the ring exchange: for every round k the (rb, cb) block pairs, rb <= cb, that
+    `rank` joins once the lists of peer (rank - k) % world are resident (round 0: its own slice).
+    Block b is built by rank b // blocks_per_rank.  Pair {b1 <= b2} belongs to the builder of b1 if
+    b1 + b2 is even, else to the builder of b2, so every pair has exactly one owner, every owner
+    holds one of the two lists locally and all ranks get the same share.  Round 0 lists the
+    diagonal pairs first, then by distance (they take longest).  Returns a list of (m, 2) int32 arrays."""
+    r, nbp = rank, blocks_per_rank
+    mine = np.arange(r * nbp, (r + 1) * nbp, dtype=np.int64)
+    rounds = []
+    for k in range(world):
+        peer = (r - k) % world
+        if k == 0:
+            a, b = np.meshgrid(mine, mine, indexing="ij")
+            keep = a <= b
+            lo, hi = a[keep], b[keep]
+            order = np.lexsort((hi, lo, hi - lo))
+            lo, hi = lo[order], hi[order]
+        else:
+            theirs = np.arange(peer * nbp, (peer + 1) * nbp, dtype=np.int64)
+            a, b = np.meshgrid(mine, theirs, indexing="ij")
+            lo, hi = np.minimum(a, b).ravel(), np.maximum(a, b).ravel()
+            owner = np.where((lo + hi) % 2 == 0, lo // nbp, hi // nbp)
+            keep = owner == r
+            lo, hi = lo[keep], hi[keep]
+        rounds.append(np.ascontiguousarray(np.stack([lo, hi], axis=1).astype(np.int32)))
+    return rounds
+
+
 def all_gather_table(local_table, local_counts, dist, device=None):
     """All-gather equally sized row slices into the full table (rank order = genome order).
     local_table: torch tensor (n_local, s) int64; local_counts: (n_local,) int32."""
@@ -130,26 +159,10 @@ class ShardedPrefilter:
         """Per round k the explicit item list (rb, cb) this rank joins once peer (rank - k)'s lists are
         resident; round 0 = the items inside its own slice (diagonal items first: they take longest)."""
         t, G, r, nbp = self.torch, self.world, self.rank, self.nbp
-        mine = np.arange(r * nbp, (r + 1) * nbp, dtype=np.int64)
         self.round_items, self.round_n = [], []
-        for k in range(G):
-            peer = (r - k) % G
-            if k == 0:
-                a, b = np.meshgrid(mine, mine, indexing="ij")
-                keep = a <= b
-                lo, hi = a[keep], b[keep]
-                order = np.lexsort((hi, lo, hi - lo))  # diagonal, then adjacent, then by distance
-                lo, hi = lo[order], hi[order]
-            else:
-                theirs = np.arange(peer * nbp, (peer + 1) * nbp, dtype=np.int64)
-                a, b = np.meshgrid(mine, theirs, indexing="ij")
-                lo, hi = np.minimum(a, b).ravel(), np.maximum(a, b).ravel()
-                owner = np.where((lo + hi) % 2 == 0, lo // nbp, hi // nbp)
-                keep = owner == r
-                lo, hi = lo[keep], hi[keep]
-            items = np.stack([lo, hi], axis=1).astype(np.int32)
+        for items in ring_round_items(r, G, nbp):
             self.round_n.append(len(items))
-            self.round_items.append(t.from_numpy(np.ascontiguousarray(items)).to(self.dev) if len(items) else None)
+            self.round_items.append(t.from_numpy(items).to(self.dev) if len(items) else None)
         # views of this rank's slice inside the table-wide buffers: lists are built and the slice is
         # uploaded in place, peers' slices are received into theirs
         e, nl = nbp * self.epb, self.n_local

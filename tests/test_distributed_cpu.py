@@ -70,3 +70,32 @@ def test_shard_ownership_is_a_balanced_partition():
         assert sum(area) == n * (n - 1) // 2
         assert max(area) / (sum(area) / g) < 1.01  # boustrophedon 64-row blocks balance the triangle
         assert all(int(gd.owner_of_row(int(r[0]), g)) == x for x, r in enumerate(rows))
+
+
+def test_ring_ownership_partitions_the_block_pairs():
+    """The ring exchange's symmetric ownership: every block pair {b1 <= b2} is joined by exactly one
+    rank, that rank built one of the two lists, round k only needs the lists of peer rank - k, and
+    the shares are balanced."""
+    from galah_b200.distributed import ring_round_items
+    for world, nbp in ((2, 3), (3, 4), (4, 5), (8, 30), (8, 1)):
+        nb = world * nbp
+        seen = np.zeros((nb, nb), np.int32)
+        shares = []
+        for r in range(world):
+            rounds = ring_round_items(r, world, nbp)
+            assert len(rounds) == world
+            total = 0
+            for k, items in enumerate(rounds):
+                peer = (r - k) % world
+                for rb, cb in items:
+                    assert rb <= cb
+                    owners = {int(rb) // nbp, int(cb) // nbp}
+                    assert r in owners and owners <= {r, peer}
+                    seen[rb, cb] += 1
+                total += len(items)
+            # round 0 starts with the diagonal pairs of the rank's own slice
+            assert all(a == b for a, b in rounds[0][:nbp])
+            shares.append(total)
+        iu = np.triu_indices(nb)
+        assert np.all(seen[iu] == 1) and seen.sum() == len(iu[0])
+        assert max(shares) - min(shares) <= nbp * nbp // 2 + nbp
