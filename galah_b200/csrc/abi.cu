@@ -110,6 +110,10 @@ struct CandFinisher {
         const double a = mash_ani_f64(x.z, x.w, k);
         c.push_back(x); ani.push_back((float)a); keep.push_back(a >= thr ? 1 : 0);
     }
+    void set(size_t q, const uint4 &x) {
+        const double a = mash_ani_f64(x.z, x.w, k);
+        c[q] = x; ani[q] = (float)a; keep[q] = a >= thr ? 1 : 0;
+    }
     int finalize(galah_b200_pair_t **out, size_t *n_out) const {
         const size_t n_cand = c.size();
         uint32_t max_i = 0;
@@ -240,6 +244,13 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
             g_ctx.host_ms[1] = (float)(now_ms() - t_wait);
             const size_t written = (size_t)std::min<unsigned long long>(got, g_ctx.cap_cand_map);
             if (got <= g_ctx.cap_cand_map) {
+                // entries consumed while the kernels were running are compared once more with the
+                // final memory: a 16-byte device store reaches host memory in one piece on every
+                // platform this runs on, but nothing written down guarantees it
+                for (size_t q = 0; q < next; q++) {
+                    const uint4 now = make_uint4(hc[q].x, hc[q].y, hc[q].z, hc[q].w);
+                    if (memcmp(&now, &fin.c[q], sizeof(uint4)) != 0) fin.set(q, now);
+                }
                 drain(written);  // everything is in place once the kernels have completed
                 if (next != written) {
                     memset(g_ctx.h_cand_map, 0, g_ctx.cap_cand_map * sizeof(uint4));
