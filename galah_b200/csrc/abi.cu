@@ -403,7 +403,7 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
 
         // ---- K0 path (whole-genome units): host threads only read (and inflate) the files; the
         // raw bytes cross PCIe once and are decoded on the device (csrc/ingest.cu)
-        if (!sinks.per_record && g_ctx.device_ingest) {
+        if (g_ctx.device_ingest) {
             std::vector<std::vector<uint8_t>> raw(want);
             auto reader = [&]() {
                 for (;;) {
@@ -425,33 +425,38 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
                 if (p < raw[x].size() && raw[x][p] != '>') all_fasta = false;
             }
             if (all_fasta) {
-                const size_t unit0 = sinks.n_units;
-                sinks.n_units += want;
                 size_t b0 = 0;
                 while (b0 < want) {  // sub-batches of at most ~2 GiB of raw bytes
                     size_t b1 = b0; uint64_t bytes = 0;
                     while (b1 < want && (b1 == b0 || bytes + raw[b1].size() + 32 <= kMaxBatchBases)) { bytes += raw[b1].size() + 32; b1++; }
-                    const size_t nb = b1 - b0;
                     RawBatch rb;
                     if (int rc = stage_raw(std::vector<std::vector<uint8_t>>(std::make_move_iterator(raw.begin() + b0),
                                                                             std::make_move_iterator(raw.begin() + b1)), rb))
                         return rc;
-                    DecodedFiles dec;
+                    DecodedFiles dec, split;
                     if (int rc = g_ctx.fasta.decode(rb.bytes, rb.file_off, rb.file_len, rb.first_byte, dec, st)) return rc;
+                    // contig mode: every record becomes its own unit (split on the device)
+                    if (sinks.per_record)
+                        if (int rc = g_ctx.fasta.split_records(dec, split, st)) return rc;
+                    const DecodedFiles &un = sinks.per_record ? split : dec;
+                    const size_t nb = un.n_bases.size();
                     std::vector<uint64_t> contig_off(nb + 1, 0);
                     std::vector<uint32_t> cs, cl;
                     uint64_t longest = 0;
                     for (size_t x = 0; x < nb; x++) {
-                        for (uint64_t r = dec.rec_off[x]; r < dec.rec_off[x + 1]; r++) {
-                            cs.push_back((uint32_t)dec.rec_start[r]);
-                            cl.push_back((uint32_t)(dec.rec_end[r] - dec.rec_start[r]));
+                        for (uint64_t r = un.rec_off[x]; r < un.rec_off[x + 1]; r++) {
+                            cs.push_back((uint32_t)un.rec_start[r]);
+                            cl.push_back((uint32_t)(un.rec_end[r] - un.rec_start[r]));
                         }
                         contig_off[x + 1] = cs.size();
-                        longest = std::max(longest, dec.n_bases[x]);
+                        longest = std::max(longest, un.n_bases[x]);
                     }
-                    if (int rc = feed(dec.d_seq2, dec.d_valid, dec.d_base_off, nb, dec.base_off, contig_off, cs, cl, longest,
-                                      unit0 + b0, done + b1))
-                        return rc;
+                    const size_t unit_first = sinks.n_units;
+                    sinks.n_units += nb;
+                    if (nb)
+                        if (int rc = feed(un.d_seq2, un.d_valid, un.d_base_off, nb, un.base_off, contig_off, cs, cl, longest,
+                                          unit_first, done + b1))
+                            return rc;
                     b0 = b1;
                 }
                 done += want;

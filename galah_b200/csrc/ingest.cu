@@ -263,6 +263,45 @@ __global__ void __launch_bounds__(kDecThreads) fasta_pack_kernel(const DecParams
         if (s_val[x]) atomicOr(&q.valid[wv0 + x], s_val[x]);
 }
 
+// Contig mode: copy every record out of the packed files into its own 128-padded unit.  One thread
+// per destination validity word (32 bases = two sequence words): the unit is found by binary
+// search on the destination offsets, the source bits arrive by funnel shifts at an arbitrary
+// bit offset, everything past the unit's length is zero.
+__global__ void __launch_bounds__(256) fasta_split_kernel(const uint32_t *__restrict__ src_seq2,
+                                                          const uint32_t *__restrict__ src_valid,
+                                                          const uint64_t *__restrict__ unit_src,
+                                                          const uint64_t *__restrict__ unit_off,
+                                                          const uint64_t *__restrict__ unit_len, uint32_t n_units,
+                                                          uint64_t n_words, uint32_t *__restrict__ dst_seq2,
+                                                          uint32_t *__restrict__ dst_valid) {
+    for (uint64_t gw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gw < n_words;
+         gw += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t d = gw << 5;  // first destination base of this word
+        uint32_t lo = 0, hi = n_units;  // last unit with unit_off[u] <= d
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (unit_off[mid] <= d) lo = mid; else hi = mid;
+        }
+        const uint64_t b = d - unit_off[lo], len = unit_len[lo];
+        uint32_t v = 0, s0 = 0, s1 = 0;
+        if (b < len) {
+            const uint32_t rem = (uint32_t)min((uint64_t)32, len - b);  // bases of the unit in this word
+            const uint64_t s = unit_src[lo] + b;
+            const uint32_t vmask = rem >= 32 ? 0xFFFFFFFFu : (1u << rem) - 1u;
+            v = __funnelshift_r(src_valid[s >> 5], src_valid[(s >> 5) + 1], (uint32_t)s & 31u) & vmask;
+            const uint32_t r0 = min(rem, 16u), r1 = rem > 16 ? rem - 16u : 0u;
+            const uint32_t m0 = r0 >= 16 ? 0xFFFFFFFFu : (1u << (2u * r0)) - 1u;
+            const uint32_t m1 = r1 >= 16 ? 0xFFFFFFFFu : (1u << (2u * r1)) - 1u;
+            s0 = __funnelshift_r(src_seq2[s >> 4], src_seq2[(s >> 4) + 1], 2u * ((uint32_t)s & 15u)) & m0;
+            const uint64_t t = s + 16;
+            s1 = r1 ? __funnelshift_r(src_seq2[t >> 4], src_seq2[(t >> 4) + 1], 2u * ((uint32_t)t & 15u)) & m1 : 0u;
+        }
+        dst_valid[gw] = v;
+        dst_seq2[2 * gw] = s0;
+        dst_seq2[2 * gw + 1] = s1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------
@@ -285,6 +324,7 @@ void FastaDecoder::release() {
     d_summ_.release(); d_counts_.release(); d_chunk_base_.release(); d_chunk_rec_.release();
     d_chunk_begin_.release(); d_chunk_end_.release(); d_file_first_.release(); d_base_off_.release();
     d_rec_off_.release(); d_rec_start_.release(); d_rec_end_.release();
+    d_useq2_.release(); d_uvalid_.release(); d_unit_src_.release(); d_unit_off_.release(); d_unit_len_.release();
     for (int x = 0; x < 2; x++) if (ev_[x]) { cudaEventDestroy(ev_[x]); ev_[x] = nullptr; }
 }
 FastaDecoder::~FastaDecoder() { release(); }
@@ -403,6 +443,45 @@ int FastaDecoder::decode(const uint8_t *h_bytes, const std::vector<uint64_t> &fi
     for (size_t f = 0; f < nf; f++)  // the last record of a file ends with the file
         if (out.rec_off[f + 1] > out.rec_off[f]) out.rec_end[out.rec_off[f + 1] - 1] = out.n_bases[f];
     out.d_seq2 = d_seq2_.p; out.d_valid = d_valid_.p; out.d_base_off = d_base_off_.p;
+    return 0;
+}
+
+int FastaDecoder::split_records(const DecodedFiles &files, DecodedFiles &units, cudaStream_t st) {
+    const size_t nf = files.n_bases.size();
+    const size_t nu = files.rec_start.size();
+    units = DecodedFiles();
+    units.n_bases.assign(nu, 0); units.n_ambiguous.assign(nu, 0); units.n_N.assign(nu, 0);
+    units.rec_off.assign(nu + 1, 0); units.rec_start.assign(nu, 0); units.rec_end.assign(nu, 0);
+    units.base_off.assign(nu + 1, 0);
+    std::vector<uint64_t> src(std::max<size_t>(nu, 1)), len(std::max<size_t>(nu, 1));
+    size_t u = 0;
+    for (size_t f = 0; f < nf; f++)
+        for (uint64_t r = files.rec_off[f]; r < files.rec_off[f + 1]; r++, u++) {
+            len[u] = files.rec_end[r] - files.rec_start[r];
+            src[u] = files.base_off[f] + files.rec_start[r];
+            units.n_bases[u] = len[u];
+            units.rec_off[u + 1] = u + 1;
+            units.rec_end[u] = len[u];
+            units.base_off[u + 1] = units.base_off[u] + (len[u] + 127) / 128 * 128;
+        }
+    const uint64_t total = units.base_off[nu];
+    if (d_useq2_.ensure(total / 16 + 16) || d_uvalid_.ensure(total / 32 + 16) || d_unit_src_.ensure(nu) ||
+        d_unit_off_.ensure(nu + 1) || d_unit_len_.ensure(nu))
+        return 2;
+    GB_CUDA(cudaMemcpyAsync(d_unit_off_.p, units.base_off.data(), (nu + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nu && total) {
+        GB_CUDA(cudaMemcpyAsync(d_unit_src_.p, src.data(), nu * 8, cudaMemcpyHostToDevice, st));
+        GB_CUDA(cudaMemcpyAsync(d_unit_len_.p, len.data(), nu * 8, cudaMemcpyHostToDevice, st));
+        const uint64_t n_words = total / 32;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_words + 255) / 256, 148ull * 32);
+        fasta_split_kernel<<<grid, 256, 0, st>>>(files.d_seq2, files.d_valid, d_unit_src_.p, d_unit_off_.p, d_unit_len_.p,
+                                                 (uint32_t)nu, n_words, d_useq2_.p, d_uvalid_.p);
+        GB_LAUNCH_CHECK();
+    }
+    GB_CUDA(cudaMemsetAsync(d_useq2_.p + total / 16, 0, 16 * 4, st));
+    GB_CUDA(cudaMemsetAsync(d_uvalid_.p + total / 32, 0, 16 * 4, st));
+    GB_CUDA(cudaStreamSynchronize(st));  // the host staging vectors die here
+    units.d_seq2 = d_useq2_.p; units.d_valid = d_uvalid_.p; units.d_base_off = d_unit_off_.p;
     return 0;
 }
 

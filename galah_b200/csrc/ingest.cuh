@@ -37,6 +37,11 @@ public:
     // if there is none.  All files FASTA.
     int decode(const uint8_t *h_bytes, const std::vector<uint64_t> &file_off, const std::vector<uint64_t> &file_len,
                const std::vector<uint64_t> &first_byte, DecodedFiles &out, cudaStream_t st);
+    // Contig mode (`--cluster-contigs`, src/cluster_argument_parsing.rs:573-629): every record of the
+    // decoded files becomes its own unit -- bases only, no separators, each unit padded to a multiple
+    // of 128 -- by one bit-shifting copy kernel on the device.  `units` gets one entry per record
+    // (rec_start = 0, rec_end = length) and device arrays owned by the decoder.
+    int split_records(const DecodedFiles &files, DecodedFiles &units, cudaStream_t st);
     float last_ms = 0.f;  // device time of the last decode (three kernels + the scans' round trips)
     void release();
 
@@ -51,6 +56,8 @@ private:
     Buf<uint8_t> d_bytes_, d_inhdr_;
     Buf<uint32_t> d_seq2_, d_valid_, d_chunk_file_, d_summ_, d_counts_, d_chunk_base_, d_chunk_rec_;
     Buf<uint64_t> d_chunk_begin_, d_chunk_end_, d_file_first_, d_base_off_, d_rec_off_, d_rec_start_, d_rec_end_;
+    Buf<uint32_t> d_useq2_, d_uvalid_;
+    Buf<uint64_t> d_unit_src_, d_unit_off_, d_unit_len_;
     cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
 

@@ -355,8 +355,9 @@ int galah_b200_pack_fasta_file(const char *path, uint32_t **seq2, uint32_t **val
 /* K0: the same ingest ON THE DEVICE (csrc/ingest.cu).  The file-taking entry points
  * (galah_b200_sketch_files, _ani_index_add_files, _finch_distances, _cluster_files, ...) use it for
  * whole-genome FASTA input: host threads only read / inflate the files, the raw bytes are uploaded
- * once and three kernels classify, count and pack them into the layout K1 / K3 read.  FASTQ
- * input and contig mode (one unit per record) take the host packer.
+ * once and three kernels classify, count and pack them into the layout K1 / K3 read; in contig
+ * mode (one unit per record) a fourth kernel copies every record into its own unit.  FASTQ
+ * input takes the host packer.
  * galah_b200_device_ingest(0 / 1) switches the device path off / on (< 0 only queries); returns
  * the previous setting (default 1).
  * galah_b200_decode_fasta_device is the parity / measurement hook: n in-memory FASTA files ->

@@ -105,3 +105,29 @@ def test_file_entry_points_agree_with_host_ingest(gb, tmp_path):
     finally:
         gb.device_ingest(prev)
     assert np.array_equal(t1, t0) and np.array_equal(c1, c0)
+
+
+def test_contig_mode_units_agree_with_host_packer(gb, tmp_path):
+    """--cluster-contigs: every record is a unit.  The device path (K0 decode + record split) must
+    give the same units as the host packer: identical skani-preclusterer output, including empty
+    records, records shorter than one word, and records that are not multiples of 16 / 32 bases."""
+    from test_skani_precluster_gpu import mutate
+    rng = np.random.default_rng(21)
+    base = random_dna(41_003, rng)
+    recs1 = [("a", base), ("empty", b""), ("a95", mutate(base, 0.05, rng)), ("tiny", random_dna(7, rng)),
+             ("b", random_dna(33_333, rng))]
+    recs2 = [("b97", mutate(recs1[4][1], 0.03, rng)), ("c", random_dna(20_001, rng)), ("a99", mutate(base, 0.01, rng))]
+    p1 = write_fasta(str(tmp_path / "m1.fna"), recs1, width=70)
+    p2 = write_fasta(str(tmp_path / "m2.fna"), recs2, width=60, newline="\r\n")
+    prev = gb.device_ingest(1)
+    try:
+        dev_hits, dev_units = gb.skani_distances([p1, p2], 90.0, 15.0, small_genomes=True, contigs=True)
+        gb.device_ingest(0)
+        host_hits, host_units = gb.skani_distances([p1, p2], 90.0, 15.0, small_genomes=True, contigs=True)
+    finally:
+        gb.device_ingest(prev)
+    assert dev_units == host_units == len(recs1) + len(recs2)
+    assert len(dev_hits) == len(host_hits) >= 3
+    for f in ("i", "j", "common", "total"):
+        assert np.array_equal(dev_hits[f], host_hits[f]), f
+    assert np.array_equal(dev_hits["ani"].view(np.uint32), host_hits["ani"].view(np.uint32))
