@@ -320,13 +320,43 @@ static int stage_raw(const std::vector<std::vector<uint8_t>> &files, RawBatch &r
 // One pass over FASTA files feeding K1 (sketches) and/or the K3 index from the SAME upload:
 // files are parsed and packed on host threads, a batch is concatenated (genome offsets multiples
 // of 128), copied to the device once, and handed to the requested sinks.
+// Marker sketches of all units, resident on the device in the K2 table layout (common row stride):
+// the file-based skani preclusterer fills it batch by batch and hands it to the screen as it is.
+struct MarkerTable {
+    uint64_t *d_rows = nullptr;
+    uint32_t *d_counts = nullptr;
+    size_t n = 0, cap_rows = 0;
+    uint32_t stride = 0;
+    ~MarkerTable() { if (d_rows) cudaFree(d_rows); if (d_counts) cudaFree(d_counts); }
+    // room for `rows` rows of `new_stride` (>= stride) hashes; existing rows keep their content
+    int reserve(size_t rows, uint32_t new_stride, cudaStream_t st) {
+        new_stride = std::max(new_stride, stride);
+        if (rows <= cap_rows && new_stride == stride) return 0;
+        const size_t new_cap = std::max(rows, rows <= cap_rows ? cap_rows : std::max(rows, 2 * cap_rows));
+        uint64_t *nr = nullptr;
+        uint32_t *nc = nullptr;
+        GB_CUDA(cudaMalloc(&nr, std::max<size_t>(new_cap * (size_t)new_stride, 1) * 8));
+        GB_CUDA(cudaMalloc(&nc, std::max<size_t>(new_cap, 1) * 4));
+        if (n) {
+            GB_CUDA(cudaMemcpy2DAsync(nr, (size_t)new_stride * 8, d_rows, (size_t)stride * 8, (size_t)stride * 8, n,
+                                      cudaMemcpyDeviceToDevice, st));
+            GB_CUDA(cudaMemcpyAsync(nc, d_counts, n * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        GB_CUDA(cudaStreamSynchronize(st));
+        if (d_rows) GB_CUDA(cudaFree(d_rows));
+        if (d_counts) GB_CUDA(cudaFree(d_counts));
+        d_rows = nr; d_counts = nc; cap_rows = new_cap; stride = new_stride;
+        return 0;
+    }
+};
+
 struct IngestSinks {
     bool sketch = false;
     int k = 21; uint32_t s = 1000; uint64_t seed = 0;
     uint64_t *hashes = nullptr; uint32_t *counts = nullptr;  // host rows, stride s
     AniIndex *ani = nullptr;
     // FracMinHash marker sketches (k = 21, density 1/c_marker): one ascending hash list per unit
-    std::vector<std::vector<uint64_t>> *markers = nullptr;
+    MarkerTable *markers = nullptr;
     uint32_t c_marker = 1000;
     bool per_record = false;  // contig mode: every FASTA record is its own unit
     size_t n_units = 0;       // out: genomes (or records) ingested
@@ -358,26 +388,27 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
             GB_CUDA(cudaStreamSynchronize(st));
         }
         if (sinks.markers) {
+            MarkerTable &mt = *sinks.markers;
             uint32_t cap = 256;
             while (cap < 16384 && cap < 1.5 * (double)longest / sinks.c_marker + 256.0) cap <<= 1;
-            DevBuf<uint64_t> d_rows;
-            DevBuf<uint32_t> d_counts;
-            if (d_rows.alloc(nb * (size_t)cap) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
-            int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, 21, sinks.c_marker, cap, d_rows.p,
-                                           d_counts.p, st);
+            // rows for everything still to come (units per file as seen so far), common stride
+            const double per_file = (double)sinks.n_units / (double)std::max<size_t>(files_done, 1);
+            const size_t rows_hint = std::max(mt.n + nb, (size_t)(per_file * (double)n) + 1);
+            if (int rc = mt.reserve(mt.n + nb > mt.cap_rows ? rows_hint : mt.n + nb, cap, st)) return rc;
+            uint64_t *d_rows = mt.d_rows + mt.n * (size_t)mt.stride;
+            uint32_t *d_cnt = mt.d_counts + mt.n;
+            int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, 21, sinks.c_marker, mt.stride, d_rows,
+                                           d_cnt, st);
             if (rc) return rc;
-            std::vector<uint64_t> rows(nb * (size_t)cap);
             std::vector<uint32_t> cnt(nb);
-            GB_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, rows.size() * 8, cudaMemcpyDeviceToHost, st));
-            GB_CUDA(cudaMemcpyAsync(cnt.data(), d_counts.p, nb * 4, cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, nb * 4, cudaMemcpyDeviceToHost, st));
             GB_CUDA(cudaStreamSynchronize(st));
-            for (size_t x = 0; x < nb; x++) {
+            for (size_t x = 0; x < nb; x++)
                 if (cnt[x] == 0xFFFFFFFFu) {
                     set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
                     return GALAH_B200_ERR_UNSUPPORTED;
                 }
-                sinks.markers->emplace_back(rows.begin() + x * (size_t)cap, rows.begin() + x * (size_t)cap + cnt[x]);
-            }
+            mt.n += nb;
         }
         if (sinks.ani) {
             const size_t before = sinks.ani->size();
@@ -596,7 +627,7 @@ static int skani_distances_impl(const char *const *paths, size_t n, float thresh
         return GALAH_B200_ERR_UNSUPPORTED;
     }
     AniIndex index(small_genomes ? 30u : 125u);
-    std::vector<std::vector<uint64_t>> markers;
+    MarkerTable markers;  // marker sketches stay on the device, in the K2 table layout
     IngestSinks sinks;
     sinks.ani = &index; sinks.markers = &markers; sinks.c_marker = small_genomes ? 200u : 1000u;
     sinks.per_record = per_record;
@@ -604,23 +635,9 @@ static int skani_distances_impl(const char *const *paths, size_t n, float thresh
     n_units = sinks.n_units;
     out.clear(); n_screened = 0;
     if (n_units < 2) return 0;
-    // marker table with a common even stride
-    size_t stride = 2;
-    for (auto &m : markers) stride = std::max(stride, m.size() + (m.size() & 1));
-    std::vector<uint64_t> table(n_units * stride, kPad);
-    std::vector<uint32_t> counts(n_units);
-    for (size_t g = 0; g < n_units; g++) {
-        std::copy(markers[g].begin(), markers[g].end(), table.begin() + g * stride);
-        counts[g] = (uint32_t)markers[g].size();
-    }
-    markers.clear(); markers.shrink_to_fit();
-    if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, table.size()) || ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, n_units))
-        return GALAH_B200_ERR_CUDA;
-    cudaStream_t st = g_ctx.stream;
-    GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, table.data(), table.size() * 8, cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(g_ctx.d_counts, counts.data(), n_units * 4, cudaMemcpyHostToDevice, st));
-    return skani_screen_and_ani(index, g_ctx.d_table, g_ctx.d_counts, n_units, stride, threshold_pct, min_af_pct, st, out,
-                                n_screened, nullptr);
+    if (markers.n != n_units) { set_error("skani preclusterer: marker table out of step with the units"); return GALAH_B200_ERR_ARG; }
+    return skani_screen_and_ani(index, markers.d_rows, markers.d_counts, n_units, markers.stride, threshold_pct,
+                                min_af_pct, g_ctx.stream, out, n_screened, nullptr);
 }
 
 }  // namespace gb200
