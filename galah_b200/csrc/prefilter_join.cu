@@ -2,42 +2,50 @@
 //
 // Replaces the serial loop at /root/reference/src/finch.rs:75-95 (for every i<j:
 // finch::distance::distance(s_i, s_j, false) -> raw_distance -> common, total).  The reference
-// walks 2s merge steps per pair.  Here the table is cut into blocks of R = kShardRows = 64
+// walks 2s merge steps per pair.  Here the table is cut into blocks of R = kShardRows = 128
 // consecutive sketches and each block is merged ONCE into a single ascending list of
 // (value, row-tag) entries ("block list", R*s entries).  A work item (rb, cb) then merge-
 // intersects block list rb with block list cb: every equal (a, b) adds 1 to
-// cnt[tag(a)][tag(b)], an R x R matrix in shared memory, so ONE merge of 2*R*s entries yields
-// the exact |A n B| of R*R pairs -- 2s/R merge steps and 2*s*9/R bytes per pair.  `total`
-// follows from one rank query per surviving pair (see prefilter.cu, "Exactness notes").
+// cnt[tag(a)][tag(b)], an R x R matrix of 16-bit counters in shared memory, so ONE merge of
+// 2*R*s entries yields the exact |A n B| of R*R pairs -- 2s/R merge steps and 2*s*4/R bytes per
+// pair.  `total` follows from one rank query per surviving pair (see prefilter.cu, "Exactness
+// notes").
 //
 // Kernels
-//   bl_init_kernel    table rows -> level-0 lists: entry = (value, tag = row % R), padding =
-//                     (2^64-1, 0xFF).  bl_len_kernel: valid entries per block (sum of counts).
-//   bl_merge_kernel   one level of the merge tree (runs of m entries -> runs of 2m), log2(R)
-//                     launches ping-ponging two buffers.  CTA = one 2048-entry output tile:
-//                     merge-path split in global memory, operands staged in shared memory,
-//                     8 sequential merge steps per thread.  Keys are ordered by (value, tag), so
+//   bl_len_kernel     valid entries per block (sum of counts) and the table-wide largest hash.
+//   bl_seed_kernel    one CTA takes 8 table rows, forms their level-0 entries (value, tag = row % R;
+//                     padding = (2^64-1, 0xFF)) in shared memory and runs the first three merge
+//                     levels there (stride <= 1024; bl_init_kernel + global levels otherwise).
+//   bl_partition_kernel / bl_merge_tma_kernel
+//                     one level of the merge tree (runs of m entries -> runs of 2m), ping-ponging
+//                     two buffers.  The merge-path splits of all tile boundaries come from a
+//                     pre-pass (one warp per boundary, 32-ary search); a merge CTA owns one
+//                     2048-entry output tile: its A and B slices arrive by TMA bulk copies, every
+//                     thread merges 8 entries, the tile leaves by TMA bulk stores
+//                     (bl_merge_kernel is the same level with staged loads / stores, for run
+//                     lengths that are not multiples of 16).  Keys are ordered by (value, tag), so
 //                     padding sorts strictly after a genuine 2^64-1 hash and the first bl_len
 //                     entries of a block list are exactly its valid entries.  The LAST level
 //                     writes the lists as structure-of-arrays: with sh = clz(largest valid hash
 //                     of the table), w = value << sh is lossless, hi = w >> 32 is an
 //                     order-preserving 32-bit key and (hi, lo) equality is value equality.
-//   prefilter_join_kernel  persistent CTAs (3 per SM) pull (rb, cb) items from an atomic
-//                     counter.  The two lists are cut into segments of D = 4608 merged entries
-//                     by merge-path splits (binary searches through L2, all segments of the
-//                     tile in parallel); each segment's A and B slices (hi, lo, tags) are
-//                     brought in by six 1-D TMA bulk copies (cp.async.bulk + mbarrier
-//                     complete_tx, SASS UBLKCP); every thread then owns 18 consecutive merge
-//                     steps found by a second merge-path split in shared memory.  The merge
-//                     runs on the dense 32-bit hi keys only (one LDS.32 per step, branch-free,
-//                     fully unrolled when the segment touches no list end).  Ties are ordered
-//                     B-first, so when a thread takes b every a with the same key lies at or
-//                     after its A cursor; the (rare) tie path walks that key run and compares
-//                     lo words -- R extra entries are staged with the segment, and a key run
-//                     that outlasts them is followed in global memory.  Diagonal items
-//                     (rb == cb) need no merge: equal values are adjacent in the one list.
-//                     After the last segment the CTA scans cnt, applies the conservative
-//                     integer thresholds and appends survivors {i, j, common, total}.
+//   prefilter_join_kernel  persistent CTAs (3 per SM) pull items from an atomic counter, longest
+//                     first (diagonal, adjacent blocks, the rest; or an explicit list).  The two
+//                     lists are cut into segments of D = 9216 merged keys by merge-path splits
+//                     (binary searches through L2, all segments of the item in parallel); a
+//                     segment's A and B key slices are brought in by two 1-D TMA bulk copies
+//                     (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP); every thread then owns
+//                     two chains of 18 consecutive merge steps, each starting at its own
+//                     merge-path split in shared memory.  The merge runs on the dense 32-bit hi
+//                     keys only (one LDS.32 per step, branch-free, fully unrolled when the
+//                     segment touches no list end).  Ties are ordered B-first, so when a thread
+//                     takes b every a with the same key lies at or after its A cursor; tie steps
+//                     are recorded in a bit mask, queued, and resolved by the whole CTA at once
+//                     (lo words and tags from global memory / L2).  Diagonal items (rb == cb)
+//                     need no merge: equal values are adjacent in the one list (hi, lo and tags
+//                     staged; lock-step run walks).  After the last segment the CTA scans cnt,
+//                     applies the conservative integer thresholds and appends survivors
+//                     {i, j, common, total}.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
