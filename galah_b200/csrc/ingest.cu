@@ -104,32 +104,79 @@ __device__ __forceinline__ void block_excl_sum2(uint32_t a, uint32_t b, uint32_t
     __syncthreads();
 }
 
-// Record start at absolute position p holding byte b?  (prev = byte at p - 1, read only if p > first)
-__device__ __forceinline__ bool is_record_start(uint32_t b, uint64_t p, uint64_t first, uint32_t prev) {
-    return b == '>' && (p == first || (p > first && prev == '\n'));
+// Per-thread view of its 32 bytes as bit masks (bit k <-> byte k): computed once, every later phase
+// is bit arithmetic on them instead of another pass over the bytes.
+struct ByteMasks {
+    uint32_t start;  // record starts: '>' that is the file's first non-blank byte or follows '\n'
+    uint32_t nl;     // '\n'
+    uint32_t ws;     // dropped bytes: blanks, and everything at or past the chunk's end
+    uint32_t amb;    // ambiguous bases (not ACGTU, not blank)
+    uint32_t nN;     // literally 'N' / 'n'
+    uint64_t codes;  // 2-bit base codes (meaningful where the byte is an unambiguous base)
+};
+
+// lut: 256-entry class table in shared memory (0..3 base, 4 ambiguous, 5 dropped); lim: live bytes
+// of this thread; prev: the byte before the thread's first one; fk: index (0..31) of the file's
+// first non-blank byte if it is one of this thread's bytes, else >= 32.
+__device__ __forceinline__ ByteMasks byte_masks(const Bytes32 &by, int lim, uint32_t prev, uint32_t fk,
+                                                const uint8_t *lut) {
+    ByteMasks m;
+    m.start = 0; m.nl = 0; m.ws = 0; m.amb = 0; m.nN = 0; m.codes = 0;
+#pragma unroll
+    for (int k = 0; k < kDecPer; k++) {
+        const uint32_t b = by.at(k);
+        const uint32_t c = lut[b];
+        const bool st = b == '>' && (prev == '\n' || (uint32_t)k == fk);
+        m.start |= st ? (1u << k) : 0u;
+        m.nl |= b == '\n' ? (1u << k) : 0u;
+        m.ws |= c == 5u ? (1u << k) : 0u;
+        m.amb |= c == 4u ? (1u << k) : 0u;
+        m.nN |= (b | 0x20u) == 'n' ? (1u << k) : 0u;
+        m.codes |= (uint64_t)(c & 3u) << (2 * k);
+        prev = b;
+    }
+    const uint32_t live = lim >= 32 ? 0xFFFFFFFFu : ((1u << lim) - 1u);
+    m.start &= live; m.nl &= live; m.amb &= live; m.nN &= live;
+    m.ws |= ~live;
+    return m;
+}
+
+// In-header mask of the thread's bytes: byte k is inside a header line iff it is a record start,
+// or byte k-1 was inside one and was not the terminating '\n' (carry: the byte before the thread's
+// first one was).  A set-dominant latch = a prefix scan with generate = start, propagate =
+// "previous byte is no newline": five Kogge-Stone steps for all 32 bytes.
+__device__ __forceinline__ uint32_t header_mask(uint32_t start, uint32_t nl, bool carry) {
+    uint32_t G = start | (carry ? 1u : 0u), P = ~(nl << 1);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        G |= P & (G << d);
+        P &= P << d;
+    }
+    return G;
+}
+
+__device__ __forceinline__ void fill_lut(uint8_t *lut) {
+    for (uint32_t x = threadIdx.x; x < 256; x += blockDim.x) lut[x] = (uint8_t)norm_code(x);
 }
 
 __global__ void __launch_bounds__(kDecThreads) fasta_scan_kernel(const DecParams q) {
     __shared__ uint32_t s_h[8], s_n[8];
+    __shared__ uint8_t s_lut[256];
     const uint32_t c = blockIdx.x, tid = threadIdx.x;
     const uint64_t begin = q.chunk_begin[c], end = q.chunk_end[c];
     const uint64_t first = q.file_first[q.chunk_file[c]];
     const uint64_t p0 = begin + (uint64_t)tid * kDecPer;
+    fill_lut(s_lut);
+    __syncthreads();
     uint32_t last_h = 0, last_n = 0;
     if (p0 < end) {
         const Bytes32 by = load32(q.bytes + p0);
-        uint32_t prev = p0 > first ? q.bytes[p0 - 1] : 0u;
+        const uint32_t prev = p0 ? q.bytes[p0 - 1] : (uint32_t)'\n';
         const int lim = (int)min((uint64_t)kDecPer, end - p0);
-#pragma unroll
-        for (int k = 0; k < kDecPer; k++) {
-            if (k < lim) {
-                const uint32_t b = by.at(k);
-                const uint64_t p = p0 + k;
-                if (is_record_start(b, p, first, prev)) last_h = (uint32_t)p + 1u;
-                if (b == '\n') last_n = (uint32_t)p + 1u;
-                prev = b;
-            }
-        }
+        const uint32_t fk = first >= p0 && first - p0 < (uint64_t)kDecPer ? (uint32_t)(first - p0) : 64u;
+        const ByteMasks m = byte_masks(by, lim, prev, fk, s_lut);
+        if (m.start) last_h = (uint32_t)p0 + (31u - (uint32_t)__clz((int)m.start)) + 1u;
+        if (m.nl) last_n = (uint32_t)p0 + (31u - (uint32_t)__clz((int)m.nl)) + 1u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -149,6 +196,7 @@ template <bool kWrite>
 __global__ void __launch_bounds__(kDecThreads) fasta_pack_kernel(const DecParams q) {
     __shared__ uint32_t s_tmp[16];
     __shared__ uint32_t s_cnt[4];
+    __shared__ uint8_t s_lut[256];
     __shared__ uint32_t s_seq[kWrite ? kDecChunk / 16 + 4 : 1];
     __shared__ uint32_t s_val[kWrite ? kDecChunk / 32 + 4 : 1];
     const uint32_t c = blockIdx.x, tid = threadIdx.x;
@@ -161,59 +209,37 @@ __global__ void __launch_bounds__(kDecThreads) fasta_pack_kernel(const DecParams
     Bytes32 by;
 #pragma unroll
     for (int k = 0; k < 8; k++) by.w[k] = 0;
-    uint32_t prev0 = 0;
-    if (live) { by = load32(q.bytes + p0); prev0 = p0 > first ? q.bytes[p0 - 1] : 0u; }
+    uint32_t prev0 = '\n';
+    if (live) { by = load32(q.bytes + p0); prev0 = p0 ? q.bytes[p0 - 1] : (uint32_t)'\n'; }
+    fill_lut(s_lut);
     if (tid < 4) s_cnt[tid] = 0;
     if (kWrite) {
         for (uint32_t x = tid; x < kDecChunk / 16 + 4; x += kDecThreads) s_seq[x] = 0;
         for (uint32_t x = tid; x < kDecChunk / 32 + 4; x += kDecThreads) s_val[x] = 0;
     }
-    // ---- phase A: this thread's last record start / newline
-    uint32_t last_h = 0, last_n = 0;
-    {
-        uint32_t prev = prev0;
-#pragma unroll
-        for (int k = 0; k < kDecPer; k++) {
-            if (k < lim) {
-                const uint32_t b = by.at(k);
-                const uint64_t p = p0 + k;
-                if (is_record_start(b, p, first, prev)) last_h = (uint32_t)p + 1u;
-                if (b == '\n') last_n = (uint32_t)p + 1u;
-                prev = b;
-            }
-        }
-    }
+    __syncthreads();
+    // ---- phase A: the thread's bytes as bit masks; its last record start / newline
+    const uint32_t fk = live && first >= p0 && first - p0 < (uint64_t)kDecPer ? (uint32_t)(first - p0) : 64u;
+    const ByteMasks m = byte_masks(by, lim, prev0, fk, s_lut);
+    const uint32_t last_h = m.start ? (uint32_t)p0 + (31u - (uint32_t)__clz((int)m.start)) + 1u : 0u;
+    const uint32_t last_n = m.nl ? (uint32_t)p0 + (31u - (uint32_t)__clz((int)m.nl)) + 1u : 0u;
     // ---- phase B: running maxima before this thread (carry: the chunk starts inside a header)
     uint32_t H0, N0;
     block_excl_max2(last_h, last_n, q.chunk_in_header[c] ? (uint32_t)begin : 0u, 0u, H0, N0, s_tmp);
-    // ---- phase C: classify and count
-    uint32_t nb = 0, nrec = 0, namb = 0, nN = 0;
-    {
-        uint32_t H = H0, N = N0, prev = prev0;
-#pragma unroll
-        for (int k = 0; k < kDecPer; k++) {
-            if (k < lim) {
-                const uint32_t b = by.at(k);
-                const uint64_t p = p0 + k;
-                if (is_record_start(b, p, first, prev)) { H = (uint32_t)p + 1u; nrec++; }
-                const uint32_t code = norm_code(b);
-                if (H <= N && code != 5u) {
-                    nb++;
-                    if (code == 4u) { namb++; nN += (b == 'N' || b == 'n') ? 1u : 0u; }
-                }
-                if (b == '\n') N = (uint32_t)p + 1u;
-                prev = b;
-            }
-        }
-    }
+    // ---- phase C: classify and count (bit arithmetic)
+    const uint32_t hdr = header_mask(m.start, m.nl, H0 > N0);
+    const uint32_t base = ~hdr & ~m.ws;          // bytes that are bases (valid or ambiguous)
+    const uint32_t good = base & ~m.amb;         // unambiguous bases: the only ones that write bits
+    const uint32_t nb = (uint32_t)__popc(base), nrec = (uint32_t)__popc(m.start);
     if (!kWrite) {
+        uint32_t cb = nb, cr = nrec, ca = (uint32_t)__popc(base & m.amb), cn = (uint32_t)__popc(base & m.amb & m.nN);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            nb += __shfl_xor_sync(0xffffffffu, nb, o); nrec += __shfl_xor_sync(0xffffffffu, nrec, o);
-            namb += __shfl_xor_sync(0xffffffffu, namb, o); nN += __shfl_xor_sync(0xffffffffu, nN, o);
+            cb += __shfl_xor_sync(0xffffffffu, cb, o); cr += __shfl_xor_sync(0xffffffffu, cr, o);
+            ca += __shfl_xor_sync(0xffffffffu, ca, o); cn += __shfl_xor_sync(0xffffffffu, cn, o);
         }
         if ((tid & 31) == 0) {
-            atomicAdd(&s_cnt[0], nb); atomicAdd(&s_cnt[1], nrec); atomicAdd(&s_cnt[2], namb); atomicAdd(&s_cnt[3], nN);
+            atomicAdd(&s_cnt[0], cb); atomicAdd(&s_cnt[1], cr); atomicAdd(&s_cnt[2], ca); atomicAdd(&s_cnt[3], cn);
         }
         __syncthreads();
         if (tid < 4) q.counts[4 * c + tid] = s_cnt[tid];
@@ -224,39 +250,67 @@ __global__ void __launch_bounds__(kDecThreads) fasta_pack_kernel(const DecParams
     block_excl_sum2(nb, nrec, eb, er, s_tmp);
     const uint32_t cb0 = q.chunk_base0[c], cr0 = q.chunk_rec0[c];
     const uint64_t off = q.base_off[f], roff = q.rec_off[f];
-    // every position this CTA writes is >= G0 and < G0 + kDecChunk + 1
+    // every position this CTA writes is >= G0 and < G0 + kDecChunk + 1; A0 = G0 rounded down to a
+    // validity word, local = position - A0 < kDecChunk + 33
     const uint64_t G0 = off + cb0 + (cr0 ? cr0 - 1u : 0u);
-    const uint64_t ws0 = G0 >> 4, wv0 = G0 >> 5;
-    {
-        uint32_t H = H0, N = N0, prev = prev0;
-        uint64_t nbase = (uint64_t)cb0 + eb;  // bases of the file before the current byte
-        uint64_t r = (uint64_t)cr0 + er;      // record starts of the file before the current byte
+    const uint64_t A0 = G0 & ~31ull;
+    // position of a base = off + (bases of the file before it) + (record starts up to it) - 1
+    const int32_t dl = (int32_t)((int64_t)(off + cb0 + cr0) - 1 - (int64_t)A0);  // in [-1, 31]
+    if (m.start == 0) {
+        // no record starts among my bytes: my bases land on consecutive positions.  Compact their
+        // codes into one 64-bit run and OR <= 3 sequence words and <= 2 validity words.
+        if (base) {
+            const uint32_t L = (uint32_t)(dl + (int32_t)(eb + er));  // local position of my first base
+            uint64_t run = 0;
+            uint32_t vrun = 0, cnt = 0;
 #pragma unroll
-        for (int k = 0; k < kDecPer; k++) {
-            if (k < lim) {
-                const uint32_t b = by.at(k);
-                const uint64_t p = p0 + k;
-                if (is_record_start(b, p, first, prev)) {
-                    H = (uint32_t)p + 1u;
-                    if (r > 0) q.rec_end[roff + r - 1] = nbase + (r - 1);
-                    q.rec_start[roff + r] = nbase + r;
-                    r++;
-                }
-                const uint32_t code = norm_code(b);
-                if (H <= N && code != 5u) {
-                    if (code < 4u) {
-                        const uint64_t G = off + nbase + (r - 1);
-                        atomicOr(&s_seq[(G >> 4) - ws0], code << (2u * ((uint32_t)G & 15u)));
-                        atomicOr(&s_val[(G >> 5) - wv0], 1u << ((uint32_t)G & 31u));
+            for (int k = 0; k < kDecPer; k++) {
+                if ((base >> k) & 1u) {
+                    if ((good >> k) & 1u) {
+                        run |= ((m.codes >> (2 * k)) & 3ull) << (2u * cnt);
+                        vrun |= 1u << cnt;
                     }
-                    nbase++;
+                    cnt++;
                 }
-                if (b == '\n') N = (uint32_t)p + 1u;
-                prev = b;
+            }
+            if (vrun) {
+                const uint32_t ws = L >> 4, so = (L & 15u) * 2u;
+                const uint32_t r_lo = (uint32_t)run, r_hi = (uint32_t)(run >> 32);
+                const uint32_t w0 = r_lo << so;
+                const uint32_t w1 = so ? (r_lo >> (32u - so)) | (r_hi << so) : r_hi;
+                const uint32_t w2 = so ? (r_hi >> (32u - so)) : 0u;
+                if (w0) atomicOr(&s_seq[ws], w0);
+                if (w1) atomicOr(&s_seq[ws + 1], w1);
+                if (w2) atomicOr(&s_seq[ws + 2], w2);
+                const uint32_t wv = L >> 5, vo = L & 31u;
+                const uint32_t v0 = vrun << vo, v1 = vo ? vrun >> (32u - vo) : 0u;
+                if (v0) atomicOr(&s_val[wv], v0);
+                if (v1) atomicOr(&s_val[wv + 1], v1);
+            }
+        }
+    } else {
+        // a record starts among my bytes (rare): byte by byte, with the record bookkeeping
+        uint32_t q32 = eb, r32 = er;  // bases / record starts of this chunk before the current byte
+#pragma unroll 1
+        for (int k = 0; k < kDecPer; k++) {
+            if ((m.start >> k) & 1u) {
+                const uint64_t nbase = (uint64_t)cb0 + q32, r = (uint64_t)cr0 + r32;
+                if (r > 0) q.rec_end[roff + r - 1] = nbase + (r - 1);
+                q.rec_start[roff + r] = nbase + r;
+                r32++;
+            }
+            if ((base >> k) & 1u) {
+                if ((good >> k) & 1u) {
+                    const uint32_t L = (uint32_t)(dl + (int32_t)(q32 + r32));
+                    atomicOr(&s_seq[L >> 4], (uint32_t)((m.codes >> (2 * k)) & 3ull) << (2u * (L & 15u)));
+                    atomicOr(&s_val[L >> 5], 1u << (L & 31u));
+                }
+                q32++;
             }
         }
     }
     __syncthreads();
+    const uint64_t ws0 = A0 >> 4, wv0 = A0 >> 5;
     for (uint32_t x = tid; x < kDecChunk / 16 + 4; x += kDecThreads)
         if (s_seq[x]) atomicOr(&q.seq2[ws0 + x], s_seq[x]);
     for (uint32_t x = tid; x < kDecChunk / 32 + 4; x += kDecThreads)
