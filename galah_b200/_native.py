@@ -30,8 +30,10 @@ class Clusters(ctypes.Structure):
 
 class AniResult(ctypes.Structure):
     _fields_ = [("ani", ctypes.c_float), ("af_query", ctypes.c_float), ("af_ref", ctypes.c_float),
-                ("sum_m", ctypes.c_uint32), ("sum_n", ctypes.c_uint32), ("cov_q", ctypes.c_uint32),
-                ("cov_r", ctypes.c_uint32), ("swapped", ctypes.c_uint32)]
+                ("estimator", ctypes.c_uint32), ("sum_fx", ctypes.c_uint64), ("n_chunks", ctypes.c_uint32),
+                ("sum_m", ctypes.c_uint32), ("span_m", ctypes.c_uint32), ("span_n", ctypes.c_uint32),
+                ("n_chains", ctypes.c_uint32), ("cov_q", ctypes.c_uint32), ("cov_r", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
 
 
 class ClusterStats(ctypes.Structure):
@@ -97,7 +99,9 @@ _SIGNATURES = {
                                                   ctypes.c_uint8, ctypes.c_int, pairpp, sizep]),
     "galah_b200_ani_index_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(vp)]),
     "galah_b200_ani_index_reserve": (ctypes.c_int, [vp, ctypes.c_size_t]),
-    "galah_b200_ani_finish": (ctypes.c_int, [ctypes.c_uint32] * 4 + [ctypes.c_uint64] * 2 + [ctypes.c_float, vp]),
+    "galah_b200_ani_finish": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_float, vp]),
+    "galah_b200_chunk_identity_fx": (ctypes.c_uint64, [ctypes.c_uint32, ctypes.c_uint32]),
     "galah_b200_print2_parse_f32": (ctypes.c_float, [ctypes.c_double]),
     "galah_b200_ani_index_free": (None, [vp]),
     "galah_b200_ani_index_add_files": (ctypes.c_int, [vp, strp, ctypes.c_size_t, ctypes.c_int]),
@@ -106,7 +110,8 @@ _SIGNATURES = {
     "galah_b200_ani_index_size": (ctypes.c_size_t, [vp]),
     "galah_b200_ani_index_genome": (ctypes.c_int, [vp, ctypes.c_size_t, u64p, u32p, u64p]),
     "galah_b200_ani_index_seeds": (ctypes.c_int, [vp, ctypes.c_size_t, u32p, u32p, u32p, ctypes.c_size_t]),
-    "galah_b200_ani_pairs": (ctypes.c_int, [vp, u32p, ctypes.c_size_t, ctypes.c_float, ctypes.POINTER(AniResult)]),
+    "galah_b200_ani_pairs": (ctypes.c_int, [vp, u32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
+                                            ctypes.POINTER(AniResult)]),
     "galah_b200_ani_last_timing": (ctypes.c_int, [vp, f32p, f32p]),
     "galah_b200_cluster_from_ani_table": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                                          ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]),
@@ -120,7 +125,7 @@ _SIGNATURES = {
     "galah_b200_skani_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_int, pairpp, sizep, sizep]),
     "galah_b200_skani_distances_packed_device": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
-                                                                ctypes.c_float, ctypes.c_int, vp,
+                                                                ctypes.c_float, ctypes.c_int, ctypes.c_int, vp,
                                                                 ctypes.POINTER(ctypes.POINTER(Pair)), sizep,
                                                                 ctypes.POINTER(ctypes.c_uint64), f32p]),
     "galah_b200_cluster_files_skani": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,

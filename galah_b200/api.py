@@ -205,8 +205,10 @@ def finch_distances(paths, min_ani=0.9, num_kmers=1000, kmer_length=21, threads=
     return _take_pairs(out, n_out)
 
 
-ANI_RESULT_DTYPE = np.dtype([("ani", "<f4"), ("af_query", "<f4"), ("af_ref", "<f4"), ("sum_m", "<u4"),
-                             ("sum_n", "<u4"), ("cov_q", "<u4"), ("cov_r", "<u4"), ("swapped", "<u4")])
+ANI_RESULT_DTYPE = np.dtype([("ani", "<f4"), ("af_query", "<f4"), ("af_ref", "<f4"), ("estimator", "<u4"),
+                             ("sum_fx", "<u8"), ("n_chunks", "<u4"), ("sum_m", "<u4"), ("span_m", "<u4"),
+                             ("span_n", "<u4"), ("n_chains", "<u4"), ("cov_q", "<u4"), ("cov_r", "<u4"),
+                             ("reserved", "<u4")])
 
 
 class AniIndex:
@@ -265,13 +267,14 @@ class AniIndex:
                                                sp.ctypes.data_as(_native.u32p), ch.ctypes.data_as(_native.u32p), max(n, 1)))
         return ks[:n], sp[:n], ch[:n]
 
-    def pairs(self, pairs, min_af_pct=15.0):
-        """pairs: (n, 2) genome ids -> ANI_RESULT_DTYPE records (ani as galah would parse it)."""
+    def pairs(self, pairs, min_af_pct=15.0, individual_contigs=False):
+        """pairs: (n, 2) genome ids, (query, reference) -> ANI_RESULT_DTYPE records (ani as galah
+        would parse it).  individual_contigs: the units are records (`skani triangle -i`)."""
         pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
         out = np.zeros(len(pairs), ANI_RESULT_DTYPE)
         if len(pairs):
             check(lib().galah_b200_ani_pairs(self._h, pairs.ctypes.data_as(_native.u32p), len(pairs),
-                                             ctypes.c_float(min_af_pct),
+                                             ctypes.c_float(min_af_pct), int(bool(individual_contigs)),
                                              out.ctypes.data_as(ctypes.POINTER(_native.AniResult))))
         return out
 
@@ -412,7 +415,8 @@ def pack_fasta_file(path):
 
 
 def skani_distances_packed_device(d_seq2, d_valid, d_base_off, base_off, lengths, threshold=95.0,
-                                  min_aligned_fraction=15.0, small_genomes=False, stream=0):
+                                  min_aligned_fraction=15.0, small_genomes=False, stream=0,
+                                  individual_contigs=True):
     """SkaniPreclusterer on units already packed on the device (contig mode at scale).  Returns
     (PAIR_DTYPE hits with ani in PERCENT, info dict with n_screened and the stage times in ms)."""
     base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
@@ -423,7 +427,7 @@ def skani_distances_packed_device(d_seq2, d_valid, d_base_off, base_off, lengths
     check(lib().galah_b200_skani_distances_packed_device(
         d_seq2, d_valid, d_base_off, base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p),
         len(lengths), ctypes.c_float(threshold), ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
-        stream, ctypes.byref(out), ctypes.byref(n_out), ctypes.byref(scr), ms))
+        int(bool(individual_contigs)), stream, ctypes.byref(out), ctypes.byref(n_out), ctypes.byref(scr), ms))
     info = {"n_screened": int(scr.value),
             **dict(zip(("index_ms", "markers_ms", "screen_ms", "ani_ms", "total_ms"), (float(x) for x in ms)))}
     return _take_pairs(out, n_out), info

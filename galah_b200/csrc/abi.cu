@@ -580,8 +580,8 @@ static std::string display_f32(float v) {
 // device: marker-containment screen through the K2 join (containment rule), K3 ANI of every
 // screened pair, `ani >= threshold` in f32 (src/skani.rs:205).  ms3 (optional): screen, ANI, total.
 static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const uint32_t *d_counts, size_t n_units,
-                                size_t stride, float threshold_pct, float min_af_pct, cudaStream_t st,
-                                std::vector<galah_b200_pair_t> &out, uint64_t &n_screened, float *ms3) {
+                                size_t stride, float threshold_pct, float min_af_pct, bool individual_contigs,
+                                cudaStream_t st, std::vector<galah_b200_pair_t> &out, uint64_t &n_screened, float *ms3) {
     const double t_begin = now_ms();
     if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
     const double frac = pow(0.80, 21.0);  // marker containment of a pair at ~80 % identity
@@ -591,7 +591,7 @@ static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const 
         if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;
         int rc = prefilter_enqueue(g_ctx.pws, d_table, d_counts, n_units, stride, 21, 0.f, 0, 1,
                                    join_supported(stride) ? 0 : 1, st, g_ctx.d_cand, g_ctx.cap_cand, g_ctx.d_n_cand,
-                                   kRuleContainment, frac);
+                                   index.c() == 30u ? kRuleContainment : kRuleContainmentBypassSmall, frac);
         if (rc) return rc;
         unsigned long long got = 0;
         GB_CUDA(cudaMemcpyAsync(&got, g_ctx.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, st));
@@ -610,7 +610,7 @@ static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const 
     std::vector<uint32_t> pairs(2 * cand.size());
     for (size_t x = 0; x < cand.size(); x++) { pairs[2 * x] = cand[x].x; pairs[2 * x + 1] = cand[x].y; }
     std::vector<AniPairResult> res(cand.size());
-    if (int rc = index.pairs(pairs.data(), cand.size(), min_af_pct, res.data(), st)) return rc;
+    if (int rc = index.pairs(pairs.data(), cand.size(), min_af_pct, individual_contigs, res.data(), st)) return rc;
     out.clear();
     for (size_t x = 0; x < cand.size(); x++)
         if (res[x].ani >= threshold_pct)  // `if ani >= threshold` in f32, src/skani.rs:205
@@ -637,7 +637,7 @@ static int skani_distances_impl(const char *const *paths, size_t n, float thresh
     if (n_units < 2) return 0;
     if (markers.n != n_units) { set_error("skani preclusterer: marker table out of step with the units"); return GALAH_B200_ERR_ARG; }
     return skani_screen_and_ani(index, markers.d_rows, markers.d_counts, n_units, markers.stride, threshold_pct,
-                                min_af_pct, g_ctx.stream, out, n_screened, nullptr);
+                                min_af_pct, per_record, g_ctx.stream, out, n_screened, nullptr);
 }
 
 }  // namespace gb200
@@ -915,13 +915,18 @@ void galah_b200_ani_index_free(galah_b200_ani_index_t *idx) {
     delete idx;
 }
 
-int galah_b200_ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
-                          uint64_t len_r, float min_af_pct, galah_b200_ani_result_t *out) {
-    if (!out) { set_error("ani_finish: out is NULL"); return GALAH_B200_ERR_ARG; }
-    const AniPairResult r = ani_finish(sum_m, sum_n, cov_q, cov_r, len_q, len_r, min_af_pct, false);
+int galah_b200_ani_finish(const galah_b200_ani_result_t *ints, uint64_t len_q, uint64_t len_r, int small_genomes,
+                          int individual_contigs, float min_af_pct, galah_b200_ani_result_t *out) {
+    if (!out || !ints) { set_error("ani_finish: NULL argument"); return GALAH_B200_ERR_ARG; }
+    AniPairInts v;
+    v.sum_fx = ints->sum_fx; v.n_chunks = ints->n_chunks; v.sum_m = ints->sum_m; v.span_m = ints->span_m;
+    v.span_n = ints->span_n; v.n_chains = ints->n_chains; v.cov_q = ints->cov_q; v.cov_r = ints->cov_r;
+    const AniPairResult r = ani_finish(v, len_q, len_r, small_genomes ? 30u : 125u, individual_contigs != 0, min_af_pct);
     memcpy(out, &r, sizeof(r));
     return 0;
 }
+
+uint64_t galah_b200_chunk_identity_fx(uint32_t m, uint32_t n) { return chunk_identity_fx(m, n); }
 
 float galah_b200_print2_parse_f32(double v) { return print2_parse_f32(v); }
 
@@ -1006,12 +1011,12 @@ int galah_b200_ani_index_seeds(const galah_b200_ani_index_t *idx, size_t g, uint
 }
 
 int galah_b200_ani_pairs(galah_b200_ani_index_t *idx, const uint32_t *pairs, size_t n_pairs, float min_af_pct,
-                         galah_b200_ani_result_t *results) {
+                         int individual_contigs, galah_b200_ani_result_t *results) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (int rc = require_ctx()) return rc;
     if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
     static_assert(sizeof(galah_b200_ani_result_t) == sizeof(AniPairResult), "result layout");
-    return idx->impl.pairs(pairs, n_pairs, min_af_pct, reinterpret_cast<AniPairResult *>(results), g_ctx.stream);
+    return idx->impl.pairs(pairs, n_pairs, min_af_pct, individual_contigs != 0, reinterpret_cast<AniPairResult *>(results), g_ctx.stream);
 }
 
 int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_ms, float *chain_ms) {
@@ -1112,7 +1117,7 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
     std::vector<uint32_t> pairs(2 * n_hits);
     for (size_t x = 0; x < n_hits; x++) { pairs[2 * x] = hits[x].i; pairs[2 * x + 1] = hits[x].j; }
     std::vector<galah_b200_ani_result_t> res(n_hits);
-    if (int rc = galah_b200_ani_pairs(idx, pairs.data(), n_hits, min_af_pct, res.data())) return rc;
+    if (int rc = galah_b200_ani_pairs(idx, pairs.data(), n_hits, min_af_pct, 0, res.data())) return rc;
     AniTable table{hits, n_hits, n_hits ? &res[0].ani : nullptr, sizeof(galah_b200_ani_result_t)};
     int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
     if (stats) {
@@ -1147,9 +1152,9 @@ int galah_b200_skani_distances(const char *const *paths, size_t n, float thresho
 int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
                                              const uint64_t *d_base_off, const uint64_t *base_off,
                                              const uint64_t *lengths, size_t n, float threshold_pct,
-                                             float min_af_pct, int small_genomes, void *stream,
-                                             galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened,
-                                             float *ms5) {
+                                             float min_af_pct, int small_genomes, int individual_contigs,
+                                             void *stream, galah_b200_pair_t **out, size_t *n_out,
+                                             uint64_t *n_screened, float *ms5) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (int rc = require_ctx()) return rc;
     *out = nullptr; *n_out = 0;
@@ -1189,7 +1194,7 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
     uint64_t screened = 0;
     float ms3[3] = {0, 0, 0};
     if (n >= 2)
-        if (int rc = skani_screen_and_ani(index, d_rows.p, d_counts.p, n, cap, threshold_pct, min_af_pct, st, hits, screened, ms3))
+        if (int rc = skani_screen_and_ani(index, d_rows.p, d_counts.p, n, cap, threshold_pct, min_af_pct, individual_contigs != 0, st, hits, screened, ms3))
             return rc;
     if (n_screened) *n_screened = screened;
     if (ms5) { ms5[0] = (float)(t1 - t0); ms5[1] = (float)(t2 - t1); ms5[2] = ms3[0]; ms5[3] = ms3[1]; ms5[4] = (float)(now_ms() - t0); }

@@ -34,6 +34,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -243,11 +244,15 @@ struct ChainParams {
     const uint32_t *n_chunks;
     const uint32_t *unit_prefix;  // [n_pairs + 1] running sum of the query genomes' chunk counts
     uint32_t n_pairs, n_units;
-    uint32_t *acc;  // 4 per pair: sumM, sumN, covq, covr
+    const unsigned long long *idtab;  // [kIdTabN * (kIdTabN + 1) / 2]: 2^40 (M/N)^(1/15) at N (N + 1) / 2 + M
+    unsigned long long *acc_fx;       // per pair: sum of the per-chunk fixed-point identities
+    uint32_t *acc;                    // kAccWords per pair: chunks, covq, covr, sum M, span M, span N, chains
+    uint32_t *overflow;               // (pair, M, N) of chunks with N >= kIdTabN; overflow[0] = count
+    uint32_t overflow_cap;
 };
 
 constexpr int kChainThreads = 128;
-constexpr int kRingFields = 5;  // q, r, f, rel<<31 | cnt<<16 | first_x, first_r
+constexpr int kRingFields = 5;  // q, r, f, rel<<31 | cnt<<29 | acc_dr<<15 | x, first_x<<16 | first_mb
 
 __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainParams p) {
     extern __shared__ int ring[];  // [kAniH][kRingFields][kChainThreads]
@@ -277,8 +282,9 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     }
 #define RING(slot, field) ring[((slot) * kRingFields + (field)) * kChainThreads + tid]
     uint32_t n_anchor = 0;
-    int best_f = 0, best_first_r = 0, best_last_r = 0;
-    uint32_t best_cnt = 0, best_first_x = 0, best_last_x = 0;
+    // per-chunk result state (oracle/skani_oracle.c, "per chunk")
+    uint32_t m_run = 0, first_q = 0xFFFFFFFFu, mb_first = 0, last_q = 0, m_at_last = 0;
+    uint32_t covq = 0, covr = 0, span_m = 0, span_n = 0, n_chains = 0;
     int f_seen = 0;  // largest score of any anchor so far: bounds every score still in the ring
     // The lanes of a warp are different chunks and walk their seeds in lock step: one seed per
     // lane per iteration.  The probe of the reference table (the random read this kernel is bound
@@ -331,6 +337,8 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
             }
         }
         const uint32_t occ = c > (uint32_t)kAniMaxOcc ? 0u : c;
+        const uint32_t m_before = m_run;  // matched seeds of this chunk before x
+        m_run += occ ? 1u : 0u;
         long long prev = -1;
         for (uint32_t m = 0; m < occ; m++) {
             // occurrence m: the smallest reference position above the previous one
@@ -348,8 +356,10 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
             prev = (long long)(uint32_t)pick;
             const int rpos = (int)(uint32_t)pick;
             const uint32_t rel = qs ^ (uint32_t)((pick >> 32) & 1);
-            int f = kAniAlpha, first_r = rpos;
-            uint32_t cnt = 1, first_x = x - x0;
+            const uint32_t xi = x - x0;
+            int f = kAniAlpha;
+            uint32_t pmeta = 0, pfirst = 0;  // best predecessor's words 3 and 4 (pmeta == 0: none)
+            int link_dq = 0, link_dr = 0;
             const uint32_t look = min(n_anchor, (uint32_t)kAniH);
             for (uint32_t b = 1; b <= look; b++) {
                 // a later predecessor can reach at most f_seen + alpha and must be strictly better
@@ -366,30 +376,55 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
                 if (gap > kAniMaxGap) continue;
                 const int cand = RING(slot, 2) + kAniAlpha - gap;
                 if (cand > f) {
-                    f = cand; cnt = ((meta >> 16) & 0x7FFFu) + 1; first_x = meta & 0xFFFFu;
-                    first_r = RING(slot, 4);
+                    f = cand; pmeta = meta; pfirst = (uint32_t)RING(slot, 4);
+                    link_dq = dq; link_dr = dr;
                 }
             }
+            // cnt code: 1, 2 or 3 (= three or more); words 3 / 4 as in kRingFields' comment
+            const uint32_t pcnt = (pmeta >> 29) & 3u;  // 0 when there is no predecessor
+            const uint32_t cnt = min(pcnt + 1u, 3u);
+            uint32_t first_x = xi, first_mb = m_before, acc_dr = 0;
+            if (pcnt) { first_x = pfirst >> 16; first_mb = pfirst & 0xFFFFu; }
+            if (pcnt == 1) acc_dr = (uint32_t)link_dr;
             const uint32_t slot = n_anchor % kAniH;
             RING(slot, 0) = qpos; RING(slot, 1) = rpos; RING(slot, 2) = f;
-            RING(slot, 3) = (int)((rel << 31) | (cnt << 16) | first_x);
-            RING(slot, 4) = first_r;
+            RING(slot, 3) = (int)((rel << 31) | (cnt << 29) | (acc_dr << 15) | xi);
+            RING(slot, 4) = (int)((first_x << 16) | first_mb);
             n_anchor++;
             f_seen = max(f_seen, f);
-            if (f > best_f) {
-                best_f = f; best_cnt = cnt; best_first_x = first_x; best_last_x = x - x0;
-                best_first_r = first_r; best_last_r = rpos;
+            if (cnt == 3) {
+                last_q = xi; m_at_last = m_before + 1;
+                if (pcnt == 2) {  // the chain's third anchor: it qualifies now
+                    if (first_q == 0xFFFFFFFFu || first_x < first_q) { first_q = first_x; mb_first = first_mb; }
+                    covq += (uint32_t)(qpos - (int)qkq[x0 + first_x].y) + kAniK;
+                    covr += ((pmeta >> 15) & 0x3FFFu) + (uint32_t)link_dr + kAniK;
+                    span_m += 3; span_n += xi - first_x + 1; n_chains++;
+                } else {
+                    covq += (uint32_t)link_dq; covr += (uint32_t)link_dr;
+                    span_m += 1; span_n += xi - (pmeta & 0x7FFFu);
+                }
             }
         }
     }
 #undef RING
-    if (best_cnt >= (uint32_t)kAniMinAnchors) {
-        const uint32_t N = best_last_x - best_first_x + 1;
-        uint32_t *acc = p.acc + 4 * (size_t)pair;
-        atomicAdd(&acc[0], best_cnt - 2);
-        atomicAdd(&acc[1], N - 2);
-        atomicAdd(&acc[2], qkq[x0 + best_last_x].y - qkq[x0 + best_first_x].y + kAniK);
-        atomicAdd(&acc[3], (uint32_t)abs(best_last_r - best_first_r) + kAniK);
+    if (first_q != 0xFFFFFFFFu) {
+        const uint32_t M = m_at_last - mb_first, N = last_q - first_q + 1;
+        if (N < (uint32_t)kIdTabN) {
+            atomicAdd(&p.acc_fx[pair], p.idtab[(size_t)N * (N + 1) / 2 + M]);
+        } else {
+            const uint32_t at = atomicAdd(&p.overflow[0], 1u);
+            if (at < p.overflow_cap) {
+                p.overflow[1 + 3 * at] = pair; p.overflow[2 + 3 * at] = M; p.overflow[3 + 3 * at] = N;
+            }
+        }
+        uint32_t *acc = p.acc + (size_t)kAccWords * pair;
+        atomicAdd(&acc[0], 1u);
+        atomicAdd(&acc[1], covq);
+        atomicAdd(&acc[2], covr);
+        atomicAdd(&acc[3], M);
+        atomicAdd(&acc[4], span_m);
+        atomicAdd(&acc[5], span_n);
+        atomicAdd(&acc[6], n_chains);
     }
 }
 
@@ -422,16 +457,30 @@ float print2_parse_f32(double v) {
     return strtof(buf, nullptr);
 }
 
-AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
-                         uint64_t len_r, float min_af_pct, bool swapped) {
+uint64_t chunk_identity_fx(uint32_t m, uint32_t n) {
+    if (m == 0 || n == 0) return 0;
+    if (m >= n) return 1ull << kAniFxBits;
+    return (uint64_t)llround(pow((double)m / (double)n, 1.0 / kAniK) * (double)(1ull << kAniFxBits));
+}
+
+AniPairResult ani_finish(const AniPairInts &v, uint64_t len_q, uint64_t len_r, uint32_t c, bool individual_contigs,
+                         float min_af_pct) {
     AniPairResult res;
-    double afq = len_q ? (double)cov_q / (double)len_q : 0.0, afr = len_r ? (double)cov_r / (double)len_r : 0.0;
+    memset(&res, 0, sizeof(res));
+    double afq = len_q ? (double)v.cov_q / (double)len_q : 0.0, afr = len_r ? (double)v.cov_r / (double)len_r : 0.0;
     afq = std::min(afq, 1.0); afr = std::min(afr, 1.0);
     res.af_query = (float)afq; res.af_ref = (float)afr;
-    res.sum_m = sum_m; res.sum_n = sum_n; res.cov_q = cov_q; res.cov_r = cov_r; res.swapped = swapped ? 1u : 0u;
-    res.ani = 0.0f;
-    if (sum_n == 0 || sum_m == 0) return res;
-    const double ani = 100.0 * pow((double)sum_m / (double)sum_n, 1.0 / kAniK);
+    res.sum_fx = v.sum_fx; res.n_chunks = v.n_chunks; res.sum_m = v.sum_m; res.span_m = v.span_m;
+    res.span_n = v.span_n; res.n_chains = v.n_chains; res.cov_q = v.cov_q; res.cov_r = v.cov_r;
+    if (v.n_chunks == 0 || v.sum_fx == 0) return res;
+    // skani replaces its raw estimate by a learned regression "for c >= 70 and >= 150,000 bases
+    // aligned and not on individual contigs"; its weights are not available, the chain-span
+    // ratio (insensitive to unaligned stretches inside a chunk) stands in for it.
+    const bool span = c >= kAniLearnedMinC && !individual_contigs && v.cov_q >= kAniLearnedMinBases &&
+                      v.span_n > 2 * v.n_chains && v.span_m > 2 * v.n_chains;
+    res.estimator = span ? 1u : 0u;
+    const double ani = span ? 100.0 * pow((double)(v.span_m - 2 * v.n_chains) / (double)(v.span_n - 2 * v.n_chains), 1.0 / kAniK)
+                            : 100.0 * ((double)v.sum_fx / ((double)v.n_chunks * (double)(1ull << kAniFxBits)));
     if (std::max(afq, afr) * 100.0 < (double)min_af_pct) return res;  // skani prints no row
     res.ani = print2_parse_f32(ani);  // skani prints {:.2}; galah parses the text as f32
     return res;
@@ -463,8 +512,10 @@ struct TmpBuf {
 };
 
 struct AniScratch {
-    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix;
+    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix, overflow;
     TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
+    TmpBuf<unsigned long long> acc_fx, idtab;
+    bool idtab_ready = false;
 };
 
 AniIndex::~AniIndex() {
@@ -611,22 +662,34 @@ int AniIndex::genome_seeds(size_t g, uint32_t *ks, uint32_t *spread, uint32_t *c
     return 0;
 }
 
-int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, AniPairResult *out, cudaStream_t st) {
+int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, bool individual_contigs,
+                    AniPairResult *out, cudaStream_t st) {
     if (n_pairs == 0) return 0;
     if (!ev_[0]) { GB_CUDA(cudaEventCreate(&ev_[0])); GB_CUDA(cudaEventCreate(&ev_[1])); }
-    std::vector<uint32_t> oriented(2 * n_pairs);
-    std::vector<uint8_t> swapped(n_pairs);
-    for (size_t x = 0; x < n_pairs; x++) {
-        const uint32_t a = pairs[2 * x], b = pairs[2 * x + 1];
-        if (a >= size() || b >= size()) { set_error("ani pairs: genome index out of range"); return 3; }
-        swapped[x] = total_len_[b] < total_len_[a];
-        oriented[2 * x] = swapped[x] ? b : a;
-        oriented[2 * x + 1] = swapped[x] ? a : b;
-    }
+    // the query is the pair's FIRST genome, as given (skani dist -q fasta1 -r fasta2, src/skani.rs:733-744)
+    for (size_t x = 0; x < n_pairs; x++)
+        if (pairs[2 * x] >= size() || pairs[2 * x + 1] >= size()) { set_error("ani pairs: genome index out of range"); return 3; }
     if (!scratch_) scratch_ = new AniScratch();
-    TmpBuf<uint32_t> &d_pairs = scratch_->pairs, &d_acc = scratch_->acc;
-    if (d_pairs.upload(oriented, st) || d_acc.alloc(4 * n_pairs)) return 2;
-    GB_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * n_pairs, st));
+    TmpBuf<uint32_t> &d_pairs = scratch_->pairs, &d_acc = scratch_->acc, &d_over = scratch_->overflow;
+    TmpBuf<unsigned long long> &d_fx = scratch_->acc_fx, &d_idtab = scratch_->idtab;
+    const uint32_t kOverflowCap = 1u << 16;
+    if (d_pairs.alloc(2 * n_pairs) || d_acc.alloc((size_t)kAccWords * n_pairs) || d_fx.alloc(n_pairs) ||
+        d_over.alloc(1 + 3 * (size_t)kOverflowCap))
+        return 2;
+    GB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs, 8 * n_pairs, cudaMemcpyHostToDevice, st));
+    if (!scratch_->idtab_ready) {
+        // 2^40 (M/N)^(1/15) for every M <= N < kIdTabN, evaluated once on the host (glibc pow, the
+        // same expression as the oracle's) so that the device only adds integers
+        std::vector<unsigned long long> tab((size_t)kIdTabN * (kIdTabN + 1) / 2 + kIdTabN, 0);
+        for (uint32_t N = 1; N < (uint32_t)kIdTabN; N++)
+            for (uint32_t M = 0; M <= N; M++) tab[(size_t)N * (N + 1) / 2 + M] = chunk_identity_fx(M, N);
+        if (d_idtab.upload(tab, st)) return 2;
+        GB_CUDA(cudaStreamSynchronize(st));
+        scratch_->idtab_ready = true;
+    }
+    GB_CUDA(cudaMemsetAsync(d_acc.p, 0, 4 * (size_t)kAccWords * n_pairs, st));
+    GB_CUDA(cudaMemsetAsync(d_fx.p, 0, 8 * n_pairs, st));
+    GB_CUDA(cudaMemsetAsync(d_over.p, 0, 4, st));
     const size_t smem = (size_t)kAniH * kRingFields * kChainThreads * sizeof(int);
     GB_CUDA(cudaFuncSetAttribute(ani_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GB_CUDA(cudaEventRecord(ev_[0], st));
@@ -638,8 +701,8 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, Ani
         size_t b1 = b0;
         uint64_t units = 0;
         unit_prefix[b0] = 0;
-        while (b1 < n_pairs && units + n_chunks_[oriented[2 * b1]] <= kMaxUnits) {
-            units += n_chunks_[oriented[2 * b1]];
+        while (b1 < n_pairs && units + n_chunks_[pairs[2 * b1]] <= kMaxUnits) {
+            units += n_chunks_[pairs[2 * b1]];
             unit_prefix[b1 + 1] = (uint32_t)units;
             b1++;
         }
@@ -653,24 +716,46 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, Ani
             ChainParams p;
             p.pairs = d_pairs.p + 2 * b0; p.kq = d_kq_.p; p.cso = d_cso_.p;
             p.table = d_table_.p; p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p; p.table_off = d_table_off_.p;
-            p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + 4 * b0;
+            p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + (size_t)kAccWords * b0; p.acc_fx = d_fx.p + b0;
+            p.idtab = d_idtab.p; p.overflow = d_over.p; p.overflow_cap = kOverflowCap;
             p.unit_prefix = d_prefix.p; p.n_pairs = (uint32_t)(b1 - b0); p.n_units = (uint32_t)units;
             ani_chain_kernel<<<(uint32_t)((units + kChainThreads - 1) / kChainThreads), kChainThreads, smem, st>>>(p);
             GB_LAUNCH_CHECK();
+            // chunks too long for the table (N >= kIdTabN; never at c = 125 / 30 on 20 kb chunks of
+            // ordinary sequence): finished on the host, batch-relative pair ids
+            uint32_t n_over = 0;
+            GB_CUDA(cudaMemcpyAsync(&n_over, d_over.p, 4, cudaMemcpyDeviceToHost, st));
+            GB_CUDA(cudaStreamSynchronize(st));
+            if (n_over > kOverflowCap) { set_error("ani pairs: too many over-long chunks"); return 3; }
+            if (n_over) {
+                std::vector<uint32_t> ov(3 * (size_t)n_over);
+                GB_CUDA(cudaMemcpy(ov.data(), d_over.p + 1, 12 * (size_t)n_over, cudaMemcpyDeviceToHost));
+                std::vector<unsigned long long> add(b1 - b0, 0);
+                for (uint32_t x = 0; x < n_over; x++) add[ov[3 * x]] += chunk_identity_fx(ov[3 * x + 1], ov[3 * x + 2]);
+                std::vector<unsigned long long> cur(b1 - b0);
+                GB_CUDA(cudaMemcpy(cur.data(), d_fx.p + b0, 8 * (b1 - b0), cudaMemcpyDeviceToHost));
+                for (size_t x = 0; x < b1 - b0; x++) cur[x] += add[x];
+                GB_CUDA(cudaMemcpy(d_fx.p + b0, cur.data(), 8 * (b1 - b0), cudaMemcpyHostToDevice));
+                GB_CUDA(cudaMemsetAsync(d_over.p, 0, 4, st));
+            }
         }
         b0 = b1;
     }
     GB_CUDA(cudaEventRecord(ev_[1], st));
-    std::vector<uint32_t> acc(4 * n_pairs);
-    GB_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 16 * n_pairs, cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> acc((size_t)kAccWords * n_pairs);
+    std::vector<unsigned long long> fx(n_pairs);
+    GB_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 4 * (size_t)kAccWords * n_pairs, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(fx.data(), d_fx.p, 8 * n_pairs, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     last_chain_ms = ms;
     for (size_t x = 0; x < n_pairs; x++) {
-        const uint32_t q = oriented[2 * x], r = oriented[2 * x + 1];
-        out[x] = ani_finish(acc[4 * x], acc[4 * x + 1], acc[4 * x + 2], acc[4 * x + 3], total_len_[q],
-                            total_len_[r], min_af_pct, swapped[x] != 0);
+        const uint32_t *a = &acc[(size_t)kAccWords * x];
+        AniPairInts v;
+        v.sum_fx = fx[x]; v.n_chunks = a[0]; v.cov_q = a[1]; v.cov_r = a[2]; v.sum_m = a[3];
+        v.span_m = a[4]; v.span_n = a[5]; v.n_chains = a[6];
+        out[x] = ani_finish(v, total_len_[pairs[2 * x]], total_len_[pairs[2 * x + 1]], c_, individual_contigs, min_af_pct);
     }
     return 0;
 }

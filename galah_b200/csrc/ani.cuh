@@ -21,12 +21,27 @@ constexpr int kAniAlpha = 20;
 constexpr int kAniH = 16;
 constexpr int kAniMaxOcc = 8;
 constexpr int kAniMinAnchors = 3;
+constexpr int kAniFxBits = 40;             // per-chunk identities are summed as 2^40 fixed point
+constexpr int kIdTabN = 1024;              // device table of identities for N < kIdTabN seeds per chunk span
+constexpr int kAccWords = 8;               // u32 accumulators per pair (7 used)
+constexpr uint32_t kAniLearnedMinC = 70;   // skani: "learned ANI used for c >= 70 and >= 150,000 bases
+constexpr uint32_t kAniLearnedMinBases = 150000;  //  aligned and not on individual contigs"
 
-struct AniPairResult {
+// integer accumulators of one pair (what the chain kernel emits)
+struct AniPairInts {
+    uint64_t sum_fx;      // sum over counted query chunks of 2^40 (M/N)^(1/15)
+    uint32_t n_chunks;    // query chunks with at least one qualified chain
+    uint32_t sum_m;       // matched seeds over those chunks' spans (diagnostic)
+    uint32_t span_m, span_n, n_chains;  // chained anchors / seeds inside chain spans / chains
+    uint32_t cov_q, cov_r;
+};
+
+struct AniPairResult {    // == galah_b200_ani_result_t
     float ani;            // what galah parses from skani's TSV column 3 (0.0 = no row)
     float af_query, af_ref;
-    uint32_t sum_m, sum_n, cov_q, cov_r;
-    uint32_t swapped;     // 1 if the second genome of the pair was the query
+    uint32_t estimator;   // 0 = mean of per-chunk identities, 1 = chain-span ratio (learned-ANI stand-in)
+    uint64_t sum_fx;
+    uint32_t n_chunks, sum_m, span_m, span_n, n_chains, cov_q, cov_r, reserved;
 };
 
 // Growable device array.
@@ -52,7 +67,10 @@ public:
                           const std::vector<uint64_t> &contig_off, const std::vector<uint32_t> &contig_start,
                           const std::vector<uint32_t> &contig_len, cudaStream_t st);
     int reserve_for(size_t n_total, cudaStream_t st);
-    int pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, AniPairResult *out, cudaStream_t st);
+    // pairs: (query, reference) genome ids -- the query is the FIRST id.  individual_contigs: the call
+    // stands for `skani triangle -i` (contig clustering), where skani never applies its learned ANI.
+    int pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, bool individual_contigs, AniPairResult *out,
+              cudaStream_t st);
     size_t size() const { return total_len_.size(); }
     uint32_t c() const { return c_; }
     // parity hooks
@@ -79,7 +97,9 @@ private:
 // strtof(sprintf("%.2f", v)), computed exactly without the text for the values an ANI can take
 float print2_parse_f32(double v);
 // integers -> the f32 galah would parse (host; mirrors oracle/skani_oracle.c skani_oracle_finish)
-AniPairResult ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
-                         uint64_t len_r, float min_af_pct, bool swapped);
+AniPairResult ani_finish(const AniPairInts &v, uint64_t len_q, uint64_t len_r, uint32_t c, bool individual_contigs,
+                         float min_af_pct);
+// 2^40 (m/n)^(1/15) rounded to nearest (glibc pow): one chunk's identity as a fixed-point integer
+uint64_t chunk_identity_fx(uint32_t m, uint32_t n);
 
 }  // namespace gb200

@@ -80,12 +80,14 @@ PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani) {
     return t;
 }
 
-PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac) {
+PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac, uint32_t bypass_below) {
     PrefilterThresholds t;
     t.cmin_by_tmin.resize((size_t)s_max + 1);
     for (uint32_t m = 0; m <= s_max; m++) {
         const double need = ceil(frac * (double)m);
         t.cmin_by_tmin[m] = need < 1.0 ? 1u : (uint32_t)need;
+        // skani compares units with fewer than 20 markers against everything unless --faster-small
+        if (m < bypass_below) t.cmin_by_tmin[m] = 0u;
     }
     t.cmin_by_total.assign(2 * (size_t)s_max + 1, 0u);
     return t;
@@ -314,7 +316,7 @@ int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
     if (reset_counter) GB_CUDA(cudaMemsetAsync(d_n_cand, 0, sizeof(unsigned long long), stream));
     if (!ws.th_valid || ws.th_s != (uint32_t)stride || ws.th_k != k || ws.th_min_ani != min_ani ||
         ws.th_rule != rule || ws.th_param != rule_param) {
-        PrefilterThresholds th = rule == kRuleContainment ? make_containment_thresholds((uint32_t)stride, rule_param)
+        PrefilterThresholds th = rule != kRuleMashAni ? make_containment_thresholds((uint32_t)stride, rule_param, rule == kRuleContainmentBypassSmall ? kMarkerBypassBelow : 0u)
                                                           : make_thresholds((uint32_t)stride, k, min_ani);
         if (ws_ensure(ws.d_cmin_by_tmin, ws.cap_tmin, th.cmin_by_tmin.size())) return 2;
         if (ws_ensure(ws.d_cmin_by_total, ws.cap_total, th.cmin_by_total.size())) return 2;

@@ -22,8 +22,11 @@ struct PrefilterThresholds {
 PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani);
 // Containment screen (skani-style marker screen): a pair survives iff min(|A|,|B|) > 0 and
 // common >= max(1, ceil(frac * min(|A|,|B|))); `total` is not used.
-PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac);
-enum PrefilterRule { kRuleMashAni = 0, kRuleContainment = 1 };
+PrefilterThresholds make_containment_thresholds(uint32_t s_max, double frac, uint32_t bypass_below);
+// kRuleContainment: marker containment for every pair (skani --faster-small, implied by --small-genomes);
+// kRuleContainmentBypassSmall: pairs whose smaller marker sketch has < kMarkerBypassBelow entries always pass.
+enum PrefilterRule { kRuleMashAni = 0, kRuleContainment = 1, kRuleContainmentBypassSmall = 2 };
+constexpr uint32_t kMarkerBypassBelow = 20;
 
 // Sharding granularity in rows == sketches per block list (== GALAH_B200_ROW_BLOCK).
 constexpr int kShardRows = 128;

@@ -201,9 +201,15 @@ typedef struct galah_b200_ani_index galah_b200_ani_index_t;
 typedef struct galah_b200_ani_result {
     float ani;                /* percent, two decimals as skani prints; 0.0 = "no row" */
     float af_query, af_ref;   /* aligned fractions (0..1) of the query / reference genome */
-    uint32_t sum_m, sum_n;    /* chained anchors / seeds in chained spans (end anchors excluded) */
+    uint32_t estimator;       /* 0 = mean of the per-chunk identities; 1 = chain-span ratio (stands in
+                                 for skani's learned ANI: c >= 70, >= 150 kb aligned, not contigs) */
+    uint64_t sum_fx;          /* sum over counted query chunks of round(2^40 (M/N)^(1/15)) */
+    uint32_t n_chunks;        /* query chunks (20 kb) holding at least one chain of >= 3 anchors */
+    uint32_t sum_m;           /* matched seeds inside those chunks' chained spans */
+    uint32_t span_m, span_n;  /* chained anchors / query seeds inside chain spans */
+    uint32_t n_chains;        /* chains of >= 3 anchors */
     uint32_t cov_q, cov_r;    /* bases covered by chains on the query / reference */
-    uint32_t swapped;         /* 1 if the pair's second genome was the (shorter) query */
+    uint32_t reserved;
 } galah_b200_ani_result_t;
 
 /* small_genomes != 0 selects c = 30 (skani --small-genomes, src/skani.rs:735-737), else c = 125 */
@@ -225,13 +231,16 @@ int galah_b200_ani_index_add_packed_device(galah_b200_ani_index_t *idx, const ui
                                            const uint32_t *d_valid, const uint64_t *d_base_off,
                                            const uint64_t *base_off, const uint64_t *lengths,
                                            size_t n, void *stream);
-/* Host finish of stage 2 (no device needed): the kernel's integer accumulators of one pair ->
- * what galah parses from skani's TSV (src/skani.rs:773-779): ANI = 100 (sum_m / sum_n)^(1/15),
- * printed with two decimals and parsed as f32; 0.0 when max(AF) * 100 < min_af_pct (no row,
- * src/skani.rs:760).  galah_b200_print2_parse_f32(v) == strtof(sprintf("%.2f", v)). */
-int galah_b200_ani_finish(uint32_t sum_m, uint32_t sum_n, uint32_t cov_q, uint32_t cov_r, uint64_t len_q,
-                          uint64_t len_r, float min_af_pct, galah_b200_ani_result_t *out);
+/* Host finish of stage 2 (no device needed): the kernel's integer accumulators of one pair (the
+ * integer fields of `ints`) -> what galah parses from skani's TSV (src/skani.rs:773-779): the
+ * ANI (estimator 0 or 1, see the struct) printed with two decimals and parsed as f32; 0.0 when
+ * max(AF) * 100 < min_af_pct (no row, src/skani.rs:760).
+ * galah_b200_print2_parse_f32(v) == strtof(sprintf("%.2f", v));
+ * galah_b200_chunk_identity_fx(m, n) == round(2^40 (m/n)^(1/15)), one chunk's term of sum_fx. */
+int galah_b200_ani_finish(const galah_b200_ani_result_t *ints, uint64_t len_q, uint64_t len_r, int small_genomes,
+                          int individual_contigs, float min_af_pct, galah_b200_ani_result_t *out);
 float galah_b200_print2_parse_f32(double v);
+uint64_t galah_b200_chunk_identity_fx(uint32_t m, uint32_t n);
 
 /* Capacity hint: the index will hold n_total_genomes genomes like the ones already added (call
  * it after the first batch).  Avoids re-allocating the device arrays while the index grows. */
@@ -243,9 +252,12 @@ int galah_b200_ani_index_genome(const galah_b200_ani_index_t *idx, size_t g, uin
  * chunk id), cap >= n_seeds entries each. */
 int galah_b200_ani_index_seeds(const galah_b200_ani_index_t *idx, size_t g, uint32_t *kmer_strand,
                                uint32_t *spread, uint32_t *chunk, size_t cap);
-/* pairs: 2 * n_pairs genome ids; results: n_pairs entries.  min_af_pct as skani's --min-af. */
+/* pairs: 2 * n_pairs genome ids, (query, reference) -- the query is the FIRST id, as in
+ * `skani dist -q fasta1 -r fasta2` (src/skani.rs:733-744; galah passes the representative first,
+ * src/clusterer.rs:262-296); results: n_pairs entries.  min_af_pct as skani's --min-af.
+ * individual_contigs != 0: the units are FASTA records (`skani triangle -i`, src/skani.rs:413). */
 int galah_b200_ani_pairs(galah_b200_ani_index_t *idx, const uint32_t *pairs, size_t n_pairs,
-                         float min_af_pct, galah_b200_ani_result_t *results);
+                         float min_af_pct, int individual_contigs, galah_b200_ani_result_t *results);
 /* Device time (CUDA events) of the last index batch build and the last pair evaluation. */
 int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_ms, float *chain_ms);
 
@@ -303,7 +315,9 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
  * Replaces SkaniPreclusterer::distances and ::distances_contigs (src/skani.rs:21-56; the
  * `skani triangle --sparse [-i]` subprocess of :109-225 and :379-498): FracMinHash marker sketches
  * (k = 21, 1/1000, or 1/200 with small_genomes) of every unit, an all-pairs marker-containment
- * screen on the GPU (the K2 join with the rule common >= max(1, ceil(0.8^21 * min(|A|,|B|)))), the
+ * screen on the GPU (the K2 join with the rule common >= max(1, ceil(0.8^21 * min(|A|,|B|))); without
+ * small_genomes -- skani's --faster-small is part of --small-genomes -- a pair whose smaller marker
+ * sketch has fewer than 20 entries is always compared), the
  * stage-2 ANI kernel on the survivors, keep ANI >= threshold_pct (f32, src/skani.rs:205).
  * per_record != 0 is contig mode: every FASTA record of every file is its own unit, numbered in
  * file order then record order (the order of `contig_names`, src/cluster_argument_parsing.rs:
@@ -325,9 +339,9 @@ int galah_b200_skani_distances(const char *const *paths, size_t n, float thresho
 int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
                                              const uint64_t *d_base_off, const uint64_t *base_off,
                                              const uint64_t *lengths, size_t n, float threshold_pct,
-                                             float min_af_pct, int small_genomes, void *stream,
-                                             galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened,
-                                             float *ms5);
+                                             float min_af_pct, int small_genomes, int individual_contigs,
+                                             void *stream, galah_b200_pair_t **out, size_t *n_out,
+                                             uint64_t *n_screened, float *ms5);
 int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct,
                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
                                    int cluster_contigs, int host_threads, galah_b200_clusters_t *out,

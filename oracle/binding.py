@@ -196,11 +196,15 @@ def _skani_sigs():
     L.skani_oracle_seeds.restype = ctypes.c_uint64
     L.skani_oracle_seeds.argtypes = [u8p, ctypes.c_uint64, u64p, u64p, ctypes.c_uint32, ctypes.c_uint32,
                                      u32p, u32p, u32p, ctypes.c_uint64, u32p, u64p]
-    L.skani_oracle_chain.restype = None
-    L.skani_oracle_chain.argtypes = [u32p, u32p, u32p, ctypes.c_uint64, u32p, u32p, ctypes.c_uint64, u64p]
+    L.skani_oracle_chain.restype = ctypes.c_uint64
+    L.skani_oracle_chain.argtypes = [u32p, u32p, u32p, ctypes.c_uint64, u32p, u32p, ctypes.c_uint64, u64p,
+                                     u32p, ctypes.c_uint64]
+    L.skani_oracle_chunk_identity_fx.restype = ctypes.c_uint64
+    L.skani_oracle_chunk_identity_fx.argtypes = [ctypes.c_uint32, ctypes.c_uint32]
     L.skani_oracle_finish.restype = ctypes.c_float
-    L.skani_oracle_finish.argtypes = [ctypes.c_uint64] * 6 + [ctypes.c_float, ctypes.POINTER(ctypes.c_double),
-                                                              ctypes.POINTER(ctypes.c_double)]
+    L.skani_oracle_finish.argtypes = [ctypes.c_uint64] * 9 + [ctypes.c_uint32, ctypes.c_int, ctypes.c_float,
+                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                      ctypes.POINTER(ctypes.c_int)]
     L._skani_ready = True
     return L
 
@@ -262,32 +266,45 @@ class AniGenome:
         return cls(*load_codes(path), c=c)
 
 
-def ani_pair_integers(a: "AniGenome", b: "AniGenome"):
-    """(sumM, sumN, covq, covr, len_q, len_r, swapped): query = the shorter genome (ties: a)."""
+def ani_pair_integers(a: "AniGenome", b: "AniGenome", chunks=False):
+    """(sum_fx, n_chunks_counted, covq, covr, len_q, len_r, sum_m): the query is `a`, the FIRST genome
+    (skani dist -q a -r b, src/skani.rs:733-744).  With chunks=True also the per-chunk (M, N) list."""
     L = _skani_sigs()
-    swapped = b.total_len < a.total_len
-    q, r = (b, a) if swapped else (a, b)
-    out = np.zeros(4, np.uint64)
-    L.skani_oracle_chain(_p(q.kmer_strand, ctypes.c_uint32), _p(q.spread, ctypes.c_uint32),
-                         _p(q.chunk, ctypes.c_uint32), len(q.kmer_strand),
-                         _p(r.kmer_strand, ctypes.c_uint32), _p(r.spread, ctypes.c_uint32),
-                         len(r.kmer_strand), _p(out, ctypes.c_uint64))
-    return int(out[0]), int(out[1]), int(out[2]), int(out[3]), q.total_len, r.total_len, swapped
+    q, r = a, b
+    out = np.zeros(8, np.uint64)
+    cap = q.n_chunks + 1
+    mn = np.zeros(2 * cap, np.uint32)
+    n = L.skani_oracle_chain(_p(q.kmer_strand, ctypes.c_uint32), _p(q.spread, ctypes.c_uint32),
+                             _p(q.chunk, ctypes.c_uint32), len(q.kmer_strand),
+                             _p(r.kmer_strand, ctypes.c_uint32), _p(r.spread, ctypes.c_uint32),
+                             len(r.kmer_strand), _p(out, ctypes.c_uint64), _p(mn, ctypes.c_uint32), cap)
+    res = (int(out[0]), int(out[1]), int(out[2]), int(out[3]), q.total_len, r.total_len, int(out[4]),
+           int(out[5]), int(out[6]), int(out[7]))
+    if chunks:
+        return res, mn[: 2 * int(n)].reshape(-1, 2).copy()
+    return res
 
 
-def ani_finish(sumM, sumN, covq, covr, len_q, len_r, min_af_pct):
-    """-> (ani f32 as galah parses it, af_q, af_r, unrounded ani)."""
+def chunk_identity_fx(m, n):
+    return int(_skani_sigs().skani_oracle_chunk_identity_fx(m, n))
+
+
+def ani_finish(ints, min_af_pct, c=125, individual_contigs=False):
+    """ints = ani_pair_integers(...) -> (ani f32 as galah parses it, af_q, af_r, unrounded ani, estimator)."""
     L = _skani_sigs()
+    sum_fx, n_counted, covq, covr, len_q, len_r, _sum_m, span_m, span_n, n_chains = ints
     af = (ctypes.c_double * 2)()
     un = ctypes.c_double(0)
-    v = L.skani_oracle_finish(sumM, sumN, covq, covr, len_q, len_r, ctypes.c_float(min_af_pct), af,
-                              ctypes.byref(un))
-    return np.float32(v), af[0], af[1], un.value
+    est = ctypes.c_int(0)
+    v = L.skani_oracle_finish(sum_fx, n_counted, covq, covr, len_q, len_r, span_m, span_n, n_chains, c,
+                              int(bool(individual_contigs)), ctypes.c_float(min_af_pct), af, ctypes.byref(un),
+                              ctypes.byref(est))
+    return np.float32(v), af[0], af[1], un.value, est.value
 
 
-def ani_pair(a, b, min_af_pct=15.0):
-    ints = ani_pair_integers(a, b)
-    return ani_finish(*ints[:6], min_af_pct)
+def ani_pair(a, b, min_af_pct=15.0, c=125, individual_contigs=False):
+    """ANI of query a vs reference b (both AniGenome built with the same c)."""
+    return ani_finish(ani_pair_integers(a, b), min_af_pct, c, individual_contigs)
 
 
 def markers(codes, rec_start, rec_end, c_marker=1000):
@@ -309,9 +326,10 @@ def markers(codes, rec_start, rec_end, c_marker=1000):
         cap = int(n)
 
 
-def skani_distances(units, threshold, min_af_pct, small_genomes=False):
-    """Oracle of SkaniPreclusterer::distances on `units` = list of (codes, rec_start, rec_end):
-    marker screen -> ANI -> keep ani >= threshold.  Returns [(i, j, common, total, ani f32)]."""
+def skani_distances(units, threshold, min_af_pct, small_genomes=False, individual_contigs=False):
+    """Oracle of SkaniPreclusterer::distances / ::distances_contigs on `units` = list of
+    (codes, rec_start, rec_end): marker screen -> ANI (query = lower index) -> keep ani >= threshold.
+    Returns [(i, j, common, total, ani f32)]."""
     import math
     L = _skani_sigs()
     L.skani_oracle_screen_fraction.restype = ctypes.c_double
@@ -323,12 +341,11 @@ def skani_distances(units, threshold, min_af_pct, small_genomes=False):
     for i in range(len(units)):
         for j in range(i + 1, len(units)):
             m = min(len(mk[i]), len(mk[j]))
-            if m == 0:
+            common, total = raw_distance(mk[i], mk[j]) if m else (0, 0)
+            bypass = (not small_genomes) and m < 20  # skani without --faster-small
+            if not bypass and (m == 0 or common < max(1, math.ceil(frac * m))):
                 continue
-            common, total = raw_distance(mk[i], mk[j])
-            if common < max(1, math.ceil(frac * m)):
-                continue
-            ani = ani_pair(gen[i], gen[j], min_af_pct)[0]
+            ani = ani_pair(gen[i], gen[j], min_af_pct, c, individual_contigs)[0]
             if np.float32(ani) >= np.float32(threshold):
                 out.append((i, j, common, total, np.float32(ani)))
     return out

@@ -10,6 +10,12 @@ Outputs (all small, committed):
                          the two inputs of the reference's only numeric known-answer test
                          (/root/reference/src/finch.rs:107-129 -> Some(0.9808188)), recompressed
                          so the GPU box can run that KAT end to end through the CUDA path
+  contigs/*.fna.gz, set2_1mbp.half_aligned.fna.gz, antonio_mags/*.fna.gz (+ abisko4/*.fna.gz)
+                         every fixture genome behind a stage-2 outcome the reference's tests pin
+                         (SURVEY.md 8c), recompressed, so those outcomes run on the GPU box
+                         (set2/1mbp.fna is byte-identical to set1/1mbp.fna: set1_1mbp.fna.gz)
+  stage2_golden.json     the stage-2 oracle's integers and ANI for every pair those outcomes read
+                         (oracle/skani_oracle.c; PARITY UNPINNED vs skani itself, see its header)
 The oracle itself is pinned against that KAT in tests/test_oracle_golden.py.
 """
 import gzip
@@ -42,7 +48,49 @@ FIXTURES = [
 ]
 
 
+STAGE2_COPIES = [
+    ("contigs/contigs.fna", "contigs/contigs.fna.gz"),
+    ("contigs/contigs_extra.fna", "contigs/contigs_extra.fna.gz"),
+    ("contigs/contigs_specific.fna", "contigs/contigs_specific.fna.gz"),
+    ("contigs/contigs_rep_bug.fna", "contigs/contigs_rep_bug.fna.gz"),
+    ("set2/1mbp.half_aligned.fna", "set2_1mbp.half_aligned.fna.gz"),
+    ("antonio_mags/BE_RX_R2_MAG52.fna", "antonio_mags/BE_RX_R2_MAG52.fna.gz"),
+    ("antonio_mags/BE_RX_R3_MAG189.fna", "antonio_mags/BE_RX_R3_MAG189.fna.gz"),
+]
+
+
+def stage2_golden():
+    """Oracle outputs for the pairs behind the reference-pinned stage-2 outcomes."""
+    import json
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from stage2_cases import CASES, units_of  # the same case list the tests read
+    out = {}
+    for name, case in CASES.items():
+        units = units_of(HERE, case)
+        c = 30 if case["small"] else 125
+        gen = [oracle.AniGenome(*u, c=c) for u in units]
+        rows = []
+        for i in range(len(units)):
+            for j in range(i + 1, len(units)):
+                ints = oracle.ani_pair_integers(gen[i], gen[j])
+                ani, afq, afr, un, est = oracle.ani_finish(ints, case["min_af"], c, case["contigs"])
+                rows.append({"i": i, "j": j, "sum_fx": ints[0], "n_chunks": ints[1], "cov_q": ints[2],
+                             "cov_r": ints[3], "sum_m": ints[6], "span_m": ints[7], "span_n": ints[8],
+                             "n_chains": ints[9], "estimator": est, "ani": float(ani),
+                             "ani_unrounded": round(un, 6), "af_q": round(afq, 6), "af_r": round(afr, 6)})
+        out[name] = rows
+    with open(os.path.join(HERE, "stage2_golden.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    return sum(len(v) for v in out.values())
+
+
 def main():
+    for src, dst in STAGE2_COPIES:
+        os.makedirs(os.path.dirname(os.path.join(HERE, dst)), exist_ok=True)
+        with open(os.path.join(REF, src), "rb") as f, gzip.GzipFile(
+                os.path.join(HERE, dst), "wb", compresslevel=9, mtime=0) as g:
+            g.write(f.read())
+    print("stage-2 golden rows:", stage2_golden())
     sketches = [oracle.sketch_fasta(os.path.join(REF, f)) for f in FIXTURES]
     table, counts = oracle.pack_table(sketches, 1000)
     pairs = oracle.prefilter(table, counts, 21, 0.9)

@@ -43,14 +43,33 @@ def test_print2_parse_matches_text_route():
 
 def test_ani_finish_matches_oracle_finish():
     rng = np.random.default_rng(9)
-    out = _native.AniResult()
+    ints, out = _native.AniResult(), _native.AniResult()
     for _ in range(20_000):
-        sum_n = int(rng.integers(0, 20_000))
-        sum_m = int(rng.integers(0, sum_n + 1))
+        n_chunks = int(rng.integers(0, 150))
+        fx = [oracle.chunk_identity_fx(int(m), int(n)) for n in rng.integers(1, 700, n_chunks)
+              for m in [rng.integers(0, n + 1)]]
+        n_chains = int(rng.integers(0, 300))
+        span_n = int(rng.integers(0, 20_000)) + 3 * n_chains
+        span_m = int(rng.integers(3 * n_chains, span_n + 1)) if span_n else 0
         len_q, len_r = int(rng.integers(1, 3_000_000)), int(rng.integers(1, 3_000_000))
         cov_q, cov_r = int(rng.integers(0, len_q * 1.1 + 1)), int(rng.integers(0, len_r * 1.1 + 1))
         min_af = float(rng.choice([0.0, 15.0, 50.0, 60.0]))
-        _native.check(_native.lib().galah_b200_ani_finish(sum_m, sum_n, cov_q, cov_r, len_q, len_r,
-                                                     ctypes.c_float(min_af), ctypes.byref(out)))
-        exp = oracle.ani_finish(sum_m, sum_n, cov_q, cov_r, len_q, len_r, min_af)
-        assert np.float32(out.ani).view(np.uint32) == np.float32(exp[0]).view(np.uint32), (sum_m, sum_n)
+        small, contigs = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        ints.sum_fx, ints.n_chunks, ints.sum_m = sum(fx), n_chunks, 0
+        ints.span_m, ints.span_n, ints.n_chains, ints.cov_q, ints.cov_r = span_m, span_n, n_chains, cov_q, cov_r
+        _native.check(_native.lib().galah_b200_ani_finish(ctypes.byref(ints), len_q, len_r, int(small), int(contigs),
+                                                          ctypes.c_float(min_af), ctypes.byref(out)))
+        exp = oracle.ani_finish((sum(fx), n_chunks, cov_q, cov_r, len_q, len_r, 0, span_m, span_n, n_chains),
+                                min_af, 30 if small else 125, contigs)
+        assert np.float32(out.ani).view(np.uint32) == np.float32(exp[0]).view(np.uint32), (span_m, span_n, n_chunks)
+        assert out.estimator == exp[4]
+
+
+def test_chunk_identity_fixed_point_matches_oracle():
+    """round(2^40 (m/n)^(1/15)): the product's table entries == the oracle's per-chunk terms."""
+    rng = np.random.default_rng(4)
+    f = _native.lib().galah_b200_chunk_identity_fx
+    for n in list(range(1, 40)) + [int(x) for x in rng.integers(40, 30_000, 400)]:
+        for m in {0, 1, n // 3, n // 2, n - 1, n, int(rng.integers(0, n + 1))}:
+            assert int(f(m, n)) == oracle.chunk_identity_fx(m, n), (m, n)
+    assert int(f(5, 5)) == 1 << 40 and int(f(0, 7)) == 0

@@ -1,6 +1,7 @@
 """K3 parity: the CUDA seed-and-chain ANI vs oracle/skani_oracle.c, through the C ABI.  Everything
-the kernels produce is integer, so the bar is bit-exact: seed lists, (sum_m, sum_n, cov_q, cov_r),
-and the f32 bits of the final ANI."""
+the kernels produce is integer, so the bar is bit-exact: seed lists, the per-pair accumulators
+(sum of fixed-point chunk identities, chunk / chain counts, span and coverage sums), and the f32
+bits of the final ANI."""
 import os
 
 import numpy as np
@@ -22,15 +23,19 @@ def oracle_genome(records, c):
         return oracle.AniGenome.from_file(p, c=c)
 
 
-def check_pairs(idx, genomes, pairs, min_af):
-    got = idx.pairs(np.array(pairs, np.uint32), min_af)
+INT_FIELDS = ("sum_fx", "n_chunks", "cov_q", "cov_r", "sum_m", "span_m", "span_n", "n_chains")
+
+
+def check_pairs(idx, genomes, pairs, min_af, c=125, contigs=False):
+    got = idx.pairs(np.array(pairs, np.uint32), min_af, individual_contigs=contigs)
     for (a, b), g in zip(pairs, got):
-        sm, sn, cq, cr, lq, lr, swapped = oracle.ani_pair_integers(genomes[a], genomes[b])
-        assert (int(g["sum_m"]), int(g["sum_n"]), int(g["cov_q"]), int(g["cov_r"]), int(g["swapped"])) == \
-               (sm, sn, cq, cr, int(swapped)), (a, b)
-        exp = oracle.ani_finish(sm, sn, cq, cr, lq, lr, min_af)
+        ints = oracle.ani_pair_integers(genomes[a], genomes[b])  # query = a, the first of the pair
+        exp_ints = (ints[0], ints[1], ints[2], ints[3], ints[6], ints[7], ints[8], ints[9])
+        assert tuple(int(g[f]) for f in INT_FIELDS) == exp_ints, (a, b)
+        exp = oracle.ani_finish(ints, min_af, c, contigs)
         assert np.float32(g["ani"]).view(np.uint32) == np.float32(exp[0]).view(np.uint32), (a, b, g["ani"], exp[0])
         assert abs(g["af_query"] - exp[1]) < 1e-6 and abs(g["af_ref"] - exp[2]) < 1e-6
+        assert int(g["estimator"]) == exp[4]
     return got
 
 
@@ -64,13 +69,15 @@ def test_seeds_and_pairs_match_oracle_on_fasta_files(gb, tmp_path, small):
         assert np.array_equal(ks, og.kmer_strand) and np.array_equal(sp, og.spread) and np.array_equal(ch, og.chunk)
     n = len(paths)
     pairs = [(a, b) for a in range(n) for b in range(n) if a != b]
-    got = check_pairs(idx, genomes, pairs, 15.0)
+    got = check_pairs(idx, genomes, pairs, 15.0, c)
     res = {p: g for p, g in zip(pairs, got)}
     assert res[(0, 1)]["ani"] > 97.5 and res[(0, 3)]["ani"] == np.float32(100.0) and res[(0, 5)]["ani"] == 0.0
     assert res[(0, 4)]["ani"] == np.float32(100.0)
-    # argument order does not matter
-    assert res[(0, 2)]["ani"] == res[(2, 0)]["ani"] and res[(2, 0)]["swapped"] != res[(0, 2)]["swapped"]
-    check_pairs(idx, genomes, pairs[:8], 99.5)  # AF gate
+    # the query is the pair's first genome: swapping the arguments swaps the aligned fractions
+    assert abs(res[(0, 2)]["af_query"] - res[(2, 0)]["af_ref"]) < 0.02
+    assert abs(float(res[(0, 2)]["ani"]) - float(res[(2, 0)]["ani"])) < 0.3
+    check_pairs(idx, genomes, pairs[:8], 99.5, c)  # AF gate
+    check_pairs(idx, genomes, pairs[:12], 15.0, c, contigs=True)  # `-i` units: never the span estimator
     idx.close()
 
 
@@ -86,7 +93,7 @@ def test_repeats_and_max_occurrence_rule(gb, tmp_path):
     idx = gb.AniIndex()
     idx.add_files(paths)
     got = check_pairs(idx, genomes, [(0, 1), (1, 0)], 0.0)
-    assert got[0]["sum_n"] > 0
+    assert got[0]["span_n"] > 0 and got[1]["n_chunks"] > 0
     idx.close()
 
 

@@ -72,7 +72,8 @@ def test_contig_mode_and_clusters(gb, tmp_path):
     p2 = write_fasta(str(tmp_path / "c2.fna"), contigs[4:])
     got, n_units = gb.skani_distances([p1, p2], 95.0, 15.0, small_genomes=True, contigs=True)
     assert n_units == 6
-    exp = oracle.skani_distances(units_of([p1, p2], per_record=True), 95.0, 15.0, small_genomes=True)
+    exp = oracle.skani_distances(units_of([p1, p2], per_record=True), 95.0, 15.0, small_genomes=True,
+                                 individual_contigs=True)
     check(got, exp)
     clusters, info = gb.cluster_skani([p1, p2], precluster_ani=95.0, ani=95.0, min_aligned_fraction=15.0,
                                       small_genomes=True, cluster_contigs=True)
@@ -117,7 +118,8 @@ def test_device_resident_contigs_match_file_path_and_oracle(gb, tmp_path):
     for f in ("i", "j", "common", "total"):
         assert np.array_equal(got[f], via_files[f]), f
     assert np.array_equal(got["ani"].view(np.uint32), via_files["ani"].view(np.uint32))
-    exp = oracle.skani_distances(units_of([path], per_record=True), 90.0, 15.0, small_genomes=True)
+    exp = oracle.skani_distances(units_of([path], per_record=True), 90.0, 15.0, small_genomes=True,
+                                 individual_contigs=True)
     check(got, exp)
     # members of a synthetic family of 10 only ever pair with each other
     assert np.all(got["i"] // 10 == got["j"] // 10)
