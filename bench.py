@@ -1,18 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- genome-pairs/sec of the finch-prefilter hot path on B200 (BASELINE.json metric).
+"""bench.py -- genome-pairs/sec (prefilter+ANI) of Galah's two-stage hot path on B200 (BASELINE.json).
 
-A "step" is one pass of the all-pairs prefilter (reference src/finch.rs:75-95) over the sketch
-table of N synthetic genomes (families of 10, 2 Mbp, seed 1, sketched on the GPU by
-K1 during untimed setup).  At --gpus 1 the workload is BASELINE.json configs[1]: 10,000 genomes,
-s = 1000, prefilter only.  At G > 1 GPUs the genome count grows as 10,000 * sqrt(G) so that the
-pair area per GPU is constant (weak scaling); every rank sketches its own genome slice, and the
-timed step is: NCCL all-gather of the sketch table -> row-block-sharded prefilter kernel.
+A "step" is ONE pass of the whole hot path (reference src/clusterer.rs:14-152 driving
+src/finch.rs:48-97 and src/skani.rs:689-788) over N synthetic genomes (families of
+10, 2 Mbp, seed 1): K1 MinHash sketches + K3 seed index of every genome, K2 all-pairs prefilter
+(finch, min_ani 0.9), K3 ANI of every prefilter hit (skani restatement, 95 %, min-AF 15), greedy
+representative selection.  At --gpus 1 the workload is BASELINE.json configs[2]: 50,000 genomes.
+Genome synthesis is setup (untimed); everything the reference does inside cluster() is timed.
 
-  value    = pairs / device time (CUDA events on the launch stream, max over ranks), inputs in HBM
-  e2e      = same metric through the host-buffer C-ABI call (H2D table, kernel, D2H pair list,
-             f64 finish + sort on the host)
-  roofline = algorithmic bytes (16,000 B/pair = 2*s*8) / kernel time vs the measured HBM peak
-  cpu_baseline = the oracle's serial pair loop (as the reference's) on a row sample, host cores
+  value    = N(N-1)/2 pairs / step time, packed genomes resident in HBM when the step starts
+             (galah_b200_cluster_packed_device; CUDA events on the library's stream)
+  e2e      = the same through galah_b200_cluster_packed with HOST buffers: every step uploads the
+             packed genomes (pinned, batches behind the previous batch's kernels) and reads the
+             survivors / accumulators / clusters back
+  roofline = the step's dominant kernel family against the measured HBM peak; `kernels` lists
+             every family with its algorithmic bytes, device time and share of the step
+  cpu_baseline = the oracle port of the same path on a bounded sample, host cores
+
+At G > 1 GPUs (one process per GPU) the genome count grows as N * sqrt(G) (constant pair area per
+GPU, "weak"): every rank sketches and indexes its own genome slice, K2 is row-block sharded, K3
+pairs go to the rank that owns the query genome and read the reference genome's table through
+peer-mapped memory over NVLink; the greedy engine runs on rank 0.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/) only.
 """
@@ -32,30 +40,19 @@ sys.path.insert(0, ROOT)
 
 S = 1000
 K = 21
-MIN_ANI = 0.9
+MIN_ANI = 0.9          # FinchPreclusterer min_ani (fraction), galah --precluster-ani 90
+ANI_PCT = 95.0         # SkaniClusterer threshold, galah --ani 95
+MIN_AF = 15.0          # galah --min-aligned-fraction 15
 SEED = 1
-BYTES_PER_PAIR = 2 * S * 8
+METRIC = "genome-pairs/sec (prefilter+ANI)"
 
 
 def n_genomes_for(gpus, base):
-    n = base * math.sqrt(gpus)
-    # per rank a whole number of families of 10 AND of row blocks of 128 (so a rank's slice is whole
-    # block lists and its build needs no gathered table): multiples of lcm(10, 128) = 640
-    q = 640 * gpus if gpus > 1 else 80
-    return max(q, int(round(n / q)) * q)
-
-
-def ncu_traffic(kernel, n, world):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json);
-    only valid for the workload it was captured on (1 GPU, same N), else None."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if world != 1 or not os.path.exists(p):
-        return None
-    with open(p) as f:
-        t = json.load(f)
-    if t.get("n_genomes") != n or kernel not in t:
-        return None
-    return t[kernel]["dram_bytes_read"] + t[kernel]["dram_bytes_write"]
+    if gpus == 1:
+        return base
+    # per rank a whole number of families of 10 AND of row blocks of 128: multiples of 640 per rank
+    q = 640 * gpus
+    return max(q, int(round(base * math.sqrt(gpus) / q)) * q)
 
 
 def peaks():
@@ -64,6 +61,19 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    if kernel not in t:
+        return None
+    return {"bytes_per_launch": t[kernel]["dram_bytes_read"] + t[kernel]["dram_bytes_write"],
+            "captured_at": t[kernel].get("workload", t.get("workload"))}
 
 
 class ClockSampler:
@@ -80,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -92,8 +102,6 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def mark(self):
-        """Drop what was sampled so far, but keep the latest row so that a timed region shorter
-        than the sampling interval still has a reading taken under the same load."""
         self.rows = self.rows[-1:]
 
     def stop(self):
@@ -113,70 +121,135 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU restatement of the reference path (oracle/), on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_path_sample(n_total, L, n_sketch, pair_target_serial, pair_target_mt, n_ani, table=None):
+    """Times the three parts of the reference's cluster() on samples of the synthetic workload and
+    combines them into the metric for the FULL workload of n_total genomes:
+      sketching   finch::sketch_files, all host threads (src/finch.rs:55-69)      -> s per genome
+      pair loop   the reference's SERIAL nested loop (src/finch.rs:75-95)          -> s per pair
+      ANI         skani per prefilter hit: both genomes re-sketched per pair, as the reference's
+                  one-subprocess-per-pair does (src/skani.rs:718-788), all host threads via the
+                  reference's rayon find_any (src/clusterer.rs:262-296)           -> s per hit
+    value = P / (n_total * t_sketch + P * t_pair + hits * t_ani),  P = n_total (n_total - 1) / 2,
+    hits = 4.5 prefilter hits per family of 10 as measured on the GPU arm (passed in by the caller
+    through n_ani's companion `hits_total`, else estimated from the sample)."""
+    import oracle
+    oracle.build()
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    tab, cnt = oracle.sketch_synth(SEED, 0, n_sketch, L, K, S, 0)
+    t_sketch = (time.perf_counter() - t0) / n_sketch            # wall per genome with all threads
+    if table is not None:
+        tab, cnt = table
+    n_tab = len(cnt)
+    rows_serial = max(1, min(n_tab - 1, int(math.ceil(pair_target_serial / max(1, n_tab - 1)))))
+    pairs_serial = sum(n_tab - 1 - i for i in range(rows_serial))
+    t0 = time.perf_counter()
+    hits = oracle.prefilter(tab, cnt, K, MIN_ANI, row_begin=0, row_end=rows_serial)
+    t_pair = (time.perf_counter() - t0) / pairs_serial
+    rows_mt, acc = 0, 0
+    while rows_mt < n_tab - 1 and acc < pair_target_mt:
+        acc += n_tab - 1 - rows_mt
+        rows_mt += 1
+    t0 = time.perf_counter()
+    n_hits_mt = oracle.prefilter_count_mt(tab, cnt, K, MIN_ANI, row_begin=0, row_end=rows_mt)
+    t_pair_mt = (time.perf_counter() - t0) / max(acc, 1)
+    # ANI: hit pairs of the sample, each with both genomes regenerated + seeded (nothing cached)
+    sample = [(int(h["i"]), int(h["j"])) for h in hits[:n_ani]]
+    t0 = time.perf_counter()
+    anis = []
+    for a, b in sample:
+        ga = oracle.AniGenome(*oracle.codes_from_ascii(oracle.synth_genome(SEED, a, L)))
+        gb_ = oracle.AniGenome(*oracle.codes_from_ascii(oracle.synth_genome(SEED, b, L)))
+        anis.append(float(oracle.ani_pair(ga, gb_, MIN_AF)[0]))
+    t_ani_serial = (time.perf_counter() - t0) / max(len(sample), 1)
+    t_ani = t_ani_serial / cores                                  # rayon over pairs in the reference
+    return {"t_sketch_per_genome_s": t_sketch, "t_pair_serial_s": t_pair, "t_pair_all_cores_s": t_pair_mt,
+            "t_ani_per_hit_serial_s": t_ani_serial, "t_ani_per_hit_all_cores_s": t_ani, "cores": cores,
+            "n_sketch": n_sketch, "pairs_serial": pairs_serial, "pairs_all_cores": acc, "n_ani": len(sample),
+            "hits_in_serial_rows": int(len(hits)), "hits_in_mt_rows": int(n_hits_mt), "table_genomes": n_tab,
+            "sample_anis": anis, "sample_pairs": sample}
+
+
+def cpu_value(parts, n_total, hits_total):
+    P = n_total * (n_total - 1) / 2
+    t = n_total * parts["t_sketch_per_genome_s"] + P * parts["t_pair_serial_s"] + hits_total * parts["t_ani_per_hit_all_cores_s"]
+    t_mt = n_total * parts["t_sketch_per_genome_s"] + P * parts["t_pair_all_cores_s"] + hits_total * parts["t_ani_per_hit_all_cores_s"]
+    return P / t, P / t_mt
+
+
+def sample_text(parts, n_total):
+    return (f"sketch of {parts['n_sketch']} genomes on {parts['cores']} threads; pair loop over rows of a "
+            f"{parts['table_genomes']}-genome sketch table of the same synthetic families: {parts['pairs_serial']} pairs "
+            f"serial (as src/finch.rs:75-95) + {parts['pairs_all_cores']} pairs on all threads; ANI of {parts['n_ani']} "
+            f"prefilter hits, both genomes re-seeded per pair (as skani per subprocess); combined for {n_total} genomes")
+
+
 def run_reference(args):
-    """CPU restatement of the reference path (oracle/): all-core sketch of a genome sample
-    (untimed, as our arm's setup), then the SERIAL pair loop exactly as src/finch.rs:75-95."""
+    """`--impl reference`: the oracle port of the reference path on the box's host cores.  Each step
+    is a bounded sample (>= 1e7 genome pairs through the pair loop, all threads where the
+    reference has threads); the headline keeps the reference's SERIAL pair loop."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     oracle.build()
+    n_total = n_genomes_for(args.gpus, args.n_genomes)
+    L = args.genome_len
     cores = os.cpu_count() or 1
-    n_sample = args.ref_genomes
-    t0 = time.time()
-    table, counts = oracle.sketch_synth(SEED, 0, n_sample, args.genome_len, K, S, 0)
-    t_sketch = time.time() - t0
-    rows = args.ref_rows
-    pairs_per_step = sum(n_sample - 1 - i for i in range(rows))
-    times = []
+    t0 = time.perf_counter()
+    n_tab = args.ref_table_genomes
+    table = oracle.sketch_synth(SEED, 0, n_tab, L, K, S, 0)   # setup of the pair-loop table (untimed)
+    t_setup = time.perf_counter() - t0
+    hits_total = 4.5 * n_total / 10 * 1.0                        # 45 within-family pairs / 10 genomes pass 0.9
+    times, vals, vals_mt, last = [], [], [], None
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        oracle.prefilter(table, counts, K, MIN_ANI, row_begin=0, row_end=rows)
+        parts = cpu_path_sample(n_total, L, n_sketch=2 * cores, pair_target_serial=2.0e5, pair_target_mt=1.0e7,
+                                n_ani=4, table=table)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
-            times.append(dt)
-    total = sum(times)
-    value = pairs_per_step * len(times) / total
-    # context only: the same rows with every host thread (the reference's loop itself is serial,
-    # src/finch.rs:75-95, so the headline of this arm stays the one-thread figure)
-    t0 = time.perf_counter()
-    oracle.prefilter_count_mt(table, counts, K, MIN_ANI, row_begin=0, row_end=rows)
-    all_cores_value = pairs_per_step / (time.perf_counter() - t0)
-    sample = (f"rows 0..{rows} x {n_sample} columns of the synthetic sketch table "
-              f"({pairs_per_step} pairs/step), serial loop as src/finch.rs:75-95; "
-              f"sketch of the {n_sample}-genome sample on {cores} threads took {t_sketch:.1f}s (untimed)")
+            v, v_mt = cpu_value(parts, n_total, hits_total)
+            times.append(dt); vals.append(v); vals_mt.append(v_mt); last = parts
+    value = float(np.mean(vals))
+    sample = sample_text(last, n_total) + f"; table sketched once in {t_setup:.1f}s (setup)"
     line = {
-        "impl": "reference", "metric": "genome-pairs/sec (finch prefilter, s=1000)", "value": value,
-        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"{n_genomes_for(args.gpus, args.n_genomes)} synthetic 2 Mbp genomes, "
-                               "s=1000 finch prefilter only (BASELINE.json configs[1])",
-                   "timed_sample": sample},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": 1, "kind": "port", "sample": sample,
-                         "all_cores_value": all_cores_value, "all_cores": cores},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_text(n_total, L, args.gpus), "timed_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "all_cores_pair_loop_value": float(np.mean(vals_mt)),
+                         "parts": {k: v for k, v in last.items() if not k.startswith("sample_")}},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def workload_text(n, L, gpus):
+    return (f"{n} synthetic {L} bp genomes (families of 10, seed {SEED}): finch prefilter s={S} k={K} min_ani {MIN_ANI} "
+            f"+ skani-restatement ANI {ANI_PCT} %, min-AF {MIN_AF} %, greedy clustering (BASELINE.json configs[2]"
+            f"{', genomes scaled by sqrt(G)' if gpus > 1 else ''})")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-genomes", type=int, default=10000, help="genomes at 1 GPU (x sqrt(G) at G GPUs)")
+    ap.add_argument("--n-genomes", type=int, default=50000, help="genomes at 1 GPU (x sqrt(G) at G GPUs)")
     ap.add_argument("--genome-len", type=int, default=2_000_000)
-    ap.add_argument("--mode", type=int, default=0, help="0 = block-list join (default), 1 = pairwise warp merge")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other-mode", action="store_true", help="skip timing the other kernel path")
-    ap.add_argument("--no-stage2", action="store_true", help="skip the stage-2 (ANI on prefilter survivors) section")
-    ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA-ingest (K0) section")
-    ap.add_argument("--cpu-rows", type=int, default=100)
-    ap.add_argument("--ref-genomes", type=int, default=2000)
-    ap.add_argument("--ref-rows", type=int, default=100)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prefilter-record", action="store_true", help="skip the prefilter-only (K2) sub-record")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-clade sub-record")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA-ingest (K0) sub-record")
+    ap.add_argument("--dense-genomes", type=int, default=2000)
+    ap.add_argument("--ref-table-genomes", type=int, default=4000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -201,110 +274,16 @@ def main():
     torch.cuda.set_device(local_rank)
     gb.init(local_rank)
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream()
-    st = stream.cuda_stream
+    lib_stream = torch.cuda.ExternalStream(gb.stream(), device=dev)  # the stream the library launches on
 
-    n = n_genomes_for(world, args.n_genomes) if args.n_genomes >= 80 else args.n_genomes
+    n = n_genomes_for(world, args.n_genomes)
     n_local = n // world
     L = args.genome_len
-
-    # ---------------- setup (untimed): synthetic genomes -> K1 sketches of this rank's slice
-    my_table = torch.empty((n_local, S), dtype=torch.int64, device=dev)
-    my_counts = torch.empty(n_local, dtype=torch.int32, device=dev)
-    batch = max(1, min(n_local, (1 << 30) // max(L, 1)))  # ~1 G bases (375 MB packed) per batch
-    lay = gb.synth_layout(batch, L)
-    d_seq = torch.zeros(lay["seq2_words"], dtype=torch.int32, device=dev)
-    d_val = torch.zeros(lay["valid_words"], dtype=torch.int32, device=dev)
-    d_off = torch.zeros(batch + 1, dtype=torch.int64, device=dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sketch_ms = 0.0
-    synth_ms = 0.0
-    stage2 = not args.no_stage2 and world == 1
-    ani_index = gb.AniIndex() if stage2 else None
-    ani_build_ms = 0.0
-    for b0 in range(0, n_local, batch):
-        nb = min(batch, n_local - b0)
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record(stream)
-        gb.synth_packed_device(SEED, rank * n_local + b0, nb, L, d_seq.data_ptr(), d_val.data_ptr(),
-                               d_off.data_ptr(), st)
-        e1.record(stream)
-        gb.sketch_packed_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), nb, K, S, 0,
-                                my_table[b0:].data_ptr(), my_counts[b0:].data_ptr(), st)
-        e2.record(stream)
-        torch.cuda.synchronize()
-        synth_ms += e0.elapsed_time(e1)
-        sketch_ms += e1.elapsed_time(e2)
-        if stage2:
-            ani_index.add_packed_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(),
-                                        np.arange(nb + 1, dtype=np.uint64) * np.uint64(lay["padded"]),
-                                        np.full(nb, L, np.uint64), st)
-            ani_build_ms += ani_index.last_timing()[0]
-            if b0 == 0:
-                ani_index.reserve(n_local)
-    del d_seq, d_val, d_off
-
-    flush = torch.empty(256 << 20, dtype=torch.int8, device=dev)  # > 126 MB L2
-    sp = None
-    if world > 1:
-        # multi-GPU: galah_b200.distributed.ShardedPrefilter is the product path; the timed step is
-        # its device part (all-reduce of the largest hash, table all-gather overlapped with the
-        # per-rank build of its own block lists, all-gather of the lists, join of the rank's shard)
-        from galah_b200.distributed import ShardedPrefilter
-        sp = ShardedPrefilter(gb, dist, n_local, S, dev)
-        sp.my_table.copy_(my_table)
-        sp.my_counts.copy_(my_counts)
-        table, counts, d_cand, d_ncand, cand_cap = sp.table, sp.counts, sp.d_cand, sp.d_ncand, sp.cand_cap
-    else:
-        table, counts = my_table, my_counts
-        cand_cap = max(1 << 20, 64 * n)
-        d_cand = torch.empty((cand_cap, 4), dtype=torch.int32, device=dev)
-        d_ncand = torch.zeros(1, dtype=torch.int64, device=dev)
-
-    def timed(mode, steps, warmup):
-        """`steps` timed passes of `mode`; returns (total_ms max over ranks, launches, per-kernel ms)."""
-        def step():
-            if world > 1 and mode == 0:
-                sp.step_device(K, MIN_ANI)
-                return
-            if world > 1:
-                dist.all_gather_into_tensor(table, my_table)
-                dist.all_gather_into_tensor(counts, my_counts)
-            gb.prefilter_enqueue(table.data_ptr(), counts.data_ptr(), n, S, K, MIN_ANI, rank, world,
-                                 mode, st, d_cand.data_ptr(), cand_cap, d_ncand.data_ptr())
-        for _ in range(warmup):
-            flush.fill_(1)
-            step()
-        sync_all()
-        if steps == 0:
-            return 0.0, 0, 0.0, 0.0
-        launches0 = gb.launch_count()
-        step_ms, build_ms, main_ms = [], [], []
-        for _ in range(steps):
-            flush.fill_(1)  # L2 flush between timed iterations (outside the events)
-            sync_all()
-            ev0.record(stream)
-            t_host = time.perf_counter()
-            step()
-            host_enqueue_ms.append(1e3 * (time.perf_counter() - t_host))
-            ev1.record(stream)
-            torch.cuda.synchronize()
-            step_ms.append(ev0.elapsed_time(ev1))
-            b, m = gb.prefilter_last_timing()
-            build_ms.append(b); main_ms.append(m)
-        sync_all()
-        launches = gb.launch_count() - launches0
-        tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        return float(tot.item()), launches, float(np.mean(build_ms)), float(np.mean(main_ms))
-
-    host_enqueue_ms = []
+    pairs = n * (n - 1) // 2
 
     def sync_all():
         torch.cuda.synchronize()
@@ -312,133 +291,302 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---------------- setup (untimed): this rank's synthetic genomes, packed, resident in HBM
+    lay = gb.synth_layout(n_local, L)
+    d_seq = torch.empty(lay["seq2_words"], dtype=torch.int32, device=dev)
+    d_val = torch.empty(lay["valid_words"], dtype=torch.int32, device=dev)
+    d_off = torch.empty(n_local + 1, dtype=torch.int64, device=dev)
+    t0 = time.perf_counter()
+    gb.synth_packed_device(SEED, rank * n_local, n_local, L, d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(),
+                           torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    synth_s = time.perf_counter() - t0
+    base_off = np.arange(n_local + 1, dtype=np.uint64) * np.uint64(lay["padded"])
+    lengths = np.full(n_local, L, np.uint64)
+    resident_bytes = d_seq.numel() * 4 + d_val.numel() * 4
+
+    pipe = None
+    if world > 1:
+        from galah_b200.distributed import ShardedPipeline
+        pipe = ShardedPipeline(gb, dist, n_local, S, dev)
+
+    def step():
+        if world > 1:
+            return pipe.step_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), base_off, lengths,
+                                    MIN_ANI, ANI_PCT, MIN_AF)
+        return gb.cluster_packed(d_seq.data_ptr(), d_val.data_ptr(), base_off, lengths, precluster_ani=MIN_ANI,
+                                 ani=ANI_PCT, min_aligned_fraction=MIN_AF, device=True, d_base_off=d_off.data_ptr())
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()  # nvidia-smi needs a moment to start: launched ahead of the warm-up passes
-    timed(args.mode, 0, args.warmup)
+        sampler.start()
+    for _ in range(args.warmup):
+        clusters, info = step()
+    sync_all()
     if rank == 0:
-        sampler.mark()   # only samples from here on (the timed region) are kept
-    total_ms, launches, build_ms, main_ms = timed(args.mode, args.steps, 0)
-    clocks = sampler.stop() if rank == 0 else None
-    pairs = n * (n - 1) // 2
-    value = pairs * args.steps / (total_ms * 1e-3)
-    n_cand = int(d_ncand.item())
-    # the other exact kernel path, for comparison (fewer steps: the pairwise kernel is ~100x slower)
-    other = None
-    if not args.no_other_mode:
-        o_steps = max(1, min(args.steps, 3))
-        o_total, o_launches, o_build, o_main = timed(1 - args.mode, o_steps, 1)
-        other = {"mode": 1 - args.mode, "value": pairs * o_steps / (o_total * 1e-3), "unit": "pairs/s",
-                 "ms_per_step": o_total / o_steps, "steps": o_steps, "main_kernel_ms": o_main,
-                 "candidates": int(d_ncand.item())}
-
-    # ---------------- e2e: host buffers through the public API (H2D + kernels + D2H + host finish)
-    # 1 GPU: the host-buffer C-ABI call.  G GPUs: galah_b200.distributed.ShardedPrefilter -- every
-    # rank uploads ITS slice of the table, all-gather over NVLink, sharded build + join.
-    h_table = table.cpu().pin_memory()
-    h_counts = counts.cpu().pin_memory()
-    np_table = h_table.numpy().view(np.uint64)   # views of the pinned host buffers
-    np_counts = h_counts.numpy().view(np.uint32)
-    e2e_times = []
-    n_pass = 0
-    if world > 1:
-        h_my_table = h_table[rank * n_local:(rank + 1) * n_local]
-        h_my_counts = h_counts[rank * n_local:(rank + 1) * n_local]
-    for it in range(2 + min(args.steps, 5)):
+        sampler.mark()
+    launches0 = gb.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall, infos = [], []
+    for it in range(args.steps):
         sync_all()
+        ev[it][0].record(lib_stream)
         t0 = time.perf_counter()
-        if world > 1:
-            res = sp(h_my_table, h_my_counts, K, MIN_ANI)
-        else:
-            res = gb.prefilter(np_table, np_counts, K, MIN_ANI, shard=rank, n_shards=world)
-        dt = time.perf_counter() - t0
-        n_pass = len(res)
-        if it >= 2:
-            e2e_times.append(dt)
-    e2e_host = gb.prefilter_last_host_timing() if world == 1 else None
-    e2e_single_upload = None
-    if world == 1:
-        # the same call with the upload pipeline off (one 80 MB copy, then the kernels)
-        prev_chunks = gb.prefilter_stream_chunks(1)
-        ts = []
-        for it in range(4):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            res1 = gb.prefilter(np_table, np_counts, K, MIN_ANI)
-            if it >= 1:
-                ts.append(time.perf_counter() - t0)
-        gb.prefilter_stream_chunks(prev_chunks)
-        assert len(res1) == len(res) and np.array_equal(res1["j"], res["j"]) and np.array_equal(
-            res1["ani"].view(np.uint32), res["ani"].view(np.uint32))
-        e2e_single_upload = {"value": n * (n - 1) // 2 / (sum(ts) / len(ts)), "ms": 1e3 * sum(ts) / len(ts),
-                             "host_ms": gb.prefilter_last_host_timing()}
-    e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
-    n_pass_t = torch.tensor([n_pass], dtype=torch.int64, device=dev)
+        clusters, info = step()
+        ev[it][1].record(lib_stream)
+        torch.cuda.synchronize()
+        wall.append(time.perf_counter() - t0)
+        infos.append(info)
+    sync_all()
+    launches = gb.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(n_pass_t, op=dist.ReduceOp.SUM)
-    e2e_value = pairs / float(e2e_t.item())
-    h2d = h_table.numel() * 8 + h_counts.numel() * 4  # whole job: at G GPUs every rank uploads 1/G of it
-    d2h = int(n_pass) * 16 + 8
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms = float(tot.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = pairs * args.steps / (total_ms * 1e-3)
+    phase = {k: float(np.mean([i[k] for i in infos])) for k in
+             ("sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "ani_chain_ms", "engine_ms", "ingest_ms", "total_ms")
+             if k in infos[0]}
+    n_hits = int(infos[-1]["n_precluster_hits"])
+    n_clusters = len(clusters) if clusters is not None else None
 
-    # ---------------- stage 2: ANI of every prefilter survivor (K3), then the greedy engine
-    two_stage = None
-    if stage2:
-        hit_pairs = np.stack([res["i"], res["j"]], axis=1).astype(np.uint32)
-        ani_index.pairs(hit_pairs[: min(len(hit_pairs), 1024)], 15.0)  # warm-up
-        t0 = time.perf_counter()
-        ani_res = ani_index.pairs(hit_pairs, 15.0)
-        t_ani = time.perf_counter() - t0
-        chain_ms = ani_index.last_timing()[1]
-        t0 = time.perf_counter()
-        clusters, cinfo = gb.cluster_from_ani_table(n, res, ani_res["ani"], 95.0)
-        t_greedy = time.perf_counter() - t0
-        table = {(int(a), int(b)): float(v) for (a, b), v in zip(hit_pairs, ani_res["ani"])}
-        seeds_per_genome = float(np.mean([ani_index.genome(g)["n_seeds"] for g in range(0, n, max(1, n // 50))]))
-        e2e_prefilter_s = float(e2e_t.item())
-        two_stage = {
-            "workload": f"ANI (c=125, k=15) of the {len(hit_pairs)} prefilter survivors, 95 % threshold, min-AF 15",
-            "ani_pairs": int(len(hit_pairs)), "ani_pairs_per_s": len(hit_pairs) / t_ani,
-            "ani_chain_kernel_ms": chain_ms, "ani_call_ms": 1e3 * t_ani,
-            "index_build_ms_total": ani_build_ms, "index_genomes_per_s": n / (ani_build_ms * 1e-3) if ani_build_ms else None,
-            "seeds_per_genome": seeds_per_genome,
-            "chain_kernel_gbs_algorithmic": (2 * seeds_per_genome * 12 * len(hit_pairs)) / (chain_ms * 1e-3) / 1e9 if chain_ms else None,
-            "greedy_engine_ms": 1e3 * t_greedy, "clusters": len(clusters),
-            "genome_pairs_per_s_prefilter_plus_ani": pairs / (e2e_prefilter_s + t_ani + t_greedy),
-            "note": "genome_pairs_per_s_prefilter_plus_ani = N(N-1)/2 pairs considered / (host-buffer prefilter call "
-                    "+ ANI call + greedy engine, all through the C ABI)",
-        }
-        if not args.no_cpu_baseline:
+    # ---------------- e2e: HOST buffers through the C ABI, every step uploads the packed genomes
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = resident_bytes
+        avail = psutil.virtual_memory().available
+        if avail > 2.5 * need + (8 << 30):
+            h_seq = torch.empty(d_seq.numel(), dtype=torch.int32, pin_memory=True)
+            h_val = torch.empty(d_val.numel(), dtype=torch.int32, pin_memory=True)
+            h_seq.copy_(d_seq); h_val.copy_(d_val)
+            torch.cuda.synchronize()
+
+            def e2e_step():
+                if world > 1:
+                    return pipe.step_host(h_seq.data_ptr(), h_val.data_ptr(), base_off, lengths, MIN_ANI, ANI_PCT, MIN_AF)
+                return gb.cluster_packed(h_seq.data_ptr(), h_val.data_ptr(), base_off, lengths, precluster_ani=MIN_ANI,
+                                         ani=ANI_PCT, min_aligned_fraction=MIN_AF, device=False)
+            ts, e_info = [], None
+            for it in range(1 + min(args.steps, 3)):
+                sync_all()
+                t0 = time.perf_counter()
+                e_clusters, e_info = e2e_step()
+                dt = time.perf_counter() - t0
+                if it >= 1:
+                    ts.append(dt)
+            e_t = torch.tensor([float(np.mean(ts))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+            same = (e_clusters == clusters) if rank == 0 else None
+            h2d = world * (need + (n_local + 1) * 8)
+            d2h = n_hits * (16 + 48) + n * 4 + 16
+            e2e = {"value": pairs / float(e_t.item()), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms": 1e3 * float(e_t.item()),
+                   "phases_ms": {k: e_info[k] for k in ("ingest_ms", "sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms") if k in e_info},
+                   "upload_overlap": "batches of ~1 G bases cross PCIe on a copy stream behind the K1 / K3-index kernels of the previous batch",
+                   "pcie_gbs_if_serial": need / 1e9 / float(e_t.item()),
+                   "clusters_identical_to_resident_run": same}
+            del h_seq, h_val
+        else:
+            e2e = {"value": None, "unit": "pairs/s", "h2d_bytes_per_step": int(need), "d2h_bytes_per_step": 0,
+                   "skipped": f"host has {avail >> 30} GiB available, pinned copy of the packed genomes needs {need >> 30} GiB"}
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        sub = {}
+        if world == 1:
+            sub = single_gpu_records(args, gb, torch, dev, d_seq, d_val, d_off, base_off, lengths, n, L, clusters)
+        # ---- roofline: one entry per kernel family, algorithmic bytes per unit from SURVEY.md 8d
+        seeds_per_genome = L / 125.0
+        fam = []
+        def add(name, kernels, ms, units, unit, bytes_per_unit, bound, note):
+            if ms is None or ms <= 0:
+                return
+            gbs = bytes_per_unit * units / (ms * 1e-3) / 1e9
+            fam.append({"family": name, "kernels": kernels, "ms_per_step": ms, "share_of_step": ms / (total_ms / args.steps),
+                        "units_per_step": units, "unit": unit, "algorithmic_bytes_per_unit": bytes_per_unit,
+                        "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "bound": bound, "note": note})
+        add("K1 sketch", ["sketch_scan_kernel", "sketch_select_kernel"], phase.get("sketch_ms"), n_local, "genome",
+            L / 4 + L / 8 + 8 * S, "integer ALU (MurmurHash3 per k-mer); HBM fraction reported as asked",
+            "L/4 packed + L/8 validity read, 8 s written per genome")
+        add("K3 index", ["ani_mark_kernel", "ani_emit_kernel"], phase.get("index_ms"), n_local, "genome",
+            L / 4 + L / 8 + seeds_per_genome * (8 + 16), "integer ALU (mm_hash64 per k-mer) + scattered table inserts",
+            "packed read + 8 B seed + 2 x 8 B table slots per seed written")
+        k2 = sub.get("prefilter_only") or {}
+        add("K2 prefilter", ["bl_* build", "prefilter_join_kernel"], k2.get("ms_per_step"), pairs, "pair", 2 * S * 8,
+            "issue slots / shared-memory wavefronts (block-list join); the 16 kB/pair figure is the reference "
+            "algorithm's traffic, which the join does not move: frac_of_hbm_peak > 1 is a REUSE factor, see own_*",
+            "own traffic: 2*s*4/128 = 62.5 B of L2-resident list keys per pair")
+        if fam and fam[-1]["family"] == "K2 prefilter":
+            own = 2 * S * 4 / gb.ROW_BLOCK
+            fam[-1]["own_bytes_per_unit"] = own
+            fam[-1]["own_gbs"] = own * pairs / (k2["join_kernel_ms"] * 1e-3) / 1e9 if k2.get("join_kernel_ms") else None
+            fam[-1]["own_frac_of_hbm_peak"] = fam[-1]["own_gbs"] / peak if fam[-1]["own_gbs"] else None
+            fam[-1]["dram_traffic"] = ncu_traffic("prefilter_join_kernel")
+        add("K3 chain", ["ani_chain_kernel"], phase.get("ani_chain_ms"), n_hits // world if world > 1 else n_hits, "hit pair",
+            2 * seeds_per_genome * 12, "latency of dependent table probes (L2 / HBM)",
+            "2 * (L/c) * 12 B seed entries per pair (SURVEY.md 8d)")
+        dom = max(fam, key=lambda f: f["ms_per_step"]) if fam else None
+        roofline = None
+        if dom:
+            roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": dom["achieved_gbs"] / peak, "traffic": (ncu_traffic(dom["kernels"][0]) or {}).get("bytes_per_launch"),
+                        "kernel": dom["family"] + " (" + ", ".join(dom["kernels"]) + ")", "kernel_ms": dom["ms_per_step"],
+                        "share_of_step": dom["share_of_step"], "algorithmic_bytes_per_unit": dom["algorithmic_bytes_per_unit"],
+                        "units_per_launch": dom["units_per_step"], "peak_source": peak_src,
+                        "note": "dominant kernel family of the step by device time; " + dom["bound"],
+                        "kernels": fam}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
             import oracle
-            sample = hit_pairs[:: max(1, len(hit_pairs) // 60)][:60]
-            gen = {}
-            for g in sorted(set(int(x) for x in sample.ravel())):
-                gen[g] = oracle.AniGenome(*oracle.codes_from_ascii(oracle.synth_genome(SEED, g, L)))
-            t0 = time.perf_counter()
-            bad = 0
-            for a, b in sample:
-                v = oracle.ani_pair(gen[int(a)], gen[int(b)], 15.0)[0]
-                bad += int(np.float32(v) != np.float32(table[(int(a), int(b))]))
-            dt = time.perf_counter() - t0
-            two_stage["cpu_baseline"] = {"value": len(sample) / dt, "unit": "ANI pairs/s", "cores": 1, "kind": "port",
-                                         "sample": f"{len(sample)} of the survivor pairs, seeds precomputed (the "
-                                                   "reference re-sketches both genomes in a fresh skani process per pair)",
-                                         "gpu_matches_oracle_on_sample": bad == 0}
+            parts = cpu_path_sample(n, L, n_sketch=2 * (os.cpu_count() or 1), pair_target_serial=2.0e5,
+                                    pair_target_mt=2.0e6, n_ani=4, table=sub.get("_table_sample"))
+            v, v_mt = cpu_value(parts, n, n_hits)
+            ok = None
+            if sub.get("_ani_lookup") is not None:
+                look = sub["_ani_lookup"]
+                ok = all(np.float32(look.get(p, -1.0)) == np.float32(a) for p, a in zip(parts["sample_pairs"], parts["sample_anis"]))
+            cpu = {"value": v, "unit": "pairs/s", "cores": parts["cores"], "kind": "port", "sample": sample_text(parts, n),
+                   "all_cores_pair_loop_value": v_mt, "gpu_matches_oracle_on_sample": ok,
+                   "parts": {k: v2 for k, v2 in parts.items() if not k.startswith("sample_")}}
+        sub = {k: v for k, v in sub.items() if not k.startswith("_")}
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_text(n, L, world), "pairs_per_step": pairs, "genomes": n,
+                       "l2": f"inputs larger than L2 ({resident_bytes >> 20} MiB of packed sequence per GPU, read once per step)",
+                       "timed_region": "K1 sketch + K3 index of every genome, K2 all pairs, K3 ANI of every prefilter hit, "
+                                       "f64 finish + greedy engine on the host; genome synthesis is setup",
+                       "sharding": "one process per GPU: genome slices for K1 / K3 index, boustrophedon row blocks for K2 "
+                                   "(NCCL all-gather of the sketch table), K3 pairs on the query's rank reading the "
+                                   "reference table through peer-mapped memory (NVLink), engine on rank 0"
+                                   if world > 1 else "single GPU"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "phases_ms": phase,
+            "result": {"prefilter_hits": n_hits, "clusters": n_clusters, "host_wall_ms_per_step": 1e3 * float(np.mean(wall)),
+                       "synth_setup_s": synth_s},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        line.update(sub)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
 
-    # ---------------- K0: FASTA ingest on the device vs the host packer
-    ingest = None
-    if rank == 0 and world == 1 and not args.no_ingest:
+
+def single_gpu_records(args, gb, torch, dev, d_seq, d_val, d_off, base_off, lengths, n, L, clusters):
+    """Sub-records of the 1-GPU line: prefilter only (K2, the configs[1] kernel at this N), a dense
+    clade, FASTA ingest.  None of them is inside the headline's timed region."""
+    out = {}
+    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.int8, device=dev)
+    table = torch.empty((n, S), dtype=torch.int64, device=dev)
+    counts = torch.empty(n, dtype=torch.int32, device=dev)
+    gb.sketch_packed_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), n, K, S, 0, table.data_ptr(),
+                            counts.data_ptr(), st)
+    torch.cuda.synchronize()
+    n_tab = min(n, args.ref_table_genomes)
+    out["_table_sample"] = (table[:n_tab].cpu().numpy().view(np.uint64), counts[:n_tab].cpu().numpy().view(np.uint32))
+
+    def time_k2(tab, cnt, nn, mode, steps, warm):
+        cand_cap = max(1 << 20, 64 * nn)
+        d_cand = torch.empty((cand_cap, 4), dtype=torch.int32, device=dev)
+        d_ncand = torch.zeros(1, dtype=torch.int64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ms, b_ms, m_ms = [], [], []
+        for it in range(warm + steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            gb.prefilter_enqueue(tab.data_ptr(), cnt.data_ptr(), nn, S, K, MIN_ANI, 0, 1, mode, st, d_cand.data_ptr(),
+                                 cand_cap, d_ncand.data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it >= warm:
+                ms.append(e0.elapsed_time(e1))
+                b, m = gb.prefilter_last_timing()
+                b_ms.append(b); m_ms.append(m)
+        return float(np.mean(ms)), float(np.mean(b_ms)), float(np.mean(m_ms)), int(d_ncand.item())
+
+    if not args.no_prefilter_record:
+        ms, b, m, ncand = time_k2(table, counts, n, 0, 10, 3)
+        P = n * (n - 1) // 2
+        out["prefilter_only"] = {"workload": f"K2 alone on the resident {n} x {S} sketch table (BASELINE.json configs[1] kernel at this N), L2 flushed",
+                                 "value": P / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "build_kernels_ms": b,
+                                 "join_kernel_ms": m, "candidates": ncand}
+        # ANI lookup of sampled hits for the CPU check (host-buffer prefilter + K3 on a slice of genomes)
+    try:
+        idx = gb.AniIndex()
+        n_s = min(n, 200)
+        idx.add_packed_device(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), base_off[: n_s + 1], lengths[:n_s], st)
+        prs = np.array([(a, b) for f in range(n_s // 10) for a in range(10 * f, 10 * f + 10) for b in range(a + 1, 10 * f + 10)], np.uint32)
+        res = idx.pairs(prs, MIN_AF)
+        out["_ani_lookup"] = {(int(a), int(b)): float(v) for (a, b), v in zip(prs, res["ani"])}
+        idx.close()
+    except Exception as e:  # the check is optional; the headline does not depend on it
+        out["_ani_lookup"] = None
+        out["ani_lookup_error"] = str(e)
+
+    if not args.no_dense:
+        nd = args.dense_genomes
+        lay = gb.synth_layout(nd, L)
+        s2 = torch.empty(lay["seq2_words"], dtype=torch.int32, device=dev)
+        v2 = torch.empty(lay["valid_words"], dtype=torch.int32, device=dev)
+        o2 = torch.empty(nd + 1, dtype=torch.int64, device=dev)
+        gb.synth_packed_device_ex(SEED + 1, 0, nd, L, nd, 2, s2.data_ptr(), v2.data_ptr(), o2.data_ptr(), st)
+        torch.cuda.synchronize()
+        bo = np.arange(nd + 1, dtype=np.uint64) * np.uint64(lay["padded"])
+        ln = np.full(nd, L, np.uint64)
+        t2 = torch.empty((nd, S), dtype=torch.int64, device=dev)
+        c2 = torch.empty(nd, dtype=torch.int32, device=dev)
+        gb.sketch_packed_device(s2.data_ptr(), v2.data_ptr(), o2.data_ptr(), nd, K, S, 0, t2.data_ptr(), c2.data_ptr(), st)
+        torch.cuda.synchronize()
+        ms0, b0, m0, nc0 = time_k2(t2, c2, nd, 0, 5, 2)
+        ms1, b1, m1, nc1 = time_k2(t2, c2, nd, 1, 3, 1)
+        P = nd * (nd - 1) // 2
+        t0 = time.perf_counter()
+        cl, info = gb.cluster_packed(s2.data_ptr(), v2.data_ptr(), bo, ln, precluster_ani=MIN_ANI, ani=ANI_PCT,
+                                     min_aligned_fraction=MIN_AF, device=True, d_base_off=o2.data_ptr())
+        t_full = time.perf_counter() - t0
+        out["dense"] = {"workload": f"ONE clade: {nd} genomes x {L} bp derived from one founder at 0..2.5 % substitutions "
+                                    "(every pair related; every block pair of the join is tie-dense)",
+                        "pairs": P, "join_mode_ms": ms0, "join_kernel_ms": m0, "pairwise_mode_ms": ms1,
+                        "prefilter_pairs_per_s_join": P / (ms0 * 1e-3), "prefilter_pairs_per_s_pairwise": P / (ms1 * 1e-3),
+                        "candidates_join": nc0, "candidates_pairwise": nc1, "modes_agree": nc0 == nc1,
+                        "two_stage_s": t_full, "two_stage_pairs_per_s": P / t_full, "prefilter_hits": int(info["n_precluster_hits"]),
+                        "phases_ms": {k: info[k] for k in ("sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms")},
+                        "clusters": len(cl)}
+        del s2, v2, o2, t2, c2
+
+    if not args.no_ingest:
         import tempfile
         rng = np.random.default_rng(SEED)
         n_files, glen, width = 48, 2_000_000, 80
         acgt = np.frombuffer(b"ACGT", np.uint8)
         files = []
+        fam_base = None
         for g in range(n_files):
-            seq = acgt[rng.integers(0, 4, size=glen)].reshape(-1, width)
+            if g % 4 == 0:
+                fam_base = acgt[rng.integers(0, 4, size=glen)]
+                seq = fam_base
+            else:
+                seq = fam_base.copy()
+                hit = rng.uniform(size=glen) < 0.01 * (g % 4)
+                seq[hit] = acgt[rng.integers(0, 4, size=int(hit.sum()))]
+            seq = seq.reshape(-1, width)
             body = np.concatenate([seq, np.full((seq.shape[0], 1), 10, np.uint8)], axis=1).tobytes()
             files.append(b">genome_%d synthetic\n" % g + body)
         raw_bytes = sum(len(f) for f in files)
-        gb.decode_fasta_device(files, unpack=False)  # warm-up: sizes the decoder's device buffers
+        gb.decode_fasta_device(files, unpack=False)
         meta, dec_ms = gb.decode_fasta_device(files, unpack=False)
         with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
             paths = []
@@ -446,105 +594,17 @@ def main():
                 paths.append(os.path.join(td, f"g{g}.fna"))
                 with open(paths[-1], "wb") as f:
                     f.write(data)
-            times = {}
-            tables = {}
-            for mode in (1, 0, 1, 0):
-                prev = gb.device_ingest(mode)
-                t0 = time.perf_counter()
-                tables[mode] = gb.sketch_files(paths, K, S)
-                times[mode] = time.perf_counter() - t0  # the second round of each mode is kept (warm)
-                gb.device_ingest(prev)
-            same = np.array_equal(tables[1][0], tables[0][0]) and np.array_equal(tables[1][1], tables[0][1])
-        ingest = {"workload": f"{n_files} synthetic FASTA files x {glen} bp, {width}-column lines ({raw_bytes} bytes)",
-                  "k0_decode_ms": dec_ms, "k0_decode_gbytes_per_s": raw_bytes / (dec_ms * 1e-3) / 1e9,
-                  "k0_note": "upload from pinned staging + 3 kernels + 2 host round trips of per-chunk summaries",
-                  "sketch_files_s_device_ingest": times[1], "sketch_files_s_host_packer": times[0],
-                  "host_threads": os.cpu_count(), "tables_identical": bool(same),
-                  "all_bases_ok": all(m["n_bases"] == glen and m["n_ambiguous"] == 0 for m in meta)}
-
-    if rank == 0:
-        peak, peak_src = peaks()
-        kernel_names = {0: "prefilter_join_kernel", 1: "prefilter_tiled_kernel"}
-        pairs_per_launch = pairs / world
-        achieved = BYTES_PER_PAIR * pairs_per_launch / (main_ms * 1e-3) / 1e9
-        # bytes the join kernel itself has to read: each (rb, cb) item streams the 32-bit keys of two
-        # block lists of R*s entries (R = 128 sketches) once for R*R pairs (lo words / tags only on key ties)
-        own_bytes_per_pair = 2 * S * 4 / gb.ROW_BLOCK if args.mode == 0 else BYTES_PER_PAIR
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            import oracle
-            oracle.build()
-            tab = h_table.numpy().view(np.uint64)
-            cnt = h_counts.numpy().view(np.uint32)
-            rows = min(args.cpu_rows, n)
+            gb.cluster(paths, precluster_ani=MIN_ANI, ani=ANI_PCT, min_aligned_fraction=MIN_AF)
             t0 = time.perf_counter()
-            exp = oracle.prefilter(tab, cnt, K, MIN_ANI, row_begin=0, row_end=rows)
-            dt = time.perf_counter() - t0
-            sample_pairs = sum(n - 1 - i for i in range(rows))
-            # the same rows from the GPU result must agree bit-exactly (the oracle as checker)
-            got = res[res["i"] < rows]
-            ok = len(got) == len(exp) and all(
-                np.array_equal(got[f], exp[f]) for f in ("i", "j", "common", "total")) and np.array_equal(
-                got["ani"].view(np.uint32), exp["ani"].view(np.uint32))
-            t1 = time.perf_counter()
-            oracle.prefilter_count_mt(tab, cnt, K, MIN_ANI, row_begin=0, row_end=rows)
-            dt_mt = time.perf_counter() - t1
-            cpu = {"value": sample_pairs / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
-                   "sample": f"rows 0..{rows} of the same {n}-genome table ({sample_pairs} pairs), serial "
-                             "loop as src/finch.rs:75-95 (the reference's pair loop is single-threaded)",
-                   "all_cores_value": sample_pairs / dt_mt, "all_cores": os.cpu_count(),
-                   "gpu_matches_oracle_on_sample": bool(ok)}
-        line = {
-            "metric": "genome-pairs/sec (finch prefilter, s=1000)", "value": value, "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": {"workload": f"{n} synthetic {L} bp genomes (families of 10, seed {SEED}), s={S} k={K} "
-                                   f"finch prefilter only, min_ani {MIN_ANI} (BASELINE.json configs[1]"
-                                   f"{' scaled by sqrt(G) genomes' if world > 1 else ''})",
-                       "pairs_per_step": pairs, "mode": args.mode,
-                       "l2": "flushed between timed iterations (256 MiB write)",
-                       "sharding": "boustrophedon row blocks of 128; inside the step: 8-byte all-reduce (largest hash), "
-                                   "NCCL all-gather of the sketch table overlapped with the per-rank build of its own "
-                                   "block lists, NCCL all-gather of the lists, join of the rank's shard"
-                                   if world > 1 else "single GPU"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "passing_pairs": int(n_pass_t.item()), "ms": 1e3 * float(e2e_t.item()),
-                    "pipeline": f"upload in {gb.prefilter_stream_chunks()} slices on a copy stream, block lists of a slice "
-                                "built as it lands, join after the last; survivors land in mapped pinned memory and "
-                                "their f64 finish runs on the host while the kernels run" if world == 1 else "per-rank slice upload, NVLink all-gathers",
-                    "host_ms": e2e_host, "single_upload": e2e_single_upload},
-            "gpu_launches": launches,
-            "host_enqueue_ms_per_step": float(np.median(host_enqueue_ms[: args.steps])) if host_enqueue_ms else None,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(kernel_names[args.mode], n, world),
-                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/ncu_traffic.json)",
-                         "kernel": kernel_names[args.mode],
-                         "kernel_ms": main_ms, "build_kernels_ms": build_ms,
-                         "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "peak_source": peak_src,
-                         "kernel_own_bytes_per_pair": own_bytes_per_pair,
-                         "kernel_own_gbs": own_bytes_per_pair * pairs_per_launch / (main_ms * 1e-3) / 1e9,
-                         "note": "achieved uses the reference algorithm's 2*s*8 B/pair (SURVEY.md 8d). The join "
-                                 "kernel computes every pair's exact intersection from ONE merge of two 128-sketch "
-                                 "block lists per 128x128 pairs, so it reads 2*s*4/128 B/pair (kernel_own_*) and the "
-                                 "fraction of the 16 kB/pair roofline exceeds 1 by design (DESIGN.md K2)"
-                                 if args.mode == 0 else
-                                 "pairwise kernel re-uses staged sketches from shared memory (16 kB/pair is read "
-                                 "from shared memory, not HBM)"},
-            "other_mode": other,
-            "two_stage": two_stage,
-            "ingest": ingest,
-            "cpu_baseline": cpu,
-            "candidates": n_cand,
-            "sketch": {"genomes_per_s": n_local / (sketch_ms * 1e-3) if sketch_ms else None,
-                       "gbases_per_s": n_local * L / (sketch_ms * 1e-3) / 1e9 if sketch_ms else None,
-                       "ms": sketch_ms, "synth_ms": synth_ms, "genomes_per_rank": n_local},
-        }
-        sys.stdout.flush()
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+            cl, info = gb.cluster(paths, precluster_ani=MIN_ANI, ani=ANI_PCT, min_aligned_fraction=MIN_AF)
+            t_files = time.perf_counter() - t0
+        out["ingest"] = {"workload": f"{n_files} synthetic FASTA files x {glen} bp, {width}-column lines ({raw_bytes} bytes), families of 4",
+                         "k0_decode_ms": dec_ms, "k0_decode_gbytes_per_s": raw_bytes / (dec_ms * 1e-3) / 1e9,
+                         "cluster_files_s": t_files, "cluster_files_fasta_gbytes_per_s": raw_bytes / t_files / 1e9,
+                         "cluster_files_phases_ms": {k: info[k] for k in ("ingest_ms", "prefilter_ms", "ani_ms", "engine_ms", "total_ms")},
+                         "clusters": len(cl), "prefilter_hits": int(info["n_precluster_hits"]),
+                         "all_bases_ok": all(m["n_bases"] == glen and m["n_ambiguous"] == 0 for m in meta)}
+    return out
 
 
 if __name__ == "__main__":

@@ -38,7 +38,9 @@ class AniResult(ctypes.Structure):
 
 class ClusterStats(ctypes.Structure):
     _fields_ = [("n_precluster_hits", ctypes.c_uint64), ("n_ani_pairs", ctypes.c_uint64),
-                ("ani_chain_ms", ctypes.c_float)]
+                ("ani_chain_ms", ctypes.c_float), ("ingest_ms", ctypes.c_float), ("sketch_ms", ctypes.c_float),
+                ("index_ms", ctypes.c_float), ("prefilter_ms", ctypes.c_float), ("ani_ms", ctypes.c_float),
+                ("engine_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
 
 
 ANI_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
@@ -122,6 +124,15 @@ _SIGNATURES = {
     "galah_b200_cluster_files": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                                 ctypes.c_int, ctypes.c_int, ctypes.POINTER(Clusters),
                                                 ctypes.POINTER(ClusterStats)]),
+    "galah_b200_cluster_packed": (ctypes.c_int, [vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
+                                                 ctypes.c_float, ctypes.c_int, ctypes.POINTER(Clusters),
+                                                 ctypes.POINTER(ClusterStats)]),
+    "galah_b200_cluster_packed_device": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
+                                                        ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                        ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),
+    "galah_b200_ingest_packed": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, f32p]),
+    "galah_b200_ani_index_export_tables": (ctypes.c_int, [vp, vp, u64p, u64p]),
+    "galah_b200_ani_index_attach_peer": (ctypes.c_int, [vp, vp, u64p, u64p, ctypes.c_size_t, u32p]),
     "galah_b200_skani_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_int, pairpp, sizep, sizep]),
     "galah_b200_skani_distances_packed_device": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
@@ -140,6 +151,9 @@ _SIGNATURES = {
     "galah_b200_genome_stats": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_int, vp]),
     "galah_b200_synth_packed_device": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
                                                       ctypes.c_uint64, vp, vp, vp, vp]),
+    "galah_b200_synth_packed_device_ex": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t,
+                                                         ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp, vp]),
+    "galah_b200_stream": (ctypes.c_void_p, []),
 }
 
 

@@ -278,6 +278,38 @@ class AniIndex:
                                              out.ctypes.data_as(ctypes.POINTER(_native.AniResult))))
         return out
 
+    def ingest_packed(self, seq2, valid, base_off, lengths, d_hashes, d_counts, device=False, d_base_off=0):
+        """Packed genomes -> K1 sketch rows in the device table (d_hashes / d_counts: device pointers,
+        stride 1000) + this index.  device=False: seq2 / valid are host addresses (uploaded in batches
+        behind the kernels); True: resident arrays (d_base_off = device copy of base_off).
+        Returns (K1 device ms, index-build device ms)."""
+        base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+        ms = (ctypes.c_float * 2)()
+        check(lib().galah_b200_ingest_packed(int(seq2), int(valid), int(d_base_off), base_off.ctypes.data_as(_native.u64p),
+                                             lengths.ctypes.data_as(_native.u64p), len(lengths), int(bool(device)),
+                                             int(d_hashes), int(d_counts), self._h, ms))
+        return float(ms[0]), float(ms[1])
+
+    def export_tables(self):
+        """(64-byte CUDA IPC handle, table_off uint64[n+1], total_len uint64[n]) of this index's hash tables."""
+        n = len(self)
+        handle = (ctypes.c_uint8 * 64)()
+        to = np.zeros(n + 1, np.uint64); tl = np.zeros(max(n, 1), np.uint64)
+        check(lib().galah_b200_ani_index_export_tables(self._h, handle, to.ctypes.data_as(_native.u64p),
+                                                       tl.ctypes.data_as(_native.u64p)))
+        return bytes(handle), to, tl[:n]
+
+    def attach_peer(self, handle, table_off, total_len):
+        """Maps a peer process's hash tables (export_tables of ITS index); returns the id of its first
+        genome in this index's numbering (usable as the reference of a pair only)."""
+        table_off = np.ascontiguousarray(table_off, np.uint64); total_len = np.ascontiguousarray(total_len, np.uint64)
+        h = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        first = ctypes.c_uint32(0)
+        check(lib().galah_b200_ani_index_attach_peer(self._h, h, table_off.ctypes.data_as(_native.u64p),
+                                                     total_len.ctypes.data_as(_native.u64p), len(total_len),
+                                                     ctypes.byref(first)))
+        return int(first.value)
+
     def last_timing(self):
         b, c = ctypes.c_float(0), ctypes.c_float(0)
         check(lib().galah_b200_ani_last_timing(self._h, ctypes.byref(b), ctypes.byref(c)))
@@ -358,8 +390,36 @@ def cluster(genomes, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0, sm
                                          ctypes.c_float(ani), ctypes.c_float(min_aligned_fraction),
                                          int(bool(small_genomes)), threads, ctypes.byref(res), ctypes.byref(stats)))
     clusters, info = _take_clusters(res)
-    info.update(n_precluster_hits=int(stats.n_precluster_hits), n_ani_pairs=int(stats.n_ani_pairs),
-                ani_chain_ms=float(stats.ani_chain_ms))
+    info.update(_stats_dict(stats))
+    return clusters, info
+
+
+def _stats_dict(stats):
+    d = {"n_precluster_hits": int(stats.n_precluster_hits), "n_ani_pairs": int(stats.n_ani_pairs)}
+    for f in ("ani_chain_ms", "ingest_ms", "sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms", "total_ms"):
+        d[f] = float(getattr(stats, f))
+    return d
+
+
+def cluster_packed(seq2, valid, base_off, lengths, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0,
+                   small_genomes=False, device=False, d_base_off=None):
+    """cluster() on genomes that are already packed (K1 / K3 layout, one contig per genome).
+    device=False: seq2 / valid are host arrays (numpy uint32 or integer addresses of pinned buffers),
+    uploaded in batches behind the kernels of the previous batch.  device=True: seq2 / valid /
+    d_base_off are device pointers (ints).  base_off / lengths: host uint64 arrays."""
+    base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+    common = (base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p), len(lengths),
+              ctypes.c_float(precluster_ani), ctypes.c_float(ani), ctypes.c_float(min_aligned_fraction),
+              int(bool(small_genomes)), ctypes.byref(res), ctypes.byref(stats))
+    if device:
+        check(lib().galah_b200_cluster_packed_device(ptr(seq2), ptr(valid), int(d_base_off), *common))
+    else:
+        check(lib().galah_b200_cluster_packed(ptr(seq2), ptr(valid), *common))
+    clusters, info = _take_clusters(res)
+    info.update(_stats_dict(stats))
     return clusters, info
 
 
@@ -501,6 +561,16 @@ def synth_layout(n, length):
     padded = (length + 127) // 128 * 128
     return {"seq2_words": n * padded // 16 + 4, "valid_words": n * padded // 32 + 4,
             "base_off": n + 1, "padded": padded}
+
+
+def stream():
+    """The CUDA stream (integer handle) the library enqueues its work on."""
+    return int(lib().galah_b200_stream() or 0)
+
+
+def synth_packed_device_ex(seed, index_begin, n, length, family_size, rate_shift, d_seq2, d_valid, d_base_off, stream=0):
+    check(lib().galah_b200_synth_packed_device_ex(seed, index_begin, n, length, family_size, rate_shift, d_seq2,
+                                                  d_valid, d_base_off, stream))
 
 
 def synth_packed_device(seed, index_begin, n, length, d_seq2, d_valid, d_base_off, stream=0):

@@ -354,6 +354,7 @@ struct IngestSinks {
     bool sketch = false;
     int k = 21; uint32_t s = 1000; uint64_t seed = 0;
     uint64_t *hashes = nullptr; uint32_t *counts = nullptr;  // host rows, stride s
+    uint64_t *d_hashes = nullptr; uint32_t *d_counts = nullptr;  // or DEVICE rows, stride s: no host round trip
     AniIndex *ani = nullptr;
     // FracMinHash marker sketches (k = 21, density 1/c_marker): one ascending hash list per unit
     MarkerTable *markers = nullptr;
@@ -375,7 +376,13 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
                     const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
                     const std::vector<uint32_t> &cs, const std::vector<uint32_t> &cl, uint64_t longest,
                     size_t unit_first, size_t files_done) -> int {
-        if (sinks.sketch) {
+        if (sinks.sketch && sinks.d_hashes) {
+            // K1 writes the rows where K2 will read them (the table never leaves the device)
+            int rc = sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, sinks.k, sinks.s, sinks.seed,
+                                    sinks.d_hashes + unit_first * (size_t)sinks.s, sinks.d_counts + unit_first,
+                                    sinks.s, st);
+            if (rc) return rc;
+        } else if (sinks.sketch) {
             DevBuf<uint64_t> d_hashes;
             DevBuf<uint32_t> d_counts;
             if (d_hashes.alloc(nb * (size_t)sinks.s) || d_counts.alloc(nb)) return GALAH_B200_ERR_CUDA;
@@ -1085,6 +1092,39 @@ int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t 
     return galah_b200_cluster_from_distances(n_genomes, hits, n_hits, 0, ani_threshold, ani_table_lookup, &table, out);
 }
 
+// Stages 2 + 3 of the whole path once the sketch table (device) and the K3 index are in place:
+// K2 on the resident table -> f64 finish -> K3 on every hit -> greedy engine.  Caller holds g_mu.
+static int cluster_from_resident(const uint64_t *d_table, const uint32_t *d_counts, size_t n, AniIndex &index,
+                                 float precluster_min_ani, float ani_threshold_pct, float min_af_pct,
+                                 galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    const uint32_t s = 1000;  // FinchPreclusterer{num_kmers: 1000, kmer_length: 21}, cluster_argument_parsing.rs:1301-1302
+    const uint8_t k = 21;
+    cudaStream_t st = g_ctx.stream;
+    const double t0 = now_ms();
+    galah_b200_pair_t *hits = nullptr;
+    size_t n_hits = 0;
+    if (int rc = run_prefilter(d_table, d_counts, n, s, k, precluster_min_ani, 0, 1, st, &hits, &n_hits)) return rc;
+    struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
+    const double t1 = now_ms();
+    // stage 2 for every precluster hit (a superset of what the reference's find_any evaluates;
+    // the greedy decisions only ever read values of hit pairs, so the clusters are the same);
+    // query = the lower index: galah passes the representative first (src/clusterer.rs:262-296)
+    std::vector<uint32_t> pairs(2 * n_hits);
+    for (size_t x = 0; x < n_hits; x++) { pairs[2 * x] = hits[x].i; pairs[2 * x + 1] = hits[x].j; }
+    std::vector<AniPairResult> res(n_hits);
+    if (int rc = index.pairs(pairs.data(), n_hits, min_af_pct, false, res.data(), st)) return rc;
+    const double t2 = now_ms();
+    AniTable table{hits, n_hits, n_hits ? &res[0].ani : nullptr, sizeof(AniPairResult)};
+    int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
+    if (stats) {
+        stats->n_precluster_hits = n_hits;
+        stats->n_ani_pairs = n_hits;
+        stats->ani_chain_ms = index.last_chain_ms;
+        stats->prefilter_ms = (float)(t1 - t0); stats->ani_ms = (float)(t2 - t1); stats->engine_ms = (float)(now_ms() - t2);
+    }
+    return rc;
+}
+
 int galah_b200_cluster_files(const char *const *paths, size_t n, float precluster_min_ani, float ani_threshold_pct,
                              float min_af_pct, int small_genomes, int host_threads,
                              galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
@@ -1093,41 +1133,201 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
     if (stats) memset(stats, 0, sizeof(*stats));
     // SkaniClusterer::initialise (src/skani.rs:696-698) asserts a percentage
     if (!(ani_threshold_pct > 1.0f)) { set_error("assertion failed: self.threshold > 1.0"); return GALAH_B200_ERR_UNSUPPORTED; }
-    const uint32_t s = 1000;  // FinchPreclusterer{num_kmers: 1000, kmer_length: 21}, cluster_argument_parsing.rs:1301-1302
-    const uint8_t k = 21;
-    std::vector<uint64_t> hashes((size_t)n * s);
-    std::vector<uint32_t> counts(n);
-    galah_b200_ani_index_t *idx = nullptr;
-    if (int rc = galah_b200_ani_index_create(small_genomes, &idx)) return rc;
-    struct Guard { galah_b200_ani_index_t *i; ~Guard() { galah_b200_ani_index_free(i); } } guard{idx};
-    {
-        std::lock_guard<std::mutex> lock(g_mu);
-        if (int rc = require_ctx()) return rc;
-        IngestSinks sinks;
-        sinks.sketch = true; sinks.k = k; sinks.s = s; sinks.seed = 0; sinks.hashes = hashes.data();
-        sinks.counts = counts.data(); sinks.ani = &idx->impl;
-        if (int rc = ingest_files(paths, n, host_threads, sinks)) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    const double t_begin = now_ms();
+    const uint32_t s = 1000;
+    AniIndex index(small_genomes ? 30u : 125u);
+    // the sketch table is written by K1 where K2 reads it: it never visits the host
+    if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, std::max<size_t>(n, 1) * s) ||
+        ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
+        return GALAH_B200_ERR_CUDA;
+    IngestSinks sinks;
+    sinks.sketch = true; sinks.k = 21; sinks.s = s; sinks.seed = 0;
+    sinks.d_hashes = g_ctx.d_table; sinks.d_counts = g_ctx.d_counts; sinks.ani = &index;
+    if (int rc = ingest_files(paths, n, host_threads, sinks)) return rc;
+    const double t_ingest = now_ms();
+    int rc = cluster_from_resident(g_ctx.d_table, g_ctx.d_counts, n, index, precluster_min_ani, ani_threshold_pct,
+                                   min_af_pct, out, stats);
+    if (stats) { stats->ingest_ms = (float)(t_ingest - t_begin); stats->total_ms = (float)(now_ms() - t_begin); }
+    return rc;
+}
+
+// Genomes that are already PACKED (K1 / K3 layout, one contig per genome) -> K1 sketch rows in the
+// device table d_table / d_counts (stride 1000) and the K3 index.  `device`: the arrays are resident
+// in HBM (d_base_off = device copy of base_off); else host arrays, uploaded in batches of ~1 G
+// bases on the copy stream while the previous batch is sketched and indexed.  Caller holds g_mu.
+static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off_or_null,
+                         const uint64_t *base_off, const uint64_t *lengths, size_t n, bool device, uint64_t *d_table,
+                         uint32_t *d_counts, AniIndex &index, float *sketch_ms_out, float *index_ms_out) {
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("packed genomes: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
+    const uint32_t s = 1000;
+    cudaStream_t st = g_ctx.stream;
+    // batches of about 1 G bases (375 MB packed): bounds the K1 / K3 scratch, and is the upload unit
+    const uint64_t kBatchBases = 1ull << 30;
+    std::vector<size_t> cut{0};
+    while (cut.back() < n) {
+        size_t b1 = cut.back() + 1;
+        while (b1 < n && base_off[b1 + 1] - base_off[cut.back()] <= kBatchBases) b1++;
+        cut.push_back(b1);
     }
-    galah_b200_pair_t *hits = nullptr;
-    size_t n_hits = 0;
-    if (int rc = galah_b200_prefilter(hashes.data(), counts.data(), n, s, k, precluster_min_ani, &hits, &n_hits)) return rc;
-    struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
-    // stage 2 for every precluster hit (a superset of what the reference's find_any evaluates;
-    // the greedy decisions only ever read values of hit pairs, so the clusters are the same)
-    std::vector<uint32_t> pairs(2 * n_hits);
-    for (size_t x = 0; x < n_hits; x++) { pairs[2 * x] = hits[x].i; pairs[2 * x + 1] = hits[x].j; }
-    std::vector<galah_b200_ani_result_t> res(n_hits);
-    if (int rc = galah_b200_ani_pairs(idx, pairs.data(), n_hits, min_af_pct, 0, res.data())) return rc;
-    AniTable table{hits, n_hits, n_hits ? &res[0].ani : nullptr, sizeof(galah_b200_ani_result_t)};
-    int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
+    const size_t n_batches = cut.size() - 1;
+    // host input: two staging slots on the device, filled on the copy stream
+    struct Slot { uint32_t *seq2 = nullptr, *valid = nullptr; uint64_t *off = nullptr; cudaEvent_t landed = nullptr, freed = nullptr; } slot[2];
+    struct SlotGuard { Slot *s; ~SlotGuard() { for (int x = 0; x < 2; x++) { cudaFree(s[x].seq2); cudaFree(s[x].valid); cudaFree(s[x].off);
+                       if (s[x].landed) cudaEventDestroy(s[x].landed); if (s[x].freed) cudaEventDestroy(s[x].freed); } } } slot_guard{slot};
+    uint64_t max_bases = 0; size_t max_n = 0;
+    for (size_t b = 0; b < n_batches; b++) {
+        max_bases = std::max(max_bases, base_off[cut[b + 1]] - base_off[cut[b]]);
+        max_n = std::max(max_n, cut[b + 1] - cut[b]);
+    }
+    if (!device) {
+        if (!g_ctx.copy_stream) GB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
+        for (int x = 0; x < 2; x++) {
+            GB_CUDA(cudaMalloc(&slot[x].seq2, (max_bases / 16 + 8) * 4));
+            GB_CUDA(cudaMalloc(&slot[x].valid, (max_bases / 32 + 8) * 4));
+            GB_CUDA(cudaMalloc(&slot[x].off, (max_n + 1) * 8));
+            GB_CUDA(cudaEventCreateWithFlags(&slot[x].landed, cudaEventDisableTiming));
+            GB_CUDA(cudaEventCreateWithFlags(&slot[x].freed, cudaEventDisableTiming));
+        }
+    }
+    std::vector<std::vector<uint64_t>> rel(n_batches);
+    auto upload = [&](size_t b) -> int {
+        Slot &sl = slot[b & 1];
+        const size_t g0 = cut[b], nb = cut[b + 1] - g0;
+        const uint64_t first = base_off[g0], total = base_off[g0 + nb] - first;
+        rel[b].resize(nb + 1);
+        for (size_t g = 0; g <= nb; g++) rel[b][g] = base_off[g0 + g] - first;
+        if (b >= 2) GB_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, sl.freed, 0));  // the slot's previous batch is consumed
+        GB_CUDA(cudaMemcpyAsync(sl.seq2, seq2 + first / 16, total / 16 * 4, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+        GB_CUDA(cudaMemcpyAsync(sl.valid, valid + first / 32, total / 32 * 4, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+        GB_CUDA(cudaMemcpyAsync(sl.off, rel[b].data(), (nb + 1) * 8, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+        GB_CUDA(cudaEventRecord(sl.landed, g_ctx.copy_stream));
+        return 0;
+    };
+    float sketch_ms = 0.f, index_ms = 0.f;
+    cudaEvent_t ev[3];
+    for (auto &e : ev) GB_CUDA(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int x = 0; x < 3; x++) cudaEventDestroy(e[x]); } } ev_guard{ev};
+    if (!device && n_batches) if (int rc = upload(0)) return rc;
+    for (size_t b = 0; b < n_batches; b++) {
+        const size_t g0 = cut[b], nb = cut[b + 1] - g0;
+        const uint32_t *b_seq2, *b_valid; const uint64_t *b_off;
+        std::vector<uint64_t> bo;
+        if (device) {
+            b_seq2 = seq2; b_valid = valid; b_off = d_base_off_or_null + g0;  // absolute offsets into the resident arrays
+            bo.assign(base_off + g0, base_off + g0 + nb + 1);
+        } else {
+            if (b + 1 < n_batches) if (int rc = upload(b + 1)) return rc;  // next batch crosses PCIe behind this one's kernels
+            GB_CUDA(cudaStreamWaitEvent(st, slot[b & 1].landed, 0));
+            b_seq2 = slot[b & 1].seq2; b_valid = slot[b & 1].valid; b_off = slot[b & 1].off;
+            bo = rel[b];
+        }
+        std::vector<uint64_t> co(nb + 1);
+        std::vector<uint32_t> cs(nb, 0), cl(nb);
+        for (size_t g = 0; g < nb; g++) { co[g] = g; cl[g] = (uint32_t)lengths[g0 + g]; }
+        co[nb] = nb;
+        GB_CUDA(cudaEventRecord(ev[0], st));
+        if (int rc = sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, s, 0, d_table + g0 * (size_t)s,
+                                    d_counts + g0, s, st))
+            return rc;
+        GB_CUDA(cudaEventRecord(ev[1], st));
+        if (int rc = index.add_packed_device(b_seq2, b_valid, b_off, nb, bo, co, cs, cl, st)) return rc;
+        if (b == 0 && n_batches > 1) if (int rc = index.reserve_for(n, st)) return rc;
+        GB_CUDA(cudaEventRecord(ev[2], st));
+        if (!device) GB_CUDA(cudaEventRecord(slot[b & 1].freed, st));
+        GB_CUDA(cudaEventSynchronize(ev[2]));
+        float a = 0.f, c = 0.f;
+        GB_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        GB_CUDA(cudaEventElapsedTime(&c, ev[1], ev[2]));
+        sketch_ms += a; index_ms += c;
+    }
+    if (sketch_ms_out) *sketch_ms_out = sketch_ms;
+    if (index_ms_out) *index_ms_out = index_ms;
+    return 0;
+}
+
+static int cluster_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off_or_null,
+                          const uint64_t *base_off, const uint64_t *lengths, size_t n, bool device,
+                          float precluster_min_ani, float ani_threshold_pct, float min_af_pct, int small_genomes,
+                          galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (!out) { set_error("cluster_packed: out is NULL"); return GALAH_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!(ani_threshold_pct > 1.0f)) { set_error("assertion failed: self.threshold > 1.0"); return GALAH_B200_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    const double t_begin = now_ms();
+    AniIndex index(small_genomes ? 30u : 125u);
+    if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, std::max<size_t>(n, 1) * 1000) ||
+        ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
+        return GALAH_B200_ERR_CUDA;
+    float sketch_ms = 0.f, index_ms = 0.f;
+    if (int rc = ingest_packed(seq2, valid, d_base_off_or_null, base_off, lengths, n, device, g_ctx.d_table,
+                               g_ctx.d_counts, index, &sketch_ms, &index_ms))
+        return rc;
+    const double t_ingest = now_ms();
+    int rc = cluster_from_resident(g_ctx.d_table, g_ctx.d_counts, n, index, precluster_min_ani, ani_threshold_pct,
+                                   min_af_pct, out, stats);
     if (stats) {
-        stats->n_precluster_hits = n_hits;
-        stats->n_ani_pairs = n_hits;
-        float b = 0, c = 0;
-        galah_b200_ani_last_timing(idx, &b, &c);
-        stats->ani_chain_ms = c;
+        stats->ingest_ms = (float)(t_ingest - t_begin); stats->total_ms = (float)(now_ms() - t_begin);
+        stats->sketch_ms = sketch_ms; stats->index_ms = index_ms;
     }
     return rc;
+}
+
+int galah_b200_ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,
+                             const uint64_t *base_off, const uint64_t *lengths, size_t n, int device,
+                             uint64_t *d_hashes, uint32_t *d_counts, galah_b200_ani_index_t *idx, float *ms2) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx || !d_hashes || !d_counts) { set_error("ingest_packed: NULL argument"); return GALAH_B200_ERR_ARG; }
+    float a = 0.f, b = 0.f;
+    int rc = ingest_packed(seq2, valid, d_base_off, base_off, lengths, n, device != 0, d_hashes, d_counts, idx->impl, &a, &b);
+    if (ms2) { ms2[0] = a; ms2[1] = b; }
+    return rc;
+}
+
+int galah_b200_ani_index_export_tables(const galah_b200_ani_index_t *idx, uint8_t handle[64], uint64_t *table_off,
+                                       uint64_t *total_len) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    std::vector<uint64_t> to, tl;
+    if (int rc = idx->impl.export_tables(&h, to, tl)) return rc;
+    memcpy(handle, &h, 64);
+    memcpy(table_off, to.data(), to.size() * 8);
+    memcpy(total_len, tl.data(), tl.size() * 8);
+    return 0;
+}
+
+int galah_b200_ani_index_attach_peer(galah_b200_ani_index_t *idx, const uint8_t handle[64], const uint64_t *table_off,
+                                     const uint64_t *total_len, size_t n_genomes, uint32_t *first_id) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx || !first_id) { set_error("ani index: NULL argument"); return GALAH_B200_ERR_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return idx->impl.attach_peer(h, table_off, total_len, n_genomes, first_id);
+}
+
+int galah_b200_cluster_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
+                                     const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                     float precluster_min_ani, float ani_threshold_pct, float min_af_pct,
+                                     int small_genomes, galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    return cluster_packed(d_seq2, d_valid, d_base_off, base_off, lengths, n, true, precluster_min_ani,
+                          ani_threshold_pct, min_af_pct, small_genomes, out, stats);
+}
+
+int galah_b200_cluster_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                              const uint64_t *lengths, size_t n, float precluster_min_ani, float ani_threshold_pct,
+                              float min_af_pct, int small_genomes, galah_b200_clusters_t *out,
+                              galah_b200_cluster_stats_t *stats) {
+    return cluster_packed(seq2, valid, nullptr, base_off, lengths, n, false, precluster_min_ani, ani_threshold_pct,
+                          min_af_pct, small_genomes, out, stats);
 }
 
 int galah_b200_skani_distances(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
@@ -1321,5 +1521,16 @@ int galah_b200_synth_packed_device(uint64_t seed, uint64_t index_begin, size_t n
     cudaStream_t st = (cudaStream_t)stream;
     return synth_enqueue(seed, index_begin, n, length, d_seq2, d_valid, d_base_off, st);
 }
+
+int galah_b200_synth_packed_device_ex(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,
+                                      uint32_t family_size, uint32_t rate_shift, uint32_t *d_seq2,
+                                      uint32_t *d_valid, uint64_t *d_base_off, void *stream) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    return synth_enqueue(seed, index_begin, n, length, d_seq2, d_valid, d_base_off, (cudaStream_t)stream, family_size,
+                         rate_shift);
+}
+
+void *galah_b200_stream(void) { return (void *)g_ctx.stream; }
 
 }  // extern "C"

@@ -239,8 +239,9 @@ struct ChainParams {
     const uint32_t *pairs;  // (query, reference) genome ids
     const uint2 *kq;  // per seed: x = kmer << 1 | strand, y = spread position
     const uint32_t *cso;
-    const unsigned long long *table;
-    const uint64_t *seed_off, *cso_off, *table_off;
+    const unsigned long long *const *pair_table;  // per pair: the reference genome's hash table (local or peer-mapped)
+    const uint32_t *pair_mask;                    // per pair: its slot count - 1
+    const uint64_t *seed_off, *cso_off;
     const uint32_t *n_chunks;
     const uint32_t *unit_prefix;  // [n_pairs + 1] running sum of the query genomes' chunk counts
     uint32_t n_pairs, n_units;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     // no early exits: every lane of a warp stays in the lock-step walk (idle lanes walk 0 seeds)
     uint32_t pair = 0, x0 = 0, x1 = 0;
     const uint2 *qkq = p.kq;
-    const unsigned long long *table = p.table;
+    const unsigned long long *table = nullptr;
     uint32_t mask = 0;
     if (u < p.n_units) {
         uint32_t lo = 0, hi = p.n_pairs;  // last pair with unit_prefix[pair] <= u
@@ -272,13 +273,13 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
         }
         pair = lo;
         const uint32_t t = u - p.unit_prefix[pair];
-        const uint32_t q = p.pairs[2 * pair], r = p.pairs[2 * pair + 1];
+        const uint32_t q = p.pairs[2 * pair];
         const uint32_t *cso = p.cso + p.cso_off[q];
         x0 = cso[t]; x1 = cso[t + 1];
         if (x1 - x0 < (uint32_t)kAniMinAnchors) x1 = x0;
         qkq = p.kq + p.seed_off[q];
-        table = p.table + p.table_off[r];
-        mask = (uint32_t)(p.table_off[r + 1] - p.table_off[r]) - 1;
+        table = p.pair_table[pair];
+        mask = p.pair_mask[pair];
     }
 #define RING(slot, field) ring[((slot) * kRingFields + (field)) * kChainThreads + tid]
     uint32_t n_anchor = 0;
@@ -514,11 +515,36 @@ struct TmpBuf {
 struct AniScratch {
     TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix, overflow;
     TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
-    TmpBuf<unsigned long long> acc_fx, idtab;
+    TmpBuf<unsigned long long> acc_fx, idtab, pair_table;
+    TmpBuf<uint32_t> pair_mask;
     bool idtab_ready = false;
 };
 
+int AniIndex::export_tables(cudaIpcMemHandle_t *handle, std::vector<uint64_t> &table_off,
+                            std::vector<uint64_t> &total_len) const {
+    if (!d_table_.p) { set_error("ani index: nothing to export"); return 3; }
+    GB_CUDA(cudaIpcGetMemHandle(handle, d_table_.p));
+    table_off = table_off_;
+    total_len = total_len_;
+    return 0;
+}
+
+int AniIndex::attach_peer(const cudaIpcMemHandle_t &handle, const uint64_t *table_off, const uint64_t *total_len,
+                          size_t n, uint32_t *first_id) {
+    void *base = nullptr;
+    GB_CUDA(cudaIpcOpenMemHandle(&base, handle, cudaIpcMemLazyEnablePeerAccess));
+    PeerGroup pg;
+    pg.base = (const unsigned long long *)base;
+    pg.table_off.assign(table_off, table_off + n + 1);
+    peers_.push_back(std::move(pg));
+    *first_id = (uint32_t)size() + peer_first_.back();
+    peer_first_.push_back(peer_first_.back() + (uint32_t)n);
+    peer_total_len_.insert(peer_total_len_.end(), total_len, total_len + n);
+    return 0;
+}
+
 AniIndex::~AniIndex() {
+    for (auto &pg : peers_) cudaIpcCloseMemHandle((void *)pg.base);
     d_kq_.release(); d_cso_.release(); d_table_.release();
     d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
     for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);
@@ -667,9 +693,27 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
     if (n_pairs == 0) return 0;
     if (!ev_[0]) { GB_CUDA(cudaEventCreate(&ev_[0])); GB_CUDA(cudaEventCreate(&ev_[1])); }
     // the query is the pair's FIRST genome, as given (skani dist -q fasta1 -r fasta2, src/skani.rs:733-744)
-    for (size_t x = 0; x < n_pairs; x++)
-        if (pairs[2 * x] >= size() || pairs[2 * x + 1] >= size()) { set_error("ani pairs: genome index out of range"); return 3; }
+    // reference ids >= size() name genomes of attached peers (attach_peer)
+    const size_t n_local = size(), n_all = n_local + n_peer_genomes();
+    std::vector<unsigned long long> h_ptab(n_pairs);
+    std::vector<uint32_t> h_pmask(n_pairs);
+    for (size_t x = 0; x < n_pairs; x++) {
+        const uint32_t q = pairs[2 * x], r = pairs[2 * x + 1];
+        if (q >= n_local || r >= n_all) { set_error("ani pairs: genome index out of range (the query must be local)"); return 3; }
+        if (r < n_local) {
+            h_ptab[x] = (unsigned long long)(uintptr_t)(d_table_.p + table_off_[r]);
+            h_pmask[x] = (uint32_t)(table_off_[r + 1] - table_off_[r]) - 1;
+        } else {
+            const uint32_t pid = r - (uint32_t)n_local;
+            const size_t g = std::upper_bound(peer_first_.begin(), peer_first_.end(), pid) - peer_first_.begin() - 1;
+            const PeerGroup &pg = peers_[g];
+            const uint32_t l = pid - peer_first_[g];
+            h_ptab[x] = (unsigned long long)(uintptr_t)(pg.base + pg.table_off[l]);
+            h_pmask[x] = (uint32_t)(pg.table_off[l + 1] - pg.table_off[l]) - 1;
+        }
+    }
     if (!scratch_) scratch_ = new AniScratch();
+    if (scratch_->pair_table.upload(h_ptab, st) || scratch_->pair_mask.upload(h_pmask, st)) return 2;
     TmpBuf<uint32_t> &d_pairs = scratch_->pairs, &d_acc = scratch_->acc, &d_over = scratch_->overflow;
     TmpBuf<unsigned long long> &d_fx = scratch_->acc_fx, &d_idtab = scratch_->idtab;
     const uint32_t kOverflowCap = 1u << 16;
@@ -715,7 +759,9 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
             GB_CUDA(cudaMemcpyAsync(d_prefix.p, unit_prefix.data() + b0, (b1 - b0 + 1) * 4, cudaMemcpyHostToDevice, st));
             ChainParams p;
             p.pairs = d_pairs.p + 2 * b0; p.kq = d_kq_.p; p.cso = d_cso_.p;
-            p.table = d_table_.p; p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p; p.table_off = d_table_off_.p;
+            p.pair_table = reinterpret_cast<const unsigned long long *const *>(scratch_->pair_table.p) + b0;
+            p.pair_mask = scratch_->pair_mask.p + b0;
+            p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p;
             p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + (size_t)kAccWords * b0; p.acc_fx = d_fx.p + b0;
             p.idtab = d_idtab.p; p.overflow = d_over.p; p.overflow_cap = kOverflowCap;
             p.unit_prefix = d_prefix.p; p.n_pairs = (uint32_t)(b1 - b0); p.n_units = (uint32_t)units;
@@ -755,7 +801,9 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
         AniPairInts v;
         v.sum_fx = fx[x]; v.n_chunks = a[0]; v.cov_q = a[1]; v.cov_r = a[2]; v.sum_m = a[3];
         v.span_m = a[4]; v.span_n = a[5]; v.n_chains = a[6];
-        out[x] = ani_finish(v, total_len_[pairs[2 * x]], total_len_[pairs[2 * x + 1]], c_, individual_contigs, min_af_pct);
+        const uint32_t r = pairs[2 * x + 1];
+        const uint64_t len_r = r < n_local ? total_len_[r] : peer_total_len_[r - n_local];
+        out[x] = ani_finish(v, total_len_[pairs[2 * x]], len_r, c_, individual_contigs, min_af_pct);
     }
     return 0;
 }

@@ -73,6 +73,15 @@ public:
               cudaStream_t st);
     size_t size() const { return total_len_.size(); }
     uint32_t c() const { return c_; }
+    // ---- multi-GPU (one process per GPU): the hash tables of genomes indexed by a PEER process
+    // are read in place over NVLink through a CUDA IPC mapping of the peer's table array.
+    // export_tables: IPC handle of this index's table array + its per-genome slot offsets / lengths.
+    // attach_peer: maps a peer's array; its n genomes become usable as the REFERENCE of a pair
+    // under the ids first_id .. first_id + n - 1 (returned), never as the query.
+    int export_tables(cudaIpcMemHandle_t *handle, std::vector<uint64_t> &table_off, std::vector<uint64_t> &total_len) const;
+    int attach_peer(const cudaIpcMemHandle_t &handle, const uint64_t *table_off, const uint64_t *total_len, size_t n,
+                    uint32_t *first_id);
+    size_t n_peer_genomes() const { return peer_total_len_.size(); }
     // parity hooks
     int genome_info(size_t g, uint64_t *n_seeds, uint32_t *n_chunks, uint64_t *total_len) const;
     int genome_seeds(size_t g, uint32_t *ks, uint32_t *spread, uint32_t *chunk_of_seed, size_t cap,
@@ -92,6 +101,11 @@ private:
     DevVec<uint32_t> d_n_chunks_;
     cudaEvent_t ev_[2] = {nullptr, nullptr};
     AniScratch *scratch_ = nullptr;
+    // peer tables (attach_peer): group g covers peer ids [peer_first_[g], peer_first_[g + 1])
+    struct PeerGroup { const unsigned long long *base; std::vector<uint64_t> table_off; };
+    std::vector<PeerGroup> peers_;
+    std::vector<uint32_t> peer_first_{0};
+    std::vector<uint64_t> peer_total_len_;
 };
 
 // strtof(sprintf("%.2f", v)), computed exactly without the text for the values an ANI can take

@@ -33,6 +33,7 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
 
 // Synthetic genomes, generated directly in packed form on the device.
 int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length, uint32_t *d_seq2,
-                  uint32_t *d_valid, uint64_t *d_base_off, cudaStream_t stream);
+                  uint32_t *d_valid, uint64_t *d_base_off, cudaStream_t stream, uint32_t family_size = 10,
+                  uint32_t rate_shift = 0);
 
 }  // namespace gb200

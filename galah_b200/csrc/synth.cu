@@ -1,6 +1,7 @@
 // Synthetic genome generator: counter-based, so any genome can be regenerated
 // from (seed, index) -- the CPU oracle holds the same definition for parity checks.
-//   family f = index / 10, member m = index % 10, substitution rate {0,.5,1,2,3,4,5,6,8,10} %
+//   family f = index / F, member m = (index % F) % 10, substitution rate {0,.5,1,2,3,4,5,6,8,10} % >> rate_shift
+//   (F = 10, rate_shift = 0: the sparse benchmark families; F = thousands, rate_shift = 2: one dense clade)
 //   founder block b (32 bases, 2 bits each, LSB first) = mix(key(seed, 2f, b))
 //   mutation draws for genome g: words mix(key(seed, 2g+1, 16b + w)), w = 0..7 give one 16-bit
 //   uniform per base (mutate iff u16 < round(rate * 65536)), w = 8 picks the replacement base
@@ -24,6 +25,7 @@ __constant__ uint32_t kSynthRateU16[10] = {0, 328, 655, 1311, 1966, 2621, 3277, 
 
 __global__ void __launch_bounds__(256) synth_kernel(uint64_t seed, uint64_t index_begin, uint32_t n,
                                                     uint64_t length, uint64_t blocks_per_genome,
+                                                    uint32_t family_size, uint32_t rate_shift,
                                                     uint2 *__restrict__ seq2, uint32_t *__restrict__ valid,
                                                     uint64_t *__restrict__ base_off) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,9 +34,9 @@ __global__ void __launch_bounds__(256) synth_kernel(uint64_t seed, uint64_t inde
     for (uint64_t x = gid; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t g = x / blocks_per_genome, b = x % blocks_per_genome;
         const uint64_t index = index_begin + g;
-        const uint64_t fam = index / 10, mem = index % 10;
+        const uint64_t fam = index / family_size, mem = (index % family_size) % 10;
         uint64_t w = synth_word(seed, 2 * fam, b);
-        const uint32_t thr = kSynthRateU16[mem];
+        const uint32_t thr = kSynthRateU16[mem] >> rate_shift;
         if (thr != 0) {
             const uint64_t sel = synth_word(seed, 2 * index + 1, 16 * b + 8);
 #pragma unroll
@@ -64,8 +66,10 @@ __global__ void __launch_bounds__(256) synth_kernel(uint64_t seed, uint64_t inde
 }
 
 int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length, uint32_t *d_seq2,
-                  uint32_t *d_valid, uint64_t *d_base_off, cudaStream_t stream) {
+                  uint32_t *d_valid, uint64_t *d_base_off, cudaStream_t stream, uint32_t family_size,
+                  uint32_t rate_shift) {
     if (n == 0) return 0;
+    if (family_size == 0 || rate_shift > 15) { set_error("synth: bad family_size / rate_shift"); return 3; }
     if (n >= 0xFFFFFFFFull) { set_error("synth: n too large"); return 3; }
     const uint64_t padded = (length + 127) / 128 * 128;
     const uint64_t bpg = padded / 32;
@@ -75,7 +79,7 @@ int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length
     if (grid > 148ull * 64) grid = 148ull * 64;
     // base_off needs gid <= n covered by the first pass of the grid
     if (grid * 256 <= n) { set_error("synth: n too large for base_off pass"); return 3; }
-    synth_kernel<<<(uint32_t)grid, 256, 0, stream>>>(seed, index_begin, (uint32_t)n, length, bpg,
+    synth_kernel<<<(uint32_t)grid, 256, 0, stream>>>(seed, index_begin, (uint32_t)n, length, bpg, family_size, rate_shift,
                                                      reinterpret_cast<uint2 *>(d_seq2), d_valid,
                                                      d_base_off);
     GB_LAUNCH_CHECK();

@@ -261,3 +261,132 @@ class ShardedPrefilter:
             raise RuntimeError("candidate buffer too small")
         self.h_cand[:got].copy_(self.d_cand[:got])
         return self.gb.finish_candidates(self.h_cand[:got].numpy().view(np.uint32), k, min_ani)
+
+
+def route_hits(hits_i, n_local, world):
+    """Rank that evaluates stage 2 of a hit (i, j), i < j: the owner of the QUERY genome i (genome
+    slices are contiguous, n_local per rank).  Pure function (CPU-tested)."""
+    return np.minimum(np.asarray(hits_i, dtype=np.int64) // n_local, world - 1)
+
+
+class ShardedPipeline:
+    """The whole two-stage path on G GPUs, one process per GPU (bench.py at --gpus > 1; BASELINE.json
+    configs[3]): rank r owns genomes [r n_local, (r + 1) n_local).
+
+      K1 + K3 index   every rank sketches and indexes ITS genomes (no communication)
+      K2              ShardedPrefilter: 8-byte all-reduce, NCCL all-gather of the sketch table and of the
+                      block lists over NVLink, boustrophedon row-block shard of the join per rank
+      hits            every rank finishes its candidates in f64 on its host; the (small) hit lists are
+                      all-gathered so that every rank knows all hits
+      K3              hit (i, j) is evaluated by the owner of the query i; when j lives on another rank
+                      its hash table is read IN PLACE over NVLink through a CUDA IPC mapping of the
+                      owner's table array (no gather of the 0.4 MB / genome index)
+      engine          ANI values are gathered to rank 0, which runs the greedy engine (host)
+    Returns (clusters, info) on rank 0 and (None, info) elsewhere."""
+
+    def __init__(self, gb, dist, n_local, stride, device):
+        import torch
+        self.gb, self.dist, self.torch = gb, dist, torch
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.n_local, self.s, self.dev = n_local, stride, device
+        self.n = n_local * self.world
+        self.sp = ShardedPrefilter(gb, dist, n_local, stride, device)
+
+    def _allgather_var(self, arr, dtype, width):
+        """All-gather of per-rank (m_r, width) host arrays of `dtype` through one padded device collective."""
+        t, dist = self.torch, self.dist
+        m = t.tensor([len(arr)], dtype=t.int64, device=self.dev)
+        ms = t.empty(self.world, dtype=t.int64, device=self.dev)
+        dist.all_gather_into_tensor(ms, m)
+        ms = ms.cpu().numpy()
+        cap = int(ms.max())
+        if cap == 0:
+            return [np.zeros((0, width), dtype) for _ in range(self.world)]
+        buf = np.zeros((cap, width), dtype)
+        buf[: len(arr)] = arr
+        mine = t.from_numpy(buf.view(np.uint8).reshape(-1)).to(self.dev)
+        allb = t.empty(self.world * mine.numel(), dtype=t.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allb, mine)
+        allb = allb.cpu().numpy().view(dtype).reshape(self.world, cap, width)
+        return [allb[r, : int(ms[r])] for r in range(self.world)]
+
+    def _run(self, seq2, valid, d_base_off, base_off, lengths, device, min_ani, ani_pct, min_af, small_genomes=False):
+        import time
+        t, gb, dist, sp = self.torch, self.gb, self.dist, self.sp
+        rank, world, n_local, n = self.rank, self.world, self.n_local, self.n
+        info = {}
+        t0 = time.perf_counter()
+        idx = gb.AniIndex(small_genomes=small_genomes)
+        k1_ms, idx_ms = idx.ingest_packed(seq2, valid, base_off, lengths, sp.my_table.data_ptr(), sp.my_counts.data_ptr(),
+                                          device=device, d_base_off=d_base_off)
+        t.cuda.synchronize()
+        t1 = time.perf_counter()
+        # ---- K2 (torch's current stream; the library's stream is idle: ingest_packed synchronised)
+        sp.step_device(21, min_ani)
+        got = int(sp.d_ncand.item())
+        if got > sp.cand_cap:
+            raise RuntimeError("candidate buffer too small")
+        sp.h_cand[:got].copy_(sp.d_cand[:got])
+        mine = gb.finish_candidates(sp.h_cand[:got].numpy().view(np.uint32), 21, min_ani)
+        t2 = time.perf_counter()
+        # ---- every rank learns all hits (20 B each) and takes those whose query genome it owns
+        packed = np.zeros((len(mine), 5), np.uint32)
+        for c, f in enumerate(("i", "j", "common", "total")):
+            packed[:, c] = mine[f]
+        packed[:, 4] = mine["ani"].view(np.uint32)
+        parts = self._allgather_var(packed, np.uint32, 5)
+        allh = np.concatenate(parts) if parts else np.zeros((0, 5), np.uint32)
+        order = np.lexsort((allh[:, 1], allh[:, 0]))
+        allh = allh[order]
+        owner = route_hits(allh[:, 0], n_local, world)
+        my_rows = np.nonzero(owner == rank)[0]
+        # ---- peer tables: IPC handles + per-genome offsets are exchanged (host metadata, 16 B / genome)
+        handle, table_off, total_len = idx.export_tables()
+        metas = [None] * world
+        dist.all_gather_object(metas, (handle, table_off, total_len))
+        j_owner = route_hits(allh[my_rows, 1], n_local, world)
+        first_id = {}
+        for peer in sorted(set(int(x) for x in j_owner) - {rank}):
+            first_id[peer] = idx.attach_peer(*metas[peer])
+        q_local = allh[my_rows, 0].astype(np.int64) - rank * n_local
+        base = np.zeros(world, np.int64)      # id of a rank's first genome in this index's numbering
+        base[rank] = 0
+        for peer, fid in first_id.items():
+            base[peer] = fid
+        r_id = base[j_owner] + (allh[my_rows, 1].astype(np.int64) - j_owner * n_local)
+        pairs = np.stack([q_local, r_id], axis=1).astype(np.uint32)
+        res = idx.pairs(pairs, min_af)
+        chain_ms = idx.last_timing()[1]
+        t3 = time.perf_counter()
+        # ---- ANI values to rank 0 (row id + f32 bits), engine there
+        back = np.zeros((len(my_rows), 2), np.uint32)
+        back[:, 0] = my_rows
+        back[:, 1] = res["ani"].view(np.uint32)
+        got_back = self._allgather_var(back, np.uint32, 2)
+        dist.barrier()          # every peer has finished reading this rank's tables
+        idx.close()
+        clusters = None
+        if rank == 0:
+            ani = np.zeros(len(allh), np.float32)
+            for part in got_back:
+                ani[part[:, 0]] = part[:, 1].view(np.float32)
+            hits = np.zeros(len(allh), PAIR_DTYPE)
+            hits["i"], hits["j"], hits["common"], hits["total"] = allh[:, 0], allh[:, 1], allh[:, 2], allh[:, 3]
+            hits["ani"] = allh[:, 4].view(np.float32)
+            clusters, cinfo = gb.cluster_from_ani_table(n, hits, ani, ani_pct)
+            info.update(cinfo)
+        t4 = time.perf_counter()
+        info.update(n_precluster_hits=len(allh), n_ani_pairs=len(allh), my_ani_pairs=len(my_rows),
+                    remote_reference_pairs=int(np.sum(j_owner != rank)), sketch_ms=k1_ms, index_ms=idx_ms,
+                    ingest_ms=1e3 * (t1 - t0), prefilter_ms=1e3 * (t2 - t1), ani_ms=1e3 * (t3 - t2), ani_chain_ms=chain_ms,
+                    engine_ms=1e3 * (t4 - t3), total_ms=1e3 * (t4 - t0))
+        return clusters, info
+
+    def step_device(self, d_seq2, d_valid, d_base_off, base_off, lengths, min_ani=0.9, ani_pct=95.0, min_af=15.0,
+                    small_genomes=False):
+        """This rank's genomes are resident in HBM (device pointers; base_off / lengths host arrays)."""
+        return self._run(d_seq2, d_valid, d_base_off, base_off, lengths, True, min_ani, ani_pct, min_af, small_genomes)
+
+    def step_host(self, h_seq2, h_valid, base_off, lengths, min_ani=0.9, ani_pct=95.0, min_af=15.0, small_genomes=False):
+        """This rank's genomes are HOST buffers (addresses of pinned memory): uploaded inside the call."""
+        return self._run(h_seq2, h_valid, 0, base_off, lengths, False, min_ani, ani_pct, min_af, small_genomes)

@@ -304,12 +304,50 @@ void galah_b200_clusters_free(galah_b200_clusters_t *c);
 typedef struct galah_b200_cluster_stats {
     uint64_t n_precluster_hits;
     uint64_t n_ani_pairs;
-    float ani_chain_ms;
+    float ani_chain_ms;   /* device time of the K3 chain kernel(s) */
+    /* host wall clock of the call's phases (ms): ingest = read/upload + K0 + K1 + K3 index;
+     * sketch_ms / index_ms = device time of K1 / the K3 index build inside it (packed entries) */
+    float ingest_ms, sketch_ms, index_ms, prefilter_ms, ani_ms, engine_ms, total_ms;
 } galah_b200_cluster_stats_t;
 int galah_b200_cluster_files(const char *const *paths, size_t n, float precluster_min_ani,
                              float ani_threshold_pct, float min_af_pct, int small_genomes,
                              int host_threads, galah_b200_clusters_t *out,
                              galah_b200_cluster_stats_t *stats);
+
+/* The same call on genomes that are already packed (layout of galah_b200_sketch_packed: 2 bits per
+ * base + validity bitmap, genome g at bases [base_off[g], base_off[g] + lengths[g]), base_off
+ * multiples of 128, one contig per genome).  _packed takes HOST arrays and uploads them in batches
+ * of ~1 G bases on a copy stream while the previous batch is sketched and indexed; _packed_device
+ * takes arrays resident in HBM (d_base_off = device copy of base_off).  base_off / lengths are host
+ * arrays in both.  What bench.py times (`e2e` and `value`). */
+int galah_b200_cluster_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                              const uint64_t *lengths, size_t n, float precluster_min_ani,
+                              float ani_threshold_pct, float min_af_pct, int small_genomes,
+                              galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats);
+int galah_b200_cluster_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
+                                     const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                     float precluster_min_ani, float ani_threshold_pct, float min_af_pct,
+                                     int small_genomes, galah_b200_clusters_t *out,
+                                     galah_b200_cluster_stats_t *stats);
+
+/* First half of the two calls above, for callers that drive the stages themselves (the multi-GPU
+ * pipeline, one process per GPU): packed genomes (host arrays if device == 0, else resident) ->
+ * K1 sketch rows written to the DEVICE table d_hashes / d_counts (stride 1000) and the genomes
+ * appended to the K3 index.  ms2 (optional): device time of K1 and of the index build. */
+int galah_b200_ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,
+                             const uint64_t *base_off, const uint64_t *lengths, size_t n, int device,
+                             uint64_t *d_hashes, uint32_t *d_counts, galah_b200_ani_index_t *idx, float *ms2);
+/* Multi-GPU stage 2 without a collective: a process exports the CUDA IPC handle of its index's
+ * hash-table array plus the per-genome slot offsets (size + 1 entries) and lengths (size entries);
+ * a peer process on the same NVLink domain attaches it, after which the peer's genomes can be the
+ * REFERENCE of a pair under ids first_id .. first_id + n_genomes - 1 (the query stays local): the
+ * chain kernel reads the peer's table in place over NVLink.  The exporting index must outlive
+ * every attached use (barrier before galah_b200_ani_index_free). */
+int galah_b200_ani_index_export_tables(const galah_b200_ani_index_t *idx, uint8_t handle[64],
+                                       uint64_t *table_off, uint64_t *total_len);
+int galah_b200_ani_index_attach_peer(galah_b200_ani_index_t *idx, const uint8_t handle[64],
+                                     const uint64_t *table_off, const uint64_t *total_len,
+                                     size_t n_genomes, uint32_t *first_id);
 
 /* ---- skani preclusterer / contig clustering ------------------------------------------------
  * Replaces SkaniPreclusterer::distances and ::distances_contigs (src/skani.rs:21-56; the
@@ -392,6 +430,15 @@ int galah_b200_decode_fasta_device(const uint8_t *const *files, const size_t *le
 int galah_b200_synth_packed_device(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,
                                    uint32_t *d_seq2, uint32_t *d_valid, uint64_t *d_base_off,
                                    void *stream);
+
+/* Families of `family_size` genomes (member m = (index % family_size) % 10 takes the rate table
+ * above shifted right by rate_shift): family_size 10, rate_shift 0 is the call above;
+ * thousands / 2 gives one dense clade (every pair related, identity >= ~95 %). */
+int galah_b200_synth_packed_device_ex(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length,
+                                      uint32_t family_size, uint32_t rate_shift, uint32_t *d_seq2,
+                                      uint32_t *d_valid, uint64_t *d_base_off, void *stream);
+/* The CUDA stream the library enqueues its own work on (for event timing by the caller). */
+void *galah_b200_stream(void);
 
 #ifdef __cplusplus
 }

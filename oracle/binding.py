@@ -163,6 +163,16 @@ def synth_genome(seed, index, length):
     return out.tobytes()
 
 
+def synth_genome_ex(seed, index, length, family_size, rate_shift):
+    L = lib()
+    L.oracle_synth_genome_ex.restype = None
+    L.oracle_synth_genome_ex.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                         ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint8)]
+    out = np.zeros(length, np.uint8)
+    L.oracle_synth_genome_ex(seed, index, length, family_size, rate_shift, _p(out, ctypes.c_uint8))
+    return out.tobytes()
+
+
 def synth_block(seed, index, block):
     return int(lib().oracle_synth_block(seed, index, block))
 

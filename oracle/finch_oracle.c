@@ -368,10 +368,16 @@ static const uint32_t SYNTH_RATE_U16[10] = {
     /* round(rate * 65536) for {0, .5, 1, 2, 3, 4, 5, 6, 8, 10} % */
     0, 328, 655, 1311, 1966, 2621, 3277, 3932, 5243, 6554};
 
+uint64_t oracle_synth_block_ex(uint64_t seed, uint64_t index, uint64_t block, uint32_t family_size,
+                               uint32_t rate_shift);
 uint64_t oracle_synth_block(uint64_t seed, uint64_t index, uint64_t block) {
-    uint64_t fam = index / 10, mem = index % 10;
+    return oracle_synth_block_ex(seed, index, block, 10, 0);
+}
+uint64_t oracle_synth_block_ex(uint64_t seed, uint64_t index, uint64_t block, uint32_t family_size,
+                               uint32_t rate_shift) {
+    uint64_t fam = index / family_size, mem = (index % family_size) % 10;
     uint64_t w = synth_word(seed, 2 * fam, block);
-    uint32_t thr = SYNTH_RATE_U16[mem];
+    uint32_t thr = SYNTH_RATE_U16[mem] >> rate_shift;
     if (thr == 0) return w;
     uint64_t sel = synth_word(seed, 2 * index + 1, 16 * block + 8);
     for (int q = 0; q < 8; q++) {
@@ -395,6 +401,15 @@ void oracle_synth_genome(uint64_t seed, uint64_t index, uint64_t L, uint8_t *out
     static const char ACGT[4] = {'A', 'C', 'G', 'T'};
     for (uint64_t b = 0; b * 32 < L; b++) {
         uint64_t w = oracle_synth_block(seed, index, b);
+        for (int t = 0; t < 32 && b * 32 + t < L; t++) out[b * 32 + t] = (uint8_t)ACGT[(w >> (2 * t)) & 3];
+    }
+}
+
+void oracle_synth_genome_ex(uint64_t seed, uint64_t index, uint64_t L, uint32_t family_size, uint32_t rate_shift,
+                            uint8_t *out) {
+    static const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    for (uint64_t b = 0; b * 32 < L; b++) {
+        uint64_t w = oracle_synth_block_ex(seed, index, b, family_size, rate_shift);
         for (int t = 0; t < 32 && b * 32 + t < L; t++) out[b * 32 + t] = (uint8_t)ACGT[(w >> (2 * t)) & 3];
     }
 }
