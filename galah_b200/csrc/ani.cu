@@ -37,6 +37,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -515,10 +516,33 @@ struct TmpBuf {
 struct AniScratch {
     TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix, overflow;
     TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
-    TmpBuf<unsigned long long> acc_fx, idtab, pair_table;
+    TmpBuf<unsigned long long> acc_fx, pair_table;
     TmpBuf<uint32_t> pair_mask;
-    bool idtab_ready = false;
 };
+
+// 2^40 (M/N)^(1/15) for every M <= N < kIdTabN, evaluated once per device on the host (glibc pow,
+// the same expression as the oracle's) so that the chain kernel only adds integers.  4.2 MB,
+// resident for the life of the process.
+static int identity_table(const unsigned long long **out, cudaStream_t st) {
+    static std::mutex mu;
+    static unsigned long long *tabs[64] = {nullptr};
+    int dev = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("ani: device ordinal out of range"); return 3; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!tabs[dev]) {
+        std::vector<unsigned long long> tab((size_t)kIdTabN * (kIdTabN + 1) / 2 + kIdTabN, 0);
+        for (uint32_t N = 1; N < (uint32_t)kIdTabN; N++)
+            for (uint32_t M = 0; M <= N; M++) tab[(size_t)N * (N + 1) / 2 + M] = chunk_identity_fx(M, N);
+        unsigned long long *d = nullptr;
+        GB_CUDA(cudaMalloc(&d, tab.size() * 8));
+        GB_CUDA(cudaMemcpyAsync(d, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, st));
+        GB_CUDA(cudaStreamSynchronize(st));
+        tabs[dev] = d;
+    }
+    *out = tabs[dev];
+    return 0;
+}
 
 int AniIndex::export_tables(cudaIpcMemHandle_t *handle, std::vector<uint64_t> &table_off,
                             std::vector<uint64_t> &total_len) const {
@@ -715,22 +739,14 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
     if (!scratch_) scratch_ = new AniScratch();
     if (scratch_->pair_table.upload(h_ptab, st) || scratch_->pair_mask.upload(h_pmask, st)) return 2;
     TmpBuf<uint32_t> &d_pairs = scratch_->pairs, &d_acc = scratch_->acc, &d_over = scratch_->overflow;
-    TmpBuf<unsigned long long> &d_fx = scratch_->acc_fx, &d_idtab = scratch_->idtab;
+    TmpBuf<unsigned long long> &d_fx = scratch_->acc_fx;
     const uint32_t kOverflowCap = 1u << 16;
     if (d_pairs.alloc(2 * n_pairs) || d_acc.alloc((size_t)kAccWords * n_pairs) || d_fx.alloc(n_pairs) ||
         d_over.alloc(1 + 3 * (size_t)kOverflowCap))
         return 2;
     GB_CUDA(cudaMemcpyAsync(d_pairs.p, pairs, 8 * n_pairs, cudaMemcpyHostToDevice, st));
-    if (!scratch_->idtab_ready) {
-        // 2^40 (M/N)^(1/15) for every M <= N < kIdTabN, evaluated once on the host (glibc pow, the
-        // same expression as the oracle's) so that the device only adds integers
-        std::vector<unsigned long long> tab((size_t)kIdTabN * (kIdTabN + 1) / 2 + kIdTabN, 0);
-        for (uint32_t N = 1; N < (uint32_t)kIdTabN; N++)
-            for (uint32_t M = 0; M <= N; M++) tab[(size_t)N * (N + 1) / 2 + M] = chunk_identity_fx(M, N);
-        if (d_idtab.upload(tab, st)) return 2;
-        GB_CUDA(cudaStreamSynchronize(st));
-        scratch_->idtab_ready = true;
-    }
+    const unsigned long long *d_idtab_p = nullptr;
+    if (int rc = identity_table(&d_idtab_p, st)) return rc;
     GB_CUDA(cudaMemsetAsync(d_acc.p, 0, 4 * (size_t)kAccWords * n_pairs, st));
     GB_CUDA(cudaMemsetAsync(d_fx.p, 0, 8 * n_pairs, st));
     GB_CUDA(cudaMemsetAsync(d_over.p, 0, 4, st));
@@ -763,7 +779,7 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
             p.pair_mask = scratch_->pair_mask.p + b0;
             p.seed_off = d_seed_off_.p; p.cso_off = d_cso_off_.p;
             p.n_chunks = d_n_chunks_.p; p.acc = d_acc.p + (size_t)kAccWords * b0; p.acc_fx = d_fx.p + b0;
-            p.idtab = d_idtab.p; p.overflow = d_over.p; p.overflow_cap = kOverflowCap;
+            p.idtab = d_idtab_p; p.overflow = d_over.p; p.overflow_cap = kOverflowCap;
             p.unit_prefix = d_prefix.p; p.n_pairs = (uint32_t)(b1 - b0); p.n_units = (uint32_t)units;
             ani_chain_kernel<<<(uint32_t)((units + kChainThreads - 1) / kChainThreads), kChainThreads, smem, st>>>(p);
             GB_LAUNCH_CHECK();
