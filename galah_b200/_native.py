@@ -117,6 +117,8 @@ _SIGNATURES = {
     "galah_b200_ani_last_timing": (ctypes.c_int, [vp, f32p, f32p]),
     "galah_b200_cluster_from_ani_table": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                                          ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]),
+    "galah_b200_cluster_from_ani_tables": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]),
     "galah_b200_cluster_from_distances": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p,
                                                          ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                                          ANI_FN, vp, ctypes.POINTER(Clusters)]),

@@ -365,6 +365,18 @@ def cluster_from_ani_table(n_genomes, hits, ani, ani_threshold):
     return _take_clusters(res)
 
 
+def cluster_from_ani_tables(n_genomes, hits, ani_fwd, ani_rev, ani_threshold):
+    """The engine with both orientations of every hit (ani_fwd: query = hits.i, ani_rev: query = hits.j)."""
+    hits = np.ascontiguousarray(hits, PAIR_DTYPE)
+    ani_fwd = np.ascontiguousarray(ani_fwd, np.float32); ani_rev = np.ascontiguousarray(ani_rev, np.float32)
+    if len(ani_fwd) != len(hits) or len(ani_rev) != len(hits):
+        raise ValueError("one ANI value per hit and orientation")
+    res = _native.Clusters()
+    check(lib().galah_b200_cluster_from_ani_tables(int(n_genomes), hits.ctypes.data, len(hits), ani_fwd.ctypes.data,
+                                                   ani_rev.ctypes.data, ctypes.c_float(ani_threshold), ctypes.byref(res)))
+    return _take_clusters(res)
+
+
 def _take_clusters(res):
     try:
         nc = int(res.n_clusters)

@@ -1064,8 +1064,20 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
 }
 
 // ANI of hit pairs served from a table (hits sorted by (i, j), ani[x] belongs to hits[x]).
+// calculate_ani(fasta1 = representative, fasta2 = genome) makes fasta1 the QUERY (skani dist -q
+// fasta1 -r fasta2, src/skani.rs:733-744).  The forward table holds query = i (the lower index):
+// what the representative search asks for (representatives precede the genome, src/clusterer.rs:
+// 229-231).  The membership pass can ask for a representative with a HIGHER index than the genome
+// (src/clusterer.rs:375-384): that is the reverse orientation, served from ani_rev when present;
+// otherwise the request is recorded (and the forward value returned) so that the caller can
+// evaluate exactly those pairs and run the engine again.
 namespace {
-struct AniTable { const galah_b200_pair_t *hits; size_t n; const float *ani; size_t stride; };
+struct AniTable {
+    const galah_b200_pair_t *hits; size_t n; const float *ani; size_t stride;
+    const float *ani_rev = nullptr;            // [n] or null
+    const uint8_t *have_rev = nullptr;         // [n] or null: ani_rev[x] is valid
+    std::vector<size_t> *rev_requests = nullptr;
+};
 int ani_table_lookup(void *ctx, uint32_t rep, uint32_t genome, float *ani) {
     const AniTable *t = (const AniTable *)ctx;
     const uint32_t a = std::min(rep, genome), b = std::max(rep, genome);
@@ -1075,20 +1087,39 @@ int ani_table_lookup(void *ctx, uint32_t rep, uint32_t genome, float *ani) {
         if (t->hits[mid].i < a || (t->hits[mid].i == a && t->hits[mid].j < b)) lo = mid + 1; else hi = mid;
     }
     if (lo >= t->n || t->hits[lo].i != a || t->hits[lo].j != b) return 0;
+    if (rep > genome) {
+        if (t->ani_rev && (!t->have_rev || t->have_rev[lo])) { *ani = t->ani_rev[lo]; return 1; }
+        if (t->rev_requests) t->rev_requests->push_back(lo);
+    }
     *ani = *(const float *)((const char *)t->ani + lo * t->stride);  // skani never yields None (src/skani.rs:760)
     return 1;
 }
 }  // namespace
 
-int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
-                                      const float *ani, float ani_threshold, galah_b200_clusters_t *out) {
-    if (n_hits && (!hits || !ani)) { set_error("cluster_from_ani_table: NULL hits / ani"); return GALAH_B200_ERR_ARG; }
+static int check_sorted_hits(const galah_b200_pair_t *hits, size_t n_hits) {
     for (size_t x = 1; x < n_hits; x++)
         if (hits[x - 1].i > hits[x].i || (hits[x - 1].i == hits[x].i && hits[x - 1].j >= hits[x].j)) {
             set_error("cluster_from_ani_table: hits must be sorted by (i, j) without duplicates");
             return GALAH_B200_ERR_ARG;
         }
+    return 0;
+}
+
+int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                      const float *ani, float ani_threshold, galah_b200_clusters_t *out) {
+    if (n_hits && (!hits || !ani)) { set_error("cluster_from_ani_table: NULL hits / ani"); return GALAH_B200_ERR_ARG; }
+    if (int rc = check_sorted_hits(hits, n_hits)) return rc;
     AniTable table{hits, n_hits, ani, sizeof(float)};
+    return galah_b200_cluster_from_distances(n_genomes, hits, n_hits, 0, ani_threshold, ani_table_lookup, &table, out);
+}
+
+int galah_b200_cluster_from_ani_tables(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                       const float *ani_fwd, const float *ani_rev, float ani_threshold,
+                                       galah_b200_clusters_t *out) {
+    if (n_hits && (!hits || !ani_fwd || !ani_rev)) { set_error("cluster_from_ani_tables: NULL argument"); return GALAH_B200_ERR_ARG; }
+    if (int rc = check_sorted_hits(hits, n_hits)) return rc;
+    AniTable table{hits, n_hits, ani_fwd, sizeof(float)};
+    table.ani_rev = ani_rev;
     return galah_b200_cluster_from_distances(n_genomes, hits, n_hits, 0, ani_threshold, ani_table_lookup, &table, out);
 }
 
@@ -1115,10 +1146,31 @@ static int cluster_from_resident(const uint64_t *d_table, const uint32_t *d_coun
     if (int rc = index.pairs(pairs.data(), n_hits, min_af_pct, false, res.data(), st)) return rc;
     const double t2 = now_ms();
     AniTable table{hits, n_hits, n_hits ? &res[0].ani : nullptr, sizeof(AniPairResult)};
+    std::vector<size_t> rev_requests;
+    table.rev_requests = &rev_requests;
     int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
+    if (rc == 0 && !rev_requests.empty()) {
+        // membership asked for representatives that come AFTER the genome: those pairs have the
+        // representative as the query.  One more K3 launch for exactly them, then the engine again
+        // (the representatives do not change: their search only reads forward values).
+        std::sort(rev_requests.begin(), rev_requests.end());
+        rev_requests.erase(std::unique(rev_requests.begin(), rev_requests.end()), rev_requests.end());
+        std::vector<uint32_t> rp(2 * rev_requests.size());
+        for (size_t x = 0; x < rev_requests.size(); x++) { rp[2 * x] = hits[rev_requests[x]].j; rp[2 * x + 1] = hits[rev_requests[x]].i; }
+        std::vector<AniPairResult> rres(rev_requests.size());
+        if (int rc2 = index.pairs(rp.data(), rev_requests.size(), min_af_pct, false, rres.data(), st)) return rc2;
+        std::vector<float> ani_rev(n_hits, 0.f);
+        std::vector<uint8_t> have_rev(n_hits, 0);
+        for (size_t x = 0; x < rev_requests.size(); x++) { ani_rev[rev_requests[x]] = rres[x].ani; have_rev[rev_requests[x]] = 1; }
+        table.ani_rev = ani_rev.data(); table.have_rev = have_rev.data(); table.rev_requests = nullptr;
+        galah_b200_clusters_free(out);
+        memset(out, 0, sizeof(*out));
+        rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
+        if (stats) stats->n_ani_pairs = n_hits + rev_requests.size();
+    }
     if (stats) {
         stats->n_precluster_hits = n_hits;
-        stats->n_ani_pairs = n_hits;
+        if (stats->n_ani_pairs == 0) stats->n_ani_pairs = n_hits;
         stats->ani_chain_ms = index.last_chain_ms;
         stats->prefilter_ms = (float)(t1 - t0); stats->ani_ms = (float)(t2 - t1); stats->engine_ms = (float)(now_ms() - t2);
     }

@@ -116,6 +116,7 @@ int PrefilterWorkspace::release() {
     cudaFree(d_fin_hi); cudaFree(d_fin_lo); cudaFree(d_fin_tags); cudaFree(d_splits);
     for (int x = 0; x < 2; x++) { cudaFree(d_bl_vals[x]); cudaFree(d_bl_tags[x]); }
     cudaFree(d_wave_counters); cudaFree(d_item_counters);
+    cudaFree(d_alt_local_rb); cudaFree(d_alt_item_prefix); cudaFree(d_alt_work_counter); cudaFree(d_dense_flag);
     for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
     *this = PrefilterWorkspace();
     return 0;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) prefilter_tiled_kernel(const Kern
     __shared__ uint32_t s_col_cnt[2][kColBlock];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (p.run_if_flag && *p.mode_flag == 0) return;  // fallback launch of a table the join handles itself
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
         fence_mbar_init();
@@ -305,6 +307,52 @@ static int upload_work_list(PrefilterWorkspace &ws, size_t n, uint32_t block_row
     return 0;
 }
 
+// Launch of the pairwise (mode 1) kernel over one shard.  alt: use the workspace's second work list
+// and run only if the device flag says so (fallback of a small tie-dense launch of the join).
+int pairwise_launch(PrefilterWorkspace &ws, KernelParams p, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
+                    bool alt) {
+    const size_t n = p.n, stride = p.stride;
+    if (alt) {
+        std::swap(ws.d_local_rb, ws.d_alt_local_rb); std::swap(ws.cap_local_rb, ws.cap_alt_local_rb);
+        std::swap(ws.d_item_prefix, ws.d_alt_item_prefix); std::swap(ws.cap_prefix, ws.cap_alt_prefix);
+        std::swap(ws.d_work_counter, ws.d_alt_work_counter);
+    }
+    int rc = upload_work_list(ws, n, kRowBlock, kColChunk, shard, n_shards, stream, p);
+    if (alt) {
+        std::swap(ws.d_local_rb, ws.d_alt_local_rb); std::swap(ws.cap_local_rb, ws.cap_alt_local_rb);
+        std::swap(ws.d_item_prefix, ws.d_alt_item_prefix); std::swap(ws.cap_prefix, ws.cap_alt_prefix);
+        std::swap(ws.d_work_counter, ws.d_alt_work_counter);
+    }
+    if (rc) return rc;
+    if (p.n_local_rb == 0) return 0;
+    p.run_if_flag = alt ? 1u : 0u;
+    if (alt) p.mode_flag = ws.d_dense_flag;
+    p.items = nullptr; p.n_explicit = 0;
+    int dev = 0, sms = kNumSMsFallback, max_smem = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    uint64_t n_items = 0;
+    {
+        const uint32_t per_group = kShardRows / kRowBlock;
+        for (uint32_t rb = 0; rb < p.n_row_blocks; rb++)
+            if (shard_of_group(rb / per_group, n_shards) == shard) n_items += (p.n_row_blocks - rb + kColChunk - 1) / kColChunk;
+    }
+    const size_t smem = tiled_smem_bytes(stride);
+    if (smem + 1024 <= (size_t)max_smem) {
+        GB_CUDA(cudaFuncSetAttribute(prefilter_tiled_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms);
+        prefilter_tiled_kernel<<<grid, kThreads, smem, stream>>>(p);
+    } else {
+        if (alt) return 0;  // sketches too large for the tiles: the join keeps the launch
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_items + 7) / 8, (uint64_t)sms * 8);
+        prefilter_generic_kernel<<<std::max(grid, 1u), 256, 0, stream>>>(p);
+    }
+    GB_LAUNCH_CHECK();
+    return 0;
+}
+
 int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const uint32_t *d_counts, size_t n,
                       size_t stride, int k, float min_ani, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
                       uint4 *d_cand, size_t cand_cap, unsigned long long *d_n_cand, KernelParams &p, int rule,
@@ -348,31 +396,8 @@ int prefilter_enqueue(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
     if (n < 2) return 0;
     if (mode == 0 && join_supported(stride)) return join_build_and_launch(ws, p, shard, n_shards, stream);
 
-    if (int rc = upload_work_list(ws, n, kRowBlock, kColChunk, shard, n_shards, stream, p)) return rc;
-    if (p.n_local_rb == 0) return 0;
-    int dev = 0, sms = kNumSMsFallback, max_smem = 0;
-    GB_CUDA(cudaGetDevice(&dev));
-    GB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    // number of items = last prefix entry; recompute on the host side
-    uint64_t n_items = 0;
-    {
-        const uint32_t per_group = kShardRows / kRowBlock;
-        for (uint32_t rb = 0; rb < p.n_row_blocks; rb++)
-            if (shard_of_group(rb / per_group, n_shards) == shard) n_items += (p.n_row_blocks - rb + kColChunk - 1) / kColChunk;
-    }
-    const size_t smem = tiled_smem_bytes(stride);
     if (ws.record(1, stream)) return 2;
-    if (smem + 1024 <= (size_t)max_smem) {
-        GB_CUDA(cudaFuncSetAttribute(prefilter_tiled_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)sms);
-        prefilter_tiled_kernel<<<grid, kThreads, smem, stream>>>(p);
-    } else {
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_items + 7) / 8, (uint64_t)sms * 8);
-        prefilter_generic_kernel<<<std::max(grid, 1u), 256, 0, stream>>>(p);
-    }
-    GB_LAUNCH_CHECK();
+    if (int rc = pairwise_launch(ws, p, shard, n_shards, stream, false)) return rc;
     if (ws.record(2, stream)) return 2;
     return 0;
 }

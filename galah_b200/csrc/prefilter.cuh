@@ -54,6 +54,13 @@ struct PrefilterWorkspace {
     uint64_t *d_item_prefix = nullptr;
     size_t cap_local_rb = 0, cap_prefix = 0;
     unsigned long long *d_work_counter = nullptr;
+    // pairwise fallback of a small tie-dense launch (join_build_and_launch): its own work list,
+    // and the device flag {0 = join runs, 1 = the pairwise kernel runs} set by bl_dense_stat_kernel
+    uint32_t *d_alt_local_rb = nullptr;
+    uint64_t *d_alt_item_prefix = nullptr;
+    size_t cap_alt_local_rb = 0, cap_alt_prefix = 0;
+    unsigned long long *d_alt_work_counter = nullptr;
+    uint32_t *d_dense_flag = nullptr;  // [0] flag, [1] equal-at-distance-16 count, [2] entries looked at
     // streamed host-buffer path: one work counter per wave, one "slice resident" event per slice
     unsigned long long *d_wave_counters = nullptr;
     size_t cap_wave_counters = 0;
@@ -107,6 +114,8 @@ struct KernelParams {
     uint32_t n_adj, adj_lr0;  // join: items (rb, rb + 1), taken next; local rows [adj_lr0, adj_lr0 + n_adj)
     unsigned long long *dbg_buf;  // per-item {start ns, end ns, sm, rb << 32 | cb} log (debug), or null
     uint32_t cb_lo;   // first column block of the launch's window (0 unless a streamed wave)
+    const uint32_t *mode_flag;  // or null; join kernel leaves at once if *mode_flag != 0, the pairwise
+    uint32_t run_if_flag;       //          kernel launched as a fallback (run_if_flag = 1) if it is 0
 };
 
 // Enqueue the prefilter for one shard.  d_cand: uint4 {i, j, common, total} candidates that
@@ -148,6 +157,8 @@ int join_launch_items(PrefilterWorkspace &ws, KernelParams &p, const uint32_t *d
                       const uint8_t *d_tags, const uint32_t *d_len, const uint32_t *d_items, size_t n_items,
                       cudaStream_t stream);
 // prefilter.cu: work list with one item per (local row block, column block >= it), block = kShardRows
+int pairwise_launch(PrefilterWorkspace &ws, KernelParams p, uint32_t shard, uint32_t n_shards, cudaStream_t stream,
+                    bool alt);
 int upload_join_work_list(PrefilterWorkspace &ws, size_t n, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream, KernelParams &p);
 

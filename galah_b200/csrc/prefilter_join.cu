@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
     extern __shared__ __align__(128) uint8_t smem_raw[];
     JoinSmem &S = *reinterpret_cast<JoinSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
+    if (p.mode_flag && *p.mode_flag != 0) return;  // small tie-dense launch: the pairwise kernel takes it
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); S.tq_n = 0; }
     __syncthreads();
     uint32_t phase = 0;
@@ -1046,6 +1047,39 @@ static int ensure_fin(PrefilterWorkspace &ws, uint64_t total, cudaStream_t strea
     return 0;
 }
 
+// How tie-dense are the block lists?  Counts the entries whose 64-bit key equals the key 16 places
+// on in the same list: zero for families of up to 16 relatives per block, most entries when a
+// block is one clade.  The last CTA to finish sets flag[0] = 1 if more than a quarter qualify.
+__global__ void __launch_bounds__(256) bl_dense_stat_kernel(const uint32_t *__restrict__ hi, const uint32_t *__restrict__ lo,
+                                                            const uint32_t *__restrict__ len, uint32_t nb, uint64_t cap,
+                                                            uint32_t *__restrict__ flag, uint32_t *__restrict__ done) {
+    uint32_t eq = 0, seen = 0;
+    for (uint32_t b = blockIdx.y; b < nb; b += gridDim.y) {
+        const uint32_t l = len[b];
+        const uint32_t *h = hi + (uint64_t)b * cap, *w = lo + (uint64_t)b * cap;
+        for (uint32_t x = blockIdx.x * 256 + threadIdx.x; x + 16 < l; x += gridDim.x * 256) {
+            eq += (h[x] == h[x + 16] && w[x] == w[x + 16]) ? 1u : 0u;
+            seen++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { eq += __shfl_xor_sync(0xffffffffu, eq, o); seen += __shfl_xor_sync(0xffffffffu, seen, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&flag[1], eq); atomicAdd(&flag[2], seen); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) + 1 == gridDim.x * gridDim.y) {
+            const uint32_t e = atomicAdd(&flag[1], 0u), sn = atomicAdd(&flag[2], 0u);
+            flag[0] = (sn > 0 && 4ull * e > sn) ? 1u : 0u;
+        }
+    }
+}
+
+// A launch of at most this many items runs every item on its own CTA at once; if the lists are
+// tie-dense each item is a long serial tie resolution (milliseconds) and the pairwise kernel,
+// which spreads the same pairs over all SMs, finishes first (crossover measured at ~2,000 items).
+constexpr uint64_t kSmallJoinItems = 2048;
+
 // Single-device path: build every list into workspace-owned arrays, then join.
 int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shard, uint32_t n_shards,
                           cudaStream_t stream) {
@@ -1056,7 +1090,24 @@ int join_build_and_launch(PrefilterWorkspace &ws, KernelParams &p, uint32_t shar
     if (int rc = blocklist_build(ws, p.hashes, p.counts, p.n, p.stride, 0, nb, ws.d_fin_hi, ws.d_fin_lo,
                                  ws.d_fin_tags, ws.d_bl_len, stream))
         return rc;
-    return join_launch(ws, p, ws.d_fin_hi, ws.d_fin_lo, ws.d_fin_tags, ws.d_bl_len, shard, n_shards, stream);
+    uint64_t n_items = 0;
+    for (uint32_t rb = 0; rb < nb; rb++) if (shard_of_group(rb, n_shards) == shard) n_items += nb - rb;
+    const bool guard = n_items <= kSmallJoinItems && n_items > 0;
+    if (guard) {
+        if (!ws.d_dense_flag) GB_CUDA(cudaMalloc(&ws.d_dense_flag, 4 * sizeof(uint32_t)));
+        GB_CUDA(cudaMemsetAsync(ws.d_dense_flag, 0, 4 * sizeof(uint32_t), stream));
+        const dim3 grid(8, std::min<uint32_t>(nb, 64));
+        bl_dense_stat_kernel<<<grid, 256, 0, stream>>>(ws.d_fin_hi, ws.d_fin_lo, ws.d_bl_len, nb, (uint64_t)kJR * p.stride,
+                                                     ws.d_dense_flag, ws.d_dense_flag + 3);
+        GB_LAUNCH_CHECK();
+        p.mode_flag = ws.d_dense_flag;
+    }
+    if (int rc = join_launch(ws, p, ws.d_fin_hi, ws.d_fin_lo, ws.d_fin_tags, ws.d_bl_len, shard, n_shards, stream)) return rc;
+    if (guard) {
+        if (int rc = pairwise_launch(ws, p, shard, n_shards, stream, true)) return rc;
+        if (ws.record(2, stream)) return 2;  // the main-kernel time covers whichever kernel did the work
+    }
+    return 0;
 }
 
 // Host-buffer path, pipelined against the PCIe upload.  The table goes up in `chunks` equal slices

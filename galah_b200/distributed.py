@@ -278,9 +278,10 @@ class ShardedPipeline:
                       block lists over NVLink, boustrophedon row-block shard of the join per rank
       hits            every rank finishes its candidates in f64 on its host; the (small) hit lists are
                       all-gathered so that every rank knows all hits
-      K3              hit (i, j) is evaluated by the owner of the query i; when j lives on another rank
-                      its hash table is read IN PLACE over NVLink through a CUDA IPC mapping of the
-                      owner's table array (no gather of the 0.4 MB / genome index)
+      K3              both orientations of a hit (i, j) are evaluated, each by the owner of its query; when the
+                      reference genome lives on another rank its hash table is read IN PLACE over NVLink
+                      through a CUDA IPC mapping of the owner's table array (no gather of the 0.4 MB /
+                      genome index)
       engine          ANI values are gathered to rank 0, which runs the greedy engine (host)
     Returns (clusters, info) on rank 0 and (None, info) elsewhere."""
 
@@ -338,46 +339,47 @@ class ShardedPipeline:
         allh = np.concatenate(parts) if parts else np.zeros((0, 5), np.uint32)
         order = np.lexsort((allh[:, 1], allh[:, 0]))
         allh = allh[order]
-        owner = route_hits(allh[:, 0], n_local, world)
-        my_rows = np.nonzero(owner == rank)[0]
+        # ---- stage-2 jobs: both orientations of every hit (calculate_ani(rep, genome) makes the
+        # representative the query, and the membership pass asks for representatives on either side of
+        # the genome); a job runs on the rank that owns its QUERY genome
+        q_all = np.concatenate([allh[:, 0], allh[:, 1]]).astype(np.int64)
+        r_all = np.concatenate([allh[:, 1], allh[:, 0]]).astype(np.int64)
+        owner = route_hits(q_all, n_local, world)
+        my_jobs = np.nonzero(owner == rank)[0]
         # ---- peer tables: IPC handles + per-genome offsets are exchanged (host metadata, 16 B / genome)
         handle, table_off, total_len = idx.export_tables()
         metas = [None] * world
         dist.all_gather_object(metas, (handle, table_off, total_len))
-        j_owner = route_hits(allh[my_rows, 1], n_local, world)
-        first_id = {}
-        for peer in sorted(set(int(x) for x in j_owner) - {rank}):
-            first_id[peer] = idx.attach_peer(*metas[peer])
-        q_local = allh[my_rows, 0].astype(np.int64) - rank * n_local
+        r_owner = route_hits(r_all[my_jobs], n_local, world)
         base = np.zeros(world, np.int64)      # id of a rank's first genome in this index's numbering
-        base[rank] = 0
-        for peer, fid in first_id.items():
-            base[peer] = fid
-        r_id = base[j_owner] + (allh[my_rows, 1].astype(np.int64) - j_owner * n_local)
+        for peer in sorted(set(int(x) for x in r_owner) - {rank}):
+            base[peer] = idx.attach_peer(*metas[peer])
+        q_local = q_all[my_jobs] - rank * n_local
+        r_id = base[r_owner] + (r_all[my_jobs] - r_owner * n_local)
         pairs = np.stack([q_local, r_id], axis=1).astype(np.uint32)
         res = idx.pairs(pairs, min_af)
         chain_ms = idx.last_timing()[1]
         t3 = time.perf_counter()
-        # ---- ANI values to rank 0 (row id + f32 bits), engine there
-        back = np.zeros((len(my_rows), 2), np.uint32)
-        back[:, 0] = my_rows
+        # ---- ANI values to rank 0 (job id + f32 bits), engine there
+        back = np.zeros((len(my_jobs), 2), np.uint32)
+        back[:, 0] = my_jobs
         back[:, 1] = res["ani"].view(np.uint32)
         got_back = self._allgather_var(back, np.uint32, 2)
         dist.barrier()          # every peer has finished reading this rank's tables
         idx.close()
         clusters = None
         if rank == 0:
-            ani = np.zeros(len(allh), np.float32)
+            ani = np.zeros(2 * len(allh), np.float32)
             for part in got_back:
                 ani[part[:, 0]] = part[:, 1].view(np.float32)
             hits = np.zeros(len(allh), PAIR_DTYPE)
             hits["i"], hits["j"], hits["common"], hits["total"] = allh[:, 0], allh[:, 1], allh[:, 2], allh[:, 3]
             hits["ani"] = allh[:, 4].view(np.float32)
-            clusters, cinfo = gb.cluster_from_ani_table(n, hits, ani, ani_pct)
+            clusters, cinfo = gb.cluster_from_ani_tables(n, hits, ani[: len(allh)], ani[len(allh):], ani_pct)
             info.update(cinfo)
         t4 = time.perf_counter()
-        info.update(n_precluster_hits=len(allh), n_ani_pairs=len(allh), my_ani_pairs=len(my_rows),
-                    remote_reference_pairs=int(np.sum(j_owner != rank)), sketch_ms=k1_ms, index_ms=idx_ms,
+        info.update(n_precluster_hits=len(allh), n_ani_pairs=2 * len(allh), my_ani_pairs=len(my_jobs),
+                    remote_reference_pairs=int(np.sum(r_owner != rank)), sketch_ms=k1_ms, index_ms=idx_ms,
                     ingest_ms=1e3 * (t1 - t0), prefilter_ms=1e3 * (t2 - t1), ani_ms=1e3 * (t3 - t2), ani_chain_ms=chain_ms,
                     engine_ms=1e3 * (t4 - t3), total_ms=1e3 * (t4 - t0))
         return clusters, info

@@ -292,6 +292,13 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
  * batched galah_b200_ani_pairs call over every precluster hit. */
 int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
                                       const float *ani, float ani_threshold, galah_b200_clusters_t *out);
+/* The same with both orientations of every hit: ani_fwd[x] = ANI with hits[x].i as the query,
+ * ani_rev[x] = with hits[x].j as the query.  calculate_ani(representative, genome) makes the
+ * representative the query (skani dist -q fasta1, src/skani.rs:733-744); the membership pass asks
+ * for representatives on either side of the genome (src/clusterer.rs:375-384). */
+int galah_b200_cluster_from_ani_tables(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                       const float *ani_fwd, const float *ani_rev, float ani_threshold,
+                                       galah_b200_clusters_t *out);
 void galah_b200_clusters_free(galah_b200_clusters_t *c);
 
 /* The whole hot path: galah::clusterer::cluster(genomes, &FinchPreclusterer{min_ani:

@@ -119,6 +119,30 @@ def test_modes_agree_on_candidates(gb):
     assert out[0].shape == out[1].shape and np.array_equal(out[0], out[1])
 
 
+def test_dense_clade_small_launch_takes_the_pairwise_fallback_and_is_exact(gb):
+    """One clade (every sketch shares most hashes with every other): a launch of few join items hands
+    the table to the pairwise kernel through a device flag (join_build_and_launch); whichever
+    kernel runs, the pair list is the oracle's, bit for bit."""
+    rng = np.random.default_rng(47)
+    n, s = 420, 1000
+    pool = np.unique(rng.integers(1, 1 << 62, size=1400, dtype=np.uint64))
+    table = np.full((n, s), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    counts = np.zeros(n, np.uint32)
+    for g in range(n):
+        keep = np.sort(rng.choice(pool, size=int(rng.integers(900, 1001)), replace=False))
+        table[g, : len(keep)] = keep
+        counts[g] = len(keep)
+    got = gb.prefilter(table, counts, 21, 0.9)
+    exp = oracle.prefilter(table, counts, 21, 0.9)
+    assert len(exp) > n * (n - 1) // 4
+    assert_pairs_equal(got, exp)
+    gb.prefilter_mode(1)
+    try:
+        assert_pairs_equal(gb.prefilter(table, counts, 21, 0.9), exp)
+    finally:
+        gb.prefilter_mode(0)
+
+
 def test_sliced_blocklist_build_then_join_matches(gb, kernel_mode):
     """The multi-GPU form: lists built in 3 equal slices (last one padded past the table), gathered,
     then joined per shard -- the union of the shards' candidates equals the one-call result."""
