@@ -346,7 +346,7 @@ def main():
     total_ms = float(tot.item())
     clocks = sampler.stop() if rank == 0 else None
     value = pairs * args.steps / (total_ms * 1e-3)
-    phase = {k: float(np.mean([i[k] for i in infos])) for k in
+    phase = {k: float(np.median([i[k] for i in infos])) for k in
              ("sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "ani_chain_ms", "engine_ms", "ingest_ms", "total_ms")
              if k in infos[0]}
     n_hits = int(infos[-1]["n_precluster_hits"])

@@ -1,6 +1,8 @@
 // extern "C" boundary of libgalah_b200.so (declared in include/galah_b200.h).
 #include "../../include/galah_b200.h"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -1294,6 +1296,9 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         GB_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
         GB_CUDA(cudaEventElapsedTime(&c, ev[1], ev[2]));
         sketch_ms += a; index_ms += c;
+        if (getenv("GALAH_B200_DEBUG"))
+            fprintf(stderr, "[ingest_packed] batch %zu/%zu: %zu genomes, K1 %.2f ms, index %.2f ms (kernels %.2f ms)\n", b,
+                    n_batches, nb, a, c, index.last_build_ms);
     }
     if (sketch_ms_out) *sketch_ms_out = sketch_ms;
     if (index_ms_out) *index_ms_out = index_ms;
