@@ -110,6 +110,7 @@ _SIGNATURES = {
     "galah_b200_ani_index_add_packed": (ctypes.c_int, [vp, u32p, u32p, u64p, ctypes.c_size_t, u64p, u32p, u32p]),
     "galah_b200_ani_index_add_packed_device": (ctypes.c_int, [vp, vp, vp, vp, u64p, u64p, ctypes.c_size_t, vp]),
     "galah_b200_ani_index_size": (ctypes.c_size_t, [vp]),
+    "galah_b200_ani_index_clear": (ctypes.c_int, [vp]),
     "galah_b200_ani_index_genome": (ctypes.c_int, [vp, ctypes.c_size_t, u64p, u32p, u64p]),
     "galah_b200_ani_index_seeds": (ctypes.c_int, [vp, ctypes.c_size_t, u32p, u32p, u32p, ctypes.c_size_t]),
     "galah_b200_ani_pairs": (ctypes.c_int, [vp, u32p, ctypes.c_size_t, ctypes.c_float, ctypes.c_int,
@@ -132,6 +133,29 @@ _SIGNATURES = {
     "galah_b200_cluster_packed_device": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
                                                         ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                         ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),
+    "galah_b200_session_create": (ctypes.c_int, [ctypes.POINTER(vp)]),
+    "galah_b200_session_free": (None, [vp]),
+    "galah_b200_session_set_clusterer": (ctypes.c_int, [vp, ctypes.c_int]),
+    "galah_b200_finch_method_name": (ctypes.c_char_p, []),
+    "galah_b200_skani_method_name": (ctypes.c_char_p, []),
+    "galah_b200_session_finch_distances": (ctypes.c_int, [vp, strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32,
+                                                          ctypes.c_uint8, ctypes.c_int, ctypes.c_int, pairpp, sizep]),
+    "galah_b200_session_finch_distances_contigs": (ctypes.c_int, [vp, strp, ctypes.c_size_t, strp, ctypes.c_size_t, pairpp, sizep]),
+    "galah_b200_session_finch_distances_with_references": (ctypes.c_int, [vp, strp, ctypes.c_size_t, strp, ctypes.c_size_t,
+                                                                          pairpp, sizep]),
+    "galah_b200_session_skani_distances": (ctypes.c_int, [vp, strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
+                                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, pairpp, sizep]),
+    "galah_b200_session_skani_distances_contigs": (ctypes.c_int, [vp, strp, ctypes.c_size_t, strp, ctypes.c_size_t,
+                                                                  ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                                  ctypes.c_int, pairpp, sizep]),
+    "galah_b200_session_skani_distances_with_references": (ctypes.c_int, [vp, strp, ctypes.c_size_t, strp, ctypes.c_size_t,
+                                                                          ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                                                          ctypes.c_int, pairpp, sizep]),
+    "galah_b200_session_calculate_ani": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_float, ctypes.c_int,
+                                                        f32p, ctypes.POINTER(ctypes.c_int)]),
+    "galah_b200_session_stats": (ctypes.c_int, [vp, u64p, u64p, u64p]),
+    "galah_b200_contig_names": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(ctypes.c_char_p)), sizep]),
+    "galah_b200_contig_names_free": (None, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t]),
     "galah_b200_ingest_packed": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, f32p]),
     "galah_b200_ani_index_export_tables": (ctypes.c_int, [vp, vp, u64p, u64p]),
     "galah_b200_ani_index_attach_peer": (ctypes.c_int, [vp, vp, u64p, u64p, ctypes.c_size_t, u32p]),

@@ -233,6 +233,10 @@ class AniIndex:
     def __len__(self):
         return int(lib().galah_b200_ani_index_size(self._h))
 
+    def clear(self):
+        """Forget every genome (and detach peers) but keep the device allocations."""
+        check(lib().galah_b200_ani_index_clear(self._h))
+
     def reserve(self, n_total_genomes):
         """Capacity hint after the first batch: the index will hold n_total_genomes like those added."""
         check(lib().galah_b200_ani_index_reserve(self._h, int(n_total_genomes)))
@@ -337,12 +341,13 @@ def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, s
 
     cb = _native.ANI_FN(_cb) if calculate_ani is not None else _native.ANI_FN()
     res = _native.Clusters()
-    check(lib().galah_b200_cluster_from_distances(int(n_genomes), hits.ctypes.data, len(hits),
-                                                  int(bool(skip_clusterer)), ctypes.c_float(ani_threshold),
-                                                  cb, None, ctypes.byref(res)))
+    rc = lib().galah_b200_cluster_from_distances(int(n_genomes), hits.ctypes.data, len(hits),
+                                                 int(bool(skip_clusterer)), ctypes.c_float(ani_threshold),
+                                                 cb, None, ctypes.byref(res))
     try:
-        if calls["exc"] is not None:
+        if calls["exc"] is not None:  # the callback's own failure comes first: the engine only saw a None
             raise calls["exc"]
+        check(rc)
         off = [res.offsets[x] for x in range(res.n_clusters + 1)]
         clusters = [[int(res.members[y]) for y in range(off[x], off[x + 1])] for x in range(res.n_clusters)]
         info = {"ani_calls": int(res.ani_calls), "n_preclusters": int(res.n_preclusters),
@@ -588,3 +593,159 @@ def synth_packed_device_ex(seed, index_begin, n, length, family_size, rate_shift
 def synth_packed_device(seed, index_begin, n, length, d_seq2, d_valid, d_base_off, stream=0):
     check(lib().galah_b200_synth_packed_device(seed, index_begin, n, length, d_seq2, d_valid,
                                                d_base_off, stream))
+
+
+# ------------------------------------------------------------------------------------------------
+# Host-side mirror of the reference's plugin interface (src/lib.rs:29-55, src/finch.rs:4-46,
+# src/skani.rs:12-74, 689-716, src/clusterer.rs:14-21): same names, argument meaning and error
+# behaviour, over the session entry points of the C ABI.  `cluster_with` below drives them in the
+# order the reference's cluster() does, so the parity tests read like the reference's own tests.
+# ------------------------------------------------------------------------------------------------
+class Session:
+    """State shared by the two trait objects of one cluster() call (include/galah_b200.h)."""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        check(lib().galah_b200_session_create(ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().galah_b200_session_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        a, b, c = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(lib().galah_b200_session_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"n_indexed": a.value, "n_pairs_computed": b.value, "n_launches": c.value}
+
+
+def _session_pairs(fn, *args):
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    check(fn(*args, ctypes.byref(out), ctypes.byref(n_out)))
+    return _take_pairs(out, n_out)
+
+
+class FinchPreclusterer:
+    """galah::finch::FinchPreclusterer { min_ani (FRACTION), num_kmers, kmer_length, low_memory }."""
+
+    def __init__(self, min_ani=0.9, num_kmers=1000, kmer_length=21, low_memory=False, session=None, threads=0):
+        self.min_ani, self.num_kmers, self.kmer_length, self.low_memory = min_ani, num_kmers, kmer_length, low_memory
+        self.session, self.threads = session or Session(), threads
+
+    def method_name(self):
+        return lib().galah_b200_finch_method_name().decode()
+
+    def distances(self, genome_fasta_paths):
+        return _session_pairs(lib().galah_b200_session_finch_distances, self.session._h, _paths_array(genome_fasta_paths),
+                              len(genome_fasta_paths), ctypes.c_float(self.min_ani), self.num_kmers, self.kmer_length,
+                              int(bool(self.low_memory)), self.threads)
+
+    def distances_contigs(self, genome_fasta_paths, contig_names):
+        return _session_pairs(lib().galah_b200_session_finch_distances_contigs, self.session._h,
+                              _paths_array(genome_fasta_paths), len(genome_fasta_paths), _paths_array(contig_names),
+                              len(contig_names))
+
+    def distances_with_references(self, genome_fasta_paths, reference_genomes):
+        return _session_pairs(lib().galah_b200_session_finch_distances_with_references, self.session._h,
+                              _paths_array(genome_fasta_paths), len(genome_fasta_paths), _paths_array(reference_genomes),
+                              len(reference_genomes))
+
+
+class SkaniPreclusterer:
+    """galah::skani::SkaniPreclusterer { threshold (PERCENT), min_aligned_threshold (FRACTION),
+    small_genomes, threads, low_memory }."""
+
+    def __init__(self, threshold=90.0, min_aligned_threshold=0.15, small_genomes=False, threads=0, low_memory=False,
+                 session=None):
+        self.threshold, self.min_aligned_threshold = threshold, min_aligned_threshold
+        self.small_genomes, self.threads, self.low_memory = small_genomes, threads, low_memory
+        self.session = session or Session()
+
+    def method_name(self):
+        return lib().galah_b200_skani_method_name().decode()
+
+    def distances(self, genome_fasta_paths):
+        return _session_pairs(lib().galah_b200_session_skani_distances, self.session._h, _paths_array(genome_fasta_paths),
+                              len(genome_fasta_paths), ctypes.c_float(self.threshold),
+                              ctypes.c_float(self.min_aligned_threshold), int(bool(self.small_genomes)),
+                              int(bool(self.low_memory)), self.threads)
+
+    def distances_contigs(self, genome_fasta_paths, contig_names):
+        return _session_pairs(lib().galah_b200_session_skani_distances_contigs, self.session._h,
+                              _paths_array(genome_fasta_paths), len(genome_fasta_paths), _paths_array(contig_names),
+                              len(contig_names), ctypes.c_float(self.threshold), ctypes.c_float(self.min_aligned_threshold),
+                              int(bool(self.small_genomes)), self.threads)
+
+    def distances_with_references(self, genome_fasta_paths, reference_genomes):
+        return _session_pairs(lib().galah_b200_session_skani_distances_with_references, self.session._h,
+                              _paths_array(genome_fasta_paths), len(genome_fasta_paths), _paths_array(reference_genomes),
+                              len(reference_genomes), ctypes.c_float(self.threshold),
+                              ctypes.c_float(self.min_aligned_threshold), int(bool(self.small_genomes)), self.threads)
+
+
+class SkaniClusterer:
+    """galah::skani::SkaniClusterer { threshold (PERCENT), min_aligned_threshold (FRACTION), small_genomes }."""
+
+    def __init__(self, threshold=95.0, min_aligned_threshold=0.15, small_genomes=False, session=None):
+        self.threshold, self.min_aligned_threshold, self.small_genomes = threshold, min_aligned_threshold, small_genomes
+        self.session = session or Session()
+
+    def initialise(self):
+        if not self.threshold > 1.0:  # assert!(self.threshold > 1.0), src/skani.rs:696-698
+            raise GalahB200Error(-1, "assertion failed: self.threshold > 1.0")
+        check(lib().galah_b200_session_set_clusterer(self.session._h, int(bool(self.small_genomes))))
+
+    def method_name(self):
+        return lib().galah_b200_skani_method_name().decode()
+
+    def get_ani_threshold(self):
+        return self.threshold
+
+    def calculate_ani(self, fasta1, fasta2):
+        ani, some = ctypes.c_float(0), ctypes.c_int(0)
+        check(lib().galah_b200_session_calculate_ani(self.session._h, os.fsencode(fasta1), os.fsencode(fasta2),
+                                                     ctypes.c_float(self.min_aligned_threshold),
+                                                     int(bool(self.small_genomes)), ctypes.byref(ani), ctypes.byref(some)))
+        return float(ani.value) if some.value else None
+
+
+def contig_names(paths):
+    """Record names as `galah cluster --cluster-contigs` collects them (duplicates raise the reference's panic text)."""
+    out = ctypes.POINTER(ctypes.c_char_p)()
+    n = ctypes.c_size_t(0)
+    check(lib().galah_b200_contig_names(_paths_array(paths), len(paths), ctypes.byref(out), ctypes.byref(n)))
+    try:
+        return [out[x].decode() for x in range(n.value)]
+    finally:
+        lib().galah_b200_contig_names_free(out, n.value)
+
+
+def cluster_with(genomes, preclusterer, clusterer, cluster_contigs=False, contig_names=None, reference_genomes=None):
+    """galah::clusterer::cluster(genomes, &preclusterer, &clusterer, cluster_contigs, contig_names,
+    reference_genomes) (src/clusterer.rs:14-152), driving the trait objects above exactly as the
+    reference does: initialise, method names -> skip_clusterer, one distances* call, then the greedy
+    engine calling clusterer.calculate_ani(representative path, genome path)."""
+    clusterer.initialise()
+    pre_name, cl_name = preclusterer.method_name(), clusterer.method_name()
+    skip = cl_name == pre_name
+    if cluster_contigs:
+        if pre_name == "finch":
+            raise GalahB200Error(-1, f"{pre_name} does not support contig comparisons.")  # src/clusterer.rs:39-41
+        skip = True
+    if reference_genomes is not None:
+        cache = preclusterer.distances_with_references(genomes, reference_genomes)
+    elif cluster_contigs:
+        cache = preclusterer.distances_contigs(genomes, contig_names)
+    else:
+        cache = preclusterer.distances(genomes)
+    names = contig_names if cluster_contigs else genomes
+    fn = None if skip else (lambda rep, g: clusterer.calculate_ani(names[rep], names[g]))
+    clusters, info = cluster_from_distances(len(names), cache, clusterer.get_ani_threshold(), fn, skip_clusterer=skip)
+    return clusters, info

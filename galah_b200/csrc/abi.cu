@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -55,7 +56,23 @@ struct Context {
     uint4 *h_cand_map = nullptr;         // zero-copy candidate list of the streamed call (mapped pinned, all-zero between calls)
     size_t cap_cand_map = 0;
     cudaEvent_t ev_done = nullptr;
+    uint32_t *slot_seq2[2] = {nullptr, nullptr}, *slot_valid[2] = {nullptr, nullptr};  // upload slots of ingest_packed
+    uint64_t *slot_off[2] = {nullptr, nullptr};
+    size_t cap_slot_seq2[2] = {0, 0}, cap_slot_valid[2] = {0, 0}, cap_slot_off[2] = {0, 0};
+    AniIndex *pipe_index[2] = {nullptr, nullptr};  // K3 index of the one-call pipelines (c = 125 / 30), re-used across calls
+    AniIndex &pipeline_index(bool small_genomes) {
+        AniIndex *&p = pipe_index[small_genomes ? 1 : 0];
+        if (!p) p = new AniIndex(small_genomes ? 30u : 125u);
+        p->clear();
+        return *p;
+    }
     int release() {
+        for (auto &p : pipe_index) { delete p; p = nullptr; }
+        for (int x = 0; x < 2; x++) {
+            cudaFree(slot_seq2[x]); cudaFree(slot_valid[x]); cudaFree(slot_off[x]);
+            slot_seq2[x] = slot_valid[x] = nullptr; slot_off[x] = nullptr;
+            cap_slot_seq2[x] = cap_slot_valid[x] = cap_slot_off[x] = 0;
+        }
         pws.release(); sws.release(); fasta.release();
         if (h_raw) cudaFreeHost(h_raw);
         h_raw = nullptr; cap_raw = 0;
@@ -355,6 +372,7 @@ struct MarkerTable {
 struct IngestSinks {
     bool sketch = false;
     int k = 21; uint32_t s = 1000; uint64_t seed = 0;
+    uint32_t stride = 0;  // row stride of d_hashes (0: s)
     uint64_t *hashes = nullptr; uint32_t *counts = nullptr;  // host rows, stride s
     uint64_t *d_hashes = nullptr; uint32_t *d_counts = nullptr;  // or DEVICE rows, stride s: no host round trip
     AniIndex *ani = nullptr;
@@ -380,9 +398,9 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
                     size_t unit_first, size_t files_done) -> int {
         if (sinks.sketch && sinks.d_hashes) {
             // K1 writes the rows where K2 will read them (the table never leaves the device)
+            const size_t stride = sinks.stride ? sinks.stride : sinks.s;
             int rc = sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, sinks.k, sinks.s, sinks.seed,
-                                    sinks.d_hashes + unit_first * (size_t)sinks.s, sinks.d_counts + unit_first,
-                                    sinks.s, st);
+                                    sinks.d_hashes + unit_first * stride, sinks.d_counts + unit_first, stride, st);
             if (rc) return rc;
         } else if (sinks.sketch) {
             DevBuf<uint64_t> d_hashes;
@@ -588,9 +606,18 @@ static std::string display_f32(float v) {
 // The skani-style preclusterer once the units are indexed (K3) and their marker table is on the
 // device: marker-containment screen through the K2 join (containment rule), K3 ANI of every
 // screened pair, `ani >= threshold` in f32 (src/skani.rs:205).  ms3 (optional): screen, ANI, total.
+// variant: kSkaniTriangle  -- `skani triangle` (src/skani.rs:109-225): every screened pair, query = lower index;
+//          kSkaniLowMem    -- `skani sketch` + `skani search` of everything against everything
+//                             (src/skani.rs:229-377): both orientations reach the cache under one key and
+//                             the later record wins; at skani's query order that is query = HIGHER index;
+//          kSkaniReferences -- `skani search` of the non-references against the sketched references
+//                             (src/skani.rs:502-687): only pairs with exactly one reference (is_ref),
+//                             query = the non-reference genome.
+enum SkaniVariant { kSkaniTriangle = 0, kSkaniLowMem = 1, kSkaniReferences = 2 };
 static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const uint32_t *d_counts, size_t n_units,
                                 size_t stride, float threshold_pct, float min_af_pct, bool individual_contigs,
-                                cudaStream_t st, std::vector<galah_b200_pair_t> &out, uint64_t &n_screened, float *ms3) {
+                                cudaStream_t st, std::vector<galah_b200_pair_t> &out, uint64_t &n_screened, float *ms3,
+                                SkaniVariant variant = kSkaniTriangle, const std::vector<uint8_t> *is_ref = nullptr) {
     const double t_begin = now_ms();
     if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
     const double frac = pow(0.80, 21.0);  // marker containment of a pair at ~80 % identity
@@ -615,9 +642,20 @@ static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const 
     }
     const double t_screen = now_ms();
     std::sort(cand.begin(), cand.end(), [](const uint4 &a, const uint4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    if (variant == kSkaniReferences) {
+        size_t keep = 0;
+        for (size_t x = 0; x < cand.size(); x++)
+            if ((*is_ref)[cand[x].x] != (*is_ref)[cand[x].y]) cand[keep++] = cand[x];
+        cand.resize(keep);
+    }
     n_screened = cand.size();
     std::vector<uint32_t> pairs(2 * cand.size());
-    for (size_t x = 0; x < cand.size(); x++) { pairs[2 * x] = cand[x].x; pairs[2 * x + 1] = cand[x].y; }
+    for (size_t x = 0; x < cand.size(); x++) {
+        bool q_is_j = variant == kSkaniLowMem;
+        if (variant == kSkaniReferences) q_is_j = (*is_ref)[cand[x].x] != 0;  // the query is the non-reference
+        pairs[2 * x] = q_is_j ? cand[x].y : cand[x].x;
+        pairs[2 * x + 1] = q_is_j ? cand[x].x : cand[x].y;
+    }
     std::vector<AniPairResult> res(cand.size());
     if (int rc = index.pairs(pairs.data(), cand.size(), min_af_pct, individual_contigs, res.data(), st)) return rc;
     out.clear();
@@ -630,9 +668,18 @@ static int skani_screen_and_ani(AniIndex &index, const uint64_t *d_table, const 
 
 static int skani_distances_impl(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
                                 bool small_genomes, bool per_record, int host_threads,
-                                std::vector<galah_b200_pair_t> &out, size_t &n_units, uint64_t &n_screened) {
+                                std::vector<galah_b200_pair_t> &out, size_t &n_units, uint64_t &n_screened,
+                                SkaniVariant variant = kSkaniTriangle, const std::vector<uint8_t> *is_ref = nullptr) {
     if (threshold_pct < 85.0f) {
         set_error("Error: skani produces inaccurate results with ANI less than 85%. Provided: " + display_f32(threshold_pct));
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    if (small_genomes && variant == kSkaniLowMem) {  // src/skani.rs:243-245
+        set_error("Error: skani does not support small genomes with low-memory preclustering");
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    if (small_genomes && variant == kSkaniReferences) {  // src/skani.rs:518-520
+        set_error("Error: skani does not support small genomes with reference genome preclustering");
         return GALAH_B200_ERR_UNSUPPORTED;
     }
     AniIndex index(small_genomes ? 30u : 125u);
@@ -646,7 +693,7 @@ static int skani_distances_impl(const char *const *paths, size_t n, float thresh
     if (n_units < 2) return 0;
     if (markers.n != n_units) { set_error("skani preclusterer: marker table out of step with the units"); return GALAH_B200_ERR_ARG; }
     return skani_screen_and_ani(index, markers.d_rows, markers.d_counts, n_units, markers.stride, threshold_pct,
-                                min_af_pct, per_record, g_ctx.stream, out, n_screened, nullptr);
+                                min_af_pct, per_record, g_ctx.stream, out, n_screened, nullptr, variant, is_ref);
 }
 
 }  // namespace gb200
@@ -866,7 +913,8 @@ int galah_b200_prefilter_shard(const uint64_t *hashes, const uint32_t *counts, s
     cudaStream_t st = g_ctx.stream;
     // whole-table single-shard join: pipeline the upload against the kernels (slices of whole blocks)
     const bool streamed = g_ctx.prefilter_mode == 0 && n_shards == 1 && g_ctx.stream_chunks > 1 &&
-                          join_supported(stride) && n >= 4 * (size_t)kShardRows;
+                          join_supported(stride) && n >= 64 * (size_t)kShardRows;  // smaller tables: one copy, and the
+                          // device path's guard against a tie-dense launch of few items applies
     if (n) {
         GB_CUDA(cudaMemcpyAsync(g_ctx.d_counts, counts, n * 4, cudaMemcpyHostToDevice, st));
         if (!streamed) GB_CUDA(cudaMemcpyAsync(g_ctx.d_table, hashes, n * stride * 8, cudaMemcpyHostToDevice, st));
@@ -895,17 +943,31 @@ int galah_b200_prefilter_last_host_timing(float *ms4) {
     return 0;
 }
 
+// finch::distances (src/finch.rs:48-97): K1 writes the sketch rows where K2 reads them (the table
+// never visits the host); any num_kmers (the row stride is rounded up to even for alignment, rows
+// hold at most num_kmers hashes).  ani (optional): the same ingest also builds the K3 index.
+static int finch_distances_locked(const char *const *paths, size_t n, float min_ani, uint32_t num_kmers,
+                                  uint8_t kmer_length, int host_threads, AniIndex *ani, galah_b200_pair_t **out,
+                                  size_t *n_out) {
+    *out = nullptr; *n_out = 0;
+    if (num_kmers == 0) { set_error("finch_distances: num_kmers must be > 0"); return GALAH_B200_ERR_ARG; }
+    const uint32_t stride = num_kmers + (num_kmers & 1);
+    if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, std::max<size_t>(n, 1) * stride) ||
+        ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
+        return GALAH_B200_ERR_CUDA;
+    IngestSinks sinks;
+    sinks.sketch = true; sinks.k = kmer_length; sinks.s = num_kmers; sinks.stride = stride; sinks.seed = 0;
+    sinks.d_hashes = g_ctx.d_table; sinks.d_counts = g_ctx.d_counts; sinks.ani = ani;
+    if (int rc = ingest_files(paths, n, host_threads, sinks)) return rc;
+    return run_prefilter(g_ctx.d_table, g_ctx.d_counts, n, stride, kmer_length, min_ani, 0, 1, g_ctx.stream, out, n_out);
+}
+
 int galah_b200_finch_distances(const char *const *paths, size_t n, float min_ani, uint32_t num_kmers,
                                uint8_t kmer_length, int host_threads, galah_b200_pair_t **out,
                                size_t *n_out) {
-    *out = nullptr; *n_out = 0;
-    const uint32_t s = num_kmers + (num_kmers & 1);  // even row stride; rows hold <= num_kmers
-    std::vector<uint64_t> hashes((size_t)n * s);
-    std::vector<uint32_t> counts(n);
-    if (num_kmers & 1) { set_error("finch_distances: odd num_kmers not supported yet"); return GALAH_B200_ERR_UNSUPPORTED; }
-    int rc = galah_b200_sketch_files(paths, n, kmer_length, s, 0, host_threads, hashes.data(), counts.data());
-    if (rc) return rc;
-    return galah_b200_prefilter(hashes.data(), counts.data(), n, s, kmer_length, min_ani, out, n_out);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    return finch_distances_locked(paths, n, min_ani, num_kmers, kmer_length, host_threads, nullptr, out, n_out);
 }
 
 struct galah_b200_ani_index { gb200::AniIndex impl; explicit galah_b200_ani_index(uint32_t c) : impl(c) {} };
@@ -1026,6 +1088,14 @@ int galah_b200_ani_pairs(galah_b200_ani_index_t *idx, const uint32_t *pairs, siz
     if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
     static_assert(sizeof(galah_b200_ani_result_t) == sizeof(AniPairResult), "result layout");
     return idx->impl.pairs(pairs, n_pairs, min_af_pct, individual_contigs != 0, reinterpret_cast<AniPairResult *>(results), g_ctx.stream);
+}
+
+int galah_b200_ani_index_clear(galah_b200_ani_index_t *idx) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx) { set_error("ani index: NULL index"); return GALAH_B200_ERR_ARG; }
+    idx->impl.clear();
+    return 0;
 }
 
 int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_ms, float *chain_ms) {
@@ -1191,7 +1261,7 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
     if (int rc = require_ctx()) return rc;
     const double t_begin = now_ms();
     const uint32_t s = 1000;
-    AniIndex index(small_genomes ? 30u : 125u);
+    AniIndex &index = g_ctx.pipeline_index(small_genomes != 0);
     // the sketch table is written by K1 where K2 reads it: it never visits the host
     if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, std::max<size_t>(n, 1) * s) ||
         ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
@@ -1228,8 +1298,9 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
     }
     const size_t n_batches = cut.size() - 1;
     // host input: two staging slots on the device, filled on the copy stream
+    // (the slots live in the context and only ever grow: no cudaMalloc / cudaFree per call)
     struct Slot { uint32_t *seq2 = nullptr, *valid = nullptr; uint64_t *off = nullptr; cudaEvent_t landed = nullptr, freed = nullptr; } slot[2];
-    struct SlotGuard { Slot *s; ~SlotGuard() { for (int x = 0; x < 2; x++) { cudaFree(s[x].seq2); cudaFree(s[x].valid); cudaFree(s[x].off);
+    struct SlotGuard { Slot *s; ~SlotGuard() { for (int x = 0; x < 2; x++) {
                        if (s[x].landed) cudaEventDestroy(s[x].landed); if (s[x].freed) cudaEventDestroy(s[x].freed); } } } slot_guard{slot};
     uint64_t max_bases = 0; size_t max_n = 0;
     for (size_t b = 0; b < n_batches; b++) {
@@ -1239,9 +1310,11 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
     if (!device) {
         if (!g_ctx.copy_stream) GB_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
         for (int x = 0; x < 2; x++) {
-            GB_CUDA(cudaMalloc(&slot[x].seq2, (max_bases / 16 + 8) * 4));
-            GB_CUDA(cudaMalloc(&slot[x].valid, (max_bases / 32 + 8) * 4));
-            GB_CUDA(cudaMalloc(&slot[x].off, (max_n + 1) * 8));
+            if (ws_ensure(g_ctx.slot_seq2[x], g_ctx.cap_slot_seq2[x], max_bases / 16 + 8) ||
+                ws_ensure(g_ctx.slot_valid[x], g_ctx.cap_slot_valid[x], max_bases / 32 + 8) ||
+                ws_ensure(g_ctx.slot_off[x], g_ctx.cap_slot_off[x], max_n + 1))
+                return GALAH_B200_ERR_CUDA;
+            slot[x].seq2 = g_ctx.slot_seq2[x]; slot[x].valid = g_ctx.slot_valid[x]; slot[x].off = g_ctx.slot_off[x];
             GB_CUDA(cudaEventCreateWithFlags(&slot[x].landed, cudaEventDisableTiming));
             GB_CUDA(cudaEventCreateWithFlags(&slot[x].freed, cudaEventDisableTiming));
         }
@@ -1316,7 +1389,7 @@ static int cluster_packed(const uint32_t *seq2, const uint32_t *valid, const uin
     std::lock_guard<std::mutex> lock(g_mu);
     if (int rc = require_ctx()) return rc;
     const double t_begin = now_ms();
-    AniIndex index(small_genomes ? 30u : 125u);
+    AniIndex &index = g_ctx.pipeline_index(small_genomes != 0);
     if (ws_ensure(g_ctx.d_table, g_ctx.cap_table, std::max<size_t>(n, 1) * 1000) ||
         ws_ensure(g_ctx.d_counts, g_ctx.cap_counts, std::max<size_t>(n, 1)))
         return GALAH_B200_ERR_CUDA;
@@ -1480,6 +1553,348 @@ int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float pre
     int rc = galah_b200_cluster_from_distances(n_units, hits, n_hits, 1, ani_threshold_pct, nullptr, nullptr, out);
     if (stats) { stats->n_precluster_hits = n_hits; stats->n_ani_pairs = n_hits; }
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Trait-shaped boundary: what an UNMODIFIED galah::clusterer::cluster() calls, in the order it
+// calls it (src/clusterer.rs:14-152): preclusterer.distances*(paths) once on the caller's thread,
+// then clusterer.calculate_ani(fasta1, fasta2) from nested rayon workers (src/clusterer.rs:262-296,
+// 375).  A session carries what the two halves must share: the paths and hit list of the last
+// distances call (so that the first calculate_ani can evaluate EVERY hit in one K3 launch), the
+// resident K3 index keyed by path, and the cache of computed values.  calculate_ani is re-entrant:
+// hits of the cache take a shared lock only.
+// ------------------------------------------------------------------------------------------
+}  // extern "C"
+
+#include <shared_mutex>
+#include <unordered_map>
+
+struct galah_b200_session {
+    std::shared_mutex mu;                 // guards everything below; lookups take it shared
+    std::unordered_map<std::string, uint32_t> path_id;  // FASTA path -> genome id in `index`
+    std::unique_ptr<gb200::AniIndex> index;
+    bool small_genomes = false;
+    float min_af_pct = -1.f;              // the cache holds values for this --min-af only
+    std::unordered_map<uint64_t, float> cache;  // (query id << 32 | reference id) -> ANI as galah parses it
+    std::vector<std::string> stash_paths;       // genomes of the last distances() call ...
+    std::vector<galah_b200_pair_t> stash_hits;  // ... and its hit list, not yet evaluated by K3
+    bool hint = false; bool hint_small = false; // clusterer configuration announced ahead of distances()
+    uint64_t n_calls = 0, n_lookups = 0, n_pairs_computed = 0, n_launches = 0;
+};
+
+namespace {
+using gb200::set_error;
+
+// Adds the paths that are not indexed yet (one ingest pass), assigns ids.  Caller: exclusive lock + g_mu.
+int session_index_paths(galah_b200_session *s, const std::vector<std::string> &paths, int host_threads) {
+    std::vector<const char *> missing;
+    std::vector<std::string> keep;
+    for (const auto &p : paths)
+        if (!s->path_id.count(p) && std::find(keep.begin(), keep.end(), p) == keep.end()) keep.push_back(p);
+    if (keep.empty()) return 0;
+    for (const auto &p : keep) missing.push_back(p.c_str());
+    if (!s->index) s->index.reset(new gb200::AniIndex(s->small_genomes ? 30u : 125u));
+    const size_t before = s->index->size();
+    gb200::IngestSinks sinks;
+    sinks.ani = s->index.get();
+    if (int rc = gb200::ingest_files(missing.data(), missing.size(), host_threads, sinks)) return rc;
+    if (s->index->size() != before + keep.size()) { set_error("session: index out of step with the paths"); return GALAH_B200_ERR_ARG; }
+    for (size_t x = 0; x < keep.size(); x++) s->path_id[keep[x]] = (uint32_t)(before + x);
+    return 0;
+}
+
+// Evaluates (query, reference) id pairs that are not cached yet, in one K3 launch.
+int session_compute(galah_b200_session *s, std::vector<uint32_t> &pairs) {
+    std::vector<uint32_t> todo;
+    for (size_t x = 0; x + 1 < pairs.size(); x += 2)
+        if (!s->cache.count(((uint64_t)pairs[x] << 32) | pairs[x + 1])) { todo.push_back(pairs[x]); todo.push_back(pairs[x + 1]); }
+    if (todo.empty()) return 0;
+    std::vector<gb200::AniPairResult> res(todo.size() / 2);
+    if (int rc = s->index->pairs(todo.data(), todo.size() / 2, s->min_af_pct, false, res.data(), gb200::g_ctx.stream)) return rc;
+    for (size_t x = 0; x < res.size(); x++) s->cache[((uint64_t)todo[2 * x] << 32) | todo[2 * x + 1]] = res[x].ani;
+    s->n_pairs_computed += res.size(); s->n_launches++;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int galah_b200_session_create(galah_b200_session_t **out) {
+    if (!out) { set_error("session: out is NULL"); return GALAH_B200_ERR_ARG; }
+    *out = new galah_b200_session();
+    return 0;
+}
+
+void galah_b200_session_free(galah_b200_session_t *s) {
+    if (!s) return;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (g_ctx.device >= 0) cudaSetDevice(g_ctx.device);
+        s->index.reset();
+    }
+    delete s;
+}
+
+int galah_b200_session_set_clusterer(galah_b200_session_t *s, int small_genomes) {
+    if (!s) { set_error("session: NULL session"); return GALAH_B200_ERR_ARG; }
+    std::unique_lock<std::shared_mutex> lk(s->mu);
+    s->hint = true; s->hint_small = small_genomes != 0;
+    return 0;
+}
+
+const char *galah_b200_finch_method_name(void) { return "finch"; }
+const char *galah_b200_skani_method_name(void) { return "skani"; }
+
+int galah_b200_session_finch_distances(galah_b200_session_t *s, const char *const *paths, size_t n, float min_ani,
+                                       uint32_t num_kmers, uint8_t kmer_length, int low_memory, int host_threads,
+                                       galah_b200_pair_t **out, size_t *n_out) {
+    if (!s || !out || !n_out) { set_error("session: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    if (low_memory) {  // src/finch.rs:14-15
+        set_error("Low-memory clustering currently only supported with skani preclusterer");
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    std::unique_lock<std::shared_mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    // with the clusterer announced, the same ingest pass builds the K3 index of every genome that is
+    // not resident yet (all of them, on a fresh session)
+    gb200::AniIndex *ani = nullptr;
+    bool fresh = false;
+    if (s->hint) {
+        if (s->index && s->small_genomes != s->hint_small) { s->index.reset(); s->path_id.clear(); s->cache.clear(); }
+        s->small_genomes = s->hint_small;
+        fresh = s->path_id.empty();
+        if (fresh) {
+            std::vector<std::string> uniq(paths, paths + n);
+            std::sort(uniq.begin(), uniq.end());
+            fresh = std::adjacent_find(uniq.begin(), uniq.end()) == uniq.end();  // duplicate paths: index lazily instead
+        }
+        if (fresh) { s->index.reset(new gb200::AniIndex(s->small_genomes ? 30u : 125u)); ani = s->index.get(); }
+    }
+    if (int rc = finch_distances_locked(paths, n, min_ani, num_kmers, kmer_length, host_threads, ani, out, n_out)) {
+        if (fresh) s->index.reset();
+        return rc;
+    }
+    if (fresh) for (size_t g = 0; g < n; g++) s->path_id[paths[g]] = (uint32_t)g;
+    s->stash_paths.assign(paths, paths + n);
+    s->stash_hits.assign(*out, *out + *n_out);
+    return 0;
+}
+
+int galah_b200_session_finch_distances_contigs(galah_b200_session_t *s, const char *const *paths, size_t n,
+                                               const char *const *contig_names, size_t n_names,
+                                               galah_b200_pair_t **out, size_t *n_out) {
+    (void)s; (void)paths; (void)n; (void)contig_names; (void)n_names;
+    // "Finch doesn't offer high-quality ANI with self-self comparisons": an empty cache (src/finch.rs:26-33)
+    if (!out || !n_out) { set_error("session: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = (galah_b200_pair_t *)malloc(sizeof(galah_b200_pair_t));
+    *n_out = 0;
+    return 0;
+}
+
+int galah_b200_session_finch_distances_with_references(galah_b200_session_t *s, const char *const *paths, size_t n,
+                                                       const char *const *reference_paths, size_t n_refs,
+                                                       galah_b200_pair_t **out, size_t *n_out) {
+    (void)s; (void)paths; (void)n; (void)reference_paths; (void)n_refs;
+    if (out) *out = nullptr;
+    if (n_out) *n_out = 0;
+    set_error("Reference genome clustering currently only supported with skani preclusterer");  // src/finch.rs:40
+    return GALAH_B200_ERR_UNSUPPORTED;
+}
+
+static int take_hits(const std::vector<galah_b200_pair_t> &hits, galah_b200_pair_t **out, size_t *n_out) {
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(hits.size(), 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!hits.empty()) memcpy(res, hits.data(), hits.size() * sizeof(galah_b200_pair_t));
+    *out = res; *n_out = hits.size();
+    return 0;
+}
+
+int galah_b200_session_skani_distances(galah_b200_session_t *s, const char *const *paths, size_t n, float threshold_pct,
+                                       float min_aligned_threshold, int small_genomes, int low_memory,
+                                       int host_threads, galah_b200_pair_t **out, size_t *n_out) {
+    if (!s || !out || !n_out) { set_error("session: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    std::unique_lock<std::shared_mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    std::vector<galah_b200_pair_t> hits;
+    size_t units = 0; uint64_t screened = 0;
+    const float min_af_pct = min_aligned_threshold * 100.0f;  // `min_aligned_threshold * 100.0` in f32, src/skani.rs:153
+    if (int rc = skani_distances_impl(paths, n, threshold_pct, min_af_pct, small_genomes != 0, false, host_threads, hits,
+                                      units, screened, low_memory ? kSkaniLowMem : kSkaniTriangle))
+        return rc;
+    s->stash_paths.clear(); s->stash_hits.clear();  // same method name on both sides: cluster() re-uses these values
+    return take_hits(hits, out, n_out);
+}
+
+// Names of the records of a FASTA / FASTQ file as galah reads them for --cluster-contigs: the
+// header line up to the first TAB (src/cluster_argument_parsing.rs:606-621).
+static int record_names(const std::string &path, std::vector<std::string> &names) {
+    std::vector<uint8_t> raw;
+    std::string err;
+    if (read_file_bytes(path, raw, err)) { set_error(err); return GALAH_B200_ERR_IO; }
+    size_t p = 0;
+    const bool fastq = !raw.empty() && raw[0] == '@';
+    size_t line_no = 0;
+    while (p < raw.size()) {
+        size_t e = p;
+        while (e < raw.size() && raw[e] != '\n') e++;
+        const bool header = fastq ? (line_no % 4 == 0) : (raw[p] == '>');
+        if (header) {
+            size_t end = e;
+            if (end > p && raw[end - 1] == '\r') end--;
+            std::string name((const char *)raw.data() + p + 1, end - p - 1);
+            const size_t tab = name.find('\t');
+            if (tab != std::string::npos) name.resize(tab);
+            names.push_back(name);
+        }
+        if (e > p || fastq) line_no++;
+        p = e + 1;
+    }
+    return 0;
+}
+
+int galah_b200_contig_names(const char *const *paths, size_t n, char ***names_out, size_t *n_names) {
+    if (!names_out || !n_names) { set_error("contig_names: NULL argument"); return GALAH_B200_ERR_ARG; }
+    std::vector<std::string> all;
+    for (size_t f = 0; f < n; f++) {
+        std::vector<std::string> names;
+        if (int rc = record_names(paths[f], names)) return rc;
+        for (auto &nm : names) {
+            if (std::find(all.begin(), all.end(), nm) != all.end()) {  // src/cluster_argument_parsing.rs:622-627
+                set_error(std::string("Duplicate contig name found in file '") + paths[f] + "': " + nm);
+                return GALAH_B200_ERR_UNSUPPORTED;
+            }
+            all.push_back(nm);
+        }
+    }
+    char **res = (char **)malloc(std::max<size_t>(all.size(), 1) * sizeof(char *));
+    for (size_t x = 0; x < all.size(); x++) res[x] = strdup(all[x].c_str());
+    *names_out = res; *n_names = all.size();
+    return 0;
+}
+
+void galah_b200_contig_names_free(char **names, size_t n) {
+    if (!names) return;
+    for (size_t x = 0; x < n; x++) free(names[x]);
+    free(names);
+}
+
+int galah_b200_session_skani_distances_contigs(galah_b200_session_t *s, const char *const *paths, size_t n,
+                                               const char *const *contig_names, size_t n_names, float threshold_pct,
+                                               float min_aligned_threshold, int small_genomes, int host_threads,
+                                               galah_b200_pair_t **out, size_t *n_out) {
+    if (!s || !out || !n_out) { set_error("session: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    // the reference maps skani's Ref_name / Query_name columns back to positions in contig_names
+    // (src/skani.rs:460-474, tabs sanitised): unit u of the device path is record u in file order,
+    // so the names of the records are checked against contig_names first
+    std::vector<std::string> recs;
+    for (size_t f = 0; f < n; f++) if (int rc = record_names(paths[f], recs)) return rc;
+    std::unordered_map<std::string, uint32_t> pos;
+    for (size_t x = 0; x < n_names; x++) {
+        std::string nm(contig_names[x]);
+        for (auto &ch : nm) if (ch == '\t') ch = ' ';
+        if (!pos.count(nm)) pos[nm] = (uint32_t)x;  // `position()` finds the first occurrence
+    }
+    std::vector<uint32_t> unit_to_name(recs.size());
+    for (size_t u = 0; u < recs.size(); u++) {
+        std::string nm = recs[u];
+        for (auto &ch : nm) if (ch == '\t') ch = ' ';
+        auto it = pos.find(nm);
+        if (it == pos.end()) { set_error("Failed to find contig name in contig_names: " + recs[u]); return GALAH_B200_ERR_UNSUPPORTED; }
+        unit_to_name[u] = it->second;
+    }
+    std::unique_lock<std::shared_mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    std::vector<galah_b200_pair_t> hits;
+    size_t units = 0; uint64_t screened = 0;
+    const float min_af_pct = min_aligned_threshold * 100.0f;
+    if (int rc = skani_distances_impl(paths, n, threshold_pct, min_af_pct, small_genomes != 0, true, host_threads, hits,
+                                      units, screened))
+        return rc;
+    if (units != recs.size()) { set_error("contig mode: the device path saw a different number of records than the header scan"); return GALAH_B200_ERR_ARG; }
+    for (auto &h : hits) {
+        const uint32_t a = unit_to_name[h.i], b = unit_to_name[h.j];
+        h.i = std::min(a, b); h.j = std::max(a, b);
+    }
+    std::sort(hits.begin(), hits.end(), [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    s->stash_paths.clear(); s->stash_hits.clear();
+    return take_hits(hits, out, n_out);
+}
+
+int galah_b200_session_skani_distances_with_references(galah_b200_session_t *s, const char *const *combined_paths,
+                                                       size_t n, const char *const *reference_paths, size_t n_refs,
+                                                       float threshold_pct, float min_aligned_threshold,
+                                                       int small_genomes, int host_threads, galah_b200_pair_t **out,
+                                                       size_t *n_out) {
+    if (!s || !out || !n_out) { set_error("session: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    std::vector<uint8_t> is_ref(n, 0);
+    for (size_t g = 0; g < n; g++)
+        for (size_t r = 0; r < n_refs; r++)
+            if (strcmp(combined_paths[g], reference_paths[r]) == 0) { is_ref[g] = 1; break; }
+    std::unique_lock<std::shared_mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    std::vector<galah_b200_pair_t> hits;
+    size_t units = 0; uint64_t screened = 0;
+    const float min_af_pct = min_aligned_threshold * 100.0f;
+    if (int rc = skani_distances_impl(combined_paths, n, threshold_pct, min_af_pct, small_genomes != 0, false, host_threads,
+                                      hits, units, screened, kSkaniReferences, &is_ref))
+        return rc;
+    s->stash_paths.clear(); s->stash_hits.clear();
+    return take_hits(hits, out, n_out);
+}
+
+int galah_b200_session_calculate_ani(galah_b200_session_t *s, const char *fasta1, const char *fasta2,
+                                     float min_aligned_threshold, int small_genomes, float *ani, int *is_some) {
+    if (!s || !fasta1 || !fasta2 || !ani) { set_error("session: NULL argument"); return GALAH_B200_ERR_ARG; }
+    const float min_af_pct = min_aligned_threshold * 100.0f;  // src/skani.rs:731-733
+    if (is_some) *is_some = 1;  // SkaniClusterer always answers Some (src/skani.rs:708-715)
+    const std::string p1(fasta1), p2(fasta2);
+    {
+        std::shared_lock<std::shared_mutex> lk(s->mu);
+        if (s->index && s->small_genomes == (small_genomes != 0) && s->min_af_pct == min_af_pct) {
+            auto a = s->path_id.find(p1), b = s->path_id.find(p2);
+            if (a != s->path_id.end() && b != s->path_id.end()) {
+                auto c = s->cache.find(((uint64_t)a->second << 32) | b->second);
+                if (c != s->cache.end()) { *ani = c->second; return 0; }
+            }
+        }
+    }
+    std::unique_lock<std::shared_mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    s->n_calls++;
+    if (s->index && s->small_genomes != (small_genomes != 0)) { s->index.reset(); s->path_id.clear(); s->cache.clear(); }
+    if (s->min_af_pct != min_af_pct) s->cache.clear();
+    s->small_genomes = small_genomes != 0; s->min_af_pct = min_af_pct;
+    // genomes of the stashed distances() call are indexed together with the two asked for
+    std::vector<std::string> need = s->stash_paths;
+    need.push_back(p1); need.push_back(p2);
+    if (int rc = session_index_paths(s, need, 0)) return rc;
+    std::vector<uint32_t> pairs;
+    for (const auto &h : s->stash_hits) {  // every hit of the preclusterer, query = the lower index (the representative)
+        pairs.push_back(s->path_id[s->stash_paths[h.i]]); pairs.push_back(s->path_id[s->stash_paths[h.j]]);
+    }
+    s->stash_hits.clear(); s->stash_paths.clear();
+    pairs.push_back(s->path_id[p1]); pairs.push_back(s->path_id[p2]);
+    if (int rc = session_compute(s, pairs)) return rc;
+    *ani = s->cache[((uint64_t)s->path_id[p1] << 32) | s->path_id[p2]];
+    return 0;
+}
+
+int galah_b200_session_stats(galah_b200_session_t *s, uint64_t *n_indexed, uint64_t *n_pairs_computed, uint64_t *n_launches) {
+    if (!s) { set_error("session: NULL session"); return GALAH_B200_ERR_ARG; }
+    std::shared_lock<std::shared_mutex> lk(s->mu);
+    if (n_indexed) *n_indexed = s->index ? s->index->size() : 0;
+    if (n_pairs_computed) *n_pairs_computed = s->n_pairs_computed;
+    if (n_launches) *n_launches = s->n_launches;
+    return 0;
 }
 
 void galah_b200_clusters_free(galah_b200_clusters_t *c) {

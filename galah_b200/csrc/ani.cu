@@ -567,6 +567,15 @@ int AniIndex::attach_peer(const cudaIpcMemHandle_t &handle, const uint64_t *tabl
     return 0;
 }
 
+void AniIndex::clear() {
+    for (auto &pg : peers_) cudaIpcCloseMemHandle((void *)pg.base);
+    peers_.clear(); peer_first_.assign(1, 0); peer_total_len_.clear();
+    seed_off_.assign(1, 0); cso_off_.assign(1, 0); table_off_.assign(1, 0);
+    total_len_.clear(); n_chunks_.clear();
+    d_kq_.n = d_cso_.n = d_table_.n = 0;
+    d_seed_off_.n = d_cso_off_.n = d_table_off_.n = d_n_chunks_.n = 0;
+}
+
 AniIndex::~AniIndex() {
     for (auto &pg : peers_) cudaIpcCloseMemHandle((void *)pg.base);
     d_kq_.release(); d_cso_.release(); d_table_.release();

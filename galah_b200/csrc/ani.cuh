@@ -67,6 +67,9 @@ public:
                           const std::vector<uint64_t> &contig_off, const std::vector<uint32_t> &contig_start,
                           const std::vector<uint32_t> &contig_len, cudaStream_t st);
     int reserve_for(size_t n_total, cudaStream_t st);
+    // Forgets every genome (and detaches the peers) but keeps the device allocations: a caller that
+    // re-indexes the same workload per call pays no cudaMalloc / cudaFree (device-wide synchronisations).
+    void clear();
     // pairs: (query, reference) genome ids -- the query is the FIRST id.  individual_contigs: the call
     // stands for `skani triangle -i` (contig clustering), where skani never applies its learned ANI.
     int pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, bool individual_contigs, AniPairResult *out,

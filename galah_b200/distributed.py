@@ -155,6 +155,12 @@ class ShardedPrefilter:
         if self.ring:
             self._init_ring()
 
+    def _grow_candidates(self, need):
+        t = self.torch
+        self.cand_cap = int(need) + (int(need) >> 2) + 1024
+        self.d_cand = t.empty((self.cand_cap, 4), dtype=t.int32, device=self.dev)
+        self.h_cand = t.empty((self.cand_cap, 4), dtype=t.int32).pin_memory()
+
     def _init_ring(self):
         """Per round k the explicit item list (rb, cb) this rank joins once peer (rank - k)'s lists are
         resident; round 0 = the items inside its own slice (diagonal items first: they take longest)."""
@@ -257,8 +263,10 @@ class ShardedPrefilter:
         self.my_counts.copy_(h_counts, non_blocking=True)
         self.step_device(k, min_ani)
         got = int(self.d_ncand.item())  # D2H + sync
-        if got > self.cand_cap:
-            raise RuntimeError("candidate buffer too small")
+        if got > self.cand_cap:  # grow and run again (as the single-GPU call does)
+            self._grow_candidates(got)
+            self.step_device(k, min_ani)
+            got = int(self.d_ncand.item())
         self.h_cand[:got].copy_(self.d_cand[:got])
         return self.gb.finish_candidates(self.h_cand[:got].numpy().view(np.uint32), k, min_ani)
 
@@ -292,6 +300,7 @@ class ShardedPipeline:
         self.n_local, self.s, self.dev = n_local, stride, device
         self.n = n_local * self.world
         self.sp = ShardedPrefilter(gb, dist, n_local, stride, device)
+        self._idx = {}   # small_genomes -> AniIndex, cleared and re-used per step (no cudaMalloc / cudaFree in a step)
 
     def _allgather_var(self, arr, dtype, width):
         """All-gather of per-rank (m_r, width) host arrays of `dtype` through one padded device collective."""
@@ -317,7 +326,10 @@ class ShardedPipeline:
         rank, world, n_local, n = self.rank, self.world, self.n_local, self.n
         info = {}
         t0 = time.perf_counter()
-        idx = gb.AniIndex(small_genomes=small_genomes)
+        if small_genomes not in self._idx:
+            self._idx[small_genomes] = gb.AniIndex(small_genomes=small_genomes)
+        idx = self._idx[small_genomes]
+        idx.clear()
         k1_ms, idx_ms = idx.ingest_packed(seq2, valid, base_off, lengths, sp.my_table.data_ptr(), sp.my_counts.data_ptr(),
                                           device=device, d_base_off=d_base_off)
         t.cuda.synchronize()
@@ -326,7 +338,9 @@ class ShardedPipeline:
         sp.step_device(21, min_ani)
         got = int(sp.d_ncand.item())
         if got > sp.cand_cap:
-            raise RuntimeError("candidate buffer too small")
+            sp._grow_candidates(got)
+            sp.step_device(21, min_ani)
+            got = int(sp.d_ncand.item())
         sp.h_cand[:got].copy_(sp.d_cand[:got])
         mine = gb.finish_candidates(sp.h_cand[:got].numpy().view(np.uint32), 21, min_ani)
         t2 = time.perf_counter()
@@ -366,7 +380,7 @@ class ShardedPipeline:
         back[:, 1] = res["ani"].view(np.uint32)
         got_back = self._allgather_var(back, np.uint32, 2)
         dist.barrier()          # every peer has finished reading this rank's tables
-        idx.close()
+        idx.clear()             # detaches the peers; the allocations stay for the next step
         clusters = None
         if rank == 0:
             ani = np.zeros(2 * len(allh), np.float32)

@@ -245,6 +245,8 @@ uint64_t galah_b200_chunk_identity_fx(uint32_t m, uint32_t n);
 /* Capacity hint: the index will hold n_total_genomes genomes like the ones already added (call
  * it after the first batch).  Avoids re-allocating the device arrays while the index grows. */
 int galah_b200_ani_index_reserve(galah_b200_ani_index_t *idx, size_t n_total_genomes);
+/* Forgets every genome (and detaches attached peers) but keeps the device allocations. */
+int galah_b200_ani_index_clear(galah_b200_ani_index_t *idx);
 size_t galah_b200_ani_index_size(const galah_b200_ani_index_t *idx);
 int galah_b200_ani_index_genome(const galah_b200_ani_index_t *idx, size_t g, uint64_t *n_seeds,
                                 uint32_t *n_chunks, uint64_t *total_len);
@@ -391,6 +393,70 @@ int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float pre
                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
                                    int cluster_contigs, int host_threads, galah_b200_clusters_t *out,
                                    galah_b200_cluster_stats_t *stats);
+
+/* ---- the trait-shaped boundary --------------------------------------------------------------
+ * What an UNMODIFIED galah::clusterer::cluster() (src/clusterer.rs:14-152) calls, in the order it
+ * calls it: PreclusterDistanceFinder::distances* once (src/lib.rs:29-45), then
+ * ClusterDistanceFinder::calculate_ani(fasta1, fasta2) from nested rayon workers (src/lib.rs:54,
+ * src/clusterer.rs:262-296, 375).  A session is the state the two trait objects of one cluster()
+ * call share (the Rust shim holds an Arc of it in both):
+ *   - *_distances stashes its paths and hit list;
+ *   - the first calculate_ani indexes those genomes (unless set_clusterer let the distances call
+ *     build the K3 index in its own ingest pass) and evaluates EVERY stashed hit in one K3 launch;
+ *   - later calls are cache lookups under a shared lock: calculate_ani is re-entrant and may be
+ *     called for any pair of paths (pairs that were never hits are indexed / computed on demand).
+ * Arguments keep the reference's units: FinchPreclusterer.min_ani is a fraction, skani thresholds
+ * are percentages, min_aligned_threshold is a FRACTION (multiplied by 100 in f32 as the reference
+ * does, src/skani.rs:153, 733).  The reference's panics become GALAH_B200_ERR_UNSUPPORTED with the
+ * reference's text in galah_b200_last_error() (src/finch.rs:15, 40; src/skani.rs:116-121, 243-245,
+ * 518-520; src/cluster_argument_parsing.rs:622-627). */
+typedef struct galah_b200_session galah_b200_session_t;
+int galah_b200_session_create(galah_b200_session_t **out);
+void galah_b200_session_free(galah_b200_session_t *s);
+/* Optional: announce the SkaniClusterer's small_genomes before distances(), so that the
+ * preclusterer's ingest pass also builds the K3 index (no second read of the files). */
+int galah_b200_session_set_clusterer(galah_b200_session_t *s, int small_genomes);
+const char *galah_b200_finch_method_name(void);  /* "finch", src/finch.rs:43-45 */
+const char *galah_b200_skani_method_name(void);  /* "skani", src/skani.rs:71-73, 704-706 */
+/* FinchPreclusterer (src/finch.rs:4-46): distances (low_memory != 0 -> the reference's panic),
+ * distances_contigs (always an empty cache), distances_with_references (always the panic). */
+int galah_b200_session_finch_distances(galah_b200_session_t *s, const char *const *paths, size_t n, float min_ani,
+                                       uint32_t num_kmers, uint8_t kmer_length, int low_memory, int host_threads,
+                                       galah_b200_pair_t **out, size_t *n_out);
+int galah_b200_session_finch_distances_contigs(galah_b200_session_t *s, const char *const *paths, size_t n,
+                                               const char *const *contig_names, size_t n_names,
+                                               galah_b200_pair_t **out, size_t *n_out);
+int galah_b200_session_finch_distances_with_references(galah_b200_session_t *s, const char *const *paths, size_t n,
+                                                       const char *const *reference_paths, size_t n_refs,
+                                                       galah_b200_pair_t **out, size_t *n_out);
+/* SkaniPreclusterer (src/skani.rs:12-74): distances (low_memory: the sketch + search form of
+ * src/skani.rs:229-377, where the later of a pair's two records wins, i.e. query = the HIGHER index),
+ * distances_contigs (indices are positions in contig_names, matched by record name as
+ * src/skani.rs:460-474 does), distances_with_references (src/skani.rs:502-687: only pairs of one
+ * reference and one non-reference of `combined_paths`; the query is the non-reference). */
+int galah_b200_session_skani_distances(galah_b200_session_t *s, const char *const *paths, size_t n, float threshold_pct,
+                                       float min_aligned_threshold, int small_genomes, int low_memory,
+                                       int host_threads, galah_b200_pair_t **out, size_t *n_out);
+int galah_b200_session_skani_distances_contigs(galah_b200_session_t *s, const char *const *paths, size_t n,
+                                               const char *const *contig_names, size_t n_names, float threshold_pct,
+                                               float min_aligned_threshold, int small_genomes, int host_threads,
+                                               galah_b200_pair_t **out, size_t *n_out);
+int galah_b200_session_skani_distances_with_references(galah_b200_session_t *s, const char *const *combined_paths,
+                                                       size_t n, const char *const *reference_paths, size_t n_refs,
+                                                       float threshold_pct, float min_aligned_threshold,
+                                                       int small_genomes, int host_threads, galah_b200_pair_t **out,
+                                                       size_t *n_out);
+/* SkaniClusterer::calculate_ani (src/skani.rs:708-715): fasta1 is the query (-q), fasta2 the
+ * reference (-r); *is_some is always 1 (skani never answers None, 0.0 stands for "no row"). */
+int galah_b200_session_calculate_ani(galah_b200_session_t *s, const char *fasta1, const char *fasta2,
+                                     float min_aligned_threshold, int small_genomes, float *ani, int *is_some);
+int galah_b200_session_stats(galah_b200_session_t *s, uint64_t *n_indexed, uint64_t *n_pairs_computed,
+                             uint64_t *n_launches);
+/* Record names of FASTA / FASTQ files as `galah cluster --cluster-contigs` collects them
+ * (src/cluster_argument_parsing.rs:596-629): header line up to the first TAB, file order then
+ * record order; duplicate names fail with the reference's panic text. */
+int galah_b200_contig_names(const char *const *paths, size_t n, char ***names_out, size_t *n_names);
+void galah_b200_contig_names_free(char **names, size_t n);
 
 /* ---- quality-ordering inputs (host logic) ---------------------------------------------------
  * Replaces galah::genome_stats::calculate_genome_stats (src/genome_stats.rs:11-51), the per-genome
