@@ -336,10 +336,15 @@ def markers(codes, rec_start, rec_end, c_marker=1000):
         cap = int(n)
 
 
-def skani_distances(units, threshold, min_af_pct, small_genomes=False, individual_contigs=False):
-    """Oracle of SkaniPreclusterer::distances / ::distances_contigs on `units` = list of
-    (codes, rec_start, rec_end): marker screen -> ANI (query = lower index) -> keep ani >= threshold.
-    Returns [(i, j, common, total, ani f32)]."""
+def skani_distances(units, threshold, min_af_pct, small_genomes=False, individual_contigs=False,
+                    variant="triangle", is_ref=None):
+    """Oracle of SkaniPreclusterer::distances / ::distances_contigs / low-memory /
+    ::distances_with_references on `units` = list of (codes, rec_start, rec_end): marker screen -> ANI
+    -> keep ani >= threshold.  variant "triangle": query = lower index (src/skani.rs:109-225);
+    "lowmem": sketch + search of everything against everything, the later record of a pair wins =
+    query the HIGHER index (src/skani.rs:229-377); "references": only pairs of one reference and one
+    non-reference (is_ref), query = the non-reference (src/skani.rs:502-687).
+    Returns [(i, j, common, total, ani f32)], i < j."""
     import math
     L = _skani_sigs()
     L.skani_oracle_screen_fraction.restype = ctypes.c_double
@@ -350,12 +355,17 @@ def skani_distances(units, threshold, min_af_pct, small_genomes=False, individua
     out = []
     for i in range(len(units)):
         for j in range(i + 1, len(units)):
+            if variant == "references" and bool(is_ref[i]) == bool(is_ref[j]):
+                continue
             m = min(len(mk[i]), len(mk[j]))
             common, total = raw_distance(mk[i], mk[j]) if m else (0, 0)
             bypass = (not small_genomes) and m < 20  # skani without --faster-small
             if not bypass and (m == 0 or common < max(1, math.ceil(frac * m))):
                 continue
-            ani = ani_pair(gen[i], gen[j], min_af_pct, c, individual_contigs)[0]
+            q, r = i, j
+            if variant == "lowmem" or (variant == "references" and is_ref[i]):
+                q, r = j, i
+            ani = ani_pair(gen[q], gen[r], min_af_pct, c, individual_contigs)[0]
             if np.float32(ani) >= np.float32(threshold):
                 out.append((i, j, common, total, np.float32(ani)))
     return out

@@ -22,6 +22,9 @@ CASES = {
     "skani_skani_two_preclusters": dict(  # src/clusterer.rs:725-757
         files=AB + [MAG52], contigs=False, small=False, pre="skani", pre_thr=90.0, ani=99.0, min_af=20.0,
         clusters=[[0, 1, 3], [2], [4]]),
+    "skani_skani_low_memory": dict(  # src/clusterer.rs:759-791 (low_memory: true)
+        files=AB + [MAG52], contigs=False, small=False, pre="skani", pre_thr=90.0, ani=99.0, min_af=20.0,
+        low_memory=True, clusters=[[0, 1, 3], [2], [4]]),
     "lib_contig_cluster": dict(  # src/clusterer.rs:793-823
         files=["contigs/contigs.fna.gz"], contigs=True, small=False, pre="skani", pre_thr=90.0, ani=99.0,
         min_af=20.0, clusters=[[0, 1], [2], [3]]),

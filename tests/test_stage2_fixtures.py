@@ -19,7 +19,8 @@ def oracle_clusters(case):
     units = units_of(GOLDEN, case)
     n = len(units)
     if case["pre"] == "skani":
-        hits = oracle.skani_distances(units, case["pre_thr"], case["min_af"], case["small"], case["contigs"])
+        hits = oracle.skani_distances(units, case["pre_thr"], case["min_af"], case["small"], case["contigs"],
+                                      variant="lowmem" if case.get("low_memory") else "triangle")
         cl, _ = cluster_oracle.cluster(n, [(i, j, a) for i, j, _, _, a in hits], case["ani"], None, skip_clusterer=True)
         return cl
     # finch preclusterer (src/finch.rs:48-97) + SkaniClusterer::calculate_ani(rep, genome)

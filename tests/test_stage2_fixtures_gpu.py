@@ -16,7 +16,12 @@ pytestmark = pytest.mark.gpu
 
 def gpu_clusters(gb, case):
     paths = paths_of(GOLDEN, case)
-    if case["pre"] == "skani":
+    if case.get("low_memory"):
+        session = gb.Session()
+        pre = gb.SkaniPreclusterer(case["pre_thr"], case["min_af"] / 100.0, case["small"], low_memory=True, session=session)
+        cl_ = gb.SkaniClusterer(case["ani"], case["min_af"] / 100.0, case["small"], session=session)
+        cl, info = gb.cluster_with(paths, pre, cl_)
+    elif case["pre"] == "skani":
         cl, info = gb.cluster_skani(paths, precluster_ani=case["pre_thr"], ani=case["ani"],
                                     min_aligned_fraction=case["min_af"], small_genomes=case["small"],
                                     cluster_contigs=case["contigs"])
