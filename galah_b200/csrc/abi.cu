@@ -1606,8 +1606,12 @@ int session_index_paths(galah_b200_session *s, const std::vector<std::string> &p
 // Evaluates (query, reference) id pairs that are not cached yet, in one K3 launch.
 int session_compute(galah_b200_session *s, std::vector<uint32_t> &pairs) {
     std::vector<uint32_t> todo;
-    for (size_t x = 0; x + 1 < pairs.size(); x += 2)
-        if (!s->cache.count(((uint64_t)pairs[x] << 32) | pairs[x + 1])) { todo.push_back(pairs[x]); todo.push_back(pairs[x + 1]); }
+    std::unordered_map<uint64_t, char> seen;
+    for (size_t x = 0; x + 1 < pairs.size(); x += 2) {
+        const uint64_t key = ((uint64_t)pairs[x] << 32) | pairs[x + 1];
+        if (s->cache.count(key) || !seen.emplace(key, 1).second) continue;
+        todo.push_back(pairs[x]); todo.push_back(pairs[x + 1]);
+    }
     if (todo.empty()) return 0;
     std::vector<gb200::AniPairResult> res(todo.size() / 2);
     if (int rc = s->index->pairs(todo.data(), todo.size() / 2, s->min_af_pct, false, res.data(), gb200::g_ctx.stream)) return rc;
