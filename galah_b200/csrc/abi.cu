@@ -416,8 +416,7 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
         }
         if (sinks.markers) {
             MarkerTable &mt = *sinks.markers;
-            uint32_t cap = 256;
-            while (cap < 16384 && cap < 1.5 * (double)longest / sinks.c_marker + 256.0) cap <<= 1;
+            const uint32_t cap = marker_row_capacity(longest, sinks.c_marker);
             // rows for everything still to come (units per file as seen so far), common stride
             const double per_file = (double)sinks.n_units / (double)std::max<size_t>(files_done, 1);
             const size_t rows_hint = std::max(mt.n + nb, (size_t)(per_file * (double)n) + 1);
@@ -432,7 +431,10 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
             GB_CUDA(cudaStreamSynchronize(st));
             for (size_t x = 0; x < nb; x++)
                 if (cnt[x] == 0xFFFFFFFFu) {
-                    set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
+                    set_error("marker sketch: a unit holds more markers than its row of " + std::to_string(mt.stride) +
+                              " (marker density 1/" + std::to_string(sinks.c_marker) + "; rows hold at most " +
+                              std::to_string(kMarkerMaxCap) + " markers, about " +
+                              std::to_string((uint64_t)kMarkerMaxCap * sinks.c_marker / 1500000) + " Mbp per unit); unsupported");
                     return GALAH_B200_ERR_UNSUPPORTED;
                 }
             mt.n += nb;
@@ -1504,8 +1506,7 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
     const double t1 = now_ms();
     // marker sketches straight into the K2 table layout (row stride = cap): they never leave the device
     const uint32_t c_marker = small_genomes ? 200u : 1000u;
-    uint32_t cap = 256;
-    while (cap < 16384 && cap < 1.5 * (double)longest / c_marker + 256.0) cap <<= 1;
+    const uint32_t cap = marker_row_capacity(longest, c_marker);
     DevBuf<uint64_t> d_rows;
     DevBuf<uint32_t> d_counts;
     if (d_rows.alloc(n * (size_t)cap) || d_counts.alloc(n)) return GALAH_B200_ERR_CUDA;
@@ -1516,7 +1517,9 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
     GB_CUDA(cudaStreamSynchronize(st));
     for (size_t g = 0; g < n; g++)
         if (cnt[g] == 0xFFFFFFFFu) {
-            set_error("marker sketch: a genome holds more than 16384 markers (longer than ~10 Mbp at c=1000); unsupported");
+            set_error("marker sketch: a unit holds more markers than its row of " + std::to_string(cap) +
+                      " (marker density 1/" + std::to_string(c_marker) + "; rows hold at most " + std::to_string(kMarkerMaxCap) +
+                      " markers, about " + std::to_string((uint64_t)kMarkerMaxCap * c_marker / 1500000) + " Mbp per unit); unsupported");
             return GALAH_B200_ERR_UNSUPPORTED;
         }
     const double t2 = now_ms();

@@ -300,6 +300,13 @@ struct ChunkParams {
     uint32_t *counts;
     uint32_t out_stride;
     uint64_t fixed_thr;      // != 0: FracMinHash mode -- keep every hash <= fixed_thr (no bottom-s cap)
+    // FracMinHash mode only: the hash range [0, fixed_thr] is cut into n_parts equal value ranges,
+    // each with its own candidate buffer of `cap` slots (cand[(g * n_parts + part) * cap ..],
+    // cand_n[g * n_parts + part]), so a row may hold n_parts * cap markers although one sort in
+    // shared memory holds cap.  part(h) = mulhi(h * frac_c, n_parts), exact and monotone in h.
+    uint32_t n_parts;        // 0 / 1: a single buffer per genome
+    uint32_t part;           // marker_select_kernel: the partition this launch finishes
+    uint64_t frac_c;         // the FracMinHash compression factor c (h * c < 2^64 for every kept h)
 };
 
 __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) {
@@ -365,9 +372,82 @@ __global__ void __launch_bounds__(256) sketch_scan_kernel(const ChunkParams p) {
         else { if (!kmer_mmhash<KT>(p.seq2, p.valid, b0 + q, p.k, h)) continue; }
         if (h > T) continue;
         if (h == kPad) { p.has_max[g] = 1; continue; }
+        if (HK == 1 && p.n_parts > 1) {
+            const uint32_t part = (uint32_t)__umul64hi(h * p.frac_c, (uint64_t)p.n_parts);
+            const size_t buf = (size_t)g * p.n_parts + part;
+            const uint32_t slot = atomicAdd(&p.cand_n[buf], 1u);
+            if (slot < p.cap) p.cand[buf * p.cap + slot] = h;
+            continue;
+        }
         const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
         if (slot < p.cap) cand[slot] = h;
     }
+}
+
+// FracMinHash rows wider than one shared-memory sort: launch `part` = 0 .. n_parts - 1 in order;
+// every launch sorts one value range of every genome, drops duplicates and appends the distinct
+// values behind what the earlier ranges wrote (counts[g] is the running length; 0xFFFFFFFF flags
+// a buffer or row overflow).  The last launch pads the row.  One CTA per genome, p.cap uint64 of
+// dynamic shared memory.
+__global__ void __launch_bounds__(256) marker_select_kernel(const ChunkParams p) {
+    extern __shared__ __align__(16) uint64_t sel[];
+    __shared__ uint32_t s_warp_sum[8];
+    const uint32_t g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t buf = (size_t)g * p.n_parts + p.part;
+    const uint32_t got = p.cand_n[buf];
+    const uint32_t base = p.part == 0 ? 0u : p.counts[g];
+    const bool bad = got > p.cap || base == 0xFFFFFFFFu;
+    const uint32_t m = min(got, p.cap);
+    uint32_t cap2 = 256;
+    while (cap2 < m) cap2 <<= 1;
+    const uint64_t *cand = p.cand + buf * p.cap;
+    for (uint32_t x = tid; x < cap2; x += 256) sel[x] = x < m ? cand[x] : kPad;
+    __syncthreads();
+    for (uint32_t size = 2; size <= cap2; size <<= 1) {
+        for (uint32_t str = size >> 1; str > 0; str >>= 1) {
+            for (uint32_t x = tid; x < (cap2 >> 1); x += 256) {
+                const uint32_t lo = 2 * x - (x & (str - 1));
+                const uint32_t hi = lo + str;
+                const bool up = (lo & size) == 0;
+                const uint64_t a = sel[lo], b = sel[hi];
+                if ((a > b) == up) { sel[lo] = b; sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t per = cap2 / 256;
+    const uint32_t x0 = tid * per;
+    uint32_t mine = 0;
+    for (uint32_t x = x0; x < x0 + per; x++) {
+        const uint64_t v = sel[x];
+        mine += (v != kPad && (x == 0 || sel[x - 1] != v)) ? 1u : 0u;
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, distinct = 0;
+    for (uint32_t w = 0; w < 8; w++) {
+        if (w < warp) before += s_warp_sum[w];
+        distinct += s_warp_sum[w];
+    }
+    if (bad || base + distinct > p.out_stride) {
+        if (tid == 0) p.counts[g] = 0xFFFFFFFFu;
+        return;
+    }
+    uint64_t *out = p.hashes + (size_t)g * p.out_stride + base;
+    uint32_t pos = before + incl - mine;
+    for (uint32_t x = x0; x < x0 + per; x++) {
+        const uint64_t v = sel[x];
+        if (v != kPad && (x == 0 || sel[x - 1] != v)) out[pos++] = v;
+    }
+    if (p.part + 1 == p.n_parts)
+        for (uint32_t x = base + distinct + tid; x < p.out_stride; x += 256) p.hashes[(size_t)g * p.out_stride + x] = kPad;
+    if (tid == 0) p.counts[g] = base + distinct;
 }
 
 // One CTA per genome.  Dynamic shared memory: cap uint64.
@@ -507,7 +587,7 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
     c.has_max = ws.d_has_max; c.item_genome = ws.d_item_genome; c.max_items = max_items;
     c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
     c.hashes = d_hashes; c.counts = d_counts; c.out_stride = (uint32_t)out_stride;
-    c.fixed_thr = 0;
+    c.fixed_thr = 0; c.n_parts = 0; c.part = 0; c.frac_c = 0;
 
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
@@ -551,7 +631,9 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
                           const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
                           uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream) {
     if (k < 1 || k > 32) { set_error("marker sketch: k must be in 1..32"); return 3; }
-    if (cap < 256 || (cap & (cap - 1)) || cap > 16384) { set_error("marker sketch: bad capacity"); return 3; }
+    if (cap < 256 || (cap & (cap - 1)) || cap > kMarkerMaxCap) { set_error("marker sketch: bad capacity"); return 3; }
+    const uint32_t n_parts = cap > kMarkerPartCap ? cap / kMarkerPartCap : 1u;  // value-range partitions of a wide row
+    const uint32_t part_cap = cap > kMarkerPartCap ? kMarkerPartCap : cap;
     if (n >= 0x7FFFFFFFull) { set_error("marker sketch: too many genomes in one batch"); return 3; }
     if (n == 0) return 0;
     uint64_t total_bases = 0, first_base = 0;
@@ -562,20 +644,22 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
     if (max_items > 0x7FFFFFFFull) { set_error("marker sketch: batch too long for one launch"); return 3; }
     if (!ws.d_redo_n) GB_CUDA(cudaMalloc(&ws.d_redo_n, sizeof(uint32_t)));
     if (sk_ensure(ws.d_chunk_off, ws.cap_chunk_off, n + 1) || sk_ensure(ws.d_thr, ws.cap_thr, n) ||
-        sk_ensure(ws.d_cand_n, ws.cap_cand_n, n) || sk_ensure(ws.d_has_max, ws.cap_has_max, n) ||
+        sk_ensure(ws.d_cand_n, ws.cap_cand_n, n * (size_t)n_parts) || sk_ensure(ws.d_has_max, ws.cap_has_max, n) ||
         sk_ensure(ws.d_redo_list, ws.cap_redo, n) ||
         sk_ensure(ws.d_item_genome, ws.cap_items, (size_t)max_items + 1) ||
         sk_ensure(ws.d_cand, ws.cap_cand, n * (size_t)cap))
         return 2;
     ChunkParams c;
     c.seq2 = d_seq2; c.valid = d_valid; c.base_off = d_base_off; c.n = (uint32_t)n; c.k = k; c.s = cap;
-    c.seed = 0; c.cap = cap; c.chunk_off = ws.d_chunk_off; c.thr = ws.d_thr; c.cand_n = ws.d_cand_n;
+    c.n_parts = n_parts; c.part = 0; c.frac_c = c_marker;
+    c.seed = 0; c.cap = part_cap; c.chunk_off = ws.d_chunk_off; c.thr = ws.d_thr; c.cand_n = ws.d_cand_n;
     c.has_max = ws.d_has_max; c.item_genome = ws.d_item_genome; c.max_items = max_items;
     c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
     c.hashes = d_rows; c.counts = d_counts; c.out_stride = cap;
     c.fixed_thr = ~0ull / c_marker - 1;  // keep h < (2^64-1)/c  <=>  h <= that - 1
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
+    if (n_parts > 1) GB_CUDA(cudaMemsetAsync(ws.d_cand_n, 0, n * (size_t)n_parts * sizeof(uint32_t), stream));
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
@@ -583,10 +667,20 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
         else sketch_scan_kernel<0, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         GB_LAUNCH_CHECK();
     }
-    const size_t smem = (size_t)cap * 8;
-    GB_CUDA(cudaFuncSetAttribute(sketch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sketch_select_kernel<<<(uint32_t)n, 256, smem, stream>>>(c);
-    GB_LAUNCH_CHECK();
+    const size_t smem = (size_t)part_cap * 8;
+    if (n_parts == 1) {
+        GB_CUDA(cudaFuncSetAttribute(sketch_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sketch_select_kernel<<<(uint32_t)n, 256, smem, stream>>>(c);
+        GB_LAUNCH_CHECK();
+        return 0;
+    }
+    // the plan kernel zeroed cand_n[0..n) only: the partitioned buffers count in n * n_parts slots
+    GB_CUDA(cudaFuncSetAttribute(marker_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (uint32_t part = 0; part < n_parts; part++) {
+        c.part = part;
+        marker_select_kernel<<<(uint32_t)n, 256, smem, stream>>>(c);
+        GB_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -26,7 +26,16 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
                    uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream);
 
-// FracMinHash marker sketches for the skani-style screen (see sketch.cu).
+// FracMinHash marker sketches for the skani-style screen (see sketch.cu).  cap: row stride, a power
+// of two in [256, kMarkerMaxCap]; rows wider than kMarkerPartCap are finished in value-range partitions.
+constexpr uint32_t kMarkerPartCap = 16384;   // markers one shared-memory sort holds
+constexpr uint32_t kMarkerMaxCap = 131072;   // 26 Mbp at c = 200, 131 Mbp at c = 1000
+// The row stride for units of up to `longest` bases at density 1 / c_marker (1.5 x the expectation + slack).
+inline uint32_t marker_row_capacity(uint64_t longest, uint32_t c_marker) {
+    uint32_t cap = 256;
+    while (cap < kMarkerMaxCap && cap < 1.5 * (double)longest / c_marker + 256.0) cap <<= 1;
+    return cap;
+}
 int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                           const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
                           uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream);

@@ -123,3 +123,20 @@ def test_device_resident_contigs_match_file_path_and_oracle(gb, tmp_path):
     check(got, exp)
     # members of a synthetic family of 10 only ever pair with each other
     assert np.all(got["i"] // 10 == got["j"] // 10)
+
+
+def test_units_with_more_markers_than_one_sort_holds(gb, tmp_path):
+    """The reference (skani) has no unit size limit (src/skani.rs:109-225).  A 3.6 Mbp genome at
+    --small-genomes marker density (1/200) holds ~18,000 markers, more than one 16,384-entry
+    shared-memory sort: its row is finished in two value-range partitions and the K2 join runs at
+    a row stride of 32,768.  Marker intersections and ANI equal the oracle's."""
+    rng = np.random.default_rng(23)
+    base = random_dna(3_600_000, rng)
+    recs = [("big0", [base]), ("big1", [mutate(base, 0.03, rng)]), ("big2_two_contigs", [base[:2_000_000], base[2_100_000:]]),
+            ("other", [random_dna(300_000, rng)])]
+    paths = [write_fasta(str(tmp_path / f"{n}.fna"), [(f"{n}_{i}", r) for i, r in enumerate(rs)]) for n, rs in recs]
+    got, n_units = gb.skani_distances(paths, 90.0, 15.0, small_genomes=True)
+    exp = oracle.skani_distances(units_of(paths), 90.0, 15.0, small_genomes=True)
+    assert n_units == 4 and len(exp) == 3
+    check(got, exp)
+    assert min(int(g["common"]) for g in got) > 5000 and max(int(g["total"]) for g in got) > 16384
