@@ -5,13 +5,19 @@
 
 #include <algorithm>
 
-// zlib ships as a shared object in this image but without its header; these three entry points
+// zlib ships as a shared object in this image but without its header; these entry points
 // are ABI-stable.  gzread() passes non-gzip files through unchanged.
 extern "C" {
 typedef struct gzFile_s *gzFile;
 gzFile gzopen(const char *path, const char *mode);
 int gzread(gzFile file, void *buf, unsigned len);
 int gzclose(gzFile file);
+const char *gzerror(gzFile file, int *errnum);
+int gzeof(gzFile file);
+#ifndef Z_OK
+#define Z_OK 0
+#define Z_STREAM_END 1
+#endif
 }
 
 namespace gb200 {
@@ -146,7 +152,14 @@ int read_file_bytes(const std::string &path, std::vector<uint8_t> &out, std::str
         if (got == 0) break;
         n += (size_t)got;
     }
+    // gzread() == 0 is also what a stream cut off mid-member returns: a truncated .gz must fail as
+    // it does in the reference (needletail), not yield a shorter genome
+    int zerr = 0;
+    const char *zmsg = gzerror(f, &zerr);
+    const bool clean = gzeof(f) && (zerr == Z_OK || zerr == Z_STREAM_END);
+    const std::string detail = zmsg ? zmsg : "";
     gzclose(f);
+    if (!clean) { err = "Failed to read (truncated or corrupt gzip: " + detail + ") " + path; return 4; }
     out.resize(n);
     return 0;
 }

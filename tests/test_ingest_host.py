@@ -34,3 +34,17 @@ def test_synthetic_edge_cases(tmp_path, width, newline, gz):
     p = write_fasta(str(tmp_path / ("x.fna.gz" if gz else "x.fna")), recs, width=width, newline=newline, gz=gz)
     codes = same(p)
     assert len(codes) == sum(len(r[1]) for r in recs) + len(recs) - 1  # one separator between records
+
+
+def test_truncated_gzip_fails_instead_of_yielding_a_shorter_genome(tmp_path):
+    """needletail (the reference's reader, src/finch.rs:69) fails on a gzip stream cut mid-member."""
+    import galah_b200 as gb
+    rng = np.random.default_rng(5)
+    p = write_fasta(str(tmp_path / "g.fna.gz"), [("r", random_dna(300_000, rng))], gz=True)
+    data = open(p, "rb").read()
+    cut = str(tmp_path / "cut.fna.gz")
+    with open(cut, "wb") as f:
+        f.write(data[: len(data) // 2])
+    gb.pack_fasta_file(p)
+    with pytest.raises(gb.GalahB200Error, match="truncated or corrupt gzip"):
+        gb.pack_fasta_file(cut)
