@@ -59,6 +59,7 @@ struct Context {
     uint32_t *slot_seq2[2] = {nullptr, nullptr}, *slot_valid[2] = {nullptr, nullptr};  // upload slots of ingest_packed
     uint64_t *slot_off[2] = {nullptr, nullptr};
     size_t cap_slot_seq2[2] = {0, 0}, cap_slot_valid[2] = {0, 0}, cap_slot_off[2] = {0, 0};
+    uint32_t *d_sel = nullptr; size_t cap_sel = 0;  // K3 seed selection bits made by the fused k = 21 scan
     AniIndex *pipe_index[2] = {nullptr, nullptr};  // K3 index of the one-call pipelines (c = 125 / 30), re-used across calls
     AniIndex &pipeline_index(bool small_genomes) {
         AniIndex *&p = pipe_index[small_genomes ? 1 : 0];
@@ -68,6 +69,7 @@ struct Context {
     }
     int release() {
         for (auto &p : pipe_index) { delete p; p = nullptr; }
+        cudaFree(d_sel); d_sel = nullptr; cap_sel = 0;
         for (int x = 0; x < 2; x++) {
             cudaFree(slot_seq2[x]); cudaFree(slot_valid[x]); cudaFree(slot_off[x]);
             slot_seq2[x] = slot_valid[x] = nullptr; slot_off[x] = nullptr;
@@ -111,6 +113,14 @@ struct DevBuf {
         return 0;
     }
 };
+
+// Seed sink of the fused k = 21 scan for a batch whose bases span [first, end): the selection bits
+// live in a context buffer until AniIndex::add_packed_device has consumed them (same stream).
+static int seed_sink_for(const AniIndex &index, uint64_t first, uint64_t end, SeedSink &sink) {
+    if (ws_ensure(g_ctx.d_sel, g_ctx.cap_sel, (size_t)((end - first) / 32 + 2))) return GALAH_B200_ERR_CUDA;
+    sink.d_sel = g_ctx.d_sel; sink.first_base = first; sink.thr = index.seed_threshold();
+    return 0;
+}
 
 // Integer candidates {i, j, common, total} -> the reference's f64 formula, threshold and f32 store
 // (src/finch.rs:78-93), sorted by (i, j) -- the iteration order of the reference's BTreeMap.  Host
@@ -396,12 +406,19 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
                     const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
                     const std::vector<uint32_t> &cs, const std::vector<uint32_t> &cl, uint64_t longest,
                     size_t unit_first, size_t files_done) -> int {
+        // one pass over the packed bases feeds the k = 21 sketch AND the K3 seed selection
+        SeedSink seed_sink{nullptr, 0, 0};
+        const bool fuse = sinks.ani && ((sinks.sketch && sinks.k == 21) || sinks.markers);
+        if (fuse) if (int rc = seed_sink_for(*sinks.ani, base_off.front(), base_off.back(), seed_sink)) return rc;
+        bool sel_ready = false;
         if (sinks.sketch && sinks.d_hashes) {
             // K1 writes the rows where K2 will read them (the table never leaves the device)
             const size_t stride = sinks.stride ? sinks.stride : sinks.s;
             int rc = sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, sinks.k, sinks.s, sinks.seed,
-                                    sinks.d_hashes + unit_first * stride, sinks.d_counts + unit_first, stride, st);
+                                    sinks.d_hashes + unit_first * stride, sinks.d_counts + unit_first, stride, st,
+                                    fuse && sinks.k == 21 ? &seed_sink : nullptr);
             if (rc) return rc;
+            sel_ready = fuse && sinks.k == 21;
         } else if (sinks.sketch) {
             DevBuf<uint64_t> d_hashes;
             DevBuf<uint32_t> d_counts;
@@ -424,7 +441,8 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
             uint64_t *d_rows = mt.d_rows + mt.n * (size_t)mt.stride;
             uint32_t *d_cnt = mt.d_counts + mt.n;
             int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_off, nb, 21, sinks.c_marker, mt.stride, d_rows,
-                                           d_cnt, st);
+                                           d_cnt, st, fuse && !sel_ready ? &seed_sink : nullptr);
+            sel_ready = sel_ready || fuse;
             if (rc) return rc;
             std::vector<uint32_t> cnt(nb);
             GB_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, nb * 4, cudaMemcpyDeviceToHost, st));
@@ -441,7 +459,8 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
         }
         if (sinks.ani) {
             const size_t before = sinks.ani->size();
-            int rc = sinks.ani->add_packed_device(d_seq2, d_valid, d_off, nb, base_off, contig_off, cs, cl, st);
+            int rc = sinks.ani->add_packed_device(d_seq2, d_valid, d_off, nb, base_off, contig_off, cs, cl, st,
+                                                  sel_ready ? seed_sink.d_sel : nullptr);
             if (rc) return rc;
             // first batch of a larger run: size the index once for everything still to come
             // (units per file as seen so far; exact for whole-genome units)
@@ -1358,11 +1377,13 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         for (size_t g = 0; g < nb; g++) { co[g] = g; cl[g] = (uint32_t)lengths[g0 + g]; }
         co[nb] = nb;
         GB_CUDA(cudaEventRecord(ev[0], st));
+        SeedSink seed_sink{nullptr, 0, 0};  // the k = 21 scan also marks the K3 seeds of the batch
+        if (int rc = seed_sink_for(index, bo.front(), bo.back(), seed_sink)) return rc;
         if (int rc = sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, s, 0, d_table + g0 * (size_t)s,
-                                    d_counts + g0, s, st))
+                                    d_counts + g0, s, st, &seed_sink))
             return rc;
         GB_CUDA(cudaEventRecord(ev[1], st));
-        if (int rc = index.add_packed_device(b_seq2, b_valid, b_off, nb, bo, co, cs, cl, st)) return rc;
+        if (int rc = index.add_packed_device(b_seq2, b_valid, b_off, nb, bo, co, cs, cl, st, seed_sink.d_sel)) return rc;
         if (b == 0 && n_batches > 1) if (int rc = index.reserve_for(n, st)) return rc;
         GB_CUDA(cudaEventRecord(ev[2], st));
         if (!device) GB_CUDA(cudaEventRecord(slot[b & 1].freed, st));
@@ -1502,7 +1523,6 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
     uint64_t longest = 0;
     for (size_t g = 0; g < n; g++) { co[g] = g; cl[g] = (uint32_t)lengths[g]; longest = std::max(longest, lengths[g]); }
     co[n] = n;
-    if (int rc = index.add_packed_device(d_seq2, d_valid, d_base_off, n, bo, co, cs, cl, st)) return rc;
     const double t1 = now_ms();
     // marker sketches straight into the K2 table layout (row stride = cap): they never leave the device
     const uint32_t c_marker = small_genomes ? 200u : 1000u;
@@ -1510,8 +1530,12 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
     DevBuf<uint64_t> d_rows;
     DevBuf<uint32_t> d_counts;
     if (d_rows.alloc(n * (size_t)cap) || d_counts.alloc(n)) return GALAH_B200_ERR_CUDA;
-    if (int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_base_off, n, 21, c_marker, cap, d_rows.p, d_counts.p, st))
+    SeedSink seed_sink{nullptr, 0, 0};  // one pass: marker sketches + K3 seed selection
+    if (int rc = seed_sink_for(index, bo.front(), bo.back(), seed_sink)) return rc;
+    if (int rc = marker_sketch_enqueue(g_ctx.sws, d_seq2, d_valid, d_base_off, n, 21, c_marker, cap, d_rows.p, d_counts.p, st,
+                                       &seed_sink))
         return rc;
+    if (int rc = index.add_packed_device(d_seq2, d_valid, d_base_off, n, bo, co, cs, cl, st, seed_sink.d_sel)) return rc;
     std::vector<uint32_t> cnt(n);
     GB_CUDA(cudaMemcpyAsync(cnt.data(), d_counts.p, n * 4, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));

@@ -587,7 +587,7 @@ AniIndex::~AniIndex() {
 int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
                                 size_t n, const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
                                 const std::vector<uint32_t> &contig_start, const std::vector<uint32_t> &contig_len,
-                                cudaStream_t st) {
+                                cudaStream_t st, const uint32_t *d_sel_in) {
     if (n == 0) return 0;
     if (base_off.size() != n + 1 || contig_off.size() != n + 1) { set_error("ani index: bad offset arrays"); return 3; }
     for (size_t g = 0; g <= n; g++)
@@ -619,13 +619,16 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
                      &d_chunk_base = scratch_->chunk_base, &d_chunk_tmp = scratch_->chunk_tmp, &d_nch = scratch_->nch;
     TmpBuf<uint64_t> &d_contig_off = scratch_->contig_off, &d_seed_off_b = scratch_->seed_off_b,
                      &d_cso_off_b = scratch_->cso_off_b, &d_table_off_b = scratch_->table_off_b;
-    if (d_sel.alloc(n_words + 1) || d_count.alloc(n)) return 2;
+    if ((!d_sel_in && d_sel.alloc(n_words + 1)) || d_count.alloc(n)) return 2;
     const uint64_t thr = ~0ull / c_;
+    const uint32_t *sel_p = d_sel_in ? d_sel_in : d_sel.p;
     {
-        const uint64_t blocks = std::min<uint64_t>((end - first + 255) / 256, (uint64_t)sms * 32);
-        ani_mark_kernel<<<(uint32_t)std::max<uint64_t>(blocks, 1), 256, 0, st>>>(d_seq2, d_valid, first, end, thr, d_sel.p);
-        GB_LAUNCH_CHECK();
-        ani_count_kernel<<<(uint32_t)n, 256, 0, st>>>(d_sel.p, d_base_off, first, d_count.p);
+        if (!d_sel_in) {
+            const uint64_t blocks = std::min<uint64_t>((end - first + 255) / 256, (uint64_t)sms * 32);
+            ani_mark_kernel<<<(uint32_t)std::max<uint64_t>(blocks, 1), 256, 0, st>>>(d_seq2, d_valid, first, end, thr, d_sel.p);
+            GB_LAUNCH_CHECK();
+        }
+        ani_count_kernel<<<(uint32_t)n, 256, 0, st>>>(sel_p, d_base_off, first, d_count.p);
         GB_LAUNCH_CHECK();
     }
     std::vector<uint32_t> count(n);
@@ -655,7 +658,7 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
         d_chunk_tmp.alloc(seed_off[n] - seed_off[0] + 1))
         return 2;
     EmitParams e;
-    e.seq2 = d_seq2; e.valid = d_valid; e.sel = d_sel.p; e.base_off = d_base_off; e.first_base = first;
+    e.seq2 = d_seq2; e.valid = d_valid; e.sel = sel_p; e.base_off = d_base_off; e.first_base = first;
     e.contig_off = d_contig_off.p; e.contig_start = d_contig_start.p; e.contig_chunk_base = d_chunk_base.p;
     e.seed_off = d_seed_off_b.p; e.cso_off = d_cso_off_b.p; e.n_chunks = d_nch.p; e.table_off = d_table_off_b.p;
     e.kq = d_kq_.p; e.cso = d_cso_.p;

@@ -65,7 +65,10 @@ public:
     int add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
                           size_t n, const std::vector<uint64_t> &base_off_host,
                           const std::vector<uint64_t> &contig_off, const std::vector<uint32_t> &contig_start,
-                          const std::vector<uint32_t> &contig_len, cudaStream_t st);
+                          const std::vector<uint32_t> &contig_len, cudaStream_t st, const uint32_t *d_sel = nullptr);
+    // d_sel: seed selection bits of the batch already made by the fused k = 21 scan (sketch.cuh
+    // SeedSink; one bit per base relative to base_off_host[0]); the mark pass is skipped then.
+    uint64_t seed_threshold() const { return ~0ull / c_; }
     int reserve_for(size_t n_total, cudaStream_t st);
     // Forgets every genome (and detaches the peers) but keeps the device allocations: a caller that
     // re-indexes the same workload per call pays no cudaMalloc / cudaFree (device-wide synchronisations).

@@ -37,6 +37,8 @@
 //                         redo list only, so the result is exact for any input.
 #include "sketch.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -307,6 +309,11 @@ struct ChunkParams {
     uint32_t n_parts;        // 0 / 1: a single buffer per genome
     uint32_t part;           // marker_select_kernel: the partition this launch finishes
     uint64_t frac_c;         // the FracMinHash compression factor c (h * c < 2^64 for every kept h)
+    // fused K3 seed marking (scan21_kernel): one bit per base position, relative to sel_first_base
+    int plan_k;              // k-mer length the chunk plan covers (0: k); 15 when seeds are marked too
+    uint32_t *sel;
+    uint64_t sel_first_base;
+    uint64_t seed_thr;       // a 15-mer is a seed iff mm_hash64(canonical) < seed_thr
 };
 
 __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) {
@@ -318,7 +325,9 @@ __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) 
     for (uint32_t g = g0; g < g1; g++) {
         const uint64_t len = p.base_off[g + 1] - p.base_off[g];
         const uint64_t npos = len >= (uint64_t)p.k ? len - p.k + 1 : 0;
-        sum += (npos + kChunk - 1) / kChunk;
+        const uint64_t pk = p.plan_k ? (uint64_t)p.plan_k : (uint64_t)p.k;
+        const uint64_t nplan = len >= pk ? len - pk + 1 : 0;
+        sum += (nplan + kChunk - 1) / kChunk;
         uint64_t T = kPad;
         const double want = 1.3 * (double)p.s + 64.0;
         if ((double)npos > want) T = (uint64_t)(18446744073709551616.0 * (want / (double)npos));
@@ -339,8 +348,9 @@ __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) 
     for (uint32_t g = g0; g < g1; g++) {
         p.chunk_off[g] = run;
         const uint64_t len = p.base_off[g + 1] - p.base_off[g];
-        const uint64_t npos = len >= (uint64_t)p.k ? len - p.k + 1 : 0;
-        run += (npos + kChunk - 1) / kChunk;
+        const uint64_t pk = p.plan_k ? (uint64_t)p.plan_k : (uint64_t)p.k;
+        const uint64_t nplan = len >= pk ? len - pk + 1 : 0;
+        run += (nplan + kChunk - 1) / kChunk;
     }
     if (tid == 1023) p.chunk_off[p.n] = s_part[1023];
     if (tid == 0) *p.redo_n = 0;
@@ -450,6 +460,117 @@ __global__ void __launch_bounds__(256) marker_select_kernel(const ChunkParams p)
     if (tid == 0) p.counts[g] = base + distinct;
 }
 
+// ------------------------------------------------------------------------------------------
+// k = 21 scan with ROLLING state (the hot kernel of the whole path): a thread owns 64 consecutive
+// k-mer start positions of its chunk and keeps, per position, in registers
+//   * the 21 ASCII bytes of the forward k-mer (5 words, a byte-wise shift register) and of its
+//     reverse complement (shifted the other way): what MurmurHash3 reads -- no per-position
+//     bit reversal / ASCII expansion;
+//   * the MSB-first 2-bit integers of both strands (canonical choice; the 15-mer of the K3 seed is
+//     the top 30 bits of the forward integer and the low 30 bits of the reverse one);
+//   * the validity of the last 21 bases as a bit mask.
+// One pass therefore feeds K1 (MODE 0: MurmurHash3 candidates under the genome's threshold) or the
+// marker sketch (MODE 1: mm_hash64 of the canonical 21-mer under the fixed threshold) AND, with
+// SEEDS, the K3 seed selection bits (mm_hash64 of the canonical 15-mer < seed_thr) that
+// ani_mark_kernel would otherwise derive from the same bytes in a second pass.
+// Loads are three aligned vector loads per thread (64 + 32 bases of sequence and validity); bases
+// past the genome's (128-padded) span are never read.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t murmur21(uint64_t k1, uint64_t k2, uint64_t kt, uint64_t seed) {
+    const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
+    uint64_t h1 = seed, h2 = seed;
+    k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ull;
+    k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+    h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ull;
+    kt *= c1; kt = rotl64(kt, 31); kt *= c2; h1 ^= kt;   // 5-byte tail goes into k1 only
+    h1 ^= 21ull; h2 ^= 21ull;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    return h1 + h2;
+}
+
+template <int MODE, bool SEEDS>
+__global__ void __launch_bounds__(256) scan21_kernel(const ChunkParams p) {
+    const uint64_t item = blockIdx.x;
+    if (item >= p.chunk_off[p.n]) return;
+    const uint32_t g = p.item_genome[item];
+    const uint64_t b0 = p.base_off[g], len = p.base_off[g + 1] - b0;  // the 128-padded span
+    const uint64_t q0 = (item - p.chunk_off[g]) * kChunk + (uint64_t)threadIdx.x * 64;
+    if (q0 >= len) return;
+    const uint64_t P0 = b0 + q0;  // multiple of 64: the vector loads below are aligned
+    const uint4 s03 = __ldg(reinterpret_cast<const uint4 *>(p.seq2 + (P0 >> 4)));
+    const uint2 v01 = __ldg(reinterpret_cast<const uint2 *>(p.valid + (P0 >> 5)));
+    uint2 s45 = make_uint2(0u, 0u);
+    uint32_t v2 = 0u;
+    if (q0 + 64 < len) {  // then q0 + 128 <= len: the next 32 bases belong to this genome
+        s45 = __ldg(reinterpret_cast<const uint2 *>(p.seq2 + (P0 >> 4) + 4));
+        v2 = __ldg(p.valid + (P0 >> 5) + 2);
+    }
+    const uint64_t T = MODE == 0 ? p.thr[g] : p.fixed_thr;
+    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;  // forward ASCII bytes 0..20 (f5: byte 20)
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0;  // reverse-complement ASCII bytes 0..20
+    uint64_t Fint = 0, Rint = 0;
+    uint32_t vbits = 0, sel0 = 0, sel1 = 0;
+    const uint64_t mask42 = (1ull << 42) - 1;
+#pragma unroll
+    for (int wi = 0; wi < 6; wi++) {
+        uint32_t w = wi == 0 ? s03.x : wi == 1 ? s03.y : wi == 2 ? s03.z : wi == 3 ? s03.w : wi == 4 ? s45.x : s45.y;
+        uint32_t vw = (wi < 2 ? v01.x : wi < 4 ? v01.y : v2) >> ((wi & 1) * 16);
+        const int j_end = wi == 5 ? 4 : 16;  // bases 80..83 are the last ones a thread needs
+#pragma unroll 1
+        for (int j = 0; j < j_end; j++) {
+            const uint32_t code = w & 3u;
+            w >>= 2;
+            const uint32_t vb = vw & 1u;
+            vw >>= 1;
+            const uint32_t fa = __byte_perm(0x54474341u, 0u, code);       // "ACGT"[code]
+            const uint32_t ra = __byte_perm(0x41434754u, 0u, code);       // "TGCA"[code]
+            f0 = __funnelshift_r(f0, f1, 8); f1 = __funnelshift_r(f1, f2, 8); f2 = __funnelshift_r(f2, f3, 8);
+            f3 = __funnelshift_r(f3, f4, 8); f4 = __funnelshift_r(f4, f5, 8); f5 = fa;
+            r5 = r4 >> 24; r4 = __funnelshift_l(r3, r4, 8); r3 = __funnelshift_l(r2, r3, 8);
+            r2 = __funnelshift_l(r1, r2, 8); r1 = __funnelshift_l(r0, r1, 8); r0 = (r0 << 8) | ra;
+            Fint = ((Fint << 2) | code) & mask42;
+            Rint = (Rint >> 2) | ((uint64_t)(3u - code) << 40);
+            vbits = (vbits >> 1) | (vb << 20);
+            const int t = wi * 16 + j;
+            if (t < 20) continue;
+            if (SEEDS && (vbits & 0x7FFFu) == 0x7FFFu) {
+                const uint32_t F15 = (uint32_t)(Fint >> 12), R15 = (uint32_t)Rint & 0x3FFFFFFFu;
+                if (mm_hash64_dev((uint64_t)min(F15, R15)) < p.seed_thr) {
+                    if (t - 20 < 32) sel0 |= 1u << (t - 20); else sel1 |= 1u << (t - 52);
+                }
+            }
+            if (vbits != 0x1FFFFFu) continue;
+            const bool fwd = Fint < Rint;
+            uint64_t h;
+            if (MODE == 0) {
+                const uint64_t k1 = fwd ? ((uint64_t)f1 << 32 | f0) : ((uint64_t)r1 << 32 | r0);
+                const uint64_t k2 = fwd ? ((uint64_t)f3 << 32 | f2) : ((uint64_t)r3 << 32 | r2);
+                const uint64_t kt = fwd ? ((uint64_t)f5 << 32 | f4) : ((uint64_t)r5 << 32 | r4);
+                h = murmur21(k1, k2, kt, p.seed);
+            } else {
+                h = mm_hash64_dev(fwd ? Fint : Rint);
+            }
+            if (h > T) continue;
+            if (h == kPad) { p.has_max[g] = 1; continue; }
+            if (MODE == 1 && p.n_parts > 1) {
+                const uint32_t part = (uint32_t)__umul64hi(h * p.frac_c, (uint64_t)p.n_parts);
+                const size_t buf = (size_t)g * p.n_parts + part;
+                const uint32_t slot = atomicAdd(&p.cand_n[buf], 1u);
+                if (slot < p.cap) p.cand[buf * p.cap + slot] = h;
+            } else {
+                const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
+                if (slot < p.cap) p.cand[(size_t)g * p.cap + slot] = h;
+            }
+        }
+    }
+    if (SEEDS) {
+        uint32_t *out = p.sel + ((P0 - p.sel_first_base) >> 5);
+        out[0] = sel0; out[1] = sel1;
+    }
+}
+
 // One CTA per genome.  Dynamic shared memory: cap uint64.
 __global__ void __launch_bounds__(256) sketch_select_kernel(const ChunkParams p) {
     extern __shared__ __align__(16) uint64_t sel[];
@@ -545,8 +666,10 @@ static int sk_ensure(T *&ptr, size_t &cap, size_t need) {
 
 int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
-                   uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream) {
+                   uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream,
+                   const SeedSink *seeds) {
     if (k < 1 || k > 32) { set_error("sketch: k must be in 1..32"); return 3; }
+    if (seeds && k != 21) { set_error("sketch: fused seed marking needs k = 21"); return 3; }
     if (s == 0) { set_error("sketch: s must be > 0"); return 3; }
     if (out_stride < s) { set_error("sketch: out_stride < s"); return 3; }
     if (n >= 0x7FFFFFFFull) { set_error("sketch: too many genomes in one batch"); return 3; }
@@ -588,13 +711,17 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
     c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
     c.hashes = d_hashes; c.counts = d_counts; c.out_stride = (uint32_t)out_stride;
     c.fixed_thr = 0; c.n_parts = 0; c.part = 0; c.frac_c = 0;
+    c.plan_k = seeds ? 15 : 0; c.sel = seeds ? seeds->d_sel : nullptr;
+    c.sel_first_base = seeds ? seeds->first_base : 0; c.seed_thr = seeds ? seeds->thr : 0;
 
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        if (k == 21) sketch_scan_kernel<21, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        if (k == 21 && seeds) scan21_kernel<0, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21_kernel<0, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21) sketch_scan_kernel<21, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else sketch_scan_kernel<0, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         GB_LAUNCH_CHECK();
     }
@@ -629,8 +756,9 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
 // markers.  Shares the plan / items / scan / select pipeline of K1.
 int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                           const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
-                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream) {
+                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream, const SeedSink *seeds) {
     if (k < 1 || k > 32) { set_error("marker sketch: k must be in 1..32"); return 3; }
+    if (seeds && k != 21) { set_error("marker sketch: fused seed marking needs k = 21"); return 3; }
     if (cap < 256 || (cap & (cap - 1)) || cap > kMarkerMaxCap) { set_error("marker sketch: bad capacity"); return 3; }
     const uint32_t n_parts = cap > kMarkerPartCap ? cap / kMarkerPartCap : 1u;  // value-range partitions of a wide row
     const uint32_t part_cap = cap > kMarkerPartCap ? kMarkerPartCap : cap;
@@ -657,13 +785,17 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
     c.cand = ws.d_cand; c.redo_list = ws.d_redo_list; c.redo_n = ws.d_redo_n;
     c.hashes = d_rows; c.counts = d_counts; c.out_stride = cap;
     c.fixed_thr = ~0ull / c_marker - 1;  // keep h < (2^64-1)/c  <=>  h <= that - 1
+    c.plan_k = seeds ? 15 : 0; c.sel = seeds ? seeds->d_sel : nullptr;
+    c.sel_first_base = seeds ? seeds->first_base : 0; c.seed_thr = seeds ? seeds->thr : 0;
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (n_parts > 1) GB_CUDA(cudaMemsetAsync(ws.d_cand_n, 0, n * (size_t)n_parts * sizeof(uint32_t), stream));
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        if (k == 21) sketch_scan_kernel<21, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        if (k == 21 && seeds) scan21_kernel<1, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21_kernel<1, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21) sketch_scan_kernel<21, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else sketch_scan_kernel<0, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         GB_LAUNCH_CHECK();
     }

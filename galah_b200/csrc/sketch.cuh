@@ -20,11 +20,22 @@ struct SketchWorkspace {
 
 uint32_t sketch_set_capacity(uint32_t s);
 
+// Optional second product of the k = 21 scan: the K3 seed selection bits (one bit per base position
+// relative to first_base; bit set iff mm_hash64(canonical 15-mer) < thr), written for every word of
+// every genome of the batch.  AniIndex::add_packed_device takes them instead of running its own
+// mark pass over the same bytes.
+struct SeedSink {
+    uint32_t *d_sel;
+    uint64_t first_base;
+    uint64_t thr;
+};
+
 // Enqueue the sketch kernel over n packed genomes (layout: see sketch.cu / galah_b200.h).
 // d_hashes: n rows of out_stride uint64 (>= s), padded with 2^64-1; d_counts: n.
 int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
-                   uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream);
+                   uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream,
+                   const SeedSink *seeds = nullptr);
 
 // FracMinHash marker sketches for the skani-style screen (see sketch.cu).  cap: row stride, a power
 // of two in [256, kMarkerMaxCap]; rows wider than kMarkerPartCap are finished in value-range partitions.
@@ -38,7 +49,7 @@ inline uint32_t marker_row_capacity(uint64_t longest, uint32_t c_marker) {
 }
 int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                           const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
-                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream);
+                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream, const SeedSink *seeds = nullptr);
 
 // Synthetic genomes, generated directly in packed form on the device.
 int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length, uint32_t *d_seq2,
