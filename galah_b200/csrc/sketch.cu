@@ -144,14 +144,17 @@ __device__ __forceinline__ bool kmer_hash(const uint32_t *__restrict__ seq2,
 
 // skani-style marker hash: mm_hash64 (minimap2's invertible mix) of the canonical k-mer taken as an
 // MSB-first 2-bit integer (oracle/skani_oracle.c).  Same window extraction as kmer_hash.
+// The shift-and-add steps are written as multiplications by the equal constants (2^21 - 1, 265, 21,
+// 2^31 + 1): the scan kernels are bound by the ALU pipe (shifts, logic), and integer
+// multiply-adds issue on the FMA pipe, which has room.
 __device__ __forceinline__ uint64_t mm_hash64_dev(uint64_t key) {
-    key = ~key + (key << 21);
+    key = key * 0x1FFFFFull - 1ull;        // ~key + (key << 21)
     key = key ^ (key >> 24);
-    key = (key + (key << 3)) + (key << 8);
+    key = key * 265ull;                     // (key + (key << 3)) + (key << 8)
     key = key ^ (key >> 14);
-    key = (key + (key << 2)) + (key << 4);
+    key = key * 21ull;                      // (key + (key << 2)) + (key << 4)
     key = key ^ (key >> 28);
-    key = key + (key << 31);
+    key = key * 0x80000001ull;              // key + (key << 31)
     return key;
 }
 template <int KT>
@@ -524,8 +527,9 @@ __global__ void __launch_bounds__(256) scan21_kernel(const ChunkParams p) {
             w >>= 2;
             const uint32_t vb = vw & 1u;
             vw >>= 1;
-            const uint32_t fa = __byte_perm(0x54474341u, 0u, code);       // "ACGT"[code]
-            const uint32_t ra = __byte_perm(0x41434754u, 0u, code);       // "TGCA"[code]
+            // selector nibbles 1..3 = 4 pick the zero operand: the result is ONE byte
+            const uint32_t fa = __byte_perm(0x54474341u, 0u, code | 0x4440u);  // "ACGT"[code]
+            const uint32_t ra = __byte_perm(0x41434754u, 0u, code | 0x4440u);  // "TGCA"[code]
             f0 = __funnelshift_r(f0, f1, 8); f1 = __funnelshift_r(f1, f2, 8); f2 = __funnelshift_r(f2, f3, 8);
             f3 = __funnelshift_r(f3, f4, 8); f4 = __funnelshift_r(f4, f5, 8); f5 = fa;
             r5 = r4 >> 24; r4 = __funnelshift_l(r3, r4, 8); r3 = __funnelshift_l(r2, r3, 8);
