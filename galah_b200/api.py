@@ -188,6 +188,16 @@ def blocklist_build_local(d_rows, d_counts, n_rows, stride, d_table_max, n_block
                                                  d_hi, d_lo, d_tags, d_len, stream))
 
 
+def marker_row_capacity(longest_unit, small_genomes=False):
+    return int(lib().galah_b200_marker_row_capacity(int(longest_unit), int(bool(small_genomes))))
+
+
+def prefilter_join_enqueue_screen(d_rows, d_counts, n, stride, faster_small, d_hi, d_lo, d_tags, d_len, shard, n_shards,
+                                  stream, d_cand, cand_cap, d_n_cand):
+    check(lib().galah_b200_prefilter_join_enqueue_screen(d_rows, d_counts, n, stride, int(bool(faster_small)), d_hi, d_lo,
+                                                         d_tags, d_len, shard, n_shards, stream, d_cand, cand_cap, d_n_cand))
+
+
 def prefilter_join_enqueue(d_hashes, d_counts, n, stride, k, min_ani, d_hi, d_lo, d_tags, d_len, shard, n_shards,
                            stream, d_cand, cand_cap, d_n_cand):
     check(lib().galah_b200_prefilter_join_enqueue(d_hashes, d_counts, n, stride, k, ctypes.c_float(min_ani), d_hi,
@@ -292,6 +302,17 @@ class AniIndex:
         check(lib().galah_b200_ingest_packed(int(seq2), int(valid), int(d_base_off), base_off.ctypes.data_as(_native.u64p),
                                              lengths.ctypes.data_as(_native.u64p), len(lengths), int(bool(device)),
                                              int(d_hashes), int(d_counts), self._h, ms))
+        return float(ms[0]), float(ms[1])
+
+    def ingest_packed_markers(self, seq2, valid, base_off, lengths, marker_stride, d_rows, d_counts, device=False,
+                              d_base_off=0):
+        """As ingest_packed, with FracMinHash marker rows (the skani-style screen's input) of stride marker_stride."""
+        base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+        ms = (ctypes.c_float * 2)()
+        check(lib().galah_b200_ingest_packed_markers(int(seq2), int(valid), int(d_base_off),
+                                                     base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p),
+                                                     len(lengths), int(bool(device)), int(marker_stride), int(d_rows),
+                                                     int(d_counts), self._h, ms))
         return float(ms[0]), float(ms[1])
 
     def export_tables(self):

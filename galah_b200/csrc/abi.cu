@@ -894,6 +894,24 @@ int galah_b200_prefilter_join_enqueue(const uint64_t *d_hashes, const uint32_t *
     return join_launch(g_ctx.pws, p, d_hi, d_lo, d_tags, d_len, shard, n_shards, st);
 }
 
+int galah_b200_prefilter_join_enqueue_screen(const uint64_t *d_rows, const uint32_t *d_counts, size_t n, size_t stride,
+                                             int faster_small, const uint32_t *d_hi, const uint32_t *d_lo,
+                                             const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard,
+                                             uint32_t n_shards, void *stream, uint32_t *d_cand, size_t cand_cap,
+                                             unsigned long long *d_n_cand) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!join_supported(stride)) { set_error("prefilter_join: unsupported stride"); return GALAH_B200_ERR_ARG; }
+    KernelParams p;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = prefilter_prepare(g_ctx.pws, d_rows, d_counts, n, stride, 21, 0.f, shard, n_shards, st,
+                                   reinterpret_cast<uint4 *>(d_cand), cand_cap, d_n_cand, p,
+                                   faster_small ? kRuleContainment : kRuleContainmentBypassSmall, pow(0.80, 21.0)))
+        return rc;
+    if (n < 2) return 0;
+    return join_launch(g_ctx.pws, p, d_hi, d_lo, d_tags, d_len, shard, n_shards, st);
+}
+
 int galah_b200_prefilter_join_items_enqueue(const uint64_t *d_hashes, const uint32_t *d_counts, size_t n, size_t stride,
                                             uint8_t k, float min_ani, const uint32_t *d_hi, const uint32_t *d_lo,
                                             const uint8_t *d_tags, const uint32_t *d_len, const uint32_t *d_items,
@@ -1302,9 +1320,12 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
 // device table d_table / d_counts (stride 1000) and the K3 index.  `device`: the arrays are resident
 // in HBM (d_base_off = device copy of base_off); else host arrays, uploaded in batches of ~1 G
 // bases on the copy stream while the previous batch is sketched and indexed.  Caller holds g_mu.
+// marker_c != 0: the rows are FracMinHash MARKER sketches (k = 21, density 1 / marker_c, row stride
+// marker_stride) for the skani-style screen instead of bottom-1000 MinHash sketches.
 static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off_or_null,
                          const uint64_t *base_off, const uint64_t *lengths, size_t n, bool device, uint64_t *d_table,
-                         uint32_t *d_counts, AniIndex &index, float *sketch_ms_out, float *index_ms_out) {
+                         uint32_t *d_counts, AniIndex &index, float *sketch_ms_out, float *index_ms_out,
+                         uint32_t marker_c = 0, uint32_t marker_stride = 0) {
     for (size_t g = 0; g <= n; g++)
         if (base_off[g] % 128) { set_error("packed genomes: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
     const uint32_t s = 1000;
@@ -1379,8 +1400,12 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         GB_CUDA(cudaEventRecord(ev[0], st));
         SeedSink seed_sink{nullptr, 0, 0};  // the k = 21 scan also marks the K3 seeds of the batch
         if (int rc = seed_sink_for(index, bo.front(), bo.back(), seed_sink)) return rc;
-        if (int rc = sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, s, 0, d_table + g0 * (size_t)s,
-                                    d_counts + g0, s, st, &seed_sink))
+        if (marker_c) {
+            if (int rc = marker_sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, marker_c, marker_stride,
+                                               d_table + g0 * (size_t)marker_stride, d_counts + g0, st, &seed_sink))
+                return rc;
+        } else if (int rc = sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, s, 0, d_table + g0 * (size_t)s,
+                                           d_counts + g0, s, st, &seed_sink))
             return rc;
         GB_CUDA(cudaEventRecord(ev[1], st));
         if (int rc = index.add_packed_device(b_seq2, b_valid, b_off, nb, bo, co, cs, cl, st, seed_sink.d_sel)) return rc;
@@ -1440,6 +1465,24 @@ int galah_b200_ingest_packed(const uint32_t *seq2, const uint32_t *valid, const 
     int rc = ingest_packed(seq2, valid, d_base_off, base_off, lengths, n, device != 0, d_hashes, d_counts, idx->impl, &a, &b);
     if (ms2) { ms2[0] = a; ms2[1] = b; }
     return rc;
+}
+
+int galah_b200_ingest_packed_markers(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,
+                                     const uint64_t *base_off, const uint64_t *lengths, size_t n, int device,
+                                     uint32_t marker_stride, uint64_t *d_rows, uint32_t *d_counts,
+                                     galah_b200_ani_index_t *idx, float *ms2) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx || !d_rows || !d_counts) { set_error("ingest_packed_markers: NULL argument"); return GALAH_B200_ERR_ARG; }
+    float a = 0.f, b = 0.f;
+    int rc = ingest_packed(seq2, valid, d_base_off, base_off, lengths, n, device != 0, d_rows, d_counts, idx->impl, &a, &b,
+                           idx->impl.c() == 30u ? 200u : 1000u, marker_stride);
+    if (ms2) { ms2[0] = a; ms2[1] = b; }
+    return rc;
+}
+
+uint32_t galah_b200_marker_row_capacity(uint64_t longest_unit, int small_genomes) {
+    return marker_row_capacity(longest_unit, small_genomes ? 200u : 1000u);
 }
 
 int galah_b200_ani_index_export_tables(const galah_b200_ani_index_t *idx, uint8_t handle[64], uint64_t *table_off,

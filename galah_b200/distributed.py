@@ -214,14 +214,16 @@ class ShardedPrefilter:
             elif rnd == 0:
                 self.d_ncand.zero_()
 
-    def step_device(self, k=21, min_ani=0.9):
+    def step_device(self, k=21, min_ani=0.9, screen=None):
         """Everything after the upload, enqueued on the current stream: my_table / my_counts (device)
-        -> candidates in d_cand / d_ncand.  No host synchronisation."""
+        -> candidates in d_cand / d_ncand.  No host synchronisation.  screen = None: the finch rule
+        (Mash ANI >= min_ani); screen = faster_small (bool): the rows are marker sketches and the join
+        applies the skani-style containment rule."""
         t, gb, dist = self.torch, self.gb, self.dist
         st = t.cuda.current_stream().cuda_stream
         n, s, w, r = self.n, self.s, self.world, self.rank
         m = w * self.nbp * self.epb
-        if self.ring:
+        if self.ring and screen is None:
             return self._step_ring(k, min_ani)
         if self.local_build:
             gb.table_max_device(self.my_table.data_ptr(), self.my_counts.data_ptr(), self.n_local, s,
@@ -251,6 +253,12 @@ class ShardedPrefilter:
             dist.all_gather_into_tensor(self.all_lo[:m], self.my_lo)
             dist.all_gather_into_tensor(self.all_tags[:m], self.my_tags)
             dist.all_gather_into_tensor(self.all_len, self.my_len)
+        if screen is not None:
+            gb.prefilter_join_enqueue_screen(self.table.data_ptr(), self.counts.data_ptr(), n, s, bool(screen),
+                                             self.all_hi.data_ptr(), self.all_lo.data_ptr(), self.all_tags.data_ptr(),
+                                             self.all_len.data_ptr(), r, w, st, self.d_cand.data_ptr(), self.cand_cap,
+                                             self.d_ncand.data_ptr())
+            return
         gb.prefilter_join_enqueue(self.table.data_ptr(), self.counts.data_ptr(), n, s, k, min_ani,
                                   self.all_hi.data_ptr(), self.all_lo.data_ptr(), self.all_tags.data_ptr(),
                                   self.all_len.data_ptr(), r, w, st, self.d_cand.data_ptr(), self.cand_cap,
@@ -396,6 +404,79 @@ class ShardedPipeline:
                     remote_reference_pairs=int(np.sum(r_owner != rank)), sketch_ms=k1_ms, index_ms=idx_ms,
                     ingest_ms=1e3 * (t1 - t0), prefilter_ms=1e3 * (t2 - t1), ani_ms=1e3 * (t3 - t2), ani_chain_ms=chain_ms,
                     engine_ms=1e3 * (t4 - t3), total_ms=1e3 * (t4 - t0))
+        return clusters, info
+
+    def run_skani(self, seq2, valid, d_base_off, base_off, lengths, device, threshold_pct=95.0, ani_pct=95.0, min_af=15.0,
+                  small_genomes=True, individual_contigs=True):
+        """cluster() with SkaniPreclusterer + SkaniClusterer / --cluster-contigs (skip_clusterer: the
+        preclusterer's ANIs decide, src/clusterer.rs:32-44) on G GPUs -- BASELINE.json configs[4].  The
+        pipeline's stride must be marker_row_capacity(longest unit, small_genomes).  Every rank makes the
+        marker sketches + K3 index of ITS units in one pass; the marker table and block lists are
+        all-gathered; the containment screen is row-block sharded; a screened pair (i, j) is evaluated
+        by the owner of i (the query, src/skani.rs:109-225) reading j's table in place; rank 0 runs the engine."""
+        import time
+        t, gb, dist, sp = self.torch, self.gb, self.dist, self.sp
+        rank, world, n_local, n = self.rank, self.world, self.n_local, self.n
+        t0 = time.perf_counter()
+        if small_genomes not in self._idx:
+            self._idx[small_genomes] = gb.AniIndex(small_genomes=small_genomes)
+        idx = self._idx[small_genomes]
+        idx.clear()
+        mk_ms, idx_ms = idx.ingest_packed_markers(seq2, valid, base_off, lengths, self.s, sp.my_table.data_ptr(),
+                                                  sp.my_counts.data_ptr(), device=device, d_base_off=d_base_off)
+        t.cuda.synchronize()
+        if int((sp.my_counts == -1).sum().item()):
+            raise RuntimeError("a unit holds more markers than the row stride")
+        t1 = time.perf_counter()
+        sp.step_device(21, 0.0, screen=small_genomes)
+        got = int(sp.d_ncand.item())
+        if got > sp.cand_cap:
+            sp._grow_candidates(got)
+            sp.step_device(21, 0.0, screen=small_genomes)
+            got = int(sp.d_ncand.item())
+        sp.h_cand[:got].copy_(sp.d_cand[:got])
+        mine = sp.h_cand[:got].numpy().view(np.uint32).copy()
+        t2 = time.perf_counter()
+        parts = self._allgather_var(mine, np.uint32, 4)
+        allc = np.concatenate(parts) if parts else np.zeros((0, 4), np.uint32)
+        allc = allc[np.lexsort((allc[:, 1], allc[:, 0]))]
+        owner = route_hits(allc[:, 0], n_local, world)
+        my_rows = np.nonzero(owner == rank)[0]
+        handle, table_off, total_len = idx.export_tables()
+        metas = [None] * world
+        dist.all_gather_object(metas, (handle, table_off, total_len))
+        r_owner = route_hits(allc[my_rows, 1], n_local, world)
+        base = np.zeros(world, np.int64)
+        for peer in sorted(set(int(x) for x in r_owner) - {rank}):
+            base[peer] = idx.attach_peer(*metas[peer])
+        q_local = allc[my_rows, 0].astype(np.int64) - rank * n_local
+        r_id = base[r_owner] + (allc[my_rows, 1].astype(np.int64) - r_owner * n_local)
+        res = idx.pairs(np.stack([q_local, r_id], axis=1).astype(np.uint32), min_af, individual_contigs=individual_contigs)
+        chain_ms = idx.last_timing()[1]
+        t3 = time.perf_counter()
+        keep = res["ani"] >= np.float32(threshold_pct)  # `if ani >= threshold`, src/skani.rs:205
+        back = np.zeros((int(keep.sum()), 2), np.uint32)
+        back[:, 0] = my_rows[keep]
+        back[:, 1] = res["ani"][keep].view(np.uint32)
+        got_back = self._allgather_var(back, np.uint32, 2)
+        dist.barrier()
+        idx.clear()
+        clusters, info = None, {}
+        if rank == 0:
+            rows = np.concatenate([p[:, 0] for p in got_back]).astype(np.int64)
+            anis = np.concatenate([p[:, 1] for p in got_back]).view(np.float32)
+            order = np.argsort(rows, kind="stable")
+            rows, anis = rows[order], anis[order]
+            hits = np.zeros(len(rows), PAIR_DTYPE)
+            hits["i"], hits["j"], hits["common"], hits["total"] = allc[rows, 0], allc[rows, 1], allc[rows, 2], allc[rows, 3]
+            hits["ani"] = anis
+            clusters, cinfo = gb.cluster_from_distances(n, hits, ani_pct, None, skip_clusterer=True)
+            info.update(cinfo)
+            info["n_hits"] = int(len(hits))
+        t4 = time.perf_counter()
+        info.update(n_screened=int(len(allc)), my_ani_pairs=int(len(my_rows)), remote_reference_pairs=int(np.sum(r_owner != rank)),
+                    markers_ms=mk_ms, index_ms=idx_ms, ingest_ms=1e3 * (t1 - t0), screen_ms=1e3 * (t2 - t1),
+                    ani_ms=1e3 * (t3 - t2), ani_chain_ms=chain_ms, engine_ms=1e3 * (t4 - t3), total_ms=1e3 * (t4 - t0))
         return clusters, info
 
     def step_device(self, d_seq2, d_valid, d_base_off, base_off, lengths, min_ani=0.9, ani_pct=95.0, min_af=15.0,

@@ -346,6 +346,21 @@ int galah_b200_cluster_packed_device(const uint32_t *d_seq2, const uint32_t *d_v
 int galah_b200_ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,
                              const uint64_t *base_off, const uint64_t *lengths, size_t n, int device,
                              uint64_t *d_hashes, uint32_t *d_counts, galah_b200_ani_index_t *idx, float *ms2);
+/* The same for the skani-style preclusterer: the rows are FracMinHash MARKER sketches (k = 21,
+ * 1/1000, or 1/200 when idx was created with small_genomes) at row stride marker_stride
+ * (galah_b200_marker_row_capacity of the longest unit), overflowing rows flagged 0xFFFFFFFF in
+ * d_counts.  galah_b200_prefilter_join_enqueue_screen is the join with the marker-containment rule
+ * (faster_small = skani --faster-small, part of --small-genomes) over such rows. */
+int galah_b200_ingest_packed_markers(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,
+                                     const uint64_t *base_off, const uint64_t *lengths, size_t n, int device,
+                                     uint32_t marker_stride, uint64_t *d_rows, uint32_t *d_counts,
+                                     galah_b200_ani_index_t *idx, float *ms2);
+uint32_t galah_b200_marker_row_capacity(uint64_t longest_unit, int small_genomes);
+int galah_b200_prefilter_join_enqueue_screen(const uint64_t *d_rows, const uint32_t *d_counts, size_t n, size_t stride,
+                                             int faster_small, const uint32_t *d_hi, const uint32_t *d_lo,
+                                             const uint8_t *d_tags, const uint32_t *d_len, uint32_t shard,
+                                             uint32_t n_shards, void *stream, uint32_t *d_cand, size_t cand_cap,
+                                             unsigned long long *d_n_cand);
 /* Multi-GPU stage 2 without a collective: a process exports the CUDA IPC handle of its index's
  * hash-table array plus the per-genome slot offsets (size + 1 entries) and lengths (size entries);
  * a peer process on the same NVLink domain attaches it, after which the peer's genomes can be the

@@ -61,6 +61,34 @@ def main():
                       f"{int(remote.item())} stage-2 jobs read a peer's table: {'OK' if same else 'MISMATCH'}", flush=True)
                 ok = ok and same
                 del a_seq, a_val, a_off
+    # ---- contig mode (BASELINE.json configs[4] shape): run_skani vs the single-GPU preclusterer + engine
+    for n_local, L, fam in ((640, 30_000, 10), (384, 20_000, 7)):
+        n = n_local * world
+
+        def synth(index_begin, count):
+            lay = gb.synth_layout(count, L)
+            d_seq = torch.empty(lay["seq2_words"], dtype=torch.int32, device=dev)
+            d_val = torch.empty(lay["valid_words"], dtype=torch.int32, device=dev)
+            d_off = torch.empty(count + 1, dtype=torch.int64, device=dev)
+            gb.synth_packed_device_ex(7, index_begin, count, L, fam, 0, d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), st)
+            torch.cuda.synchronize()
+            return d_seq, d_val, d_off, np.arange(count + 1, dtype=np.uint64) * np.uint64(lay["padded"]), np.full(count, L, np.uint64)
+
+        d_seq, d_val, d_off, bo, ln = synth(rank * n_local, n_local)
+        pipe = ShardedPipeline(gb, dist, n_local, gb.marker_row_capacity(L, True), dev)
+        clusters, info = pipe.run_skani(d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), bo, ln, True, 92.0, 92.0, 15.0,
+                                        small_genomes=True, individual_contigs=True)
+        remote = torch.tensor([info["remote_reference_pairs"]], device=dev)
+        dist.all_reduce(remote)
+        if rank == 0:
+            a_seq, a_val, a_off, a_bo, a_ln = synth(0, n)
+            hits, _ = gb.skani_distances_packed_device(a_seq.data_ptr(), a_val.data_ptr(), a_off.data_ptr(), a_bo, a_ln, 92.0,
+                                                       15.0, small_genomes=True, stream=st)
+            exp, _ = gb.cluster_from_distances(n, hits, 92.0, None, skip_clusterer=True)
+            same = clusters == exp and info["n_hits"] == len(hits)
+            print(f"contigs n_local={n_local} L={L} family={fam}: {len(exp)} clusters, {len(hits)} hits, "
+                  f"{int(remote.item())} pairs read a peer's table: {'OK' if same else 'MISMATCH'}", flush=True)
+            ok = ok and same
     if rank == 0:
         print("ALL OK" if ok else "FAILED", flush=True)
     dist.barrier()
