@@ -365,17 +365,12 @@ def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, s
     rc = lib().galah_b200_cluster_from_distances(int(n_genomes), hits.ctypes.data, len(hits),
                                                  int(bool(skip_clusterer)), ctypes.c_float(ani_threshold),
                                                  cb, None, ctypes.byref(res))
-    try:
+    if calls["exc"] is not None or rc:
+        lib().galah_b200_clusters_free(ctypes.byref(res))
         if calls["exc"] is not None:  # the callback's own failure comes first: the engine only saw a None
             raise calls["exc"]
         check(rc)
-        off = [res.offsets[x] for x in range(res.n_clusters + 1)]
-        clusters = [[int(res.members[y]) for y in range(off[x], off[x + 1])] for x in range(res.n_clusters)]
-        info = {"ani_calls": int(res.ani_calls), "n_preclusters": int(res.n_preclusters),
-                "largest_precluster": int(res.largest_precluster)}
-    finally:
-        lib().galah_b200_clusters_free(ctypes.byref(res))
-    return clusters, info
+    return _take_clusters(res)
 
 
 def cluster_from_ani_table(n_genomes, hits, ani, ani_threshold):

@@ -38,6 +38,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 
 #include "common.cuh"
 
@@ -824,14 +825,31 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
     float ms = 0.f;
     GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     last_chain_ms = ms;
-    for (size_t x = 0; x < n_pairs; x++) {
-        const uint32_t *a = &acc[(size_t)kAccWords * x];
-        AniPairInts v;
-        v.sum_fx = fx[x]; v.n_chunks = a[0]; v.cov_q = a[1]; v.cov_r = a[2]; v.sum_m = a[3];
-        v.span_m = a[4]; v.span_n = a[5]; v.n_chains = a[6];
-        const uint32_t r = pairs[2 * x + 1];
-        const uint64_t len_r = r < n_local ? total_len_[r] : peer_total_len_[r - n_local];
-        out[x] = ani_finish(v, total_len_[pairs[2 * x]], len_r, c_, individual_contigs, min_af_pct);
+    // host finish (a division or pow + the exact two-decimal rounding per pair): split over the host
+    // threads when the call is large, so that it does not become the serial tail of the stage
+    auto finish_range = [&](size_t x0, size_t x1) {
+        for (size_t x = x0; x < x1; x++) {
+            const uint32_t *a = &acc[(size_t)kAccWords * x];
+            AniPairInts v;
+            v.sum_fx = fx[x]; v.n_chunks = a[0]; v.cov_q = a[1]; v.cov_r = a[2]; v.sum_m = a[3];
+            v.span_m = a[4]; v.span_n = a[5]; v.n_chains = a[6];
+            const uint32_t r = pairs[2 * x + 1];
+            const uint64_t len_r = r < n_local ? total_len_[r] : peer_total_len_[r - n_local];
+            out[x] = ani_finish(v, total_len_[pairs[2 * x]], len_r, c_, individual_contigs, min_af_pct);
+        }
+    };
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t nt = n_pairs >= 65536 ? std::min<size_t>(hw, 32) : 1;
+    if (nt == 1) {
+        finish_range(0, n_pairs);
+    } else {
+        std::vector<std::thread> th;
+        const size_t per = (n_pairs + nt - 1) / nt;
+        for (size_t t = 0; t < nt; t++) {
+            const size_t x0 = t * per, x1 = std::min(n_pairs, x0 + per);
+            if (x0 < x1) th.emplace_back(finish_range, x0, x1);
+        }
+        for (auto &t : th) t.join();
     }
     return 0;
 }

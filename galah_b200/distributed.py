@@ -359,7 +359,7 @@ class ShardedPipeline:
         packed[:, 4] = mine["ani"].view(np.uint32)
         parts = self._allgather_var(packed, np.uint32, 5)
         allh = np.concatenate(parts) if parts else np.zeros((0, 5), np.uint32)
-        order = np.lexsort((allh[:, 1], allh[:, 0]))
+        order = np.argsort((allh[:, 0].astype(np.uint64) << np.uint64(32)) | allh[:, 1].astype(np.uint64), kind="stable")
         allh = allh[order]
         # ---- stage-2 jobs: both orientations of every hit (calculate_ani(rep, genome) makes the
         # representative the query, and the membership pass asks for representatives on either side of
@@ -439,7 +439,7 @@ class ShardedPipeline:
         t2 = time.perf_counter()
         parts = self._allgather_var(mine, np.uint32, 4)
         allc = np.concatenate(parts) if parts else np.zeros((0, 4), np.uint32)
-        allc = allc[np.lexsort((allc[:, 1], allc[:, 0]))]
+        allc = allc[np.argsort((allc[:, 0].astype(np.uint64) << np.uint64(32)) | allc[:, 1].astype(np.uint64), kind="stable")]
         owner = route_hits(allc[:, 0], n_local, world)
         my_rows = np.nonzero(owner == rank)[0]
         handle, table_off, total_len = idx.export_tables()
