@@ -357,8 +357,11 @@ def main():
     if not args.no_e2e:
         import psutil
         need = resident_bytes
-        avail = psutil.virtual_memory().available
-        if avail > 2.5 * need + (8 << 30):
+        vm = psutil.virtual_memory()
+        avail = vm.available
+        # every rank pins a host copy of ITS packed genomes: all of them together must stay well inside
+        # the box's memory (a box driven out of memory is worse than a missing sub-record)
+        if need * world <= 0.45 * vm.total and avail > 1.3 * need * world + (16 << 30):
             h_seq = torch.empty(d_seq.numel(), dtype=torch.int32, pin_memory=True)
             h_val = torch.empty(d_val.numel(), dtype=torch.int32, pin_memory=True)
             h_seq.copy_(d_seq); h_val.copy_(d_val)
@@ -392,7 +395,8 @@ def main():
             del h_seq, h_val
         else:
             e2e = {"value": None, "unit": "pairs/s", "h2d_bytes_per_step": int(need), "d2h_bytes_per_step": 0,
-                   "skipped": f"host has {avail >> 30} GiB available, pinned copy of the packed genomes needs {need >> 30} GiB"}
+                   "skipped": f"host has {avail >> 30} GiB available of {vm.total >> 30}; the pinned copies of the packed genomes "
+                              f"need {need * world >> 30} GiB on this box (limit: 45 % of its memory)"}
 
     line = None
     if rank == 0:
