@@ -328,6 +328,26 @@ class ShardedPipeline:
         allb = allb.cpu().numpy().view(dtype).reshape(self.world, cap, width)
         return [allb[r, : int(ms[r])] for r in range(self.world)]
 
+    def _route_var(self, arr, dest, dtype, width):
+        """Variable all-to-all of the rows of a host (m, width) array of `dtype`: row x goes to rank
+        dest[x]; returns the rows this rank receives (grouped by source rank, source order kept).
+        One NCCL all_to_all_single over byte buffers (the counts travel first)."""
+        t, dist = self.torch, self.dist
+        world = self.world
+        order = np.argsort(dest, kind="stable")
+        send = np.ascontiguousarray(arr[order])
+        counts = np.bincount(dest, minlength=world).astype(np.int64)
+        c_in = t.from_numpy(counts).to(self.dev)
+        c_out = t.empty(world, dtype=t.int64, device=self.dev)
+        dist.all_to_all_single(c_out, c_in)
+        recv_counts = c_out.cpu().numpy()
+        row = width * np.dtype(dtype).itemsize
+        src = t.from_numpy(send.view(np.uint8).reshape(-1)).to(self.dev) if len(send) else t.empty(0, dtype=t.uint8, device=self.dev)
+        dst = t.empty(int(recv_counts.sum()) * row, dtype=t.uint8, device=self.dev)
+        dist.all_to_all_single(dst, src, output_split_sizes=[int(c) * row for c in recv_counts],
+                               input_split_sizes=[int(c) * row for c in counts])
+        return dst.cpu().numpy().view(dtype).reshape(-1, width)
+
     def _run(self, seq2, valid, d_base_off, base_off, lengths, device, min_ani, ani_pct, min_af, small_genomes=False):
         import time
         t, gb, dist, sp = self.torch, self.gb, self.dist, self.sp
@@ -437,44 +457,43 @@ class ShardedPipeline:
         sp.h_cand[:got].copy_(sp.d_cand[:got])
         mine = sp.h_cand[:got].numpy().view(np.uint32).copy()
         t2 = time.perf_counter()
-        parts = self._allgather_var(mine, np.uint32, 4)
-        allc = np.concatenate(parts) if parts else np.zeros((0, 4), np.uint32)
-        allc = allc[np.argsort((allc[:, 0].astype(np.uint64) << np.uint64(32)) | allc[:, 1].astype(np.uint64), kind="stable")]
-        owner = route_hits(allc[:, 0], n_local, world)
-        my_rows = np.nonzero(owner == rank)[0]
+        # every screened pair travels ONCE, to the rank that owns its query genome (the lower index)
+        myc = self._route_var(mine, route_hits(mine[:, 0], n_local, world), np.uint32, 4)
+        myc = myc[np.argsort((myc[:, 0].astype(np.uint64) << np.uint64(32)) | myc[:, 1].astype(np.uint64), kind="stable")]
         handle, table_off, total_len = idx.export_tables()
         metas = [None] * world
         dist.all_gather_object(metas, (handle, table_off, total_len))
-        r_owner = route_hits(allc[my_rows, 1], n_local, world)
+        r_owner = route_hits(myc[:, 1], n_local, world)
         base = np.zeros(world, np.int64)
         for peer in sorted(set(int(x) for x in r_owner) - {rank}):
             base[peer] = idx.attach_peer(*metas[peer])
-        q_local = allc[my_rows, 0].astype(np.int64) - rank * n_local
-        r_id = base[r_owner] + (allc[my_rows, 1].astype(np.int64) - r_owner * n_local)
+        q_local = myc[:, 0].astype(np.int64) - rank * n_local
+        r_id = base[r_owner] + (myc[:, 1].astype(np.int64) - r_owner * n_local)
         res = idx.pairs(np.stack([q_local, r_id], axis=1).astype(np.uint32), min_af, individual_contigs=individual_contigs)
         chain_ms = idx.last_timing()[1]
         t3 = time.perf_counter()
         keep = res["ani"] >= np.float32(threshold_pct)  # `if ani >= threshold`, src/skani.rs:205
-        back = np.zeros((int(keep.sum()), 2), np.uint32)
-        back[:, 0] = my_rows[keep]
-        back[:, 1] = res["ani"][keep].view(np.uint32)
-        got_back = self._allgather_var(back, np.uint32, 2)
+        back = np.zeros((int(keep.sum()), 5), np.uint32)
+        back[:, :4] = myc[keep]
+        back[:, 4] = res["ani"][keep].view(np.uint32)
+        n_screened = t.tensor([len(myc)], dtype=t.int64, device=self.dev)
+        dist.all_reduce(n_screened)
+        hits_all = self._route_var(back, np.zeros(len(back), np.int64), np.uint32, 5)  # the hits go to rank 0 only
         dist.barrier()
         idx.clear()
         clusters, info = None, {}
         if rank == 0:
-            rows = np.concatenate([p[:, 0] for p in got_back]).astype(np.int64)
-            anis = np.concatenate([p[:, 1] for p in got_back]).view(np.float32)
-            order = np.argsort(rows, kind="stable")
-            rows, anis = rows[order], anis[order]
-            hits = np.zeros(len(rows), PAIR_DTYPE)
-            hits["i"], hits["j"], hits["common"], hits["total"] = allc[rows, 0], allc[rows, 1], allc[rows, 2], allc[rows, 3]
-            hits["ani"] = anis
+            hits_all = hits_all[np.argsort((hits_all[:, 0].astype(np.uint64) << np.uint64(32)) | hits_all[:, 1].astype(np.uint64),
+                                           kind="stable")]
+            hits = np.zeros(len(hits_all), PAIR_DTYPE)
+            hits["i"], hits["j"], hits["common"], hits["total"] = hits_all[:, 0], hits_all[:, 1], hits_all[:, 2], hits_all[:, 3]
+            hits["ani"] = hits_all[:, 4].view(np.float32)
             clusters, cinfo = gb.cluster_from_distances(n, hits, ani_pct, None, skip_clusterer=True)
             info.update(cinfo)
             info["n_hits"] = int(len(hits))
+        allc, my_rows = myc, np.arange(len(myc))
         t4 = time.perf_counter()
-        info.update(n_screened=int(len(allc)), my_ani_pairs=int(len(my_rows)), remote_reference_pairs=int(np.sum(r_owner != rank)),
+        info.update(n_screened=int(n_screened.item()), my_ani_pairs=int(len(my_rows)), remote_reference_pairs=int(np.sum(r_owner != rank)),
                     markers_ms=mk_ms, index_ms=idx_ms, ingest_ms=1e3 * (t1 - t0), screen_ms=1e3 * (t2 - t1),
                     ani_ms=1e3 * (t3 - t2), ani_chain_ms=chain_ms, engine_ms=1e3 * (t4 - t3), total_ms=1e3 * (t4 - t0))
         return clusters, info
