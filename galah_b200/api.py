@@ -398,13 +398,56 @@ def cluster_from_ani_tables(n_genomes, hits, ani_fwd, ani_rev, ani_threshold):
     return _take_clusters(res)
 
 
+class ClusterList:
+    """galah's Vec<Vec<usize>> as two arrays (members concatenated, representative first in each
+    cluster; offsets): behaves like a read-only list of lists, without building a million Python
+    lists unless asked to (`tolist()`)."""
+
+    def __init__(self, members, offsets):
+        self.members, self.offsets = members, offsets
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def __getitem__(self, x):
+        if isinstance(x, slice):
+            return [self[y] for y in range(*x.indices(len(self)))]
+        if x < 0:
+            x += len(self)
+        return self.members[self.offsets[x]:self.offsets[x + 1]].tolist()
+
+    def __iter__(self):
+        m, o = self.members.tolist(), self.offsets.tolist()
+        return (m[o[x]:o[x + 1]] for x in range(len(o) - 1))
+
+    def tolist(self):
+        return list(self)
+
+    def __eq__(self, other):
+        if isinstance(other, ClusterList):
+            return np.array_equal(self.members, other.members) and np.array_equal(self.offsets, other.offsets)
+        return self.tolist() == other
+
+    def __repr__(self):
+        return repr(self.tolist()) if len(self) <= 64 else f"<ClusterList of {len(self)} clusters, {len(self.members)} members>"
+
+    def sha1(self):
+        """Digest of the cluster SET (clusters sorted by their member lists), for comparing runs."""
+        import hashlib
+        order = sorted(range(len(self)), key=lambda x: self.members[self.offsets[x]:self.offsets[x + 1]].tobytes()) \
+            if len(self) < 4096 else np.lexsort((np.diff(self.offsets), self.members[self.offsets[:-1]]))
+        h = hashlib.sha1()
+        for x in order:
+            h.update(self.members[self.offsets[x]:self.offsets[x + 1]].astype(np.uint32).tobytes()); h.update(b"|")
+        return h.hexdigest()
+
+
 def _take_clusters(res):
     try:
         nc = int(res.n_clusters)
         off = np.ctypeslib.as_array(res.offsets, shape=(nc + 1,)).astype(np.int64) if nc else np.zeros(1, np.int64)
         mem = np.ctypeslib.as_array(res.members, shape=(int(off[-1]),)).copy() if nc and off[-1] else np.zeros(0, np.uint32)
-        m, o = mem.tolist(), off.tolist()
-        clusters = [m[o[x]:o[x + 1]] for x in range(nc)]
+        clusters = ClusterList(mem, off)
         info = {"ani_calls": int(res.ani_calls), "n_preclusters": int(res.n_preclusters),
                 "largest_precluster": int(res.largest_precluster)}
     finally:

@@ -79,15 +79,12 @@ def main():
         if it >= 1:
             times.append(float(dt.item())); infos.append(info)
     if rank == 0:
-        h = hashlib.sha1()
-        for c in sorted(clusters):
-            h.update(np.asarray(c, np.uint32).tobytes()); h.update(b"|")
         pairs = n * (n - 1) // 2
         t = float(np.mean(times))
         keys = [k for k in infos[-1] if k.endswith("_ms")]
         line = {"config": f"BASELINE.json configs[{args.config}]", "n_gpus": world, "units": n, "unit_bp": L, "pairs": pairs,
                 "seconds_per_pass": t, "pairs_per_s": pairs / t, "clusters": len(clusters),
-                "clusters_sha1": h.hexdigest(), "phases_ms_rank0": {k: float(np.median([i[k] for i in infos])) for k in keys},
+                "clusters_sha1": clusters.sha1(), "phases_ms_rank0": {k: float(np.median([i[k] for i in infos])) for k in keys},
                 "counts": {k: infos[-1][k] for k in infos[-1] if not k.endswith("_ms") and isinstance(infos[-1][k], (int, float))},
                 "resident_gb_per_gpu": (d_seq.numel() + d_val.numel()) * 4 / 1e9}
         print(json.dumps(line), flush=True)
