@@ -575,6 +575,221 @@ __global__ void __launch_bounds__(256) scan21_kernel(const ChunkParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// scan21 v2 (default): the same pass with the instruction count cut where ncu showed it going
+// (r2_ncu_full_k1_scan21.txt: 204 thread-instructions per k-mer, ALU pipe 74 %, FMA 25 %):
+//   * no warm-up: the state after the first 20 bases is built directly from the loaded words
+//     (bit-pair reversal for the forward integer, two PRMT look-ups per word for the ASCII bytes)
+//     instead of 20 silent rolling steps per 64 outputs;
+//   * validity of all 21-base / 15-base windows of the thread as two 64-bit masks from five
+//     shift-and-AND steps on the 96 validity bits, one bit test per position in the loop;
+//   * both 2-bit integers live LEFT-aligned in their 64-bit registers: bases fall off the top by
+//     themselves (no mask), and since k is odd a k-mer never equals its reverse complement, so the
+//     stale bits under the reverse integer cannot change `forward < reverse`;
+//   * 64-bit multiplies by constants as one wide multiply + two multiply-adds (3 FMA-pipe
+//     instructions; the compiler's expansion takes 4), MurmurHash3 specialised for seed 0;
+//   * the last xor-shift of both fmix64 and the low half of the final sum are only evaluated for
+//     hashes whose HIGH words can still be under the threshold (7 of 10,000).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return (uint64_t)hi << 32 | lo; }
+template <uint64_t C>
+__device__ __forceinline__ uint64_t mul64c(uint64_t a) {
+    const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
+    uint64_t w;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(alo), "r"((uint32_t)C));
+    uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(alo), "r"((uint32_t)(C >> 32)));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(ahi), "r"((uint32_t)C));
+    return pack64(lo, hi);
+}
+template <uint32_t M, uint64_t ADD>  // a * M + ADD, M < 2^32
+__device__ __forceinline__ uint64_t mad64s(uint64_t a) {
+    const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
+    uint64_t w;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(alo), "r"(M), "l"(ADD));
+    uint32_t hi = (uint32_t)(w >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(ahi), "r"(M));
+    return pack64((uint32_t)w, hi);
+}
+__device__ __forceinline__ uint64_t rotl64f(uint64_t x, int r) {  // r in 1..63, r != 32
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (r < 32) return pack64(__funnelshift_l(hi, lo, r), __funnelshift_l(lo, hi, r));
+    return pack64(__funnelshift_l(lo, hi, r - 32), __funnelshift_l(hi, lo, r - 32));
+}
+// x ^= x >> 33 only touches the low word
+__device__ __forceinline__ uint64_t xsr33(uint64_t x) {
+    const uint32_t hi = (uint32_t)(x >> 32);
+    return pack64((uint32_t)x ^ (hi >> 1), hi);
+}
+__device__ __forceinline__ uint64_t mm_hash64_v2(uint64_t key) {
+    key = mad64s<0x1FFFFFu, ~0ull>(key);  // ~key + (key << 21)
+    key ^= key >> 24;
+    key = mad64s<265u, 0ull>(key);
+    key ^= key >> 14;
+    key = mad64s<21u, 0ull>(key);
+    key ^= key >> 28;
+    key = mul64c<0x80000001ull>(key);
+    return key;
+}
+// the 96 validity bits ANDed with themselves shifted right by s
+__device__ __forceinline__ void and_shr96(uint32_t &x0, uint32_t &x1, uint32_t &x2, int s) {
+    const uint32_t y0 = __funnelshift_r(x0, x1, s), y1 = __funnelshift_r(x1, x2, s), y2 = x2 >> s;
+    x0 &= y0; x1 &= y1; x2 &= y2;
+}
+// 2-bit groups of a word in reverse order
+__device__ __forceinline__ uint32_t rev2_32(uint32_t v) {
+    v = __brev(v);
+    return ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+}
+// 8 bases (low 16 bits of x) -> nibble selectors of two PRMTs (base 0 in nibble 0)
+__device__ __forceinline__ uint32_t nibbles8(uint32_t x) {
+    x = __byte_perm(x, 0u, 0x4140);               // bytes: b0, 0, b1, 0
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    return (x | (x << 2)) & 0x33333333u;
+}
+
+template <int MODE, bool SEEDS, bool SEED0>
+__global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
+    const uint64_t item = blockIdx.x;
+    if (item >= p.chunk_off[p.n]) return;
+    const uint32_t g = p.item_genome[item];
+    const uint64_t b0 = p.base_off[g], len = p.base_off[g + 1] - b0;  // the 128-padded span
+    const uint64_t q0 = (item - p.chunk_off[g]) * kChunk + (uint64_t)threadIdx.x * 64;
+    if (q0 >= len) return;
+    const uint64_t P0 = b0 + q0;  // multiple of 64: the vector loads below are aligned
+    const uint4 s03 = __ldg(reinterpret_cast<const uint4 *>(p.seq2 + (P0 >> 4)));
+    const uint2 v01 = __ldg(reinterpret_cast<const uint2 *>(p.valid + (P0 >> 5)));
+    uint2 s45 = make_uint2(0u, 0u);
+    uint32_t v2 = 0u;
+    if (q0 + 64 < len) {  // then q0 + 128 <= len: the next 32 bases belong to this genome
+        s45 = __ldg(reinterpret_cast<const uint2 *>(p.seq2 + (P0 >> 4) + 4));
+        v2 = __ldg(p.valid + (P0 >> 5) + 2);
+    }
+    const uint64_t T = MODE == 0 ? p.thr[g] : p.fixed_thr;
+    const uint32_t Th1 = min((uint32_t)(T >> 32), 0xFFFFFFFEu) + 1u;
+
+    // ---- window validity: KV bit t = bases t .. t+20 valid, SV bit t = bases t .. t+14 valid
+    uint32_t kv0, kv1, sv0, sv1;
+    {
+        uint32_t a0 = v01.x, a1 = v01.y, a2 = v2;
+        and_shr96(a0, a1, a2, 1);   // windows of 2
+        and_shr96(a0, a1, a2, 2);   // 4
+        and_shr96(a0, a1, a2, 4);   // 8
+        sv0 = a0 & __funnelshift_r(a0, a1, 7);   // [t, t+8) and [t+7, t+15)
+        sv1 = a1 & __funnelshift_r(a1, a2, 7);
+        and_shr96(a0, a1, a2, 8);   // 16
+        kv0 = a0 & __funnelshift_r(a0, a1, 5);   // [t, t+16) and [t+5, t+21)
+        kv1 = a1 & __funnelshift_r(a1, a2, 5);
+    }
+    if ((kv0 | kv1 | (SEEDS ? sv0 | sv1 : 0u)) == 0u) {  // no window of this thread is valid
+        if (SEEDS) { uint32_t *out = p.sel + ((P0 - p.sel_first_base) >> 5); out[0] = 0u; out[1] = 0u; }
+        return;
+    }
+
+    // ---- state after bases 0 .. 19 (what 20 rolling steps from zero would leave)
+    uint32_t f0, f1, f2, f3, f4, f5;   // forward ASCII bytes: byte i + 1 = base i
+    uint32_t r0, r1, r2, r3, r4, r5;   // reverse-complement ASCII bytes: byte j = comp(base 19 - j)
+    uint32_t Flo, Fhi, Rlo, Rhi;        // left-aligned 2-bit integers (42 significant bits on top)
+    {
+        const uint32_t n0 = nibbles8(s03.x), n1 = nibbles8(s03.x >> 16), n2 = nibbles8(s03.y);
+        const uint32_t A0 = __byte_perm(0x54474341u, 0u, n0), A1 = __byte_perm(0x54474341u, 0u, n0 >> 16);
+        const uint32_t A2 = __byte_perm(0x54474341u, 0u, n1), A3 = __byte_perm(0x54474341u, 0u, n1 >> 16);
+        const uint32_t A4 = __byte_perm(0x54474341u, 0u, n2);
+        f0 = A0 << 8; f1 = __funnelshift_l(A0, A1, 8); f2 = __funnelshift_l(A1, A2, 8);
+        f3 = __funnelshift_l(A2, A3, 8); f4 = __funnelshift_l(A3, A4, 8); f5 = A4 >> 24;
+        const uint32_t B0 = __byte_perm(0x41434754u, 0u, n0), B1 = __byte_perm(0x41434754u, 0u, n0 >> 16);
+        const uint32_t B2 = __byte_perm(0x41434754u, 0u, n1), B3 = __byte_perm(0x41434754u, 0u, n1 >> 16);
+        const uint32_t B4 = __byte_perm(0x41434754u, 0u, n2);
+        r0 = __byte_perm(B4, 0u, 0x0123); r1 = __byte_perm(B3, 0u, 0x0123); r2 = __byte_perm(B2, 0u, 0x0123);
+        r3 = __byte_perm(B1, 0u, 0x0123); r4 = __byte_perm(B0, 0u, 0x0123); r5 = 0u;
+        // forward: base i at bits 60 - 2 i (base 19 at 22..23)
+        const uint64_t Fr = pack64(rev2_32(s03.y & 0xFFu), rev2_32(s03.x)) >> 2;
+        Flo = (uint32_t)Fr; Fhi = (uint32_t)(Fr >> 32);
+        // reverse: complement of base i at bits 24 + 2 i (base 19 on top)
+        const uint64_t Rr = pack64(~s03.x, ~s03.y & 0xFFu) << 24;
+        Rlo = (uint32_t)Rr; Rhi = (uint32_t)(Rr >> 32);
+    }
+    uint32_t sel0 = 0, sel1 = 0;
+#pragma unroll
+    for (int wi = 0; wi < 4; wi++) {
+        // the 16 bases that enter during this block: bases 16 wi + 20 .. 16 wi + 35
+        const uint32_t wa = wi == 0 ? s03.y : wi == 1 ? s03.z : wi == 2 ? s03.w : s45.x;
+        const uint32_t wb = wi == 0 ? s03.z : wi == 1 ? s03.w : wi == 2 ? s45.x : s45.y;
+        uint32_t inc = __funnelshift_r(wa, wb, 8);
+        // validity bits of the block: k-mer windows in bits 0..15, seed windows in bits 16..31
+        uint32_t mv = __byte_perm(wi < 2 ? kv0 : kv1, wi < 2 ? sv0 : sv1, (wi & 1) ? 0x7632 : 0x5410);
+        if (!SEEDS) mv &= 0xFFFFu;
+#pragma unroll 1
+        for (int j = 0; j < 16; j++) {
+            const uint32_t fa = __byte_perm(0x54474341u, 0u, (inc & 3u) | 0x4440u);  // "ACGT"[code]
+            f0 = __funnelshift_r(f0, f1, 8); f1 = __funnelshift_r(f1, f2, 8); f2 = __funnelshift_r(f2, f3, 8);
+            f3 = __funnelshift_r(f3, f4, 8); f4 = __funnelshift_r(f4, f5, 8); f5 = fa;
+            r5 = r4 >> 24; r4 = __funnelshift_l(r3, r4, 8); r3 = __funnelshift_l(r2, r3, 8);
+            r2 = __funnelshift_l(r1, r2, 8); r1 = __funnelshift_l(r0, r1, 8);
+            r0 = __byte_perm(r0, 0x41434754u, (inc & 3u) | 0x2104u);  // bytes: "TGCA"[code], r0.b0, r0.b1, r0.b2
+            Fhi = __funnelshift_l(Flo, Fhi, 2);
+            Flo = (Flo << 2) | ((inc << 22) & 0x00C00000u);
+            Rlo = __funnelshift_r(Rlo, Rhi, 2);
+            Rhi = (Rhi >> 2) | (~(inc << 30) & 0xC0000000u);
+            inc >>= 2;
+            const uint32_t m = mv;
+            mv >>= 1;
+            if (SEEDS && (m & 0x10000u)) {
+                const uint32_t F15 = Fhi >> 2, R15 = __funnelshift_r(Rlo, Rhi, 22) & 0x3FFFFFFFu;
+                if (mm_hash64_v2((uint64_t)min(F15, R15)) < p.seed_thr) {
+                    if (wi < 2) sel0 |= 1u << ((wi & 1) * 16 + j); else sel1 |= 1u << ((wi & 1) * 16 + j);
+                }
+            }
+            if (!(m & 1u)) continue;
+            const bool fwd = pack64(Flo, Fhi) < pack64(Rlo, Rhi);
+            uint64_t h;
+            if (MODE == 0) {
+                const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
+                uint64_t k1 = fwd ? pack64(f0, f1) : pack64(r0, r1);
+                uint64_t k2 = fwd ? pack64(f2, f3) : pack64(r2, r3);
+                uint64_t kt = fwd ? pack64(f4, f5) : pack64(r4, r5);
+                k1 = mul64c<c1>(k1); k1 = rotl64f(k1, 31); k1 = mul64c<c2>(k1);
+                k2 = mul64c<c2>(k2); k2 = rotl64f(k2, 33); k2 = mul64c<c1>(k2);
+                kt = mul64c<c1>(kt); kt = rotl64f(kt, 31); kt = mul64c<c2>(kt);
+                uint64_t h1, h2;
+                if (SEED0) {
+                    h1 = rotl64f(k1, 27); h1 = mad64s<5u, 0x52dce729ull>(h1);
+                    h2 = rotl64f(k2, 31); h2 += h1; h2 = mad64s<5u, 0x38495ab5ull>(h2);
+                } else {
+                    h1 = p.seed ^ k1; h1 = rotl64f(h1, 27); h1 += p.seed; h1 = mad64s<5u, 0x52dce729ull>(h1);
+                    h2 = p.seed ^ k2; h2 = rotl64f(h2, 31); h2 += h1; h2 = mad64s<5u, 0x38495ab5ull>(h2);
+                }
+                h1 ^= kt;
+                h1 ^= 21ull; h2 ^= 21ull;
+                h1 += h2; h2 += h1;
+                h1 = mul64c<0xc4ceb9fe1a85ec53ull>(xsr33(mul64c<0xff51afd7ed558ccdull>(xsr33(h1))));
+                h2 = mul64c<0xc4ceb9fe1a85ec53ull>(xsr33(mul64c<0xff51afd7ed558ccdull>(xsr33(h2))));
+                // the last xor-shift leaves the high words as they are: hash.hi is s or s + 1
+                const uint32_t s1 = (uint32_t)(h1 >> 32) + (uint32_t)(h2 >> 32) + 1u;
+                if (s1 > Th1) continue;
+                h = xsr33(h1) + xsr33(h2);
+            } else {
+                h = mm_hash64_v2((fwd ? pack64(Flo, Fhi) : pack64(Rlo, Rhi)) >> 22);
+            }
+            if (h > T) continue;
+            if (h == kPad) { p.has_max[g] = 1; continue; }
+            if (MODE == 1 && p.n_parts > 1) {
+                const uint32_t part = (uint32_t)__umul64hi(h * p.frac_c, (uint64_t)p.n_parts);
+                const size_t buf = (size_t)g * p.n_parts + part;
+                const uint32_t slot = atomicAdd(&p.cand_n[buf], 1u);
+                if (slot < p.cap) p.cand[buf * p.cap + slot] = h;
+            } else {
+                const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
+                if (slot < p.cap) p.cand[(size_t)g * p.cap + slot] = h;
+            }
+        }
+    }
+    if (SEEDS) {
+        uint32_t *out = p.sel + ((P0 - p.sel_first_base) >> 5);
+        out[0] = sel0; out[1] = sel1;
+    }
+}
+
 // One CTA per genome.  Dynamic shared memory: cap uint64.
 __global__ void __launch_bounds__(256) sketch_select_kernel(const ChunkParams p) {
     extern __shared__ __align__(16) uint64_t sel[];
@@ -723,7 +938,12 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        if (k == 21 && seeds) scan21_kernel<0, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        const bool v1 = getenv("GALAH_B200_SCAN_V1") != nullptr;  // the first rolling kernel, kept for A/B timing
+        if (k == 21 && !v1 && seeds && seed == 0) scan21v2_kernel<0, true, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !v1 && seeds) scan21v2_kernel<0, true, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !v1 && seed == 0) scan21v2_kernel<0, false, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !v1) scan21v2_kernel<0, false, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && seeds) scan21_kernel<0, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21_kernel<0, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else if (k == 21) sketch_scan_kernel<21, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else sketch_scan_kernel<0, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
@@ -797,7 +1017,10 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        if (k == 21 && seeds) scan21_kernel<1, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        const bool v1 = getenv("GALAH_B200_SCAN_V1") != nullptr;
+        if (k == 21 && !v1 && seeds) scan21v2_kernel<1, true, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !v1) scan21v2_kernel<1, false, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && seeds) scan21_kernel<1, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21_kernel<1, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else if (k == 21) sketch_scan_kernel<21, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else sketch_scan_kernel<0, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
