@@ -312,7 +312,7 @@ struct ChunkParams {
     uint32_t n_parts;        // 0 / 1: a single buffer per genome
     uint32_t part;           // marker_select_kernel: the partition this launch finishes
     uint64_t frac_c;         // the FracMinHash compression factor c (h * c < 2^64 for every kept h)
-    // fused K3 seed marking (scan21_kernel): one bit per base position, relative to sel_first_base
+    // fused K3 seed marking (scan21v2_kernel): one bit per base position, relative to sel_first_base
     int plan_k;              // k-mer length the chunk plan covers (0: k); 15 when seeds are marked too
     uint32_t *sel;
     uint64_t sel_first_base;
@@ -466,130 +466,33 @@ __global__ void __launch_bounds__(256) marker_select_kernel(const ChunkParams p)
 // ------------------------------------------------------------------------------------------
 // k = 21 scan with ROLLING state (the hot kernel of the whole path): a thread owns 64 consecutive
 // k-mer start positions of its chunk and keeps, per position, in registers
-//   * the 21 ASCII bytes of the forward k-mer (5 words, a byte-wise shift register) and of its
-//     reverse complement (shifted the other way): what MurmurHash3 reads -- no per-position
-//     bit reversal / ASCII expansion;
-//   * the MSB-first 2-bit integers of both strands (canonical choice; the 15-mer of the K3 seed is
-//     the top 30 bits of the forward integer and the low 30 bits of the reverse one);
-//   * the validity of the last 21 bases as a bit mask.
-// One pass therefore feeds K1 (MODE 0: MurmurHash3 candidates under the genome's threshold) or the
-// marker sketch (MODE 1: mm_hash64 of the canonical 21-mer under the fixed threshold) AND, with
-// SEEDS, the K3 seed selection bits (mm_hash64 of the canonical 15-mer < seed_thr) that
-// ani_mark_kernel would otherwise derive from the same bytes in a second pass.
+//   * the 21 ASCII bytes of the forward k-mer (a byte-wise shift register over 6 words) and of its
+//     reverse complement (shifted the other way): what MurmurHash3 reads -- no per-position bit
+//     reversal / ASCII expansion;
+//   * the MSB-first 2-bit integers of both strands, LEFT-aligned in 64 bits (canonical choice; the
+//     15-mer of the K3 seed is the top 30 bits of the forward integer and bits 22..51 of the reverse
+//     one).  Bases fall off the top by themselves (no mask), and since k is odd a k-mer never equals
+//     its reverse complement, so the stale bits under the reverse integer cannot change
+//     `forward < reverse`.
+// One pass feeds K1 (MODE 0: MurmurHash3 candidates under the genome's threshold) or the marker
+// sketch (MODE 1: mm_hash64 of the canonical 21-mer under the fixed threshold) AND, with SEEDS, the
+// K3 seed selection bits (mm_hash64 of the canonical 15-mer < seed_thr).
 // Loads are three aligned vector loads per thread (64 + 32 bases of sequence and validity); bases
 // past the genome's (128-padded) span are never read.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t murmur21(uint64_t k1, uint64_t k2, uint64_t kt, uint64_t seed) {
-    const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
-    uint64_t h1 = seed, h2 = seed;
-    k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
-    h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729ull;
-    k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
-    h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5ull;
-    kt *= c1; kt = rotl64(kt, 31); kt *= c2; h1 ^= kt;   // 5-byte tail goes into k1 only
-    h1 ^= 21ull; h2 ^= 21ull;
-    h1 += h2; h2 += h1;
-    h1 = fmix64(h1); h2 = fmix64(h2);
-    return h1 + h2;
-}
-
-template <int MODE, bool SEEDS>
-__global__ void __launch_bounds__(256) scan21_kernel(const ChunkParams p) {
-    const uint64_t item = blockIdx.x;
-    if (item >= p.chunk_off[p.n]) return;
-    const uint32_t g = p.item_genome[item];
-    const uint64_t b0 = p.base_off[g], len = p.base_off[g + 1] - b0;  // the 128-padded span
-    const uint64_t q0 = (item - p.chunk_off[g]) * kChunk + (uint64_t)threadIdx.x * 64;
-    if (q0 >= len) return;
-    const uint64_t P0 = b0 + q0;  // multiple of 64: the vector loads below are aligned
-    const uint4 s03 = __ldg(reinterpret_cast<const uint4 *>(p.seq2 + (P0 >> 4)));
-    const uint2 v01 = __ldg(reinterpret_cast<const uint2 *>(p.valid + (P0 >> 5)));
-    uint2 s45 = make_uint2(0u, 0u);
-    uint32_t v2 = 0u;
-    if (q0 + 64 < len) {  // then q0 + 128 <= len: the next 32 bases belong to this genome
-        s45 = __ldg(reinterpret_cast<const uint2 *>(p.seq2 + (P0 >> 4) + 4));
-        v2 = __ldg(p.valid + (P0 >> 5) + 2);
-    }
-    const uint64_t T = MODE == 0 ? p.thr[g] : p.fixed_thr;
-    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;  // forward ASCII bytes 0..20 (f5: byte 20)
-    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0;  // reverse-complement ASCII bytes 0..20
-    uint64_t Fint = 0, Rint = 0;
-    uint32_t vbits = 0, sel0 = 0, sel1 = 0;
-    const uint64_t mask42 = (1ull << 42) - 1;
-#pragma unroll
-    for (int wi = 0; wi < 6; wi++) {
-        uint32_t w = wi == 0 ? s03.x : wi == 1 ? s03.y : wi == 2 ? s03.z : wi == 3 ? s03.w : wi == 4 ? s45.x : s45.y;
-        uint32_t vw = (wi < 2 ? v01.x : wi < 4 ? v01.y : v2) >> ((wi & 1) * 16);
-        const int j_end = wi == 5 ? 4 : 16;  // bases 80..83 are the last ones a thread needs
-#pragma unroll 1
-        for (int j = 0; j < j_end; j++) {
-            const uint32_t code = w & 3u;
-            w >>= 2;
-            const uint32_t vb = vw & 1u;
-            vw >>= 1;
-            // selector nibbles 1..3 = 4 pick the zero operand: the result is ONE byte
-            const uint32_t fa = __byte_perm(0x54474341u, 0u, code | 0x4440u);  // "ACGT"[code]
-            const uint32_t ra = __byte_perm(0x41434754u, 0u, code | 0x4440u);  // "TGCA"[code]
-            f0 = __funnelshift_r(f0, f1, 8); f1 = __funnelshift_r(f1, f2, 8); f2 = __funnelshift_r(f2, f3, 8);
-            f3 = __funnelshift_r(f3, f4, 8); f4 = __funnelshift_r(f4, f5, 8); f5 = fa;
-            r5 = r4 >> 24; r4 = __funnelshift_l(r3, r4, 8); r3 = __funnelshift_l(r2, r3, 8);
-            r2 = __funnelshift_l(r1, r2, 8); r1 = __funnelshift_l(r0, r1, 8); r0 = (r0 << 8) | ra;
-            Fint = ((Fint << 2) | code) & mask42;
-            Rint = (Rint >> 2) | ((uint64_t)(3u - code) << 40);
-            vbits = (vbits >> 1) | (vb << 20);
-            const int t = wi * 16 + j;
-            if (t < 20) continue;
-            if (SEEDS && (vbits & 0x7FFFu) == 0x7FFFu) {
-                const uint32_t F15 = (uint32_t)(Fint >> 12), R15 = (uint32_t)Rint & 0x3FFFFFFFu;
-                if (mm_hash64_dev((uint64_t)min(F15, R15)) < p.seed_thr) {
-                    if (t - 20 < 32) sel0 |= 1u << (t - 20); else sel1 |= 1u << (t - 52);
-                }
-            }
-            if (vbits != 0x1FFFFFu) continue;
-            const bool fwd = Fint < Rint;
-            uint64_t h;
-            if (MODE == 0) {
-                const uint64_t k1 = fwd ? ((uint64_t)f1 << 32 | f0) : ((uint64_t)r1 << 32 | r0);
-                const uint64_t k2 = fwd ? ((uint64_t)f3 << 32 | f2) : ((uint64_t)r3 << 32 | r2);
-                const uint64_t kt = fwd ? ((uint64_t)f5 << 32 | f4) : ((uint64_t)r5 << 32 | r4);
-                h = murmur21(k1, k2, kt, p.seed);
-            } else {
-                h = mm_hash64_dev(fwd ? Fint : Rint);
-            }
-            if (h > T) continue;
-            if (h == kPad) { p.has_max[g] = 1; continue; }
-            if (MODE == 1 && p.n_parts > 1) {
-                const uint32_t part = (uint32_t)__umul64hi(h * p.frac_c, (uint64_t)p.n_parts);
-                const size_t buf = (size_t)g * p.n_parts + part;
-                const uint32_t slot = atomicAdd(&p.cand_n[buf], 1u);
-                if (slot < p.cap) p.cand[buf * p.cap + slot] = h;
-            } else {
-                const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
-                if (slot < p.cap) p.cand[(size_t)g * p.cap + slot] = h;
-            }
-        }
-    }
-    if (SEEDS) {
-        uint32_t *out = p.sel + ((P0 - p.sel_first_base) >> 5);
-        out[0] = sel0; out[1] = sel1;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// scan21 v2 (default): the same pass with the instruction count cut where ncu showed it going
-// (r2_ncu_full_k1_scan21.txt: 204 thread-instructions per k-mer, ALU pipe 74 %, FMA 25 %):
+// Instruction diet (ncu: r2_ncu_full_k1_scan21.txt -> r2_ncu_full_k1_scan21v2.txt, 204 -> 152
+// thread-instructions per k-mer; the kernel is bound by the ALU pipe, 0.5 warp-instructions per
+// clock per sub-partition for LOP3 / SHF / PRMT / SEL as measured by tools/pipe_bench.cu):
 //   * no warm-up: the state after the first 20 bases is built directly from the loaded words
-//     (bit-pair reversal for the forward integer, two PRMT look-ups per word for the ASCII bytes)
-//     instead of 20 silent rolling steps per 64 outputs;
+//     (bit-pair reversal for the forward integer, PRMT look-ups for the ASCII bytes);
 //   * validity of all 21-base / 15-base windows of the thread as two 64-bit masks from five
 //     shift-and-AND steps on the 96 validity bits, one bit test per position in the loop;
-//   * both 2-bit integers live LEFT-aligned in their 64-bit registers: bases fall off the top by
-//     themselves (no mask), and since k is odd a k-mer never equals its reverse complement, so the
-//     stale bits under the reverse integer cannot change `forward < reverse`;
-//   * 64-bit multiplies by constants as one wide multiply + two multiply-adds (3 FMA-pipe
-//     instructions; the compiler's expansion takes 4), MurmurHash3 specialised for seed 0;
+//   * 64-bit multiplies by constants as one wide multiply + two multiply-adds, MurmurHash3
+//     specialised for seed 0;
 //   * the last xor-shift of both fmix64 and the low half of the final sum are only evaluated for
 //     hashes whose HIGH words can still be under the threshold (7 of 10,000).
+// Tried and measured without gain: byte shifts as IMAD.HI + IMAD (IMAD.HI / IMAD.WIDE issue at
+// 0.25 per clock, half of IMAD), strand choice by predicated multiplies (ptxas turns them back into
+// SEL), 6 CTAs per SM at 40 registers.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t pack64(uint32_t lo, uint32_t hi) { return (uint64_t)hi << 32 | lo; }
 template <uint64_t C>
@@ -602,11 +505,13 @@ __device__ __forceinline__ uint64_t mul64c(uint64_t a) {
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(ahi), "r"((uint32_t)C));
     return pack64(lo, hi);
 }
-template <uint32_t M, uint64_t ADD>  // a * M + ADD, M < 2^32
-__device__ __forceinline__ uint64_t mad64s(uint64_t a) {
+// a * M + add, M < 2^32 (ptxas turns a constant `add` into IMAD.WIDE + IADD3 + IMAD.X whatever
+// form it is handed in: immediate, constant bank or register pair -- measured, not fought further)
+template <uint32_t M>
+__device__ __forceinline__ uint64_t mad64s(uint64_t a, uint64_t add) {
     const uint32_t alo = (uint32_t)a, ahi = (uint32_t)(a >> 32);
     uint64_t w;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(alo), "r"(M), "l"(ADD));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(w) : "r"(alo), "r"(M), "l"(add));
     uint32_t hi = (uint32_t)(w >> 32);
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(ahi), "r"(M));
     return pack64((uint32_t)w, hi);
@@ -621,12 +526,12 @@ __device__ __forceinline__ uint64_t xsr33(uint64_t x) {
     const uint32_t hi = (uint32_t)(x >> 32);
     return pack64((uint32_t)x ^ (hi >> 1), hi);
 }
-__device__ __forceinline__ uint64_t mm_hash64_v2(uint64_t key) {
-    key = mad64s<0x1FFFFFu, ~0ull>(key);  // ~key + (key << 21)
+__device__ __forceinline__ uint64_t mm_hash64_v2(uint64_t key, uint64_t minus1) {
+    key = mad64s<0x1FFFFFu>(key, minus1);  // ~key + (key << 21)
     key ^= key >> 24;
-    key = mad64s<265u, 0ull>(key);
+    key = mad64s<265u>(key, 0ull);
     key ^= key >> 14;
-    key = mad64s<21u, 0ull>(key);
+    key = mad64s<21u>(key, 0ull);
     key ^= key >> 28;
     key = mul64c<0x80000001ull>(key);
     return key;
@@ -648,6 +553,21 @@ __device__ __forceinline__ uint32_t nibbles8(uint32_t x) {
     return (x | (x << 2)) & 0x33333333u;
 }
 
+template <int MODE>
+__device__ __forceinline__ void scan_emit(const ChunkParams &p, uint32_t g, uint64_t T, uint64_t h) {
+    if (h > T) return;
+    if (h == kPad) { p.has_max[g] = 1; return; }
+    if (MODE == 1 && p.n_parts > 1) {
+        const uint32_t part = (uint32_t)__umul64hi(h * p.frac_c, (uint64_t)p.n_parts);
+        const size_t buf = (size_t)g * p.n_parts + part;
+        const uint32_t slot = atomicAdd(&p.cand_n[buf], 1u);
+        if (slot < p.cap) p.cand[buf * p.cap + slot] = h;
+    } else {
+        const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
+        if (slot < p.cap) p.cand[(size_t)g * p.cap + slot] = h;
+    }
+}
+
 template <int MODE, bool SEEDS, bool SEED0>
 __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
     const uint64_t item = blockIdx.x;
@@ -666,7 +586,9 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
         v2 = __ldg(p.valid + (P0 >> 5) + 2);
     }
     const uint64_t T = MODE == 0 ? p.thr[g] : p.fixed_thr;
-    const uint32_t Th1 = min((uint32_t)(T >> 32), 0xFFFFFFFEu) + 1u;
+    uint32_t Th1 = min((uint32_t)(T >> 32), 0xFFFFFFFEu) + 1u;
+    asm volatile("" : "+r"(Th1));  // keep it in a register: re-deriving it per position costs two ALU slots
+    const uint64_t addA = 0x52dce729ull, addB = 0x38495ab5ull, minus1 = ~0ull;
 
     // ---- window validity: KV bit t = bases t .. t+20 valid, SV bit t = bases t .. t+14 valid
     uint32_t kv0, kv1, sv0, sv1;
@@ -719,8 +641,11 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
         // validity bits of the block: k-mer windows in bits 0..15, seed windows in bits 16..31
         uint32_t mv = __byte_perm(wi < 2 ? kv0 : kv1, wi < 2 ? sv0 : sv1, (wi & 1) ? 0x7632 : 0x5410);
         if (!SEEDS) mv &= 0xFFFFu;
+        // `bit` walks over this block's 16 positions of the seed word and ends the loop (no counter)
+        uint32_t bit = (wi & 1) ? 0x10000u : 1u;
+        const uint32_t bit_end = (wi & 1) ? 0u : 0x10000u;
 #pragma unroll 1
-        for (int j = 0; j < 16; j++) {
+        do {
             const uint32_t fa = __byte_perm(0x54474341u, 0u, (inc & 3u) | 0x4440u);  // "ACGT"[code]
             f0 = __funnelshift_r(f0, f1, 8); f1 = __funnelshift_r(f1, f2, 8); f2 = __funnelshift_r(f2, f3, 8);
             f3 = __funnelshift_r(f3, f4, 8); f4 = __funnelshift_r(f4, f5, 8); f5 = fa;
@@ -732,57 +657,46 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
             Rlo = __funnelshift_r(Rlo, Rhi, 2);
             Rhi = (Rhi >> 2) | (~(inc << 30) & 0xC0000000u);
             inc >>= 2;
-            const uint32_t m = mv;
+            const uint32_t m = mv, cur = bit;
             mv >>= 1;
+            bit <<= 1;
             if (SEEDS && (m & 0x10000u)) {
                 const uint32_t F15 = Fhi >> 2, R15 = __funnelshift_r(Rlo, Rhi, 22) & 0x3FFFFFFFu;
-                if (mm_hash64_v2((uint64_t)min(F15, R15)) < p.seed_thr) {
-                    if (wi < 2) sel0 |= 1u << ((wi & 1) * 16 + j); else sel1 |= 1u << ((wi & 1) * 16 + j);
+                if (mm_hash64_v2((uint64_t)min(F15, R15), minus1) < p.seed_thr) {
+                    if (wi < 2) sel0 |= cur; else sel1 |= cur;
                 }
             }
-            if (!(m & 1u)) continue;
-            const bool fwd = pack64(Flo, Fhi) < pack64(Rlo, Rhi);
-            uint64_t h;
-            if (MODE == 0) {
-                const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
-                uint64_t k1 = fwd ? pack64(f0, f1) : pack64(r0, r1);
-                uint64_t k2 = fwd ? pack64(f2, f3) : pack64(r2, r3);
-                uint64_t kt = fwd ? pack64(f4, f5) : pack64(r4, r5);
-                k1 = mul64c<c1>(k1); k1 = rotl64f(k1, 31); k1 = mul64c<c2>(k1);
-                k2 = mul64c<c2>(k2); k2 = rotl64f(k2, 33); k2 = mul64c<c1>(k2);
-                kt = mul64c<c1>(kt); kt = rotl64f(kt, 31); kt = mul64c<c2>(kt);
-                uint64_t h1, h2;
-                if (SEED0) {
-                    h1 = rotl64f(k1, 27); h1 = mad64s<5u, 0x52dce729ull>(h1);
-                    h2 = rotl64f(k2, 31); h2 += h1; h2 = mad64s<5u, 0x38495ab5ull>(h2);
+            if (m & 1u) {
+                const bool fwd = pack64(Flo, Fhi) < pack64(Rlo, Rhi);
+                if (MODE == 0) {
+                    const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
+                    uint64_t k1 = mul64c<c1>(fwd ? pack64(f0, f1) : pack64(r0, r1));
+                    uint64_t k2 = mul64c<c2>(fwd ? pack64(f2, f3) : pack64(r2, r3));
+                    uint64_t kt = mul64c<c1>(fwd ? pack64(f4, f5) : pack64(r4, r5));
+                    k1 = rotl64f(k1, 31); k1 = mul64c<c2>(k1);
+                    k2 = rotl64f(k2, 33); k2 = mul64c<c1>(k2);
+                    kt = rotl64f(kt, 31); kt = mul64c<c2>(kt);
+                    uint64_t h1, h2;
+                    if (SEED0) {
+                        h1 = rotl64f(k1, 27); h1 = mad64s<5u>(h1, addA);
+                        h2 = rotl64f(k2, 31); h2 += h1; h2 = mad64s<5u>(h2, addB);
+                    } else {
+                        h1 = p.seed ^ k1; h1 = rotl64f(h1, 27); h1 += p.seed; h1 = mad64s<5u>(h1, addA);
+                        h2 = p.seed ^ k2; h2 = rotl64f(h2, 31); h2 += h1; h2 = mad64s<5u>(h2, addB);
+                    }
+                    h1 ^= kt;
+                    h1 ^= 21ull; h2 ^= 21ull;
+                    h1 += h2; h2 += h1;
+                    h1 = mul64c<0xc4ceb9fe1a85ec53ull>(xsr33(mul64c<0xff51afd7ed558ccdull>(xsr33(h1))));
+                    h2 = mul64c<0xc4ceb9fe1a85ec53ull>(xsr33(mul64c<0xff51afd7ed558ccdull>(xsr33(h2))));
+                    // the last xor-shift leaves the high words as they are: hash.hi is s or s + 1
+                    const uint32_t s1 = (uint32_t)(h1 >> 32) + (uint32_t)(h2 >> 32) + 1u;
+                    if (s1 <= Th1) scan_emit<MODE>(p, g, T, xsr33(h1) + xsr33(h2));
                 } else {
-                    h1 = p.seed ^ k1; h1 = rotl64f(h1, 27); h1 += p.seed; h1 = mad64s<5u, 0x52dce729ull>(h1);
-                    h2 = p.seed ^ k2; h2 = rotl64f(h2, 31); h2 += h1; h2 = mad64s<5u, 0x38495ab5ull>(h2);
+                    scan_emit<MODE>(p, g, T, mm_hash64_v2((fwd ? pack64(Flo, Fhi) : pack64(Rlo, Rhi)) >> 22, minus1));
                 }
-                h1 ^= kt;
-                h1 ^= 21ull; h2 ^= 21ull;
-                h1 += h2; h2 += h1;
-                h1 = mul64c<0xc4ceb9fe1a85ec53ull>(xsr33(mul64c<0xff51afd7ed558ccdull>(xsr33(h1))));
-                h2 = mul64c<0xc4ceb9fe1a85ec53ull>(xsr33(mul64c<0xff51afd7ed558ccdull>(xsr33(h2))));
-                // the last xor-shift leaves the high words as they are: hash.hi is s or s + 1
-                const uint32_t s1 = (uint32_t)(h1 >> 32) + (uint32_t)(h2 >> 32) + 1u;
-                if (s1 > Th1) continue;
-                h = xsr33(h1) + xsr33(h2);
-            } else {
-                h = mm_hash64_v2((fwd ? pack64(Flo, Fhi) : pack64(Rlo, Rhi)) >> 22);
             }
-            if (h > T) continue;
-            if (h == kPad) { p.has_max[g] = 1; continue; }
-            if (MODE == 1 && p.n_parts > 1) {
-                const uint32_t part = (uint32_t)__umul64hi(h * p.frac_c, (uint64_t)p.n_parts);
-                const size_t buf = (size_t)g * p.n_parts + part;
-                const uint32_t slot = atomicAdd(&p.cand_n[buf], 1u);
-                if (slot < p.cap) p.cand[buf * p.cap + slot] = h;
-            } else {
-                const uint32_t slot = atomicAdd(&p.cand_n[g], 1u);
-                if (slot < p.cap) p.cand[(size_t)g * p.cap + slot] = h;
-            }
-        }
+        } while (bit != bit_end);
     }
     if (SEEDS) {
         uint32_t *out = p.sel + ((P0 - p.sel_first_base) >> 5);
@@ -938,13 +852,11 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        const bool v1 = getenv("GALAH_B200_SCAN_V1") != nullptr;  // the first rolling kernel, kept for A/B timing
-        if (k == 21 && !v1 && seeds && seed == 0) scan21v2_kernel<0, true, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && !v1 && seeds) scan21v2_kernel<0, true, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && !v1 && seed == 0) scan21v2_kernel<0, false, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && !v1) scan21v2_kernel<0, false, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && seeds) scan21_kernel<0, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21_kernel<0, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        const bool generic = getenv("GALAH_B200_OLD_SCAN") != nullptr;  // the position-per-thread kernel, for A/B timing
+        if (k == 21 && seeds && seed == 0) scan21v2_kernel<0, true, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && seeds) scan21v2_kernel<0, true, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !generic && seed == 0) scan21v2_kernel<0, false, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !generic) scan21v2_kernel<0, false, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else if (k == 21) sketch_scan_kernel<21, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else sketch_scan_kernel<0, 0><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         GB_LAUNCH_CHECK();
@@ -1017,11 +929,8 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
     sketch_items_kernel<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (max_items > 0) {
-        const bool v1 = getenv("GALAH_B200_SCAN_V1") != nullptr;
-        if (k == 21 && !v1 && seeds) scan21v2_kernel<1, true, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && !v1) scan21v2_kernel<1, false, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && seeds) scan21_kernel<1, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
-        else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21_kernel<1, false><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        if (k == 21 && seeds) scan21v2_kernel<1, true, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
+        else if (k == 21 && !getenv("GALAH_B200_OLD_SCAN")) scan21v2_kernel<1, false, true><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else if (k == 21) sketch_scan_kernel<21, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         else sketch_scan_kernel<0, 1><<<(uint32_t)max_items, 256, 0, stream>>>(c);
         GB_LAUNCH_CHECK();
