@@ -1287,6 +1287,9 @@ static int cluster_from_resident(const uint64_t *d_table, const uint32_t *d_coun
         engine_ms += now_ms() - t4;
         if (stats) stats->n_ani_pairs = n_hits + rev_requests.size();
     }
+    if (getenv("GALAH_B200_DEBUG"))
+        fprintf(stderr, "[cluster_from_resident] prefilter %.2f ms, ani (both launches) %.2f ms, engine (both passes) %.2f ms, "
+                "%zu hits, %zu reverse requests\n", t1 - t0, t2 - t1, engine_ms, n_hits, rev_requests.size());
     if (stats) {
         stats->n_precluster_hits = n_hits;
         if (stats->n_ani_pairs == 0) stats->n_ani_pairs = n_hits;
