@@ -60,6 +60,9 @@ struct Context {
     uint64_t *slot_off[2] = {nullptr, nullptr};
     size_t cap_slot_seq2[2] = {0, 0}, cap_slot_valid[2] = {0, 0}, cap_slot_off[2] = {0, 0};
     uint32_t *d_sel = nullptr; size_t cap_sel = 0;  // K3 seed selection bits made by the fused k = 21 scan
+    uint32_t *d_sel2 = nullptr; size_t cap_sel2 = 0;  // second buffer: batch b + 1 is scanned while batch b is indexed
+    cudaStream_t scan_stream = nullptr;  // ingest_packed: K1 scans of the next batch run beside the K3 index build
+    cudaEvent_t ev_scan[2] = {nullptr, nullptr};
     AniIndex *pipe_index[2] = {nullptr, nullptr};  // K3 index of the one-call pipelines (c = 125 / 30), re-used across calls
     AniIndex &pipeline_index(bool small_genomes) {
         AniIndex *&p = pipe_index[small_genomes ? 1 : 0];
@@ -70,6 +73,10 @@ struct Context {
     int release() {
         for (auto &p : pipe_index) { delete p; p = nullptr; }
         cudaFree(d_sel); d_sel = nullptr; cap_sel = 0;
+        cudaFree(d_sel2); d_sel2 = nullptr; cap_sel2 = 0;
+        if (scan_stream) cudaStreamDestroy(scan_stream);
+        scan_stream = nullptr;
+        for (auto &e : ev_scan) { if (e) cudaEventDestroy(e); e = nullptr; }
         for (int x = 0; x < 2; x++) {
             cudaFree(slot_seq2[x]); cudaFree(slot_valid[x]); cudaFree(slot_off[x]);
             slot_seq2[x] = slot_valid[x] = nullptr; slot_off[x] = nullptr;
@@ -771,7 +778,13 @@ int galah_b200_init(int device) {
         g_ctx.stream = nullptr;
     }
     GB_CUDA(cudaSetDevice(device));
-    if (!g_ctx.stream) GB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    if (!g_ctx.stream) {
+        // highest priority: the small kernels of the K3 index build must get SM slots while a K1 scan of
+        // the next batch (tens of thousands of CTAs, lowest priority, scan_stream) is resident
+        int prio_lo = 0, prio_hi = 0;
+        GB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        GB_CUDA(cudaStreamCreateWithPriority(&g_ctx.stream, cudaStreamNonBlocking, prio_hi));
+    }
     g_ctx.device = device;
     return 0;
 }
@@ -1386,52 +1399,89 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         GB_CUDA(cudaEventRecord(sl.landed, g_ctx.copy_stream));
         return 0;
     };
+    // Two streams, software-pipelined over the batches: the K1 scan (+ K3 seed marks) of batch b + 1 is
+    // enqueued on scan_stream BEFORE the host walks through the K3 index build of batch b on the
+    // main stream (that build has host round trips: seed counts down, offsets up), so the GPU always
+    // has the next scan queued while the host is busy.  Seed-selection bits are double-buffered.
     float sketch_ms = 0.f, index_ms = 0.f;
-    cudaEvent_t ev[3];
-    for (auto &e : ev) GB_CUDA(cudaEventCreate(&e));
-    struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int x = 0; x < 3; x++) cudaEventDestroy(e[x]); } } ev_guard{ev};
-    if (!device && n_batches) if (int rc = upload(0)) return rc;
+    if (!g_ctx.scan_stream) {
+        int prio_lo = 0, prio_hi = 0;
+        GB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        GB_CUDA(cudaStreamCreateWithPriority(&g_ctx.scan_stream, cudaStreamNonBlocking, prio_lo));
+    }
+    for (auto &e : g_ctx.ev_scan) if (!e) GB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaStream_t sk = g_ctx.scan_stream;
+    cudaEvent_t ev[2][2], ev_ix[2];  // [slot]: scan begin / end on sk; index begin / end on st
+    for (auto &pr : ev) for (auto &e : pr) GB_CUDA(cudaEventCreate(&e));
+    for (auto &e : ev_ix) GB_CUDA(cudaEventCreate(&e));
+    struct EvGuard { cudaEvent_t (*e)[2]; cudaEvent_t *x; ~EvGuard() {
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) cudaEventDestroy(e[a][b]);
+        cudaEventDestroy(x[0]); cudaEventDestroy(x[1]); } } ev_guard{ev, ev_ix};
+    // the main stream may still be working for the caller: the first scan starts behind it
+    GB_CUDA(cudaEventRecord(ev_ix[0], st));
+    GB_CUDA(cudaStreamWaitEvent(sk, ev_ix[0], 0));
+    struct Batch { const uint32_t *seq2, *valid; const uint64_t *off; std::vector<uint64_t> bo; SeedSink sink; } bt[2];
+    auto scan = [&](size_t b) -> int {
+        Batch &B = bt[b & 1];
+        const size_t g0 = cut[b], nb = cut[b + 1] - g0;
+        if (device) {
+            B.seq2 = seq2; B.valid = valid; B.off = d_base_off_or_null + g0;  // absolute offsets into the resident arrays
+            B.bo.assign(base_off + g0, base_off + g0 + nb + 1);
+        } else {
+            GB_CUDA(cudaStreamWaitEvent(sk, slot[b & 1].landed, 0));
+            B.seq2 = slot[b & 1].seq2; B.valid = slot[b & 1].valid; B.off = slot[b & 1].off;
+            B.bo = rel[b];
+        }
+        // the k = 21 scan also marks the K3 seeds of the batch
+        uint32_t *&d_sel = (b & 1) ? g_ctx.d_sel2 : g_ctx.d_sel;
+        size_t &cap_sel = (b & 1) ? g_ctx.cap_sel2 : g_ctx.cap_sel;
+        if (ws_ensure(d_sel, cap_sel, (size_t)((B.bo.back() - B.bo.front()) / 32 + 2))) return GALAH_B200_ERR_CUDA;
+        B.sink = SeedSink{d_sel, B.bo.front(), index.seed_threshold()};
+        const uint64_t span[2] = {B.bo.front(), B.bo.back()};
+        GB_CUDA(cudaEventRecord(ev[b & 1][0], sk));
+        if (marker_c) {
+            if (int rc = marker_sketch_enqueue(g_ctx.sws, B.seq2, B.valid, B.off, nb, 21, marker_c, marker_stride,
+                                               d_table + g0 * (size_t)marker_stride, d_counts + g0, sk, &B.sink, span))
+                return rc;
+        } else if (int rc = sketch_enqueue(g_ctx.sws, B.seq2, B.valid, B.off, nb, 21, s, 0, d_table + g0 * (size_t)s,
+                                           d_counts + g0, s, sk, &B.sink, span))
+            return rc;
+        GB_CUDA(cudaEventRecord(ev[b & 1][1], sk));
+        GB_CUDA(cudaEventRecord(g_ctx.ev_scan[b & 1], sk));
+        return 0;
+    };
+    // host input: batches b + 1 and b + 2 cross PCIe behind the kernels of batch b (two slots)
+    if (!device) for (size_t b = 0; b < std::min<size_t>(n_batches, 2); b++) if (int rc = upload(b)) return rc;
+    if (n_batches) if (int rc = scan(0)) return rc;
     for (size_t b = 0; b < n_batches; b++) {
         const size_t g0 = cut[b], nb = cut[b + 1] - g0;
-        const uint32_t *b_seq2, *b_valid; const uint64_t *b_off;
-        std::vector<uint64_t> bo;
-        if (device) {
-            b_seq2 = seq2; b_valid = valid; b_off = d_base_off_or_null + g0;  // absolute offsets into the resident arrays
-            bo.assign(base_off + g0, base_off + g0 + nb + 1);
-        } else {
-            if (b + 1 < n_batches) if (int rc = upload(b + 1)) return rc;  // next batch crosses PCIe behind this one's kernels
-            GB_CUDA(cudaStreamWaitEvent(st, slot[b & 1].landed, 0));
-            b_seq2 = slot[b & 1].seq2; b_valid = slot[b & 1].valid; b_off = slot[b & 1].off;
-            bo = rel[b];
-        }
+        if (b + 1 < n_batches) if (int rc = scan(b + 1)) return rc;
+        Batch &B = bt[b & 1];
         std::vector<uint64_t> co(nb + 1);
         std::vector<uint32_t> cs(nb, 0), cl(nb);
         for (size_t g = 0; g < nb; g++) { co[g] = g; cl[g] = (uint32_t)lengths[g0 + g]; }
         co[nb] = nb;
-        GB_CUDA(cudaEventRecord(ev[0], st));
-        SeedSink seed_sink{nullptr, 0, 0};  // the k = 21 scan also marks the K3 seeds of the batch
-        if (int rc = seed_sink_for(index, bo.front(), bo.back(), seed_sink)) return rc;
-        if (marker_c) {
-            if (int rc = marker_sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, marker_c, marker_stride,
-                                               d_table + g0 * (size_t)marker_stride, d_counts + g0, st, &seed_sink))
-                return rc;
-        } else if (int rc = sketch_enqueue(g_ctx.sws, b_seq2, b_valid, b_off, nb, 21, s, 0, d_table + g0 * (size_t)s,
-                                           d_counts + g0, s, st, &seed_sink))
-            return rc;
-        GB_CUDA(cudaEventRecord(ev[1], st));
-        if (int rc = index.add_packed_device(b_seq2, b_valid, b_off, nb, bo, co, cs, cl, st, seed_sink.d_sel)) return rc;
+        GB_CUDA(cudaStreamWaitEvent(st, g_ctx.ev_scan[b & 1], 0));
+        GB_CUDA(cudaEventRecord(ev_ix[0], st));
+        if (int rc = index.add_packed_device(B.seq2, B.valid, B.off, nb, B.bo, co, cs, cl, st, B.sink.d_sel)) return rc;
         if (b == 0 && n_batches > 1) if (int rc = index.reserve_for(n, st)) return rc;
-        GB_CUDA(cudaEventRecord(ev[2], st));
-        if (!device) GB_CUDA(cudaEventRecord(slot[b & 1].freed, st));
-        GB_CUDA(cudaEventSynchronize(ev[2]));
+        GB_CUDA(cudaEventRecord(ev_ix[1], st));
+        if (!device) {
+            GB_CUDA(cudaEventRecord(slot[b & 1].freed, st));  // scan(b) ended before index(b) began: the slot is consumed
+            if (b + 2 < n_batches) if (int rc = upload(b + 2)) return rc;
+        }
+        GB_CUDA(cudaEventSynchronize(ev_ix[1]));
         float a = 0.f, c = 0.f;
-        GB_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
-        GB_CUDA(cudaEventElapsedTime(&c, ev[1], ev[2]));
+        GB_CUDA(cudaEventElapsedTime(&a, ev[b & 1][0], ev[b & 1][1]));
+        GB_CUDA(cudaEventElapsedTime(&c, ev_ix[0], ev_ix[1]));
         sketch_ms += a; index_ms += c;
         if (getenv("GALAH_B200_DEBUG"))
             fprintf(stderr, "[ingest_packed] batch %zu/%zu: %zu genomes, K1 %.2f ms, index %.2f ms (kernels %.2f ms)\n", b,
                     n_batches, nb, a, c, index.last_build_ms);
     }
+    // the sketch rows are complete when scan_stream is: later work on the main stream waits for it
+    GB_CUDA(cudaEventRecord(ev_ix[0], sk));
+    GB_CUDA(cudaStreamWaitEvent(st, ev_ix[0], 0));
     if (sketch_ms_out) *sketch_ms_out = sketch_ms;
     if (index_ms_out) *index_ms_out = index_ms;
     return 0;

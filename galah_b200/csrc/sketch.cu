@@ -800,7 +800,7 @@ static int sk_ensure(T *&ptr, size_t &cap, size_t need) {
 int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
                    uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream,
-                   const SeedSink *seeds) {
+                   const SeedSink *seeds, const uint64_t *host_span) {
     if (k < 1 || k > 32) { set_error("sketch: k must be in 1..32"); return 3; }
     if (seeds && k != 21) { set_error("sketch: fused seed marking needs k = 21"); return 3; }
     if (s == 0) { set_error("sketch: s must be > 0"); return 3; }
@@ -818,12 +818,14 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
         return 5;
     }
     // the scan grid is sized from the batch length: one 8-byte read of base_off[n]
-    uint64_t total_bases = 0;
-    GB_CUDA(cudaMemcpyAsync(&total_bases, d_base_off + n, 8, cudaMemcpyDeviceToHost, stream));
-    GB_CUDA(cudaStreamSynchronize(stream));
-    uint64_t first_base = 0;
-    GB_CUDA(cudaMemcpyAsync(&first_base, d_base_off, 8, cudaMemcpyDeviceToHost, stream));
-    GB_CUDA(cudaStreamSynchronize(stream));
+    uint64_t total_bases = 0, first_base = 0;
+    if (host_span) {
+        first_base = host_span[0]; total_bases = host_span[1];
+    } else {
+        GB_CUDA(cudaMemcpyAsync(&total_bases, d_base_off + n, 8, cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaMemcpyAsync(&first_base, d_base_off, 8, cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaStreamSynchronize(stream));
+    }
     const uint64_t max_items = (total_bases - first_base) / kChunk + n;
     if (max_items > 0x7FFFFFFFull) { set_error("sketch: batch too long for one launch"); return 3; }
 
@@ -892,7 +894,8 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
 // markers.  Shares the plan / items / scan / select pipeline of K1.
 int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                           const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
-                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream, const SeedSink *seeds) {
+                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream, const SeedSink *seeds,
+                          const uint64_t *host_span) {
     if (k < 1 || k > 32) { set_error("marker sketch: k must be in 1..32"); return 3; }
     if (seeds && k != 21) { set_error("marker sketch: fused seed marking needs k = 21"); return 3; }
     if (cap < 256 || (cap & (cap - 1)) || cap > kMarkerMaxCap) { set_error("marker sketch: bad capacity"); return 3; }
@@ -901,9 +904,13 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
     if (n >= 0x7FFFFFFFull) { set_error("marker sketch: too many genomes in one batch"); return 3; }
     if (n == 0) return 0;
     uint64_t total_bases = 0, first_base = 0;
-    GB_CUDA(cudaMemcpyAsync(&total_bases, d_base_off + n, 8, cudaMemcpyDeviceToHost, stream));
-    GB_CUDA(cudaMemcpyAsync(&first_base, d_base_off, 8, cudaMemcpyDeviceToHost, stream));
-    GB_CUDA(cudaStreamSynchronize(stream));
+    if (host_span) {
+        first_base = host_span[0]; total_bases = host_span[1];
+    } else {
+        GB_CUDA(cudaMemcpyAsync(&total_bases, d_base_off + n, 8, cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaMemcpyAsync(&first_base, d_base_off, 8, cudaMemcpyDeviceToHost, stream));
+        GB_CUDA(cudaStreamSynchronize(stream));
+    }
     const uint64_t max_items = (total_bases - first_base) / kChunk + n;
     if (max_items > 0x7FFFFFFFull) { set_error("marker sketch: batch too long for one launch"); return 3; }
     if (!ws.d_redo_n) GB_CUDA(cudaMalloc(&ws.d_redo_n, sizeof(uint32_t)));

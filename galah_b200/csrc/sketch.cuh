@@ -35,7 +35,9 @@ struct SeedSink {
 int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                    const uint64_t *d_base_off, size_t n, int k, uint32_t s, uint64_t seed,
                    uint64_t *d_hashes, uint32_t *d_counts, size_t out_stride, cudaStream_t stream,
-                   const SeedSink *seeds = nullptr);
+                   const SeedSink *seeds = nullptr, const uint64_t *host_span = nullptr);
+// host_span: {base_off[0], base_off[n]} when the caller knows them on the host -- the call then
+// enqueues without reading them back (no stream synchronisation: batches can be pipelined).
 
 // FracMinHash marker sketches for the skani-style screen (see sketch.cu).  cap: row stride, a power
 // of two in [256, kMarkerMaxCap]; rows wider than kMarkerPartCap are finished in value-range partitions.
@@ -49,7 +51,8 @@ inline uint32_t marker_row_capacity(uint64_t longest, uint32_t c_marker) {
 }
 int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *d_valid,
                           const uint64_t *d_base_off, size_t n, int k, uint32_t c_marker, uint32_t cap,
-                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream, const SeedSink *seeds = nullptr);
+                          uint64_t *d_rows, uint32_t *d_counts, cudaStream_t stream, const SeedSink *seeds = nullptr,
+                          const uint64_t *host_span = nullptr);
 
 // Synthetic genomes, generated directly in packed form on the device.
 int synth_enqueue(uint64_t seed, uint64_t index_begin, size_t n, uint64_t length, uint32_t *d_seq2,
