@@ -59,6 +59,9 @@ int DevVec<T>::reserve(size_t need, cudaStream_t st) {
 }
 
 constexpr unsigned long long kEmpty = ~0ull;
+// bit 63 of a bucket's LAST slot: some key whose home is this bucket lives beyond it (k-mers are 30
+// bits, so bits 33..62 hold them and bit 63 is free; an empty slot is all ones)
+constexpr unsigned long long kOverflowFlag = 1ull << 63;
 
 __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
     key = ~key + (key << 21);
@@ -241,8 +244,12 @@ __global__ void __launch_bounds__(kEmitThreads) ani_emit_kernel(const EmitParams
         const uint2 kq = p.kq[so + x];
         const uint32_t ks = kq.x;
         const unsigned long long e = ((unsigned long long)(ks >> 1) << 33) | ((unsigned long long)(ks & 1) << 32) | kq.y;
-        uint32_t slot = table_slot(ks >> 1, mask);
+        const uint32_t home = table_slot(ks >> 1, mask);
+        uint32_t slot = home;
         while (atomicCAS(&table[slot], kEmpty, e) != kEmpty) slot = (slot + 1) & mask;
+        // a key that left its home bucket flags the bucket (its last slot is occupied by now: this
+        // insert walked over it), so that a reader of a full bucket WITHOUT the flag can stop there
+        if (((slot - home) & mask) >= 4u) atomicOr(&table[home + 3], kOverflowFlag);
     }
 }
 
@@ -264,9 +271,15 @@ struct ChainParams {
 };
 
 constexpr int kChainThreads = 128;
+constexpr int kChainCtasPerSm = 4;  // 40 kB anchor ring + 16 kB bucket slots per CTA
 constexpr int kRingFields = 5;  // q, r, f, rel<<31 | cnt<<29 | acc_dr<<15 | x, first_x<<16 | first_mb
 
-__global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainParams p) {
+// Four seeds (one aligned 32-byte sector of the interleaved (k-mer, position) array) in one load.
+__device__ __forceinline__ void load_seeds4(const uint2 *p, unsigned long long (&k)[4]) {
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(k[0]), "=l"(k[1]), "=l"(k[2]), "=l"(k[3]) : "l"(p));
+}
+
+__global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm) ani_chain_kernel(const ChainParams p) {
     extern __shared__ int ring[];  // [kAniH][kRingFields][kChainThreads]
     const uint32_t tid = threadIdx.x;
     // work units = (pair, query chunk), flattened over the batch so every thread has one
@@ -274,6 +287,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     // no early exits: every lane of a warp stays in the lock-step walk (idle lanes walk 0 seeds)
     uint32_t pair = 0, x0 = 0, x1 = 0;
     const uint2 *qkq = p.kq;
+    uint64_t so = 0;
     const unsigned long long *table = nullptr;
     uint32_t mask = 0;
     if (u < p.n_units) {
@@ -288,7 +302,8 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
         const uint32_t *cso = p.cso + p.cso_off[q];
         x0 = cso[t]; x1 = cso[t + 1];
         if (x1 - x0 < (uint32_t)kAniMinAnchors) x1 = x0;
-        qkq = p.kq + p.seed_off[q];
+        so = p.seed_off[q];
+        qkq = p.kq + so;
         table = p.pair_table[pair];
         mask = p.pair_mask[pair];
     }
@@ -299,35 +314,18 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
     uint32_t covq = 0, covr = 0, span_m = 0, span_n = 0, n_chains = 0;
     int f_seen = 0;  // largest score of any anchor so far: bounds every score still in the ring
     // The lanes of a warp are different chunks and walk their seeds in lock step: one seed per
-    // lane per iteration.  The probe of the reference table (the random read this kernel is bound
+    // lane per step.  The probe of the reference table (the random read this kernel is bound
     // by) then runs converged across the warp; only lanes whose seed occurs 1..8 times in the
     // reference go on to the chaining step(s), which the f_seen bound keeps to one or two
     // look-backs for colinear anchors.
-    // Two-deep software pipeline over the chunk's seeds: seed x+2's (k-mer, position) and seed
-    // x+1's home slot are requested while seed x is processed.
     // The probe sequence is read four slots (one 32-byte sector) at a time: linear probing keeps a
     // cluster contiguous, so one read usually holds the whole run up to its empty slot and the
     // chain of dependent reads -- max over the warp's lanes -- is one or two long instead of
     // the cluster length.
-    const uint2 kq1 = x0 < x1 ? qkq[x0] : make_uint2(0u, 0u), kq2 = x0 + 1 < x1 ? qkq[x0 + 1] : make_uint2(0u, 0u);
-    uint32_t ks1 = kq1.x, ks2 = kq2.x;
-    int qp1 = (int)kq1.y, qp2 = (int)kq2.y;
-    unsigned long long g1[4] = {kEmpty, kEmpty, kEmpty, kEmpty};
-    if (x0 < x1) load_bucket(table + table_slot(ks1 >> 1, mask), g1);
-    // The trip count is the warp's longest chunk and every iteration starts with a warp barrier, so
-    // the lanes re-join after the divergent chaining step whatever the compiler's own
-    // reconvergence points are.
-    const uint32_t len = x1 - x0, max_len = __reduce_max_sync(0xffffffffu, len);
-    for (uint32_t it = 0; it < max_len; it++) {
-        __syncwarp();
-        if (it >= len) continue;
-        const uint32_t x = x0 + it;
-        const uint32_t ks = ks1;
-        unsigned long long v[4] = {g1[0], g1[1], g1[2], g1[3]};
-        const int qpos = qp1;
-        ks1 = ks2; qp1 = qp2;
-        if (x + 1 < x1) load_bucket(table + table_slot(ks1 >> 1, mask), g1);
-        if (x + 2 < x1) { const uint2 kq = qkq[x + 2]; ks2 = kq.x; qp2 = (int)kq.y; }
+    // One seed: count its occurrences in the reference table (first bucket already in v), then chain.
+    auto process = [&](const unsigned long long seed, unsigned long long (&v)[4], const uint32_t x) {
+        const uint32_t ks = (uint32_t)seed;
+        const int qpos = (int)(uint32_t)(seed >> 32);
         const uint32_t km = ks >> 1, qs = ks & 1;
         const uint32_t home = table_slot(km, mask);
         uint32_t c = 0;
@@ -340,10 +338,12 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
                 for (uint32_t i = 0; i < 4; i++) {
                     if (open) {
                         if (v[i] == kEmpty) open = false;
-                        else if ((uint32_t)(v[i] >> 33) == km) { only = v[i]; c++; }
+                        else if (((uint32_t)(v[i] >> 33) & 0x3FFFFFFFu) == km) { only = v[i]; c++; }
                     }
                 }
                 if (!open) break;
+                // a full home bucket: its keys go on beyond it only if it carries the overflow flag
+                if (g == home && !(v[3] & kOverflowFlag)) break;
                 g = (g + 4) & mask;
                 load_bucket(table + g, v);
             }
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
                 for (uint32_t slot = home;; slot = (slot + 1) & mask) {
                     const unsigned long long e2 = table[slot];
                     if (e2 == kEmpty) break;
-                    if ((uint32_t)(e2 >> 33) != km) continue;
+                    if (((uint32_t)(e2 >> 33) & 0x3FFFFFFFu) != km) continue;
                     const long long sp = (long long)(uint32_t)e2;
                     if (sp > prev && (pick == kEmpty || sp < (long long)(uint32_t)pick)) pick = e2;
                 }
@@ -417,7 +417,60 @@ __global__ void __launch_bounds__(kChainThreads) ani_chain_kernel(const ChainPar
                 }
             }
         }
+    };
+    // Software pipeline, four steps deep: while seed X is processed, the home buckets of seeds
+    // X+1 .. X+4 are in flight as cp.async copies into a per-thread slot ring in shared memory, and the
+    // seed groups (aligned groups of four seeds = one 32-byte sector, absolute seed indices) up to
+    // twelve seeds ahead as register loads.  The kernel is bound by the latency of the bucket reads;
+    // cp.async groups complete in order and are waited for by COUNT (wait_group 3 = "the copy issued
+    // four steps ago has landed"), which register loads cannot express: with four LDG sites sharing
+    // the warp's six scoreboards ptxas made every step wait for the copy issued one step earlier
+    // (ncu: three of the four unrolled consumers stalled, the first one did not).
+    uint4 *bk = reinterpret_cast<uint4 *>(ring + kAniH * kRingFields * kChainThreads);  // [4 slots][2 halves][threads]
+    auto bucket_issue = [&](const int j, const unsigned long long seed) {
+        const unsigned long long *src = table + table_slot((uint32_t)seed >> 1, mask);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(bk + (j * 2) * kChainThreads + tid);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(kChainThreads * 16)), "l"(src + 2));
+    };
+    const uint64_t X0 = so + x0, X1 = so + x1;
+    const uint64_t XA = X0 & ~3ull;
+    const uint32_t n_groups = x1 > x0 ? (uint32_t)((X1 - XA + 3) >> 2) : 0u;
+    const uint32_t max_groups = __reduce_max_sync(0xffffffffu, n_groups);
+    unsigned long long kA[4] = {0, 0, 0, 0}, kB[4] = {0, 0, 0, 0}, kC[4] = {0, 0, 0, 0};
+    if (n_groups > 0) load_seeds4(p.kq + XA, kA);
+    if (n_groups > 1) load_seeds4(p.kq + XA + 4, kB);
+    if (n_groups > 2) load_seeds4(p.kq + XA + 8, kC);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint64_t X = XA + j;
+        if (X >= X0 && X < X1) bucket_issue(j, kA[j]);
+        asm volatile("cp.async.commit_group;");
     }
+    // The trip count is the warp's longest chunk and every step starts with a warp barrier, so the
+    // lanes re-join after the divergent chaining step whatever the compiler's own reconvergence
+    // points are.
+    for (uint32_t G = 0; G < max_groups; G++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            __syncwarp();
+            asm volatile("cp.async.wait_group 3;" ::: "memory");
+            const uint64_t X = XA + 4ull * G + j;
+            if (X >= X0 && X < X1) {
+                const uint4 h0 = bk[(j * 2) * kChainThreads + tid], h1 = bk[(j * 2 + 1) * kChainThreads + tid];
+                unsigned long long v[4] = {(unsigned long long)h0.y << 32 | h0.x, (unsigned long long)h0.w << 32 | h0.z,
+                                           (unsigned long long)h1.y << 32 | h1.x, (unsigned long long)h1.w << 32 | h1.z};
+                process(kA[j], v, (uint32_t)(X - so));
+            }
+            kA[j] = kB[j];
+            if (X + 4 >= X0 && X + 4 < X1) bucket_issue(j, kA[j]);
+            asm volatile("cp.async.commit_group;");
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) kB[j] = kC[j];
+        if (G + 3 < n_groups) load_seeds4(p.kq + XA + 4ull * (G + 3), kC);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #undef RING
     if (first_q != 0xFFFFFFFFu) {
         const uint32_t M = m_at_last - mb_first, N = last_q - first_q + 1;
@@ -653,10 +706,10 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
         seed_off[g + 1] = seed_off[g] + count[g];
         cso_off[g + 1] = cso_off[g] + n_chunks[g] + 1;
         uint64_t slots = 16;
-        while (slots < 2ull * count[g]) slots <<= 1;
+        while (slots < 4ull * count[g]) slots <<= 1;  // load factor <= 1/4: about one key per 4-slot bucket
         table_off[g + 1] = table_off[g] + slots;
     }
-    if (d_kq_.reserve(seed_off[n] + 1, st) ||
+    if (d_kq_.reserve(seed_off[n] + 8, st) ||
         d_cso_.reserve(cso_off[n] + 1, st) || d_table_.reserve(table_off[n] + 1, st) ||
         d_seed_off_.reserve(g0 + n + 2, st) || d_cso_off_.reserve(g0 + n + 2, st) ||
         d_table_off_.reserve(g0 + n + 2, st) || d_n_chunks_.reserve(g0 + n + 1, st))
@@ -775,7 +828,7 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
     GB_CUDA(cudaMemsetAsync(d_acc.p, 0, 4 * (size_t)kAccWords * n_pairs, st));
     GB_CUDA(cudaMemsetAsync(d_fx.p, 0, 8 * n_pairs, st));
     GB_CUDA(cudaMemsetAsync(d_over.p, 0, 4, st));
-    const size_t smem = (size_t)kAniH * kRingFields * kChainThreads * sizeof(int);
+    const size_t smem = (size_t)kAniH * kRingFields * kChainThreads * sizeof(int) + (size_t)4 * 32 * kChainThreads;
     GB_CUDA(cudaFuncSetAttribute(ani_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GB_CUDA(cudaEventRecord(ev_[0], st));
     const double td1 = now();
