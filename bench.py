@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-clade sub-record")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTA-ingest (K0) sub-record")
     ap.add_argument("--dense-genomes", type=int, default=2000)
-    ap.add_argument("--ref-table-genomes", type=int, default=4000)
+    ap.add_argument("--ref-table-genomes", type=int, default=4500, help="reference arm: genomes of its sketch table (4500 -> 1.01e7 pairs per step)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -414,10 +414,23 @@ def main():
             fam.append({"family": name, "kernels": kernels, "ms_per_step": ms, "share_of_step": ms / (total_ms / args.steps),
                         "units_per_step": units, "unit": unit, "algorithmic_bytes_per_unit": bytes_per_unit,
                         "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "bound": bound, "note": note})
-        add("K1 sketch", ["sketch_scan_kernel", "sketch_select_kernel"], phase.get("sketch_ms"), n_local, "genome",
-            L / 4 + L / 8 + 8 * S, "integer ALU (MurmurHash3 per k-mer); HBM fraction reported as asked",
-            "L/4 packed + L/8 validity read, 8 s written per genome")
-        add("K3 index", ["ani_mark_kernel", "ani_emit_kernel"], phase.get("index_ms"), n_local, "genome",
+        add("K1 sketch", ["scan21v2_kernel", "sketch_select_kernel"], phase.get("sketch_ms"), n_local, "genome",
+            L / 4 + L / 8 + 8 * S, "ALU pipe (LOP3 / SHF / PRMT / SEL at 0.5 warp-instructions per clock and sub-partition, "
+            "profiles/r2_pipe_rates_b200.txt); HBM fraction reported as asked, see instruction_roofline",
+            "L/4 packed + L/8 validity read, 8 s written per genome; the time is taken while the K3 index kernels of the "
+            "previous batch share the SMs (two streams), so K1 + K3 index > ingest")
+        if fam and fam[-1]["family"] == "K1 sketch" and clocks and clocks.get("sm_mhz"):
+            # what bounds the kernel: ALU-pipe instructions per k-mer position (counted in the SASS of the hot path)
+            alu_per_kmer, sms, subparts = 88.0, 148, 4
+            peak_kmers = sms * subparts * 0.5 * 32 * clocks["sm_mhz"] * 1e6 / alu_per_kmer
+            got_kmers = n_local * float(L) / (fam[-1]["ms_per_step"] * 1e-3)
+            fam[-1]["instruction_roofline"] = {
+                "bound": "ALU pipe", "alu_pipe_instructions_per_kmer": alu_per_kmer, "fma_pipe_instructions_per_kmer": 52.0,
+                "all_instructions_per_kmer": 152.0, "peak_kmers_per_s": peak_kmers, "achieved_kmers_per_s": got_kmers,
+                "frac": got_kmers / peak_kmers,
+                "source": "SASS count of scan21v2_kernel<0,1,1>'s loop + measured pipe rates (tools/pipe_bench.cu); ncu: "
+                          "sm__inst_executed_pipe_alu 78 % (profiles/r2_ncu_full_k1_scan21v2.txt)"}
+        add("K3 index", ["ani_count_kernel", "ani_emit_kernel"], phase.get("index_ms"), n_local, "genome",
             L / 4 + L / 8 + seeds_per_genome * (8 + 16), "integer ALU (mm_hash64 per k-mer) + scattered table inserts",
             "packed read + 8 B seed + 2 x 8 B table slots per seed written")
         k2 = sub.get("prefilter_only") or {}
@@ -432,8 +445,9 @@ def main():
             fam[-1]["own_frac_of_hbm_peak"] = fam[-1]["own_gbs"] / peak if fam[-1]["own_gbs"] else None
             fam[-1]["dram_traffic"] = ncu_traffic("prefilter_join_kernel")
         add("K3 chain", ["ani_chain_kernel"], phase.get("ani_chain_ms"), n_hits // world if world > 1 else n_hits, "hit pair",
-            2 * seeds_per_genome * 12, "latency of dependent table probes (L2 / HBM)",
-            "2 * (L/c) * 12 B seed entries per pair (SURVEY.md 8d)")
+            2 * seeds_per_genome * 12, "latency of table probes (L2 / HBM) + SIMT divergence of the chaining step",
+            "2 * (L/c) * 12 B seed entries per pair (SURVEY.md 8d); both K3 launches of a step (hits, then the reverse "
+            "orientation of the pairs the membership pass asks for)")
         dom = max(fam, key=lambda f: f["ms_per_step"]) if fam else None
         roofline = None
         if dom:
