@@ -638,35 +638,37 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
         const uint32_t wa = wi == 0 ? s03.y : wi == 1 ? s03.z : wi == 2 ? s03.w : s45.x;
         const uint32_t wb = wi == 0 ? s03.z : wi == 1 ? s03.w : wi == 2 ? s45.x : s45.y;
         uint32_t inc = __funnelshift_r(wa, wb, 8);
-        // validity bits of the block: k-mer windows in bits 0..15, seed windows in bits 16..31
-        uint32_t mv = __byte_perm(wi < 2 ? kv0 : kv1, wi < 2 ? sv0 : sv1, (wi & 1) ? 0x7632 : 0x5410);
-        if (!SEEDS) mv &= 0xFFFFu;
+        // validity bits of the block, at the bit positions `bit` walks over (no shifting in the loop)
+        const uint32_t kv16 = wi < 2 ? kv0 : kv1, sv16 = wi < 2 ? sv0 : sv1;
         // `bit` walks over this block's 16 positions of the seed word and ends the loop (no counter)
         uint32_t bit = (wi & 1) ? 0x10000u : 1u;
         const uint32_t bit_end = (wi & 1) ? 0u : 0x10000u;
 #pragma unroll 1
         do {
-            const uint32_t fa = __byte_perm(0x54474341u, 0u, (inc & 3u) | 0x4440u);  // "ACGT"[code]
+            const uint32_t code = inc & 3u;
+            const uint32_t fa = __byte_perm(0x54474341u, 0u, code | 0x4440u);  // "ACGT"[code]
             f0 = __funnelshift_r(f0, f1, 8); f1 = __funnelshift_r(f1, f2, 8); f2 = __funnelshift_r(f2, f3, 8);
             f3 = __funnelshift_r(f3, f4, 8); f4 = __funnelshift_r(f4, f5, 8); f5 = fa;
             r5 = r4 >> 24; r4 = __funnelshift_l(r3, r4, 8); r3 = __funnelshift_l(r2, r3, 8);
             r2 = __funnelshift_l(r1, r2, 8); r1 = __funnelshift_l(r0, r1, 8);
-            r0 = __byte_perm(r0, 0x41434754u, (inc & 3u) | 0x2104u);  // bytes: "TGCA"[code], r0.b0, r0.b1, r0.b2
+            r0 = __byte_perm(r0, 0x41434754u, code | 0x2104u);  // bytes: "TGCA"[code], r0.b0, r0.b1, r0.b2
+            // the integer updates as multiply-adds (FMA pipe; the ALU pipe is the one that is full):
+            // forward  lo' = lo * 4 + code * 2^22
+            // reverse  hi' = ((hi >> 2) | 3 << 30) - code * 2^30  (the funnel shift brings the two ones in)
             Fhi = __funnelshift_l(Flo, Fhi, 2);
-            Flo = (Flo << 2) | ((inc << 22) & 0x00C00000u);
+            Flo = Flo * 4u + code * 0x00400000u;
             Rlo = __funnelshift_r(Rlo, Rhi, 2);
-            Rhi = (Rhi >> 2) | (~(inc << 30) & 0xC0000000u);
+            Rhi = __funnelshift_r(Rhi, 0xFFFFFFFFu, 2) + code * 0xC0000000u;
             inc >>= 2;
-            const uint32_t m = mv, cur = bit;
-            mv >>= 1;
+            const uint32_t cur = bit;
             bit <<= 1;
-            if (SEEDS && (m & 0x10000u)) {
+            if (SEEDS && (sv16 & cur)) {
                 const uint32_t F15 = Fhi >> 2, R15 = __funnelshift_r(Rlo, Rhi, 22) & 0x3FFFFFFFu;
                 if (mm_hash64_v2((uint64_t)min(F15, R15), minus1) < p.seed_thr) {
                     if (wi < 2) sel0 |= cur; else sel1 |= cur;
                 }
             }
-            if (m & 1u) {
+            if (kv16 & cur) {
                 const bool fwd = pack64(Flo, Fhi) < pack64(Rlo, Rhi);
                 if (MODE == 0) {
                     const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
