@@ -553,6 +553,19 @@ __device__ __forceinline__ uint32_t nibbles8(uint32_t x) {
     return (x | (x << 2)) & 0x33333333u;
 }
 
+// a < b on 64-bit operands as the borrow of a - b: 0xFFFFFFFF if a < b, else 0.  Three add-with-carry
+// instructions (IADD3 issues at twice the rate of the ALU pipe and beside it, profiles/r2_pipe_rates_b200.txt)
+// in place of two ISETP; the result is used arithmetically, see sel32.
+__device__ __forceinline__ uint32_t neg_borrow64(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi) {
+    uint32_t nb;
+    asm("{\n\t.reg .u32 t0, t1;\n\tsub.cc.u32 t0, %1, %3;\n\tsubc.cc.u32 t1, %2, %4;\n\tsubc.u32 %0, 0, 0;\n\t}"
+        : "=r"(nb) : "r"(alo), "r"(ahi), "r"(blo), "r"(bhi));
+    return nb;
+}
+// nb == 0xFFFFFFFF ? f : r  as  r + nb * (r - f): a subtract and a multiply-add (FMA pipe) instead of
+// a SEL (ALU pipe, the one the scan saturates)
+__device__ __forceinline__ uint32_t sel32(uint32_t nb, uint32_t f, uint32_t r) { return r + nb * (r - f); }
+
 template <int MODE>
 __device__ __forceinline__ void scan_emit(const ChunkParams &p, uint32_t g, uint64_t T, uint64_t h) {
     if (h > T) return;
@@ -664,17 +677,20 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
             bit <<= 1;
             if (SEEDS && (sv16 & cur)) {
                 const uint32_t F15 = Fhi >> 2, R15 = __funnelshift_r(Rlo, Rhi, 22) & 0x3FFFFFFFu;
-                if (mm_hash64_v2((uint64_t)min(F15, R15), minus1) < p.seed_thr) {
-                    if (wi < 2) sel0 |= cur; else sel1 |= cur;
-                }
+                const uint64_t hs = mm_hash64_v2((uint64_t)min(F15, R15), minus1);
+                const uint32_t pick = cur & neg_borrow64((uint32_t)hs, (uint32_t)(hs >> 32), (uint32_t)p.seed_thr,
+                                                         (uint32_t)(p.seed_thr >> 32));
+                if (wi < 2) sel0 |= pick; else sel1 |= pick;
             }
             if (kv16 & cur) {
-                const bool fwd = pack64(Flo, Fhi) < pack64(Rlo, Rhi);
+                const uint32_t nb = neg_borrow64(Flo, Fhi, Rlo, Rhi);  // all ones: the forward strand is canonical
+                const bool fwd = nb != 0u;
                 if (MODE == 0) {
                     const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
-                    uint64_t k1 = mul64c<c1>(fwd ? pack64(f0, f1) : pack64(r0, r1));
-                    uint64_t k2 = mul64c<c2>(fwd ? pack64(f2, f3) : pack64(r2, r3));
-                    uint64_t kt = mul64c<c1>(fwd ? pack64(f4, f5) : pack64(r4, r5));
+                    // three of the six words by multiply-add, three by SEL: measured best (both pipes level)
+                    uint64_t k1 = mul64c<c1>(pack64(sel32(nb, f0, r0), sel32(nb, f1, r1)));
+                    uint64_t k2 = mul64c<c2>(pack64(sel32(nb, f2, r2), fwd ? f3 : r3));
+                    uint64_t kt = mul64c<c1>(pack64(fwd ? f4 : r4, fwd ? f5 : r5));
                     k1 = rotl64f(k1, 31); k1 = mul64c<c2>(k1);
                     k2 = rotl64f(k2, 33); k2 = mul64c<c1>(k2);
                     kt = rotl64f(kt, 31); kt = mul64c<c2>(kt);

@@ -27,6 +27,13 @@
 #define OP_MIX_AFF(x, y) do { OP_LOP3(x, y); OP_IMAD(x, y); OP_IMADC(x, y); } while (0)
 #define OP_MIX_AH(x, y) do { OP_LOP3(x, y); OP_MULHI(x, y); } while (0)
 #define OP_MIX_AW(x, y) do { OP_LOP3(x, y); OP_WIDEONLY(x, y); } while (0)
+#define OP_MIX_AI(x, y) do { OP_LOP3(x, y); OP_ADD(x, y); } while (0)
+#define OP_MIX_FI(x, y) do { OP_IMAD(x, y); OP_ADD(x, y); } while (0)
+#define OP_MIX_AFI(x, y) do { OP_LOP3(x, y); OP_IMAD(x, y); OP_ADD(x, y); } while (0)
+#define OP_MIX_AAFI(x, y) do { OP_LOP3(x, y); OP_SHF(x, y); OP_IMAD(x, y); OP_ADD(x, y); } while (0)
+#define OP_VIADD(x, y) asm volatile("add.u32 %0, %0, 12345;" : "+r"(x))
+#define OP_SETP(x, y) asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; @p add.u32 %0, %0, 7;}" : "+r"(x) : "r"(y))
+#define OP_MIN(x, y) asm volatile("min.u32 %0, %0, %1; add.u32 %0, %0, 3;" : "+r"(x) : "r"(y))
 
 #define KERNEL(NAME, OP, NINST)                                                                   \
     __global__ void __launch_bounds__(1024) k_##NAME(uint32_t *out, uint32_t seed, unsigned long long *cyc) { \
@@ -78,6 +85,13 @@ KERNEL(mix_aaf, OP_MIX_AAF, 3)
 KERNEL(mix_aff, OP_MIX_AFF, 3)
 KERNEL(mix_ah, OP_MIX_AH, 2)
 KERNEL(mix_aw, OP_MIX_AW, 2)
+KERNEL(mix_ai, OP_MIX_AI, 2)
+KERNEL(mix_fi, OP_MIX_FI, 2)
+KERNEL(mix_afi, OP_MIX_AFI, 3)
+KERNEL(mix_aafi, OP_MIX_AAFI, 4)
+KERNEL(viadd, OP_VIADD, 1)
+KERNEL(setp_padd, OP_SETP, 2)
+KERNEL(min_add, OP_MIN, 2)
 
 int main() {
     int sms = 0;
@@ -92,5 +106,7 @@ int main() {
     run_mulhic(out, cyc, sms); run_wide(out, cyc, sms); run_wideonly(out, cyc, sms); run_shl(out, cyc, sms);
     run_shr(out, cyc, sms); run_mix_af(out, cyc, sms); run_mix_aaf(out, cyc, sms); run_mix_aff(out, cyc, sms);
     run_mix_ah(out, cyc, sms); run_mix_aw(out, cyc, sms);
+    run_mix_ai(out, cyc, sms); run_mix_fi(out, cyc, sms); run_mix_afi(out, cyc, sms); run_mix_aafi(out, cyc, sms);
+    run_viadd(out, cyc, sms); run_setp_padd(out, cyc, sms); run_min_add(out, cyc, sms);
     return 0;
 }
