@@ -11,7 +11,6 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgalah_b200.so")
-CLI_PATH = os.path.join(PKG_DIR, "bin", "galah-b200")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -47,7 +46,7 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    """Compile the shared library (and the CLI, if its source exists). Returns the .so path."""
+    """Compile the shared library. Returns the .so path."""
     if force or _stale(LIB_PATH, _deps()):
         objdir = os.path.join(PKG_DIR, "build")
         os.makedirs(objdir, exist_ok=True)
@@ -69,12 +68,6 @@ def build(force=False, verbose=False):
         link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                "-Xcompiler", "-pthread", "-l:libz.so.1"]
         subprocess.check_call(link)
-    cli_src = os.path.join(CSRC, "cli", "main.cpp")
-    if os.path.exists(cli_src) and (force or _stale(CLI_PATH, [cli_src, LIB_PATH])):
-        os.makedirs(os.path.dirname(CLI_PATH), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(PKG_DIR, "..", "include"),
-                               cli_src, "-o", CLI_PATH, "-L", PKG_DIR, "-lgalah_b200",
-                               "-Wl,-rpath,$ORIGIN/..", "-pthread"])
     return LIB_PATH
 
 
