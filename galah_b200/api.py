@@ -499,6 +499,29 @@ def cluster_packed(seq2, valid, base_off, lengths, precluster_ani=0.9, ani=95.0,
     return clusters, info
 
 
+def init_devices(n_devices):
+    """Binds devices 0 .. n_devices-1 of THIS process for cluster_packed_multi (peer access opened)."""
+    check(lib().galah_b200_init_devices(int(n_devices)))
+
+
+def cluster_packed_multi(seq2, valid, base_off, lengths, n_devices, precluster_ani=0.9, ani=95.0,
+                         min_aligned_fraction=15.0, small_genomes=False):
+    """cluster() on packed genomes in HOST arrays over n_devices GPUs of this process (one host thread
+    per device inside the library; init_devices(n_devices) first).  Same result as cluster_packed."""
+    base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+    check(lib().galah_b200_cluster_packed_multi(ptr(seq2), ptr(valid), base_off.ctypes.data_as(_native.u64p),
+                                                lengths.ctypes.data_as(_native.u64p), len(lengths), int(n_devices),
+                                                ctypes.c_float(precluster_ani), ctypes.c_float(ani),
+                                                ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+                                                ctypes.byref(res), ctypes.byref(stats)))
+    clusters, info = _take_clusters(res)
+    info.update(_stats_dict(stats))
+    return clusters, info
+
+
 def skani_distances(paths, threshold=90.0, min_aligned_fraction=15.0, small_genomes=False, contigs=False, threads=0):
     """GPU replacement for SkaniPreclusterer::distances / distances_contigs (reference
     src/skani.rs:21-56).  Returns (PAIR_DTYPE hits with ANI in percent, number of units)."""

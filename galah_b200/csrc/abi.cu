@@ -9,6 +9,7 @@
 #include <chrono>
 #include <atomic>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -97,8 +98,17 @@ struct Context {
         return 0;
     }
 };
-static Context g_ctx;
-static std::mutex g_mu;
+// One context (stream, workspaces, pipeline index) and one lock PER DEVICE.  A thread works on the
+// process's primary device (the one galah_b200_init bound last) unless it is one of the per-device
+// workers of a multi-device call (galah_b200_cluster_packed_multi), which pin themselves to theirs.
+constexpr int kMaxDevices = 16;
+static Context g_ctxs[kMaxDevices];
+static std::mutex g_mus[kMaxDevices];
+static std::atomic<int> g_primary{0};
+static thread_local int t_dev = -1;
+static inline int cur_dev() { return t_dev >= 0 ? t_dev : g_primary.load(); }
+#define g_ctx (::gb200::g_ctxs[::gb200::cur_dev()])
+#define g_mu (::gb200::g_mus[::gb200::cur_dev()])
 
 static int require_ctx() {
     if (g_ctx.device < 0) {
@@ -754,8 +764,9 @@ int galah_b200_device_count(void) {
     return n;
 }
 
-int galah_b200_init(int device) {
-    std::lock_guard<std::mutex> lock(g_mu);
+static std::mutex g_init_mu;  // serialises (re)binding; taken before any per-device lock
+
+static int init_locked(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -771,21 +782,65 @@ int galah_b200_init(int device) {
                   "' is not sm_100; kernels are built for sm_100a only");
         return GALAH_B200_ERR_NO_DEVICE;
     }
-    if (g_ctx.device >= 0 && g_ctx.device != device) {
-        cudaSetDevice(g_ctx.device);
-        g_ctx.release();
-        if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
-        g_ctx.stream = nullptr;
+    if (device >= kMaxDevices) { set_error("galah_b200_init: device index beyond the context table"); return GALAH_B200_ERR_ARG; }
+    if (t_dev < 0) {
+        // the calling thread is not a pinned worker: `device` becomes the process's primary device, and
+        // what an earlier primary device held is released (one resident working set per process, as before)
+        const int old = g_primary.load();
+        if (old != device && g_ctxs[old].device >= 0) {
+            std::lock_guard<std::mutex> lock_old(g_mus[old]);
+            cudaSetDevice(g_ctxs[old].device);
+            g_ctxs[old].release();
+            if (g_ctxs[old].stream) cudaStreamDestroy(g_ctxs[old].stream);
+            g_ctxs[old].stream = nullptr;
+            g_ctxs[old].device = -1;
+        }
+        g_primary.store(device);
     }
+    std::lock_guard<std::mutex> lock(g_mus[device]);
+    Context &C = g_ctxs[device];
     GB_CUDA(cudaSetDevice(device));
-    if (!g_ctx.stream) {
+    if (!C.stream) {
         // highest priority: the small kernels of the K3 index build must get SM slots while a K1 scan of
         // the next batch (tens of thousands of CTAs, lowest priority, scan_stream) is resident
         int prio_lo = 0, prio_hi = 0;
         GB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        GB_CUDA(cudaStreamCreateWithPriority(&g_ctx.stream, cudaStreamNonBlocking, prio_hi));
+        GB_CUDA(cudaStreamCreateWithPriority(&C.stream, cudaStreamNonBlocking, prio_hi));
     }
-    g_ctx.device = device;
+    C.device = device;
+    return 0;
+}
+
+int galah_b200_init(int device) {
+    std::lock_guard<std::mutex> lock(g_init_mu);
+    return init_locked(device);
+}
+
+// Binds devices 0 .. n_devices - 1 for galah_b200_cluster_packed_multi (device 0 stays the primary
+// device of every single-device entry point) and opens peer access between every pair of them.
+int galah_b200_init_devices(int n_devices) {
+    std::lock_guard<std::mutex> lock(g_init_mu);
+    if (n_devices < 1 || n_devices > kMaxDevices) { set_error("galah_b200_init_devices: bad device count"); return GALAH_B200_ERR_ARG; }
+    if (int rc = init_locked(0)) return rc;
+    for (int d = 1; d < n_devices; d++) {
+        t_dev = d;  // bind slot d without moving the primary device
+        const int rc = init_locked(d);
+        t_dev = -1;
+        if (rc) return rc;
+    }
+    for (int a = 0; a < n_devices; a++) {
+        GB_CUDA(cudaSetDevice(a));
+        for (int b = 0; b < n_devices; b++) {
+            if (a == b) continue;
+            int can = 0;
+            GB_CUDA(cudaDeviceCanAccessPeer(&can, a, b));
+            if (!can) { set_error("galah_b200_init_devices: devices without peer access"); return GALAH_B200_ERR_UNSUPPORTED; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) GB_CUDA(e);
+            cudaGetLastError();
+        }
+    }
+    GB_CUDA(cudaSetDevice(0));
     return 0;
 }
 
@@ -1587,6 +1642,190 @@ int galah_b200_cluster_packed(const uint32_t *seq2, const uint32_t *valid, const
                           min_af_pct, small_genomes, out, stats);
 }
 
+// ------------------------------------------------------------------------------------------
+// The whole path on G devices of ONE process (what a single galah process with several GPUs calls):
+// one host thread per device, pinned to that device's context.
+//   slices     device r owns the genomes [g0[r], g0[r+1]) (equal counts, whole K2 row blocks)
+//   K1 + index every device sketches and indexes ITS slice (host buffers uploaded in batches)
+//   exchange   every device copies the other devices' sketch rows into its own table with
+//              cudaMemcpyPeerAsync (copy engines over NVLink; no kernel, no host staging)
+//   K2         every device builds the block lists and joins ITS row-block shard of the pair grid
+//              (run_prefilter's shard / n_shards: the same boustrophedon split as the multi-process path)
+//   hits       merged and sorted on the host (they are 20 bytes each)
+//   K3         both orientations of every hit, each on the device that owns its QUERY genome; a
+//              reference genome on another device is read IN PLACE through its hash table's device
+//              pointer (peer access, unified addressing)
+//   engine     thread 0
+// ------------------------------------------------------------------------------------------
+namespace {
+struct MultiBarrier {
+    std::mutex mu; std::condition_variable cv; int n, waiting = 0; uint64_t phase = 0;
+    explicit MultiBarrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        const uint64_t my = phase;
+        if (++waiting == n) { waiting = 0; phase++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return phase != my; });
+    }
+};
+}  // namespace
+
+int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                                    const uint64_t *lengths, size_t n, int n_devices, float precluster_min_ani,
+                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
+                                    galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (!out) { set_error("cluster_packed_multi: out is NULL"); return GALAH_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!(ani_threshold_pct > 1.0f)) { set_error("assertion failed: self.threshold > 1.0"); return GALAH_B200_ERR_UNSUPPORTED; }
+    const int G = n_devices;
+    if (G < 1 || G > kMaxDevices) { set_error("cluster_packed_multi: bad device count"); return GALAH_B200_ERR_ARG; }
+    for (int d = 0; d < G; d++)
+        if (g_ctxs[d].device != d) { set_error("cluster_packed_multi: call galah_b200_init_devices(n_devices) first"); return GALAH_B200_ERR_NO_DEVICE; }
+    const double t_begin = now_ms();
+    const uint32_t s = 1000;
+    // slices: equal genome counts, whole row blocks of the K2 grid (the last slice takes what is left)
+    size_t per = (n + (size_t)G - 1) / (size_t)G;
+    per = (per + GALAH_B200_ROW_BLOCK - 1) / GALAH_B200_ROW_BLOCK * GALAH_B200_ROW_BLOCK;
+    std::vector<size_t> g0((size_t)G + 1);
+    for (int r = 0; r <= G; r++) g0[r] = std::min(n, (size_t)r * per);
+
+    MultiBarrier bar(G);
+    std::vector<int> rcs((size_t)G, 0);
+    std::vector<std::string> errs((size_t)G);
+    std::atomic<int> failed{0};
+    std::vector<std::vector<galah_b200_pair_t>> rank_hits((size_t)G);
+    std::vector<galah_b200_pair_t> all_hits;
+    std::vector<float> ani_fwd, ani_rev;
+    std::vector<float> t_ingest((size_t)G, 0.f), t_sketch((size_t)G, 0.f), t_index((size_t)G, 0.f), t_chain((size_t)G, 0.f);
+    double t_k2 = 0.0, t_k3 = 0.0, t_engine = 0.0;
+
+    auto worker = [&](int r) {
+        t_dev = r;
+        std::lock_guard<std::mutex> lock(g_mus[r]);
+        Context &C = g_ctxs[r];
+        // a failing device keeps walking through the barriers (with nothing to do) so that nobody hangs
+        auto fail = [&](int rc) { if (!rcs[r]) { rcs[r] = rc; errs[r] = galah_b200_last_error(); failed.store(1); } };
+        int rc = require_ctx();
+        if (rc) fail(rc);
+        cudaStream_t st = C.stream;
+        const size_t nr = g0[r + 1] - g0[r];
+        AniIndex *index = nullptr;
+        if (!rc) {
+            index = &C.pipeline_index(small_genomes != 0);
+            if (ws_ensure(C.d_table, C.cap_table, std::max<size_t>(n, 1) * s) ||
+                ws_ensure(C.d_counts, C.cap_counts, std::max<size_t>(n, 1)))
+                fail(GALAH_B200_ERR_CUDA);
+        }
+        const double ta = now_ms();
+        if (!rcs[r] && nr) {
+            float a = 0.f, b = 0.f;
+            rc = ingest_packed(seq2, valid, nullptr, base_off + g0[r], lengths + g0[r], nr, false,
+                               C.d_table + g0[r] * (size_t)s, C.d_counts + g0[r], *index, &a, &b);
+            if (rc) fail(rc);
+            t_sketch[r] = a; t_index[r] = b;
+        }
+        if (!rcs[r] && cudaStreamSynchronize(st) != cudaSuccess) fail(GALAH_B200_ERR_CUDA);
+        t_ingest[r] = (float)(now_ms() - ta);
+        bar.wait();  // ---- every slice of the sketch table exists on its owner
+        const double tb = now_ms();
+        if (!failed.load()) {
+            for (int p = 0; p < G && !rcs[r]; p++) {
+                const size_t np = g0[p + 1] - g0[p];
+                if (p == r || np == 0) continue;
+                if (cudaMemcpyPeerAsync(C.d_table + g0[p] * (size_t)s, r, g_ctxs[p].d_table + g0[p] * (size_t)s, p,
+                                        np * (size_t)s * 8, st) != cudaSuccess ||
+                    cudaMemcpyPeerAsync(C.d_counts + g0[p], r, g_ctxs[p].d_counts + g0[p], p, np * 4, st) != cudaSuccess) {
+                    set_error("cluster_packed_multi: peer copy of the sketch rows failed");
+                    fail(GALAH_B200_ERR_CUDA);
+                }
+            }
+            if (!rcs[r]) {
+                galah_b200_pair_t *hits = nullptr;
+                size_t n_hits = 0;
+                rc = run_prefilter(C.d_table, C.d_counts, n, s, 21, precluster_min_ani, (uint32_t)r, (uint32_t)G, st, &hits, &n_hits);
+                if (rc) fail(rc);
+                else rank_hits[r].assign(hits, hits + n_hits);
+                free(hits);
+            }
+        }
+        bar.wait();  // ---- every shard's hits are on the host
+        if (r == 0 && !failed.load()) {
+            for (auto &v : rank_hits) all_hits.insert(all_hits.end(), v.begin(), v.end());
+            std::sort(all_hits.begin(), all_hits.end(), [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) {
+                return a.i != b.i ? a.i < b.i : a.j < b.j; });
+            ani_fwd.assign(all_hits.size(), 0.f); ani_rev.assign(all_hits.size(), 0.f);
+            t_k2 = now_ms() - tb;
+        }
+        bar.wait();  // ---- the merged hit list is visible to everybody
+        const double tc = now_ms();
+        if (!failed.load() && nr) {
+            auto owner = [&](uint32_t g) { return (int)std::min<size_t>((size_t)g / per, (size_t)G - 1); };
+            // jobs of this device: (hit, orientation) whose query genome it owns
+            std::vector<uint32_t> job_hit, job_pairs;
+            std::vector<uint8_t> job_rev;
+            std::vector<int64_t> peer_first((size_t)G, -1);
+            for (size_t h = 0; h < all_hits.size() && !rcs[r]; h++) {
+                for (int o = 0; o < 2; o++) {
+                    const uint32_t q = o ? all_hits[h].j : all_hits[h].i, ref = o ? all_hits[h].i : all_hits[h].j;
+                    if (owner(q) != r) continue;
+                    const int pr = owner(ref);
+                    uint32_t ref_id;
+                    if (pr == r) ref_id = ref - (uint32_t)g0[r];
+                    else {
+                        if (peer_first[pr] < 0) {
+                            const AniIndex *pi = g_ctxs[pr].pipe_index[small_genomes ? 1 : 0];
+                            uint32_t first = 0;
+                            rc = index->attach_peer_direct(pi->table_base(), pi->table_offsets().data(), pi->total_lengths().data(),
+                                                           pi->size(), &first);
+                            if (rc) { fail(rc); break; }
+                            peer_first[pr] = first;
+                        }
+                        ref_id = (uint32_t)peer_first[pr] + (ref - (uint32_t)g0[pr]);
+                    }
+                    job_hit.push_back((uint32_t)h); job_rev.push_back((uint8_t)o);
+                    job_pairs.push_back(q - (uint32_t)g0[r]); job_pairs.push_back(ref_id);
+                }
+            }
+            if (!rcs[r] && !job_hit.empty()) {
+                std::vector<AniPairResult> res(job_hit.size());
+                rc = index->pairs(job_pairs.data(), job_hit.size(), min_af_pct, false, res.data(), st);
+                if (rc) fail(rc);
+                else {
+                    for (size_t x = 0; x < job_hit.size(); x++) (job_rev[x] ? ani_rev : ani_fwd)[job_hit[x]] = res[x].ani;
+                    t_chain[r] = index->last_chain_ms;
+                }
+            }
+        }
+        bar.wait();  // ---- every ANI value is in the shared tables; nobody reads a peer's index any more
+        if (r == 0) t_k3 = now_ms() - tc;
+        if (index) index->clear();
+        if (r == 0 && !failed.load()) {
+            const double td = now_ms();
+            rc = galah_b200_cluster_from_ani_tables(n, all_hits.data(), all_hits.size(), ani_fwd.data(), ani_rev.data(),
+                                                    ani_threshold_pct, out);
+            if (rc) fail(rc);
+            t_engine = now_ms() - td;
+        }
+        t_dev = -1;
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; r++) th.emplace_back(worker, r);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < G; r++)
+        if (rcs[r]) { set_error("device " + std::to_string(r) + ": " + errs[r]); return rcs[r]; }
+    if (stats) {
+        stats->n_precluster_hits = all_hits.size(); stats->n_ani_pairs = 2 * all_hits.size();
+        stats->ingest_ms = *std::max_element(t_ingest.begin(), t_ingest.end());
+        stats->sketch_ms = *std::max_element(t_sketch.begin(), t_sketch.end());
+        stats->index_ms = *std::max_element(t_index.begin(), t_index.end());
+        stats->ani_chain_ms = *std::max_element(t_chain.begin(), t_chain.end());
+        stats->prefilter_ms = (float)t_k2; stats->ani_ms = (float)t_k3; stats->engine_ms = (float)t_engine;
+        stats->total_ms = (float)(now_ms() - t_begin);
+    }
+    return 0;
+}
+
 int galah_b200_skani_distances(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,
                                int small_genomes, int per_record, int host_threads, galah_b200_pair_t **out,
                                size_t *n_out, size_t *n_units) {
@@ -1745,7 +1984,7 @@ int session_compute(galah_b200_session *s, std::vector<uint32_t> &pairs) {
     }
     if (todo.empty()) return 0;
     std::vector<gb200::AniPairResult> res(todo.size() / 2);
-    if (int rc = s->index->pairs(todo.data(), todo.size() / 2, s->min_af_pct, false, res.data(), gb200::g_ctx.stream)) return rc;
+    if (int rc = s->index->pairs(todo.data(), todo.size() / 2, s->min_af_pct, false, res.data(), g_ctx.stream)) return rc;
     for (size_t x = 0; x < res.size(); x++) s->cache[((uint64_t)todo[2 * x] << 32) | todo[2 * x + 1]] = res[x].ani;
     s->n_pairs_computed += res.size(); s->n_launches++;
     return 0;

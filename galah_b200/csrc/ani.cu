@@ -630,8 +630,21 @@ int AniIndex::attach_peer(const cudaIpcMemHandle_t &handle, const uint64_t *tabl
     return 0;
 }
 
+int AniIndex::attach_peer_direct(const unsigned long long *base, const uint64_t *table_off, const uint64_t *total_len,
+                                 size_t n, uint32_t *first_id) {
+    PeerGroup pg;
+    pg.base = base;
+    pg.table_off.assign(table_off, table_off + n + 1);
+    pg.ipc = false;
+    peers_.push_back(std::move(pg));
+    *first_id = (uint32_t)size() + peer_first_.back();
+    peer_first_.push_back(peer_first_.back() + (uint32_t)n);
+    peer_total_len_.insert(peer_total_len_.end(), total_len, total_len + n);
+    return 0;
+}
+
 void AniIndex::clear() {
-    for (auto &pg : peers_) cudaIpcCloseMemHandle((void *)pg.base);
+    for (auto &pg : peers_) if (pg.ipc) cudaIpcCloseMemHandle((void *)pg.base);
     peers_.clear(); peer_first_.assign(1, 0); peer_total_len_.clear();
     seed_off_.assign(1, 0); cso_off_.assign(1, 0); table_off_.assign(1, 0);
     total_len_.clear(); n_chunks_.clear();
@@ -640,7 +653,7 @@ void AniIndex::clear() {
 }
 
 AniIndex::~AniIndex() {
-    for (auto &pg : peers_) cudaIpcCloseMemHandle((void *)pg.base);
+    for (auto &pg : peers_) if (pg.ipc) cudaIpcCloseMemHandle((void *)pg.base);
     d_kq_.release(); d_cso_.release(); d_table_.release();
     d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
     for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);

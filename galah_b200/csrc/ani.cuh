@@ -87,6 +87,13 @@ public:
     int export_tables(cudaIpcMemHandle_t *handle, std::vector<uint64_t> &table_off, std::vector<uint64_t> &total_len) const;
     int attach_peer(const cudaIpcMemHandle_t &handle, const uint64_t *table_off, const uint64_t *total_len, size_t n,
                     uint32_t *first_id);
+    // The same inside ONE process that drives several devices (galah_b200_cluster_packed_multi): the
+    // peer's table array is addressed directly (peer access enabled, unified addressing), no IPC.
+    int attach_peer_direct(const unsigned long long *base, const uint64_t *table_off, const uint64_t *total_len, size_t n,
+                           uint32_t *first_id);
+    const unsigned long long *table_base() const { return d_table_.p; }
+    const std::vector<uint64_t> &table_offsets() const { return table_off_; }
+    const std::vector<uint64_t> &total_lengths() const { return total_len_; }
     size_t n_peer_genomes() const { return peer_total_len_.size(); }
     // parity hooks
     int genome_info(size_t g, uint64_t *n_seeds, uint32_t *n_chunks, uint64_t *total_len) const;
@@ -108,7 +115,7 @@ private:
     cudaEvent_t ev_[2] = {nullptr, nullptr};
     AniScratch *scratch_ = nullptr;
     // peer tables (attach_peer): group g covers peer ids [peer_first_[g], peer_first_[g + 1])
-    struct PeerGroup { const unsigned long long *base; std::vector<uint64_t> table_off; };
+    struct PeerGroup { const unsigned long long *base; std::vector<uint64_t> table_off; bool ipc = true; };
     std::vector<PeerGroup> peers_;
     std::vector<uint32_t> peer_first_{0};
     std::vector<uint64_t> peer_total_len_;

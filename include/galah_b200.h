@@ -339,6 +339,23 @@ int galah_b200_cluster_packed_device(const uint32_t *d_seq2, const uint32_t *d_v
                                      int small_genomes, galah_b200_clusters_t *out,
                                      galah_b200_cluster_stats_t *stats);
 
+/* The same call on SEVERAL GPUs of one process -- what a single galah process on a multi-GPU box
+ * calls in place of clusterer::cluster (src/clusterer.rs:14-152; the reference parallelises over
+ * rayon threads, src/clusterer.rs:190-214, 267-293: here the unit of parallelism is a device).
+ * galah_b200_init_devices(n) binds devices 0 .. n-1 (one context, stream and workspace each) and
+ * opens peer access between them; device 0 stays the device of every single-GPU entry point.
+ * galah_b200_cluster_packed_multi takes HOST arrays (layout of galah_b200_cluster_packed) and runs
+ * one host thread per device: genome slices for K1 / the K3 index, the sketch rows exchanged by
+ * peer copies (copy engines over NVLink), row-block shards of the K2 grid, K3 pairs on the device
+ * that owns the query genome reading the reference's hash table in place on its peer, the greedy
+ * engine on the host.  Clusters are identical to the single-GPU call's. */
+int galah_b200_init_devices(int n_devices);
+int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                                    const uint64_t *lengths, size_t n, int n_devices,
+                                    float precluster_min_ani, float ani_threshold_pct, float min_af_pct,
+                                    int small_genomes, galah_b200_clusters_t *out,
+                                    galah_b200_cluster_stats_t *stats);
+
 /* First half of the two calls above, for callers that drive the stages themselves (the multi-GPU
  * pipeline, one process per GPU): packed genomes (host arrays if device == 0, else resident) ->
  * K1 sketch rows written to the DEVICE table d_hashes / d_counts (stride 1000) and the genomes

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""The in-process multi-device entry (galah_b200_cluster_packed_multi, one host thread per GPU inside the
+library) against the single-GPU call on the same host buffers: identical clusters, plus timings.
+
+    python tools/check_multi_device.py [--genomes 2560] [--len 1000000] [--devices G] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genomes", type=int, default=2560)
+    ap.add_argument("--len", type=int, default=1_000_000)
+    ap.add_argument("--devices", type=int, default=0, help="0 = all visible")
+    ap.add_argument("--passes", type=int, default=2)
+    ap.add_argument("--skip-single", action="store_true")
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    import torch
+    import galah_b200 as gb
+    G = args.devices or torch.cuda.device_count()
+    n, L = args.genomes, args.len
+    gb.init(0)
+    dev = torch.device("cuda", 0)
+    lay = gb.synth_layout(n, L)
+    # synthesise in slabs on device 0, keep the packed genomes in pinned host memory
+    h_seq = torch.empty(lay["seq2_words"], dtype=torch.int32, pin_memory=True)
+    h_val = torch.empty(lay["valid_words"], dtype=torch.int32, pin_memory=True)
+    slab = max(1, min(n, (8 << 30) // max(1, lay["padded"] // 4)))
+    for g0 in range(0, n, slab):
+        m = min(slab, n - g0)
+        l2 = gb.synth_layout(m, L)
+        d_seq = torch.empty(l2["seq2_words"], dtype=torch.int32, device=dev)
+        d_val = torch.empty(l2["valid_words"], dtype=torch.int32, device=dev)
+        d_off = torch.empty(m + 1, dtype=torch.int64, device=dev)
+        gb.synth_packed_device(1, g0, m, L, d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        w0, v0 = g0 * lay["padded"] // 16, g0 * lay["padded"] // 32
+        h_seq[w0: w0 + m * lay["padded"] // 16].copy_(d_seq[: m * lay["padded"] // 16])
+        h_val[v0: v0 + m * lay["padded"] // 32].copy_(d_val[: m * lay["padded"] // 32])
+        del d_seq, d_val, d_off
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    base_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(lay["padded"])
+    lengths = np.full(n, L, np.uint64)
+    pairs = n * (n - 1) // 2
+    out = {"genomes": n, "genome_bp": L, "pairs": pairs, "devices": G}
+    single = None
+    if not args.skip_single:
+        for _ in range(args.passes):
+            t0 = time.perf_counter()
+            single, info1 = gb.cluster_packed(h_seq.data_ptr(), h_val.data_ptr(), base_off, lengths, device=False)
+            out["single_gpu_s"] = time.perf_counter() - t0
+        out["single_gpu_clusters"] = len(single)
+        out["single_gpu_sha1"] = single.sha1()
+    gb.init_devices(G)
+    for _ in range(args.passes):
+        t0 = time.perf_counter()
+        multi, info = gb.cluster_packed_multi(h_seq.data_ptr(), h_val.data_ptr(), base_off, lengths, G)
+        out["multi_s"] = time.perf_counter() - t0
+    out["multi_clusters"] = len(multi)
+    out["multi_sha1"] = multi.sha1()
+    out["multi_pairs_per_s"] = pairs / out["multi_s"]
+    out["multi_phases_ms"] = {k: round(float(v), 2) for k, v in info.items() if k.endswith("_ms")}
+    out["counts"] = {k: int(v) for k, v in info.items() if not k.endswith("_ms")}
+    ok = single is None or (single == multi)
+    out["identical_to_single_gpu"] = None if single is None else bool(ok)
+    print(json.dumps(out), flush=True)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(out, f)
+    print("ALL OK" if ok else "MISMATCH", flush=True)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
