@@ -137,6 +137,9 @@ _SIGNATURES = {
     "galah_b200_cluster_packed_multi": (ctypes.c_int, [vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                                        ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                        ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),
+    "galah_b200_cluster_files_multi": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                      ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Clusters),
+                                                      ctypes.POINTER(ClusterStats)]),
     "galah_b200_session_create": (ctypes.c_int, [ctypes.POINTER(vp)]),
     "galah_b200_session_free": (None, [vp]),
     "galah_b200_session_set_clusterer": (ctypes.c_int, [vp, ctypes.c_int]),

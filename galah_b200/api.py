@@ -470,6 +470,21 @@ def cluster(genomes, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0, sm
     return clusters, info
 
 
+def cluster_multi(genomes, n_devices, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0, small_genomes=False,
+                  threads=0):
+    """cluster() over n_devices GPUs of this process (init_devices(n_devices) first): the path list is cut
+    into one slice per device, each read / decoded / sketched / indexed on its device."""
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    check(lib().galah_b200_cluster_files_multi(_paths_array(genomes), len(genomes), int(n_devices),
+                                               ctypes.c_float(precluster_ani), ctypes.c_float(ani),
+                                               ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)), threads,
+                                               ctypes.byref(res), ctypes.byref(stats)))
+    clusters, info = _take_clusters(res)
+    info.update(_stats_dict(stats))
+    return clusters, info
+
+
 def _stats_dict(stats):
     d = {"n_precluster_hits": int(stats.n_precluster_hits), "n_ani_pairs": int(stats.n_ani_pairs)}
     for f in ("ani_chain_ms", "ingest_ms", "sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms", "total_ms"):

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <memory>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -1670,10 +1671,13 @@ struct MultiBarrier {
 };
 }  // namespace
 
-int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
-                                    const uint64_t *lengths, size_t n, int n_devices, float precluster_min_ani,
-                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
-                                    galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+// ingest(r, first genome, genome count, sketch rows, counts, index, K1 ms, index ms): device r's slice -> its rows of
+// its own sketch table + its K3 index; runs on the worker thread pinned to device r, which holds that device's lock
+using MultiIngest = std::function<int(int, size_t, size_t, uint64_t *, uint32_t *, AniIndex &, float *, float *)>;
+
+static int cluster_multi(size_t n, int n_devices, const MultiIngest &ingest, float precluster_min_ani,
+                         float ani_threshold_pct, float min_af_pct, int small_genomes,
+                         galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
     if (!out) { set_error("cluster_packed_multi: out is NULL"); return GALAH_B200_ERR_ARG; }
     memset(out, 0, sizeof(*out));
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -1720,8 +1724,7 @@ int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid,
         const double ta = now_ms();
         if (!rcs[r] && nr) {
             float a = 0.f, b = 0.f;
-            rc = ingest_packed(seq2, valid, nullptr, base_off + g0[r], lengths + g0[r], nr, false,
-                               C.d_table + g0[r] * (size_t)s, C.d_counts + g0[r], *index, &a, &b);
+            rc = ingest(r, g0[r], nr, C.d_table + g0[r] * (size_t)s, C.d_counts + g0[r], *index, &a, &b);
             if (rc) fail(rc);
             t_sketch[r] = a; t_index[r] = b;
         }
@@ -1824,6 +1827,35 @@ int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid,
         stats->total_ms = (float)(now_ms() - t_begin);
     }
     return 0;
+}
+
+int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                                    const uint64_t *lengths, size_t n, int n_devices, float precluster_min_ani,
+                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
+                                    galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("packed genomes: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
+    const MultiIngest ingest = [&](int, size_t first, size_t count, uint64_t *d_rows, uint32_t *d_cnt, AniIndex &index,
+                                   float *k1_ms, float *ix_ms) {
+        return ingest_packed(seq2, valid, nullptr, base_off + first, lengths + first, count, false, d_rows, d_cnt, index,
+                             k1_ms, ix_ms);
+    };
+    return cluster_multi(n, n_devices, ingest, precluster_min_ani, ani_threshold_pct, min_af_pct, small_genomes, out, stats);
+}
+
+int galah_b200_cluster_files_multi(const char *const *paths, size_t n, int n_devices, float precluster_min_ani,
+                                   float ani_threshold_pct, float min_af_pct, int small_genomes, int host_threads,
+                                   galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int per_device = std::max(1, host_threads / std::max(1, n_devices));
+    const MultiIngest ingest = [&](int, size_t first, size_t count, uint64_t *d_rows, uint32_t *d_cnt, AniIndex &index,
+                                   float *, float *) {
+        IngestSinks sinks;
+        sinks.sketch = true; sinks.k = 21; sinks.s = 1000; sinks.seed = 0;
+        sinks.d_hashes = d_rows; sinks.d_counts = d_cnt; sinks.ani = &index;
+        return ingest_files(paths + first, count, per_device, sinks);
+    };
+    return cluster_multi(n, n_devices, ingest, precluster_min_ani, ani_threshold_pct, min_af_pct, small_genomes, out, stats);
 }
 
 int galah_b200_skani_distances(const char *const *paths, size_t n, float threshold_pct, float min_af_pct,

@@ -355,6 +355,12 @@ int galah_b200_cluster_packed_multi(const uint32_t *seq2, const uint32_t *valid,
                                     float precluster_min_ani, float ani_threshold_pct, float min_af_pct,
                                     int small_genomes, galah_b200_clusters_t *out,
                                     galah_b200_cluster_stats_t *stats);
+/* galah_b200_cluster_files on several GPUs: device r reads, decodes (K0), sketches and indexes the
+ * r-th slice of the path list with host_threads / n_devices reader threads; the rest as above. */
+int galah_b200_cluster_files_multi(const char *const *paths, size_t n, int n_devices, float precluster_min_ani,
+                                   float ani_threshold_pct, float min_af_pct, int small_genomes,
+                                   int host_threads, galah_b200_clusters_t *out,
+                                   galah_b200_cluster_stats_t *stats);
 
 /* First half of the two calls above, for callers that drive the stages themselves (the multi-GPU
  * pipeline, one process per GPU): packed genomes (host arrays if device == 0, else resident) ->

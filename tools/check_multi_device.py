@@ -73,6 +73,32 @@ def main():
     out["counts"] = {k: int(v) for k, v in info.items() if not k.endswith("_ms")}
     ok = single is None or (single == multi)
     out["identical_to_single_gpu"] = None if single is None else bool(ok)
+    # the same through FASTA files: 300 small genomes (families of 3) written here, clustered on one and on G devices
+    import tempfile
+    rng = np.random.default_rng(7)
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for fam in range(100):
+            founder = rng.integers(0, 4, 120_000, dtype=np.uint8)
+            for member in range(3):
+                seq = founder.copy()
+                if member:
+                    pos = rng.choice(len(seq), size=len(seq) // (60 * member), replace=False)
+                    seq[pos] = (seq[pos] + rng.integers(1, 4, len(pos), dtype=np.uint8)) % 4
+                text = np.frombuffer(b"ACGT", dtype=np.uint8)[seq]
+                path = os.path.join(tmp, f"g{fam:03d}_{member}.fna")
+                with open(path, "wb") as f:
+                    f.write(b">c1\n")
+                    for x in range(0, len(text), 80):
+                        f.write(text[x:x + 80].tobytes() + b"\n")
+                paths.append(path)
+        gb.init(0)
+        one, _ = gb.cluster(paths)
+        gb.init_devices(G)
+        many, finfo = gb.cluster_multi(paths, G)
+        out["files"] = {"genomes": len(paths), "clusters": len(one), "identical_to_single_gpu": bool(one == many),
+                        "multi_phases_ms": {k: round(float(v), 2) for k, v in finfo.items() if k.endswith("_ms")}}
+        ok = ok and (one == many)
     print(json.dumps(out), flush=True)
     if args.json:
         with open(args.json, "w") as f:
