@@ -1212,10 +1212,10 @@ int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_m
     return 0;
 }
 
-int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
-                                      int skip_clusterer, float ani_threshold,
-                                      galah_b200_ani_fn calculate_ani, void *ctx,
-                                      galah_b200_clusters_t *out) {
+static int cluster_engine_call(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits, int skip_clusterer,
+                               float ani_threshold, galah_b200_ani_fn calculate_ani, void *ctx,
+                               const AniByHitFn *by_hit, galah_b200_clusters_t *out,
+                               const ReversePrefetchFn *prefetch_reverse = nullptr) {
     if (!out) { set_error("cluster: out is NULL"); return GALAH_B200_ERR_ARG; }
     memset(out, 0, sizeof(*out));
     std::vector<PreclusterHit> h(n_hits);
@@ -1227,7 +1227,7 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
         };
     ClusterResult res;
     std::string err;
-    if (cluster_from_hits(n_genomes, h.data(), n_hits, skip_clusterer != 0, ani_threshold, fn, res, err)) {
+    if (cluster_from_hits(n_genomes, h.data(), n_hits, skip_clusterer != 0, ani_threshold, fn, res, err, by_hit, prefetch_reverse)) {
         set_error("cluster: " + err);
         return GALAH_B200_ERR_UNSUPPORTED;
     }
@@ -1241,6 +1241,13 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
     out->n_preclusters = res.n_preclusters;
     out->largest_precluster = res.largest_precluster;
     return 0;
+}
+
+int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                      int skip_clusterer, float ani_threshold,
+                                      galah_b200_ani_fn calculate_ani, void *ctx,
+                                      galah_b200_clusters_t *out) {
+    return cluster_engine_call(n_genomes, hits, n_hits, skip_clusterer, ani_threshold, calculate_ani, ctx, nullptr, out);
 }
 
 // ANI of hit pairs served from a table (hits sorted by (i, j), ani[x] belongs to hits[x]).
@@ -1258,21 +1265,21 @@ struct AniTable {
     const uint8_t *have_rev = nullptr;         // [n] or null: ani_rev[x] is valid
     std::vector<size_t> *rev_requests = nullptr;
 };
-int ani_table_lookup(void *ctx, uint32_t rep, uint32_t genome, float *ani) {
-    const AniTable *t = (const AniTable *)ctx;
-    const uint32_t a = std::min(rep, genome), b = std::max(rep, genome);
-    size_t lo = 0, hi = t->n;
-    while (lo < hi) {
-        const size_t mid = (lo + hi) >> 1;
-        if (t->hits[mid].i < a || (t->hits[mid].i == a && t->hits[mid].j < b)) lo = mid + 1; else hi = mid;
-    }
-    if (lo >= t->n || t->hits[lo].i != a || t->hits[lo].j != b) return 0;
+// The engine hands over the index of the hit the pair belongs to: no search.
+bool ani_table_by_hit(const AniTable &t, uint32_t rep, uint32_t genome, size_t hit, float *ani) {
     if (rep > genome) {
-        if (t->ani_rev && (!t->have_rev || t->have_rev[lo])) { *ani = t->ani_rev[lo]; return 1; }
-        if (t->rev_requests) t->rev_requests->push_back(lo);
+        if (t.ani_rev && (!t.have_rev || t.have_rev[hit])) { *ani = t.ani_rev[hit]; return true; }
+        if (t.rev_requests) t.rev_requests->push_back(hit);
     }
-    *ani = *(const float *)((const char *)t->ani + lo * t->stride);  // skani never yields None (src/skani.rs:760)
-    return 1;
+    *ani = *(const float *)((const char *)t.ani + hit * t.stride);  // skani never yields None (src/skani.rs:760)
+    return true;
+}
+int cluster_from_table(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits, float ani_threshold,
+                       const AniTable &table, galah_b200_clusters_t *out, const ReversePrefetchFn *prefetch_reverse = nullptr) {
+    const AniByHitFn fn = [&table](uint32_t rep, uint32_t genome, size_t hit, float *ani) {
+        return ani_table_by_hit(table, rep, genome, hit, ani);
+    };
+    return cluster_engine_call(n_genomes, hits, n_hits, 0, ani_threshold, nullptr, nullptr, &fn, out, prefetch_reverse);
 }
 }  // namespace
 
@@ -1290,7 +1297,7 @@ int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t 
     if (n_hits && (!hits || !ani)) { set_error("cluster_from_ani_table: NULL hits / ani"); return GALAH_B200_ERR_ARG; }
     if (int rc = check_sorted_hits(hits, n_hits)) return rc;
     AniTable table{hits, n_hits, ani, sizeof(float)};
-    return galah_b200_cluster_from_distances(n_genomes, hits, n_hits, 0, ani_threshold, ani_table_lookup, &table, out);
+    return cluster_from_table(n_genomes, hits, n_hits, ani_threshold, table, out);
 }
 
 int galah_b200_cluster_from_ani_tables(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
@@ -1300,7 +1307,7 @@ int galah_b200_cluster_from_ani_tables(size_t n_genomes, const galah_b200_pair_t
     if (int rc = check_sorted_hits(hits, n_hits)) return rc;
     AniTable table{hits, n_hits, ani_fwd, sizeof(float)};
     table.ani_rev = ani_rev;
-    return galah_b200_cluster_from_distances(n_genomes, hits, n_hits, 0, ani_threshold, ani_table_lookup, &table, out);
+    return cluster_from_table(n_genomes, hits, n_hits, ani_threshold, table, out);
 }
 
 // Stages 2 + 3 of the whole path once the sketch table (device) and the K3 index are in place:
@@ -1324,46 +1331,43 @@ static int cluster_from_resident(const uint64_t *d_table, const uint32_t *d_coun
     for (size_t x = 0; x < n_hits; x++) { pairs[2 * x] = hits[x].i; pairs[2 * x + 1] = hits[x].j; }
     std::vector<AniPairResult> res(n_hits);
     if (int rc = index.pairs(pairs.data(), n_hits, min_af_pct, false, res.data(), st)) return rc;
-    double t2 = now_ms();
+    const double t2 = now_ms();
     float chain_ms = index.last_chain_ms;
-    double engine_ms = 0.0;
+    // The membership sweep asks for representatives that come AFTER the genome: those pairs have the
+    // representative as the query.  The engine reports them once every representative is known (its
+    // search only reads forward values); exactly those pairs get one more K3 launch, then the
+    // engine goes on to the memberships -- one engine pass, two K3 launches.
     AniTable table{hits, n_hits, n_hits ? &res[0].ani : nullptr, sizeof(AniPairResult)};
-    std::vector<size_t> rev_requests;
-    table.rev_requests = &rev_requests;
-    int rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
-    engine_ms += now_ms() - t2;
-    if (rc == 0 && !rev_requests.empty()) {
-        // membership asked for representatives that come AFTER the genome: those pairs have the
-        // representative as the query.  One more K3 launch for exactly them, then the engine again
-        // (the representatives do not change: their search only reads forward values).
-        const double t3 = now_ms();
-        std::sort(rev_requests.begin(), rev_requests.end());
-        rev_requests.erase(std::unique(rev_requests.begin(), rev_requests.end()), rev_requests.end());
-        std::vector<uint32_t> rp(2 * rev_requests.size());
-        for (size_t x = 0; x < rev_requests.size(); x++) { rp[2 * x] = hits[rev_requests[x]].j; rp[2 * x + 1] = hits[rev_requests[x]].i; }
-        std::vector<AniPairResult> rres(rev_requests.size());
-        if (int rc2 = index.pairs(rp.data(), rev_requests.size(), min_af_pct, false, rres.data(), st)) return rc2;
+    std::vector<float> ani_rev(n_hits, 0.f);
+    std::vector<uint8_t> have_rev(n_hits, 0);
+    table.ani_rev = ani_rev.data(); table.have_rev = have_rev.data();
+    double rev_ms = 0.0;
+    size_t n_rev = 0;
+    const ReversePrefetchFn prefetch = [&](const std::vector<size_t> &want) -> int {
+        const double ta = now_ms();
+        std::vector<uint32_t> rp(2 * want.size());
+        for (size_t x = 0; x < want.size(); x++) { rp[2 * x] = hits[want[x]].j; rp[2 * x + 1] = hits[want[x]].i; }
+        std::vector<AniPairResult> rres(want.size());
+        if (int rc2 = index.pairs(rp.data(), want.size(), min_af_pct, false, rres.data(), st)) return rc2;
         chain_ms += index.last_chain_ms;
-        std::vector<float> ani_rev(n_hits, 0.f);
-        std::vector<uint8_t> have_rev(n_hits, 0);
-        for (size_t x = 0; x < rev_requests.size(); x++) { ani_rev[rev_requests[x]] = rres[x].ani; have_rev[rev_requests[x]] = 1; }
-        table.ani_rev = ani_rev.data(); table.have_rev = have_rev.data(); table.rev_requests = nullptr;
-        galah_b200_clusters_free(out);
-        memset(out, 0, sizeof(*out));
-        const double t4 = now_ms();
-        t2 += t4 - t3;  // the reverse launch belongs to the ANI phase
-        rc = galah_b200_cluster_from_distances(n, hits, n_hits, 0, ani_threshold_pct, ani_table_lookup, &table, out);
-        engine_ms += now_ms() - t4;
-        if (stats) stats->n_ani_pairs = n_hits + rev_requests.size();
-    }
+        for (size_t x = 0; x < want.size(); x++) { ani_rev[want[x]] = rres[x].ani; have_rev[want[x]] = 1; }
+        n_rev = want.size();
+        rev_ms = now_ms() - ta;
+        return 0;
+    };
+    int rc = cluster_from_table(n, hits, n_hits, ani_threshold_pct, table, out, &prefetch);
+    const double t3 = now_ms();
+    const double engine_ms = (t3 - t2) - rev_ms;  // the reverse launch belongs to the ANI phase
+    const double ani_total_ms = (t2 - t1) + rev_ms;
+    if (stats) stats->n_ani_pairs = n_hits + n_rev;
     if (getenv("GALAH_B200_DEBUG"))
-        fprintf(stderr, "[cluster_from_resident] prefilter %.2f ms, ani (both launches) %.2f ms, engine (both passes) %.2f ms, "
-                "%zu hits, %zu reverse requests\n", t1 - t0, t2 - t1, engine_ms, n_hits, rev_requests.size());
+        fprintf(stderr, "[cluster_from_resident] prefilter %.2f ms, ani (both launches) %.2f ms, engine %.2f ms, "
+                "%zu hits, %zu reverse requests\n", t1 - t0, ani_total_ms, engine_ms, n_hits, n_rev);
     if (stats) {
         stats->n_precluster_hits = n_hits;
         if (stats->n_ani_pairs == 0) stats->n_ani_pairs = n_hits;
         stats->ani_chain_ms = chain_ms;
-        stats->prefilter_ms = (float)(t1 - t0); stats->ani_ms = (float)(t2 - t1); stats->engine_ms = (float)engine_ms;
+        stats->prefilter_ms = (float)(t1 - t0); stats->ani_ms = (float)ani_total_ms; stats->engine_ms = (float)engine_ms;
     }
     return rc;
 }

@@ -27,7 +27,11 @@
 // (CSR adjacency + union-find), O(hits) instead of O(N^2) -- SURVEY.md 8f item 1.
 #include "cluster_engine.hpp"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 
 namespace gb200 {
@@ -51,6 +55,7 @@ struct Adjacency {  // CSR over both directions, neighbours ascending
     std::vector<uint64_t> off;
     std::vector<uint32_t> nbr;
     std::vector<float> ani;
+    std::vector<uint32_t> hit;  // index of the precluster hit behind the slot
     // index of (a, b) in nbr/ani, or -1
     int64_t find(uint32_t a, uint32_t b) const {
         const uint32_t *lo = nbr.data() + off[a], *hi = nbr.data() + off[a + 1];
@@ -68,10 +73,13 @@ struct OptAni { bool some; float ani; };
 }  // namespace
 
 int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool skip_clusterer,
-                      float ani_threshold, const AniFn &calculate_ani, ClusterResult &out,
-                      std::string &err) {
+                      float ani_threshold, const AniFn &calculate_ani_fn, ClusterResult &out,
+                      std::string &err, const AniByHitFn *by_hit, const ReversePrefetchFn *prefetch_reverse) {
     out = ClusterResult();
     out.offsets.push_back(0);
+    const bool dbg = getenv("GALAH_B200_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (n == 0) {
         // the reference indexes preclusters[0] unconditionally (src/clusterer.rs:84)
         err = "index out of bounds: the len is 0 but the index is 0";
@@ -83,45 +91,48 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
             return 1;
         }
     }
-    if (!skip_clusterer && !calculate_ani) { err = "calculate_ani callback required"; return 1; }
+    if (!skip_clusterer && !calculate_ani_fn && !by_hit) { err = "calculate_ani callback required"; return 1; }
 
     // ---- adjacency (later duplicates of a key overwrite earlier ones, as BTreeMap::insert does)
     Adjacency adj;
     adj.off.assign(n + 1, 0);
     {
-        // unique keys, last write wins: stable sort by key, keep the last record of every run
-        std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
-        for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
+        // unique keys, last write wins.  The usual input -- the preclusterer's own output -- is already
+        // strictly ascending by key: then the hits are used as they are; otherwise stable sort by key and
+        // keep the last record of every run.
         bool sorted = true;
-        for (size_t h = 1; h < n_hits && sorted; h++) sorted = keyed[h - 1].first < keyed[h].first;
-        if (!sorted)
+        for (size_t h = 1; h < n_hits && sorted; h++)
+            sorted = pair_key(hits[h - 1].i, hits[h - 1].j) < pair_key(hits[h].i, hits[h].j);
+        std::vector<std::pair<uint64_t, uint32_t>> uniq;  // (key, index of the last hit with that key)
+        uniq.reserve(n_hits);
+        if (sorted) {
+            for (size_t h = 0; h < n_hits; h++) uniq.emplace_back(pair_key(hits[h].i, hits[h].j), (uint32_t)h);
+        } else {
+            std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
+            for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
             std::stable_sort(keyed.begin(), keyed.end(),
                              [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &b) { return a.first < b.first; });
-        std::vector<std::pair<uint64_t, float>> uniq;
-        uniq.reserve(n_hits);
-        for (size_t h = 0; h < n_hits; h++)
-            if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.emplace_back(keyed[h].first, hits[keyed[h].second].ani);
+            for (size_t h = 0; h < n_hits; h++)
+                if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.emplace_back(keyed[h].first, keyed[h].second);
+        }
         for (const auto &kv : uniq) {
             adj.off[(uint32_t)(kv.first >> 32) + 1]++;
             adj.off[(uint32_t)kv.first + 1]++;
         }
         for (size_t g = 0; g < n; g++) adj.off[g + 1] += adj.off[g];
-        adj.nbr.resize(adj.off[n]); adj.ani.resize(adj.off[n]);
+        adj.nbr.resize(adj.off[n]); adj.ani.resize(adj.off[n]); adj.hit.resize(adj.off[n]);
         std::vector<uint64_t> fill(adj.off.begin(), adj.off.end() - 1);
+        // keys ascend, so every row receives its neighbours in ascending order: first the smaller
+        // partners (as the second genome of earlier keys), then the larger ones
         for (const auto &kv : uniq) {
             const uint32_t a = (uint32_t)(kv.first >> 32), b = (uint32_t)kv.first;
-            adj.nbr[fill[a]] = b; adj.ani[fill[a]++] = kv.second;
-            adj.nbr[fill[b]] = a; adj.ani[fill[b]++] = kv.second;
-        }
-        std::vector<std::pair<uint32_t, float>> tmp;
-        for (size_t g = 0; g < n; g++) {
-            tmp.clear();
-            for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++) tmp.emplace_back(adj.nbr[x], adj.ani[x]);
-            if (!std::is_sorted(tmp.begin(), tmp.end())) std::sort(tmp.begin(), tmp.end());
-            for (size_t x = 0; x < tmp.size(); x++) { adj.nbr[adj.off[g] + x] = tmp[x].first; adj.ani[adj.off[g] + x] = tmp[x].second; }
+            const float v = hits[kv.second].ani;
+            adj.nbr[fill[a]] = b; adj.ani[fill[a]] = v; adj.hit[fill[a]++] = kv.second;
+            adj.nbr[fill[b]] = a; adj.ani[fill[b]] = v; adj.hit[fill[b]++] = kv.second;
         }
     }
 
+    const double t1 = now();
     // ---- partition_sketches: single linkage
     Dsu dsu(n);
     for (size_t g = 0; g < n; g++)
@@ -151,6 +162,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         out.largest_precluster = set_size[order[0]];
     }
 
+    const double t2 = now();
     std::vector<uint8_t> is_rep(n, 0);
     std::vector<uint32_t> cluster_of_rep(n, 0);
     // clusterer cache (src/clusterer.rs:236-239, 398-405), one slot per adjacency edge: a pair is
@@ -160,12 +172,16 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     struct Cand { float pre; uint32_t j; uint64_t edge; };
     std::vector<Cand> cands;
 
-    std::vector<uint32_t> reps, assigned_rep;  // per precluster: representatives; (genome -> its cluster) of non-reps
+    // Two sweeps over the preclusters (they are independent of each other, so the order of the
+    // calculate_ani calls across preclusters is free): all representatives first, then all
+    // memberships -- between the two a table-driven caller learns which reverse-orientation values
+    // the membership sweep is going to ask for and can produce them in one batch.
+    std::vector<uint32_t> all_reps;               // representatives, precluster after precluster
+    std::vector<uint64_t> reps_off(1, 0);         // [n_preclusters + 1]
     std::vector<std::pair<uint32_t, uint32_t>> joins;  // (cluster index within the precluster, genome), genome ascending
     std::vector<uint64_t> cl_fill;
     for (size_t pc = 0; pc + 1 < pc_off.size(); pc++) {
         const uint32_t *mb = pc_members.data() + pc_off[pc], *me = pc_members.data() + pc_off[pc + 1];
-        reps.clear(); joins.clear();
         // ---- representatives
         for (const uint32_t *ip = mb; ip != me; ip++) {
             const uint32_t i = *ip;
@@ -180,7 +196,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                 float ani = c.pre;
                 bool some = true;
                 if (!skip_clusterer) {
-                    some = calculate_ani(c.j, i, &ani);
+                    some = by_hit ? (*by_hit)(c.j, i, adj.hit[c.edge], &ani) : calculate_ani_fn(c.j, i, &ani);
                     out.ani_calls++;
                     if (some) { edge_state[c.edge] = 1; edge_ani[c.edge] = ani; }
                 }
@@ -189,10 +205,29 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                     if (!skip_clusterer) break;  // find_any stops at the first hit
                 }
             }
-            if (rep) { is_rep[i] = 1; reps.push_back(i); }
+            if (rep) { is_rep[i] = 1; all_reps.push_back(i); }
         }
+        reps_off.push_back(all_reps.size());
+    }
+    if (prefetch_reverse && !skip_clusterer) {
+        // what the membership sweep will ask for with the representative BEHIND the genome
+        std::vector<size_t> want;
+        for (uint32_t i = 0; i < n; i++) {
+            if (is_rep[i]) continue;
+            for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++) {
+                const uint32_t r = adj.nbr[x];
+                if (r > i && is_rep[r] && !edge_state[x]) want.push_back(adj.hit[x]);
+            }
+        }
+        if (!want.empty() && (*prefetch_reverse)(want)) { err = "reverse-orientation ANI batch failed"; return 2; }
+    }
+    for (size_t pc = 0; pc + 1 < pc_off.size(); pc++) {
+        const uint32_t *mb = pc_members.data() + pc_off[pc], *me = pc_members.data() + pc_off[pc + 1];
+        const uint32_t *reps = all_reps.data() + reps_off[pc];
+        const size_t n_reps = reps_off[pc + 1] - reps_off[pc];
+        joins.clear();
         // ---- memberships
-        for (size_t c = 0; c < reps.size(); c++) cluster_of_rep[reps[c]] = (uint32_t)c;
+        for (size_t c = 0; c < n_reps; c++) cluster_of_rep[reps[c]] = (uint32_t)c;
         for (const uint32_t *ip = mb; ip != me; ip++) {
             const uint32_t i = *ip;
             if (is_rep[i]) continue;
@@ -209,7 +244,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                     if (edge_state[x]) v = OptAni{edge_state[x] == 1, edge_ani[x]};
                     else {
                         float ani = 0.f;
-                        const bool some = calculate_ani(r, i, &ani);
+                        const bool some = by_hit ? (*by_hit)(r, i, adj.hit[x], &ani) : calculate_ani_fn(r, i, &ani);
                         out.ani_calls++;
                         v = OptAni{some, ani};
                         edge_state[x] = some ? 1 : 2; edge_ani[x] = ani;
@@ -226,19 +261,20 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         }
         // clusters of this precluster in representative order: representative first, then its
         // members in ascending genome order (the order they were assigned in)
-        cl_fill.assign(reps.size() + 1, 0);
+        cl_fill.assign(n_reps + 1, 0);
         for (const auto &jn : joins) cl_fill[jn.first + 1]++;
         const uint64_t base = out.members.size();
-        for (size_t c = 0; c < reps.size(); c++) cl_fill[c + 1] += cl_fill[c] + 1;  // +1: the representative
-        out.members.resize(base + cl_fill[reps.size()]);
-        for (size_t c = 0; c < reps.size(); c++) {
+        for (size_t c = 0; c < n_reps; c++) cl_fill[c + 1] += cl_fill[c] + 1;  // +1: the representative
+        out.members.resize(base + cl_fill[n_reps]);
+        for (size_t c = 0; c < n_reps; c++) {
             const uint64_t at = base + (c ? cl_fill[c] : 0);
             out.members[at] = reps[c];
             out.offsets.push_back(base + cl_fill[c + 1]);
         }
-        for (size_t c = reps.size(); c-- > 0;) cl_fill[c + 1] = c ? cl_fill[c] + 1 : 1;  // next free slot after each representative
+        for (size_t c = n_reps; c-- > 0;) cl_fill[c + 1] = c ? cl_fill[c] + 1 : 1;  // next free slot after each representative
         for (const auto &jn : joins) out.members[base + cl_fill[jn.first + 1]++] = jn.second;
     }
+    if (dbg) fprintf(stderr, "[engine] adjacency %.2f ms, preclusters %.2f ms, greedy %.2f ms\n", t1 - t0, t2 - t1, now() - t2);
     return 0;
 }
 

@@ -17,6 +17,13 @@ struct PreclusterHit {
 // calculate_ani(fasta1 = candidate representative, fasta2 = genome under consideration)
 // -> true and *ani for Some(ani), false for None  (src/lib.rs:54).
 using AniFn = std::function<bool(uint32_t rep, uint32_t genome, float *ani)>;
+// The same for callers that hold their ANI values in tables parallel to `hits`: `hit` is the index
+// of the precluster hit the pair belongs to (the engine only ever asks about hit pairs), so the
+// value is one array read instead of a search per call.
+using AniByHitFn = std::function<bool(uint32_t rep, uint32_t genome, size_t hit, float *ani)>;
+// Called once, after every representative is known and before the membership sweep, with the hits
+// whose REVERSE orientation (query = the higher index) that sweep will ask for; non-zero aborts.
+using ReversePrefetchFn = std::function<int(const std::vector<size_t> &hits)>;
 
 struct ClusterResult {
     std::vector<uint32_t> members;   // concatenated clusters, representative first
@@ -28,6 +35,7 @@ struct ClusterResult {
 // Returns 0, or non-zero with `err` set (mirrors the reference's panics).
 int cluster_from_hits(size_t n_genomes, const PreclusterHit *hits, size_t n_hits, bool skip_clusterer,
                       float ani_threshold, const AniFn &calculate_ani, ClusterResult &out,
-                      std::string &err);
+                      std::string &err, const AniByHitFn *by_hit = nullptr,
+                      const ReversePrefetchFn *prefetch_reverse = nullptr);
 
 }  // namespace gb200
