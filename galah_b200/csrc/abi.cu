@@ -188,8 +188,22 @@ struct CandFinisher {
 static int finish_candidates(const uint4 *cand, size_t n_cand, int k, float min_ani, galah_b200_pair_t **out,
                              size_t *n_out) {
     CandFinisher fin(k, min_ani);
-    fin.reserve(n_cand);
-    for (size_t x = 0; x < n_cand; x++) fin.add(cand[x]);
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t nt = n_cand >= 32768 ? std::min<size_t>(hw, 16) : 1;
+    if (nt == 1) {
+        fin.reserve(n_cand);
+        for (size_t x = 0; x < n_cand; x++) fin.add(cand[x]);
+    } else {
+        // the f64 logarithm per candidate is the cost (13 ns each): large lists are split over the host threads
+        fin.c.resize(n_cand); fin.ani.resize(n_cand); fin.keep.resize(n_cand);
+        std::vector<std::thread> th;
+        const size_t per = (n_cand + nt - 1) / nt;
+        for (size_t t = 0; t < nt; t++) {
+            const size_t x0 = t * per, x1 = std::min(n_cand, x0 + per);
+            if (x0 < x1) th.emplace_back([&fin, cand, x0, x1] { for (size_t x = x0; x < x1; x++) fin.set(x, cand[x]); });
+        }
+        for (auto &t : th) t.join();
+    }
     return fin.finalize(out, n_out);
 }
 

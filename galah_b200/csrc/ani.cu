@@ -576,7 +576,27 @@ struct TmpBuf {
     }
 };
 
+// Grow-only pinned host buffer: device -> host copies into pageable memory are staged by the driver at
+// ~2 GB/s (2.4 ms for the 4 MB of accumulators of 148k pairs); pinned, the same copy takes 0.2 ms.
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    int alloc(size_t n) {
+        if (n <= cap) return 0;
+        if (p) GB_CUDA(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4 + 16;
+        GB_CUDA(cudaMallocHost(&p, want * sizeof(T)));
+        cap = want;
+        return 0;
+    }
+};
+
 struct AniScratch {
+    PinnedBuf<uint32_t> h_acc;
+    PinnedBuf<unsigned long long> h_fx;
     TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix, overflow;
     TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
     TmpBuf<unsigned long long> acc_fx, pair_table;
@@ -897,10 +917,11 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
     }
     GB_CUDA(cudaEventRecord(ev_[1], st));
     const double td2 = now();
-    std::vector<uint32_t> acc((size_t)kAccWords * n_pairs);
-    std::vector<unsigned long long> fx(n_pairs);
-    GB_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 4 * (size_t)kAccWords * n_pairs, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaMemcpyAsync(fx.data(), d_fx.p, 8 * n_pairs, cudaMemcpyDeviceToHost, st));
+    if (scratch_->h_acc.alloc((size_t)kAccWords * n_pairs) || scratch_->h_fx.alloc(n_pairs)) return 2;
+    const uint32_t *acc = scratch_->h_acc.p;
+    const unsigned long long *fx = scratch_->h_fx.p;
+    GB_CUDA(cudaMemcpyAsync(scratch_->h_acc.p, d_acc.p, 4 * (size_t)kAccWords * n_pairs, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(scratch_->h_fx.p, d_fx.p, 8 * n_pairs, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
@@ -920,7 +941,7 @@ int AniIndex::pairs(const uint32_t *pairs, size_t n_pairs, float min_af_pct, boo
         }
     };
     const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
-    const size_t nt = n_pairs >= 65536 ? std::min<size_t>(hw, 32) : 1;
+    const size_t nt = n_pairs >= 8192 ? std::min<size_t>(hw, 32) : 1;
     if (nt == 1) {
         finish_range(0, n_pairs);
     } else {
