@@ -493,6 +493,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if infos and isinstance(infos[-1].get("host_detail_ms"), dict):
+            line["host_detail_ms_rank0"] = infos[-1]["host_detail_ms"]  # multi-GPU: the host side of the ANI / engine phases
         line.update(sub)
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -638,8 +638,16 @@ int AniIndex::export_tables(cudaIpcMemHandle_t *handle, std::vector<uint64_t> &t
 
 int AniIndex::attach_peer(const cudaIpcMemHandle_t &handle, const uint64_t *table_off, const uint64_t *total_len,
                           size_t n, uint32_t *first_id) {
+    // Opening a mapping costs hundreds of milliseconds for a multi-GB array (measured: 750 ms per step
+    // on BASELINE configs[4]) and a peer re-uses its allocation from step to step: mappings are kept
+    // open, keyed by the handle, until this index is destroyed.
     void *base = nullptr;
-    GB_CUDA(cudaIpcOpenMemHandle(&base, handle, cudaIpcMemLazyEnablePeerAccess));
+    for (const auto &c : ipc_cache_)
+        if (memcmp(&c.first, &handle, sizeof(handle)) == 0) base = c.second;
+    if (!base) {
+        GB_CUDA(cudaIpcOpenMemHandle(&base, handle, cudaIpcMemLazyEnablePeerAccess));
+        ipc_cache_.emplace_back(handle, base);
+    }
     PeerGroup pg;
     pg.base = (const unsigned long long *)base;
     pg.table_off.assign(table_off, table_off + n + 1);
@@ -664,7 +672,6 @@ int AniIndex::attach_peer_direct(const unsigned long long *base, const uint64_t 
 }
 
 void AniIndex::clear() {
-    for (auto &pg : peers_) if (pg.ipc) cudaIpcCloseMemHandle((void *)pg.base);
     peers_.clear(); peer_first_.assign(1, 0); peer_total_len_.clear();
     seed_off_.assign(1, 0); cso_off_.assign(1, 0); table_off_.assign(1, 0);
     total_len_.clear(); n_chunks_.clear();
@@ -673,7 +680,7 @@ void AniIndex::clear() {
 }
 
 AniIndex::~AniIndex() {
-    for (auto &pg : peers_) if (pg.ipc) cudaIpcCloseMemHandle((void *)pg.base);
+    for (auto &c : ipc_cache_) cudaIpcCloseMemHandle(c.second);
     d_kq_.release(); d_cso_.release(); d_table_.release();
     d_seed_off_.release(); d_cso_off_.release(); d_table_off_.release(); d_n_chunks_.release();
     for (int x = 0; x < 2; x++) if (ev_[x]) cudaEventDestroy(ev_[x]);

@@ -117,6 +117,7 @@ private:
     // peer tables (attach_peer): group g covers peer ids [peer_first_[g], peer_first_[g + 1])
     struct PeerGroup { const unsigned long long *base; std::vector<uint64_t> table_off; bool ipc = true; };
     std::vector<PeerGroup> peers_;
+    std::vector<std::pair<cudaIpcMemHandle_t, void *>> ipc_cache_;  // open IPC mappings, kept across clear()
     std::vector<uint32_t> peer_first_{0};
     std::vector<uint64_t> peer_total_len_;
 };

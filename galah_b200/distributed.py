@@ -372,6 +372,8 @@ class ShardedPipeline:
         sp.h_cand[:got].copy_(sp.d_cand[:got])
         mine = gb.finish_candidates(sp.h_cand[:got].numpy().view(np.uint32), 21, min_ani)
         t2 = time.perf_counter()
+        tm = {}
+        tq = time.perf_counter()
         # ---- every rank learns all hits (20 B each) and takes those whose query genome it owns
         packed = np.zeros((len(mine), 5), np.uint32)
         for c, f in enumerate(("i", "j", "common", "total")):
@@ -381,6 +383,7 @@ class ShardedPipeline:
         allh = np.concatenate(parts) if parts else np.zeros((0, 5), np.uint32)
         order = np.argsort((allh[:, 0].astype(np.uint64) << np.uint64(32)) | allh[:, 1].astype(np.uint64), kind="stable")
         allh = allh[order]
+        tm["hits_gather_sort_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         # ---- stage-2 jobs: both orientations of every hit (calculate_ani(rep, genome) makes the
         # representative the query, and the membership pass asks for representatives on either side of
         # the genome); a job runs on the rank that owns its QUERY genome
@@ -389,18 +392,22 @@ class ShardedPipeline:
         owner = route_hits(q_all, n_local, world)
         my_jobs = np.nonzero(owner == rank)[0]
         # ---- peer tables: IPC handles + per-genome offsets are exchanged (host metadata, 16 B / genome)
+        tm["jobs_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         handle, table_off, total_len = idx.export_tables()
         metas = [None] * world
         dist.all_gather_object(metas, (handle, table_off, total_len))
+        tm["meta_exchange_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         r_owner = route_hits(r_all[my_jobs], n_local, world)
         base = np.zeros(world, np.int64)      # id of a rank's first genome in this index's numbering
         for peer in sorted(set(int(x) for x in r_owner) - {rank}):
             base[peer] = idx.attach_peer(*metas[peer])
+        tm["attach_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         q_local = q_all[my_jobs] - rank * n_local
         r_id = base[r_owner] + (r_all[my_jobs] - r_owner * n_local)
         pairs = np.stack([q_local, r_id], axis=1).astype(np.uint32)
         res = idx.pairs(pairs, min_af)
         chain_ms = idx.last_timing()[1]
+        tm["pairs_call_ms"] = 1e3 * (time.perf_counter() - tq)
         t3 = time.perf_counter()
         # ---- ANI values to rank 0 (job id + f32 bits), engine there
         back = np.zeros((len(my_jobs), 2), np.uint32)
@@ -409,6 +416,7 @@ class ShardedPipeline:
         got_back = self._allgather_var(back, np.uint32, 2)
         dist.barrier()          # every peer has finished reading this rank's tables
         idx.clear()             # detaches the peers; the allocations stay for the next step
+        tm["ani_gather_ms"] = 1e3 * (time.perf_counter() - t3); tq = time.perf_counter()
         clusters = None
         if rank == 0:
             ani = np.zeros(2 * len(allh), np.float32)
@@ -419,6 +427,8 @@ class ShardedPipeline:
             hits["ani"] = allh[:, 4].view(np.float32)
             clusters, cinfo = gb.cluster_from_ani_tables(n, hits, ani[: len(allh)], ani[len(allh):], ani_pct)
             info.update(cinfo)
+            tm["engine_call_ms"] = 1e3 * (time.perf_counter() - tq)
+        info["host_detail_ms"] = {k: round(v, 2) for k, v in tm.items()}
         t4 = time.perf_counter()
         info.update(n_precluster_hits=len(allh), n_ani_pairs=2 * len(allh), my_ani_pairs=len(my_jobs),
                     remote_reference_pairs=int(np.sum(r_owner != rank)), sketch_ms=k1_ms, index_ms=idx_ms,
@@ -457,20 +467,27 @@ class ShardedPipeline:
         sp.h_cand[:got].copy_(sp.d_cand[:got])
         mine = sp.h_cand[:got].numpy().view(np.uint32).copy()
         t2 = time.perf_counter()
+        tm = {}
+        tq = time.perf_counter()
         # every screened pair travels ONCE, to the rank that owns its query genome (the lower index)
         myc = self._route_var(mine, route_hits(mine[:, 0], n_local, world), np.uint32, 4)
+        tm["route_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         myc = myc[np.argsort((myc[:, 0].astype(np.uint64) << np.uint64(32)) | myc[:, 1].astype(np.uint64), kind="stable")]
+        tm["sort_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         handle, table_off, total_len = idx.export_tables()
         metas = [None] * world
         dist.all_gather_object(metas, (handle, table_off, total_len))
+        tm["meta_exchange_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         r_owner = route_hits(myc[:, 1], n_local, world)
         base = np.zeros(world, np.int64)
         for peer in sorted(set(int(x) for x in r_owner) - {rank}):
             base[peer] = idx.attach_peer(*metas[peer])
+        tm["attach_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
         q_local = myc[:, 0].astype(np.int64) - rank * n_local
         r_id = base[r_owner] + (myc[:, 1].astype(np.int64) - r_owner * n_local)
         res = idx.pairs(np.stack([q_local, r_id], axis=1).astype(np.uint32), min_af, individual_contigs=individual_contigs)
         chain_ms = idx.last_timing()[1]
+        tm["pairs_call_ms"] = 1e3 * (time.perf_counter() - tq)
         t3 = time.perf_counter()
         keep = res["ani"] >= np.float32(threshold_pct)  # `if ani >= threshold`, src/skani.rs:205
         back = np.zeros((int(keep.sum()), 5), np.uint32)
@@ -481,6 +498,7 @@ class ShardedPipeline:
         hits_all = self._route_var(back, np.zeros(len(back), np.int64), np.uint32, 5)  # the hits go to rank 0 only
         dist.barrier()
         idx.clear()
+        tm["hits_route_ms"] = 1e3 * (time.perf_counter() - t3); tq = time.perf_counter()
         clusters, info = None, {}
         if rank == 0:
             hits_all = hits_all[np.argsort((hits_all[:, 0].astype(np.uint64) << np.uint64(32)) | hits_all[:, 1].astype(np.uint64),
@@ -491,6 +509,8 @@ class ShardedPipeline:
             clusters, cinfo = gb.cluster_from_distances(n, hits, ani_pct, None, skip_clusterer=True)
             info.update(cinfo)
             info["n_hits"] = int(len(hits))
+            tm["engine_call_ms"] = 1e3 * (time.perf_counter() - tq)
+        info["host_detail_ms"] = {k: round(v, 2) for k, v in tm.items()}
         allc, my_rows = myc, np.arange(len(myc))
         t4 = time.perf_counter()
         info.update(n_screened=int(n_screened.item()), my_ani_pairs=int(len(my_rows)), remote_reference_pairs=int(np.sum(r_owner != rank)),

@@ -81,11 +81,12 @@ def main():
     if rank == 0:
         pairs = n * (n - 1) // 2
         t = float(np.mean(times))
-        keys = [k for k in infos[-1] if k.endswith("_ms")]
+        keys = [k for k in infos[-1] if k.endswith("_ms") and not isinstance(infos[-1][k], dict)]
         line = {"config": f"BASELINE.json configs[{args.config}]", "n_gpus": world, "units": n, "unit_bp": L, "pairs": pairs,
                 "seconds_per_pass": t, "pairs_per_s": pairs / t, "clusters": len(clusters),
                 "clusters_sha1": clusters.sha1(), "phases_ms_rank0": {k: float(np.median([i[k] for i in infos])) for k in keys},
                 "counts": {k: infos[-1][k] for k in infos[-1] if not k.endswith("_ms") and isinstance(infos[-1][k], (int, float))},
+                "host_detail_ms_rank0": infos[-1].get("host_detail_ms"),
                 "resident_gb_per_gpu": (d_seq.numel() + d_val.numel()) * 4 / 1e9}
         print(json.dumps(line), flush=True)
     dist.barrier()
