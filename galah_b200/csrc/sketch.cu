@@ -536,6 +536,23 @@ __device__ __forceinline__ uint64_t mm_hash64_v2(uint64_t key, uint64_t minus1) 
     key = mul64c<0x80000001ull>(key);
     return key;
 }
+// The same for a 30-bit key (the canonical 15-mer of a K3 seed), used ONLY for `hash < seed_thr`:
+// key * (2^21 - 1) - 1 is below 2^51 for key >= 1, so the first xor-shift (by 24) leaves the high
+// word alone -- two ALU-pipe instructions less.  key = 0 (poly-A) takes a different value this way
+// (0xa992.. instead of 0x77cf..), both far above any threshold 2^64 / c with c >= 3, so the selection
+// is the same (the host refuses a seed density above 1/3; checked against the full hash in
+// tests/test_sketch_gpu.py through the seed lists of the K3 index).
+__device__ __forceinline__ uint64_t mm_hash64_key30(uint32_t key30, uint64_t minus1) {
+    uint64_t key = mad64s<0x1FFFFFu>((uint64_t)key30, minus1);
+    const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+    key = pack64(lo ^ __funnelshift_r(lo, hi, 24), hi);
+    key = mad64s<265u>(key, 0ull);
+    key ^= key >> 14;
+    key = mad64s<21u>(key, 0ull);
+    key ^= key >> 28;
+    key = mul64c<0x80000001ull>(key);
+    return key;
+}
 // the 96 validity bits ANDed with themselves shifted right by s
 __device__ __forceinline__ void and_shr96(uint32_t &x0, uint32_t &x1, uint32_t &x2, int s) {
     const uint32_t y0 = __funnelshift_r(x0, x1, s), y1 = __funnelshift_r(x1, x2, s), y2 = x2 >> s;
@@ -677,7 +694,7 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
             bit <<= 1;
             if (SEEDS && (sv16 & cur)) {
                 const uint32_t F15 = Fhi >> 2, R15 = __funnelshift_r(Rlo, Rhi, 22) & 0x3FFFFFFFu;
-                const uint64_t hs = mm_hash64_v2((uint64_t)min(F15, R15), minus1);
+                const uint64_t hs = mm_hash64_key30(min(F15, R15), minus1);
                 const uint32_t pick = cur & neg_borrow64((uint32_t)hs, (uint32_t)(hs >> 32), (uint32_t)p.seed_thr,
                                                          (uint32_t)(p.seed_thr >> 32));
                 if (wi < 2) sel0 |= pick; else sel1 |= pick;
@@ -821,6 +838,7 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
                    const SeedSink *seeds, const uint64_t *host_span) {
     if (k < 1 || k > 32) { set_error("sketch: k must be in 1..32"); return 3; }
     if (seeds && k != 21) { set_error("sketch: fused seed marking needs k = 21"); return 3; }
+    if (seeds && seeds->thr > ~0ull / 3) { set_error("sketch: seed density above 1/3 is not supported by the fused marking"); return 3; }
     if (s == 0) { set_error("sketch: s must be > 0"); return 3; }
     if (out_stride < s) { set_error("sketch: out_stride < s"); return 3; }
     if (n >= 0x7FFFFFFFull) { set_error("sketch: too many genomes in one batch"); return 3; }
@@ -916,6 +934,7 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
                           const uint64_t *host_span) {
     if (k < 1 || k > 32) { set_error("marker sketch: k must be in 1..32"); return 3; }
     if (seeds && k != 21) { set_error("marker sketch: fused seed marking needs k = 21"); return 3; }
+    if (seeds && seeds->thr > ~0ull / 3) { set_error("marker sketch: seed density above 1/3 is not supported by the fused marking"); return 3; }
     if (cap < 256 || (cap & (cap - 1)) || cap > kMarkerMaxCap) { set_error("marker sketch: bad capacity"); return 3; }
     const uint32_t n_parts = cap > kMarkerPartCap ? cap / kMarkerPartCap : 1u;  // value-range partitions of a wide row
     const uint32_t part_cap = cap > kMarkerPartCap ? kMarkerPartCap : cap;
