@@ -415,21 +415,25 @@ def main():
                         "units_per_step": units, "unit": unit, "algorithmic_bytes_per_unit": bytes_per_unit,
                         "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak, "bound": bound, "note": note})
         add("K1 sketch", ["scan21v2_kernel", "sketch_select_kernel"], phase.get("sketch_ms"), n_local, "genome",
-            L / 4 + L / 8 + 8 * S, "ALU pipe (LOP3 / SHF / PRMT / SEL at 0.5 warp-instructions per clock and sub-partition, "
-            "profiles/r2_pipe_rates_b200.txt); HBM fraction reported as asked, see instruction_roofline",
+            L / 4 + L / 8 + 8 * S, "integer issue slots: ALU and FMA pipes level (profiles/r2_pipe_rates_b200.txt); "
+            "HBM fraction reported as asked, see instruction_roofline",
             "L/4 packed + L/8 validity read, 8 s written per genome; the time is taken while the K3 index kernels of the "
             "previous batch share the SMs (two streams), so K1 + K3 index > ingest")
         if fam and fam[-1]["family"] == "K1 sketch" and clocks and clocks.get("sm_mhz"):
-            # what bounds the kernel: ALU-pipe instructions per k-mer position (counted in the SASS of the hot path)
-            alu_per_kmer, sms, subparts = 88.0, 148, 4
-            peak_kmers = sms * subparts * 0.5 * 32 * clocks["sm_mhz"] * 1e6 / alu_per_kmer
+            # what bounds the kernel: issue slots per k-mer position, counted in the SASS of the hot path of
+            # scan21v2_kernel<0,1,1> (tools: cuobjdump -sass): 63 ALU-pipe (LOP3 / SHF / PRMT / SEL / ISETP, 0.5 per clock
+            # and sub-partition), 46 IMAD + 16 IMAD.WIDE (0.5 / 0.25 per clock: 78 FMA-pipe slots), 12 IADD3, 10 other
+            # = 147 instructions = 163 issue clocks (a wide multiply holds its pipe for two slots); the two pipes are level
+            issue_clocks_per_kmer, sms, subparts = 163.0, 148, 4
+            peak_kmers = sms * subparts * 32 * clocks["sm_mhz"] * 1e6 / issue_clocks_per_kmer
             got_kmers = n_local * float(L) / (fam[-1]["ms_per_step"] * 1e-3)
             fam[-1]["instruction_roofline"] = {
-                "bound": "ALU pipe", "alu_pipe_instructions_per_kmer": alu_per_kmer, "fma_pipe_instructions_per_kmer": 52.0,
-                "all_instructions_per_kmer": 152.0, "peak_kmers_per_s": peak_kmers, "achieved_kmers_per_s": got_kmers,
-                "frac": got_kmers / peak_kmers,
-                "source": "SASS count of scan21v2_kernel<0,1,1>'s loop + measured pipe rates (tools/pipe_bench.cu); ncu: "
-                          "sm__inst_executed_pipe_alu 78 % (profiles/r2_ncu_full_k1_scan21v2.txt)"}
+                "bound": "issue slots (FMA pipe 156 clocks, ALU pipe 126 clocks, issue 163 clocks per warp and k-mer position)",
+                "alu_pipe_instructions_per_kmer": 63, "imad_per_kmer": 46, "imad_wide_per_kmer": 16, "iadd3_per_kmer": 12,
+                "all_instructions_per_kmer": 147, "issue_clocks_per_kmer": issue_clocks_per_kmer,
+                "peak_kmers_per_s": peak_kmers, "achieved_kmers_per_s": got_kmers, "frac": got_kmers / peak_kmers,
+                "source": "SASS count of the loop + measured pipe rates (tools/pipe_bench.cu, profiles/r2_pipe_rates_b200.txt); "
+                          "the time also holds the K3 index kernels of the previous batch, which share the SMs"}
         add("K3 index", ["ani_count_kernel", "ani_emit_kernel"], phase.get("index_ms"), n_local, "genome",
             L / 4 + L / 8 + seeds_per_genome * (8 + 16), "integer ALU (mm_hash64 per k-mer) + scattered table inserts",
             "packed read + 8 B seed + 2 x 8 B table slots per seed written")
