@@ -104,10 +104,11 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         for (size_t h = 1; h < n_hits && sorted; h++)
             sorted = pair_key(hits[h - 1].i, hits[h - 1].j) < pair_key(hits[h].i, hits[h].j);
         std::vector<std::pair<uint64_t, uint32_t>> uniq;  // (key, index of the last hit with that key)
-        uniq.reserve(n_hits);
         if (sorted) {
-            for (size_t h = 0; h < n_hits; h++) uniq.emplace_back(pair_key(hits[h].i, hits[h].j), (uint32_t)h);
+            uniq.resize(n_hits);
+            for (size_t h = 0; h < n_hits; h++) uniq[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
         } else {
+            uniq.reserve(n_hits);
             std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
             for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
             std::stable_sort(keyed.begin(), keyed.end(),
@@ -151,9 +152,16 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
             set_id[g] = (uint32_t)set_of_root[r];
             set_size[set_id[g]]++;
         }
+        // sets by size, largest first, ties in set order: a counting sort on the size (stable), O(sets + largest)
         std::vector<uint32_t> order(set_size.size());
-        std::iota(order.begin(), order.end(), 0u);
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return set_size[a] > set_size[b]; });
+        {
+            uint32_t largest = 0;
+            for (const uint32_t z : set_size) largest = std::max(largest, z);
+            std::vector<uint64_t> at((size_t)largest + 2, 0);  // at[z] = first slot of size z, sizes descending
+            for (const uint32_t z : set_size) at[largest - z + 1]++;
+            for (size_t z = 0; z + 1 < at.size(); z++) at[z + 1] += at[z];
+            for (uint32_t sid = 0; sid < set_size.size(); sid++) order[at[largest - set_size[sid]]++] = sid;
+        }
         std::vector<uint64_t> start(set_size.size());
         pc_off.assign(1, 0);
         for (const uint32_t sid : order) { start[sid] = pc_off.back(); pc_off.push_back(pc_off.back() + set_size[sid]); }
