@@ -178,6 +178,10 @@ _SIGNATURES = {
                                                                 ctypes.c_float, ctypes.c_int, ctypes.c_int, vp,
                                                                 ctypes.POINTER(ctypes.POINTER(Pair)), sizep,
                                                                 ctypes.POINTER(ctypes.c_uint64), f32p]),
+    "galah_b200_skani_distances_packed_multi": (ctypes.c_int, [vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
+                                                               ctypes.c_float, ctypes.c_int, ctypes.c_int,
+                                                               ctypes.POINTER(ctypes.POINTER(Pair)), sizep,
+                                                               ctypes.POINTER(ctypes.c_uint64)]),
     "galah_b200_cluster_files_skani": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                       ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),

@@ -607,6 +607,22 @@ def skani_distances_packed_device(d_seq2, d_valid, d_base_off, base_off, lengths
     return _take_pairs(out, n_out), info
 
 
+def skani_distances_packed_multi(seq2, valid, base_off, lengths, n_devices, threshold=95.0, min_aligned_fraction=15.0,
+                                 small_genomes=False, individual_contigs=True):
+    """SkaniPreclusterer on packed units in HOST arrays over n_devices GPUs of this process
+    (init_devices first).  Returns (PAIR_DTYPE hits, {"n_screened": ...}), identical to the single-GPU call."""
+    base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+    out = ctypes.POINTER(Pair)()
+    n_out = ctypes.c_size_t(0)
+    scr = ctypes.c_uint64(0)
+    ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+    check(lib().galah_b200_skani_distances_packed_multi(
+        ptr(seq2), ptr(valid), base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p), len(lengths),
+        int(n_devices), ctypes.c_float(threshold), ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+        int(bool(individual_contigs)), ctypes.byref(out), ctypes.byref(n_out), ctypes.byref(scr)))
+    return _take_pairs(out, n_out), {"n_screened": int(scr.value)}
+
+
 def device_ingest(enable=-1):
     """K0 switch: decode FASTA bytes on the device (1, default) or pack on host threads (0);
     < 0 only queries.  Returns the previous setting."""

@@ -1955,6 +1955,179 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
     return 0;
 }
 
+// SkaniPreclusterer::distances / ::distances_contigs (src/skani.rs:21-56, 109-225, 379-498) on packed
+// units in HOST arrays over G devices of this process: the structure of cluster_multi with marker
+// sketches in place of MinHash sketches, the containment screen in place of the finch rule, and
+// every screened pair (i < j) evaluated ONCE, with i as the query, on the device that owns i.
+int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                                            const uint64_t *lengths, size_t n, int n_devices, float threshold_pct,
+                                            float min_af_pct, int small_genomes, int individual_contigs,
+                                            galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened) {
+    if (!out || !n_out) { set_error("skani_distances_packed_multi: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    if (n_screened) *n_screened = 0;
+    if (threshold_pct < 85.0f) {
+        set_error("Error: skani produces inaccurate results with ANI less than 85%. Provided: " + display_f32(threshold_pct));
+        return GALAH_B200_ERR_UNSUPPORTED;
+    }
+    const int G = n_devices;
+    if (G < 1 || G > kMaxDevices) { set_error("skani_distances_packed_multi: bad device count"); return GALAH_B200_ERR_ARG; }
+    for (int d = 0; d < G; d++)
+        if (g_ctxs[d].device != d) { set_error("skani_distances_packed_multi: call galah_b200_init_devices(n_devices) first"); return GALAH_B200_ERR_NO_DEVICE; }
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("packed units: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
+    uint64_t longest = 0;
+    for (size_t g = 0; g < n; g++) longest = std::max(longest, lengths[g]);
+    const uint32_t c_marker = small_genomes ? 200u : 1000u;
+    const uint32_t cap = marker_row_capacity(longest, c_marker);
+    size_t per = (n + (size_t)G - 1) / (size_t)G;
+    per = (per + GALAH_B200_ROW_BLOCK - 1) / GALAH_B200_ROW_BLOCK * GALAH_B200_ROW_BLOCK;
+    std::vector<size_t> g0((size_t)G + 1);
+    for (int r = 0; r <= G; r++) g0[r] = std::min(n, (size_t)r * per);
+    auto owner = [&](uint32_t g) { return (int)std::min<size_t>((size_t)g / per, (size_t)G - 1); };
+
+    MultiBarrier bar(G);
+    std::vector<int> rcs((size_t)G, 0);
+    std::vector<std::string> errs((size_t)G);
+    std::atomic<int> failed{0};
+    std::vector<std::vector<uint4>> inbox((size_t)G);
+    std::vector<std::mutex> inbox_mu((size_t)G);
+    std::vector<std::vector<galah_b200_pair_t>> rank_hits((size_t)G);
+    std::atomic<uint64_t> screened{0};
+
+    auto worker = [&](int r) {
+        t_dev = r;
+        std::lock_guard<std::mutex> lock(g_mus[r]);
+        Context &C = g_ctxs[r];
+        auto fail = [&](int rc) { if (!rcs[r]) { rcs[r] = rc; errs[r] = galah_b200_last_error(); failed.store(1); } };
+        int rc = require_ctx();
+        if (rc) fail(rc);
+        cudaStream_t st = C.stream;
+        const size_t nr = g0[r + 1] - g0[r];
+        AniIndex *index = nullptr;
+        if (!rc) {
+            index = &C.pipeline_index(small_genomes != 0);
+            if (ws_ensure(C.d_table, C.cap_table, std::max<size_t>(n, 1) * cap) ||
+                ws_ensure(C.d_counts, C.cap_counts, std::max<size_t>(n, 1)))
+                fail(GALAH_B200_ERR_CUDA);
+        }
+        if (!rcs[r] && nr) {
+            rc = ingest_packed(seq2, valid, nullptr, base_off + g0[r], lengths + g0[r], nr, false, C.d_table + g0[r] * (size_t)cap,
+                               C.d_counts + g0[r], *index, nullptr, nullptr, c_marker, cap);
+            if (rc) fail(rc);
+        }
+        if (!rcs[r]) {
+            std::vector<uint32_t> cnt(nr);
+            if ((nr && cudaMemcpyAsync(cnt.data(), C.d_counts + g0[r], nr * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
+                cudaStreamSynchronize(st) != cudaSuccess) {
+                set_error("skani_distances_packed_multi: reading the marker counts failed"); fail(GALAH_B200_ERR_CUDA);
+            }
+            for (size_t x = 0; x < nr && !rcs[r]; x++)
+                if (cnt[x] == 0xFFFFFFFFu) {
+                    set_error("marker sketch: a unit holds more markers than its row of " + std::to_string(cap) + "; unsupported");
+                    fail(GALAH_B200_ERR_UNSUPPORTED);
+                }
+        }
+        bar.wait();  // ---- every slice of the marker table exists on its owner
+        if (!failed.load() && n >= 2) {
+            for (int p = 0; p < G && !rcs[r]; p++) {
+                const size_t np = g0[p + 1] - g0[p];
+                if (p == r || np == 0) continue;
+                if (cudaMemcpyPeerAsync(C.d_table + g0[p] * (size_t)cap, r, g_ctxs[p].d_table + g0[p] * (size_t)cap, p,
+                                        np * (size_t)cap * 8, st) != cudaSuccess ||
+                    cudaMemcpyPeerAsync(C.d_counts + g0[p], r, g_ctxs[p].d_counts + g0[p], p, np * 4, st) != cudaSuccess) {
+                    set_error("skani_distances_packed_multi: peer copy of the marker rows failed");
+                    fail(GALAH_B200_ERR_CUDA);
+                }
+            }
+            // the containment screen on this device's row-block shard (skani_screen_and_ani, sharded)
+            std::vector<uint4> cand;
+            if (!rcs[r]) {
+                if (!C.d_n_cand && cudaMalloc(&C.d_n_cand, sizeof(unsigned long long)) != cudaSuccess) fail(GALAH_B200_ERR_CUDA);
+                const double frac = pow(0.80, 21.0);
+                size_t want = std::max<size_t>(1 << 16, 64 * n / (size_t)G);
+                while (!rcs[r]) {
+                    if (ws_ensure(C.d_cand, C.cap_cand, want)) { fail(GALAH_B200_ERR_CUDA); break; }
+                    rc = prefilter_enqueue(C.pws, C.d_table, C.d_counts, n, cap, 21, 0.f, (uint32_t)r, (uint32_t)G,
+                                           join_supported(cap) ? 0 : 1, st, C.d_cand, C.cap_cand, C.d_n_cand,
+                                           index->c() == 30u ? kRuleContainment : kRuleContainmentBypassSmall, frac);
+                    if (rc) { fail(rc); break; }
+                    unsigned long long got = 0;
+                    if (cudaMemcpyAsync(&got, C.d_n_cand, sizeof(got), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                        cudaStreamSynchronize(st) != cudaSuccess) { set_error("screen: count read failed"); fail(GALAH_B200_ERR_CUDA); break; }
+                    if (got > C.cap_cand) { want = (size_t)got; continue; }
+                    cand.resize((size_t)got);
+                    if (got && (cudaMemcpyAsync(cand.data(), C.d_cand, (size_t)got * sizeof(uint4), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                                cudaStreamSynchronize(st) != cudaSuccess)) { set_error("screen: candidate read failed"); fail(GALAH_B200_ERR_CUDA); }
+                    break;
+                }
+            }
+            // every screened pair travels once, to the device that owns its query (the lower index)
+            if (!rcs[r]) {
+                std::vector<std::vector<uint4>> outbox((size_t)G);
+                for (const uint4 &c : cand) outbox[owner(c.x)].push_back(c);
+                for (int p = 0; p < G; p++) {
+                    if (outbox[p].empty()) continue;
+                    std::lock_guard<std::mutex> lk(inbox_mu[p]);
+                    inbox[p].insert(inbox[p].end(), outbox[p].begin(), outbox[p].end());
+                }
+            }
+        }
+        bar.wait();  // ---- every device holds the screened pairs whose query it owns
+        if (!failed.load() && nr) {
+            std::vector<uint4> &mine = inbox[r];
+            std::sort(mine.begin(), mine.end(), [](const uint4 &a, const uint4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+            screened.fetch_add(mine.size());
+            std::vector<uint32_t> pairs(2 * mine.size());
+            std::vector<int64_t> peer_first((size_t)G, -1);
+            for (size_t x = 0; x < mine.size() && !rcs[r]; x++) {
+                const int pr = owner(mine[x].y);
+                uint32_t ref_id;
+                if (pr == r) ref_id = mine[x].y - (uint32_t)g0[r];
+                else {
+                    if (peer_first[pr] < 0) {
+                        const AniIndex *pi = g_ctxs[pr].pipe_index[small_genomes ? 1 : 0];
+                        uint32_t first = 0;
+                        rc = index->attach_peer_direct(pi->table_base(), pi->table_offsets().data(), pi->total_lengths().data(),
+                                                       pi->size(), &first);
+                        if (rc) { fail(rc); break; }
+                        peer_first[pr] = first;
+                    }
+                    ref_id = (uint32_t)peer_first[pr] + (mine[x].y - (uint32_t)g0[pr]);
+                }
+                pairs[2 * x] = mine[x].x - (uint32_t)g0[r]; pairs[2 * x + 1] = ref_id;
+            }
+            if (!rcs[r] && !mine.empty()) {
+                std::vector<AniPairResult> res(mine.size());
+                rc = index->pairs(pairs.data(), mine.size(), min_af_pct, individual_contigs != 0, res.data(), st);
+                if (rc) fail(rc);
+                else
+                    for (size_t x = 0; x < mine.size(); x++)
+                        if (res[x].ani >= threshold_pct)  // `if ani >= threshold` in f32, src/skani.rs:205
+                            rank_hits[r].push_back(galah_b200_pair_t{mine[x].x, mine[x].y, mine[x].z, mine[x].w, res[x].ani});
+            }
+        }
+        bar.wait();  // ---- nobody reads a peer's index any more
+        if (index) index->clear();
+        t_dev = -1;
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; r++) th.emplace_back(worker, r);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < G; r++)
+        if (rcs[r]) { set_error("device " + std::to_string(r) + ": " + errs[r]); return rcs[r]; }
+    // the devices own ascending slices of the query index: their lists concatenate into (i, j) order
+    size_t total = 0;
+    for (auto &v : rank_hits) total += v.size();
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(total, 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    size_t at = 0;
+    for (auto &v : rank_hits) { if (!v.empty()) memcpy(res + at, v.data(), v.size() * sizeof(galah_b200_pair_t)); at += v.size(); }
+    *out = res; *n_out = total;
+    if (n_screened) *n_screened = screened.load();
+    return 0;
+}
+
 int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct, float ani_threshold_pct,
                                    float min_af_pct, int small_genomes, int cluster_contigs, int host_threads,
                                    galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {

@@ -427,6 +427,16 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
                                              float min_af_pct, int small_genomes, int individual_contigs,
                                              void *stream, galah_b200_pair_t **out, size_t *n_out,
                                              uint64_t *n_screened, float *ms5);
+/* The same on HOST arrays over several GPUs of this process (galah_b200_init_devices first): unit
+ * slices for the marker sketches and the K3 index, marker rows exchanged by peer copies, row-block
+ * shards of the containment screen, every screened pair (i < j) evaluated once -- i is the query,
+ * as in `skani triangle` (src/skani.rs:109-225) -- on the device that owns unit i, which reads
+ * unit j's table in place on its peer.  Hits in (i, j) order, identical to the single-GPU call's;
+ * cluster them with galah_b200_cluster_from_distances(skip_clusterer = 1): BASELINE.json configs[4]. */
+int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                                            const uint64_t *lengths, size_t n, int n_devices, float threshold_pct,
+                                            float min_af_pct, int small_genomes, int individual_contigs,
+                                            galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened);
 int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct,
                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
                                    int cluster_contigs, int host_threads, galah_b200_clusters_t *out,

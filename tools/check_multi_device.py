@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--passes", type=int, default=2)
     ap.add_argument("--skip-single", action="store_true")
     ap.add_argument("--json", default=None)
+    ap.add_argument("--contigs", type=int, default=20480, help="units of the skani-preclusterer check (0 = skip)")
+    ap.add_argument("--contig-len", type=int, default=50_000)
     args = ap.parse_args()
     import torch
     import galah_b200 as gb
@@ -99,6 +101,47 @@ def main():
         out["files"] = {"genomes": len(paths), "clusters": len(one), "identical_to_single_gpu": bool(one == many),
                         "multi_phases_ms": {k: round(float(v), 2) for k, v in finfo.items() if k.endswith("_ms")}}
         ok = ok and (one == many)
+    # ---- the skani preclusterer (contig mode) on the same buffers read as contigs of --contig-len bases
+    if args.contigs:
+        nc, Lc = args.contigs, args.contig_len
+        layc = gb.synth_layout(nc, Lc)
+        hc_seq = torch.empty(layc["seq2_words"], dtype=torch.int32, pin_memory=True)
+        hc_val = torch.empty(layc["valid_words"], dtype=torch.int32, pin_memory=True)
+        gb.init(0)
+        dc_seq = torch.zeros(layc["seq2_words"], dtype=torch.int32, device=dev)
+        dc_val = torch.zeros(layc["valid_words"], dtype=torch.int32, device=dev)
+        dc_off = torch.zeros(nc + 1, dtype=torch.int64, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        for c0 in range(0, nc, 1 << 16):
+            m = min(1 << 16, nc - c0)
+            gb.synth_packed_device(1, c0, m, Lc, dc_seq[c0 * layc["padded"] // 16:].data_ptr(),
+                                   dc_val[c0 * layc["padded"] // 32:].data_ptr(), dc_off[c0:].data_ptr(), st)
+        torch.cuda.synchronize()
+        c_off = np.arange(nc + 1, dtype=np.uint64) * np.uint64(layc["padded"])
+        dc_off.copy_(torch.from_numpy(c_off.view(np.int64)))
+        hc_seq.copy_(dc_seq); hc_val.copy_(dc_val)
+        torch.cuda.synchronize()
+        c_len = np.full(nc, Lc, np.uint64)
+        t0 = time.perf_counter()
+        h1, i1 = gb.skani_distances_packed_device(dc_seq.data_ptr(), dc_val.data_ptr(), dc_off.data_ptr(), c_off, c_len, 95.0, 15.0,
+                                                  small_genomes=True, stream=st)
+        t_one = time.perf_counter() - t0
+        del dc_seq, dc_val
+        torch.cuda.empty_cache()
+        gb.init_devices(G)
+        for _ in range(args.passes):
+            t0 = time.perf_counter()
+            hm, im = gb.skani_distances_packed_multi(hc_seq.data_ptr(), hc_val.data_ptr(), c_off, c_len, G, 95.0, 15.0, small_genomes=True)
+            t_many = time.perf_counter() - t0
+        same = len(h1) == len(hm) and bool(np.all(h1 == hm))
+        t0 = time.perf_counter()
+        ccl, _ = gb.cluster_from_distances(nc, hm, 95.0, None, skip_clusterer=True)
+        t_engine = time.perf_counter() - t0
+        out["contigs"] = {"units": nc, "unit_bp": Lc, "pairs": nc * (nc - 1) // 2, "hits": int(len(hm)), "n_screened": im["n_screened"],
+                          "single_gpu_resident_s": t_one, "multi_host_buffers_s": t_many, "engine_s": t_engine,
+                          "clusters": len(ccl), "clusters_sha1": ccl.sha1(), "identical_to_single_gpu": same,
+                          "pairs_per_s": (nc * (nc - 1) // 2) / (t_many + t_engine)}
+        ok = ok and same
     print(json.dumps(out), flush=True)
     if args.json:
         with open(args.json, "w") as f:
