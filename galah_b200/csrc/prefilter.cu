@@ -374,10 +374,12 @@ int prefilter_prepare(PrefilterWorkspace &ws, const uint64_t *d_hashes, const ui
                                 cudaMemcpyHostToDevice, stream));
         ws.th_s = (uint32_t)stride; ws.th_k = k; ws.th_min_ani = min_ani; ws.th_valid = true;
         ws.th_rule = rule; ws.th_param = rule_param;
+        ws.th_zero_from = th.zero_fails_from();
     }
     p = KernelParams{};
     p.hashes = d_hashes; p.counts = d_counts; p.n = (uint32_t)n; p.stride = (uint32_t)stride;
     p.cmin_by_tmin = ws.d_cmin_by_tmin; p.cmin_by_total = ws.d_cmin_by_total;
+    p.zero_fails_from = ws.th_zero_from;
     p.cand = d_cand; p.cand_cap = cand_cap; p.n_cand = d_n_cand;
     ws.ev_recorded = false;
     if (ws.record(0, stream)) return 2;

@@ -17,6 +17,13 @@ double mash_ani_f64(uint64_t common, uint64_t total, int k);
 // Conservative integer thresholds derived from min_ani (see prefilter.cu).
 struct PrefilterThresholds {
     std::vector<uint32_t> cmin_by_tmin;   // [s_max + 1]
+    // smallest m0 such that cmin_by_tmin[m] >= 1 for every m >= m0: a pair of sketches with at least m0
+    // hashes each and NO common hash cannot pass (lets the join skip the zero counters of a block pair)
+    uint32_t zero_fails_from() const {
+        uint32_t m0 = (uint32_t)cmin_by_tmin.size();
+        while (m0 > 0 && cmin_by_tmin[m0 - 1] >= 1u) m0--;
+        return m0;
+    }
     std::vector<uint32_t> cmin_by_total;  // [2 * s_max + 1]
 };
 PrefilterThresholds make_thresholds(uint32_t s_max, int k, float min_ani);
@@ -49,6 +56,7 @@ struct PrefilterWorkspace {
     size_t cap_tmin = 0, cap_total = 0;
     uint32_t th_s = 0; int th_k = 0; float th_min_ani = -1.f; bool th_valid = false;
     int th_rule = 0; double th_param = 0.0;
+    uint32_t th_zero_from = 0;
     // work list of the current launch: local row blocks + item prefix + atomic work counter
     uint32_t *d_local_rb = nullptr;
     uint64_t *d_item_prefix = nullptr;
@@ -100,6 +108,7 @@ struct KernelParams {
     unsigned long long *work_counter;
     const uint32_t *cmin_by_tmin;
     const uint32_t *cmin_by_total;
+    uint32_t zero_fails_from;     // see PrefilterThresholds::zero_fails_from
     uint4 *cand;
     unsigned long long cand_cap;
     unsigned long long *n_cand;

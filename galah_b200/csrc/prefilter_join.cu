@@ -708,6 +708,9 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         B.tag = p.bl_tags + (uint64_t)cb * p.bl_cap; B.len = p.bl_len[cb];
         const uint32_t la = A.len, lb = B.len;
         __syncthreads();
+        // every sketch of both blocks is long enough that a pair without a common hash cannot pass:
+        // the threshold pass may then skip the zero counters word by word (almost all of them)
+        const bool skip_zero = __syncthreads_and(tid >= kJR || (S.na[tid] >= p.zero_fails_from && S.nb[tid] >= p.zero_fails_from)) != 0;
 
         if (rb == cb) {
             // ---- diagonal item: equal values are adjacent in the single list (ordered by tag
@@ -830,6 +833,21 @@ __global__ void __launch_bounds__(kJThreads, kJCtasPerSm) prefilter_join_kernel(
         __syncthreads();
 
         // ---- threshold the count matrix; survivors get their exact `total` and are appended
+        if (skip_zero && rb != cb) {
+            for (uint32_t w = tid; w < kJR * kJR / 2; w += kJThreads) {
+                const uint32_t word = S.cnt[w];
+                if (word == 0u) continue;
+#pragma unroll
+                for (uint32_t h = 0; h < 2; h++) {
+                    const uint32_t common = (word >> (16u * h)) & 0xFFFFu;
+                    if (common == 0u) continue;
+                    const uint32_t e = 2u * w + h, r = e / kJR, c = e % kJR;
+                    const uint32_t gi = row0 + r, gj = col0 + c;
+                    if (gi >= p.n || gj >= p.n) continue;
+                    finish_pair(p, gi, gj, p.hashes + (size_t)gi * p.stride, S.na[r], p.hashes + (size_t)gj * p.stride, S.nb[c], common);
+                }
+            }
+        } else
         for (uint32_t e = tid; e < kJR * kJR; e += kJThreads) {
             const uint32_t r = e / kJR, c = e % kJR;
             const uint32_t gi = row0 + r, gj = col0 + c;
