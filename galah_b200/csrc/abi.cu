@@ -63,6 +63,7 @@ struct Context {
     size_t cap_slot_seq2[2] = {0, 0}, cap_slot_valid[2] = {0, 0}, cap_slot_off[2] = {0, 0};
     uint32_t *d_sel = nullptr; size_t cap_sel = 0;  // K3 seed selection bits made by the fused k = 21 scan
     uint32_t *d_sel2 = nullptr; size_t cap_sel2 = 0;  // second buffer: batch b + 1 is scanned while batch b is indexed
+    uint32_t *d_seedcnt[2] = {nullptr, nullptr}; size_t cap_seedcnt[2] = {0, 0};  // seeds per genome, counted by the scan
     cudaStream_t scan_stream = nullptr;  // ingest_packed: K1 scans of the next batch run beside the K3 index build
     cudaEvent_t ev_scan[2] = {nullptr, nullptr};
     AniIndex *pipe_index[2] = {nullptr, nullptr};  // K3 index of the one-call pipelines (c = 125 / 30), re-used across calls
@@ -76,6 +77,7 @@ struct Context {
         for (auto &p : pipe_index) { delete p; p = nullptr; }
         cudaFree(d_sel); d_sel = nullptr; cap_sel = 0;
         cudaFree(d_sel2); d_sel2 = nullptr; cap_sel2 = 0;
+        for (int x = 0; x < 2; x++) { cudaFree(d_seedcnt[x]); d_seedcnt[x] = nullptr; cap_seedcnt[x] = 0; }
         if (scan_stream) cudaStreamDestroy(scan_stream);
         scan_stream = nullptr;
         for (auto &e : ev_scan) { if (e) cudaEventDestroy(e); e = nullptr; }
@@ -1510,7 +1512,8 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         uint32_t *&d_sel = (b & 1) ? g_ctx.d_sel2 : g_ctx.d_sel;
         size_t &cap_sel = (b & 1) ? g_ctx.cap_sel2 : g_ctx.cap_sel;
         if (ws_ensure(d_sel, cap_sel, (size_t)((B.bo.back() - B.bo.front()) / 32 + 2))) return GALAH_B200_ERR_CUDA;
-        B.sink = SeedSink{d_sel, B.bo.front(), index.seed_threshold()};
+        if (ws_ensure(g_ctx.d_seedcnt[b & 1], g_ctx.cap_seedcnt[b & 1], nb)) return GALAH_B200_ERR_CUDA;
+        B.sink = SeedSink{d_sel, B.bo.front(), index.seed_threshold(), g_ctx.d_seedcnt[b & 1]};
         const uint64_t span[2] = {B.bo.front(), B.bo.back()};
         GB_CUDA(cudaEventRecord(ev[b & 1][0], sk));
         if (marker_c) {
@@ -1537,7 +1540,7 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         co[nb] = nb;
         GB_CUDA(cudaStreamWaitEvent(st, g_ctx.ev_scan[b & 1], 0));
         GB_CUDA(cudaEventRecord(ev_ix[0], st));
-        if (int rc = index.add_packed_device(B.seq2, B.valid, B.off, nb, B.bo, co, cs, cl, st, B.sink.d_sel)) return rc;
+        if (int rc = index.add_packed_device(B.seq2, B.valid, B.off, nb, B.bo, co, cs, cl, st, B.sink.d_sel, B.sink.d_seed_count)) return rc;
         if (b == 0 && n_batches > 1) if (int rc = index.reserve_for(n, st)) return rc;
         GB_CUDA(cudaEventRecord(ev_ix[1], st));
         if (!device) {

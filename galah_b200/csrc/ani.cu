@@ -150,6 +150,7 @@ struct EmitParams {
     uint2 *kq;  // per seed: x = kmer << 1 | strand, y = spread position (one 8-byte read per seed)
     uint32_t *cso, *chunk_tmp;
     unsigned long long *table;
+    uint32_t *mismatch;  // set to genome + 1 if the selection bits hold another number of seeds than the host was told
 };
 
 // One bucket (four 8-byte slots, 32-byte aligned) in ONE 256-bit load (SASS LDG.E.256, sm_100):
@@ -193,6 +194,13 @@ __global__ void __launch_bounds__(kEmitThreads) ani_emit_kernel(const EmitParams
     __syncthreads();
     uint32_t running = 0;
     for (uint32_t x = 0; x < warp; x++) running += s_warp[x];
+    if (warp == 31) {  // the arrays were sized from a count made elsewhere (the scan's own, or ani_count_kernel)
+        if (running + mine != n_seeds) { if (lane == 0) atomicExch(p.mismatch, g + 1u); return; }
+    } else {
+        uint32_t total = running;
+        for (uint32_t x = warp; x < 32; x++) total += s_warp[x];
+        if (total != n_seeds) return;  // whole CTA leaves: nothing is written past the space the host reserved
+    }
     for (uint64_t wb = wa; wb < wz; wb += 32) {
         const uint64_t w = wb + lane;
         uint32_t word = w < wz ? sel_word(p.sel, w, limit) : 0u;
@@ -597,7 +605,7 @@ struct PinnedBuf {
 struct AniScratch {
     PinnedBuf<uint32_t> h_acc;
     PinnedBuf<unsigned long long> h_fx;
-    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix, overflow;
+    TmpBuf<uint32_t> sel, count, contig_start, chunk_base, chunk_tmp, nch, pairs, acc, unit_prefix, overflow, mismatch;
     TmpBuf<uint64_t> contig_off, seed_off_b, cso_off_b, table_off_b;
     TmpBuf<unsigned long long> acc_fx, pair_table;
     TmpBuf<uint32_t> pair_mask;
@@ -690,7 +698,7 @@ AniIndex::~AniIndex() {
 int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
                                 size_t n, const std::vector<uint64_t> &base_off, const std::vector<uint64_t> &contig_off,
                                 const std::vector<uint32_t> &contig_start, const std::vector<uint32_t> &contig_len,
-                                cudaStream_t st, const uint32_t *d_sel_in) {
+                                cudaStream_t st, const uint32_t *d_sel_in, const uint32_t *d_count_in) {
     if (n == 0) return 0;
     if (base_off.size() != n + 1 || contig_off.size() != n + 1) { set_error("ani index: bad offset arrays"); return 3; }
     for (size_t g = 0; g <= n; g++)
@@ -720,6 +728,8 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     if (!scratch_) scratch_ = new AniScratch();
     TmpBuf<uint32_t> &d_sel = scratch_->sel, &d_count = scratch_->count, &d_contig_start = scratch_->contig_start,
                      &d_chunk_base = scratch_->chunk_base, &d_chunk_tmp = scratch_->chunk_tmp, &d_nch = scratch_->nch;
+    if (scratch_->mismatch.alloc(1)) return 2;
+    GB_CUDA(cudaMemsetAsync(scratch_->mismatch.p, 0, 4, st));
     TmpBuf<uint64_t> &d_contig_off = scratch_->contig_off, &d_seed_off_b = scratch_->seed_off_b,
                      &d_cso_off_b = scratch_->cso_off_b, &d_table_off_b = scratch_->table_off_b;
     if ((!d_sel_in && d_sel.alloc(n_words + 1)) || d_count.alloc(n)) return 2;
@@ -731,11 +741,13 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
             ani_mark_kernel<<<(uint32_t)std::max<uint64_t>(blocks, 1), 256, 0, st>>>(d_seq2, d_valid, first, end, thr, d_sel.p);
             GB_LAUNCH_CHECK();
         }
-        ani_count_kernel<<<(uint32_t)n, 256, 0, st>>>(sel_p, d_base_off, first, d_count.p);
-        GB_LAUNCH_CHECK();
+        if (!(d_sel_in && d_count_in)) {
+            ani_count_kernel<<<(uint32_t)n, 256, 0, st>>>(sel_p, d_base_off, first, d_count.p);
+            GB_LAUNCH_CHECK();
+        }
     }
     std::vector<uint32_t> count(n);
-    GB_CUDA(cudaMemcpyAsync(count.data(), d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(count.data(), d_sel_in && d_count_in ? d_count_in : d_count.p, n * 4, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
 
     // absolute offsets of the new genomes in the index arrays
@@ -767,6 +779,7 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     e.kq = d_kq_.p; e.cso = d_cso_.p;
     e.chunk_tmp = d_chunk_tmp.p - seed_off[0];  // indexed with absolute seed offsets
     e.table = d_table_.p;
+    e.mismatch = scratch_->mismatch.p;
     ani_emit_kernel<<<(uint32_t)n, kEmitThreads, 0, st>>>(e);
     GB_LAUNCH_CHECK();
     // persistent per-genome metadata (device copies hold n+1 offsets: entry g0+n is the running end)
@@ -774,8 +787,14 @@ int AniIndex::add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid,
     GB_CUDA(cudaMemcpyAsync(d_cso_off_.p + g0, cso_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     GB_CUDA(cudaMemcpyAsync(d_table_off_.p + g0, table_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     GB_CUDA(cudaMemcpyAsync(d_n_chunks_.p + g0, n_chunks.data(), n * 4, cudaMemcpyHostToDevice, st));
+    uint32_t mismatch = 0;
+    GB_CUDA(cudaMemcpyAsync(&mismatch, scratch_->mismatch.p, 4, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaEventRecord(ev_[1], st));
     GB_CUDA(cudaStreamSynchronize(st));  // host staging vectors die here
+    if (mismatch) {
+        set_error("ani index: seed count of genome " + std::to_string(mismatch - 1) + " of the batch disagrees with its selection bits");
+        return 3;
+    }
     float ms = 0.f;
     GB_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
     last_build_ms = ms;

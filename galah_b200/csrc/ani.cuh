@@ -65,7 +65,9 @@ public:
     int add_packed_device(const uint32_t *d_seq2, const uint32_t *d_valid, const uint64_t *d_base_off,
                           size_t n, const std::vector<uint64_t> &base_off_host,
                           const std::vector<uint64_t> &contig_off, const std::vector<uint32_t> &contig_start,
-                          const std::vector<uint32_t> &contig_len, cudaStream_t st, const uint32_t *d_sel = nullptr);
+                          const std::vector<uint32_t> &contig_len, cudaStream_t st, const uint32_t *d_sel = nullptr,
+                          const uint32_t *d_seed_count = nullptr);
+    // d_seed_count (with d_sel): seeds per genome already counted by the scan -- no counting pass.
     // d_sel: seed selection bits of the batch already made by the fused k = 21 scan (sketch.cuh
     // SeedSink; one bit per base relative to base_off_host[0]); the mark pass is skipped then.
     uint64_t seed_threshold() const { return ~0ull / c_; }

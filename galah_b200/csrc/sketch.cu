@@ -317,6 +317,7 @@ struct ChunkParams {
     uint32_t *sel;
     uint64_t sel_first_base;
     uint64_t seed_thr;       // a 15-mer is a seed iff mm_hash64(canonical) < seed_thr
+    uint32_t *seed_count;    // [n] or null: seeds per genome, added up by the scan
 };
 
 __global__ void __launch_bounds__(1024) sketch_plan_kernel(const ChunkParams p) {
@@ -736,6 +737,11 @@ __global__ void __launch_bounds__(256) scan21v2_kernel(const ChunkParams p) {
     if (SEEDS) {
         uint32_t *out = p.sel + ((P0 - p.sel_first_base) >> 5);
         out[0] = sel0; out[1] = sel1;
+        if (p.seed_count) {  // the lanes that are still here add up their seeds: one atomic per warp
+            const unsigned lanes = __activemask();
+            const uint32_t tot = __reduce_add_sync(lanes, (uint32_t)(__popc(sel0) + __popc(sel1)));
+            if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)lanes) - 1) && tot) atomicAdd(p.seed_count + g, tot);
+        }
     }
 }
 
@@ -884,6 +890,8 @@ int sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uint32_t *
     c.fixed_thr = 0; c.n_parts = 0; c.part = 0; c.frac_c = 0;
     c.plan_k = seeds ? 15 : 0; c.sel = seeds ? seeds->d_sel : nullptr;
     c.sel_first_base = seeds ? seeds->first_base : 0; c.seed_thr = seeds ? seeds->thr : 0;
+    c.seed_count = seeds ? seeds->d_seed_count : nullptr;
+    if (c.seed_count) GB_CUDA(cudaMemsetAsync(c.seed_count, 0, n * sizeof(uint32_t), stream));
 
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
@@ -967,6 +975,8 @@ int marker_sketch_enqueue(SketchWorkspace &ws, const uint32_t *d_seq2, const uin
     c.fixed_thr = ~0ull / c_marker - 1;  // keep h < (2^64-1)/c  <=>  h <= that - 1
     c.plan_k = seeds ? 15 : 0; c.sel = seeds ? seeds->d_sel : nullptr;
     c.sel_first_base = seeds ? seeds->first_base : 0; c.seed_thr = seeds ? seeds->thr : 0;
+    c.seed_count = seeds ? seeds->d_seed_count : nullptr;
+    if (c.seed_count) GB_CUDA(cudaMemsetAsync(c.seed_count, 0, n * sizeof(uint32_t), stream));
     sketch_plan_kernel<<<1, 1024, 0, stream>>>(c);
     GB_LAUNCH_CHECK();
     if (n_parts > 1) GB_CUDA(cudaMemsetAsync(ws.d_cand_n, 0, n * (size_t)n_parts * sizeof(uint32_t), stream));

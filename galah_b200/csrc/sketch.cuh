@@ -28,6 +28,9 @@ struct SeedSink {
     uint32_t *d_sel;
     uint64_t first_base;
     uint64_t thr;
+    // optional: seeds per genome of the batch, counted by the scan itself (zeroed by the enqueue call);
+    // AniIndex::add_packed_device then needs no counting pass over the selection bits
+    uint32_t *d_seed_count = nullptr;
 };
 
 // Enqueue the sketch kernel over n packed genomes (layout: see sketch.cu / galah_b200.h).
