@@ -173,8 +173,11 @@ __device__ __forceinline__ uint32_t table_slot(uint32_t km, uint32_t mask) {
 // barrier rounds of the 256-thread version (1.09 ms per 512-genome batch, all of it latency) are
 // gone and four times as many dependent load chains are in flight per genome.
 constexpr int kEmitThreads = 1024;
-__global__ void __launch_bounds__(kEmitThreads) ani_emit_kernel(const EmitParams p) {
+constexpr int kEmitWords = 4;     // mask words per lane and round
+constexpr int kEmitStage = 256;   // staged seeds per warp and round (8x the expectation at 1 seed per 30 positions)
+__global__ void __launch_bounds__(kEmitThreads, 2) ani_emit_kernel(const EmitParams p) {
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_stage[32][kEmitStage];
     const uint32_t g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t b0 = p.base_off[g];
     const uint64_t w0 = (b0 - p.first_base) >> 5, w1 = (p.base_off[g + 1] - p.first_base) >> 5;
@@ -201,34 +204,69 @@ __global__ void __launch_bounds__(kEmitThreads) ani_emit_kernel(const EmitParams
         for (uint32_t x = warp; x < 32; x++) total += s_warp[x];
         if (total != n_seeds) return;  // whole CTA leaves: nothing is written past the space the host reserved
     }
-    for (uint64_t wb = wa; wb < wz; wb += 32) {
-        const uint64_t w = wb + lane;
-        uint32_t word = w < wz ? sel_word(p.sel, w, limit) : 0u;
-        const uint32_t pc = __popc(word);
-        uint32_t incl = pc;
+    // One seed: canonical 15-mer, contig, spread position, chunk -> slot `rank` of the genome's arrays.
+    auto emit_seed = [&](const uint32_t rel, const uint32_t rank) {
+        uint32_t canon = 0, strand = 0;
+        canon15(p.seq2, p.valid, b0 + rel, canon, strand);
+        uint32_t lo = 0, hi = n_contigs;  // last contig with start <= rel
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.contig_start[c0 + mid] <= rel) lo = mid; else hi = mid;
+        }
+        p.kq[so + rank] = make_uint2((canon << 1) | strand, rel + lo * (uint32_t)(kAniBand + 1));
+        p.chunk_tmp[so + rank] = p.contig_chunk_base[c0 + lo] + (rel - p.contig_start[c0 + lo]) / kAniChunk;
+    };
+    // A warp takes 128 mask words per round (four per lane, loaded together), ranks their set bits with
+    // four warp scans and STAGES the seed positions in shared memory in rank order; the lanes then take
+    // one staged seed each, so the dependent loads of a round (the k-mer's bases, the contig table) are
+    // in flight for 32 seeds at once instead of behind each other in a per-lane loop over a word's bits.
+    uint32_t *stage = s_stage[warp];
+    const uint64_t rel0 = (b0 - p.first_base);  // bit position of the genome's first base in the mask
+    for (uint64_t wb = wa; wb < wz; wb += 32 * kEmitWords) {
+        uint32_t word[kEmitWords], at[kEmitWords];
+        uint32_t tot = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += t;
+        for (int u = 0; u < kEmitWords; u++) {
+            const uint64_t w = wb + 32 * u + lane;
+            word[u] = w < wz ? sel_word(p.sel, w, limit) : 0u;
         }
-        uint32_t rank = running + incl - pc;
-        running += __shfl_sync(0xffffffffu, incl, 31);
-        while (word) {
-            const uint32_t bit = __ffs(word) - 1;
-            word &= word - 1;
-            const uint64_t P = p.first_base + (w << 5) + bit;
-            uint32_t canon = 0, strand = 0;
-            canon15(p.seq2, p.valid, P, canon, strand);
-            const uint32_t rel = (uint32_t)(P - b0);
-            uint32_t lo = 0, hi = n_contigs;  // last contig with start <= rel
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (p.contig_start[c0 + mid] <= rel) lo = mid; else hi = mid;
+#pragma unroll
+        for (int u = 0; u < kEmitWords; u++) {
+            const uint32_t pc = __popc(word[u]);
+            uint32_t incl = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
             }
-            p.kq[so + rank] = make_uint2((canon << 1) | strand, rel + lo * (uint32_t)(kAniBand + 1));
-            p.chunk_tmp[so + rank] = p.contig_chunk_base[c0 + lo] + (rel - p.contig_start[c0 + lo]) / kAniChunk;
-            rank++;
+            at[u] = tot + incl - pc;
+            tot += __shfl_sync(0xffffffffu, incl, 31);
         }
+        if (tot <= (uint32_t)kEmitStage) {
+#pragma unroll
+            for (int u = 0; u < kEmitWords; u++) {
+                uint32_t bits = word[u], x = at[u];
+                const uint32_t wrel = (uint32_t)(((wb + 32 * u + lane) << 5) - rel0);
+                while (bits) {
+                    stage[x++] = wrel + (uint32_t)(__ffs(bits) - 1);
+                    bits &= bits - 1;
+                }
+            }
+            __syncwarp();
+            for (uint32_t x = lane; x < tot; x += 32) emit_seed(stage[x], running + x);
+            __syncwarp();
+        } else {  // a round denser than the staging area (never at 1 seed per 30 .. 125 positions of real sequence)
+#pragma unroll
+            for (int u = 0; u < kEmitWords; u++) {
+                uint32_t bits = word[u], x = running + at[u];
+                const uint32_t wrel = (uint32_t)(((wb + 32 * u + lane) << 5) - rel0);
+                while (bits) {
+                    emit_seed(wrel + (uint32_t)(__ffs(bits) - 1), x++);
+                    bits &= bits - 1;
+                }
+            }
+        }
+        running += tot;
     }
     __syncthreads();  // every seed of the genome is written before the tables below read them
     // chunk -> first seed table (cso[t] = index of the first seed with chunk >= t; cso[n_chunks] = n_seeds)
