@@ -1431,7 +1431,7 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
     const uint32_t s = 1000;
     cudaStream_t st = g_ctx.stream;
     // batches of about 1 G bases (375 MB packed): bounds the K1 / K3 scratch, and is the upload unit
-    const uint64_t kBatchBases = 1ull << 30;
+    const uint64_t kBatchBases = 1ull << 30;  // (0.5 .. 4 G bases per batch measured within 1 % of each other)
     std::vector<size_t> cut{0};
     while (cut.back() < n) {
         size_t b1 = cut.back() + 1;
