@@ -164,6 +164,10 @@ _SIGNATURES = {
     "galah_b200_contig_names": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.POINTER(ctypes.POINTER(ctypes.c_char_p)), sizep]),
     "galah_b200_contig_names_free": (None, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_size_t]),
     "galah_b200_ingest_packed": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_int, vp, vp, vp, f32p]),
+    "galah_b200_ingest_packed_sparse": (ctypes.c_int, [vp, u64p, u64p, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, vp, vp, vp, f32p]),
+    "galah_b200_cluster_packed_sparse": (ctypes.c_int, [vp, u64p, u64p, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
+                                                        ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.POINTER(Clusters),
+                                                        ctypes.POINTER(ClusterStats)]),
     "galah_b200_ingest_packed_markers": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32,
                                                         vp, vp, vp, f32p]),
     "galah_b200_marker_row_capacity": (ctypes.c_uint32, [ctypes.c_uint64, ctypes.c_int]),

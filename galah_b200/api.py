@@ -304,6 +304,17 @@ class AniIndex:
                                              int(d_hashes), int(d_counts), self._h, ms))
         return float(ms[0]), float(ms[1])
 
+    def ingest_packed_sparse(self, seq2, invalid_ranges, base_off, lengths, d_hashes, d_counts):
+        """ingest_packed from HOST buffers without the validity bitmap: invalid_ranges = (begin, end) uint64 arrays
+        of the invalid base ranges (absolute, sorted, disjoint; empty when every base is A/C/G/T)."""
+        base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+        ib = np.ascontiguousarray(invalid_ranges[0], np.uint64); ie = np.ascontiguousarray(invalid_ranges[1], np.uint64)
+        ms = (ctypes.c_float * 2)()
+        check(lib().galah_b200_ingest_packed_sparse(int(seq2), ib.ctypes.data_as(_native.u64p), ie.ctypes.data_as(_native.u64p), len(ib),
+                                                    base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p),
+                                                    len(lengths), int(d_hashes), int(d_counts), self._h, ms))
+        return float(ms[0]), float(ms[1])
+
     def ingest_packed_markers(self, seq2, valid, base_off, lengths, marker_stride, d_rows, d_counts, device=False,
                               d_base_off=0):
         """As ingest_packed, with FracMinHash marker rows (the skani-style screen's input) of stride marker_stride."""
@@ -490,6 +501,25 @@ def _stats_dict(stats):
     for f in ("ani_chain_ms", "ingest_ms", "sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms", "total_ms"):
         d[f] = float(getattr(stats, f))
     return d
+
+
+def cluster_packed_sparse(seq2, invalid_ranges, base_off, lengths, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0,
+                          small_genomes=False):
+    """cluster_packed on HOST buffers without the validity bitmap (a third of the bytes stays off PCIe):
+    invalid_ranges = (begin, end) uint64 arrays of the invalid base ranges, absolute, sorted, disjoint."""
+    base_off = np.ascontiguousarray(base_off, np.uint64); lengths = np.ascontiguousarray(lengths, np.uint64)
+    ib = np.ascontiguousarray(invalid_ranges[0], np.uint64); ie = np.ascontiguousarray(invalid_ranges[1], np.uint64)
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    ptr = lambda a: a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+    check(lib().galah_b200_cluster_packed_sparse(ptr(seq2), ib.ctypes.data_as(_native.u64p), ie.ctypes.data_as(_native.u64p), len(ib),
+                                                 base_off.ctypes.data_as(_native.u64p), lengths.ctypes.data_as(_native.u64p),
+                                                 len(lengths), ctypes.c_float(precluster_ani), ctypes.c_float(ani),
+                                                 ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+                                                 ctypes.byref(res), ctypes.byref(stats)))
+    clusters, info = _take_clusters(res)
+    info.update(_stats_dict(stats))
+    return clusters, info
 
 
 def cluster_packed(seq2, valid, base_off, lengths, precluster_ani=0.9, ani=95.0, min_aligned_fraction=15.0,

@@ -59,8 +59,9 @@ struct Context {
     size_t cap_cand_map = 0;
     cudaEvent_t ev_done = nullptr;
     uint32_t *slot_seq2[2] = {nullptr, nullptr}, *slot_valid[2] = {nullptr, nullptr};  // upload slots of ingest_packed
-    uint64_t *slot_off[2] = {nullptr, nullptr};
-    size_t cap_slot_seq2[2] = {0, 0}, cap_slot_valid[2] = {0, 0}, cap_slot_off[2] = {0, 0};
+    uint64_t *slot_off[2] = {nullptr, nullptr}, *slot_len[2] = {nullptr, nullptr}, *slot_ranges[2] = {nullptr, nullptr};
+    size_t cap_slot_seq2[2] = {0, 0}, cap_slot_valid[2] = {0, 0}, cap_slot_off[2] = {0, 0}, cap_slot_len[2] = {0, 0},
+           cap_slot_ranges[2] = {0, 0};
     uint32_t *d_sel = nullptr; size_t cap_sel = 0;  // K3 seed selection bits made by the fused k = 21 scan
     uint32_t *d_sel2 = nullptr; size_t cap_sel2 = 0;  // second buffer: batch b + 1 is scanned while batch b is indexed
     uint32_t *d_seedcnt[2] = {nullptr, nullptr}; size_t cap_seedcnt[2] = {0, 0};  // seeds per genome, counted by the scan
@@ -82,9 +83,9 @@ struct Context {
         scan_stream = nullptr;
         for (auto &e : ev_scan) { if (e) cudaEventDestroy(e); e = nullptr; }
         for (int x = 0; x < 2; x++) {
-            cudaFree(slot_seq2[x]); cudaFree(slot_valid[x]); cudaFree(slot_off[x]);
-            slot_seq2[x] = slot_valid[x] = nullptr; slot_off[x] = nullptr;
-            cap_slot_seq2[x] = cap_slot_valid[x] = cap_slot_off[x] = 0;
+            cudaFree(slot_seq2[x]); cudaFree(slot_valid[x]); cudaFree(slot_off[x]); cudaFree(slot_len[x]); cudaFree(slot_ranges[x]);
+            slot_seq2[x] = slot_valid[x] = nullptr; slot_off[x] = slot_len[x] = slot_ranges[x] = nullptr;
+            cap_slot_seq2[x] = cap_slot_valid[x] = cap_slot_off[x] = cap_slot_len[x] = cap_slot_ranges[x] = 0;
         }
         pws.release(); sws.release(); fasta.release();
         if (h_raw) cudaFreeHost(h_raw);
@@ -1422,10 +1423,16 @@ int galah_b200_cluster_files(const char *const *paths, size_t n, float precluste
 // bases on the copy stream while the previous batch is sketched and indexed.  Caller holds g_mu.
 // marker_c != 0: the rows are FracMinHash MARKER sketches (k = 21, density 1 / marker_c, row stride
 // marker_stride) for the skani-style screen instead of bottom-1000 MinHash sketches.
+// Host input without a validity bitmap (valid == nullptr): every base of a genome's length is valid but the
+// listed ranges (absolute base coordinates, half open, sorted by begin); the bitmap of a batch is then made
+// on the device and a third of the bytes stays off PCIe.
+struct SparseValidity { const uint64_t *begin, *end; size_t n; };
+
 static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off_or_null,
                          const uint64_t *base_off, const uint64_t *lengths, size_t n, bool device, uint64_t *d_table,
                          uint32_t *d_counts, AniIndex &index, float *sketch_ms_out, float *index_ms_out,
-                         uint32_t marker_c = 0, uint32_t marker_stride = 0) {
+                         uint32_t marker_c = 0, uint32_t marker_stride = 0, const SparseValidity *sparse = nullptr) {
+    if (!device && !valid && !sparse) { set_error("packed genomes: no validity bitmap and no invalid-range list"); return GALAH_B200_ERR_ARG; }
     for (size_t g = 0; g <= n; g++)
         if (base_off[g] % 128) { set_error("packed genomes: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
     const uint32_t s = 1000;
@@ -1441,7 +1448,8 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
     const size_t n_batches = cut.size() - 1;
     // host input: two staging slots on the device, filled on the copy stream
     // (the slots live in the context and only ever grow: no cudaMalloc / cudaFree per call)
-    struct Slot { uint32_t *seq2 = nullptr, *valid = nullptr; uint64_t *off = nullptr; cudaEvent_t landed = nullptr, freed = nullptr; } slot[2];
+    struct Slot { uint32_t *seq2 = nullptr, *valid = nullptr; uint64_t *off = nullptr, *len = nullptr, *ranges = nullptr;
+                  cudaEvent_t landed = nullptr, freed = nullptr; } slot[2];
     struct SlotGuard { Slot *s; ~SlotGuard() { for (int x = 0; x < 2; x++) {
                        if (s[x].landed) cudaEventDestroy(s[x].landed); if (s[x].freed) cudaEventDestroy(s[x].freed); } } } slot_guard{slot};
     uint64_t max_bases = 0; size_t max_n = 0;
@@ -1454,14 +1462,16 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         for (int x = 0; x < 2; x++) {
             if (ws_ensure(g_ctx.slot_seq2[x], g_ctx.cap_slot_seq2[x], max_bases / 16 + 8) ||
                 ws_ensure(g_ctx.slot_valid[x], g_ctx.cap_slot_valid[x], max_bases / 32 + 8) ||
-                ws_ensure(g_ctx.slot_off[x], g_ctx.cap_slot_off[x], max_n + 1))
+                ws_ensure(g_ctx.slot_off[x], g_ctx.cap_slot_off[x], max_n + 1) ||
+                (sparse && ws_ensure(g_ctx.slot_len[x], g_ctx.cap_slot_len[x], max_n + 1)))
                 return GALAH_B200_ERR_CUDA;
             slot[x].seq2 = g_ctx.slot_seq2[x]; slot[x].valid = g_ctx.slot_valid[x]; slot[x].off = g_ctx.slot_off[x];
+            slot[x].len = g_ctx.slot_len[x];
             GB_CUDA(cudaEventCreateWithFlags(&slot[x].landed, cudaEventDisableTiming));
             GB_CUDA(cudaEventCreateWithFlags(&slot[x].freed, cudaEventDisableTiming));
         }
     }
-    std::vector<std::vector<uint64_t>> rel(n_batches);
+    std::vector<std::vector<uint64_t>> rel(n_batches), rel_ranges(sparse ? n_batches : 0);
     auto upload = [&](size_t b) -> int {
         Slot &sl = slot[b & 1];
         const size_t g0 = cut[b], nb = cut[b + 1] - g0;
@@ -1470,8 +1480,27 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
         for (size_t g = 0; g <= nb; g++) rel[b][g] = base_off[g0 + g] - first;
         if (b >= 2) GB_CUDA(cudaStreamWaitEvent(g_ctx.copy_stream, sl.freed, 0));  // the slot's previous batch is consumed
         GB_CUDA(cudaMemcpyAsync(sl.seq2, seq2 + first / 16, total / 16 * 4, cudaMemcpyHostToDevice, g_ctx.copy_stream));
-        GB_CUDA(cudaMemcpyAsync(sl.valid, valid + first / 32, total / 32 * 4, cudaMemcpyHostToDevice, g_ctx.copy_stream));
         GB_CUDA(cudaMemcpyAsync(sl.off, rel[b].data(), (nb + 1) * 8, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+        if (valid) {
+            GB_CUDA(cudaMemcpyAsync(sl.valid, valid + first / 32, total / 32 * 4, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+        } else {
+            // the batch's invalid ranges, relative to its first base (they are sorted: two binary searches)
+            const uint64_t last = first + total;
+            const size_t r0 = std::lower_bound(sparse->end, sparse->end + sparse->n, first + 1) - sparse->end;
+            const size_t r1 = std::lower_bound(sparse->begin, sparse->begin + sparse->n, last) - sparse->begin;
+            std::vector<uint64_t> &rr = rel_ranges[b];
+            rr.clear();
+            for (size_t x = r0; x < r1; x++) {
+                const uint64_t rb = std::max(sparse->begin[x], first), re = std::min(sparse->end[x], last);
+                if (rb < re) { rr.push_back(rb - first); rr.push_back(re - first); }
+            }
+            int which = (int)(b & 1);
+            if (ws_ensure(g_ctx.slot_ranges[which], g_ctx.cap_slot_ranges[which], rr.size() + 2)) return GALAH_B200_ERR_CUDA;
+            sl.ranges = g_ctx.slot_ranges[which];
+            GB_CUDA(cudaMemcpyAsync(sl.len, lengths + g0, nb * 8, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+            if (!rr.empty()) GB_CUDA(cudaMemcpyAsync(sl.ranges, rr.data(), rr.size() * 8, cudaMemcpyHostToDevice, g_ctx.copy_stream));
+            if (int rc = validity_from_ranges_enqueue(sl.valid, sl.off, sl.len, nb, sl.ranges, rr.size() / 2, g_ctx.copy_stream)) return rc;
+        }
         GB_CUDA(cudaEventRecord(sl.landed, g_ctx.copy_stream));
         return 0;
     };
@@ -1564,10 +1593,21 @@ static int ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint
     return 0;
 }
 
+static int check_sparse(const uint64_t *begin, const uint64_t *end, size_t n_inv) {
+    if (n_inv && (!begin || !end)) { set_error("invalid ranges: NULL arrays"); return GALAH_B200_ERR_ARG; }
+    for (size_t x = 0; x < n_inv; x++)
+        if (begin[x] >= end[x] || (x && begin[x] < end[x - 1])) {
+            set_error("invalid ranges: must be non-empty, sorted and disjoint");
+            return GALAH_B200_ERR_ARG;
+        }
+    return 0;
+}
+
 static int cluster_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off_or_null,
                           const uint64_t *base_off, const uint64_t *lengths, size_t n, bool device,
                           float precluster_min_ani, float ani_threshold_pct, float min_af_pct, int small_genomes,
-                          galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+                          galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats,
+                          const SparseValidity *sparse = nullptr) {
     if (!out) { set_error("cluster_packed: out is NULL"); return GALAH_B200_ERR_ARG; }
     memset(out, 0, sizeof(*out));
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -1581,7 +1621,7 @@ static int cluster_packed(const uint32_t *seq2, const uint32_t *valid, const uin
         return GALAH_B200_ERR_CUDA;
     float sketch_ms = 0.f, index_ms = 0.f;
     if (int rc = ingest_packed(seq2, valid, d_base_off_or_null, base_off, lengths, n, device, g_ctx.d_table,
-                               g_ctx.d_counts, index, &sketch_ms, &index_ms))
+                               g_ctx.d_counts, index, &sketch_ms, &index_ms, 0, 0, sparse))
         return rc;
     const double t_ingest = now_ms();
     int rc = cluster_from_resident(g_ctx.d_table, g_ctx.d_counts, n, index, precluster_min_ani, ani_threshold_pct,
@@ -1603,6 +1643,30 @@ int galah_b200_ingest_packed(const uint32_t *seq2, const uint32_t *valid, const 
     int rc = ingest_packed(seq2, valid, d_base_off, base_off, lengths, n, device != 0, d_hashes, d_counts, idx->impl, &a, &b);
     if (ms2) { ms2[0] = a; ms2[1] = b; }
     return rc;
+}
+
+int galah_b200_ingest_packed_sparse(const uint32_t *seq2, const uint64_t *invalid_begin, const uint64_t *invalid_end,
+                                    size_t n_invalid, const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                    uint64_t *d_hashes, uint32_t *d_counts, galah_b200_ani_index_t *idx, float *ms2) {
+    if (int rc = check_sparse(invalid_begin, invalid_end, n_invalid)) return rc;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (int rc = require_ctx()) return rc;
+    if (!idx || !d_hashes || !d_counts) { set_error("ingest_packed_sparse: NULL argument"); return GALAH_B200_ERR_ARG; }
+    const SparseValidity sv{invalid_begin, invalid_end, n_invalid};
+    float a = 0.f, b = 0.f;
+    int rc = ingest_packed(seq2, nullptr, nullptr, base_off, lengths, n, false, d_hashes, d_counts, idx->impl, &a, &b, 0, 0, &sv);
+    if (ms2) { ms2[0] = a; ms2[1] = b; }
+    return rc;
+}
+
+int galah_b200_cluster_packed_sparse(const uint32_t *seq2, const uint64_t *invalid_begin, const uint64_t *invalid_end,
+                                     size_t n_invalid, const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                     float precluster_min_ani, float ani_threshold_pct, float min_af_pct, int small_genomes,
+                                     galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (int rc = check_sparse(invalid_begin, invalid_end, n_invalid)) return rc;
+    const SparseValidity sv{invalid_begin, invalid_end, n_invalid};
+    return cluster_packed(seq2, nullptr, nullptr, base_off, lengths, n, false, precluster_min_ani, ani_threshold_pct,
+                          min_af_pct, small_genomes, out, stats, &sv);
 }
 
 int galah_b200_ingest_packed_markers(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,

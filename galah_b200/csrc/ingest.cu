@@ -539,4 +539,47 @@ int FastaDecoder::split_records(const DecodedFiles &files, DecodedFiles &units, 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Validity bitmap of packed genomes from a SPARSE description (galah_b200_cluster_packed_sparse):
+// every base of a genome's `length` is valid except the listed ranges (N runs, record breaks); the
+// padding behind a genome is invalid.  The bitmap is a third of the packed bytes and almost
+// constant, so callers that hold packed genomes on the host need not send it over PCIe.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) validity_fill_kernel(uint32_t *__restrict__ valid, const uint64_t *__restrict__ off,
+                                                            const uint64_t *__restrict__ lengths, uint32_t n) {
+    const uint32_t g = blockIdx.x;
+    if (g >= n) return;
+    const uint64_t w0 = off[g] >> 5, w1 = off[g + 1] >> 5, len = lengths[g];
+    for (uint64_t w = w0 + threadIdx.x; w < w1; w += 256) {
+        const uint64_t bit0 = (w - w0) << 5;
+        valid[w] = bit0 + 32 <= len ? 0xFFFFFFFFu : bit0 >= len ? 0u : (1u << (uint32_t)(len - bit0)) - 1u;
+    }
+}
+// ranges: (begin, end) pairs in bases relative to the bitmap's first bit, half open; one warp per range
+__global__ void __launch_bounds__(256) validity_clear_kernel(uint32_t *__restrict__ valid, const uint64_t *__restrict__ ranges,
+                                                             uint32_t n_ranges) {
+    const uint32_t r = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n_ranges) return;
+    const uint64_t b = ranges[2 * r], e = ranges[2 * r + 1];
+    if (e <= b) return;
+    const uint64_t wb = b >> 5, we = (e - 1) >> 5;
+    for (uint64_t w = wb + lane; w <= we; w += 32) {
+        uint32_t m = 0xFFFFFFFFu;
+        if (w == wb) m &= 0xFFFFFFFFu << (uint32_t)(b & 31);
+        if (w == we) m &= 0xFFFFFFFFu >> (31u - (uint32_t)((e - 1) & 31));
+        atomicAnd(&valid[w], ~m);  // ranges of one genome may share a word
+    }
+}
+int validity_from_ranges_enqueue(uint32_t *d_valid, const uint64_t *d_off, const uint64_t *d_lengths, size_t n,
+                                 const uint64_t *d_ranges, size_t n_ranges, cudaStream_t st) {
+    if (n == 0) return 0;
+    validity_fill_kernel<<<(uint32_t)n, 256, 0, st>>>(d_valid, d_off, d_lengths, (uint32_t)n);
+    GB_LAUNCH_CHECK();
+    if (n_ranges) {
+        validity_clear_kernel<<<(uint32_t)((n_ranges * 32 + 255) / 256), 256, 0, st>>>(d_valid, d_ranges, (uint32_t)n_ranges);
+        GB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 }  // namespace gb200

@@ -61,4 +61,10 @@ private:
     cudaEvent_t ev_[2] = {nullptr, nullptr};
 };
 
+// Validity bitmap (1 bit per base, layout of K1) of n packed genomes from their lengths and a list of
+// invalid ranges: d_off = n + 1 base offsets relative to the bitmap's first bit (multiples of 128),
+// d_ranges = n_ranges (begin, end) pairs relative to the same origin.  Two small kernels on `st`.
+int validity_from_ranges_enqueue(uint32_t *d_valid, const uint64_t *d_off, const uint64_t *d_lengths, size_t n,
+                                 const uint64_t *d_ranges, size_t n_ranges, cudaStream_t st);
+
 }  // namespace gb200

@@ -358,8 +358,11 @@ class ShardedPipeline:
             self._idx[small_genomes] = gb.AniIndex(small_genomes=small_genomes)
         idx = self._idx[small_genomes]
         idx.clear()
-        k1_ms, idx_ms = idx.ingest_packed(seq2, valid, base_off, lengths, sp.my_table.data_ptr(), sp.my_counts.data_ptr(),
-                                          device=device, d_base_off=d_base_off)
+        if isinstance(valid, tuple):   # host buffers without the validity bitmap: (invalid begin, invalid end) arrays
+            k1_ms, idx_ms = idx.ingest_packed_sparse(seq2, valid, base_off, lengths, sp.my_table.data_ptr(), sp.my_counts.data_ptr())
+        else:
+            k1_ms, idx_ms = idx.ingest_packed(seq2, valid, base_off, lengths, sp.my_table.data_ptr(), sp.my_counts.data_ptr(),
+                                              device=device, d_base_off=d_base_off)
         t.cuda.synchronize()
         t1 = time.perf_counter()
         # ---- K2 (torch's current stream; the library's stream is idle: ingest_packed synchronised)
@@ -524,5 +527,6 @@ class ShardedPipeline:
         return self._run(d_seq2, d_valid, d_base_off, base_off, lengths, True, min_ani, ani_pct, min_af, small_genomes)
 
     def step_host(self, h_seq2, h_valid, base_off, lengths, min_ani=0.9, ani_pct=95.0, min_af=15.0, small_genomes=False):
-        """This rank's genomes are HOST buffers (addresses of pinned memory): uploaded inside the call."""
+        """This rank's genomes are HOST buffers (addresses of pinned memory): uploaded inside the call.
+        h_valid: address of the validity bitmap, or a (begin, end) tuple of invalid base ranges (no bitmap upload)."""
         return self._run(h_seq2, h_valid, 0, base_off, lengths, False, min_ani, ani_pct, min_af, small_genomes)

@@ -362,6 +362,18 @@ int galah_b200_cluster_files_multi(const char *const *paths, size_t n, int n_dev
                                    int host_threads, galah_b200_clusters_t *out,
                                    galah_b200_cluster_stats_t *stats);
 
+/* galah_b200_cluster_packed without the validity bitmap: every base of a genome's `lengths[g]` is
+ * valid except the listed ranges [invalid_begin[x], invalid_end[x]) (absolute base coordinates in
+ * the packed arrays, sorted, disjoint: the N runs and record breaks a FASTA reader meets --
+ * needletail's normalisation inside finch::sketch_files, src/finch.rs:55-69); the bitmap is built
+ * on the device per upload batch.  The bitmap is a third of the packed bytes and almost constant:
+ * a host-buffer call is bound by PCIe, so not sending it is a third less time on the wire. */
+int galah_b200_cluster_packed_sparse(const uint32_t *seq2, const uint64_t *invalid_begin, const uint64_t *invalid_end,
+                                     size_t n_invalid, const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                     float precluster_min_ani, float ani_threshold_pct, float min_af_pct,
+                                     int small_genomes, galah_b200_clusters_t *out,
+                                     galah_b200_cluster_stats_t *stats);
+
 /* First half of the two calls above, for callers that drive the stages themselves (the multi-GPU
  * pipeline, one process per GPU): packed genomes (host arrays if device == 0, else resident) ->
  * K1 sketch rows written to the DEVICE table d_hashes / d_counts (stride 1000) and the genomes
@@ -369,6 +381,10 @@ int galah_b200_cluster_files_multi(const char *const *paths, size_t n, int n_dev
 int galah_b200_ingest_packed(const uint32_t *seq2, const uint32_t *valid, const uint64_t *d_base_off,
                              const uint64_t *base_off, const uint64_t *lengths, size_t n, int device,
                              uint64_t *d_hashes, uint32_t *d_counts, galah_b200_ani_index_t *idx, float *ms2);
+/* Host arrays without the validity bitmap (see galah_b200_cluster_packed_sparse). */
+int galah_b200_ingest_packed_sparse(const uint32_t *seq2, const uint64_t *invalid_begin, const uint64_t *invalid_end,
+                                    size_t n_invalid, const uint64_t *base_off, const uint64_t *lengths, size_t n,
+                                    uint64_t *d_hashes, uint32_t *d_counts, galah_b200_ani_index_t *idx, float *ms2);
 /* The same for the skani-style preclusterer: the rows are FracMinHash MARKER sketches (k = 21,
  * 1/1000, or 1/200 when idx was created with small_genomes) at row stride marker_stride
  * (galah_b200_marker_row_capacity of the longest unit), overflowing rows flagged 0xFFFFFFFF in

@@ -131,3 +131,61 @@ def test_contig_mode_units_agree_with_host_packer(gb, tmp_path):
     for f in ("i", "j", "common", "total"):
         assert np.array_equal(dev_hits[f], host_hits[f]), f
     assert np.array_equal(dev_hits["ani"].view(np.uint32), host_hits["ani"].view(np.uint32))
+
+
+def test_packed_genomes_without_the_validity_bitmap(gb):
+    """galah_b200_cluster_packed_sparse: the validity bitmap built on the device from the genomes' lengths and a list
+    of invalid ranges gives the clusters (and hit counts) of the call that is handed the bitmap -- on genomes with
+    N runs, a range that ends a genome, ranges sharing a bitmap word, and a genome whose length is not a multiple of 128."""
+    rng = np.random.default_rng(11)
+    n, L = 24, 150_037
+    padded = (L + 127) // 128 * 128
+    founders = [rng.integers(0, 4, L, dtype=np.uint8) for _ in range(6)]
+    codes = np.zeros((n, padded), np.uint8)
+    valid = np.zeros((n, padded), bool)
+    begins, ends = [], []
+    for g in range(n):
+        seq = founders[g % 6].copy()
+        pos = rng.choice(L, size=L // 50, replace=False)
+        seq[pos] = (seq[pos] + 1 + (g // 6)) % 4
+        codes[g, :L] = seq
+        valid[g, :L] = True
+        cuts = [(1000 + 37 * g, 1000 + 37 * g + 5), (1000 + 37 * g + 9, 1000 + 37 * g + 21), (70_000, 70_400)]
+        if g % 5 == 0:
+            cuts.append((L - 300, L))           # the genome's tail is N
+        for b, e in cuts:
+            valid[g, b:e] = False
+            begins.append(g * padded + b); ends.append(g * padded + e)
+    flat = codes.reshape(-1).astype(np.uint32)
+    seq2 = np.zeros(n * padded // 16, np.uint32)
+    for k in range(16):
+        seq2 |= flat[k::16] << np.uint32(2 * k)
+    vbits = np.packbits(valid.reshape(-1), bitorder="little").view(np.uint32)
+    base_off = np.arange(n + 1, dtype=np.uint64) * np.uint64(padded)
+    lengths = np.full(n, L, np.uint64)
+    want, info_w = gb.cluster_packed(seq2, vbits, base_off, lengths)
+    got, info_g = gb.cluster_packed_sparse(seq2, (np.array(begins, np.uint64), np.array(ends, np.uint64)), base_off, lengths)
+    assert got == want
+    assert info_g["n_precluster_hits"] == info_w["n_precluster_hits"] and info_g["n_ani_pairs"] == info_w["n_ani_pairs"]
+    # bit for bit: the K1 sketch rows and the K3 seeds made from the device-built bitmap equal those made from the uploaded one
+    import torch
+    dev = torch.device("cuda", 0)
+    rows, seeds = [], []
+    for sparse in (False, True):
+        idx = gb.AniIndex()
+        table = torch.zeros((n, 1000), dtype=torch.int64, device=dev)
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        if sparse:
+            idx.ingest_packed_sparse(seq2.ctypes.data, (np.array(begins, np.uint64), np.array(ends, np.uint64)), base_off, lengths,
+                                     table.data_ptr(), counts.data_ptr())
+        else:
+            idx.ingest_packed(seq2.ctypes.data, vbits.ctypes.data, base_off, lengths, table.data_ptr(), counts.data_ptr())
+        torch.cuda.synchronize()
+        rows.append((table.cpu().numpy().copy(), counts.cpu().numpy().copy()))
+        seeds.append([idx.seeds(g) for g in (0, 5, n - 1)])
+        idx.close()
+    assert np.array_equal(rows[0][0], rows[1][0]) and np.array_equal(rows[0][1], rows[1][1])
+    for a, b in zip(seeds[0], seeds[1]):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(gb.GalahB200Error):
+        gb.cluster_packed_sparse(seq2, (np.array([10, 5], np.uint64), np.array([20, 8], np.uint64)), base_off, lengths)
