@@ -1272,22 +1272,17 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
 // fasta1 -r fasta2, src/skani.rs:733-744).  The forward table holds query = i (the lower index):
 // what the representative search asks for (representatives precede the genome, src/clusterer.rs:
 // 229-231).  The membership pass can ask for a representative with a HIGHER index than the genome
-// (src/clusterer.rs:375-384): that is the reverse orientation, served from ani_rev when present;
-// otherwise the request is recorded (and the forward value returned) so that the caller can
-// evaluate exactly those pairs and run the engine again.
+// (src/clusterer.rs:375-384): that is the reverse orientation, served from ani_rev when present
+// (the forward value otherwise).  Lookups are pure reads: the engine calls them from several threads.
 namespace {
 struct AniTable {
     const galah_b200_pair_t *hits; size_t n; const float *ani; size_t stride;
     const float *ani_rev = nullptr;            // [n] or null
     const uint8_t *have_rev = nullptr;         // [n] or null: ani_rev[x] is valid
-    std::vector<size_t> *rev_requests = nullptr;
 };
 // The engine hands over the index of the hit the pair belongs to: no search.
 bool ani_table_by_hit(const AniTable &t, uint32_t rep, uint32_t genome, size_t hit, float *ani) {
-    if (rep > genome) {
-        if (t.ani_rev && (!t.have_rev || t.have_rev[hit])) { *ani = t.ani_rev[hit]; return true; }
-        if (t.rev_requests) t.rev_requests->push_back(hit);
-    }
+    if (rep > genome && t.ani_rev && (!t.have_rev || t.have_rev[hit])) { *ani = t.ani_rev[hit]; return true; }
     *ani = *(const float *)((const char *)t.ani + hit * t.stride);  // skani never yields None (src/skani.rs:760)
     return true;
 }

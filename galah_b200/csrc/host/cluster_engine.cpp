@@ -31,8 +31,10 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <numeric>
+#include <thread>
 
 namespace gb200 {
 
@@ -178,19 +180,46 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     std::vector<uint8_t> edge_state(adj.nbr.size(), 0);  // 0 = not computed, 1 = Some(ani), 2 = None
     std::vector<float> edge_ani(adj.nbr.size(), 0.f);
     struct Cand { float pre; uint32_t j; uint64_t edge; };
-    std::vector<Cand> cands;
+    const size_t n_pc = pc_off.size() - 1;
 
-    // Two sweeps over the preclusters (they are independent of each other, so the order of the
-    // calculate_ani calls across preclusters is free): all representatives first, then all
-    // memberships -- between the two a table-driven caller learns which reverse-orientation values
-    // the membership sweep is going to ask for and can produce them in one batch.
-    std::vector<uint32_t> all_reps;               // representatives, precluster after precluster
-    std::vector<uint64_t> reps_off(1, 0);         // [n_preclusters + 1]
-    std::vector<std::pair<uint32_t, uint32_t>> joins;  // (cluster index within the precluster, genome), genome ascending
-    std::vector<uint64_t> cl_fill;
-    for (size_t pc = 0; pc + 1 < pc_off.size(); pc++) {
+    // Two sweeps over the preclusters: all representatives first, then all memberships -- between
+    // the two a table-driven caller learns which reverse-orientation values the membership sweep is
+    // going to ask for and can produce them in one batch.  Preclusters are independent of each other
+    // (the reference runs them on rayon threads, src/clusterer.rs:190-214): with ANI values served
+    // from tables (or skip_clusterer) the sweeps are split over the host threads; a caller-supplied
+    // calculate_ani callback is only ever invoked from the calling thread, in precluster order.
+    // A precluster's clusters partition its members, so precluster pc owns members[pc_off[pc] ..
+    // pc_off[pc + 1]) of the output and its representatives sit in the same range of rep_slot.
+    std::vector<uint32_t> rep_slot(n), n_reps_pc(n_pc, 0);
+    const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t n_threads = ((by_hit || skip_clusterer) && n_pc >= 4096) ? std::min<size_t>(hw, 16) : 1;
+    std::atomic<uint64_t> ani_calls{0};
+    auto sweep = [&](const std::function<void(size_t, std::vector<Cand> &, std::vector<std::pair<uint32_t, uint32_t>> &,
+                                              std::vector<uint64_t> &, uint64_t &)> &body) {
+        std::atomic<size_t> next{0};
+        auto run = [&] {
+            std::vector<Cand> cands;
+            std::vector<std::pair<uint32_t, uint32_t>> joins;
+            std::vector<uint64_t> cl_fill;
+            uint64_t calls = 0;
+            for (;;) {
+                const size_t p0 = next.fetch_add(256);
+                if (p0 >= n_pc) break;
+                for (size_t pc = p0; pc < std::min(n_pc, p0 + 256); pc++) body(pc, cands, joins, cl_fill, calls);
+            }
+            ani_calls.fetch_add(calls);
+        };
+        if (n_threads == 1) { run(); return; }
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < n_threads; t++) th.emplace_back(run);
+        for (auto &t : th) t.join();
+    };
+
+    // ---- representatives
+    sweep([&](size_t pc, std::vector<Cand> &cands, std::vector<std::pair<uint32_t, uint32_t>> &, std::vector<uint64_t> &,
+              uint64_t &calls) {
         const uint32_t *mb = pc_members.data() + pc_off[pc], *me = pc_members.data() + pc_off[pc + 1];
-        // ---- representatives
+        uint32_t n_reps = 0;
         for (const uint32_t *ip = mb; ip != me; ip++) {
             const uint32_t i = *ip;
             cands.clear();
@@ -205,7 +234,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                 bool some = true;
                 if (!skip_clusterer) {
                     some = by_hit ? (*by_hit)(c.j, i, adj.hit[c.edge], &ani) : calculate_ani_fn(c.j, i, &ani);
-                    out.ani_calls++;
+                    calls++;
                     if (some) { edge_state[c.edge] = 1; edge_ani[c.edge] = ani; }
                 }
                 if (some && ani >= ani_threshold) {
@@ -213,10 +242,13 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                     if (!skip_clusterer) break;  // find_any stops at the first hit
                 }
             }
-            if (rep) { is_rep[i] = 1; all_reps.push_back(i); }
+            if (rep) { is_rep[i] = 1; rep_slot[pc_off[pc] + n_reps++] = i; }
         }
-        reps_off.push_back(all_reps.size());
-    }
+        n_reps_pc[pc] = n_reps;
+    });
+    std::vector<uint64_t> cluster_base(n_pc + 1, 0);  // clusters before precluster pc
+    for (size_t pc = 0; pc < n_pc; pc++) cluster_base[pc + 1] = cluster_base[pc] + n_reps_pc[pc];
+
     if (prefetch_reverse && !skip_clusterer) {
         // what the membership sweep will ask for with the representative BEHIND the genome
         std::vector<size_t> want;
@@ -229,12 +261,17 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         }
         if (!want.empty() && (*prefetch_reverse)(want)) { err = "reverse-orientation ANI batch failed"; return 2; }
     }
-    for (size_t pc = 0; pc + 1 < pc_off.size(); pc++) {
+
+    // ---- memberships, written straight into the precluster's range of the output
+    out.members.assign(n, 0);
+    out.offsets.assign(cluster_base[n_pc] + 1, 0);
+    std::atomic<int64_t> orphan{-1};
+    sweep([&](size_t pc, std::vector<Cand> &, std::vector<std::pair<uint32_t, uint32_t>> &joins, std::vector<uint64_t> &cl_fill,
+              uint64_t &calls) {
         const uint32_t *mb = pc_members.data() + pc_off[pc], *me = pc_members.data() + pc_off[pc + 1];
-        const uint32_t *reps = all_reps.data() + reps_off[pc];
-        const size_t n_reps = reps_off[pc + 1] - reps_off[pc];
+        const uint32_t *reps = rep_slot.data() + pc_off[pc];
+        const size_t n_reps = n_reps_pc[pc];
         joins.clear();
-        // ---- memberships
         for (size_t c = 0; c < n_reps; c++) cluster_of_rep[reps[c]] = (uint32_t)c;
         for (const uint32_t *ip = mb; ip != me; ip++) {
             const uint32_t i = *ip;
@@ -253,17 +290,17 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                     else {
                         float ani = 0.f;
                         const bool some = by_hit ? (*by_hit)(r, i, adj.hit[x], &ani) : calculate_ani_fn(r, i, &ani);
-                        out.ani_calls++;
+                        calls++;
                         v = OptAni{some, ani};
                         edge_state[x] = some ? 1 : 2; edge_ani[x] = ani;
                     }
                 }
                 if (v.some && (!have_best || v.ani > best)) { have_best = true; best = v.ani; best_rep = r; }
             }
-            if (!have_best) {
-                err = "called `Option::unwrap()` on a `None` value (genome " + std::to_string(i) +
-                      " has no representative with an ANI; src/clusterer.rs:444)";
-                return 1;
+            if (!have_best) {  // the reference panics here; remember the first such genome
+                int64_t none = -1;
+                orphan.compare_exchange_strong(none, (int64_t)i);
+                return;
             }
             joins.emplace_back(cluster_of_rep[best_rep], i);
         }
@@ -271,16 +308,21 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         // members in ascending genome order (the order they were assigned in)
         cl_fill.assign(n_reps + 1, 0);
         for (const auto &jn : joins) cl_fill[jn.first + 1]++;
-        const uint64_t base = out.members.size();
+        const uint64_t base = pc_off[pc];
         for (size_t c = 0; c < n_reps; c++) cl_fill[c + 1] += cl_fill[c] + 1;  // +1: the representative
-        out.members.resize(base + cl_fill[n_reps]);
         for (size_t c = 0; c < n_reps; c++) {
             const uint64_t at = base + (c ? cl_fill[c] : 0);
             out.members[at] = reps[c];
-            out.offsets.push_back(base + cl_fill[c + 1]);
+            out.offsets[cluster_base[pc] + c + 1] = base + cl_fill[c + 1];
         }
         for (size_t c = n_reps; c-- > 0;) cl_fill[c + 1] = c ? cl_fill[c] + 1 : 1;  // next free slot after each representative
         for (const auto &jn : joins) out.members[base + cl_fill[jn.first + 1]++] = jn.second;
+    });
+    out.ani_calls = ani_calls.load();
+    if (orphan.load() >= 0) {
+        err = "called `Option::unwrap()` on a `None` value (genome " + std::to_string(orphan.load()) +
+              " has no representative with an ANI; src/clusterer.rs:444)";
+        return 1;
     }
     if (dbg) fprintf(stderr, "[engine] adjacency %.2f ms, preclusters %.2f ms, greedy %.2f ms\n", t1 - t0, t2 - t1, now() - t2);
     return 0;

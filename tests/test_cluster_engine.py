@@ -150,3 +150,41 @@ def test_ani_table_entry_matches_callback_entry():
         gb.cluster_from_ani_table(n, hits[::-1].copy(), ani, 95.0)
     empty, _ = gb.cluster_from_ani_table(3, hits[:0], ani[:0], 95.0)
     assert empty == [[0], [1], [2]]
+
+
+def test_threaded_sweeps_match_the_serial_engine():
+    """With ANI values served from tables the two sweeps run on the host threads (>= 4096 preclusters);
+    a Python callback keeps the serial path: both give the same clusters, order and call counts, also for
+    the two-orientation tables and for skip_clusterer."""
+    rng = np.random.default_rng(23)
+    n = 48_000
+    pairs = []
+    for base in range(0, n, 8):
+        for a in range(base, base + 8):
+            for b in range(a + 1, base + 8):
+                if rng.uniform() < 0.6:
+                    pairs.append((a, b, float(np.float32(rng.uniform(0.9, 1.0)))))
+    hits = make_hits(pairs)
+    fwd = np.round(rng.uniform(92.0, 100.0, len(hits)), 2).astype(np.float32)
+    rev = np.round(rng.uniform(92.0, 100.0, len(hits)), 2).astype(np.float32)
+    key = {(int(h["i"]), int(h["j"])): x for x, h in enumerate(hits)}
+
+    def f2(rep, g):
+        x = key[(min(rep, g), max(rep, g))]
+        return float(fwd[x] if rep < g else rev[x])
+    got, ginfo = gb.cluster_from_ani_tables(n, hits, fwd, rev, 95.0)
+    want, winfo = gb.cluster_from_distances(n, hits, 95.0, f2)
+    assert got == want and ginfo["ani_calls"] == winfo["ani_calls"]
+    assert ginfo["n_preclusters"] >= 4096
+    one, oinfo = gb.cluster_from_ani_table(n, hits, fwd, 95.0)
+    want1, w1info = gb.cluster_from_distances(n, hits, 95.0, lambda rep, g: float(fwd[key[(min(rep, g), max(rep, g))]]))
+    assert one == want1 and oinfo["ani_calls"] == w1info["ani_calls"]
+    pct = hits.copy()
+    pct["ani"] = fwd
+    skip, sinfo = gb.cluster_from_distances(n, pct, 95.0, None, skip_clusterer=True)
+    # blocks of 8 genomes are closed under the hits: the oracle (quadratic) checks the first 1,600 genomes
+    m = 1600
+    sub = pct[pct["j"] < m]
+    exp, _ = co.cluster(m, [(int(h["i"]), int(h["j"]), h["ani"]) for h in sub], 95.0, None, skip_clusterer=True)
+    assert [c for c in skip if c[0] < m] == exp and sinfo["ani_calls"] == 0
+    assert sorted(g for c in skip for g in c) == list(range(n))
