@@ -72,8 +72,11 @@ def ncu_traffic(kernel):
         t = json.load(f)
     if kernel not in t:
         return None
-    return {"bytes_per_launch": t[kernel]["dram_bytes_read"] + t[kernel]["dram_bytes_write"],
-            "captured_at": t[kernel].get("workload", t.get("workload"))}
+    out = {"bytes_per_launch": t[kernel]["dram_bytes_read"] + t[kernel]["dram_bytes_write"],
+           "captured_at": t[kernel].get("workload", t.get("workload"))}
+    if t[kernel].get("units_in_capture"):
+        out["bytes_per_unit"] = out["bytes_per_launch"] / t[kernel]["units_in_capture"]
+    return out
 
 
 class ClockSampler:
@@ -476,9 +479,14 @@ def main():
             "orientation of the pairs the membership pass asks for)")
         dom = max(fam, key=lambda f: f["ms_per_step"]) if fam else None
         roofline = None
+        dom_traffic = None
         if dom:
+            # measured DRAM bytes of the dominant kernel, scaled to the units this line's `achieved` covers
+            tr = ncu_traffic(dom["kernels"][0]) or {}
+            dom_traffic = tr["bytes_per_unit"] * dom["units_per_step"] if tr.get("bytes_per_unit") else tr.get("bytes_per_launch")
+            dom["dram_traffic"] = tr or None
             roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": dom["achieved_gbs"] / peak, "traffic": (ncu_traffic(dom["kernels"][0]) or {}).get("bytes_per_launch"),
+                        "frac": dom["achieved_gbs"] / peak, "traffic": dom_traffic,
                         "kernel": dom["family"] + " (" + ", ".join(dom["kernels"]) + ")", "kernel_ms": dom["ms_per_step"],
                         "share_of_step": dom["share_of_step"], "algorithmic_bytes_per_unit": dom["algorithmic_bytes_per_unit"],
                         "units_per_launch": dom["units_per_step"], "peak_source": peak_src,
@@ -599,10 +607,18 @@ def single_gpu_records(args, gb, torch, dev, d_seq, d_val, d_off, base_off, leng
         ms0, b0, m0, nc0 = time_k2(t2, c2, nd, 0, 5, 2)
         ms1, b1, m1, nc1 = time_k2(t2, c2, nd, 1, 3, 1)
         P = nd * (nd - 1) // 2
-        t0 = time.perf_counter()
-        cl, info = gb.cluster_packed(s2.data_ptr(), v2.data_ptr(), bo, ln, precluster_ani=MIN_ANI, ani=ANI_PCT,
-                                     min_aligned_fraction=MIN_AF, device=True, d_base_off=o2.data_ptr())
-        t_full = time.perf_counter() - t0
+        def two_stage(mode):
+            gb.cluster_lazy(mode)
+            try:
+                t0 = time.perf_counter()
+                c, i = gb.cluster_packed(s2.data_ptr(), v2.data_ptr(), bo, ln, precluster_ani=MIN_ANI, ani=ANI_PCT,
+                                         min_aligned_fraction=MIN_AF, device=True, d_base_off=o2.data_ptr())
+                return c, i, time.perf_counter() - t0
+            finally:
+                gb.cluster_lazy(-1)
+        two_stage(-1)  # warm-up (workspaces sized for this input)
+        cl, info, t_full = two_stage(-1)   # default: stage 2 in waves on a hit list this dense
+        cl_e, info_e, t_eager = two_stage(0)  # K3 on every precluster hit up front
         out["dense"] = {"workload": f"ONE clade: {nd} genomes x {L} bp derived from one founder at 0..2.5 % substitutions "
                                     "(every pair related; every block pair of the join is tie-dense)",
                         "pairs": P, "join_mode_ms": ms0, "join_kernel_ms": m0, "pairwise_mode_ms": ms1,
@@ -610,7 +626,13 @@ def single_gpu_records(args, gb, torch, dev, d_seq, d_val, d_off, base_off, leng
                         "candidates_join": nc0, "candidates_pairwise": nc1, "modes_agree": nc0 == nc1,
                         "two_stage_s": t_full, "two_stage_pairs_per_s": P / t_full, "prefilter_hits": int(info["n_precluster_hits"]),
                         "phases_ms": {k: info[k] for k in ("sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms")},
-                        "clusters": len(cl)}
+                        "clusters": len(cl), "stage2": "in waves: only the (representative, genome) pairs the reference's two "
+                        "passes evaluate (galah_b200_cluster_lazy, default on dense hit lists)",
+                        "ani_pairs_evaluated": int(info["n_ani_pairs"]), "ani_waves": int(info["ani_waves"]),
+                        "eager": {"two_stage_s": t_eager, "two_stage_pairs_per_s": P / t_eager,
+                                  "ani_pairs_evaluated": int(info_e["n_ani_pairs"]),
+                                  "phases_ms": {k: info_e[k] for k in ("sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms")},
+                                  "clusters_identical": bool(cl == cl_e)}}
         del s2, v2, o2, t2, c2
 
     if not args.no_ingest:

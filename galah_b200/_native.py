@@ -40,11 +40,13 @@ class ClusterStats(ctypes.Structure):
     _fields_ = [("n_precluster_hits", ctypes.c_uint64), ("n_ani_pairs", ctypes.c_uint64),
                 ("ani_chain_ms", ctypes.c_float), ("ingest_ms", ctypes.c_float), ("sketch_ms", ctypes.c_float),
                 ("index_ms", ctypes.c_float), ("prefilter_ms", ctypes.c_float), ("ani_ms", ctypes.c_float),
-                ("engine_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
+                ("engine_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("ani_waves", ctypes.c_uint32)]
 
 
 ANI_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
                           ctypes.POINTER(ctypes.c_float))
+ANI_BATCH_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                                ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_float))
 
 _lib = None
 
@@ -123,6 +125,10 @@ _SIGNATURES = {
     "galah_b200_cluster_from_distances": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p,
                                                          ctypes.c_size_t, ctypes.c_int, ctypes.c_float,
                                                          ANI_FN, vp, ctypes.POINTER(Clusters)]),
+    "galah_b200_cluster_from_distances_batched": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                                                 ctypes.c_float, ANI_BATCH_FN, vp, ctypes.c_uint32,
+                                                                 ctypes.POINTER(Clusters), ctypes.POINTER(ctypes.c_uint32)]),
+    "galah_b200_cluster_lazy": (ctypes.c_int, [ctypes.c_int]),
     "galah_b200_clusters_free": (None, [ctypes.POINTER(Clusters)]),
     "galah_b200_cluster_files": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                                 ctypes.c_int, ctypes.c_int, ctypes.POINTER(Clusters),

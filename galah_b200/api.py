@@ -384,6 +384,48 @@ def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, s
     return _take_clusters(res)
 
 
+def cluster_from_distances_batched(n_genomes, hits, ani_threshold, calculate_ani_batch, max_waves=0):
+    """The clustering engine with stage 2 asked for in waves: `calculate_ani_batch(reps, genomes)` gets two
+    uint32 arrays (reps[x] is the query) and returns one float or None per pair.  Same clusters, order and
+    ani_calls as cluster_from_distances; info["ani_waves"] = batches asked."""
+    hits = np.ascontiguousarray(hits, PAIR_DTYPE)
+    calls = {"exc": None}
+
+    def _cb(_ctx, reps, genomes, n, some, ani):
+        try:
+            r = np.ctypeslib.as_array(reps, shape=(n,)).copy()
+            g = np.ctypeslib.as_array(genomes, shape=(n,)).copy()
+            vals = calculate_ani_batch(r, g)
+            if len(vals) != n:
+                raise ValueError("calculate_ani_batch: one value per pair")
+            for x, v in enumerate(vals):
+                some[x] = 0 if v is None else 1
+                ani[x] = 0.0 if v is None else float(v)
+        except BaseException as e:  # never unwind through C
+            calls["exc"] = e
+            return 1
+        return 0
+
+    cb = _native.ANI_BATCH_FN(_cb)
+    res = _native.Clusters()
+    waves = ctypes.c_uint32(0)
+    rc = lib().galah_b200_cluster_from_distances_batched(int(n_genomes), hits.ctypes.data, len(hits), ctypes.c_float(ani_threshold),
+                                                         cb, None, int(max_waves), ctypes.byref(res), ctypes.byref(waves))
+    if calls["exc"] is not None or rc:
+        lib().galah_b200_clusters_free(ctypes.byref(res))
+        if calls["exc"] is not None:
+            raise calls["exc"]
+        check(rc)
+    clusters, info = _take_clusters(res)
+    info["ani_waves"] = int(waves.value)
+    return clusters, info
+
+
+def cluster_lazy(mode):
+    """Stage 2 of the one-call pipelines: 0 = every precluster hit up front, 1 = in waves, -1 = by hit density (default)."""
+    check(lib().galah_b200_cluster_lazy(int(mode)))
+
+
 def cluster_from_ani_table(n_genomes, hits, ani, ani_threshold):
     """The clustering engine with calculate_ani served from a table: ani[x] (percent) belongs to
     hits[x]; hits sorted by (i, j) -- the batched form the Rust shim uses."""
@@ -497,7 +539,8 @@ def cluster_multi(genomes, n_devices, precluster_ani=0.9, ani=95.0, min_aligned_
 
 
 def _stats_dict(stats):
-    d = {"n_precluster_hits": int(stats.n_precluster_hits), "n_ani_pairs": int(stats.n_ani_pairs)}
+    d = {"n_precluster_hits": int(stats.n_precluster_hits), "n_ani_pairs": int(stats.n_ani_pairs),
+         "ani_waves": int(stats.ani_waves)}
     for f in ("ani_chain_ms", "ingest_ms", "sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms", "total_ms"):
         d[f] = float(getattr(stats, f))
     return d

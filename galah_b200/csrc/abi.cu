@@ -179,10 +179,26 @@ struct CandFinisher {
         for (size_t x = 0; x < n_cand; x++)
             if (keep[x]) res[fill[c[x].x]++] = galah_b200_pair_t{c[x].x, c[x].y, c[x].z, c[x].w, ani[x]};
         auto by_j = [](const galah_b200_pair_t &a, const galah_b200_pair_t &b) { return a.j < b.j; };
-        for (size_t r = 0; r + 1 < row_start.size(); r++) {
-            galah_b200_pair_t *b = res + row_start[r], *e = res + row_start[r + 1];
-            if (e - b > 1 && !std::is_sorted(b, e, by_j)) std::sort(b, e, by_j);
-        }
+        // rows arrive in the order the kernel's CTAs appended them: sort each by j (rows are independent:
+        // long lists -- dense collections -- are split over the host threads, 64 rows at a time)
+        const size_t n_rows = row_start.size() - 1;
+        std::atomic<size_t> next_row{0};
+        auto sort_rows = [&] {
+            for (;;) {
+                const size_t r0 = next_row.fetch_add(64);
+                if (r0 >= n_rows) break;
+                for (size_t r = r0; r < std::min(n_rows, r0 + 64); r++) {
+                    galah_b200_pair_t *b = res + row_start[r], *e = res + row_start[r + 1];
+                    if (e - b > 1 && !std::is_sorted(b, e, by_j)) std::sort(b, e, by_j);
+                }
+            }
+        };
+        const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
+        const size_t nt = n_pass >= (1u << 17) ? std::min<size_t>(hw, 16) : 1;
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(sort_rows);
+        sort_rows();
+        for (auto &t : th) t.join();
         *out = res; *n_out = n_pass;
         return 0;
     }
@@ -1232,7 +1248,8 @@ int galah_b200_ani_last_timing(const galah_b200_ani_index_t *idx, float *build_m
 static int cluster_engine_call(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits, int skip_clusterer,
                                float ani_threshold, galah_b200_ani_fn calculate_ani, void *ctx,
                                const AniByHitFn *by_hit, galah_b200_clusters_t *out,
-                               const ReversePrefetchFn *prefetch_reverse = nullptr) {
+                               const ReversePrefetchFn *prefetch_reverse = nullptr, const AniBatchFn *batch = nullptr,
+                               uint32_t max_waves = 16, uint32_t *waves_out = nullptr) {
     if (!out) { set_error("cluster: out is NULL"); return GALAH_B200_ERR_ARG; }
     memset(out, 0, sizeof(*out));
     std::vector<PreclusterHit> h(n_hits);
@@ -1244,10 +1261,12 @@ static int cluster_engine_call(size_t n_genomes, const galah_b200_pair_t *hits, 
         };
     ClusterResult res;
     std::string err;
-    if (cluster_from_hits(n_genomes, h.data(), n_hits, skip_clusterer != 0, ani_threshold, fn, res, err, by_hit, prefetch_reverse)) {
+    if (cluster_from_hits(n_genomes, h.data(), n_hits, skip_clusterer != 0, ani_threshold, fn, res, err, by_hit, prefetch_reverse,
+                          batch, max_waves)) {
         set_error("cluster: " + err);
         return GALAH_B200_ERR_UNSUPPORTED;
     }
+    if (waves_out) *waves_out = res.ani_waves;
     out->n_clusters = res.offsets.size() - 1;
     out->members = (uint32_t *)malloc(std::max<size_t>(res.members.size(), 1) * sizeof(uint32_t));
     out->offsets = (uint64_t *)malloc(res.offsets.size() * sizeof(uint64_t));
@@ -1265,6 +1284,28 @@ int galah_b200_cluster_from_distances(size_t n_genomes, const galah_b200_pair_t 
                                       galah_b200_ani_fn calculate_ani, void *ctx,
                                       galah_b200_clusters_t *out) {
     return cluster_engine_call(n_genomes, hits, n_hits, skip_clusterer, ani_threshold, calculate_ani, ctx, nullptr, out);
+}
+
+int galah_b200_cluster_from_distances_batched(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                              float ani_threshold, galah_b200_ani_batch_fn calculate_ani_batch, void *ctx,
+                                              uint32_t max_waves, galah_b200_clusters_t *out, uint32_t *n_waves) {
+    if (!calculate_ani_batch) { set_error("cluster_from_distances_batched: NULL callback"); return GALAH_B200_ERR_ARG; }
+    std::vector<uint32_t> reps, genomes;
+    const AniBatchFn batch = [&](const std::vector<AniRequest> &reqs, uint8_t *some, float *ani) -> int {
+        reps.resize(reqs.size()); genomes.resize(reqs.size());
+        for (size_t q = 0; q < reqs.size(); q++) { reps[q] = reqs[q].rep; genomes[q] = reqs[q].genome; }
+        return calculate_ani_batch(ctx, reps.data(), genomes.data(), reqs.size(), some, ani);
+    };
+    return cluster_engine_call(n_genomes, hits, n_hits, 0, ani_threshold, nullptr, nullptr, nullptr, out, nullptr, &batch,
+                               max_waves ? max_waves : 16, n_waves);
+}
+
+// -1: by the density of the hit list (default), 0: every precluster hit evaluated up front, 1: in waves
+static std::atomic<int> g_lazy_mode{-1};
+int galah_b200_cluster_lazy(int mode) {
+    if (mode < -1 || mode > 1) { set_error("cluster_lazy: mode must be -1 (auto), 0 (eager) or 1 (waves)"); return GALAH_B200_ERR_ARG; }
+    g_lazy_mode.store(mode);
+    return 0;
 }
 
 // ANI of hit pairs served from a table (hits sorted by (i, j), ani[x] belongs to hits[x]).
@@ -1336,6 +1377,42 @@ static int cluster_from_resident(const uint64_t *d_table, const uint32_t *d_coun
     if (int rc = run_prefilter(d_table, d_counts, n, s, k, precluster_min_ani, 0, 1, st, &hits, &n_hits)) return rc;
     struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
     const double t1 = now_ms();
+    // Dense hit lists (collections of near-identical genomes, galah's stated use case): stage 2 in waves --
+    // only the (representative, genome) pairs the reference's two passes evaluate, a batch per wave, all
+    // preclusters together.  Sparse lists: one launch over every hit (+ one for the reverse orientations)
+    // is cheaper than the waves' round trips.  Same clusters either way.
+    const int lazy_mode = g_lazy_mode.load();
+    if (lazy_mode == 1 || (lazy_mode < 0 && n_hits >= 16 * n)) {
+        double ani_ms = 0.0;
+        float chain_ms = 0.f;
+        size_t n_asked = 0;
+        std::vector<uint32_t> qp;
+        std::vector<AniPairResult> qres;
+        const AniBatchFn batch = [&](const std::vector<AniRequest> &reqs, uint8_t *some, float *ani) -> int {
+            const double ta = now_ms();
+            qp.resize(2 * reqs.size()); qres.resize(reqs.size());
+            // calculate_ani(fasta1 = representative, fasta2 = genome): the representative is the query
+            for (size_t q = 0; q < reqs.size(); q++) { qp[2 * q] = reqs[q].rep; qp[2 * q + 1] = reqs[q].genome; }
+            if (int rc2 = index.pairs(qp.data(), reqs.size(), min_af_pct, false, qres.data(), st)) return rc2;
+            for (size_t q = 0; q < reqs.size(); q++) { some[q] = 1; ani[q] = qres[q].ani; }  // skani never yields None (src/skani.rs:760)
+            chain_ms += index.last_chain_ms;
+            n_asked += reqs.size();
+            ani_ms += now_ms() - ta;
+            return 0;
+        };
+        uint32_t waves = 0;
+        int rc = cluster_engine_call(n, hits, n_hits, 0, ani_threshold_pct, nullptr, nullptr, nullptr, out, nullptr, &batch, 16, &waves);
+        const double t3 = now_ms();
+        if (getenv("GALAH_B200_DEBUG"))
+            fprintf(stderr, "[cluster_from_resident] prefilter %.2f ms, ani in %u waves %.2f ms (%zu of %zu hit pairs), engine %.2f ms\n",
+                    t1 - t0, waves, ani_ms, n_asked, n_hits, (t3 - t1) - ani_ms);
+        if (stats) {
+            stats->n_precluster_hits = n_hits; stats->n_ani_pairs = n_asked; stats->ani_chain_ms = chain_ms;
+            stats->prefilter_ms = (float)(t1 - t0); stats->ani_ms = (float)ani_ms; stats->engine_ms = (float)((t3 - t1) - ani_ms);
+            stats->ani_waves = waves;
+        }
+        return rc;
+    }
     // stage 2 for every precluster hit (a superset of what the reference's find_any evaluates;
     // the greedy decisions only ever read values of hit pairs, so the clusters are the same);
     // query = the lower index: galah passes the representative first (src/clusterer.rs:262-296)

@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <new>
 #include <numeric>
 #include <thread>
 
@@ -53,11 +54,34 @@ struct Dsu {
     }
 };
 
+// Edge arrays are written exactly once right after they are sized: plain buffers that are not cleared
+// first (a vector's resize touches every page a second time; at millions of hits that is the cost).
+template <typename T>
+struct RawBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf &) = delete;
+    RawBuf &operator=(const RawBuf &) = delete;
+    ~RawBuf() { free(p); }
+    void resize(size_t count, bool zero = false) {
+        free(p);
+        n = count;
+        p = (T *)(zero ? calloc(std::max<size_t>(count, 1), sizeof(T)) : malloc(std::max<size_t>(count, 1) * sizeof(T)));
+        if (!p) throw std::bad_alloc();
+    }
+    size_t size() const { return n; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t x) { return p[x]; }
+    const T &operator[](size_t x) const { return p[x]; }
+};
+
 struct Adjacency {  // CSR over both directions, neighbours ascending
     std::vector<uint64_t> off;
-    std::vector<uint32_t> nbr;
-    std::vector<float> ani;
-    std::vector<uint32_t> hit;  // index of the precluster hit behind the slot
+    RawBuf<uint32_t> nbr;
+    RawBuf<float> ani;
+    RawBuf<uint32_t> hit;  // index of the precluster hit behind the slot
     // index of (a, b) in nbr/ani, or -1
     int64_t find(uint32_t a, uint32_t b) const {
         const uint32_t *lo = nbr.data() + off[a], *hi = nbr.data() + off[a + 1];
@@ -76,7 +100,8 @@ struct OptAni { bool some; float ani; };
 
 int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool skip_clusterer,
                       float ani_threshold, const AniFn &calculate_ani_fn, ClusterResult &out,
-                      std::string &err, const AniByHitFn *by_hit, const ReversePrefetchFn *prefetch_reverse) {
+                      std::string &err, const AniByHitFn *by_hit, const ReversePrefetchFn *prefetch_reverse,
+                      const AniBatchFn *batch, uint32_t max_waves) {
     out = ClusterResult();
     out.offsets.push_back(0);
     const bool dbg = getenv("GALAH_B200_DEBUG") != nullptr;
@@ -93,7 +118,8 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
             return 1;
         }
     }
-    if (!skip_clusterer && !calculate_ani_fn && !by_hit) { err = "calculate_ani callback required"; return 1; }
+    if (!skip_clusterer && !calculate_ani_fn && !by_hit && !batch) { err = "calculate_ani callback required"; return 1; }
+    const bool lazy = batch && !skip_clusterer;
 
     // ---- adjacency (later duplicates of a key overwrite earlier ones, as BTreeMap::insert does)
     Adjacency adj;
@@ -105,33 +131,35 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         bool sorted = true;
         for (size_t h = 1; h < n_hits && sorted; h++)
             sorted = pair_key(hits[h - 1].i, hits[h - 1].j) < pair_key(hits[h].i, hits[h].j);
-        std::vector<std::pair<uint64_t, uint32_t>> uniq;  // (key, index of the last hit with that key)
-        if (sorted) {
-            uniq.resize(n_hits);
-            for (size_t h = 0; h < n_hits; h++) uniq[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
-        } else {
+        std::vector<uint32_t> uniq;  // indices of the hits that count, ascending by key (unsorted input only)
+        if (!sorted) {
             uniq.reserve(n_hits);
             std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
             for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
             std::stable_sort(keyed.begin(), keyed.end(),
                              [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &b) { return a.first < b.first; });
             for (size_t h = 0; h < n_hits; h++)
-                if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.emplace_back(keyed[h].first, keyed[h].second);
+                if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.push_back(keyed[h].second);
         }
-        for (const auto &kv : uniq) {
-            adj.off[(uint32_t)(kv.first >> 32) + 1]++;
-            adj.off[(uint32_t)kv.first + 1]++;
+        const size_t n_uniq = sorted ? n_hits : uniq.size();
+        auto hit_at = [&](size_t u) -> uint32_t { return sorted ? (uint32_t)u : uniq[u]; };
+        for (size_t u = 0; u < n_uniq; u++) {
+            const PreclusterHit &h = hits[hit_at(u)];
+            adj.off[std::min(h.i, h.j) + 1]++;
+            adj.off[std::max(h.i, h.j) + 1]++;
         }
         for (size_t g = 0; g < n; g++) adj.off[g + 1] += adj.off[g];
         adj.nbr.resize(adj.off[n]); adj.ani.resize(adj.off[n]); adj.hit.resize(adj.off[n]);
         std::vector<uint64_t> fill(adj.off.begin(), adj.off.end() - 1);
         // keys ascend, so every row receives its neighbours in ascending order: first the smaller
         // partners (as the second genome of earlier keys), then the larger ones
-        for (const auto &kv : uniq) {
-            const uint32_t a = (uint32_t)(kv.first >> 32), b = (uint32_t)kv.first;
-            const float v = hits[kv.second].ani;
-            adj.nbr[fill[a]] = b; adj.ani[fill[a]] = v; adj.hit[fill[a]++] = kv.second;
-            adj.nbr[fill[b]] = a; adj.ani[fill[b]] = v; adj.hit[fill[b]++] = kv.second;
+        for (size_t u = 0; u < n_uniq; u++) {
+            const uint32_t x = hit_at(u);
+            const PreclusterHit &h = hits[x];
+            const uint32_t a = std::min(h.i, h.j), b = std::max(h.i, h.j);
+            const uint64_t pa = fill[a]++, pb = fill[b]++;
+            adj.nbr[pa] = b; adj.ani[pa] = h.ani; adj.hit[pa] = x;
+            adj.nbr[pb] = a; adj.ani[pb] = h.ani; adj.hit[pb] = x;
         }
     }
 
@@ -177,8 +205,10 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     std::vector<uint32_t> cluster_of_rep(n, 0);
     // clusterer cache (src/clusterer.rs:236-239, 398-405), one slot per adjacency edge: a pair is
     // only ever looked up from the row of the genome being placed, so the edge index is its key
-    std::vector<uint8_t> edge_state(adj.nbr.size(), 0);  // 0 = not computed, 1 = Some(ani), 2 = None
-    std::vector<float> edge_ani(adj.nbr.size(), 0.f);
+    RawBuf<uint8_t> edge_state;  // 0 = not computed, 1 = Some(ani), 2 = None
+    RawBuf<float> edge_ani;      // read only where edge_state says computed
+    edge_state.resize(adj.nbr.size(), true);
+    edge_ani.resize(adj.nbr.size());
     struct Cand { float pre; uint32_t j; uint64_t edge; };
     const size_t n_pc = pc_off.size() - 1;
 
@@ -192,7 +222,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     // pc_off[pc + 1]) of the output and its representatives sit in the same range of rep_slot.
     std::vector<uint32_t> rep_slot(n), n_reps_pc(n_pc, 0);
     const size_t hw = std::max<size_t>(1, std::thread::hardware_concurrency());
-    const size_t n_threads = ((by_hit || skip_clusterer) && n_pc >= 4096) ? std::min<size_t>(hw, 16) : 1;
+    const size_t n_threads = ((by_hit || skip_clusterer || lazy) && n_pc >= 4096) ? std::min<size_t>(hw, 16) : 1;
     std::atomic<uint64_t> ani_calls{0};
     auto sweep = [&](const std::function<void(size_t, std::vector<Cand> &, std::vector<std::pair<uint32_t, uint32_t>> &,
                                               std::vector<uint64_t> &, uint64_t &)> &body) {
@@ -215,7 +245,126 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         for (auto &t : th) t.join();
     };
 
-    // ---- representatives
+    // ---- representatives, lazily in waves (AniBatchFn): all preclusters at once.
+    // state: 0 open, 1 representative, 2 member.  pending[g] = hit partners below g that are not settled
+    // towards g yet: a lower partner settles when it becomes a member, or -- a representative -- when its
+    // ANI with g has been applied.  An open genome whose pending count reaches zero without having been
+    // claimed (ANI >= threshold with a representative below it) is a representative: exactly
+    // src/clusterer.rs:216-259, where genome i is tested against the representatives found before it.
+    // Every request is a pair the reference evaluates too: (representative, partner) for every partner
+    // that is not an earlier representative (tested in the representative pass if the partner comes
+    // later and was still undecided, asked for by the membership pass otherwise).
+    bool any_none = false;
+    if (lazy) {
+        std::vector<uint8_t> state(n, 0);
+        std::vector<uint32_t> pending(n, 0), fresh, ready, claimed;
+        for (uint32_t g = 0; g < n; g++) {
+            for (uint64_t x = adj.off[g]; x < adj.off[g + 1] && adj.nbr[x] < g; x++) pending[g]++;
+            if (!pending[g]) { state[g] = 1; fresh.push_back(g); }
+        }
+        std::vector<AniRequest> reqs;
+        std::vector<uint64_t> slot;  // per request: the edge slot in the GENOME's row (the cache key)
+        std::vector<uint8_t> some;
+        std::vector<float> ani;
+        uint64_t calls = 0;
+        auto ask = [&]() -> int {
+            if (reqs.empty()) return 0;
+            some.assign(reqs.size(), 0); ani.assign(reqs.size(), 0.f);
+            if ((*batch)(reqs, some.data(), ani.data())) { err = "ANI batch failed"; return 2; }
+            out.ani_waves++;
+            calls += reqs.size();
+            for (size_t q = 0; q < reqs.size(); q++) {
+                edge_state[slot[q]] = some[q] ? 1 : 2; edge_ani[slot[q]] = ani[q];
+                any_none = any_none || !some[q];
+            }
+            return 0;
+        };
+        uint32_t waves = 0;
+        while (!fresh.empty() && waves < max_waves) {
+            waves++;
+            reqs.clear(); slot.clear();
+            for (const uint32_t r : fresh)
+                for (uint64_t y = adj.off[r]; y < adj.off[r + 1]; y++) {
+                    const uint32_t i = adj.nbr[y];
+                    if (state[i] == 1) continue;  // an earlier representative: (i, r) was asked for when i was confirmed
+                    reqs.push_back(AniRequest{r, i, adj.hit[y]});
+                    slot.push_back((uint64_t)adj.find(i, r));  // the same edge in i's row
+                }
+            if (int rc = ask()) return rc;
+            ready.clear(); claimed.clear();
+            for (size_t q = 0; q < reqs.size(); q++) {
+                const uint32_t r = reqs[q].rep, i = reqs[q].genome;
+                if (i < r) continue;  // a member below the representative: only its membership needs the value
+                if (state[i] == 0 && some[q] && ani[q] >= ani_threshold) { state[i] = 2; claimed.push_back(i); }
+                if (--pending[i] == 0) ready.push_back(i);
+            }
+            for (const uint32_t m : claimed)
+                for (uint64_t y = adj.off[m + 1]; y-- > adj.off[m] && adj.nbr[y] > m;)
+                    if (--pending[adj.nbr[y]] == 0) ready.push_back(adj.nbr[y]);
+            fresh.clear();
+            for (const uint32_t g : ready)
+                if (state[g] == 0) { state[g] = 1; fresh.push_back(g); }
+        }
+        if (!fresh.empty()) {
+            // wave budget spent (long chains of mutually distant genomes): everything the undecided genomes
+            // can still ask about in ONE batch -- the pairs of the representatives confirmed last, and for
+            // every open genome its open partners below it --, then the undecided genomes are settled in index order
+            reqs.clear(); slot.clear();
+            for (const uint32_t r : fresh)
+                for (uint64_t y = adj.off[r]; y < adj.off[r + 1]; y++) {
+                    const uint32_t i = adj.nbr[y];
+                    if (state[i] == 1) continue;
+                    reqs.push_back(AniRequest{r, i, adj.hit[y]});
+                    slot.push_back((uint64_t)adj.find(i, r));  // the same edge in i's row
+                }
+            for (uint32_t i = 0; i < n; i++) {
+                if (state[i] != 0) continue;
+                for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
+                    if (state[adj.nbr[x]] == 0) { reqs.push_back(AniRequest{adj.nbr[x], i, adj.hit[x]}); slot.push_back(x); }
+            }
+            if (int rc = ask()) return rc;
+            for (uint32_t i = 0; i < n; i++) {
+                if (state[i] != 0) continue;
+                state[i] = 1;
+                for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
+                    if (state[adj.nbr[x]] == 1 && edge_state[x] == 1 && edge_ani[x] >= ani_threshold) { state[i] = 2; break; }
+            }
+        }
+        // what the membership sweep reads and nobody asked for yet (only after the one-batch finish)
+        reqs.clear(); slot.clear();
+        for (uint32_t i = 0; i < n; i++) {
+            if (state[i] != 2) continue;
+            for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++)
+                if (state[adj.nbr[x]] == 1 && !edge_state[x]) { reqs.push_back(AniRequest{adj.nbr[x], i, adj.hit[x]}); slot.push_back(x); }
+        }
+        if (int rc = ask()) return rc;
+        for (size_t pc = 0; pc < n_pc; pc++) {
+            uint32_t n_reps = 0;
+            for (uint64_t m = pc_off[pc]; m < pc_off[pc + 1]; m++) {
+                const uint32_t g = pc_members[m];
+                if (state[g] == 0) { err = "wave engine left genome " + std::to_string(g) + " undecided"; return 3; }
+                if (state[g] == 1) { is_rep[g] = 1; rep_slot[pc_off[pc] + n_reps++] = g; }
+            }
+            n_reps_pc[pc] = n_reps;
+        }
+        if (any_none) {
+            // the reference caches only Some(ani) in its representative pass, so a None met there before the
+            // first passing representative is computed again by the membership pass (src/clusterer.rs:236-239, 398-405)
+            std::vector<Cand> cands;
+            for (uint32_t i = 0; i < n; i++) {
+                if (is_rep[i]) continue;
+                cands.clear();
+                for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
+                    if (is_rep[adj.nbr[x]]) cands.push_back(Cand{adj.ani[x], adj.nbr[x], x});
+                std::stable_sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.pre < b.pre; });
+                for (const auto &c : cands) {
+                    if (edge_state[c.edge] == 2) calls++;
+                    else if (edge_ani[c.edge] >= ani_threshold) break;
+                }
+            }
+        }
+        ani_calls.fetch_add(calls);
+    } else
     sweep([&](size_t pc, std::vector<Cand> &cands, std::vector<std::pair<uint32_t, uint32_t>> &, std::vector<uint64_t> &,
               uint64_t &calls) {
         const uint32_t *mb = pc_members.data() + pc_off[pc], *me = pc_members.data() + pc_off[pc + 1];
@@ -249,7 +398,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     std::vector<uint64_t> cluster_base(n_pc + 1, 0);  // clusters before precluster pc
     for (size_t pc = 0; pc < n_pc; pc++) cluster_base[pc + 1] = cluster_base[pc] + n_reps_pc[pc];
 
-    if (prefetch_reverse && !skip_clusterer) {
+    if (prefetch_reverse && !skip_clusterer && !lazy) {
         // what the membership sweep will ask for with the representative BEHIND the genome
         std::vector<size_t> want;
         for (uint32_t i = 0; i < n; i++) {
@@ -287,6 +436,7 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
                     v = OptAni{true, adj.ani[x]};
                 } else {
                     if (edge_state[x]) v = OptAni{edge_state[x] == 1, edge_ani[x]};
+                    else if (lazy) { v = OptAni{false, 0.f}; }  // cannot happen: the waves asked for every such pair
                     else {
                         float ani = 0.f;
                         const bool some = by_hit ? (*by_hit)(r, i, adj.hit[x], &ani) : calculate_ani_fn(r, i, &ani);

@@ -301,6 +301,28 @@ int galah_b200_cluster_from_ani_table(size_t n_genomes, const galah_b200_pair_t 
 int galah_b200_cluster_from_ani_tables(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
                                        const float *ani_fwd, const float *ani_rev, float ani_threshold,
                                        galah_b200_clusters_t *out);
+/* The same engine with stage 2 asked for in BATCHES (what a GPU backend wants): the engine works out
+ * in waves which (representative, genome) pairs the reference's two passes evaluate
+ * (src/clusterer.rs:216-300, 350-449) -- every precluster hit of a representative with a genome that is
+ * not an earlier representative -- and hands them to calculate_ani_batch, all preclusters together;
+ * wave w holds the pairs of the representatives confirmed by wave w - 1.  For a collection of
+ * near-identical genomes that is (representatives x genomes) evaluations instead of one per hit.
+ * The callback fills some[x] (0 = None) and ani[x] for the n pairs (reps[x] is the QUERY, as
+ * calculate_ani(fasta1, fasta2) makes fasta1, src/skani.rs:733-744) and returns 0, or non-zero to
+ * abort.  After max_waves waves (0: 16) everything the undecided genomes can still ask for goes
+ * out as one batch.  Clusters, their order and ani_calls equal galah_b200_cluster_from_distances'
+ * (ani_calls as long as the wave budget holds).  *n_waves (optional): callback invocations. */
+typedef int (*galah_b200_ani_batch_fn)(void *ctx, const uint32_t *reps, const uint32_t *genomes, size_t n,
+                                       uint8_t *some, float *ani);
+int galah_b200_cluster_from_distances_batched(size_t n_genomes, const galah_b200_pair_t *hits, size_t n_hits,
+                                              float ani_threshold, galah_b200_ani_batch_fn calculate_ani_batch,
+                                              void *ctx, uint32_t max_waves, galah_b200_clusters_t *out,
+                                              uint32_t *n_waves);
+/* How the one-call pipelines (galah_b200_cluster_files / _packed*) run stage 2: 0 = K3 on every
+ * precluster hit up front (+ one launch for the reverse orientations the membership pass needs),
+ * 1 = in waves as above, -1 (default) = waves when the hit list is dense (>= 16 hits per genome).
+ * The clusters are the same in every mode. */
+int galah_b200_cluster_lazy(int mode);
 void galah_b200_clusters_free(galah_b200_clusters_t *c);
 
 /* The whole hot path: galah::clusterer::cluster(genomes, &FinchPreclusterer{min_ani:
@@ -317,6 +339,7 @@ typedef struct galah_b200_cluster_stats {
     /* host wall clock of the call's phases (ms): ingest = read/upload + K0 + K1 + K3 index;
      * sketch_ms / index_ms = device time of K1 / the K3 index build inside it (packed entries) */
     float ingest_ms, sketch_ms, index_ms, prefilter_ms, ani_ms, engine_ms, total_ms;
+    uint32_t ani_waves;   /* stage-2 batches when it ran in waves (galah_b200_cluster_lazy), else 0 */
 } galah_b200_cluster_stats_t;
 int galah_b200_cluster_files(const char *const *paths, size_t n, float precluster_min_ani,
                              float ani_threshold_pct, float min_af_pct, int small_genomes,

@@ -188,3 +188,81 @@ def test_threaded_sweeps_match_the_serial_engine():
     exp, _ = co.cluster(m, [(int(h["i"]), int(h["j"]), h["ani"]) for h in sub], 95.0, None, skip_clusterer=True)
     assert [c for c in skip if c[0] < m] == exp and sinfo["ani_calls"] == 0
     assert sorted(g for c in skip for g in c) == list(range(n))
+
+
+def _batch_of(f, log=None):
+    def batch(reps, genomes):
+        if log is not None:
+            log.append(list(zip(reps.tolist(), genomes.tolist())))
+        return [f(int(r), int(g)) for r, g in zip(reps, genomes)]
+    return batch
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_wave_engine_matches_serial_engine_and_oracle(seed):
+    """galah_b200_cluster_from_distances_batched (stage 2 asked for in waves) == the callback engine == the
+    Python restatement: clusters, order, ani_calls -- with orientation-dependent values, ties at the threshold
+    and Nones; every pair is asked for once, with the representative as the query; also when the wave budget
+    runs out (max_waves 1, 2, 3: the one-batch finish)."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 90))
+    fam = rng.integers(0, max(1, n // 6), size=n)
+    pairs, ani2 = [], {}
+    p_none = 0.0 if seed % 2 else 0.06
+    for i in range(n):
+        for j in range(i + 1, n):
+            if rng.uniform() < (0.8 if fam[i] == fam[j] else 0.02):
+                pairs.append((i, j, float(np.float32(rng.uniform(0.9, 1.0)))))
+            for key in ((i, j), (j, i)):
+                ani2[key] = rng.choice([None, 94.0, 95.0, 96.5, 99.0, float(np.float32(rng.uniform(90, 100)))],
+                                       p=[p_none, 0.2 - p_none, 0.2, 0.2, 0.1, 0.3])
+    hits = make_hits(pairs)
+    f = lambda rep, g: ani2[(rep, g)]
+    try:
+        exp, einfo = co.cluster(n, pairs, 95.0, f)
+    except RuntimeError:
+        with pytest.raises(gb.GalahB200Error) as e:
+            gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(f))
+        assert "Option::unwrap()" in str(e.value)
+        return
+    serial, sinfo = gb.cluster_from_distances(n, hits, 95.0, f)
+    log = []
+    got, info = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(f, log))
+    assert got == serial == exp
+    assert info["ani_calls"] == sinfo["ani_calls"] == einfo["ani_calls"]
+    assert info["ani_waves"] == len(log)
+    asked = [p for wave in log for p in wave]
+    hit_set = {(i, j) for i, j, _ in pairs}
+    assert len(asked) == len(set(asked)) and all((min(p), max(p)) in hit_set for p in asked)
+    reps = {c[0] for c in got}
+    assert all(r in reps for r, _ in asked)  # the query is always a representative
+    for w in (1, 2, 3):
+        short, winfo = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(f), max_waves=w)
+        assert short == exp and winfo["ani_waves"] <= w + 2
+
+
+def test_wave_engine_on_one_clade_asks_for_representatives_only():
+    """One clade of 600 genomes, every pair a precluster hit (179,700 hits), everything within the threshold of
+    genome 0: the reference evaluates 599 pairs (genome 0 against everybody), and so do the waves -- in one batch."""
+    n = 600
+    pairs = [(a, b, 0.99) for a in range(n) for b in range(a + 1, n)]
+    hits = make_hits(pairs)
+    log = []
+    got, info = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(lambda r, g: 98.0, log))
+    assert got == [list(range(n))]
+    assert info["ani_calls"] == n - 1 and info["ani_waves"] == 1 and log[0] == [(0, g) for g in range(1, n)]
+    # two sub-clades that are far from each other: genome 0 and the first genome of the other sub-clade
+    far = lambda r, g: 98.0 if (r % 2) == (g % 2) else 80.0
+    got2, info2 = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(far))
+    ser2, sinfo2 = gb.cluster_from_distances(n, hits, 95.0, far)
+    assert got2 == ser2 == [list(range(0, n, 2)), list(range(1, n, 2))]
+    assert info2["ani_calls"] == sinfo2["ani_calls"] == (n - 1) + (n - 2) and info2["ani_waves"] == 2
+
+
+def test_wave_engine_callback_failure_aborts():
+    hits = make_hits([(0, 1, 0.95), (1, 2, 0.95)])
+
+    def boom(reps, genomes):
+        raise KeyError("backend down")
+    with pytest.raises(KeyError):
+        gb.cluster_from_distances_batched(3, hits, 95.0, boom)

@@ -74,3 +74,58 @@ def test_contig_hits_match_golden(gb, name):
     got = {(int(h["i"]), int(h["j"])): float(h["ani"]) for h in hits}
     # a golden pair can be missing only if the marker screen dropped it; none of the pinned cases has one
     assert got == {k: float(np.float32(v)) for k, v in want.items()}, name
+
+
+def _both_modes(gb, run):
+    """run() with stage 2 on every precluster hit, then in waves (galah_b200_cluster_lazy)."""
+    try:
+        gb.cluster_lazy(0)
+        eager = run()
+        gb.cluster_lazy(1)
+        waves = run()
+    finally:
+        gb.cluster_lazy(-1)
+    return eager, waves
+
+
+@pytest.mark.parametrize("name", ["finch_skani_abisko4_95", "finch_skani_abisko4_99", "cli_min_aligned_fraction_0.2",
+                                  "cli_min_aligned_fraction_0.6"])
+def test_stage2_in_waves_gives_the_pinned_outcome(gb, name):
+    """The one-call pipeline with stage 2 asked for in waves (only the pairs the reference's two passes
+    evaluate): the reference-pinned clusters, in the same order as with every hit evaluated up front."""
+    case = CASES[name]
+    run = lambda: gb.cluster(paths_of(GOLDEN, case), precluster_ani=case["pre_thr"], ani=case["ani"],
+                             min_aligned_fraction=case["min_af"], small_genomes=case["small"])
+    (eager, ei), (waves, wi) = _both_modes(gb, run)
+    assert waves == eager and sorted(sorted(c) for c in waves) == case["clusters"]
+    assert ei["ani_waves"] == 0 and (wi["ani_waves"] >= 1 or wi["n_precluster_hits"] == 0)
+    assert wi["n_ani_pairs"] <= ei["n_ani_pairs"]
+
+
+def test_stage2_in_waves_on_synthetic_families(gb):
+    """Four synthetic families of 10 genomes (substitution rates 0 .. 10 %: several representatives per family at
+    95 %, so the waves go several rounds deep) resident on the device: clusters, order and precluster statistics
+    equal the eager pipeline's; fewer pairs are evaluated; a wave budget of one batch is covered by the CPU tests."""
+    import torch
+    seed, n, L = 3, 40, 300_000
+    lay = gb.synth_layout(n, L)
+    dev = torch.device("cuda", 0)
+    d_seq = torch.zeros(lay["seq2_words"], dtype=torch.int32, device=dev)
+    d_val = torch.zeros(lay["valid_words"], dtype=torch.int32, device=dev)
+    d_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gb.synth_packed_device(seed, 0, n, L, d_seq.data_ptr(), d_val.data_ptr(), d_off.data_ptr(), st)
+    torch.cuda.synchronize()
+    base_off = d_off.cpu().numpy().astype(np.uint64)
+    lengths = np.full(n, L, np.uint64)
+    run = lambda: gb.cluster_packed(d_seq.data_ptr(), d_val.data_ptr(), base_off, lengths, precluster_ani=0.9, ani=95.0,
+                                    min_aligned_fraction=15.0, device=True, d_base_off=d_off.data_ptr())
+    (eager, ei), (waves, wi) = _both_modes(gb, run)
+    assert waves == eager
+    assert sorted(g for c in waves for g in c) == list(range(n)) and all(c[0] // 10 == g // 10 for c in waves for g in c)
+    assert len(waves) > 4  # more than one representative per family
+    for key in ("n_precluster_hits", "n_preclusters", "largest_precluster"):
+        assert wi[key] == ei[key]
+    assert wi["ani_waves"] >= 2 and 0 < wi["n_ani_pairs"] < ei["n_ani_pairs"]
+    # the engine's own count of calculate_ani invocations is the reference's in both modes
+    assert wi["ani_calls"] == ei["ani_calls"] == wi["n_ani_pairs"]
