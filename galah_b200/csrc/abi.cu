@@ -271,7 +271,11 @@ static int run_prefilter(const uint64_t *d_hashes, const uint32_t *d_counts, siz
     }
     const double t_begin = now_ms();
     if (!g_ctx.d_n_cand) GB_CUDA(cudaMalloc(&g_ctx.d_n_cand, sizeof(unsigned long long)));
+    // room for 32 survivors per genome, or for EVERY pair when that is at most 4 M entries (64 MB): a small
+    // collection of near-identical genomes passes all its pairs and would otherwise run the kernels twice
+    const size_t all_pairs = n * (n - (n ? 1 : 0)) / 2;
     size_t cap = std::max<size_t>(1 << 16, 32 * n);
+    if (!h_hashes && n_shards <= 1 && all_pairs <= ((size_t)1 << 22)) cap = std::max<size_t>(1 << 16, all_pairs);
     std::vector<uint4> cand;
     for (;;) {
         if (ws_ensure(g_ctx.d_cand, g_ctx.cap_cand, cap)) return GALAH_B200_ERR_CUDA;

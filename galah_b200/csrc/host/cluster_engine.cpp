@@ -153,13 +153,30 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         std::vector<uint64_t> fill(adj.off.begin(), adj.off.end() - 1);
         // keys ascend, so every row receives its neighbours in ascending order: first the smaller
         // partners (as the second genome of earlier keys), then the larger ones
-        for (size_t u = 0; u < n_uniq; u++) {
-            const uint32_t x = hit_at(u);
-            const PreclusterHit &h = hits[x];
-            const uint32_t a = std::min(h.i, h.j), b = std::max(h.i, h.j);
-            const uint64_t pa = fill[a]++, pb = fill[b]++;
-            adj.nbr[pa] = b; adj.ani[pa] = h.ani; adj.hit[pa] = x;
-            adj.nbr[pb] = a; adj.ani[pb] = h.ani; adj.hit[pb] = x;
+        // rows [r0, r1): every thread of a large list walks all hits in key order and writes the slots of its own rows
+        auto fill_rows = [&](uint32_t r0, uint32_t r1) {
+            for (size_t u = 0; u < n_uniq; u++) {
+                const uint32_t x = hit_at(u);
+                const PreclusterHit &h = hits[x];
+                const uint32_t a = std::min(h.i, h.j), b = std::max(h.i, h.j);
+                if (a >= r0 && a < r1) { const uint64_t pa = fill[a]++; adj.nbr[pa] = b; adj.ani[pa] = h.ani; adj.hit[pa] = x; }
+                if (b >= r0 && b < r1) { const uint64_t pb = fill[b]++; adj.nbr[pb] = a; adj.ani[pb] = h.ani; adj.hit[pb] = x; }
+            }
+        };
+        const size_t hw_fill = std::max<size_t>(1, std::thread::hardware_concurrency());
+        const size_t nt_fill = n_uniq >= ((size_t)1 << 19) ? std::min<size_t>(hw_fill, 16) : 1;
+        if (nt_fill == 1) {
+            fill_rows(0, (uint32_t)n);
+        } else {
+            // row ranges holding about the same number of slots (the scattered writes are the cost)
+            std::vector<uint32_t> cut(nt_fill + 1, (uint32_t)n);
+            cut[0] = 0;
+            for (size_t t = 1; t < nt_fill; t++)
+                cut[t] = (uint32_t)(std::lower_bound(adj.off.begin(), adj.off.end(), adj.off[n] / nt_fill * t) - adj.off.begin());
+            std::vector<std::thread> th;
+            for (size_t t = 0; t < nt_fill; t++)
+                if (cut[t] < cut[t + 1]) th.emplace_back(fill_rows, cut[t], cut[t + 1]);
+            for (auto &t : th) t.join();
         }
     }
 

@@ -266,3 +266,31 @@ def test_wave_engine_callback_failure_aborts():
         raise KeyError("backend down")
     with pytest.raises(KeyError):
         gb.cluster_from_distances_batched(3, hits, 95.0, boom)
+
+
+def test_large_dense_list_threaded_adjacency():
+    """> 2^19 hits: the adjacency rows are filled by several host threads (row ranges).  One clade of 1,100 genomes
+    (604,450 hits) in two far-apart halves; table engine, wave engine and skip_clusterer agree with the closed form."""
+    n = 1100
+    iu = np.triu_indices(n, 1)
+    hits = np.zeros(len(iu[0]), gb.PAIR_DTYPE)
+    hits["i"], hits["j"] = iu[0], iu[1]
+    same = (hits["i"] % 2) == (hits["j"] % 2)
+    hits["ani"] = np.where(same, 98.0, 80.0).astype(np.float32)
+    assert len(hits) > (1 << 19)
+    want = [list(range(0, n, 2)), list(range(1, n, 2))]
+    ani = hits["ani"].copy()
+    got, info = gb.cluster_from_ani_tables(n, hits, ani, ani, 95.0)
+    assert got == want and info["ani_calls"] == (n - 1) + (n - 2)
+    waves, winfo = gb.cluster_from_distances_batched(
+        n, hits, 95.0, lambda reps, genomes: np.where((reps % 2) == (genomes % 2), 98.0, 80.0).tolist())
+    assert waves == want and winfo["ani_calls"] == info["ani_calls"] and winfo["ani_waves"] == 2
+    skip, _ = gb.cluster_from_distances(n, hits, 95.0, None, skip_clusterer=True)
+    assert skip == want
+    # unsorted input with a duplicate key: the later record wins (BTreeMap::insert)
+    shuffled = hits[np.random.default_rng(5).permutation(len(hits))]
+    dup = shuffled[:1].copy()
+    extra = np.concatenate([dup, shuffled])
+    extra[0]["ani"] = 1.0  # overwritten by the later record of the same key
+    again, _ = gb.cluster_from_distances(n, extra, 95.0, None, skip_clusterer=True)
+    assert again == want
