@@ -68,7 +68,21 @@ def build(force=False, verbose=False):
         link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                "-Xcompiler", "-pthread", "-l:libz.so.1"]
         subprocess.check_call(link)
+    build_cli(force)
     return LIB_PATH
+
+
+CLI_PATH = os.path.join(PKG_DIR, "galah-b200")
+
+
+def build_cli(force=False):
+    """galah-b200: the `galah cluster` command line over the C ABI (csrc/cli/main.cpp), next to the library."""
+    src = os.path.join(CSRC, "cli", "main.cpp")
+    hdr = os.path.join(PKG_DIR, "..", "include", "galah_b200.h")
+    if force or _stale(CLI_PATH, [src, hdr, LIB_PATH]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(PKG_DIR, "..", "include"), src, "-o", CLI_PATH,
+                               "-L", PKG_DIR, "-l:libgalah_b200.so", "-Wl,-rpath,$ORIGIN"])
+    return CLI_PATH
 
 
 if __name__ == "__main__":
