@@ -184,6 +184,11 @@ _SIGNATURES = {
     "galah_b200_ani_index_attach_peer": (ctypes.c_int, [vp, vp, u64p, u64p, ctypes.c_size_t, u32p]),
     "galah_b200_skani_distances": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_float, ctypes.c_float, ctypes.c_int,
                                                   ctypes.c_int, ctypes.c_int, pairpp, sizep, sizep]),
+    "galah_b200_skani_distances_multi": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, pairpp, sizep, sizep]),
+    "galah_b200_cluster_files_skani_multi": (ctypes.c_int, [strp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                            ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                            ctypes.POINTER(Clusters), ctypes.POINTER(ClusterStats)]),
     "galah_b200_skani_distances_packed_device": (ctypes.c_int, [vp, vp, vp, u64p, u64p, ctypes.c_size_t, ctypes.c_float,
                                                                 ctypes.c_float, ctypes.c_int, ctypes.c_int, vp,
                                                                 ctypes.POINTER(ctypes.POINTER(Pair)), sizep,

@@ -637,6 +637,33 @@ def cluster_skani(genomes, precluster_ani=90.0, ani=95.0, min_aligned_fraction=1
     return clusters, info
 
 
+def skani_distances_multi(paths, n_devices, threshold=90.0, min_aligned_fraction=15.0, small_genomes=False, contigs=False,
+                          threads=0):
+    """skani_distances over n_devices GPUs of this process (init_devices first): device r ingests the r-th slice of
+    the path list.  Same hit list as the single-GPU call."""
+    out = ctypes.POINTER(Pair)()
+    n_out, n_units = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    check(lib().galah_b200_skani_distances_multi(_paths_array(paths), len(paths), int(n_devices), ctypes.c_float(threshold),
+                                                 ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+                                                 int(bool(contigs)), threads, ctypes.byref(out), ctypes.byref(n_out),
+                                                 ctypes.byref(n_units)))
+    return _take_pairs(out, n_out), int(n_units.value)
+
+
+def cluster_skani_multi(genomes, n_devices, precluster_ani=90.0, ani=95.0, min_aligned_fraction=15.0, small_genomes=False,
+                        cluster_contigs=False, threads=0):
+    """cluster_skani over n_devices GPUs of this process (init_devices first)."""
+    res = _native.Clusters()
+    stats = _native.ClusterStats()
+    check(lib().galah_b200_cluster_files_skani_multi(_paths_array(genomes), len(genomes), int(n_devices),
+                                                     ctypes.c_float(precluster_ani), ctypes.c_float(ani),
+                                                     ctypes.c_float(min_aligned_fraction), int(bool(small_genomes)),
+                                                     int(bool(cluster_contigs)), threads, ctypes.byref(res), ctypes.byref(stats)))
+    clusters, info = _take_clusters(res)
+    info.update(n_precluster_hits=int(stats.n_precluster_hits))
+    return clusters, info
+
+
 def pack_fasta_file(path):
     """Host ingest of one file -> (codes uint8 per base: 0..3 = ACGT, 4 = invalid, rec_start, rec_end) in
     packed coordinates (unpacked here for comparison with the oracle's load_codes)."""

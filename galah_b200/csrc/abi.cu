@@ -2102,32 +2102,36 @@ int galah_b200_skani_distances_packed_device(const uint32_t *d_seq2, const uint3
 // units in HOST arrays over G devices of this process: the structure of cluster_multi with marker
 // sketches in place of MinHash sketches, the containment screen in place of the finch rule, and
 // every screened pair (i < j) evaluated ONCE, with i as the query, on the device that owns i.
-int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
-                                            const uint64_t *lengths, size_t n, int n_devices, float threshold_pct,
-                                            float min_af_pct, int small_genomes, int individual_contigs,
-                                            galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened) {
-    if (!out || !n_out) { set_error("skani_distances_packed_multi: NULL argument"); return GALAH_B200_ERR_ARG; }
-    *out = nullptr; *n_out = 0;
+// The skani preclusterer over G devices of this process.  `ingest(r, index, slice)` puts device r's units into its K3
+// index and their marker rows EITHER in place into the device's copy of the global marker table (packed input: unit
+// slices g0 and the row stride `cap` are known up front) OR into a table of its own (file input: the number of units
+// of a slice and the longest unit are only known once its files are read; the global layout is agreed at a barrier
+// and every device re-strides its rows into its slice of the global table).  From there on both forms are one code
+// path: marker rows exchanged by peer copies, row-block shards of the containment screen, every screened pair
+// (i < j) evaluated on the device that owns unit i, which reads unit j's hash table in place on its peer.
+static int take_hits(const std::vector<galah_b200_pair_t> &hits, galah_b200_pair_t **out, size_t *n_out) {
+    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(hits.size(), 1) * sizeof(galah_b200_pair_t));
+    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
+    if (!hits.empty()) memcpy(res, hits.data(), hits.size() * sizeof(galah_b200_pair_t));
+    *out = res; *n_out = hits.size();
+    return 0;
+}
+
+struct MultiSlice { size_t n_units = 0; MarkerTable local; };
+using MultiMarkerIngest = std::function<int(int r, AniIndex &index, MultiSlice &slice)>;
+
+static int skani_distances_multi(int G, bool layout_known, std::vector<size_t> g0_in, uint32_t cap_in, const MultiMarkerIngest &ingest,
+                                 float threshold_pct, float min_af_pct, int small_genomes, int individual_contigs,
+                                 std::vector<galah_b200_pair_t> &hits_out, size_t *n_units_out, uint64_t *n_screened) {
+    hits_out.clear();
     if (n_screened) *n_screened = 0;
     if (threshold_pct < 85.0f) {
         set_error("Error: skani produces inaccurate results with ANI less than 85%. Provided: " + display_f32(threshold_pct));
         return GALAH_B200_ERR_UNSUPPORTED;
     }
-    const int G = n_devices;
-    if (G < 1 || G > kMaxDevices) { set_error("skani_distances_packed_multi: bad device count"); return GALAH_B200_ERR_ARG; }
+    if (G < 1 || G > kMaxDevices) { set_error("skani_distances_multi: bad device count"); return GALAH_B200_ERR_ARG; }
     for (int d = 0; d < G; d++)
-        if (g_ctxs[d].device != d) { set_error("skani_distances_packed_multi: call galah_b200_init_devices(n_devices) first"); return GALAH_B200_ERR_NO_DEVICE; }
-    for (size_t g = 0; g <= n; g++)
-        if (base_off[g] % 128) { set_error("packed units: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
-    uint64_t longest = 0;
-    for (size_t g = 0; g < n; g++) longest = std::max(longest, lengths[g]);
-    const uint32_t c_marker = small_genomes ? 200u : 1000u;
-    const uint32_t cap = marker_row_capacity(longest, c_marker);
-    size_t per = (n + (size_t)G - 1) / (size_t)G;
-    per = (per + GALAH_B200_ROW_BLOCK - 1) / GALAH_B200_ROW_BLOCK * GALAH_B200_ROW_BLOCK;
-    std::vector<size_t> g0((size_t)G + 1);
-    for (int r = 0; r <= G; r++) g0[r] = std::min(n, (size_t)r * per);
-    auto owner = [&](uint32_t g) { return (int)std::min<size_t>((size_t)g / per, (size_t)G - 1); };
+        if (g_ctxs[d].device != d) { set_error("skani_distances_multi: call galah_b200_init_devices(n_devices) first"); return GALAH_B200_ERR_NO_DEVICE; }
 
     MultiBarrier bar(G);
     std::vector<int> rcs((size_t)G, 0);
@@ -2136,7 +2140,9 @@ int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t
     std::vector<std::vector<uint4>> inbox((size_t)G);
     std::vector<std::mutex> inbox_mu((size_t)G);
     std::vector<std::vector<galah_b200_pair_t>> rank_hits((size_t)G);
+    std::vector<MultiSlice> slices((size_t)G);
     std::atomic<uint64_t> screened{0};
+    size_t n_total = layout_known ? g0_in.back() : 0;
 
     auto worker = [&](int r) {
         t_dev = r;
@@ -2146,24 +2152,52 @@ int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t
         int rc = require_ctx();
         if (rc) fail(rc);
         cudaStream_t st = C.stream;
-        const size_t nr = g0[r + 1] - g0[r];
+        std::vector<size_t> g0 = g0_in;  // unit slices: device p owns units [g0[p], g0[p + 1])
+        uint32_t cap = cap_in;           // row stride of the global marker table
+        size_t n = layout_known ? g0.back() : 0;
         AniIndex *index = nullptr;
         if (!rc) {
             index = &C.pipeline_index(small_genomes != 0);
-            if (ws_ensure(C.d_table, C.cap_table, std::max<size_t>(n, 1) * cap) ||
-                ws_ensure(C.d_counts, C.cap_counts, std::max<size_t>(n, 1)))
+            if (layout_known && (ws_ensure(C.d_table, C.cap_table, std::max<size_t>(n, 1) * cap) ||
+                                 ws_ensure(C.d_counts, C.cap_counts, std::max<size_t>(n, 1))))
                 fail(GALAH_B200_ERR_CUDA);
         }
-        if (!rcs[r] && nr) {
-            rc = ingest_packed(seq2, valid, nullptr, base_off + g0[r], lengths + g0[r], nr, false, C.d_table + g0[r] * (size_t)cap,
-                               C.d_counts + g0[r], *index, nullptr, nullptr, c_marker, cap);
+        if (!rcs[r]) {
+            rc = ingest(r, *index, slices[r]);
             if (rc) fail(rc);
         }
-        if (!rcs[r]) {
+        if (!layout_known) {
+            bar.wait();  // ---- every slice knows its unit count and its row stride: agree on the global layout
+            g0.assign((size_t)G + 1, 0);
+            cap = 0;
+            for (int p = 0; p < G; p++) { g0[p + 1] = g0[p] + slices[p].n_units; cap = std::max(cap, slices[p].local.stride); }
+            n = g0[G];
+            if (r == 0) n_total = n;
+            const size_t nr = g0[r + 1] - g0[r];
+            if (!failed.load() && n >= 2) {
+                if (ws_ensure(C.d_table, C.cap_table, n * (size_t)cap) || ws_ensure(C.d_counts, C.cap_counts, n)) fail(GALAH_B200_ERR_CUDA);
+                const MarkerTable &mt = slices[r].local;
+                if (!rcs[r] && nr && mt.n != nr) { set_error("skani preclusterer: marker table out of step with the units"); fail(GALAH_B200_ERR_ARG); }
+                if (!rcs[r] && nr) {
+                    // own rows at the common stride; whatever lies beyond a row's own stride reads as "no hash"
+                    uint64_t *dst = C.d_table + g0[r] * (size_t)cap;
+                    if (cudaMemsetAsync(dst, 0xFF, nr * (size_t)cap * 8, st) != cudaSuccess ||
+                        cudaMemcpy2DAsync(dst, (size_t)cap * 8, mt.d_rows, (size_t)mt.stride * 8, (size_t)mt.stride * 8, nr,
+                                          cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+                        cudaMemcpyAsync(C.d_counts + g0[r], mt.d_counts, nr * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+                        cudaStreamSynchronize(st) != cudaSuccess) {
+                        set_error("skani_distances_multi: re-striding the marker rows failed"); fail(GALAH_B200_ERR_CUDA);
+                    }
+                }
+            }
+        }
+        const size_t nr = g0[r + 1] - g0[r];
+        auto owner = [&](uint32_t g) { return (int)(std::upper_bound(g0.begin() + 1, g0.end(), (size_t)g) - (g0.begin() + 1)); };
+        if (layout_known && !rcs[r]) {
             std::vector<uint32_t> cnt(nr);
             if ((nr && cudaMemcpyAsync(cnt.data(), C.d_counts + g0[r], nr * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
                 cudaStreamSynchronize(st) != cudaSuccess) {
-                set_error("skani_distances_packed_multi: reading the marker counts failed"); fail(GALAH_B200_ERR_CUDA);
+                set_error("skani_distances_multi: reading the marker counts failed"); fail(GALAH_B200_ERR_CUDA);
             }
             for (size_t x = 0; x < nr && !rcs[r]; x++)
                 if (cnt[x] == 0xFFFFFFFFu) {
@@ -2179,7 +2213,7 @@ int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t
                 if (cudaMemcpyPeerAsync(C.d_table + g0[p] * (size_t)cap, r, g_ctxs[p].d_table + g0[p] * (size_t)cap, p,
                                         np * (size_t)cap * 8, st) != cudaSuccess ||
                     cudaMemcpyPeerAsync(C.d_counts + g0[p], r, g_ctxs[p].d_counts + g0[p], p, np * 4, st) != cudaSuccess) {
-                    set_error("skani_distances_packed_multi: peer copy of the marker rows failed");
+                    set_error("skani_distances_multi: peer copy of the marker rows failed");
                     fail(GALAH_B200_ERR_CUDA);
                 }
             }
@@ -2260,15 +2294,92 @@ int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t
     for (int r = 0; r < G; r++)
         if (rcs[r]) { set_error("device " + std::to_string(r) + ": " + errs[r]); return rcs[r]; }
     // the devices own ascending slices of the query index: their lists concatenate into (i, j) order
-    size_t total = 0;
-    for (auto &v : rank_hits) total += v.size();
-    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(total, 1) * sizeof(galah_b200_pair_t));
-    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
-    size_t at = 0;
-    for (auto &v : rank_hits) { if (!v.empty()) memcpy(res + at, v.data(), v.size() * sizeof(galah_b200_pair_t)); at += v.size(); }
-    *out = res; *n_out = total;
+    for (auto &v : rank_hits) hits_out.insert(hits_out.end(), v.begin(), v.end());
+    if (n_units_out) *n_units_out = n_total;
     if (n_screened) *n_screened = screened.load();
     return 0;
+}
+
+int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t *valid, const uint64_t *base_off,
+                                            const uint64_t *lengths, size_t n, int n_devices, float threshold_pct,
+                                            float min_af_pct, int small_genomes, int individual_contigs,
+                                            galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened) {
+    if (!out || !n_out) { set_error("skani_distances_packed_multi: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    const int G = n_devices;
+    if (G < 1 || G > kMaxDevices) { set_error("skani_distances_packed_multi: bad device count"); return GALAH_B200_ERR_ARG; }
+    for (size_t g = 0; g <= n; g++)
+        if (base_off[g] % 128) { set_error("packed units: base_off must be multiples of 128"); return GALAH_B200_ERR_ARG; }
+    uint64_t longest = 0;
+    for (size_t g = 0; g < n; g++) longest = std::max(longest, lengths[g]);
+    const uint32_t c_marker = small_genomes ? 200u : 1000u;
+    const uint32_t cap = marker_row_capacity(longest, c_marker);
+    size_t per = (n + (size_t)G - 1) / (size_t)G;
+    per = (per + GALAH_B200_ROW_BLOCK - 1) / GALAH_B200_ROW_BLOCK * GALAH_B200_ROW_BLOCK;
+    std::vector<size_t> g0((size_t)G + 1);
+    for (int r = 0; r <= G; r++) g0[r] = std::min(n, (size_t)r * per);
+    const MultiMarkerIngest ingest = [&](int r, AniIndex &index, MultiSlice &slice) -> int {
+        const size_t nr = g0[r + 1] - g0[r];
+        slice.n_units = nr;
+        if (!nr) return 0;
+        Context &C = g_ctxs[r];
+        return ingest_packed(seq2, valid, nullptr, base_off + g0[r], lengths + g0[r], nr, false, C.d_table + g0[r] * (size_t)cap,
+                             C.d_counts + g0[r], index, nullptr, nullptr, c_marker, cap);
+    };
+    std::vector<galah_b200_pair_t> hits;
+    if (int rc = skani_distances_multi(G, true, g0, cap, ingest, threshold_pct, min_af_pct, small_genomes, individual_contigs, hits,
+                                       nullptr, n_screened))
+        return rc;
+    return take_hits(hits, out, n_out);
+}
+
+// The file form: device r reads, decodes (K0), marker-sketches and indexes the r-th slice of the path list; in contig
+// mode every record is a unit, so a slice's unit count is known only after its files are read.
+int galah_b200_skani_distances_multi(const char *const *paths, size_t n, int n_devices, float threshold_pct, float min_af_pct,
+                                     int small_genomes, int per_record, int host_threads, galah_b200_pair_t **out,
+                                     size_t *n_out, size_t *n_units) {
+    if (!out || !n_out) { set_error("skani_distances_multi: NULL argument"); return GALAH_B200_ERR_ARG; }
+    *out = nullptr; *n_out = 0;
+    if (n_units) *n_units = 0;
+    const int G = n_devices;
+    if (G < 1 || G > kMaxDevices) { set_error("skani_distances_multi: bad device count"); return GALAH_B200_ERR_ARG; }
+    if (host_threads <= 0) host_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int per_device = std::max(1, host_threads / G);
+    const size_t per = (n + (size_t)G - 1) / (size_t)G;  // files per device
+    const MultiMarkerIngest ingest = [&](int r, AniIndex &index, MultiSlice &slice) -> int {
+        const size_t f0 = std::min(n, (size_t)r * per), f1 = std::min(n, (size_t)(r + 1) * per);
+        slice.n_units = 0;
+        if (f0 == f1) return 0;
+        IngestSinks sinks;
+        sinks.ani = &index; sinks.markers = &slice.local; sinks.c_marker = small_genomes ? 200u : 1000u;
+        sinks.per_record = per_record != 0;
+        if (int rc = ingest_files(paths + f0, f1 - f0, per_device, sinks)) return rc;
+        slice.n_units = sinks.n_units;
+        return 0;
+    };
+    std::vector<galah_b200_pair_t> hits;
+    if (int rc = skani_distances_multi(G, false, std::vector<size_t>(), 0, ingest, threshold_pct, min_af_pct, small_genomes, per_record, hits,
+                                       n_units, nullptr))
+        return rc;
+    return take_hits(hits, out, n_out);
+}
+
+int galah_b200_cluster_files_skani_multi(const char *const *paths, size_t n, int n_devices, float precluster_ani_pct,
+                                         float ani_threshold_pct, float min_af_pct, int small_genomes, int cluster_contigs,
+                                         int host_threads, galah_b200_clusters_t *out, galah_b200_cluster_stats_t *stats) {
+    if (!out) { set_error("cluster_files_skani_multi: out is NULL"); return GALAH_B200_ERR_ARG; }
+    memset(out, 0, sizeof(*out));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (!(ani_threshold_pct > 1.0f)) { set_error("assertion failed: self.threshold > 1.0"); return GALAH_B200_ERR_UNSUPPORTED; }
+    galah_b200_pair_t *hits = nullptr;
+    size_t n_hits = 0, n_units = 0;
+    if (int rc = galah_b200_skani_distances_multi(paths, n, n_devices, precluster_ani_pct, min_af_pct, small_genomes, cluster_contigs,
+                                                  host_threads, &hits, &n_hits, &n_units))
+        return rc;
+    struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
+    int rc = galah_b200_cluster_from_distances(n_units, hits, n_hits, 1, ani_threshold_pct, nullptr, nullptr, out);
+    if (stats) { stats->n_precluster_hits = n_hits; stats->n_ani_pairs = n_hits; }
+    return rc;
 }
 
 int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct, float ani_threshold_pct,
@@ -2441,14 +2552,6 @@ int galah_b200_session_finch_distances_with_references(galah_b200_session_t *s, 
     if (n_out) *n_out = 0;
     set_error("Reference genome clustering currently only supported with skani preclusterer");  // src/finch.rs:40
     return GALAH_B200_ERR_UNSUPPORTED;
-}
-
-static int take_hits(const std::vector<galah_b200_pair_t> &hits, galah_b200_pair_t **out, size_t *n_out) {
-    galah_b200_pair_t *res = (galah_b200_pair_t *)malloc(std::max<size_t>(hits.size(), 1) * sizeof(galah_b200_pair_t));
-    if (!res) { set_error("out of host memory"); return GALAH_B200_ERR_ARG; }
-    if (!hits.empty()) memcpy(res, hits.data(), hits.size() * sizeof(galah_b200_pair_t));
-    *out = res; *n_out = hits.size();
-    return 0;
 }
 
 int galah_b200_session_skani_distances(galah_b200_session_t *s, const char *const *paths, size_t n, float threshold_pct,

@@ -339,10 +339,11 @@ int main(int argc, char **argv) {
                            : galah_b200_cluster_files(paths.data(), n, pre_frac, ani_pct, af_pct, small, o.threads, &cl, &stats);
         if (rc) die_lib("cluster");
     } else if (references.empty() && !o.low_memory) {
-        if (o.gpus > 1 && !o.quiet)
-            fprintf(stderr, "[WARN] --gpus %d: the file-based skani preclusterer runs on one device\n", o.gpus);
-        if (galah_b200_cluster_files_skani(paths.data(), n, pre_pct, ani_pct, af_pct, small, o.cluster_contigs, o.threads, &cl, &stats))
-            die_lib("cluster");
+        const int rc = o.gpus > 1 ? galah_b200_cluster_files_skani_multi(paths.data(), n, o.gpus, pre_pct, ani_pct, af_pct, small,
+                                                                         o.cluster_contigs, o.threads, &cl, &stats)
+                                  : galah_b200_cluster_files_skani(paths.data(), n, pre_pct, ani_pct, af_pct, small, o.cluster_contigs,
+                                                                   o.threads, &cl, &stats);
+        if (rc) die_lib("cluster");
     } else {
         // low-memory / reference forms of the skani preclusterer (src/skani.rs:229-377, 502-687), then the engine
         // with skip_clusterer (same method names, src/clusterer.rs:32-36)

@@ -476,6 +476,18 @@ int galah_b200_skani_distances_packed_multi(const uint32_t *seq2, const uint32_t
                                             const uint64_t *lengths, size_t n, int n_devices, float threshold_pct,
                                             float min_af_pct, int small_genomes, int individual_contigs,
                                             galah_b200_pair_t **out, size_t *n_out, uint64_t *n_screened);
+/* The file-based preclusterer and the whole skani + skani call over several GPUs of this process
+ * (galah_b200_init_devices first): device r reads, decodes (K0), marker-sketches and indexes the r-th
+ * slice of the path list; the devices agree on the unit numbering and the marker row stride once
+ * every slice is read (in contig mode a file's record count is not known before), then proceed as
+ * galah_b200_skani_distances_packed_multi.  Hits and clusters identical to the single-GPU calls'. */
+int galah_b200_skani_distances_multi(const char *const *paths, size_t n, int n_devices, float threshold_pct,
+                                     float min_af_pct, int small_genomes, int per_record, int host_threads,
+                                     galah_b200_pair_t **out, size_t *n_out, size_t *n_units);
+int galah_b200_cluster_files_skani_multi(const char *const *paths, size_t n, int n_devices, float precluster_ani_pct,
+                                         float ani_threshold_pct, float min_af_pct, int small_genomes,
+                                         int cluster_contigs, int host_threads, galah_b200_clusters_t *out,
+                                         galah_b200_cluster_stats_t *stats);
 int galah_b200_cluster_files_skani(const char *const *paths, size_t n, float precluster_ani_pct,
                                    float ani_threshold_pct, float min_af_pct, int small_genomes,
                                    int cluster_contigs, int host_threads, galah_b200_clusters_t *out,

@@ -101,6 +101,44 @@ def main():
         out["files"] = {"genomes": len(paths), "clusters": len(one), "identical_to_single_gpu": bool(one == many),
                         "multi_phases_ms": {k: round(float(v), 2) for k, v in finfo.items() if k.endswith("_ms")}}
         ok = ok and (one == many)
+        # the file-based skani preclusterer (galah_b200_skani_distances_multi / _cluster_files_skani_multi): the same
+        # genomes, then contig mode on multi-record files with 1..6 records each (a slice's unit count is only known
+        # once its files are read), then the reference's own five-genome fixture (src/clusterer.rs:725-757)
+        cfiles = []
+        for fam in range(40):
+            founder = rng.integers(0, 4, 30_000, dtype=np.uint8)
+            path = os.path.join(tmp, f"contigs{fam:02d}.fna")
+            with open(path, "wb") as f:
+                for rec in range(1 + fam % 6):
+                    seq = founder.copy()
+                    if rec:
+                        pos = rng.choice(len(seq), size=len(seq) // (40 * rec), replace=False)
+                        seq[pos] = (seq[pos] + rng.integers(1, 4, len(pos), dtype=np.uint8)) % 4
+                    f.write(f">f{fam}_r{rec} some description\n".encode())
+                    text = np.frombuffer(b"ACGT", dtype=np.uint8)[seq]
+                    for x in range(0, len(text), 70):
+                        f.write(text[x:x + 70].tobytes() + b"\n")
+            cfiles.append(path)
+        golden = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+        fixture = [os.path.join(golden, "abisko4", f) for f in ("73.20120800_S1X.13.fna.gz", "73.20120600_S2D.19.fna.gz",
+                                                                "73.20120700_S3X.12.fna.gz", "73.20110800_S2D.13.fna.gz")]
+        fixture.append(os.path.join(golden, "antonio_mags", "BE_RX_R2_MAG52.fna.gz"))
+        sk = {}
+        for name, plist, kw in (("genomes", paths, dict(threshold=95.0, small_genomes=False, contigs=False)),
+                                ("contigs", cfiles, dict(threshold=95.0, small_genomes=True, contigs=True)),
+                                ("fixture", fixture, dict(threshold=90.0, min_aligned_fraction=20.0))):
+            gb.init(0)
+            h_one, u_one = gb.skani_distances(plist, **kw)
+            gb.init_devices(G)
+            h_many, u_many = gb.skani_distances_multi(plist, G, **kw)
+            same = u_one == u_many and len(h_one) == len(h_many) and bool(np.all(h_one == h_many))
+            sk[name] = {"files": len(plist), "units": u_many, "hits": int(len(h_many)), "identical_to_single_gpu": same}
+            ok = ok and same
+        gb.init_devices(G)
+        fx, _ = gb.cluster_skani_multi(fixture, G, precluster_ani=90.0, ani=99.0, min_aligned_fraction=20.0)
+        sk["fixture"]["clusters"] = fx.tolist()
+        ok = ok and sorted(sorted(c) for c in fx.tolist()) == [[0, 1, 3], [2], [4]]
+        out["skani_files"] = sk
     # ---- the skani preclusterer (contig mode) on the same buffers read as contigs of --contig-len bases
     if args.contigs:
         nc, Lc = args.contigs, args.contig_len
