@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <chrono>
@@ -538,35 +539,105 @@ static int ingest_files(const char *const *paths, size_t n, int host_threads, In
         // ---- K0 path (whole-genome units): host threads only read (and inflate) the files; the
         // raw bytes cross PCIe once and are decoded on the device (csrc/ingest.cu)
         if (g_ctx.device_ingest) {
-            std::vector<std::vector<uint8_t>> raw(want);
-            auto reader = [&]() {
+            // Plain files are read by the host threads STRAIGHT into the pinned staging buffer (their sizes are known
+            // from the probe, so every file's place is); gzip files are inflated into memory first.  The probe also
+            // sniffs the first non-blank byte: anything but '>' (FASTQ) sends the batch to the host packer below.
+            struct Probe { bool plain = false; uint64_t size = 0; bool fasta = true; };
+            std::vector<Probe> probe(want);
+            std::vector<std::vector<uint8_t>> raw(want);  // inflated gzip members / unseekable inputs only
+            auto sniff = [](const uint8_t *d, size_t len, bool whole) {
+                size_t p = 0;
+                while (p < len && (d[p] == '\n' || d[p] == '\r')) p++;
+                if (p < len) return d[p] == '>';
+                return whole;  // an empty / all-blank file decodes to nothing; an undecided head goes to the host packer
+            };
+            auto prober = [&]() {
                 for (;;) {
                     size_t x = next.fetch_add(1);
                     if (x >= want) break;
-                    rcs[x] = read_file_bytes(paths[done + x], raw[x], errs[x]);
+                    const char *path = paths[done + x];
+                    FILE *fp = fopen(path, "rb");
+                    if (!fp) { errs[x] = std::string("Failed to open fasta file ") + path; rcs[x] = 4; continue; }
+                    uint8_t head[4096];
+                    const size_t got = fread(head, 1, sizeof(head), fp);
+                    struct stat sb;
+                    const bool gz = got >= 2 && head[0] == 0x1f && head[1] == 0x8b;
+                    const bool regular = fstat(fileno(fp), &sb) == 0 && S_ISREG(sb.st_mode);
+                    fclose(fp);
+                    if (!gz && regular) {
+                        probe[x].plain = true; probe[x].size = (uint64_t)sb.st_size;
+                        probe[x].fasta = sniff(head, got, got == (size_t)sb.st_size);
+                    } else {
+                        rcs[x] = read_file_bytes(path, raw[x], errs[x]);
+                        probe[x].size = raw[x].size();
+                        probe[x].fasta = sniff(raw[x].data(), raw[x].size(), true);
+                    }
                 }
             };
-            std::vector<std::thread> th;
-            for (int t = 1; t < nt; t++) th.emplace_back(reader);
-            reader();
-            for (auto &t : th) t.join();
+            {
+                std::vector<std::thread> th;
+                for (int t = 1; t < nt; t++) th.emplace_back(prober);
+                prober();
+                for (auto &t : th) t.join();
+            }
             for (size_t x = 0; x < want; x++)
                 if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
             bool all_fasta = true;
-            for (size_t x = 0; x < want && all_fasta; x++) {
-                size_t p = 0;
-                while (p < raw[x].size() && (raw[x][p] == '\n' || raw[x][p] == '\r')) p++;
-                if (p < raw[x].size() && raw[x][p] != '>') all_fasta = false;
-            }
+            for (size_t x = 0; x < want; x++) all_fasta = all_fasta && probe[x].fasta;
             if (all_fasta) {
                 size_t b0 = 0;
                 while (b0 < want) {  // sub-batches of at most ~2 GiB of raw bytes
                     size_t b1 = b0; uint64_t bytes = 0;
-                    while (b1 < want && (b1 == b0 || bytes + raw[b1].size() + 32 <= kMaxBatchBases)) { bytes += raw[b1].size() + 32; b1++; }
+                    while (b1 < want && (b1 == b0 || bytes + probe[b1].size + 32 <= kMaxBatchBases)) { bytes += probe[b1].size + 32; b1++; }
+                    const size_t nf = b1 - b0;
                     RawBatch rb;
-                    if (int rc = stage_raw(std::vector<std::vector<uint8_t>>(std::make_move_iterator(raw.begin() + b0),
-                                                                            std::make_move_iterator(raw.begin() + b1)), rb))
-                        return rc;
+                    rb.file_off.assign(nf + 1, 0); rb.file_len.assign(nf, 0); rb.first_byte.assign(nf, 0);
+                    for (size_t f = 0; f < nf; f++) {
+                        rb.file_len[f] = probe[b0 + f].size;
+                        rb.file_off[f + 1] = (rb.file_off[f] + probe[b0 + f].size + 31) / 32 * 32;
+                    }
+                    const size_t need = rb.file_off[nf] + 64;
+                    if (g_ctx.cap_raw < need) {
+                        if (g_ctx.h_raw) GB_CUDA(cudaFreeHost(g_ctx.h_raw));
+                        g_ctx.h_raw = nullptr; g_ctx.cap_raw = 0;
+                        const size_t grow = need + need / 4;
+                        GB_CUDA(cudaMallocHost(&g_ctx.h_raw, grow));
+                        g_ctx.cap_raw = grow;
+                    }
+                    rb.bytes = g_ctx.h_raw;
+                    std::atomic<size_t> next_file{0};
+                    auto filler = [&]() {
+                        for (;;) {
+                            const size_t f = next_file.fetch_add(1);
+                            if (f >= nf) break;
+                            const size_t x = b0 + f;
+                            uint8_t *dst = rb.bytes + rb.file_off[f];
+                            const size_t len = (size_t)probe[x].size;
+                            if (probe[x].plain) {
+                                FILE *fp = fopen(paths[done + x], "rb");
+                                const size_t rd = fp && len ? fread(dst, 1, len, fp) : 0;
+                                // one more byte must not be there: the file is as long as the probe saw it
+                                const bool longer = fp && fgetc(fp) != EOF;
+                                if (fp) fclose(fp);
+                                if (!fp || rd != len || longer) { errs[x] = std::string("Failed to read ") + paths[done + x]; rcs[x] = 4; continue; }
+                            } else if (len) {
+                                memcpy(dst, raw[x].data(), len);
+                                std::vector<uint8_t>().swap(raw[x]);
+                            }
+                            memset(dst + len, '\n', rb.file_off[f + 1] - rb.file_off[f] - len);
+                            size_t p = 0;
+                            while (p < len && (dst[p] == '\n' || dst[p] == '\r')) p++;
+                            rb.first_byte[f] = rb.file_off[f] + p;
+                        }
+                    };
+                    {
+                        std::vector<std::thread> th;
+                        for (int t = 1; t < nt; t++) th.emplace_back(filler);
+                        filler();
+                        for (auto &t : th) t.join();
+                    }
+                    for (size_t x = b0; x < b1; x++)
+                        if (rcs[x]) { set_error(errs[x]); return GALAH_B200_ERR_IO; }
                     DecodedFiles dec, split;
                     if (int rc = g_ctx.fasta.decode(rb.bytes, rb.file_off, rb.file_len, rb.first_byte, dec, st)) return rc;
                     // contig mode: every record becomes its own unit (split on the device)

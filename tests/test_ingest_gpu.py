@@ -189,3 +189,48 @@ def test_packed_genomes_without_the_validity_bitmap(gb):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
     with pytest.raises(gb.GalahB200Error):
         gb.cluster_packed_sparse(seq2, (np.array([10, 5], np.uint64), np.array([20, 8], np.uint64)), base_off, lengths)
+
+
+def test_file_reads_straight_into_the_staging_buffer(gb, tmp_path):
+    """Plain files are read by the host threads directly into the pinned K0 staging buffer (sizes from a probe),
+    gzip twins are inflated first: an empty file, a file that starts with blank lines, a file shorter than the
+    probe's 4 kB head, a 5 kB run of blank lines before the header (undecided head: the batch takes the host packer),
+    plain / gz mixed -- same sketch rows as the host packer; a FASTQ file in the batch and a missing file behave as before."""
+    rng = np.random.default_rng(11)
+    recs = [("c0", random_dna(30_011, rng)), ("c1", random_dna(9_973, rng))]
+    paths = [write_fasta(str(tmp_path / "plain.fna"), recs),
+             write_fasta(str(tmp_path / "twin.fna.gz"), recs, gz=True),
+             write_fasta(str(tmp_path / "short.fna"), [("s", random_dna(700, rng))])]
+    empty = str(tmp_path / "empty.fna")
+    open(empty, "wb").close()
+    blank = str(tmp_path / "blank_start.fna")
+    with open(blank, "wb") as f:
+        f.write(b"\n\r\n\n" + open(paths[0], "rb").read())
+    paths += [empty, blank]
+
+    def both(plist):
+        prev = gb.device_ingest(1)
+        try:
+            dev = gb.sketch_files(plist, 21, 1000)
+            gb.device_ingest(0)
+            host = gb.sketch_files(plist, 21, 1000)
+        finally:
+            gb.device_ingest(prev)
+        assert np.array_equal(dev[0], host[0]) and np.array_equal(dev[1], host[1])
+        return dev
+    t, c = both(paths)
+    assert c[0] == c[1] == c[4] == 1000 and np.array_equal(t[0], t[1]) and np.array_equal(t[0], t[4])
+    assert c[3] == 0 and 0 < c[2] <= 680
+    long_blank = str(tmp_path / "long_blank.fna")
+    with open(long_blank, "wb") as f:
+        f.write(b"\n" * 5000 + open(paths[0], "rb").read())
+    t2, c2 = both(paths + [long_blank])
+    assert np.array_equal(t2[5], t[0]) and np.array_equal(t2[:5], t)
+    fq = str(tmp_path / "reads.fq")
+    with open(fq, "wb") as f:
+        f.write(b"@r1\n" + recs[0][1][:5000] + b"\n+\n" + b"I" * 5000 + b"\n")
+    t3, c3 = both([paths[0], fq])
+    assert np.array_equal(t3[0], t[0]) and c3[1] > 0
+    with pytest.raises(gb.GalahB200Error) as e:
+        gb.sketch_files([paths[0], str(tmp_path / "missing.fna")], 21, 1000)
+    assert "Failed to open fasta file" in str(e.value)
