@@ -422,7 +422,7 @@ def cluster_from_distances_batched(n_genomes, hits, ani_threshold, calculate_ani
 
 
 def cluster_lazy(mode):
-    """Stage 2 of the one-call pipelines: 0 = every precluster hit up front, 1 = in waves, -1 = by hit density (default)."""
+    """Stage 2 of the one-call pipelines: 0 = every precluster hit up front, 1 / -1 = in waves (default)."""
     check(lib().galah_b200_cluster_lazy(int(mode)))
 
 

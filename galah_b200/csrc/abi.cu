@@ -1375,7 +1375,7 @@ int galah_b200_cluster_from_distances_batched(size_t n_genomes, const galah_b200
                                max_waves ? max_waves : 16, n_waves);
 }
 
-// -1: by the density of the hit list (default), 0: every precluster hit evaluated up front, 1: in waves
+// 0: every precluster hit evaluated up front; 1 / -1 (default): in waves
 static std::atomic<int> g_lazy_mode{-1};
 int galah_b200_cluster_lazy(int mode) {
     if (mode < -1 || mode > 1) { set_error("cluster_lazy: mode must be -1 (auto), 0 (eager) or 1 (waves)"); return GALAH_B200_ERR_ARG; }
@@ -1452,12 +1452,13 @@ static int cluster_from_resident(const uint64_t *d_table, const uint32_t *d_coun
     if (int rc = run_prefilter(d_table, d_counts, n, s, k, precluster_min_ani, 0, 1, st, &hits, &n_hits)) return rc;
     struct HitGuard { galah_b200_pair_t *h; ~HitGuard() { free(h); } } hit_guard{hits};
     const double t1 = now_ms();
-    // Dense hit lists (collections of near-identical genomes, galah's stated use case): stage 2 in waves --
-    // only the (representative, genome) pairs the reference's two passes evaluate, a batch per wave, all
-    // preclusters together.  Sparse lists: one launch over every hit (+ one for the reverse orientations)
-    // is cheaper than the waves' round trips.  Same clusters either way.
+    // Stage 2 in waves (default): only the (representative, genome) pairs the reference's two passes evaluate
+    // (src/clusterer.rs:216-300, 350-449), a batch per wave, all preclusters together.  A collection of
+    // near-identical genomes (galah's stated use case) needs representatives x genomes evaluations instead of
+    // one per hit; synthetic families of 10 need about a third of their hits' two orientations, in 3 waves.
+    // galah_b200_cluster_lazy(0) evaluates every hit up front instead.  Same clusters either way.
     const int lazy_mode = g_lazy_mode.load();
-    if (lazy_mode == 1 || (lazy_mode < 0 && n_hits >= 16 * n)) {
+    if (lazy_mode != 0) {
         double ani_ms = 0.0;
         float chain_ms = 0.f;
         size_t n_asked = 0;

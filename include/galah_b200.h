@@ -318,10 +318,9 @@ int galah_b200_cluster_from_distances_batched(size_t n_genomes, const galah_b200
                                               float ani_threshold, galah_b200_ani_batch_fn calculate_ani_batch,
                                               void *ctx, uint32_t max_waves, galah_b200_clusters_t *out,
                                               uint32_t *n_waves);
-/* How the one-call pipelines (galah_b200_cluster_files / _packed*) run stage 2: 0 = K3 on every
- * precluster hit up front (+ one launch for the reverse orientations the membership pass needs),
- * 1 = in waves as above, -1 (default) = waves when the hit list is dense (>= 16 hits per genome).
- * The clusters are the same in every mode. */
+/* How the single-device one-call pipelines (galah_b200_cluster_files / _packed*) run stage 2:
+ * 1 or -1 (default) = in waves as above, 0 = K3 on every precluster hit up front (+ one launch for
+ * the reverse orientations the membership pass needs).  The clusters are the same in both modes. */
 int galah_b200_cluster_lazy(int mode);
 void galah_b200_clusters_free(galah_b200_clusters_t *c);
 
