@@ -627,7 +627,7 @@ def single_gpu_records(args, gb, torch, dev, d_seq, d_val, d_off, base_off, leng
             finally:
                 gb.cluster_lazy(-1)
         two_stage(-1)  # warm-up (workspaces sized for this input)
-        cl, info, t_full = two_stage(-1)   # default: stage 2 in waves on a hit list this dense
+        cl, info, t_full = two_stage(-1)   # default: stage 2 in waves
         cl_e, info_e, t_eager = two_stage(0)  # K3 on every precluster hit up front
         out["dense"] = {"workload": f"ONE clade: {nd} genomes x {L} bp derived from one founder at 0..2.5 % substitutions "
                                     "(every pair related; every block pair of the join is tie-dense)",
@@ -637,7 +637,7 @@ def single_gpu_records(args, gb, torch, dev, d_seq, d_val, d_off, base_off, leng
                         "two_stage_s": t_full, "two_stage_pairs_per_s": P / t_full, "prefilter_hits": int(info["n_precluster_hits"]),
                         "phases_ms": {k: info[k] for k in ("sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms")},
                         "clusters": len(cl), "stage2": "in waves: only the (representative, genome) pairs the reference's two "
-                        "passes evaluate (galah_b200_cluster_lazy, default on dense hit lists)",
+                        "passes evaluate (galah_b200_cluster_lazy, the default)",
                         "ani_pairs_evaluated": int(info["n_ani_pairs"]), "ani_waves": int(info["ani_waves"]),
                         "eager": {"two_stage_s": t_eager, "two_stage_pairs_per_s": P / t_eager,
                                   "ani_pairs_evaluated": int(info_e["n_ani_pairs"]),
