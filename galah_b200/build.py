@@ -69,7 +69,18 @@ def build(force=False, verbose=False):
                                                                "-Xcompiler", "-pthread", "-l:libz.so.1"]
         subprocess.check_call(link)
     build_cli(force)
+    build_tools(force)
     return LIB_PATH
+
+
+def build_tools(force=False):
+    """tools/bin/pipe_bench: the integer pipe-rate micro-benchmark behind K1's instruction roofline (tools/pipe_bench.cu)."""
+    src = os.path.join(PKG_DIR, "..", "tools", "pipe_bench.cu")
+    out = os.path.join(PKG_DIR, "..", "tools", "bin", "pipe_bench")
+    if os.path.exists(src) and (force or _stale(out, [src])):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call([_nvcc(), "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src])
+    return out
 
 
 CLI_PATH = os.path.join(PKG_DIR, "galah-b200")
