@@ -79,7 +79,7 @@ def build_tools(force=False):
     out = os.path.join(PKG_DIR, "..", "tools", "bin", "pipe_bench")
     if os.path.exists(src) and (force or _stale(out, [src])):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call([_nvcc(), "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src])
+        subprocess.check_call([_nvcc(), "-O3", "-diag-suppress", "177", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, src])
     return out
 
 
