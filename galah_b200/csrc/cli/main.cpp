@@ -10,6 +10,7 @@
 // filtering -- genomes are clustered in the order given, which is what the reference does without quality
 // input (cluster_argument_parsing.rs:880-883) --, the fastANI backend, --full-help.
 #include <dirent.h>
+#include <errno.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,7 +33,7 @@ struct Options {
     float ani = 95.f, min_af = 15.f, precluster_ani = 90.f;  // crate::DEFAULT_* (src/lib.rs:78-85)
     std::string precluster_method = "skani", cluster_method = "skani";
     bool small_genomes = false, cluster_contigs = false, small_contigs = false, large_contigs = false, low_memory = false;
-    int threads = 1, gpus = 1, device = 0;
+    int threads = 0, gpus = 1, device = 0;  // threads: 0 = every host core (they only read and inflate files)
     bool quiet = false;
     std::string out_clusters, out_rep_list, out_rep_dir, out_rep_dir_copy;
 };
@@ -58,7 +59,7 @@ void usage(FILE *f) {
           "  --cluster-method <skani>     [default: skani]  --small-genomes   --low-memory\n"
           "  --cluster-contigs (with --small-contigs or --large-contigs)\n"
           "  --reference-genomes <PATH>... | --reference-genomes-list <FILE>\n"
-          "  -t, --threads <N>            host threads for reading files [default: 1]\n"
+          "  -t, --threads <N>            host threads for reading files [default: all cores; galah's default is 1]\n"
           "  --gpus <N>                   devices of this box to use [default: 1]   --device <ID> [default: 0]\n"
           "Output (at least one):\n"
           "  -o, --output-cluster-definition <FILE>      representative<TAB>member lines\n"
@@ -163,7 +164,7 @@ Options parse(int argc, char **argv) {
     if (o.out_clusters.empty() && o.out_rep_list.empty() && o.out_rep_dir.empty() && o.out_rep_dir_copy.empty())
         die("error: the following required arguments were not provided:\n  --output-cluster-definition <output-cluster-definition>\n"
             "  (or one of --output-representative-list, --output-representative-fasta-directory[-copy])", 2);
-    if (o.threads < 1) o.threads = 1;
+    if (o.threads < 0) o.threads = 0;
     if (o.gpus < 1) die("error: --gpus must be at least 1", 2);
     return o;
 }

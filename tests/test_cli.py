@@ -158,3 +158,32 @@ def test_cluster_definition_rep_directories_and_low_memory(gb, tmp_path):
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout)
     assert outs[0] == outs[1] == want  # src/clusterer.rs:692-723, 759-791
+
+
+@pytest.mark.gpu
+def test_reference_genomes_and_directory_input(gb, tmp_path):
+    """--reference-genomes (src/skani.rs:502-687 through the CLI: references first in the combined list, clusters only
+    across the two groups) and -d / -x directory input (sorted listing)."""
+    import shutil
+    from stage2_cases import AB
+    p = [g(f) for f in AB]
+    r = run("cluster", "-f", p[1], p[3], p[2], "--reference-genomes", p[0], "--ani", "99", "--min-aligned-fraction", "20",
+            "-o", "/dev/stdout", "-q")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == lines((p[0], p[0]), (p[0], p[1]), (p[0], p[3]), (p[2], p[2]))
+    listing = tmp_path / "refs.txt"
+    listing.write_text(p[0] + "\n\n")
+    r2 = run("cluster", "-f", p[1], p[3], p[2], "--reference-genomes-list", str(listing), "--ani", "99", "--min-aligned-fraction", "20",
+             "-o", "/dev/stdout", "-q")
+    assert r2.returncode == 0 and r2.stdout == r.stdout, r2.stderr
+    d = tmp_path / "genomes"
+    d.mkdir()
+    for f in (p[0], p[1]):
+        shutil.copy(f, d / os.path.basename(f))
+    (d / "notes.txt").write_text("not a genome")
+    r = run("cluster", "-d", str(d), "-x", "gz", "--ani", "99", "--min-aligned-fraction", "20", "-o", "/dev/stdout", "-q")
+    assert r.returncode == 0, r.stderr
+    first, second = sorted(str(d / os.path.basename(f)) for f in (p[0], p[1]))
+    assert r.stdout == lines((first, first), (first, second))
+    r = run("cluster", "-d", str(d), "-x", "fasta", "-o", "/dev/stdout", "-q")
+    assert r.returncode == 1 and "Found 0 genomes" in r.stderr
