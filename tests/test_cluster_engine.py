@@ -294,3 +294,24 @@ def test_large_dense_list_threaded_adjacency():
     extra[0]["ani"] = 1.0  # overwritten by the later record of the same key
     again, _ = gb.cluster_from_distances(n, extra, 95.0, None, skip_clusterer=True)
     assert again == want
+
+
+def test_wave_engine_long_chains_take_the_one_batch_finish():
+    """A path graph of 60 genomes whose neighbours are all BELOW the threshold: every genome is a representative and
+    genome i is only settled once i - 1 has been applied -- 60 dependent waves.  The default budget (16 waves) ends in
+    the one-batch finish; a budget of 100 walks the whole chain.  Same clusters and -- with the budget large enough --
+    the same calculate_ani count as the serial engine.  Then the same path with every third link ABOVE the threshold."""
+    n = 60
+    pairs = [(i, i + 1, 0.95) for i in range(n - 1)]
+    hits = make_hits(pairs)
+    for rule in (lambda r, g: 90.0, lambda r, g: 97.0 if min(r, g) % 3 == 0 else 90.0):
+        serial, sinfo = gb.cluster_from_distances(n, hits, 95.0, rule)
+        exp, einfo = co.cluster(n, pairs, 95.0, rule)
+        assert serial == exp and sinfo["ani_calls"] == einfo["ani_calls"]
+        short, winfo = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(rule))
+        assert short == serial and winfo["ani_waves"] <= 18
+        full, finfo = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(rule), max_waves=100)
+        assert full == serial and finfo["ani_calls"] == sinfo["ani_calls"]
+    # all below the threshold: one wave per genome of the chain but the last
+    alone, ainfo = gb.cluster_from_distances_batched(n, hits, 95.0, _batch_of(lambda r, g: 90.0), max_waves=100)
+    assert alone == [[g] for g in range(n)] and ainfo["ani_waves"] == n - 1
