@@ -329,8 +329,9 @@ void galah_b200_clusters_free(galah_b200_clusters_t *c);
  * ani_threshold_pct (PERCENT), min_aligned_threshold: min_af_pct / 100, small_genomes}, false,
  * None, None) (src/clusterer.rs:14-152 as called from src/cluster_argument_parsing.rs:1514-1530).
  * Every file is read and uploaded once; K1 sketches and the K3 index are built from the same
- * device buffers; K2 gives the precluster hits; K3 evaluates every hit pair; the host engine
- * does the greedy selection.  Cluster order is the reference's at --threads 1. */
+ * device buffers; K2 gives the precluster hits; the host engine does the greedy selection and
+ * asks K3, a batch per wave, for the hit pairs it needs (galah_b200_cluster_lazy).  Cluster order
+ * is the reference's at --threads 1. */
 typedef struct galah_b200_cluster_stats {
     uint64_t n_precluster_hits;
     uint64_t n_ani_pairs;
