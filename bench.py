@@ -5,9 +5,8 @@ A "step" is ONE pass of the whole hot path (reference src/clusterer.rs:14-152 dr
 src/finch.rs:48-97 and src/skani.rs:689-788) over N synthetic genomes (families of
 10, 2 Mbp, seed 1): K1 MinHash sketches + K3 seed index of every genome, K2 all-pairs prefilter
 (finch, min_ani 0.9), K3 ANI (skani restatement, 95 %, min-AF 15) of the prefilter hits the greedy
-selection asks about -- on one GPU exactly the (representative, genome) pairs the reference's two
-passes evaluate, a batch per wave of the engine; in the sharded runs every hit in both orientations --,
-greedy representative selection.  At --gpus 1 the workload is BASELINE.json configs[2]: 50,000 genomes.
+selection asks about -- exactly the (representative, genome) pairs the reference's two passes
+evaluate, a batch per wave of the engine --, greedy representative selection.  At --gpus 1 the workload is BASELINE.json configs[2]: 50,000 genomes.
 Genome synthesis is setup (untimed); everything the reference does inside cluster() is timed.
 
   value    = N(N-1)/2 pairs / step time, packed genomes resident in HBM when the step starts
@@ -478,9 +477,8 @@ def main():
         n_eval = int(infos[-1].get("my_ani_pairs") or infos[-1].get("n_ani_pairs") or n_hits)
         add("K3 chain", ["ani_chain_kernel"], phase.get("ani_chain_ms"), n_eval, "pair evaluation",
             2 * seeds_per_genome * 12, "latency of table probes (L2 / HBM) + SIMT divergence of the chaining step",
-            "2 * (L/c) * 12 B seed entries per pair (SURVEY.md 8d); every K3 launch of a step: 1 GPU -- one per wave of the "
-            "greedy engine, only the (representative, genome) pairs the reference's two passes evaluate; sharded runs -- "
-            "all hits, then the reverse orientations the membership pass asks for")
+            "2 * (L/c) * 12 B seed entries per pair (SURVEY.md 8d); every K3 launch of a step: one per wave of the greedy "
+            "engine, only the (representative, genome) pairs the reference's two passes evaluate (sharded runs: this rank's share)")
         if fam and fam[-1]["family"] == "K3 chain":
             fam[-1]["ani_waves"] = int(infos[-1].get("ani_waves", 0))
             fam[-1]["prefilter_hits"] = n_hits
@@ -520,9 +518,9 @@ def main():
             "config": {"workload": workload_text(n, L, world), "pairs_per_step": pairs, "genomes": n,
                        "l2": f"inputs larger than L2 ({resident_bytes >> 20} MiB of packed sequence per GPU, read once per step)",
                        "timed_region": "K1 sketch + K3 index of every genome, K2 all pairs, " +
-                                       ("K3 ANI of the (representative, genome) hit pairs the reference's greedy passes evaluate, "
-                                        "asked for in waves by the engine, " if world == 1 else
-                                        "K3 ANI of every prefilter hit in both orientations, ") +
+                                       "K3 ANI of the (representative, genome) hit pairs the reference's greedy passes evaluate, "
+                                       "asked for in waves by the engine" + (", " if world == 1 else " (replicated on every rank; a request "
+                                       "runs on the owner of its query, a wave's values are all-gathered), ") +
                                        "f64 finish + greedy engine on the host; genome synthesis is setup",
                        "sharding": "one process per GPU: genome slices for K1 / K3 index, boustrophedon row blocks for K2 "
                                    "(NCCL all-gather of the sketch table), K3 pairs on the query's rank reading the "

@@ -386,7 +386,8 @@ def cluster_from_distances(n_genomes, hits, ani_threshold, calculate_ani=None, s
 
 def cluster_from_distances_batched(n_genomes, hits, ani_threshold, calculate_ani_batch, max_waves=0):
     """The clustering engine with stage 2 asked for in waves: `calculate_ani_batch(reps, genomes)` gets two
-    uint32 arrays (reps[x] is the query) and returns one float or None per pair.  Same clusters, order and
+    uint32 arrays (reps[x] is the query) and returns one float or None per pair (or a numpy float array when every
+    pair has a value).  Same clusters, order and
     ani_calls as cluster_from_distances; info["ani_waves"] = batches asked."""
     hits = np.ascontiguousarray(hits, PAIR_DTYPE)
     calls = {"exc": None}
@@ -398,9 +399,13 @@ def cluster_from_distances_batched(n_genomes, hits, ani_threshold, calculate_ani
             vals = calculate_ani_batch(r, g)
             if len(vals) != n:
                 raise ValueError("calculate_ani_batch: one value per pair")
-            for x, v in enumerate(vals):
-                some[x] = 0 if v is None else 1
-                ani[x] = 0.0 if v is None else float(v)
+            if isinstance(vals, np.ndarray):  # a float array: every pair has a value (no per-element Python work)
+                np.ctypeslib.as_array(ani, shape=(n,))[:] = vals.astype(np.float32, copy=False)
+                np.ctypeslib.as_array(some, shape=(n,))[:] = 1
+            else:
+                for x, v in enumerate(vals):
+                    some[x] = 0 if v is None else 1
+                    ani[x] = 0.0 if v is None else float(v)
         except BaseException as e:  # never unwind through C
             calls["exc"] = e
             return 1

@@ -285,6 +285,59 @@ def route_hits(hits_i, n_local, world):
     return np.minimum(np.asarray(hits_i, dtype=np.int64) // n_local, world - 1)
 
 
+def allgather_var(dist, dev, arr, dtype, width):
+    """All-gather of per-rank (m_r, width) host arrays of `dtype` through one padded collective on `dev` (the sizes
+    travel first).  Returns one array per rank."""
+    import torch as t
+    world = dist.get_world_size()
+    m = t.tensor([len(arr)], dtype=t.int64, device=dev)
+    ms = t.empty(world, dtype=t.int64, device=dev)
+    dist.all_gather_into_tensor(ms, m)
+    ms = ms.cpu().numpy()
+    cap = int(ms.max())
+    if cap == 0:
+        return [np.zeros((0, width), dtype) for _ in range(world)]
+    buf = np.zeros((cap, width), dtype)
+    buf[: len(arr)] = arr
+    mine = t.from_numpy(buf.view(np.uint8).reshape(-1)).to(dev)
+    allb = t.empty(world * mine.numel(), dtype=t.uint8, device=dev)
+    dist.all_gather_into_tensor(allb, mine)
+    allb = allb.cpu().numpy().view(dtype).reshape(world, cap, width)
+    return [allb[r, : int(ms[r])] for r in range(world)]
+
+
+def cluster_in_waves_replicated(gb, dist, dev, hits, n, n_local, ani_threshold, evaluate_mine, stats=None):
+    """Stage 2 + the greedy engine on every rank of a sharded run.  All ranks hold the same hit list, so their engines
+    (galah_b200_cluster_from_distances_batched) ask for the same (representative, genome) pairs wave by wave -- exactly
+    the pairs the reference's two passes evaluate (src/clusterer.rs:216-300, 350-449; the representative is the query).
+    A request is evaluated by the rank that owns its QUERY genome (`evaluate_mine(q, r)`: global ids -> float32 ANIs),
+    the values of a wave are all-gathered (8 B per request) and every engine moves on identically: one small
+    collective per wave, no gather of all hits' values in both orientations.  Returns (clusters, info) on every rank."""
+    import time
+    rank, world = dist.get_rank(), dist.get_world_size()
+    stats = stats if stats is not None else {}
+    for k in ("pairs_ms", "gather_ms", "mine", "asked"):
+        stats.setdefault(k, 0)
+
+    def ani_batch(reps, genomes):
+        ta = time.perf_counter()
+        q, r = reps.astype(np.int64), genomes.astype(np.int64)
+        my = np.nonzero(route_hits(q, n_local, world) == rank)[0]
+        back = np.zeros((len(my), 2), np.uint32)
+        back[:, 0] = my
+        if len(my):
+            back[:, 1] = np.ascontiguousarray(evaluate_mine(q[my], r[my]), np.float32).view(np.uint32)
+        tb = time.perf_counter()
+        out = np.zeros(len(reps), np.float32)
+        for part in allgather_var(dist, dev, back, np.uint32, 2):
+            out[part[:, 0]] = part[:, 1].view(np.float32)
+        stats["pairs_ms"] += 1e3 * (tb - ta); stats["gather_ms"] += 1e3 * (time.perf_counter() - tb)
+        stats["mine"] += len(my); stats["asked"] += len(reps)
+        return out
+
+    return gb.cluster_from_distances_batched(n, hits, ani_threshold, ani_batch)
+
+
 class ShardedPipeline:
     """The whole two-stage path on G GPUs, one process per GPU (bench.py at --gpus > 1; BASELINE.json
     configs[3]): rank r owns genomes [r n_local, (r + 1) n_local).
@@ -311,22 +364,7 @@ class ShardedPipeline:
         self._idx = {}   # small_genomes -> AniIndex, cleared and re-used per step (no cudaMalloc / cudaFree in a step)
 
     def _allgather_var(self, arr, dtype, width):
-        """All-gather of per-rank (m_r, width) host arrays of `dtype` through one padded device collective."""
-        t, dist = self.torch, self.dist
-        m = t.tensor([len(arr)], dtype=t.int64, device=self.dev)
-        ms = t.empty(self.world, dtype=t.int64, device=self.dev)
-        dist.all_gather_into_tensor(ms, m)
-        ms = ms.cpu().numpy()
-        cap = int(ms.max())
-        if cap == 0:
-            return [np.zeros((0, width), dtype) for _ in range(self.world)]
-        buf = np.zeros((cap, width), dtype)
-        buf[: len(arr)] = arr
-        mine = t.from_numpy(buf.view(np.uint8).reshape(-1)).to(self.dev)
-        allb = t.empty(self.world * mine.numel(), dtype=t.uint8, device=self.dev)
-        dist.all_gather_into_tensor(allb, mine)
-        allb = allb.cpu().numpy().view(dtype).reshape(self.world, cap, width)
-        return [allb[r, : int(ms[r])] for r in range(self.world)]
+        return allgather_var(self.dist, self.dev, arr, dtype, width)
 
     def _route_var(self, arr, dest, dtype, width):
         """Variable all-to-all of the rows of a host (m, width) array of `dtype`: row x goes to rank
@@ -387,56 +425,55 @@ class ShardedPipeline:
         order = np.argsort((allh[:, 0].astype(np.uint64) << np.uint64(32)) | allh[:, 1].astype(np.uint64), kind="stable")
         allh = allh[order]
         tm["hits_gather_sort_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
-        # ---- stage-2 jobs: both orientations of every hit (calculate_ani(rep, genome) makes the
-        # representative the query, and the membership pass asks for representatives on either side of
-        # the genome); a job runs on the rank that owns its QUERY genome
+        # ---- stage 2 in waves, the greedy engine REPLICATED on every rank: all ranks hold the same hit list, so their
+        # engines ask for the same (representative, genome) pairs wave by wave -- exactly the pairs the reference's two
+        # passes evaluate (src/clusterer.rs:216-300, 350-449; calculate_ani(rep, genome) makes the representative the
+        # query).  A request runs on the rank that owns its QUERY genome, reading the other genome's table in place on
+        # its peer; the values of a wave are all-gathered (8 B per request) and every engine moves on identically.
         q_all = np.concatenate([allh[:, 0], allh[:, 1]]).astype(np.int64)
         r_all = np.concatenate([allh[:, 1], allh[:, 0]]).astype(np.int64)
-        owner = route_hits(q_all, n_local, world)
-        my_jobs = np.nonzero(owner == rank)[0]
-        # ---- peer tables: IPC handles + per-genome offsets are exchanged (host metadata, 16 B / genome)
+        mine_possible = route_hits(q_all, n_local, world) == rank
         tm["jobs_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
+        # ---- peer tables: IPC handles + per-genome offsets are exchanged (host metadata, 16 B / genome)
         handle, table_off, total_len = idx.export_tables()
         metas = [None] * world
         dist.all_gather_object(metas, (handle, table_off, total_len))
         tm["meta_exchange_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
-        r_owner = route_hits(r_all[my_jobs], n_local, world)
         base = np.zeros(world, np.int64)      # id of a rank's first genome in this index's numbering
-        for peer in sorted(set(int(x) for x in r_owner) - {rank}):
+        for peer in sorted(set(int(x) for x in route_hits(r_all[mine_possible], n_local, world)) - {rank}):
             base[peer] = idx.attach_peer(*metas[peer])
         tm["attach_ms"] = 1e3 * (time.perf_counter() - tq); tq = time.perf_counter()
-        q_local = q_all[my_jobs] - rank * n_local
-        r_id = base[r_owner] + (r_all[my_jobs] - r_owner * n_local)
-        pairs = np.stack([q_local, r_id], axis=1).astype(np.uint32)
-        res = idx.pairs(pairs, min_af)
-        chain_ms = idx.last_timing()[1]
-        tm["pairs_call_ms"] = 1e3 * (time.perf_counter() - tq)
+        hits = np.zeros(len(allh), PAIR_DTYPE)
+        hits["i"], hits["j"], hits["common"], hits["total"] = allh[:, 0], allh[:, 1], allh[:, 2], allh[:, 3]
+        hits["ani"] = allh[:, 4].view(np.float32)
+        wave = {"chain_ms": 0.0, "remote": 0}
+
+        def evaluate_mine(q, r):  # global genome ids of the pairs whose query this rank owns
+            r_owner = route_hits(r, n_local, world)
+            pairs = np.stack([q - rank * n_local, base[r_owner] + (r - r_owner * n_local)], axis=1).astype(np.uint32)
+            res = idx.pairs(pairs, min_af)
+            wave["chain_ms"] += idx.last_timing()[1]
+            wave["remote"] += int(np.sum(r_owner != rank))
+            return res["ani"]
+
+        clusters, cinfo = cluster_in_waves_replicated(gb, dist, self.dev, hits, n, n_local, ani_pct, evaluate_mine, wave)
         t3 = time.perf_counter()
-        # ---- ANI values to rank 0 (job id + f32 bits), engine there
-        back = np.zeros((len(my_jobs), 2), np.uint32)
-        back[:, 0] = my_jobs
-        back[:, 1] = res["ani"].view(np.uint32)
-        got_back = self._allgather_var(back, np.uint32, 2)
         dist.barrier()          # every peer has finished reading this rank's tables
         idx.clear()             # detaches the peers; the allocations stay for the next step
-        tm["ani_gather_ms"] = 1e3 * (time.perf_counter() - t3); tq = time.perf_counter()
-        clusters = None
-        if rank == 0:
-            ani = np.zeros(2 * len(allh), np.float32)
-            for part in got_back:
-                ani[part[:, 0]] = part[:, 1].view(np.float32)
-            hits = np.zeros(len(allh), PAIR_DTYPE)
-            hits["i"], hits["j"], hits["common"], hits["total"] = allh[:, 0], allh[:, 1], allh[:, 2], allh[:, 3]
-            hits["ani"] = allh[:, 4].view(np.float32)
-            clusters, cinfo = gb.cluster_from_ani_tables(n, hits, ani[: len(allh)], ani[len(allh):], ani_pct)
-            info.update(cinfo)
-            tm["engine_call_ms"] = 1e3 * (time.perf_counter() - tq)
+        chain_ms = wave["chain_ms"]
+        tm["pairs_call_ms"] = wave["pairs_ms"]; tm["ani_gather_ms"] = wave["gather_ms"]
+        tm["engine_call_ms"] = 1e3 * (t3 - tq) - wave["pairs_ms"] - wave["gather_ms"]
+        info.update(cinfo)
+        if rank != 0:
+            clusters = None
         info["host_detail_ms"] = {k: round(v, 2) for k, v in tm.items()}
         t4 = time.perf_counter()
-        info.update(n_precluster_hits=len(allh), n_ani_pairs=2 * len(allh), my_ani_pairs=len(my_jobs),
-                    remote_reference_pairs=int(np.sum(r_owner != rank)), sketch_ms=k1_ms, index_ms=idx_ms,
-                    ingest_ms=1e3 * (t1 - t0), prefilter_ms=1e3 * (t2 - t1), ani_ms=1e3 * (t3 - t2), ani_chain_ms=chain_ms,
-                    engine_ms=1e3 * (t4 - t3), total_ms=1e3 * (t4 - t0))
+        # ani_ms: K3 launches + the per-wave exchanges; engine_ms: the replicated engine's own work + the closing barrier
+        ani_total = (1e3 * (tq - t2)) + wave["pairs_ms"] + wave["gather_ms"]
+        info.update(n_precluster_hits=len(allh), n_ani_pairs=wave["asked"], my_ani_pairs=wave["mine"],
+                    remote_reference_pairs=wave["remote"], sketch_ms=k1_ms, index_ms=idx_ms,
+                    ingest_ms=1e3 * (t1 - t0), prefilter_ms=1e3 * (t2 - t1), ani_ms=ani_total, ani_chain_ms=chain_ms,
+                    engine_ms=1e3 * (t4 - t2) - ani_total, total_ms=1e3 * (t4 - t0))
         return clusters, info
 
     def run_skani(self, seq2, valid, d_base_off, base_off, lengths, device, threshold_pct=95.0, ani_pct=95.0, min_af=15.0,
