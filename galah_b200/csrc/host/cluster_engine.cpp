@@ -96,6 +96,203 @@ inline uint64_t pair_key(uint32_t a, uint32_t b) {
 
 struct OptAni { bool some; float ani; };
 
+// CSR adjacency of the hit list, both directions, neighbours ascending.  Later duplicates of a key overwrite
+// earlier ones, as BTreeMap::insert does (src/sorted_pair_genome_distance_cache.rs:22-28).
+void build_adjacency(size_t n, const PreclusterHit *hits, size_t n_hits, Adjacency &adj) {
+    adj.off.assign(n + 1, 0);
+    // unique keys, last write wins.  The usual input -- the preclusterer's own output -- is already
+    // strictly ascending by key: then the hits are used as they are; otherwise stable sort by key and
+    // keep the last record of every run.
+    bool sorted = true;
+    for (size_t h = 1; h < n_hits && sorted; h++)
+        sorted = pair_key(hits[h - 1].i, hits[h - 1].j) < pair_key(hits[h].i, hits[h].j);
+    std::vector<uint32_t> uniq;  // indices of the hits that count, ascending by key (unsorted input only)
+    if (!sorted) {
+        uniq.reserve(n_hits);
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
+        for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
+        std::stable_sort(keyed.begin(), keyed.end(),
+                         [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &b) { return a.first < b.first; });
+        for (size_t h = 0; h < n_hits; h++)
+            if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.push_back(keyed[h].second);
+    }
+    const size_t n_uniq = sorted ? n_hits : uniq.size();
+    auto hit_at = [&](size_t u) -> uint32_t { return sorted ? (uint32_t)u : uniq[u]; };
+    for (size_t u = 0; u < n_uniq; u++) {
+        const PreclusterHit &h = hits[hit_at(u)];
+        adj.off[std::min(h.i, h.j) + 1]++;
+        adj.off[std::max(h.i, h.j) + 1]++;
+    }
+    for (size_t g = 0; g < n; g++) adj.off[g + 1] += adj.off[g];
+    adj.nbr.resize(adj.off[n]); adj.ani.resize(adj.off[n]); adj.hit.resize(adj.off[n]);
+    std::vector<uint64_t> fill(adj.off.begin(), adj.off.end() - 1);
+    // keys ascend, so every row receives its neighbours in ascending order: first the smaller
+    // partners (as the second genome of earlier keys), then the larger ones
+    // rows [r0, r1): every thread of a large list walks all hits in key order and writes the slots of its own rows
+    auto fill_rows = [&](uint32_t r0, uint32_t r1) {
+        for (size_t u = 0; u < n_uniq; u++) {
+            const uint32_t x = hit_at(u);
+            const PreclusterHit &h = hits[x];
+            const uint32_t a = std::min(h.i, h.j), b = std::max(h.i, h.j);
+            if (a >= r0 && a < r1) { const uint64_t pa = fill[a]++; adj.nbr[pa] = b; adj.ani[pa] = h.ani; adj.hit[pa] = x; }
+            if (b >= r0 && b < r1) { const uint64_t pb = fill[b]++; adj.nbr[pb] = a; adj.ani[pb] = h.ani; adj.hit[pb] = x; }
+        }
+    };
+    const size_t hw_fill = std::max<size_t>(1, std::thread::hardware_concurrency());
+    const size_t nt_fill = n_uniq >= ((size_t)1 << 19) ? std::min<size_t>(hw_fill, 16) : 1;
+    if (nt_fill == 1) {
+        fill_rows(0, (uint32_t)n);
+    } else {
+        // row ranges holding about the same number of slots (the scattered writes are the cost)
+        std::vector<uint32_t> cut(nt_fill + 1, (uint32_t)n);
+        cut[0] = 0;
+        for (size_t t = 1; t < nt_fill; t++)
+            cut[t] = (uint32_t)(std::lower_bound(adj.off.begin(), adj.off.end(), adj.off[n] / nt_fill * t) - adj.off.begin());
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nt_fill; t++)
+            if (cut[t] < cut[t + 1]) th.emplace_back(fill_rows, cut[t], cut[t + 1]);
+        for (auto &t : th) t.join();
+    }
+}
+
+// partition_sketches (src/clusterer.rs:452-487): single-linkage components of the hit graph, as one flat array
+// (CSR): sets in order of their smallest member, members ascending, then ordered by size, largest first
+// (src/clusterer.rs:67-79; stable, so equal sizes keep the order of their smallest members).
+void partition_preclusters(size_t n, const Adjacency &adj, std::vector<uint32_t> &pc_members, std::vector<uint64_t> &pc_off,
+                           uint32_t &n_preclusters, uint32_t &largest_precluster) {
+    Dsu dsu(n);
+    for (size_t g = 0; g < n; g++)
+        for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++)
+            if (adj.nbr[x] < g) dsu.join((uint32_t)g, adj.nbr[x]);
+    // preclusters as one flat array (CSR): sets in order of their smallest member (the root),
+    // members ascending, then ordered by size, largest first (stable)
+    pc_members.assign(n, 0);
+    {
+        std::vector<uint32_t> set_id(n), set_size;
+        std::vector<int64_t> set_of_root(n, -1);
+        for (uint32_t g = 0; g < n; g++) {
+            const uint32_t r = dsu.find(g);
+            if (set_of_root[r] < 0) { set_of_root[r] = (int64_t)set_size.size(); set_size.push_back(0); }
+            set_id[g] = (uint32_t)set_of_root[r];
+            set_size[set_id[g]]++;
+        }
+        // sets by size, largest first, ties in set order: a counting sort on the size (stable), O(sets + largest)
+        std::vector<uint32_t> order(set_size.size());
+        {
+            uint32_t largest = 0;
+            for (const uint32_t z : set_size) largest = std::max(largest, z);
+            std::vector<uint64_t> at((size_t)largest + 2, 0);  // at[z] = first slot of size z, sizes descending
+            for (const uint32_t z : set_size) at[largest - z + 1]++;
+            for (size_t z = 0; z + 1 < at.size(); z++) at[z + 1] += at[z];
+            for (uint32_t sid = 0; sid < set_size.size(); sid++) order[at[largest - set_size[sid]]++] = sid;
+        }
+        std::vector<uint64_t> start(set_size.size());
+        pc_off.assign(1, 0);
+        for (const uint32_t sid : order) { start[sid] = pc_off.back(); pc_off.push_back(pc_off.back() + set_size[sid]); }
+        for (uint32_t g = 0; g < n; g++) pc_members[start[set_id[g]]++] = g;
+        n_preclusters = (uint32_t)set_size.size();
+        largest_precluster = set_size[order[0]];
+    }
+}
+
+// Representatives found lazily, in waves (AniBatchFn), all preclusters at once.
+// state: 0 open, 1 representative, 2 member.  pending[g] = hit partners below g that are not settled
+// towards g yet: a lower partner settles when it becomes a member, or -- a representative -- when its
+// ANI with g has been applied.  An open genome whose pending count reaches zero without having been
+// claimed (ANI >= threshold with a representative below it) is a representative: exactly
+// src/clusterer.rs:216-259, where genome i is tested against the representatives found before it.
+// Every request is a pair the reference evaluates too: (representative, partner) for every partner
+// that is not an earlier representative (tested in the representative pass if the partner comes
+// later and was still undecided, asked for by the membership pass otherwise).
+// Fills state (1 representative, 2 member), the edge cache with every value asked for, `calls` with the number
+// of pairs asked, `waves_asked` with the number of batches; any_none: some answer was None.
+int representatives_in_waves(size_t n, const Adjacency &adj, float ani_threshold, const AniBatchFn &batch_fn, uint32_t max_waves,
+                             RawBuf<uint8_t> &edge_state, RawBuf<float> &edge_ani, std::vector<uint8_t> &state, uint64_t &calls,
+                             uint32_t &waves_asked, bool &any_none, std::string &err) {
+    state.assign(n, 0);
+    std::vector<uint32_t> pending(n, 0), fresh, ready, claimed;
+    for (uint32_t g = 0; g < n; g++) {
+        for (uint64_t x = adj.off[g]; x < adj.off[g + 1] && adj.nbr[x] < g; x++) pending[g]++;
+        if (!pending[g]) { state[g] = 1; fresh.push_back(g); }
+    }
+    std::vector<AniRequest> reqs;
+    std::vector<uint64_t> slot;  // per request: the edge slot in the GENOME's row (the cache key)
+    std::vector<uint8_t> some;
+    std::vector<float> ani;
+    auto ask = [&]() -> int {
+        if (reqs.empty()) return 0;
+        some.assign(reqs.size(), 0); ani.assign(reqs.size(), 0.f);
+        if (batch_fn(reqs, some.data(), ani.data())) { err = "ANI batch failed"; return 2; }
+        waves_asked++;
+        calls += reqs.size();
+        for (size_t q = 0; q < reqs.size(); q++) {
+            edge_state[slot[q]] = some[q] ? 1 : 2; edge_ani[slot[q]] = ani[q];
+            any_none = any_none || !some[q];
+        }
+        return 0;
+    };
+    uint32_t waves = 0;
+    while (!fresh.empty() && waves < max_waves) {
+        waves++;
+        reqs.clear(); slot.clear();
+        for (const uint32_t r : fresh)
+            for (uint64_t y = adj.off[r]; y < adj.off[r + 1]; y++) {
+                const uint32_t i = adj.nbr[y];
+                if (state[i] == 1) continue;  // an earlier representative: (i, r) was asked for when i was confirmed
+                reqs.push_back(AniRequest{r, i, adj.hit[y]});
+                slot.push_back((uint64_t)adj.find(i, r));  // the same edge in i's row
+            }
+        if (int rc = ask()) return rc;
+        ready.clear(); claimed.clear();
+        for (size_t q = 0; q < reqs.size(); q++) {
+            const uint32_t r = reqs[q].rep, i = reqs[q].genome;
+            if (i < r) continue;  // a member below the representative: only its membership needs the value
+            if (state[i] == 0 && some[q] && ani[q] >= ani_threshold) { state[i] = 2; claimed.push_back(i); }
+            if (--pending[i] == 0) ready.push_back(i);
+        }
+        for (const uint32_t m : claimed)
+            for (uint64_t y = adj.off[m + 1]; y-- > adj.off[m] && adj.nbr[y] > m;)
+                if (--pending[adj.nbr[y]] == 0) ready.push_back(adj.nbr[y]);
+        fresh.clear();
+        for (const uint32_t g : ready)
+            if (state[g] == 0) { state[g] = 1; fresh.push_back(g); }
+    }
+    if (!fresh.empty()) {
+        // wave budget spent (long chains of mutually distant genomes): everything the undecided genomes
+        // can still ask about in ONE batch -- the pairs of the representatives confirmed last, and for
+        // every open genome its open partners below it --, then the undecided genomes are settled in index order
+        reqs.clear(); slot.clear();
+        for (const uint32_t r : fresh)
+            for (uint64_t y = adj.off[r]; y < adj.off[r + 1]; y++) {
+                const uint32_t i = adj.nbr[y];
+                if (state[i] == 1) continue;
+                reqs.push_back(AniRequest{r, i, adj.hit[y]});
+                slot.push_back((uint64_t)adj.find(i, r));  // the same edge in i's row
+            }
+        for (uint32_t i = 0; i < n; i++) {
+            if (state[i] != 0) continue;
+            for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
+                if (state[adj.nbr[x]] == 0) { reqs.push_back(AniRequest{adj.nbr[x], i, adj.hit[x]}); slot.push_back(x); }
+        }
+        if (int rc = ask()) return rc;
+        for (uint32_t i = 0; i < n; i++) {
+            if (state[i] != 0) continue;
+            state[i] = 1;
+            for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
+                if (state[adj.nbr[x]] == 1 && edge_state[x] == 1 && edge_ani[x] >= ani_threshold) { state[i] = 2; break; }
+        }
+    }
+    // what the membership sweep reads and nobody asked for yet (only after the one-batch finish)
+    reqs.clear(); slot.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        if (state[i] != 2) continue;
+        for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++)
+            if (state[adj.nbr[x]] == 1 && !edge_state[x]) { reqs.push_back(AniRequest{adj.nbr[x], i, adj.hit[x]}); slot.push_back(x); }
+    }
+    if (int rc = ask()) return rc;
+    return 0;
+}
+
 }  // namespace
 
 int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool skip_clusterer,
@@ -121,101 +318,15 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
     if (!skip_clusterer && !calculate_ani_fn && !by_hit && !batch) { err = "calculate_ani callback required"; return 1; }
     const bool lazy = batch && !skip_clusterer;
 
-    // ---- adjacency (later duplicates of a key overwrite earlier ones, as BTreeMap::insert does)
+    // ---- adjacency
     Adjacency adj;
-    adj.off.assign(n + 1, 0);
-    {
-        // unique keys, last write wins.  The usual input -- the preclusterer's own output -- is already
-        // strictly ascending by key: then the hits are used as they are; otherwise stable sort by key and
-        // keep the last record of every run.
-        bool sorted = true;
-        for (size_t h = 1; h < n_hits && sorted; h++)
-            sorted = pair_key(hits[h - 1].i, hits[h - 1].j) < pair_key(hits[h].i, hits[h].j);
-        std::vector<uint32_t> uniq;  // indices of the hits that count, ascending by key (unsorted input only)
-        if (!sorted) {
-            uniq.reserve(n_hits);
-            std::vector<std::pair<uint64_t, uint32_t>> keyed(n_hits);
-            for (size_t h = 0; h < n_hits; h++) keyed[h] = {pair_key(hits[h].i, hits[h].j), (uint32_t)h};
-            std::stable_sort(keyed.begin(), keyed.end(),
-                             [](const std::pair<uint64_t, uint32_t> &a, const std::pair<uint64_t, uint32_t> &b) { return a.first < b.first; });
-            for (size_t h = 0; h < n_hits; h++)
-                if (h + 1 == n_hits || keyed[h + 1].first != keyed[h].first) uniq.push_back(keyed[h].second);
-        }
-        const size_t n_uniq = sorted ? n_hits : uniq.size();
-        auto hit_at = [&](size_t u) -> uint32_t { return sorted ? (uint32_t)u : uniq[u]; };
-        for (size_t u = 0; u < n_uniq; u++) {
-            const PreclusterHit &h = hits[hit_at(u)];
-            adj.off[std::min(h.i, h.j) + 1]++;
-            adj.off[std::max(h.i, h.j) + 1]++;
-        }
-        for (size_t g = 0; g < n; g++) adj.off[g + 1] += adj.off[g];
-        adj.nbr.resize(adj.off[n]); adj.ani.resize(adj.off[n]); adj.hit.resize(adj.off[n]);
-        std::vector<uint64_t> fill(adj.off.begin(), adj.off.end() - 1);
-        // keys ascend, so every row receives its neighbours in ascending order: first the smaller
-        // partners (as the second genome of earlier keys), then the larger ones
-        // rows [r0, r1): every thread of a large list walks all hits in key order and writes the slots of its own rows
-        auto fill_rows = [&](uint32_t r0, uint32_t r1) {
-            for (size_t u = 0; u < n_uniq; u++) {
-                const uint32_t x = hit_at(u);
-                const PreclusterHit &h = hits[x];
-                const uint32_t a = std::min(h.i, h.j), b = std::max(h.i, h.j);
-                if (a >= r0 && a < r1) { const uint64_t pa = fill[a]++; adj.nbr[pa] = b; adj.ani[pa] = h.ani; adj.hit[pa] = x; }
-                if (b >= r0 && b < r1) { const uint64_t pb = fill[b]++; adj.nbr[pb] = a; adj.ani[pb] = h.ani; adj.hit[pb] = x; }
-            }
-        };
-        const size_t hw_fill = std::max<size_t>(1, std::thread::hardware_concurrency());
-        const size_t nt_fill = n_uniq >= ((size_t)1 << 19) ? std::min<size_t>(hw_fill, 16) : 1;
-        if (nt_fill == 1) {
-            fill_rows(0, (uint32_t)n);
-        } else {
-            // row ranges holding about the same number of slots (the scattered writes are the cost)
-            std::vector<uint32_t> cut(nt_fill + 1, (uint32_t)n);
-            cut[0] = 0;
-            for (size_t t = 1; t < nt_fill; t++)
-                cut[t] = (uint32_t)(std::lower_bound(adj.off.begin(), adj.off.end(), adj.off[n] / nt_fill * t) - adj.off.begin());
-            std::vector<std::thread> th;
-            for (size_t t = 0; t < nt_fill; t++)
-                if (cut[t] < cut[t + 1]) th.emplace_back(fill_rows, cut[t], cut[t + 1]);
-            for (auto &t : th) t.join();
-        }
-    }
+    build_adjacency(n, hits, n_hits, adj);
 
     const double t1 = now();
-    // ---- partition_sketches: single linkage
-    Dsu dsu(n);
-    for (size_t g = 0; g < n; g++)
-        for (uint64_t x = adj.off[g]; x < adj.off[g + 1]; x++)
-            if (adj.nbr[x] < g) dsu.join((uint32_t)g, adj.nbr[x]);
-    // preclusters as one flat array (CSR): sets in order of their smallest member (the root),
-    // members ascending, then ordered by size, largest first (stable)
-    std::vector<uint32_t> pc_members(n);
+    // ---- partition_sketches
+    std::vector<uint32_t> pc_members;
     std::vector<uint64_t> pc_off;
-    {
-        std::vector<uint32_t> set_id(n), set_size, root_of(n);
-        std::vector<int64_t> set_of_root(n, -1);
-        for (uint32_t g = 0; g < n; g++) {
-            const uint32_t r = dsu.find(g);
-            if (set_of_root[r] < 0) { set_of_root[r] = (int64_t)set_size.size(); set_size.push_back(0); }
-            set_id[g] = (uint32_t)set_of_root[r];
-            set_size[set_id[g]]++;
-        }
-        // sets by size, largest first, ties in set order: a counting sort on the size (stable), O(sets + largest)
-        std::vector<uint32_t> order(set_size.size());
-        {
-            uint32_t largest = 0;
-            for (const uint32_t z : set_size) largest = std::max(largest, z);
-            std::vector<uint64_t> at((size_t)largest + 2, 0);  // at[z] = first slot of size z, sizes descending
-            for (const uint32_t z : set_size) at[largest - z + 1]++;
-            for (size_t z = 0; z + 1 < at.size(); z++) at[z + 1] += at[z];
-            for (uint32_t sid = 0; sid < set_size.size(); sid++) order[at[largest - set_size[sid]]++] = sid;
-        }
-        std::vector<uint64_t> start(set_size.size());
-        pc_off.assign(1, 0);
-        for (const uint32_t sid : order) { start[sid] = pc_off.back(); pc_off.push_back(pc_off.back() + set_size[sid]); }
-        for (uint32_t g = 0; g < n; g++) pc_members[start[set_id[g]]++] = g;
-        out.n_preclusters = (uint32_t)set_size.size();
-        out.largest_precluster = set_size[order[0]];
-    }
+    partition_preclusters(n, adj, pc_members, pc_off, out.n_preclusters, out.largest_precluster);
 
     const double t2 = now();
     std::vector<uint8_t> is_rep(n, 0);
@@ -262,99 +373,14 @@ int cluster_from_hits(size_t n, const PreclusterHit *hits, size_t n_hits, bool s
         for (auto &t : th) t.join();
     };
 
-    // ---- representatives, lazily in waves (AniBatchFn): all preclusters at once.
-    // state: 0 open, 1 representative, 2 member.  pending[g] = hit partners below g that are not settled
-    // towards g yet: a lower partner settles when it becomes a member, or -- a representative -- when its
-    // ANI with g has been applied.  An open genome whose pending count reaches zero without having been
-    // claimed (ANI >= threshold with a representative below it) is a representative: exactly
-    // src/clusterer.rs:216-259, where genome i is tested against the representatives found before it.
-    // Every request is a pair the reference evaluates too: (representative, partner) for every partner
-    // that is not an earlier representative (tested in the representative pass if the partner comes
-    // later and was still undecided, asked for by the membership pass otherwise).
+    // ---- representatives: lazily in waves (representatives_in_waves), or by the sweep below
     bool any_none = false;
     if (lazy) {
-        std::vector<uint8_t> state(n, 0);
-        std::vector<uint32_t> pending(n, 0), fresh, ready, claimed;
-        for (uint32_t g = 0; g < n; g++) {
-            for (uint64_t x = adj.off[g]; x < adj.off[g + 1] && adj.nbr[x] < g; x++) pending[g]++;
-            if (!pending[g]) { state[g] = 1; fresh.push_back(g); }
-        }
-        std::vector<AniRequest> reqs;
-        std::vector<uint64_t> slot;  // per request: the edge slot in the GENOME's row (the cache key)
-        std::vector<uint8_t> some;
-        std::vector<float> ani;
+        std::vector<uint8_t> state;
         uint64_t calls = 0;
-        auto ask = [&]() -> int {
-            if (reqs.empty()) return 0;
-            some.assign(reqs.size(), 0); ani.assign(reqs.size(), 0.f);
-            if ((*batch)(reqs, some.data(), ani.data())) { err = "ANI batch failed"; return 2; }
-            out.ani_waves++;
-            calls += reqs.size();
-            for (size_t q = 0; q < reqs.size(); q++) {
-                edge_state[slot[q]] = some[q] ? 1 : 2; edge_ani[slot[q]] = ani[q];
-                any_none = any_none || !some[q];
-            }
-            return 0;
-        };
-        uint32_t waves = 0;
-        while (!fresh.empty() && waves < max_waves) {
-            waves++;
-            reqs.clear(); slot.clear();
-            for (const uint32_t r : fresh)
-                for (uint64_t y = adj.off[r]; y < adj.off[r + 1]; y++) {
-                    const uint32_t i = adj.nbr[y];
-                    if (state[i] == 1) continue;  // an earlier representative: (i, r) was asked for when i was confirmed
-                    reqs.push_back(AniRequest{r, i, adj.hit[y]});
-                    slot.push_back((uint64_t)adj.find(i, r));  // the same edge in i's row
-                }
-            if (int rc = ask()) return rc;
-            ready.clear(); claimed.clear();
-            for (size_t q = 0; q < reqs.size(); q++) {
-                const uint32_t r = reqs[q].rep, i = reqs[q].genome;
-                if (i < r) continue;  // a member below the representative: only its membership needs the value
-                if (state[i] == 0 && some[q] && ani[q] >= ani_threshold) { state[i] = 2; claimed.push_back(i); }
-                if (--pending[i] == 0) ready.push_back(i);
-            }
-            for (const uint32_t m : claimed)
-                for (uint64_t y = adj.off[m + 1]; y-- > adj.off[m] && adj.nbr[y] > m;)
-                    if (--pending[adj.nbr[y]] == 0) ready.push_back(adj.nbr[y]);
-            fresh.clear();
-            for (const uint32_t g : ready)
-                if (state[g] == 0) { state[g] = 1; fresh.push_back(g); }
-        }
-        if (!fresh.empty()) {
-            // wave budget spent (long chains of mutually distant genomes): everything the undecided genomes
-            // can still ask about in ONE batch -- the pairs of the representatives confirmed last, and for
-            // every open genome its open partners below it --, then the undecided genomes are settled in index order
-            reqs.clear(); slot.clear();
-            for (const uint32_t r : fresh)
-                for (uint64_t y = adj.off[r]; y < adj.off[r + 1]; y++) {
-                    const uint32_t i = adj.nbr[y];
-                    if (state[i] == 1) continue;
-                    reqs.push_back(AniRequest{r, i, adj.hit[y]});
-                    slot.push_back((uint64_t)adj.find(i, r));  // the same edge in i's row
-                }
-            for (uint32_t i = 0; i < n; i++) {
-                if (state[i] != 0) continue;
-                for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
-                    if (state[adj.nbr[x]] == 0) { reqs.push_back(AniRequest{adj.nbr[x], i, adj.hit[x]}); slot.push_back(x); }
-            }
-            if (int rc = ask()) return rc;
-            for (uint32_t i = 0; i < n; i++) {
-                if (state[i] != 0) continue;
-                state[i] = 1;
-                for (uint64_t x = adj.off[i]; x < adj.off[i + 1] && adj.nbr[x] < i; x++)
-                    if (state[adj.nbr[x]] == 1 && edge_state[x] == 1 && edge_ani[x] >= ani_threshold) { state[i] = 2; break; }
-            }
-        }
-        // what the membership sweep reads and nobody asked for yet (only after the one-batch finish)
-        reqs.clear(); slot.clear();
-        for (uint32_t i = 0; i < n; i++) {
-            if (state[i] != 2) continue;
-            for (uint64_t x = adj.off[i]; x < adj.off[i + 1]; x++)
-                if (state[adj.nbr[x]] == 1 && !edge_state[x]) { reqs.push_back(AniRequest{adj.nbr[x], i, adj.hit[x]}); slot.push_back(x); }
-        }
-        if (int rc = ask()) return rc;
+        if (int rc = representatives_in_waves(n, adj, ani_threshold, *batch, max_waves, edge_state, edge_ani, state, calls,
+                                              out.ani_waves, any_none, err))
+            return rc;
         for (size_t pc = 0; pc < n_pc; pc++) {
             uint32_t n_reps = 0;
             for (uint64_t m = pc_off[pc]; m < pc_off[pc + 1]; m++) {
