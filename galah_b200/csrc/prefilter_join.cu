@@ -368,8 +368,8 @@ __global__ void __launch_bounds__(kMThreads) bl_merge_tma_kernel(const uint64_t 
                                                                  const unsigned long long *__restrict__ gmax,
                                                                  uint32_t *__restrict__ dhi,
                                                                  uint32_t *__restrict__ dlo) {
-    extern __shared__ __align__(128) uint8_t merge_smem_raw[];
-    MergeTmaSmem &S = *reinterpret_cast<MergeTmaSmem *>(merge_smem_raw);
+    extern __shared__ __align__(128) uint8_t merge_tma_smem_raw[];
+    MergeTmaSmem &S = *reinterpret_cast<MergeTmaSmem *>(merge_tma_smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t o = blockIdx.x / chunks_per_run, c = blockIdx.x % chunks_per_run;
     const uint64_t base = (uint64_t)o * 2 * m;
