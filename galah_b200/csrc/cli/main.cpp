@@ -34,7 +34,7 @@ struct Options {
     std::string precluster_method = "skani", cluster_method = "skani";
     bool small_genomes = false, cluster_contigs = false, small_contigs = false, large_contigs = false, low_memory = false;
     int threads = 0, gpus = 1, device = 0;  // threads: 0 = every host core (they only read and inflate files)
-    bool quiet = false;
+    bool quiet = false, print_config = false;
     std::string out_clusters, out_rep_list, out_rep_dir, out_rep_dir_copy;
 };
 
@@ -65,7 +65,7 @@ void usage(FILE *f) {
           "  -o, --output-cluster-definition <FILE>      representative<TAB>member lines\n"
           "  --output-representative-list <FILE>\n"
           "  --output-representative-fasta-directory <DIR> | --output-representative-fasta-directory-copy <DIR>\n"
-          "  -q, --quiet    -h, --help    --version\n", f);
+          "  -q, --quiet    -h, --help    --version    --print-config (the effective parameters, then exit)\n", f);
 }
 
 float parse_f32(const std::string &flag, const char *v) {
@@ -138,6 +138,7 @@ Options parse(int argc, char **argv) {
         else if (a == "--output-representative-list") o.out_rep_list = value();
         else if (a == "--output-representative-fasta-directory") o.out_rep_dir = value();
         else if (a == "--output-representative-fasta-directory-copy") o.out_rep_dir_copy = value();
+        else if (a == "--print-config") o.print_config = true;
         else if (a == "-q" || a == "--quiet") o.quiet = true;
         else if (a == "-v" || a == "--verbose") o.quiet = false;
         else if (a == "-h" || a == "--help") { usage(stdout); exit(0); }
@@ -161,7 +162,7 @@ Options parse(int argc, char **argv) {
     if (o.low_memory && refs) die("error: the argument '--low-memory' cannot be used with '--reference-genomes'", 2);
     if (!o.references.empty() && !o.reference_list.empty())
         die("error: the argument '--reference-genomes' cannot be used with '--reference-genomes-list'", 2);
-    if (o.out_clusters.empty() && o.out_rep_list.empty() && o.out_rep_dir.empty() && o.out_rep_dir_copy.empty())
+    if (!o.print_config && o.out_clusters.empty() && o.out_rep_list.empty() && o.out_rep_dir.empty() && o.out_rep_dir_copy.empty())
         die("error: the following required arguments were not provided:\n  --output-cluster-definition <output-cluster-definition>\n"
             "  (or one of --output-representative-list, --output-representative-fasta-directory[-copy])", 2);
     if (o.threads < 0) o.threads = 0;
@@ -282,6 +283,18 @@ int main(int argc, char **argv) {
     const float af_pct = af_frac * 100.0f;    // --min-af as the skani callers form it (src/skani.rs:153, 742)
     const bool skip_clusterer = o.precluster_method == o.cluster_method;
     const float pre_pct = (skip_clusterer ? ani_frac : pre_frac) * 100.0f;  // SkaniPreclusterer.threshold (:1300-1352)
+
+    if (o.print_config) {
+        // the values the reference's structs would hold (FinchPreclusterer.min_ani, SkaniPreclusterer.threshold,
+        // SkaniClusterer.threshold, --min-af as the skani callers form it), nine significant digits: exact for f32
+        printf("genomes\t%zu\nreferences\t%zu\nprecluster_method\t%s\ncluster_method\t%s\nskip_clusterer\t%d\n"
+               "finch_min_ani\t%.9g\nskani_precluster_threshold\t%.9g\nani_threshold\t%.9g\nmin_af_percent\t%.9g\n"
+               "small_genomes\t%d\ncluster_contigs\t%d\nlow_memory\t%d\n",
+               genomes.size(), references.size(), o.precluster_method.c_str(), o.cluster_method.c_str(),
+               (int)(skip_clusterer || o.cluster_contigs), (double)pre_frac, (double)pre_pct, (double)ani_pct, (double)af_pct,
+               (int)small, (int)o.cluster_contigs, (int)o.low_memory);
+        return 0;
+    }
 
     // what the reference refuses inside cluster(): no device is needed to say so
     if (o.cluster_contigs && o.precluster_method == "finch") die("finch does not support contig comparisons.");  // src/clusterer.rs:39-41

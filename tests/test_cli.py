@@ -187,3 +187,31 @@ def test_reference_genomes_and_directory_input(gb, tmp_path):
     assert r.stdout == lines((first, first), (first, second))
     r = run("cluster", "-d", str(d), "-x", "fasta", "-o", "/dev/stdout", "-q")
     assert r.returncode == 1 and "Found 0 genomes" in r.stderr
+
+
+def test_percentages_follow_the_references_f32_arithmetic():
+    """parse_percentage (src/cluster_argument_parsing.rs:1491-1512) divides by 100 in f32 and the backends multiply by 100
+    again (:1300-1352, 1478-1485; src/skani.rs:153, 742): --min-aligned-fraction 15 reaches skani as 15.000001, 60 as
+    60.000004, 0.2 as 20; --ani 95 as 95; finch's min_ani 90 as 0.9f.  skip_clusterer: same method names, or contigs."""
+    import numpy as np
+
+    def config(*args):
+        r = run("cluster", "-f", "a.fna", "b.fna", "--print-config", *args)
+        assert r.returncode == 0, r.stderr
+        return dict(line.split("\t") for line in r.stdout.strip().split("\n"))
+    c = config()
+    assert np.float32(c["min_af_percent"]) == np.float32(0.15) * np.float32(100.0) == np.float32(15.000001)
+    assert float(c["ani_threshold"]) == 95.0 and float(c["skani_precluster_threshold"]) == 95.0  # skip_clusterer: --ani
+    assert c["skip_clusterer"] == "1" and c["precluster_method"] == c["cluster_method"] == "skani"
+    c = config("--min-aligned-fraction", "60", "--precluster-method", "finch", "--ani", "99")
+    assert np.float32(c["min_af_percent"]) == np.float32(0.6) * np.float32(100.0) == np.float32(60.000004)
+    assert np.float32(c["finch_min_ani"]) == np.float32(0.9) and c["skip_clusterer"] == "0"
+    assert float(c["ani_threshold"]) == float(np.float32(0.99) * np.float32(100.0)) and float(c["skani_precluster_threshold"]) == 90.0
+    c = config("--min-aligned-fraction", "0.2", "--precluster-ani", "0.85")
+    assert float(c["min_af_percent"]) == 20.0
+    c = config("--cluster-contigs", "--small-contigs", "--small-genomes")
+    assert c["small_genomes"] == "1" and c["cluster_contigs"] == "1" and c["skip_clusterer"] == "1"
+    c = config("--cluster-contigs", "--large-contigs", "--small-genomes")  # --small-genomes is ignored for contigs (:1760-1782)
+    assert c["small_genomes"] == "0"
+    c = config("--reference-genomes", "r1.fna", "r2.fna")
+    assert c["genomes"] == "4" and c["references"] == "2"
