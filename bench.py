@@ -406,7 +406,8 @@ def main():
             same = (e_clusters == clusters and cl_bitmap == clusters) if rank == 0 else None
             seq_bytes = d_seq.numel() * 4
             h2d = world * (seq_bytes + (n_local + 1) * 8 + n_local * 8)
-            d2h = n_hits * (16 + 48) + n * 4 + 16
+            # survivors (16 B each), the K3 accumulators of every evaluated pair (7 x u32 + one u64), counts
+            d2h = n_hits * 16 + int(e_info.get("my_ani_pairs") or e_info.get("n_ani_pairs") or n_hits) * 36 * (world if world > 1 else 1) + n * 4 + 16
             e2e = {"value": pairs / float(e_t.item()), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms": 1e3 * float(e_t.item()),
                    "phases_ms": {k: e_info[k] for k in ("ingest_ms", "sketch_ms", "index_ms", "prefilter_ms", "ani_ms", "engine_ms") if k in e_info},
