@@ -14,7 +14,7 @@
 using namespace gb200;
 int main(int argc, char **argv) {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;  // 0: small random graphs, 1: many preclusters (threaded sweeps), 2: dense (threaded fill)
-    std::mt19937_64 rng(7);
+    std::mt19937_64 rng(argc > 2 ? strtoull(argv[2], nullptr, 10) : 7);  // optional second argument: the seed
     int rounds = mode == 0 ? 300 : 3;
     for (int round = 0; round < rounds; round++) {
         size_t n = mode == 0 ? 1 + rng() % 120 : mode == 1 ? 60000 : 1100;
