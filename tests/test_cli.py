@@ -215,3 +215,25 @@ def test_percentages_follow_the_references_f32_arithmetic():
     assert c["small_genomes"] == "0"
     c = config("--reference-genomes", "r1.fna", "r2.fna")
     assert c["genomes"] == "4" and c["references"] == "2"
+
+
+def test_genome_input_flags_without_a_device(tmp_path):
+    """-f, --genome-fasta-list (a path is the text before the first TAB, blank lines skipped) and -d with -x
+    (docs/tools/cluster.md:40-62) add up; an empty selection is refused before any device is touched."""
+    listing = tmp_path / "list.txt"
+    listing.write_text("x/one.fna\tquality 98\n\n  \nx/two.fna\n")
+    d = tmp_path / "dir"
+    d.mkdir()
+    for name in ("b.fa", "a.fa", "c.fna", "notes.txt"):
+        (d / name).write_text(">c\nACGT\n")
+    r = run("cluster", "-f", "z.fna", "--genome-fasta-list", str(listing), "-d", str(d), "-x", "fa", "--print-config")
+    assert r.returncode == 0, r.stderr
+    assert dict(line.split("\t") for line in r.stdout.strip().split("\n"))["genomes"] == "5"
+    r = run("cluster", "-d", str(d), "-x", "fasta", "-o", "/dev/null")
+    assert r.returncode == 1 and "Found 0 genomes" in r.stderr
+    r = run("cluster", "--genome-fasta-list", str(tmp_path / "missing.txt"), "-o", "/dev/null")
+    assert r.returncode == 1 and "Failed to read genome fasta list" in r.stderr
+    r = run("cluster", "-o", "/dev/null")
+    assert r.returncode == 1 and "No genome fasta files found" in r.stderr
+    r = run("derep", "-f", "a.fna")
+    assert r.returncode == 2 and "unrecognized subcommand" in r.stderr
